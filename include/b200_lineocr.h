@@ -1,0 +1,156 @@
+/* b200_lineocr.h -- C ABI of the B200-native text-line recognition path (libb200_lineocr.so).
+ *
+ * The reference (DCGM/pero-ocr v0.7.0) is pure Python and has no FFI: its "plugin surface" is the duck-typed
+ * engine object held by PageParser.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  All pointers are plain device or host pointers as stated; no
+ * framework types cross this boundary.  The library owns only the packed weights and the workspace it
+ * allocates in b200ocr_create / b200ocr_reserve; every input/output buffer is caller-owned.
+ * Calls are stream-ordered on the given CUDA stream, perform no hidden synchronisation and no allocation
+ * (b200ocr_forward fails with B200OCR_E_WORKSPACE if the reserved workspace is too small).
+ * One engine per device, not thread-safe -- same as the reference engine objects.
+ */
+#ifndef B200_LINEOCR_H
+#define B200_LINEOCR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200ocr_engine b200ocr_engine_t;
+
+enum b200ocr_status {
+    B200OCR_OK = 0,
+    B200OCR_E_INVALID = 1,   /* bad argument / unsupported shape */
+    B200OCR_E_CUDA = 2,      /* CUDA runtime or driver error (text in b200ocr_last_error) */
+    B200OCR_E_WORKSPACE = 3, /* b200ocr_reserve was not called or is too small for this batch */
+    B200OCR_E_NO_DEVICE = 4  /* no sm_100 device visible: there is no CPU fallback */
+};
+
+enum b200ocr_layer_kind {
+    B200OCR_CONV_FIRST = 1, /* u8 NHWC image -> /255 -> 3x3 conv (pad 1) + bias + act; CUDA cores (K = 27) */
+    B200OCR_CONV = 2,       /* kh x kw conv, fp16 NHWC in, tcgen05 implicit GEMM, fused bias+act+affine+max-pool */
+    B200OCR_BILSTM = 3,     /* one bidirectional LSTM layer (PyTorch gate order i,f,g,o) */
+    B200OCR_CTC_HEAD = 4,   /* per-frame linear -> logits [N,T,C] (+ fused per-frame argmax / max / logsumexp) */
+    B200OCR_UPSAMPLE = 5,   /* nearest-neighbour x`pool_h` upsampling to fp32 NCHW maps (ParseNet tail) */
+    B200OCR_LN_PE = 6,      /* LayerNorm over channels + sinusoidal positional encoding (transformer.py:316-332,378-381) */
+    B200OCR_TRANSFORMER_LAYER = 7 /* post-LN nn.TransformerEncoderLayer, ReLU FFN (transformer.py:371-373) */
+};
+
+enum b200ocr_act { B200OCR_ACT_NONE = 0, B200OCR_ACT_RELU = 1, B200OCR_ACT_LEAKY_RELU = 2 /* slope 0.01 */ };
+
+enum b200ocr_precision {
+    B200OCR_PREC_FP16 = 0,  /* fp16 operands, fp32 accumulate (same 10-bit mantissa as cuDNN's default TF32 convs) */
+    B200OCR_PREC_FP16X3 = 1 /* hi/lo fp16 split of both operands, 3 MMAs per product: ~fp32-faithful */
+};
+
+/* One layer.  All weight pointers are HOST pointers to fp32 arrays in PyTorch's native layouts; the library
+ * packs them (fp16, tap-major, K-major) into device memory it owns.  Unused fields are 0 / NULL. */
+typedef struct b200ocr_layer {
+    int32_t kind;
+    int32_t cin, cout;
+    int32_t kh, kw, pad_h, pad_w;
+    int32_t act;
+    int32_t pool_h, pool_w;  /* fused max-pool after the activation (1,1 = none) */
+    const float* weight;     /* conv: [cout][cin][kh][kw]; linear: [cout][cin] */
+    const float* bias;       /* [cout] */
+    const float* post_scale; /* optional eval-mode BatchNorm folded to y*scale+shift, applied AFTER act (+pool) */
+    const float* post_shift;
+    /* B200OCR_BILSTM: index 0 = forward, 1 = reverse direction; w_ih [4H][cin], w_hh [4H][H], biases [4H] */
+    int32_t hidden;
+    const float* w_ih[2];
+    const float* w_hh[2];
+    const float* b_ih[2];
+    const float* b_hh[2];
+    /* B200OCR_TRANSFORMER_LAYER / B200OCR_LN_PE */
+    int32_t heads, dim_ff;
+    const float* in_proj_w;  /* [3D][D] */
+    const float* in_proj_b;  /* [3D] */
+    const float* out_proj_w; /* [D][D] */
+    const float* out_proj_b;
+    const float* lin1_w;     /* [dim_ff][D] */
+    const float* lin1_b;
+    const float* lin2_w;     /* [D][dim_ff] */
+    const float* lin2_b;
+    const float* norm1_w;    /* LN_PE uses norm1_* as its LayerNorm parameters */
+    const float* norm1_b;
+    const float* norm2_w;
+    const float* norm2_b;
+} b200ocr_layer_t;
+
+typedef struct b200ocr_net_desc {
+    int32_t n_layers;
+    const b200ocr_layer_t* layers;
+    int32_t precision;   /* enum b200ocr_precision */
+    int32_t line_height; /* input crop height (40) */
+    int32_t device;      /* CUDA device ordinal */
+} b200ocr_net_desc_t;
+
+/* Replaces PytorchEngineLineOCR._load_exported_model (pero_ocr/ocr_engine/pytorch_ocr_engine.py:52-57):
+ * builds the device-resident network from host weights.  Returns B200OCR_OK and *out, else a status
+ * (message via b200ocr_last_error(NULL)). */
+int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out);
+
+/* Pre-allocates activations/workspace for batches up to max_lines x (line_height x max_width_px).
+ * (The reference relies on torch's caching allocator + torch.cuda.empty_cache(), line_ocr_engine.py:174-175.) */
+int b200ocr_reserve(b200ocr_engine_t* e, int32_t max_lines, int32_t max_width_px);
+
+/* Replaces the device part of PytorchEngineLineOCR.run_ocr (pytorch_ocr_engine.py:59-74): `/255`, NHWC->net,
+ * self.model(batch) (:64-69), greedy_decode_ctc (:13-34) up to (not including) the id->char join.
+ *   crops      device u8 [n][h][w][3]  (the padded batch built by BaseEngineLineOCR.process_lines, :121-123)
+ *   logits     device f32 [n][T][C] or NULL (T = w/4, C = classes incl. blank LAST) -- run_ocr's 2nd result (:72)
+ *   labels     device i32 [n][T]  collapsed label ids, left-packed, rest -1
+ *   lengths    device i32 [n]
+ *   confidence device f32 [n] or NULL: min over non-blank runs of the run's max softmax prob over ALL T frames
+ *              (PageParser.get_prob, document_ocr/page_parser.py:437-450)
+ *   best_path  device i32 [n][T] or NULL: raw per-frame argmax ("bit-exact CTC argmax indices")
+ */
+int b200ocr_forward(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_t h, int32_t w, float* logits,
+                    int32_t* labels, int32_t* lengths, float* confidence, int32_t* best_path, void* cuda_stream);
+
+/* ParseNet-style conv net: replaces `self.net(image)` in TorchParseNet.get_maps
+ * (pero_ocr/layout_engines/torch_parsenet.py:51-53).  image: device u8 [1][h][w][3]; maps: device f32
+ * [1][cout][h][w] (NCHW, like the TorchScript blob's first output). */
+int b200ocr_forward_maps(b200ocr_engine_t* e, const uint8_t* image, int32_t h, int32_t w, float* maps,
+                         void* cuda_stream);
+
+void b200ocr_destroy(b200ocr_engine_t* e);
+
+/* Last error text of this engine (or of the last failed b200ocr_create when e == NULL). */
+const char* b200ocr_last_error(const b200ocr_engine_t* e);
+
+/* Number of kernels this library launched on behalf of `e` since creation (bench.py's gpu_launches). */
+int64_t b200ocr_launch_count(const b200ocr_engine_t* e);
+
+/* Algorithmic FLOPs (2*MACs) of one forward at (n, w) and the share of the implicit-GEMM conv kernel. */
+double b200ocr_forward_flops(const b200ocr_engine_t* e, int32_t n, int32_t w, double* conv_gemm_flops);
+
+/* Replaces greedy_decode_ctc (pytorch_ocr_engine.py:13-34) and decoding.decoders.GreedyDecoder.__call__
+ * (pero_ocr/decoding/decoders.py:42-62) on materialised scores.
+ *   scores  device f32, layout 0 = [n][t][c] (run_ocr / decoder layout), 1 = [n][c][t] (model output layout)
+ *   labels/lengths/confidence/best_path as in b200ocr_forward; frame_max: device f32 [n][t] or NULL (per-frame
+ *   max score, GreedyDecoder's `maxes`); frame_lse: device f32 [n][t] or NULL (per-frame logsumexp). */
+int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int32_t layout, int32_t* labels,
+                       int32_t* lengths, float* confidence, int32_t* best_path, float* frame_max, float* frame_lse,
+                       void* cuda_stream);
+
+/* Replaces CTCPrefixLogRawNumpyDecoder.__call__ without LM (pero_ocr/decoding/decoders.py:220-299).
+ *   logprobs  device f64 [n][t][c] normalised log-probabilities, blank last
+ *   out_labels device i32 [n][k][t], out_lengths i32 [n][k] (-1 = unused beam slot), out_scores f64 [n][k]
+ *   (logaddexp(Pb, Pnb) per surviving prefix), status i32 [n]: 0 ok, 1 = not normalised (reference raises
+ *   ValueError, decoders.py:223-224). */
+int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
+                            int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream);
+
+/* ---- debug / test hooks (not used by the product path) ------------------------------------------------- */
+/* Route every implicit-GEMM layer through a naive one-thread-per-output CUDA-core kernel (same packed fp16
+ * operands, fp32 accumulate) so the tcgen05 path can be checked on a GPU box where the reference is absent. */
+int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
+/* Copies the fp32-expanded output activation of layer `layer` of the LAST forward to host `out` (NHWC). */
+int b200ocr_debug_read_activation(b200ocr_engine_t* e, int32_t layer, float* out, int64_t capacity, int64_t* written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_LINEOCR_H */

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY -- seeded synthetic inputs shared by oracle/make_golden.py, tests/ and bench.py.
+
+Everything is drawn from numpy's PCG64 (``default_rng``), which is stable across machines and numpy versions,
+so the GPU box regenerates bit-identical inputs and weights without shipping them.
+"""
+import numpy as np
+from scipy.special import log_softmax
+
+BLANK = '<BLANK>'
+
+# Recogniser cases hosted by the reference engine in make_golden.py.  `engine_batch_size` is the constructor
+# argument of PytorchEngineLineOCR (pixel budget = 480 * batch_size, line_ocr_engine.py:55): 1 forces several
+# width-sorted batches of different widths, and an over-budget line that is cropped (line_ocr_engine.py:125-127).
+ENGINE_CASES = {
+    'lstm': dict(classes=120, seed=0, out_gain=6.0, net_kw={}, engine_batch_size=1,
+                 widths=[256, 200, 131, 64, 33, 500, 224, 97]),
+    'transformer': dict(classes=120, seed=3, out_gain=2.5, net_kw={'layers': 2}, engine_batch_size=1,
+                        widths=[256, 180, 77, 40, 224, 500]),
+}
+PARSENET_CASE = dict(seed=5, downsample=2, height=250, width=330)
+CONFIG1_BEAM_LINES = 6
+
+
+def json_characters(n):
+    """`n` distinct printable characters for the engine JSON (the engine appends U+200B and blank is last)."""
+    return [chr(0x100 + i) for i in range(n)]
+
+
+def line_crop(rng, width, height=40):
+    """One synthetic "gray" crop [H,W,3] u8: equal channels."""
+    g = rng.integers(0, 256, (height, width), dtype=np.uint8)
+    return np.repeat(g[:, :, None], 3, axis=2)
+
+
+def engine_lines(kind):
+    spec = ENGINE_CASES[kind]
+    rng = np.random.default_rng(100 + spec['seed'])
+    lines = [line_crop(rng, w) for w in spec['widths']]
+    # one genuinely coloured line: the net sees 3 distinct channels
+    lines[1] = rng.integers(0, 256, lines[1].shape, dtype=np.uint8)
+    return lines
+
+
+def bench_crops(n, width=1280, seed=0, height=40):
+    """BASELINE.json configs 2/3/5: n gray 40 x width crops, default_rng(seed)."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 256, (n, height, width), dtype=np.uint8)
+    return np.repeat(g[:, :, :, None], 3, axis=3)
+
+
+def config1_logits():
+    """BASELINE.json config 1: 128 lines x T=256 x C=120, blank last."""
+    rng = np.random.default_rng(1234)
+    raw = (rng.standard_normal((128, 256, 120)) * 4).astype(np.float32)
+    lp = log_softmax(raw, axis=2)
+    letters = [chr(0x100 + i) for i in range(119)] + [BLANK]
+    return raw, lp, letters
+
+
+def peaky_logprobs(rng, n, t, c, sharp=9.0, p_blank=0.55, p_repeat=0.3):
+    """Log-probabilities shaped like a trained CTC net's: one dominant class per frame, blank-heavy,
+    with repeats, plus low-level noise so that a few classes pass the decoder's > -10 relevance gate."""
+    out = np.empty((n, t, c), dtype=np.float64)
+    for i in range(n):
+        raw = rng.standard_normal((t, c)) * 1.5
+        prev = c - 1
+        for f in range(t):
+            u = rng.random()
+            if u < p_blank:
+                k = c - 1
+            elif u < p_blank + p_repeat and prev != c - 1:
+                k = prev
+            else:
+                k = int(rng.integers(0, c - 1))
+            raw[f, k] += sharp * rng.uniform(0.4, 1.0)
+            prev = k
+        out[i] = log_softmax(raw, axis=1)
+    return out
+
+
+def peaky_cases():
+    rng = np.random.default_rng(77)
+    small = [chr(ord('a') + i) for i in range(5)] + [BLANK]
+    big = [chr(0x100 + i) for i in range(119)] + [BLANK]
+    return {
+        'peaky_small': (peaky_logprobs(rng, 6, 40, 6, sharp=5.0), small),
+        'peaky_big': (peaky_logprobs(rng, 4, 96, 120, sharp=12.0), big),
+    }
+
+
+def greedy_edge_cases():
+    """[N,C,T] f32 score tensors for greedy_decode_ctc's tie / first-frame / NaN rules."""
+    chars = ['a', 'b', 'c', '']
+    C = 4
+
+    def frames(rows):
+        a = np.array(rows, dtype=np.float32)         # [T,C]
+        return a.T[None].copy()                      # [1,C,T]
+    return {
+        'tie_lowest_index': (frames([[1, 1, 0, 0]]), chars),
+        'tie_char_beats_blank': (frames([[0, 2, 0, 2]]), chars),
+        'first_frame_kept': (frames([[5, 0, 0, 0], [5, 0, 0, 0], [0, 0, 0, 5]]), chars),
+        'a_blank_a': (frames([[5, 0, 0, 0], [0, 0, 0, 5], [5, 0, 0, 0]]), chars),
+        'all_blank': (frames([[0, 0, 0, 5]] * 4), chars),
+        'nan_wins': (frames([[0, np.nan, 0, 5], [0, 0, 3, 0]]), chars),
+        'repeat_then_switch': (frames([[0, 4, 0, 0], [0, 4, 0, 0], [0, 0, 4, 0], [0, 0, 4, 0], [0, 4, 0, 0]]), chars),
+        'batch': (np.concatenate([frames([[5, 0, 0, 0], [0, 0, 0, 5], [0, 5, 0, 0]]),
+                                  frames([[0, 0, 0, 5], [0, 0, 5, 0], [0, 0, 5, 0]])]), chars),
+    }
+
+
+def confidence_logits():
+    """Raw logit matrices [T,C] f32 for the sparsify -> dense -> confidence chain."""
+    rng = np.random.default_rng(55)
+    out = []
+    for t, c, s in ((30, 12, 6.0), (64, 120, 10.0), (17, 120, 3.0), (1, 5, 4.0)):
+        lp = peaky_logprobs(rng, 1, t, c, sharp=s)[0]
+        out.append((lp + rng.uniform(-3, 3, (t, 1))).astype(np.float32))   # un-normalised, like raw net output
+    return out
+
+
+def parsenet_image():
+    spec = PARSENET_CASE
+    rng = np.random.default_rng(500 + spec['seed'])
+    return rng.integers(0, 256, (spec['height'], spec['width'], 3), dtype=np.uint8)

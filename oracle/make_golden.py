@@ -1,0 +1,269 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/* by running the UNMODIFIED reference classes.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+What is executed from the reference (nothing is copied; the tree is imported read-only):
+  * pero_ocr.ocr_engine.pytorch_ocr_engine.PytorchEngineLineOCR / greedy_decode_ctc, hosting TorchScript
+    exports of oracle/nets.py (the reference ships no recogniser definition, pytorch_ocr_engine.py:52-57)
+  * pero_ocr.ocr_engine.transformer.build_net -> ConvolutionalEncoder + LineSelfAttentionEncoder, loaded with
+    the same seeded weights, to pin oracle/nets.py's restatement of that architecture
+  * pero_ocr.decoding.decoders.GreedyDecoder / CTCPrefixLogRawNumpyDecoder
+  * pero_ocr.layout_engines.torch_parsenet.TorchParseNet.get_maps
+  * pero_ocr.document_ocr.page_parser.PageParser.compute_line_confidence / line_confident_enough and
+    pero_ocr.core.layout.TextLine.get_dense_logits / get_full_logprobs (imported behind stub modules for the
+    absent lxml / shapely / skimage / arabic_reshaper packages -- SURVEY.md appendix A.4)
+
+Inputs and weights are regenerated from seeds by the tests; only reference OUTPUTS are stored.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+from . import cases                                   # noqa: E402
+from .nets import make_net, seeded_state_dict         # noqa: E402
+
+
+def _install_stubs():
+    """Stand-ins for packages absent from this image; only import-time names are provided."""
+    import xml.etree.ElementTree as ET
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            pass
+
+    lx = mod('lxml')
+    lx.etree = mod('lxml.etree', **{k: getattr(ET, k) for k in dir(ET) if not k.startswith('_')})
+    geo = mod('shapely.geometry', LineString=_Dummy, Polygon=_Dummy, MultiPoint=_Dummy, MultiLineString=_Dummy,
+              MultiPolygon=_Dummy, Point=_Dummy, GeometryCollection=_Dummy)
+    geo.polygon = mod('shapely.geometry.polygon', Polygon=_Dummy)
+    sh = mod('shapely', geometry=geo)
+    sh.ops = mod('shapely.ops', unary_union=None, polygonize=None, nearest_points=None)
+    sh.affinity = mod('shapely.affinity')
+    sh.errors = mod('shapely.errors', TopologicalError=Exception)
+    sk = mod('skimage')
+    sk.draw = mod('skimage.draw', polygon2mask=None, polygon=None, line=None)
+    sk.measure = mod('skimage.measure')
+    mod('arabic_reshaper', ArabicReshaper=_Dummy)
+
+
+def _export_engine(tmp, net, name, n_chars):
+    """TorchScript export + engine JSON in the form PytorchEngineLineOCR reads (line_ocr_engine.py:19-46)."""
+    ck = os.path.join(tmp, name + '.pt')
+    scripted = torch.jit.script(net)
+    scripted.save(ck)
+    scripted.save(ck + '.cpu')                       # CPU suffix rule, pytorch_ocr_engine.py:53-54
+    js = os.path.join(tmp, name + '.json')
+    with open(js, 'w', encoding='utf8') as f:
+        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': name + '.pt',
+                   'characters': cases.json_characters(n_chars), 'net_name': 'B200_GOLDEN'}, f)
+    return js
+
+
+def golden_engine(kind, tmp):
+    from pero_ocr.ocr_engine.pytorch_ocr_engine import PytorchEngineLineOCR
+    spec = cases.ENGINE_CASES[kind]
+    net = make_net(kind, spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
+    js = _export_engine(tmp, net, kind, spec['classes'] - 2)
+    eng = PytorchEngineLineOCR(js, torch.device('cpu'), batch_size=spec['engine_batch_size'])
+    lines = cases.engine_lines(kind)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr, lg, co = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+        tr_s, lg_s, co_s = eng.process_lines([l.copy() for l in lines], sparse_logits=True)
+        tr_t, lg_t, co_t = eng.process_lines([l.copy() for l in lines], sparse_logits=False, tight_crop_logits=True)
+    assert tr == tr_s == tr_t
+    out = {'n': np.int64(len(lines)), 'chars': np.array(eng.characters)}
+    for i in range(len(lines)):
+        out[f'logits_{i}'] = lg[i].astype(np.float32)
+        out[f'tight_{i}'] = lg_t[i].astype(np.float32)
+        sp = lg_s[i]
+        out[f'csc_data_{i}'] = sp.data
+        out[f'csc_indices_{i}'] = sp.indices
+        out[f'csc_indptr_{i}'] = sp.indptr
+        out[f'coords_{i}'] = np.array(co[i], dtype=np.int64)
+    out['transcriptions'] = np.array(tr)
+    # raw per-frame argmax of the full batch logits ("bit-exact CTC argmax indices")
+    out['best_path'] = np.concatenate([l.argmax(axis=1).astype(np.int32) for l in lg])
+    np.savez_compressed(os.path.join(GOLDEN, f'engine_{kind}.npz'), **out)
+    margins = np.concatenate([np.sort(l, axis=1)[:, -1] - np.sort(l, axis=1)[:, -2] for l in lg])
+    return {'lines': len(lines), 'transcription_lengths': [len(t) for t in tr],
+            'top2_margin_median': float(np.median(margins)), 'top2_margin_min': float(margins.min()),
+            'logit_absmax': float(max(np.abs(l).max() for l in lg))}
+
+
+def check_reference_architecture():
+    """oracle/nets.py vs the reference's own ConvolutionalEncoder + LineSelfAttentionEncoder (same weights)."""
+    import torchvision
+    from pero_ocr.ocr_engine import transformer as ref_tr
+    orig = torchvision.models.vgg16
+    torchvision.models.vgg16 = lambda pretrained=False, **k: orig(weights=None)   # no network here; random init
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = ref_tr.build_net({'dim_model': 512, 'dim_ff': 2048, 'heads': 8, 'encoder_layers': 2,
+                                    'decoder_layers': 1, 'conv_subsampling': [8, 4]}, input_height=40,
+                                   input_channels=3, nb_output_symbols=118).eval()
+    finally:
+        torchvision.models.vgg16 = orig
+    ours = make_net('transformer', 120, seed=3, layers=2)
+    sd = ours.state_dict()
+    # map our parameter names onto the reference module tree
+    ref_front = ref.encoder_frontend
+    ref_convs = [m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.Conv2d)]
+    our_convs = [m for m in ours.conv if isinstance(m, torch.nn.Conv2d)]
+    assert len(ref_convs) == len(our_convs) == 9
+    for r, o in zip(ref_convs, our_convs):
+        assert r.weight.shape == o.weight.shape
+        r.load_state_dict(o.state_dict())
+    ref_bn = [m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    assert len(ref_bn) == 1
+    ref_bn[0].load_state_dict([m for m in ours.conv if isinstance(m, torch.nn.BatchNorm2d)][0].state_dict())
+    ref_front.aggregation_conv[0].load_state_dict(ours.agg.state_dict())
+    ref.encoder.input_norm.load_state_dict(ours.input_norm.state_dict())
+    ref.encoder.trans_encoder.load_state_dict(ours.trans_encoder.state_dict())
+    # structural check of the layer list (activations / pool strides), SURVEY.md section 8(a) a6
+    ref_layers = [type(m).__name__ + (str(tuple(m.kernel_size)) if isinstance(m, torch.nn.MaxPool2d) else '')
+                  for m in ref_front.blocks_2d.modules()
+                  if isinstance(m, (torch.nn.ReLU, torch.nn.LeakyReLU, torch.nn.MaxPool2d))]
+    ref_layers = [l for l in ref_layers if l != 'MaxPool2d(1, 1)']        # identity pool after block 4
+    our_layers = [type(m).__name__ + (str(tuple(m.kernel_size)) if isinstance(m, torch.nn.MaxPool2d) else '')
+                  for m in ours.conv if isinstance(m, (torch.nn.ReLU, torch.nn.LeakyReLU, torch.nn.MaxPool2d))]
+    assert ref_layers == our_layers, (ref_layers, our_layers)
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.random((2, 3, 40, 192), dtype=np.float32))
+    with torch.no_grad():
+        enc_ref = ref.encode(x)                                       # [T,N,512]
+        y = ours.agg_act(ours.agg(ours.conv(x))).squeeze(2).permute(2, 0, 1)
+        y = ours.input_norm(y)
+        enc_ours = ours.trans_encoder(y + ours.pe[:y.size(0)])
+    diff = float((enc_ref - enc_ours).abs().max())
+    assert diff < 1e-5, diff
+    return {'encode_max_abs_diff_vs_reference_TransformerOCR.encode': diff, 'layer_list': our_layers}
+
+
+def golden_decoders():
+    from pero_ocr.decoding.decoders import GreedyDecoder, CTCPrefixLogRawNumpyDecoder, BLANK_SYMBOL
+    from pero_ocr.ocr_engine.pytorch_ocr_engine import greedy_decode_ctc
+    out = {}
+    # BASELINE.json config 1: 128 x (256 x 120)
+    raw, lp, letters = cases.config1_logits()
+    gd = GreedyDecoder(letters)
+    g_str, g_sc = [], []
+    for m in lp:
+        boh = gd(m)
+        h = list(boh)[0]
+        g_str.append(h.transcript)
+        g_sc.append(h.vis_sc)
+    t_str = greedy_decode_ctc(torch.from_numpy(raw.transpose(0, 2, 1).copy()), letters[:-1] + [''])
+    assert t_str == g_str
+    out['config1_greedy'] = np.array(g_str)
+    out['config1_greedy_score'] = np.array(g_sc, dtype=np.float64)
+    bd = CTCPrefixLogRawNumpyDecoder(letters, k=16)
+    nb = cases.CONFIG1_BEAM_LINES
+    for i in range(nb):
+        boh = bd(lp[i].astype(np.float64))
+        out[f'config1_beam_best_{i}'] = np.array(boh.best_hyp())
+        out[f'config1_beam_hyps_{i}'] = np.array([h.transcript for h in boh])
+        out[f'config1_beam_scores_{i}'] = np.array([h.vis_sc for h in boh], dtype=np.float64)
+    # peaky logits (what a trained net emits): few relevant characters per frame, k = 1, 4, 16
+    for name, (lp2, letters2) in cases.peaky_cases().items():
+        for k in (1, 4, 16):
+            bd2 = CTCPrefixLogRawNumpyDecoder(letters2, k=k)
+            for i, m in enumerate(lp2):
+                boh = bd2(m)
+                out[f'{name}_k{k}_best_{i}'] = np.array(boh.best_hyp())
+                out[f'{name}_k{k}_hyps_{i}'] = np.array([h.transcript for h in boh])
+                out[f'{name}_k{k}_scores_{i}'] = np.array([h.vis_sc for h in boh], dtype=np.float64)
+        g2 = GreedyDecoder(letters2)
+        out[f'{name}_greedy'] = np.array([list(g2(m))[0].transcript for m in lp2])
+        out[f'{name}_greedy_score'] = np.array([list(g2(m))[0].vis_sc for m in lp2], dtype=np.float64)
+    # greedy_decode_ctc tie / NaN / first-frame semantics
+    for name, (arr, chars) in cases.greedy_edge_cases().items():
+        out[f'edge_{name}'] = np.array(greedy_decode_ctc(torch.from_numpy(arr.copy()), chars))
+    np.savez_compressed(os.path.join(GOLDEN, 'decoders.npz'), **out)
+    return {'config1_lines': len(g_str), 'beam_lines': nb}
+
+
+def golden_confidence():
+    _install_stubs()
+    from pero_ocr.document_ocr.page_parser import PageParser, line_confident_enough
+    from pero_ocr.core.layout import TextLine
+    from pero_ocr.ocr_engine.softmax import softmax
+    from scipy import sparse
+    out = {}
+    lg = cases.confidence_logits()
+    conf, dense_all, lp_all, enough = [], [], [], []
+    for i, m in enumerate(lg):
+        m = m.copy()
+        probs = softmax(m, axis=1)
+        m[probs < 0.0001] = 0                                        # line_ocr_engine.py:168-171
+        line = TextLine(id=str(i), logits=sparse.csc_matrix(m))
+        conf.append(PageParser.compute_line_confidence(line))
+        dense_all.append(line.get_dense_logits())
+        lp_all.append(line.get_full_logprobs())
+        enough.append(bool(line_confident_enough(lp_all[-1], 0.5)))
+    out['confidence'] = np.array(conf, dtype=np.float64)
+    out['confident_enough_0.5'] = np.array(enough)
+    for i in range(len(lg)):
+        out[f'dense_{i}'] = dense_all[i]
+        out[f'logprobs_{i}'] = lp_all[i]
+    np.savez_compressed(os.path.join(GOLDEN, 'confidence.npz'), **out)
+    return {'lines': len(lg)}
+
+
+def golden_parsenet(tmp):
+    from pero_ocr.layout_engines.torch_parsenet import TorchParseNet
+    spec = cases.PARSENET_CASE
+    net = make_net('parsenet', seed=spec['seed'])
+    path = os.path.join(tmp, 'parsenet.pt')
+    s = torch.jit.script(net)
+    s.save(path + '.cpu')
+    pn = TorchParseNet(path, torch.device('cpu'), downsample=spec['downsample'], adaptive_downsample=False)
+    img = cases.parsenet_image()
+    with contextlib.redirect_stdout(io.StringIO()):
+        maps = pn.get_maps(img, spec['downsample'])
+        maps2, ds2 = pn.get_maps_with_optimal_resolution(img)
+    assert np.array_equal(maps, maps2) and ds2 == spec['downsample']
+    np.savez_compressed(os.path.join(GOLDEN, 'parsenet.npz'), maps=maps.astype(np.float32))
+    return {'maps_shape': list(maps.shape), 'absmax': float(np.abs(maps).max())}
+
+
+def main():
+    sys.path.insert(0, REF)
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    report = {'reference': 'DCGM/pero-ocr v0.7.0 @ /root/reference', 'torch': torch.__version__,
+              'numpy': np.__version__}
+    with tempfile.TemporaryDirectory() as tmp:
+        report['architecture_check'] = check_reference_architecture()
+        report['decoders'] = golden_decoders()
+        report['engine_lstm'] = golden_engine('lstm', tmp)
+        report['engine_transformer'] = golden_engine('transformer', tmp)
+        report['parsenet'] = golden_parsenet(tmp)
+        report['confidence'] = golden_confidence()
+    with open(os.path.join(GOLDEN, 'REPORT.json'), 'w') as f:
+        json.dump(report, f, indent=1, sort_keys=True)
+    print(json.dumps(report, indent=1, sort_keys=True))
+
+
+if __name__ == '__main__':
+    main()
