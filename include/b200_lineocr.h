@@ -115,6 +115,9 @@ int b200ocr_forward(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_
 int b200ocr_forward_maps(b200ocr_engine_t* e, const uint8_t* image, int32_t h, int32_t w, float* maps,
                          void* cuda_stream);
 
+/* Workspace for b200ocr_forward_maps on canvases up to max_h x max_w. */
+int b200ocr_reserve_maps(b200ocr_engine_t* e, int32_t max_h, int32_t max_w);
+
 void b200ocr_destroy(b200ocr_engine_t* e);
 
 /* Last error text of this engine (or of the last failed b200ocr_create when e == NULL). */
@@ -147,8 +150,11 @@ int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_
 /* Route every implicit-GEMM layer through a naive one-thread-per-output CUDA-core kernel (same packed fp16
  * operands, fp32 accumulate) so the tcgen05 path can be checked on a GPU box where the reference is absent. */
 int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
-/* Copies the fp32-expanded output activation of layer `layer` of the LAST forward to host `out` (NHWC). */
-int b200ocr_debug_read_activation(b200ocr_engine_t* e, int32_t layer, float* out, int64_t capacity, int64_t* written);
+/* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
+ * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */
+int b200ocr_debug_forward_prefix(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_t h, int32_t w,
+                                 int32_t n_layers, float* out, int64_t capacity, int64_t* written, int32_t* shape4,
+                                 void* cuda_stream);
 
 #ifdef __cplusplus
 }

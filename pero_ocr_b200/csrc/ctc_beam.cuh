@@ -1,0 +1,12 @@
+// CTC prefix beam search (log domain, fp64) -- replaces CTCPrefixLogRawNumpyDecoder.__call__ without LM
+// (pero_ocr/decoding/decoders.py:220-299).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// 0 = configuration not supported (k > 64, c > 1024 or the candidate table does not fit shared memory)
+size_t ctc_beam_workspace_bytes(int n, int t, int c, int k);
+
+cudaError_t launch_ctc_prefix_beam(const double* logprobs, int n, int t, int c, int k, int32_t* out_labels,
+                                   int32_t* out_lengths, double* out_scores, int32_t* status, void* workspace,
+                                   cudaStream_t stream);

@@ -1,0 +1,792 @@
+// Host side of libb200_lineocr.so: weight packing, workspace planning, layer walk, C ABI (include/b200_lineocr.h).
+#include "../../include/b200_lineocr.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ctc_beam.cuh"
+#include "igemm.cuh"
+#include "kernels.cuh"
+#include "lstm_tc.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct Gemm {  // one dense contraction: packed fp16 weights [plane][tap][cout_pad][cin] + fp32 epilogue vectors
+    int cin = 0, cout = 0, kh = 1, kw = 1, pad_h = 0, pad_w = 0, bn = 64, cout_pad = 0, planes = 1;
+    __half* w = nullptr;
+    float* bias = nullptr;
+    float* post_scale = nullptr;
+    float* post_shift = nullptr;
+    CUtensorMap tmB;
+};
+
+struct LayerRT {
+    int kind = 0, act = 0, pool_h = 1, pool_w = 1;
+    Gemm g;                  // CONV / CTC_HEAD / BILSTM input projection
+    float* w_t = nullptr;    // CONV_FIRST: fp32 [27][cout]
+    float* bias0 = nullptr;  // CONV_FIRST
+    int cout0 = 0;
+    int hidden = 0;          // BILSTM
+    __half* w_rec = nullptr;
+    float* w_hh_t = nullptr;
+    CUtensorMap tmW;
+    int heads = 0, dim_ff = 0;  // TRANSFORMER
+    Gemm g_in, g_out, g_l1, g_l2;
+    float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
+};
+
+struct Shape {
+    int n, h, w, c;
+};
+
+}  // namespace
+
+struct b200ocr_engine {
+    int device = 0, num_sms = 148, precision = 0, planes = 1, npass = 1, line_height = 40;
+    bool use_ref = false;
+    std::vector<LayerRT> layers;
+    std::vector<void*> owned;
+    // workspace
+    void* hbuf[3] = {nullptr, nullptr, nullptr};
+    size_t hbuf_bytes[3] = {0, 0, 0};
+    void* fbuf[3] = {nullptr, nullptr, nullptr};
+    size_t fbuf_bytes[3] = {0, 0, 0};
+    int32_t* best = nullptr;
+    float *fmax = nullptr, *flse = nullptr, *fprob = nullptr;
+    size_t frames_cap = 0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(b200ocr_engine* e, int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    else g_create_error = buf;
+    return status;
+}
+
+#define CU_TRY(e, call)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t err__ = (call);                                                                       \
+        if (err__ != cudaSuccess)                                                                         \
+            return fail(e, B200OCR_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, \
+                        __LINE__);                                                                        \
+    } while (0)
+
+template <typename T>
+int upload(b200ocr_engine* e, const T* host, size_t count, T** dev) {
+    CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(dev), std::max<size_t>(count, 1) * sizeof(T)));
+    e->owned.push_back(*dev);
+    CU_TRY(e, cudaMemcpy(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int make_map_2d(b200ocr_engine* e, CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+    return 0;
+}
+
+int make_map_act(b200ocr_engine* e, CUtensorMap* m, const void* base, int n, int h, int w, int c_total, int th) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)c_total, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c_total * 2, (cuuint64_t)w * c_total * 2, (cuuint64_t)h * w * c_total * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(32 / th), (cuuint32_t)th, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
+    return 0;
+}
+
+// weight: PyTorch [cout][cin][kh][kw] fp32 (linear: kh = kw = 1)
+int build_gemm(b200ocr_engine* e, Gemm& g, const float* weight, const float* bias, const float* post_scale,
+               const float* post_shift, int cin, int cout, int kh, int kw, int pad_h, int pad_w) {
+    if (cin % 64) return fail(e, B200OCR_E_INVALID, "implicit GEMM needs cin %% 64 == 0 (got %d)", cin);
+    g.cin = cin; g.cout = cout; g.kh = kh; g.kw = kw; g.pad_h = pad_h; g.pad_w = pad_w;
+    g.planes = e->planes;
+    g.bn = igemm_pick_bn(cout);
+    g.cout_pad = ((cout + g.bn - 1) / g.bn) * g.bn;
+    const int taps = kh * kw;
+    const size_t rows = static_cast<size_t>(g.planes) * taps * g.cout_pad;
+    std::vector<__half> packed(rows * cin, __float2half(0.f));
+    for (int o = 0; o < cout; ++o)
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < taps; ++t) {
+                const float v = weight[(static_cast<size_t>(o) * cin + c) * taps + t];
+                const __half hi = __float2half_rn(v);
+                packed[(static_cast<size_t>(t) * g.cout_pad + o) * cin + c] = hi;
+                if (g.planes == 2)
+                    packed[((static_cast<size_t>(taps) + t) * g.cout_pad + o) * cin + c] =
+                        __float2half_rn(v - __half2float(hi));
+            }
+    if (int s = upload(e, packed.data(), packed.size(), &g.w)) return s;
+    if (bias) {
+        std::vector<float> b(g.cout_pad, 0.f);
+        std::copy(bias, bias + cout, b.begin());
+        if (int s = upload(e, b.data(), b.size(), &g.bias)) return s;
+    }
+    if (post_scale) {
+        std::vector<float> a(g.cout_pad, 1.f), b(g.cout_pad, 0.f);
+        std::copy(post_scale, post_scale + cout, a.begin());
+        std::copy(post_shift, post_shift + cout, b.begin());
+        if (int s = upload(e, a.data(), a.size(), &g.post_scale)) return s;
+        if (int s = upload(e, b.data(), b.size(), &g.post_shift)) return s;
+    }
+    return make_map_2d(e, &g.tmB, g.w, cin, rows, g.bn);
+}
+
+struct EpiOut {
+    int epi = EPI_ACT_F16;
+    __half* out_h = nullptr;
+    float* out_f32 = nullptr;
+    const float* residual = nullptr;
+    int32_t* best = nullptr;
+    float *fmax = nullptr, *flse = nullptr, *fprob = nullptr;
+};
+
+// input: fp16 NHWC [in.n][in.h][in.w][planes * g.cin]
+int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int act, int pool_h, int pool_w,
+             const EpiOut& o, cudaStream_t st, Shape* out_s) {
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_img = in_s.n; p.h_in = in_s.h; p.w_in = in_s.w; p.cin = g.cin; p.cout = g.cout;
+    p.kh = g.kh; p.kw = g.kw; p.pad_h = g.pad_h; p.pad_w = g.pad_w;
+    p.h_out = in_s.h + 2 * g.pad_h - g.kh + 1;
+    p.w_out = in_s.w + 2 * g.pad_w - g.kw + 1;
+    p.pool_h = pool_h; p.pool_w = pool_w; p.act = act; p.npass = e->npass;
+    if (p.h_out <= 0 || p.w_out <= 0) return fail(e, B200OCR_E_INVALID, "empty convolution output");
+    if (p.h_out % pool_h || p.w_out % pool_w)
+        return fail(e, B200OCR_E_INVALID, "pooled layer needs even output (%d x %d)", p.h_out, p.w_out);
+    igemm_fill_geometry(p, g.bn);
+    p.epi = o.epi;
+    p.bias = g.bias; p.post_scale = g.post_scale; p.post_shift = g.post_shift; p.residual = o.residual;
+    p.out_h = o.out_h; p.out_cstride = g.cout * e->planes; p.out_lo_off = e->planes == 2 ? g.cout : -1;
+    p.out_f32 = o.out_f32; p.best = o.best; p.fmax = o.fmax; p.flse = o.flse; p.fprob = o.fprob;
+    if (o.epi == EPI_ACT_F16 && (g.cout % 32))
+        return fail(e, B200OCR_E_INVALID, "fp16 activation output needs cout %% 32 == 0 (got %d)", g.cout);
+    if (o.epi == EPI_CTC && p.tiles_n != 1)
+        return fail(e, B200OCR_E_INVALID, "fused CTC head supports at most 256 classes");
+    if (out_s) *out_s = Shape{in_s.n, p.h_out / pool_h, p.w_out / pool_w, g.cout};
+    if (e->use_ref) {
+        if (o.epi == EPI_CTC) return fail(e, B200OCR_E_INVALID, "internal: CTC epilogue has no reference kernel");
+        CU_TRY(e, launch_igemm_ref(p, in, g.w, st));
+        e->launches++;
+        return 0;
+    }
+    CUtensorMap tmA;
+    if (int s = make_map_act(e, &tmA, in, in_s.n, in_s.h, in_s.w, e->planes * g.cin, p.th)) return s;
+    CU_TRY(e, launch_igemm_tc(p, tmA, g.tmB, g.bn, e->num_sms, st));
+    e->launches++;
+    return 0;
+}
+
+size_t hbytes(const b200ocr_engine* e, Shape s) {
+    return static_cast<size_t>(s.n) * s.h * s.w * s.c * e->planes * sizeof(__half);
+}
+size_t fbytes(Shape s) { return static_cast<size_t>(s.n) * s.h * s.w * s.c * sizeof(float); }
+
+struct Need {
+    size_t h[3] = {0, 0, 0}, f[3] = {0, 0, 0}, frames = 0;
+    void hn(int i, size_t b) { h[i] = std::max(h[i], b); }
+    void fn(int i, size_t b) { f[i] = std::max(f[i], b); }
+};
+
+struct Outputs {
+    float* logits = nullptr;
+    int32_t *labels = nullptr, *lengths = nullptr, *best_path = nullptr;
+    float* confidence = nullptr;
+    float* maps = nullptr;
+};
+
+// Walks the layer list.  dry != nullptr: only collects workspace needs.  Otherwise launches.
+int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_layers, const Outputs& out,
+         cudaStream_t st, Need* dry, Shape* final_shape, const void** final_ptr, bool* final_is_f32) {
+    Shape cur{n, h, w, 3};
+    const __half* cur_h = nullptr;  // fp16 activation
+    const float* cur_f = nullptr;   // fp32 activation (residual stream / maps)
+    int hslot = -1;                 // slot of cur_h
+    auto next_h = [&](int avoid_a, int avoid_b) {
+        for (int i = 0; i < 3; ++i)
+            if (i != avoid_a && i != avoid_b) return i;
+        return 0;
+    };
+    const int L = std::min<int>(n_layers, e->layers.size());
+    for (int li = 0; li < L; ++li) {
+        LayerRT& ly = e->layers[li];
+        const int next_kind = li + 1 < (int)e->layers.size() ? e->layers[li + 1].kind : 0;
+        switch (ly.kind) {
+            case B200OCR_CONV_FIRST: {
+                Shape os{cur.n, cur.h, cur.w, ly.cout0};
+                const int slot = 0;
+                if (dry) dry->hn(slot, hbytes(e, os));
+                else {
+                    if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
+                                                e->planes, static_cast<__half*>(e->hbuf[slot]), st));
+                    e->launches++;
+                    cur_h = static_cast<__half*>(e->hbuf[slot]);
+                }
+                hslot = slot;
+                cur = os;
+                cur_f = nullptr;
+                break;
+            }
+            case B200OCR_CONV: {
+                if (hslot < 0) return fail(e, B200OCR_E_INVALID, "layer %d: conv needs an fp16 activation input", li);
+                const bool to_f32 = next_kind == B200OCR_UPSAMPLE || next_kind == B200OCR_LN_PE;
+                Shape os{cur.n, (cur.h + 2 * ly.g.pad_h - ly.g.kh + 1) / ly.pool_h,
+                         (cur.w + 2 * ly.g.pad_w - ly.g.kw + 1) / ly.pool_w, ly.g.cout};
+                EpiOut eo;
+                int slot = -1;
+                if (to_f32) {
+                    eo.epi = EPI_F32;
+                    if (dry) dry->fn(0, fbytes(os));
+                    else {
+                        if (fbytes(os) > e->fbuf_bytes[0]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                        eo.out_f32 = static_cast<float*>(e->fbuf[0]);
+                    }
+                } else {
+                    slot = next_h(hslot, -1);
+                    if (dry) dry->hn(slot, hbytes(e, os));
+                    else {
+                        if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                        eo.out_h = static_cast<__half*>(e->hbuf[slot]);
+                    }
+                }
+                if (!dry) {
+                    Shape chk;
+                    if (int s = run_gemm(e, ly.g, cur_h, cur, ly.act, ly.pool_h, ly.pool_w, eo, st, &chk)) return s;
+                }
+                cur = os;
+                if (to_f32) {
+                    cur_f = static_cast<float*>(e->fbuf[0]);
+                    cur_h = nullptr;
+                    hslot = -1;
+                } else {
+                    cur_h = static_cast<__half*>(e->hbuf[slot]);
+                    hslot = slot;
+                    cur_f = nullptr;
+                }
+                break;
+            }
+            case B200OCR_BILSTM: {
+                if (hslot < 0 || cur.h != 1) return fail(e, B200OCR_E_INVALID, "layer %d: BiLSTM needs [n][1][T][D] fp16 input", li);
+                const int T = cur.w, H = ly.hidden;
+                Shape rows{1, 1, cur.n * T, cur.c};
+                Shape pre_s{1, 1, cur.n * T, 8 * H};
+                Shape os{cur.n, 1, T, 2 * H};
+                const int slot = next_h(hslot, -1);
+                if (dry) {
+                    dry->fn(1, fbytes(pre_s));
+                    dry->hn(slot, hbytes(e, os));
+                } else {
+                    if (fbytes(pre_s) > e->fbuf_bytes[1] || hbytes(e, os) > e->hbuf_bytes[slot])
+                        return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    EpiOut eo;
+                    eo.epi = EPI_F32;
+                    eo.out_f32 = static_cast<float*>(e->fbuf[1]);
+                    if (int s = run_gemm(e, ly.g, cur_h, rows, 0, 1, 1, eo, st, nullptr)) return s;
+                    __half* o = static_cast<__half*>(e->hbuf[slot]);
+                    if (e->use_ref) {
+                        CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->planes, e->planes == 1, o, st));
+                    } else {
+                        CU_TRY(e, launch_lstm_tc(ly.tmW, eo.out_f32, o, cur.n, T, H, e->planes, st));
+                    }
+                    e->launches++;
+                    cur_h = o;
+                }
+                hslot = slot;
+                cur = os;
+                break;
+            }
+            case B200OCR_LN_PE: {
+                if (!cur_f && !dry) return fail(e, B200OCR_E_INVALID, "layer %d: LayerNorm needs an fp32 input", li);
+                // cur: [n][1][T][D] fp32 in fbuf[0] -> residual stream fp32 (fbuf[2]) + fp16 operand (hbuf[0])
+                const int T = cur.w;
+                if (dry) {
+                    dry->fn(2, fbytes(cur));
+                    dry->hn(0, hbytes(e, cur));
+                } else {
+                    if (fbytes(cur) > e->fbuf_bytes[2] || hbytes(e, cur) > e->hbuf_bytes[0])
+                        return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    CU_TRY(e, launch_layernorm(cur_f, cur.n * T, cur.c, ly.n1w, ly.n1b, 1e-5f, T,
+                                               static_cast<float*>(e->fbuf[2]), static_cast<__half*>(e->hbuf[0]),
+                                               e->planes, st));
+                    e->launches++;
+                    cur_f = static_cast<float*>(e->fbuf[2]);
+                    cur_h = static_cast<__half*>(e->hbuf[0]);
+                }
+                hslot = 0;
+                break;
+            }
+            case B200OCR_TRANSFORMER_LAYER: {
+                // in: residual x fp32 (fbuf[2]) + x fp16 (hbuf[0]); out: same slots
+                if (hslot != 0) return fail(e, B200OCR_E_INVALID, "layer %d: transformer layer must follow LN_PE or another transformer layer", li);
+                const int T = cur.w, D = cur.c, R = cur.n * T;
+                Shape rows{1, 1, R, D};
+                Shape qkv_s{1, 1, R, 3 * D}, ff_s{1, 1, R, ly.dim_ff};
+                if (dry) {
+                    dry->fn(0, fbytes(qkv_s));
+                    dry->fn(1, fbytes(rows));
+                    dry->hn(1, hbytes(e, rows));
+                    dry->hn(2, hbytes(e, ff_s));
+                } else {
+                    if (fbytes(qkv_s) > e->fbuf_bytes[0] || fbytes(rows) > e->fbuf_bytes[1] ||
+                        hbytes(e, rows) > e->hbuf_bytes[1] || hbytes(e, ff_s) > e->hbuf_bytes[2])
+                        return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    float* x = static_cast<float*>(e->fbuf[2]);
+                    float* qkv = static_cast<float*>(e->fbuf[0]);
+                    float* tmp = static_cast<float*>(e->fbuf[1]);
+                    __half* xh = static_cast<__half*>(e->hbuf[0]);
+                    __half* ah = static_cast<__half*>(e->hbuf[1]);
+                    __half* fh = static_cast<__half*>(e->hbuf[2]);
+                    EpiOut eo;
+                    eo.epi = EPI_F32; eo.out_f32 = qkv;
+                    if (int s = run_gemm(e, ly.g_in, xh, rows, 0, 1, 1, eo, st, nullptr)) return s;
+                    CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->planes, st));
+                    e->launches++;
+                    EpiOut er;
+                    er.epi = EPI_RES_F32; er.out_f32 = tmp; er.residual = x;
+                    if (int s = run_gemm(e, ly.g_out, ah, rows, 0, 1, 1, er, st, nullptr)) return s;
+                    CU_TRY(e, launch_layernorm(tmp, R, D, ly.n1w, ly.n1b, 1e-5f, 0, x, xh, e->planes, st));
+                    e->launches++;
+                    EpiOut ef;
+                    ef.epi = EPI_ACT_F16; ef.out_h = fh;
+                    if (int s = run_gemm(e, ly.g_l1, xh, rows, B200OCR_ACT_RELU, 1, 1, ef, st, nullptr)) return s;
+                    Shape ffrows{1, 1, R, ly.dim_ff};
+                    er.out_f32 = tmp; er.residual = x;
+                    if (int s = run_gemm(e, ly.g_l2, fh, ffrows, 0, 1, 1, er, st, nullptr)) return s;
+                    CU_TRY(e, launch_layernorm(tmp, R, D, ly.n2w, ly.n2b, 1e-5f, 0, x, xh, e->planes, st));
+                    e->launches++;
+                }
+                break;
+            }
+            case B200OCR_CTC_HEAD: {
+                if (hslot < 0 || cur.h != 1) return fail(e, B200OCR_E_INVALID, "layer %d: CTC head needs [n][1][T][D] fp16 input", li);
+                const int T = cur.w, C = ly.g.cout;
+                const size_t frames = static_cast<size_t>(cur.n) * T;
+                Shape rows{1, 1, cur.n * T, cur.c};
+                Shape lg{cur.n, 1, T, C};
+                if (dry) {
+                    dry->frames = std::max(dry->frames, frames);
+                    dry->fn(0, fbytes(lg));  // reference-kernel path materialises logits even when not asked for
+                } else {
+                    if (frames > e->frames_cap) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    int32_t* best = out.best_path ? out.best_path : e->best;
+                    if (e->use_ref) {
+                        float* logits = out.logits;
+                        if (!logits) {
+                            if (fbytes(lg) > e->fbuf_bytes[0]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                            logits = static_cast<float*>(e->fbuf[0]);
+                        }
+                        EpiOut eo;
+                        eo.epi = EPI_F32; eo.out_f32 = logits;
+                        if (int s = run_gemm(e, ly.g, cur_h, rows, 0, 1, 1, eo, st, nullptr)) return s;
+                        CU_TRY(e, launch_frame_stats(logits, cur.n, T, C, 0, best, e->fmax, e->flse, e->fprob, st));
+                        e->launches++;
+                    } else {
+                        EpiOut eo;
+                        eo.epi = EPI_CTC; eo.out_f32 = out.logits; eo.best = best;
+                        eo.fmax = e->fmax; eo.flse = e->flse; eo.fprob = out.confidence ? e->fprob : nullptr;
+                        if (int s = run_gemm(e, ly.g, cur_h, rows, 0, 1, 1, eo, st, nullptr)) return s;
+                    }
+                    if (out.labels) {
+                        CU_TRY(e, launch_ctc_collapse(best, out.confidence ? e->fprob : nullptr, cur.n, T, C - 1,
+                                                      out.labels, out.lengths, out.confidence, st));
+                        e->launches++;
+                    }
+                }
+                cur = lg;
+                cur_f = out.logits;
+                cur_h = nullptr;
+                hslot = -1;
+                break;
+            }
+            case B200OCR_UPSAMPLE: {
+                if (!dry) {
+                    if (!cur_f) return fail(e, B200OCR_E_INVALID, "layer %d: upsample needs an fp32 input", li);
+                    if (out.maps) {
+                        CU_TRY(e, launch_upsample_nchw(cur_f, cur.n, cur.h, cur.w, cur.c, ly.pool_h, out.maps, st));
+                        e->launches++;
+                    }
+                }
+                cur = Shape{cur.n, cur.h * ly.pool_h, cur.w * ly.pool_h, cur.c};
+                cur_f = out.maps;
+                break;
+            }
+            default:
+                return fail(e, B200OCR_E_INVALID, "layer %d: unknown kind %d", li, ly.kind);
+        }
+    }
+    if (final_shape) *final_shape = cur;
+    if (final_ptr) *final_ptr = cur_h ? static_cast<const void*>(cur_h) : static_cast<const void*>(cur_f);
+    if (final_is_f32) *final_is_f32 = cur_h == nullptr;
+    return 0;
+}
+
+int check_device(b200ocr_engine* e, int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= device)
+        return fail(e, B200OCR_E_NO_DEVICE, "no CUDA device %d visible (there is no CPU fallback)", device);
+    cudaDeviceProp prop;
+    CU_TRY(e, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(e, B200OCR_E_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                    prop.major, prop.minor);
+    return 0;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
+    if (!desc || !out || desc->n_layers <= 0 || !desc->layers) return fail(nullptr, B200OCR_E_INVALID, "bad descriptor");
+    *out = nullptr;
+    if (int s = check_device(nullptr, desc->device)) return s;
+    b200ocr_engine* e = new b200ocr_engine();
+    auto bail = [&](int s) {
+        g_create_error = e->err;
+        b200ocr_destroy(e);
+        return s;
+    };
+    e->device = desc->device;
+    if (cudaSetDevice(e->device) != cudaSuccess) return bail(fail(e, B200OCR_E_CUDA, "cudaSetDevice failed"));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, e->device);
+    e->num_sms = prop.multiProcessorCount;
+    e->precision = desc->precision;
+    e->planes = desc->precision == B200OCR_PREC_FP16X3 ? 2 : 1;
+    e->npass = e->planes == 2 ? 3 : 1;
+    e->line_height = desc->line_height;
+    e->layers.resize(desc->n_layers);
+    for (int i = 0; i < desc->n_layers; ++i) {
+        const b200ocr_layer_t& d = desc->layers[i];
+        LayerRT& ly = e->layers[i];
+        ly.kind = d.kind; ly.act = d.act;
+        ly.pool_h = d.pool_h > 0 ? d.pool_h : 1;
+        ly.pool_w = d.pool_w > 0 ? d.pool_w : 1;
+        int s = 0;
+        switch (d.kind) {
+            case B200OCR_CONV_FIRST: {
+                if (d.cin != 3 || d.kh != 3 || d.kw != 3 || d.cout > 64 || (d.cout % 8))
+                    return bail(fail(e, B200OCR_E_INVALID, "layer %d: first conv must be 3x3, 3 -> <=64 channels", i));
+                std::vector<float> wt(27 * d.cout);
+                for (int o = 0; o < d.cout; ++o)
+                    for (int c = 0; c < 3; ++c)
+                        for (int r = 0; r < 3; ++r)
+                            for (int q = 0; q < 3; ++q)
+                                wt[((r * 3 + q) * 3 + c) * d.cout + o] = d.weight[((o * 3 + c) * 3 + r) * 3 + q];
+                ly.cout0 = d.cout;
+                if ((s = upload(e, wt.data(), wt.size(), &ly.w_t))) return bail(s);
+                if (d.bias && (s = upload(e, d.bias, (size_t)d.cout, &ly.bias0))) return bail(s);
+                break;
+            }
+            case B200OCR_CONV:
+            case B200OCR_CTC_HEAD:
+                if ((s = build_gemm(e, ly.g, d.weight, d.bias, d.post_scale, d.post_shift, d.cin, d.cout,
+                                    d.kh > 0 ? d.kh : 1, d.kw > 0 ? d.kw : 1, d.pad_h, d.pad_w)))
+                    return bail(s);
+                break;
+            case B200OCR_BILSTM: {
+                const int H = d.hidden;
+                if (H != 256) return bail(fail(e, B200OCR_E_INVALID, "layer %d: BiLSTM hidden size must be 256", i));
+                // input projection of both directions as one GEMM: rows [dir][4H], bias = b_ih + b_hh
+                std::vector<float> wih(static_cast<size_t>(8) * H * d.cin), bsum(8 * H);
+                for (int dir = 0; dir < 2; ++dir) {
+                    std::copy(d.w_ih[dir], d.w_ih[dir] + static_cast<size_t>(4) * H * d.cin,
+                              wih.begin() + static_cast<size_t>(dir) * 4 * H * d.cin);
+                    for (int k = 0; k < 4 * H; ++k) bsum[dir * 4 * H + k] = d.b_ih[dir][k] + d.b_hh[dir][k];
+                }
+                if ((s = build_gemm(e, ly.g, wih.data(), bsum.data(), nullptr, nullptr, d.cin, 8 * H, 1, 1, 0, 0)))
+                    return bail(s);
+                ly.hidden = H;
+                // recurrent weights for the tcgen05 kernel: [dir][plane][cta j][row = gate*32 + u][k]
+                const int P = e->planes;
+                std::vector<__half> rec(static_cast<size_t>(2) * P * 8 * 128 * H);
+                std::vector<float> wt(static_cast<size_t>(2) * H * 4 * H);
+                for (int dir = 0; dir < 2; ++dir)
+                    for (int g = 0; g < 4; ++g)
+                        for (int u = 0; u < H; ++u)
+                            for (int k = 0; k < H; ++k) {
+                                const float v = d.w_hh[dir][(static_cast<size_t>(g) * H + u) * H + k];
+                                const __half hi = __float2half_rn(v);
+                                const int j = u / 32, row = g * 32 + (u % 32);
+                                rec[(((static_cast<size_t>(dir) * P + 0) * 8 + j) * 128 + row) * H + k] = hi;
+                                if (P == 2)
+                                    rec[(((static_cast<size_t>(dir) * P + 1) * 8 + j) * 128 + row) * H + k] =
+                                        __float2half_rn(v - __half2float(hi));
+                                // cross-check kernel: fp32 (x3) or the fp16-rounded value (fp16 mode), [dir][k][4H]
+                                wt[(static_cast<size_t>(dir) * H + k) * 4 * H + g * H + u] = P == 2 ? v : __half2float(hi);
+                            }
+                if ((s = upload(e, rec.data(), rec.size(), &ly.w_rec))) return bail(s);
+                if ((s = upload(e, wt.data(), wt.size(), &ly.w_hh_t))) return bail(s);
+                if ((s = make_map_2d(e, &ly.tmW, ly.w_rec, H, static_cast<uint64_t>(2) * P * 8 * 128, 128))) return bail(s);
+                break;
+            }
+            case B200OCR_LN_PE:
+                if ((s = upload(e, d.norm1_w, (size_t)d.cin, &ly.n1w))) return bail(s);
+                if ((s = upload(e, d.norm1_b, (size_t)d.cin, &ly.n1b))) return bail(s);
+                break;
+            case B200OCR_TRANSFORMER_LAYER: {
+                const int D = d.cin;
+                ly.heads = d.heads; ly.dim_ff = d.dim_ff;
+                if ((s = build_gemm(e, ly.g_in, d.in_proj_w, d.in_proj_b, nullptr, nullptr, D, 3 * D, 1, 1, 0, 0))) return bail(s);
+                if ((s = build_gemm(e, ly.g_out, d.out_proj_w, d.out_proj_b, nullptr, nullptr, D, D, 1, 1, 0, 0))) return bail(s);
+                if ((s = build_gemm(e, ly.g_l1, d.lin1_w, d.lin1_b, nullptr, nullptr, D, d.dim_ff, 1, 1, 0, 0))) return bail(s);
+                if ((s = build_gemm(e, ly.g_l2, d.lin2_w, d.lin2_b, nullptr, nullptr, d.dim_ff, D, 1, 1, 0, 0))) return bail(s);
+                if ((s = upload(e, d.norm1_w, (size_t)D, &ly.n1w))) return bail(s);
+                if ((s = upload(e, d.norm1_b, (size_t)D, &ly.n1b))) return bail(s);
+                if ((s = upload(e, d.norm2_w, (size_t)D, &ly.n2w))) return bail(s);
+                if ((s = upload(e, d.norm2_b, (size_t)D, &ly.n2b))) return bail(s);
+                break;
+            }
+            case B200OCR_UPSAMPLE:
+                break;
+            default:
+                return bail(fail(e, B200OCR_E_INVALID, "layer %d: unknown kind %d", i, d.kind));
+        }
+    }
+    *out = e;
+    return B200OCR_OK;
+}
+
+int b200ocr_reserve(b200ocr_engine_t* e, int32_t max_lines, int32_t max_width_px) {
+    if (!e || max_lines <= 0 || max_width_px <= 0) return fail(e, B200OCR_E_INVALID, "bad reserve arguments");
+    CU_TRY(e, cudaSetDevice(e->device));
+    Need need;
+    Outputs none;
+    if (int s = walk(e, nullptr, max_lines, e->line_height, max_width_px, 1 << 30, none, nullptr, &need, nullptr,
+                     nullptr, nullptr))
+        return s;
+    for (int i = 0; i < 3; ++i) {
+        if (need.h[i] > e->hbuf_bytes[i]) {
+            if (e->hbuf[i]) cudaFree(e->hbuf[i]);
+            e->hbuf[i] = nullptr; e->hbuf_bytes[i] = 0;
+            CU_TRY(e, cudaMalloc(&e->hbuf[i], need.h[i]));
+            e->hbuf_bytes[i] = need.h[i];
+        }
+        if (need.f[i] > e->fbuf_bytes[i]) {
+            if (e->fbuf[i]) cudaFree(e->fbuf[i]);
+            e->fbuf[i] = nullptr; e->fbuf_bytes[i] = 0;
+            CU_TRY(e, cudaMalloc(&e->fbuf[i], need.f[i]));
+            e->fbuf_bytes[i] = need.f[i];
+        }
+    }
+    if (need.frames > e->frames_cap) {
+        if (e->best) { cudaFree(e->best); cudaFree(e->fmax); cudaFree(e->flse); cudaFree(e->fprob); }
+        e->frames_cap = 0;
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->best), need.frames * 4));
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->fmax), need.frames * 4));
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->flse), need.frames * 4));
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->fprob), need.frames * 4));
+        e->frames_cap = need.frames;
+    }
+    return B200OCR_OK;
+}
+
+int b200ocr_forward(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_t h, int32_t w, float* logits,
+                    int32_t* labels, int32_t* lengths, float* confidence, int32_t* best_path, void* cuda_stream) {
+    if (!e) return B200OCR_E_INVALID;
+    if (!crops || n <= 0 || h != e->line_height || w <= 0 || (w % 8))
+        return fail(e, B200OCR_E_INVALID, "bad forward arguments (n=%d h=%d w=%d; h must be %d, w a multiple of 8)", n, h,
+                    w, e->line_height);
+    if (labels && !lengths) return fail(e, B200OCR_E_INVALID, "labels requires lengths");
+    Outputs o;
+    o.logits = logits; o.labels = labels; o.lengths = lengths; o.confidence = confidence; o.best_path = best_path;
+    return walk(e, crops, n, h, w, 1 << 30, o, static_cast<cudaStream_t>(cuda_stream), nullptr, nullptr, nullptr, nullptr);
+}
+
+int b200ocr_forward_maps(b200ocr_engine_t* e, const uint8_t* image, int32_t h, int32_t w, float* maps, void* cuda_stream) {
+    if (!e) return B200OCR_E_INVALID;
+    if (!image || !maps || h <= 0 || w <= 0) return fail(e, B200OCR_E_INVALID, "bad forward_maps arguments");
+    Need need;
+    Outputs none;
+    if (int s = walk(e, nullptr, 1, h, w, 1 << 30, none, nullptr, &need, nullptr, nullptr, nullptr)) return s;
+    for (int i = 0; i < 3; ++i)
+        if (need.h[i] > e->hbuf_bytes[i] || need.f[i] > e->fbuf_bytes[i])
+            return fail(e, B200OCR_E_WORKSPACE, "workspace too small: call b200ocr_reserve_maps first");
+    Outputs o;
+    o.maps = maps;
+    return walk(e, image, 1, h, w, 1 << 30, o, static_cast<cudaStream_t>(cuda_stream), nullptr, nullptr, nullptr, nullptr);
+}
+
+int b200ocr_reserve_maps(b200ocr_engine_t* e, int32_t max_h, int32_t max_w) {
+    if (!e || max_h <= 0 || max_w <= 0) return fail(e, B200OCR_E_INVALID, "bad reserve arguments");
+    const int saved = e->line_height;
+    e->line_height = max_h;
+    const int s = b200ocr_reserve(e, 1, max_w);
+    e->line_height = saved;
+    return s;
+}
+
+void b200ocr_destroy(b200ocr_engine_t* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (void* p : e->owned) cudaFree(p);
+    for (int i = 0; i < 3; ++i) {
+        if (e->hbuf[i]) cudaFree(e->hbuf[i]);
+        if (e->fbuf[i]) cudaFree(e->fbuf[i]);
+    }
+    if (e->best) { cudaFree(e->best); cudaFree(e->fmax); cudaFree(e->flse); cudaFree(e->fprob); }
+    delete e;
+}
+
+const char* b200ocr_last_error(const b200ocr_engine_t* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int64_t b200ocr_launch_count(const b200ocr_engine_t* e) { return e ? e->launches : 0; }
+
+double b200ocr_forward_flops(const b200ocr_engine_t* e, int32_t n, int32_t w, double* conv_gemm_flops) {
+    if (!e) return 0.0;
+    double total = 0.0, gemm = 0.0;
+    int h = e->line_height, cw = w;
+    for (const LayerRT& ly : e->layers) {
+        auto gf = [&](const Gemm& g, double pixels) { return 2.0 * pixels * g.cout * g.cin * g.kh * g.kw; };
+        switch (ly.kind) {
+            case B200OCR_CONV_FIRST:
+                total += 2.0 * n * h * cw * ly.cout0 * 27;
+                break;
+            case B200OCR_CONV: {
+                const int ho = h + 2 * ly.g.pad_h - ly.g.kh + 1, wo = cw + 2 * ly.g.pad_w - ly.g.kw + 1;
+                const double f = gf(ly.g, static_cast<double>(n) * ho * wo);
+                total += f; gemm += f;
+                h = ho / ly.pool_h; cw = wo / ly.pool_w;
+                break;
+            }
+            case B200OCR_BILSTM: {
+                const double f = gf(ly.g, static_cast<double>(n) * cw);
+                const double r = 2.0 * n * cw * 2 * 4 * ly.hidden * ly.hidden;
+                total += f + r; gemm += f;
+                break;
+            }
+            case B200OCR_CTC_HEAD: {
+                const double f = gf(ly.g, static_cast<double>(n) * cw);
+                total += f; gemm += f;
+                break;
+            }
+            case B200OCR_TRANSFORMER_LAYER: {
+                const double px = static_cast<double>(n) * cw;
+                const double f = gf(ly.g_in, px) + gf(ly.g_out, px) + gf(ly.g_l1, px) + gf(ly.g_l2, px);
+                const double a = 4.0 * n * cw * cw * ly.g_out.cin;
+                total += f + a; gemm += f;
+                break;
+            }
+            default: break;
+        }
+    }
+    if (conv_gemm_flops) *conv_gemm_flops = gemm;
+    return total;
+}
+
+int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int32_t layout, int32_t* labels,
+                       int32_t* lengths, float* confidence, int32_t* best_path, float* frame_max, float* frame_lse,
+                       void* cuda_stream) {
+    if (!scores || n < 0 || t <= 0 || c <= 1 || !labels || !lengths || !best_path || (layout != 0 && layout != 1))
+        return fail(nullptr, B200OCR_E_INVALID, "bad ctc_greedy arguments");
+    if (n == 0) return B200OCR_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    float* fprob = nullptr;
+    if (confidence) CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&fprob), static_cast<size_t>(n) * t * 4, st));
+    CU_TRY(nullptr, launch_frame_stats(scores, n, t, c, layout, best_path, frame_max, frame_lse, fprob, st));
+    CU_TRY(nullptr, launch_ctc_collapse(best_path, fprob, n, t, c - 1, labels, lengths, confidence, st));
+    if (fprob) CU_TRY(nullptr, cudaFreeAsync(fprob, st));
+    return B200OCR_OK;
+}
+
+int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
+                            int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream) {
+    if (!logprobs || n < 0 || t <= 0 || c <= 1 || k < 1 || !out_labels || !out_lengths || !out_scores || !status)
+        return fail(nullptr, B200OCR_E_INVALID, "bad ctc_prefix_beam arguments");
+    if (n == 0) return B200OCR_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    void* ws = nullptr;
+    const size_t ws_bytes = ctc_beam_workspace_bytes(n, t, c, k);
+    if (ws_bytes == 0) return fail(nullptr, B200OCR_E_INVALID, "beam size / class count not supported (k <= 64, c <= 1024)");
+    CU_TRY(nullptr, cudaMallocAsync(&ws, ws_bytes, st));
+    cudaError_t err = launch_ctc_prefix_beam(logprobs, n, t, c, k, out_labels, out_lengths, out_scores, status, ws, st);
+    cudaFreeAsync(ws, st);
+    if (err != cudaSuccess) return fail(nullptr, B200OCR_E_CUDA, "prefix beam launch failed: %s", cudaGetErrorString(err));
+    return B200OCR_OK;
+}
+
+int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on) {
+    if (!e) return B200OCR_E_INVALID;
+    e->use_ref = on != 0;
+    return B200OCR_OK;
+}
+
+int b200ocr_debug_forward_prefix(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_t h, int32_t w,
+                                 int32_t n_layers, float* out, int64_t capacity, int64_t* written, int32_t* shape4,
+                                 void* cuda_stream) {
+    if (!e || !crops || !out || n_layers <= 0) return fail(e, B200OCR_E_INVALID, "bad debug arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    Outputs o;
+    Shape fs;
+    const void* ptr = nullptr;
+    bool is_f32 = false;
+    if (int s = walk(e, crops, n, h, w, n_layers, o, st, nullptr, &fs, &ptr, &is_f32)) return s;
+    const int64_t count = static_cast<int64_t>(fs.n) * fs.h * fs.w * fs.c;
+    if (shape4) { shape4[0] = fs.n; shape4[1] = fs.h; shape4[2] = fs.w; shape4[3] = fs.c; }
+    if (written) *written = count;
+    if (count > capacity || !ptr) return fail(e, B200OCR_E_INVALID, "debug buffer too small (%lld needed)", (long long)count);
+    if (is_f32) {
+        CU_TRY(e, cudaMemcpyAsync(out, ptr, count * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        float* tmp = nullptr;
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(&tmp), count * 4));
+        CU_TRY(e, launch_h2f(static_cast<const __half*>(ptr), fs.n * fs.h * fs.w, fs.c, e->planes, tmp, st));
+        CU_TRY(e, cudaMemcpyAsync(out, tmp, count * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(e, cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    CU_TRY(e, cudaStreamSynchronize(st));
+    return B200OCR_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

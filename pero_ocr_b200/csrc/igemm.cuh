@@ -1,4 +1,8 @@
 // Shared declarations for the implicit-GEMM convolution / GEMM kernels.
+//
+// One kernel family serves every dense contraction on the hot path:
+//   out[pixel][cout] = epilogue( sum_{tap, cin} in[pixel + tap][cin] * w[tap][cout][cin] )
+// A "pixel" is a position of an NHWC fp16 activation tensor; a plain GEMM is the 1x1 case on a [1][1][M][K] image.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -22,7 +26,8 @@ struct IgemmParams {
     int pool_h, pool_w;
     int act;
     int npass;  // 1 (fp16) or 3 (fp16x3: hi*hi + hi*lo + lo*hi)
-    int tiles_x, tiles_y, tiles_n;
+    int th;     // rows per segment (1 or 2); a segment is th x (32/th) output pixels = one TMEM lane quarter
+    int segs_per_row, row_groups, total_segs, m_tiles, tiles_n;
     int epi;
     const float* bias;        // [cout] or null
     const float* post_scale;  // [cout] or null
@@ -35,16 +40,26 @@ struct IgemmParams {
     int32_t* best;            // EPI_CTC
     float* fmax;
     float* flse;
+    float* fprob;             // best-class probability under the reference's sparsified softmax (or null)
 };
 
-// Launches the tcgen05 kernel.  tmA / tmB are built by make_tmaps_for_igemm().  Returns cudaGetLastError().
-cudaError_t launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int th,
-                            int num_sms, cudaStream_t stream);
+inline void igemm_fill_geometry(IgemmParams& p, int bn) {
+    p.th = (p.pool_h == 2 || (p.h_out % 2 == 0)) ? 2 : 1;
+    const int segw = 32 / p.th;
+    p.segs_per_row = (p.w_out + segw - 1) / segw;
+    p.row_groups = (p.h_out + p.th - 1) / p.th;
+    p.total_segs = p.n_img * p.row_groups * p.segs_per_row;
+    p.m_tiles = (p.total_segs + 3) / 4;
+    p.tiles_n = (p.cout + bn - 1) / bn;
+    p.cout_pad = p.tiles_n * bn;
+}
+
+inline int igemm_pick_bn(int cout) { return cout > 128 ? 256 : (cout > 64 ? 128 : 64); }
+
+// Launches the tcgen05 kernel.  tmA: 4D map over the input activation (C, W, H, N), box (64, 32/th, th, 1),
+// 128B swizzle; tmB: 2D map over the packed weights (cin, rows), box (64, bn).  Returns cudaGetLastError().
+cudaError_t launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int num_sms,
+                            cudaStream_t stream);
 
 // Naive CUDA-core kernel with identical semantics (debug / cross-check only).
-cudaError_t launch_igemm_ref(const IgemmParams& p, const __half* in, const __half* w_packed, int w_ld,
-                             cudaStream_t stream);
-
-// Tile geometry decisions shared by the launcher and the host planner.
-inline int igemm_pick_bn(int cout) { return cout > 128 ? 256 : (cout > 64 ? 128 : 64); }
-inline int igemm_pick_th(int pool_h, int h_out) { return (pool_h == 2 || (h_out >= 2 && (h_out % 2) == 0)) ? 2 : 1; }
+cudaError_t launch_igemm_ref(const IgemmParams& p, const __half* in, const __half* w_packed, cudaStream_t stream);

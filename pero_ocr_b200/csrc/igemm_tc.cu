@@ -1,0 +1,399 @@
+// tcgen05 implicit-GEMM convolution / GEMM for sm_100a.
+//
+// Replaces the cuDNN / cuBLAS calls hidden inside the reference's TorchScript recogniser blob
+// (pero_ocr/ocr_engine/pytorch_ocr_engine.py:64-69; layer list = pero_ocr/ocr_engine/transformer.py:75-148,335-363).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0     TMA producer: per (pass, tap, 64-channel chunk) four 4-D box loads of the NHWC activation
+//              (shifted by the tap; out-of-bounds = conv zero padding, filled by TMA) + one 2-D load of the weights
+//   warp 1     allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
+//   warps 2-5  epilogue: tcgen05.ld (one output pixel per thread, 32 channels per load), bias + activation,
+//              max-pool by warp shuffles, BatchNorm affine, fp16 hi/lo split, vectorised NHWC stores -- or the
+//              fused CTC epilogue (per-frame argmax / max / logsumexp; logits optional)
+// A tile is 4 segments of 32 output pixels (th x 32/th); segment q feeds TMEM lanes [32q, 32q+32), so a 2x2 or
+// 2x1 max-pool never leaves the warp.
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 fp16
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (192 * 1024) / kStageBytes;
+    static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;  // two accumulators
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct SegCoord {
+    int img, h0, w0;
+};
+
+__device__ __forceinline__ SegCoord seg_coord(const IgemmParams& p, int seg) {
+    SegCoord c;
+    if (seg >= p.total_segs) {  // past the end: every load is out of bounds (zeros), every store masked
+        c.img = p.n_img;
+        c.h0 = 0;
+        c.w0 = 0;
+        return c;
+    }
+    const int per_img = p.row_groups * p.segs_per_row;
+    c.img = seg / per_img;
+    const int r = seg - c.img * per_img;
+    const int rg = r / p.segs_per_row;
+    c.h0 = rg * p.th;
+    c.w0 = (r - rg * p.segs_per_row) * (32 / p.th);
+    return c;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const IgemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full = bars;                      // [kStages]
+    uint64_t* empty = bars + C::kStages;        // [kStages]
+    uint64_t* tfull = bars + 2 * C::kStages;    // [2]
+    uint64_t* tempty = bars + 2 * C::kStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int taps = p.kh * p.kw;
+    const int kchunks = p.cin >> 6;
+    const int k_iters = p.npass * taps * kchunks;
+    const int total_tiles = p.m_tiles * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < C::kStages; ++i) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull[i], 1);
+            ptx::mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.tiles_n;
+                const int nt = tile - mt * p.tiles_n;
+                SegCoord sc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sc[q] = seg_coord(p, mt * 4 + q);
+                for (int pass = 0; pass < p.npass; ++pass) {
+                    const int pa = (pass == 2) ? 1 : 0;  // activation plane
+                    const int pb = (pass == 1) ? 1 : 0;  // weight plane
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const int r = tap / p.kw;
+                        const int s = tap - r * p.kw;
+                        const int brow = (pb * taps + tap) * p.cout_pad + nt * BN;
+                        for (int kc = 0; kc < kchunks; ++kc) {
+                            ptx::mbar_wait(&empty[stage], phase ^ 1);
+                            uint8_t* sA = smem + stage * C::kStageBytes;
+                            uint8_t* sB = sA + kABytes;
+                            ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                ptx::tma_load_4d(sA + q * 4096, &tmA, &full[stage], pa * p.cin + kc * 64,
+                                                 sc[q].w0 + s - p.pad_w, sc[q].h0 + r - p.pad_h, sc[q].img);
+                            ptx::tma_load_2d(sB, &tmB, &full[stage], kc * 64, brow);
+                            if (++stage == C::kStages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int it = 0; it < k_iters; ++it) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr);
+                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)  // 4 x K=16 inside the 128-byte swizzle atom: +32 B per step
+                        ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+                    ptx::mma_commit(&empty[stage]);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::mma_commit(&tfull[acc]);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int segw = 32 / p.th;
+        const int dh = lane / segw;
+        const int dw = lane - dh * segw;
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.tiles_n;
+            const int nt = tile - mt * p.tiles_n;
+            const SegCoord sc = seg_coord(p, mt * 4 + q);
+            const int ho = sc.h0 + dh, wo = sc.w0 + dw;
+            const bool valid = sc.img < p.n_img && ho < p.h_out && wo < p.w_out;
+            ptx::mbar_wait(&tfull[acc], acc_phase[acc]);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+            if (p.epi == EPI_ACT_F16) {
+                const bool writer = valid && (dh % p.pool_h == 0) && (dw % p.pool_w == 0);
+                const int hp = ho / p.pool_h, wp = wo / p.pool_w;
+                const int Hp = p.h_out / p.pool_h, Wp = p.w_out / p.pool_w;
+                __half* orow = p.out_h + (static_cast<size_t>(sc.img) * Hp * Wp + static_cast<size_t>(hp) * Wp + wp) *
+                                             p.out_cstride;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n0 = nt * BN + c0;
+                    if (n0 >= p.cout) break;  // warp-uniform
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(t_addr + c0, r);
+                    ptx::tmem_ld_wait();
+                    uint32_t ph[16], pl[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float v[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            float x = __uint_as_float(r[j + e]) + (p.bias ? __ldg(p.bias + n0 + j + e) : 0.f);
+                            x = apply_act(x, p.act);
+                            if (p.pool_w == 2) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                            if (p.pool_h == 2) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, segw));
+                            if (p.post_scale)
+                                x = x * __ldg(p.post_scale + n0 + j + e) + __ldg(p.post_shift + n0 + j + e);
+                            v[e] = x;
+                        }
+                        const __half2 h2 = __floats2half2_rn(v[0], v[1]);
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn(v[0] - hf.x, v[1] - hf.y);
+                        ph[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                        pl[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    if (writer) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                        if (p.out_lo_off >= 0) {
+                            uint4* dl = reinterpret_cast<uint4*>(orow + p.out_lo_off + n0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                        }
+                    }
+                }
+            } else if (p.epi == EPI_CTC) {
+                // one frame per thread: running first-max argmax (torch.argmax: NaN counts as maximal),
+                // online logsumexp
+                const size_t pix = (static_cast<size_t>(sc.img) * p.h_out + ho) * p.w_out + wo;
+                float best_v = -INFINITY, run_m = -INFINITY, run_s = 0.f;
+                int best_i = 0;
+                bool best_nan = false;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (c0 >= p.cout) break;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(t_addr + c0, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = c0 + j;
+                        if (n < p.cout) {
+                            const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                            r[j] = __float_as_uint(v);
+                            if (!best_nan) {
+                                if (v != v) {
+                                    best_nan = true;
+                                    best_i = n;
+                                    best_v = v;
+                                } else if (n == 0 || v > best_v) {
+                                    best_v = v;
+                                    best_i = n;
+                                }
+                            }
+                            const float m2 = fmaxf(run_m, v);
+                            run_s = run_s * __expf(run_m - m2) + __expf(v - m2);
+                            run_m = m2;
+                        }
+                    }
+                    if (valid && p.out_f32) {
+                        float* dst = p.out_f32 + pix * p.cout + c0;
+                        if ((p.cout & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (c0 + j < p.cout)
+                                    *reinterpret_cast<float4*>(dst + j) =
+                                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < p.cout) dst[j] = __uint_as_float(r[j]);
+                        }
+                    }
+                }
+                if (valid) {
+                    p.best[pix] = best_i;
+                    if (p.fmax) p.fmax[pix] = best_v;
+                    if (p.flse) p.flse[pix] = run_m + __logf(run_s);
+                }
+                if (p.fprob) {
+                    // second sweep over the accumulator: softmax mass of the classes the reference keeps when it
+                    // sparsifies (p >= 1e-4, line_ocr_engine.py:168-171); dropped ones re-enter as logit -80
+                    // (core/layout.py:65-68) before the confidence log-softmax (page_parser.py:486-490)
+                    float kept = 0.f;
+                    int dropped = 0;
+                    const float thr = 1e-4f * run_s;
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        if (c0 >= p.cout) break;
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32b_x32(t_addr + c0, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = c0 + j;
+                            if (n < p.cout) {
+                                const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                                const float e = __expf(v - run_m);
+                                if (e < thr || v == 0.f) ++dropped;
+                                else kept += e;
+                            }
+                        }
+                    }
+                    kept += dropped * __expf(-80.f - run_m);
+                    if (valid) p.fprob[pix] = __expf(best_v - run_m) / kept;
+                }
+            } else {  // EPI_F32 / EPI_RES_F32
+                const size_t pix = (static_cast<size_t>(sc.img) * p.h_out + ho) * p.w_out + wo;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n0 = nt * BN + c0;
+                    if (n0 >= p.cout) break;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(t_addr + c0, r);
+                    ptx::tmem_ld_wait();
+                    if (valid) {
+                        float* dst = p.out_f32 + pix * p.cout + n0;
+                        const float* res = (p.epi == EPI_RES_F32) ? p.residual + pix * p.cout + n0 : nullptr;
+                        if ((p.cout & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (n0 + j < p.cout) {
+                                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                                    if (p.bias) {
+                                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                    }
+                                    v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+                                    v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+                                    if (res) {
+                                        const float4 e = __ldg(reinterpret_cast<const float4*>(res + j));
+                                        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+                                    }
+                                    *reinterpret_cast<float4*>(dst + j) = v;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (n0 + j < p.cout) {
+                                    float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+                                    v = apply_act(v, p.act);
+                                    if (res) v += __ldg(res + j);
+                                    dst[j] = v;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+            acc_phase[acc] ^= 1;
+            acc ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BN>
+cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                      cudaStream_t stream) {
+    using C = Cfg<BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int total_tiles = p.m_tiles * p.tiles_n;
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    igemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int num_sms,
+                            cudaStream_t stream) {
+    switch (bn) {
+        case 64: return launch_bn<64>(p, tmA, tmB, num_sms, stream);
+        case 128: return launch_bn<128>(p, tmA, tmB, num_sms, stream);
+        case 256: return launch_bn<256>(p, tmA, tmB, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}

@@ -1,0 +1,473 @@
+// Non-GEMM kernels of the line-recognition path (sm_100a) + CUDA-core cross-check kernels.
+#include "kernels.cuh"
+#include "igemm.cuh"
+
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ first conv
+// One CTA = 128 consecutive output pixels of one image row.  The 3 x 130 x 3 input patch is staged in shared
+// memory as fp32 (x / 255, zero outside the image), each thread computes one pixel x 64 channels in fp32 and the
+// fp16 (hi | lo) pixel records are written back through shared memory so global stores are fully coalesced.
+constexpr int CF_PX = 128;
+
+__global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
+                                                          const float* __restrict__ w_t, const float* __restrict__ bias,
+                                                          int cout, int act, int planes, __half* __restrict__ out) {
+    __shared__ float s_in[3][CF_PX + 2][3];
+    __shared__ float s_w[27 * 64];
+    __shared__ float s_b[64];
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // [CF_PX][planes*cout] fp16 staging
+    __half* s_out = reinterpret_cast<__half*>(s_dyn);
+
+    const int tiles_w = (w + CF_PX - 1) / CF_PX;
+    const int tw = blockIdx.x % tiles_w;
+    const int row = (blockIdx.x / tiles_w) % h;
+    const int img = blockIdx.x / (tiles_w * h);
+    const int w0 = tw * CF_PX;
+
+    for (int i = threadIdx.x; i < 27 * cout; i += CF_PX) s_w[i] = w_t[i];
+    for (int i = threadIdx.x; i < cout; i += CF_PX) s_b[i] = bias ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 3 * (CF_PX + 2) * 3; i += CF_PX) {
+        const int c = i % 3;
+        const int x = (i / 3) % (CF_PX + 2);
+        const int r = i / (3 * (CF_PX + 2));
+        const int yy = row + r - 1, xx = w0 + x - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+            v = static_cast<float>(in[((static_cast<size_t>(img) * h + yy) * w + xx) * 3 + c]) / 255.0f;
+        s_in[r][x][c] = v;
+    }
+    __syncthreads();
+
+    float acc[64];
+#pragma unroll
+    for (int o = 0; o < 64; ++o) acc[o] = 0.f;
+    // PyTorch weight [cout][c][r][s]; w_t index ((r*3+s)*3+c)*cout + o
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float x = s_in[r][threadIdx.x + s][c];
+                const float* wr = &s_w[((r * 3 + s) * 3 + c) * cout];
+#pragma unroll
+                for (int o = 0; o < 64; ++o)
+                    if (o < cout) acc[o] = fmaf(x, wr[o], acc[o]);
+            }
+    const int rec = planes * cout;
+    __half* my = s_out + threadIdx.x * rec;
+#pragma unroll
+    for (int o = 0; o < 64; ++o) {
+        if (o < cout) {
+            const float v = act_fn(acc[o] + s_b[o], act);
+            const __half hi = __float2half_rn(v);
+            my[o] = hi;
+            if (planes == 2) my[cout + o] = __float2half_rn(v - __half2float(hi));
+        }
+    }
+    __syncthreads();
+    const int npx = min(CF_PX, w - w0);
+    const size_t base = ((static_cast<size_t>(img) * h + row) * w + w0) * rec;
+    const int total16 = npx * rec / 8;  // uint4 = 8 halves; rec is a multiple of 8
+    const uint4* src = reinterpret_cast<const uint4*>(s_out);
+    uint4* dst = reinterpret_cast<uint4*>(out + base);
+    for (int i = threadIdx.x; i < total16; i += CF_PX) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------ frame stats
+__device__ __forceinline__ void stat_update(float v, int idx, float& bv, int& bi, bool& bnan) {
+    if (bnan) return;
+    if (v != v) {
+        bnan = true;
+        bi = idx;
+        bv = v;
+    } else if (idx == 0 || v > bv) {
+        bv = v;
+        bi = idx;
+    }
+}
+
+// one thread per frame; works for both layouts through (stride_c, stride_t)
+__global__ void frame_stats_kernel(const float* __restrict__ s, int n, int t, int c, long stride_n, long stride_t,
+                                   long stride_c, int32_t* best, float* fmax, float* flse, float* fprob) {
+    const long f = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    if (f >= static_cast<long>(n) * t) return;
+    const int line = static_cast<int>(f / t), fr = static_cast<int>(f % t);
+    const float* p = s + line * stride_n + fr * stride_t;
+    float bv = -INFINITY, m = -INFINITY, sum = 0.f;
+    int bi = 0;
+    bool bnan = false;
+    for (int j = 0; j < c; ++j) {
+        const float v = p[j * stride_c];
+        stat_update(v, j, bv, bi, bnan);
+        const float m2 = fmaxf(m, v);
+        sum = sum * __expf(m - m2) + __expf(v - m2);
+        m = m2;
+    }
+    best[f] = bi;
+    if (fmax) fmax[f] = bv;
+    if (flse) flse[f] = m + __logf(sum);
+    if (fprob) {
+        // best-class probability under the reference's sparsify -> dense(-80) -> log-softmax chain
+        // (line_ocr_engine.py:168-171, core/layout.py:65-68, page_parser.py:486-490)
+        float kept = 0.f;
+        int dropped = 0;
+        const float thr = 1e-4f * sum;
+        for (int j = 0; j < c; ++j) {
+            const float v = p[j * stride_c];
+            const float e = __expf(v - m);
+            if (e < thr || v == 0.f) ++dropped;
+            else kept += e;
+        }
+        kept += dropped * __expf(-80.f - m);
+        fprob[f] = __expf(bv - m) / kept;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CTC collapse
+// one warp per line
+__global__ void ctc_collapse_kernel(const int32_t* __restrict__ best, const float* __restrict__ fprob, int n, int t,
+                                    int blank, int32_t* labels, int32_t* lengths, float* confidence) {
+    const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (line >= n) return;
+    const int32_t* b = best + static_cast<size_t>(line) * t;
+    int32_t* out = labels + static_cast<size_t>(line) * t;
+    int count = 0;
+    for (int base = 0; base < t; base += 32) {
+        const int i = base + lane;
+        int cur = blank, prev = blank;
+        if (i < t) {
+            cur = b[i];
+            prev = (i == 0) ? blank : b[i - 1];
+        }
+        const bool keep = (i < t) && cur != prev && cur != blank;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[count + __popc(mask & ((1u << lane) - 1))] = cur;
+        count += __popc(mask);
+    }
+    for (int i = count + lane; i < t; i += 32) out[i] = -1;
+    if (lane == 0) {
+        lengths[line] = count;
+        if (confidence) {
+            const float* pr = fprob + static_cast<size_t>(line) * t;
+            float worst = 1.f, run_p = 1.f;
+            int run_id = -1;
+            for (int i = 0; i < t; ++i) {
+                const int id = b[i];
+                const float p = pr[i];
+                if (id != run_id) {
+                    worst = fminf(worst, run_p);
+                    run_p = p;
+                    run_id = id;
+                } else {
+                    run_p = fmaxf(run_p, p);
+                }
+            }
+            confidence[line] = fminf(worst, run_p);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LSTM (ref)
+// grid (ceil(n/4), 2 directions), 4H/4 = H threads: thread j owns hidden unit j of 4 lines.
+constexpr int LR_LINES = 4;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void lstm_ref_kernel(const float* __restrict__ pre, const float* __restrict__ w_hh_t, int n, int T, int H,
+                                int planes, int round_fp16, __half* __restrict__ out) {
+    extern __shared__ float s_h[];  // [LR_LINES][H]
+    const int dir = blockIdx.y;
+    const int line0 = blockIdx.x * LR_LINES;
+    const int j = threadIdx.x;
+    const float* wt = w_hh_t + static_cast<size_t>(dir) * H * 4 * H;
+    float c[LR_LINES];
+    for (int l = 0; l < LR_LINES; ++l) {
+        c[l] = 0.f;
+        s_h[l * H + j] = 0.f;
+    }
+    __syncthreads();
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? (T - 1 - step) : step;
+        float a[4][LR_LINES];
+        for (int g = 0; g < 4; ++g)
+            for (int l = 0; l < LR_LINES; ++l) a[g][l] = 0.f;
+        for (int k = 0; k < H; ++k) {
+            float hk[LR_LINES];
+            for (int l = 0; l < LR_LINES; ++l) hk[l] = s_h[l * H + k];
+            for (int g = 0; g < 4; ++g) {
+                const float wv = wt[static_cast<size_t>(k) * 4 * H + g * H + j];
+                for (int l = 0; l < LR_LINES; ++l) a[g][l] = fmaf(wv, hk[l], a[g][l]);
+            }
+        }
+        __syncthreads();
+        for (int l = 0; l < LR_LINES; ++l) {
+            const int line = line0 + l;
+            if (line >= n) continue;
+            const size_t row = static_cast<size_t>(line) * T + t;
+            const float* pr = pre + row * (8 * H) + dir * 4 * H;
+            const float gi = sigmoidf_(a[0][l] + pr[j]);
+            const float gf = sigmoidf_(a[1][l] + pr[H + j]);
+            const float gg = tanhf(a[2][l] + pr[2 * H + j]);
+            const float go = sigmoidf_(a[3][l] + pr[3 * H + j]);
+            c[l] = gf * c[l] + gi * gg;
+            const float hv = go * tanhf(c[l]);
+            const __half hi = __float2half_rn(hv);
+            __half* o = out + row * (planes * 2 * H) + dir * H + j;
+            o[0] = hi;
+            if (planes == 2) o[2 * H] = __float2half_rn(hv - __half2float(hi));
+            s_h[l * H + j] = round_fp16 ? __half2float(hi) : hv;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ igemm (ref)
+// one thread per (pooled output pixel, cout)
+__global__ void igemm_ref_kernel(const IgemmParams p, const __half* __restrict__ in, const __half* __restrict__ wp) {
+    const int Hp = p.h_out / p.pool_h, Wp = p.w_out / p.pool_w;
+    const long total = static_cast<long>(p.n_img) * Hp * Wp * p.cout;
+    const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const int co = static_cast<int>(idx % p.cout);
+    long pix = idx / p.cout;
+    const int wq = static_cast<int>(pix % Wp);
+    const int hq = static_cast<int>((pix / Wp) % Hp);
+    const int img = static_cast<int>(pix / (static_cast<long>(Wp) * Hp));
+    const int taps = p.kh * p.kw;
+    const int planes = p.npass == 3 ? 2 : 1;
+    const int cstride = planes * p.cin;
+    float result = -INFINITY;
+    for (int ph = 0; ph < p.pool_h; ++ph)
+        for (int pw = 0; pw < p.pool_w; ++pw) {
+            const int ho = hq * p.pool_h + ph, wo = wq * p.pool_w + pw;
+            float acc = 0.f;
+            for (int pass = 0; pass < p.npass; ++pass) {
+                const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int r = tap / p.kw, s = tap % p.kw;
+                    const int hi_ = ho + r - p.pad_h, wi = wo + s - p.pad_w;
+                    if (hi_ < 0 || hi_ >= p.h_in || wi < 0 || wi >= p.w_in) continue;
+                    const __half* a = in + ((static_cast<size_t>(img) * p.h_in + hi_) * p.w_in + wi) * cstride +
+                                      pa * p.cin;
+                    const __half* b = wp + (static_cast<size_t>(pb * taps + tap) * p.cout_pad + co) * p.cin;
+                    for (int k = 0; k < p.cin; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
+                }
+            }
+            float v = acc + (p.bias ? p.bias[co] : 0.f);
+            if (p.epi != EPI_RES_F32) v = act_fn(v, p.act);
+            result = fmaxf(result, v);
+        }
+    const size_t opix = (static_cast<size_t>(img) * Hp + hq) * Wp + wq;
+    if (p.epi == EPI_ACT_F16) {
+        if (p.post_scale) result = result * p.post_scale[co] + p.post_shift[co];
+        const __half hi = __float2half_rn(result);
+        p.out_h[opix * p.out_cstride + co] = hi;
+        if (p.out_lo_off >= 0)
+            p.out_h[opix * p.out_cstride + p.out_lo_off + co] = __float2half_rn(result - __half2float(hi));
+    } else {
+        if (p.epi == EPI_RES_F32) result += p.residual[opix * p.cout + co];
+        p.out_f32[opix * p.cout + co] = result;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+__global__ void upsample_nchw_kernel(const float* __restrict__ in, int n, int h, int w, int c, int f, float* out) {
+    const long total = static_cast<long>(n) * c * h * f * w * f;
+    const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const int W = w * f, Hh = h * f;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % Hh);
+    const int ch = static_cast<int>((idx / (static_cast<long>(W) * Hh)) % c);
+    const int img = static_cast<int>(idx / (static_cast<long>(W) * Hh * c));
+    out[idx] = in[((static_cast<size_t>(img) * h + y / f) * w + x / f) * c + ch];
+}
+
+// one warp per row
+__global__ void layernorm_kernel(const float* __restrict__ in, int rows, int d, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, int pe_T, float* out_f32, __half* out_h,
+                                 int planes) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = in + static_cast<size_t>(row) * d;
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) s += x[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / d;
+    float v = 0.f;
+    for (int i = lane; i < d; i += 32) {
+        const float dlt = x[i] - mean;
+        v += dlt * dlt;
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / d + eps);
+    const int t = pe_T > 0 ? row % pe_T : 0;
+    for (int i = lane; i < d; i += 32) {
+        float y = (x[i] - mean) * rstd * gamma[i] + beta[i];
+        if (pe_T > 0) {
+            // pe[t, 2m] = sin(t * exp(2m * -ln(1e4)/d)), pe[t, 2m+1] = cos(same)   (transformer.py:323-327)
+            const int m2 = i & ~1;
+            const float div = expf(static_cast<float>(m2) * (-logf(10000.0f) / d));
+            const float ang = static_cast<float>(t) * div;
+            y += (i & 1) ? cosf(ang) : sinf(ang);
+        }
+        if (out_f32) out_f32[static_cast<size_t>(row) * d + i] = y;
+        if (out_h) {
+            const __half hi = __float2half_rn(y);
+            out_h[static_cast<size_t>(row) * planes * d + i] = hi;
+            if (planes == 2) out_h[static_cast<size_t>(row) * planes * d + d + i] = __float2half_rn(y - __half2float(hi));
+        }
+    }
+}
+
+__global__ void h2f_kernel(const __half* __restrict__ in, long rows, int d, int planes, float* out) {
+    const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    if (idx >= rows * d) return;
+    const long r = idx / d;
+    const int i = static_cast<int>(idx % d);
+    float v = __half2float(in[r * planes * d + i]);
+    if (planes == 2) v += __half2float(in[r * planes * d + d + i]);
+    out[idx] = v;
+}
+
+// One CTA per (line, head); K and V of the head staged in shared memory as fp32, one warp per query row.
+__global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, int D, int heads, __half* out, int planes) {
+    extern __shared__ float s_att[];
+    const int dh = D / heads;
+    float* sK = s_att;                 // [T][dh+1]
+    float* sV = sK + T * (dh + 1);     // [T][dh+1]
+    float* sP = sV + T * (dh + 1);     // [warps][T]
+    const int line = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + static_cast<size_t>(line) * T * 3 * D;
+    for (int i = threadIdx.x; i < T * dh; i += blockDim.x) {
+        const int t = i / dh, e = i % dh;
+        sK[t * (dh + 1) + e] = base[static_cast<size_t>(t) * 3 * D + D + head * dh + e];
+        sV[t * (dh + 1) + e] = base[static_cast<size_t>(t) * 3 * D + 2 * D + head * dh + e];
+    }
+    __syncthreads();
+    const float scale = rsqrtf(static_cast<float>(dh));
+    float* p = sP + warp * T;
+    for (int tq = warp; tq < T; tq += warps) {
+        const float* q = base + static_cast<size_t>(tq) * 3 * D + head * dh;
+        float m = -INFINITY;
+        for (int tk = lane; tk < T; tk += 32) {
+            float s = 0.f;
+            for (int e = 0; e < dh; ++e) s = fmaf(q[e] * scale, sK[tk * (dh + 1) + e], s);
+            p[tk] = s;
+            m = fmaxf(m, s);
+        }
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+        for (int tk = lane; tk < T; tk += 32) {
+            const float e = expf(p[tk] - m);
+            p[tk] = e;
+            sum += e;
+        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncwarp();
+        const float inv = 1.f / sum;
+        for (int e = lane; e < dh; e += 32) {
+            float acc = 0.f;
+            for (int tk = 0; tk < T; ++tk) acc = fmaf(p[tk], sV[tk * (dh + 1) + e], acc);
+            acc *= inv;
+            const size_t row = static_cast<size_t>(line) * T + tq;
+            const __half hi = __float2half_rn(acc);
+            out[row * planes * D + head * dh + e] = hi;
+            if (planes == 2) out[row * planes * D + D + head * dh + e] = __float2half_rn(acc - __half2float(hi));
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
+                              int act, int planes, __half* out, cudaStream_t stream) {
+    if (cout > 64 || (cout * planes) % 8) return cudaErrorInvalidValue;
+    const int tiles_w = (w + CF_PX - 1) / CF_PX;
+    const size_t dyn = static_cast<size_t>(CF_PX) * planes * cout * sizeof(__half);
+    conv_first_kernel<<<n * h * tiles_w, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, cout, act, planes, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frame_stats(const float* scores, int n, int t, int c, int layout, int32_t* best, float* fmax,
+                               float* flse, float* fprob, cudaStream_t stream) {
+    const long frames = static_cast<long>(n) * t;
+    if (frames == 0) return cudaSuccess;
+    const long sn = static_cast<long>(t) * c;
+    const long st = layout == 0 ? c : 1;
+    const long sc = layout == 0 ? 1 : t;
+    frame_stats_kernel<<<static_cast<unsigned>((frames + 127) / 128), 128, 0, stream>>>(scores, n, t, c, sn, st, sc,
+                                                                                         best, fmax, flse, fprob);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ctc_collapse(const int32_t* best, const float* fprob, int n, int t, int blank, int32_t* labels,
+                                int32_t* lengths, float* confidence, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    ctc_collapse_kernel<<<(n * 32 + 127) / 128, 128, 0, stream>>>(best, fprob, n, t, blank, labels, lengths,
+                                                                  fprob ? confidence : nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lstm_ref(const float* pre, const float* w_hh_t, int n, int T, int H, int planes, int round_fp16,
+                            __half* out, cudaStream_t stream) {
+    dim3 grid((n + LR_LINES - 1) / LR_LINES, 2);
+    lstm_ref_kernel<<<grid, H, LR_LINES * H * sizeof(float), stream>>>(pre, w_hh_t, n, T, H, planes, round_fp16, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_igemm_ref(const IgemmParams& p, const __half* in, const __half* w_packed, cudaStream_t stream) {
+    const long total = static_cast<long>(p.n_img) * (p.h_out / p.pool_h) * (p.w_out / p.pool_w) * p.cout;
+    if (total == 0) return cudaSuccess;
+    igemm_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p, in, w_packed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upsample_nchw(const float* in, int n, int h, int w, int c, int f, float* out, cudaStream_t stream) {
+    const long total = static_cast<long>(n) * c * h * f * w * f;
+    upsample_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, n, h, w, c, f, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* in, int rows, int d, const float* gamma, const float* beta, float eps,
+                             int pe_T, float* out_f32, __half* out_h, int planes, cudaStream_t stream) {
+    layernorm_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(in, rows, d, gamma, beta, eps, pe_T, out_f32, out_h,
+                                                                  planes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_h2f(const __half* in, int rows, int d, int planes, float* out, cudaStream_t stream) {
+    const long total = static_cast<long>(rows) * d;
+    h2f_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, rows, d, planes, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int planes,
+                             cudaStream_t stream) {
+    const int dh = D / heads;
+    const int warps = 8;
+    const size_t smem = (2 * static_cast<size_t>(T) * (dh + 1) + static_cast<size_t>(warps) * T) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    attention_kernel<<<n * heads, warps * 32, smem, stream>>>(qkv, n, T, D, heads, out, planes);
+    return cudaGetLastError();
+}

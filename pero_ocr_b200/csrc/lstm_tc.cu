@@ -1,0 +1,283 @@
+// Persistent bidirectional-LSTM recurrence on tcgen05 (sm_100a).
+//
+// Replaces the cuDNN RNN call inside the reference's TorchScript recogniser blob (SURVEY.md 2b K3;
+// pero_ocr/ocr_engine/pytorch_ocr_engine.py:64-69).  The input projection x W_ih^T + b is one big GEMM done
+// beforehand (igemm_tc.cu, fp32 "pre-gates"); this kernel runs the T strictly sequential steps.
+//
+// One thread-block cluster of 8 CTAs owns 32 lines of one direction for all T steps:
+//   * CTA j keeps the W_hh rows of hidden units [32j, 32j+32) (4 gates x 32 units = 128 rows x K=256, fp16 hi
+//     (+lo)) resident in shared memory for the whole kernel -- loaded once by TMA, 128B-swizzled, operand A;
+//   * h_{t-1} of the 32 lines (N=32 x K=256, fp16 hi (+lo)) is operand B in the no-swizzle core-matrix layout,
+//     double-buffered; one elected thread issues the 16 (x3) tcgen05.mma (M=128,N=32,K=16) of the step into TMEM;
+//   * epilogue: tcgen05.ld -> shared-memory transpose so that one thread holds i,f,g,o of (line, 8 units),
+//     gates + cell update in fp32 (cell state lives in registers for all T steps), h_t is written to HBM (fp16
+//     hi|lo, next layer's GEMM operand) and into the CTA's own slice of the next B buffer, which is then pushed to
+//     the 7 peer CTAs with cp.async.bulk (shared::cta -> shared::cluster) completing on the peers' mbarriers:
+//     no cluster-wide barrier inside the time loop.
+#include "lstm_tc.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kH = 256;          // hidden units per direction
+constexpr int kCl = 8;           // CTAs per cluster
+constexpr int kUnits = kH / kCl; // 32 hidden units per CTA
+constexpr int kLines = 32;       // lines per cluster (MMA N)
+constexpr int kThreads = 128;
+constexpr int kWPlane = 128 * kH * 2;        // 64 KB: 4 K-chunks of [128 rows][64 fp16]
+constexpr int kHPlane = kLines * kH * 2;     // 16 KB: [k/8][n/8][n%8][k%8]
+constexpr int kSliceBytes = kUnits * kLines * 2;  // 2 KB: this CTA's k range inside a B plane
+constexpr int kGStride = 33;
+
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            dst_cluster_addr),
+        "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B; LBO = K-direction core-matrix stride, SBO = 8-row-group stride
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) {
+    // tanh(x) = 1 - 2 / (exp(2x) + 1): full fp32 accuracy up to the __expf error (2 ulp), no cancellation blow-up
+    // for |x| >~ 1e-2; below that the relative error of the result is still < 1e-5.
+    const float e = __expf(2.f * x);
+    return 1.f - 2.f / (e + 1.f);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ pre, __half* __restrict__ out,
+               int n_lines, int T, int planes, int line_groups) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;                                  // planes * 64 KB
+    uint8_t* sH = sW + planes * kWPlane;                 // 2 buffers * planes * 16 KB
+    float* sG = reinterpret_cast<float*>(sH + 2 * planes * kHPlane);   // [128][33]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 128 * kGStride);
+    uint64_t* wfull = bars;
+    uint64_t* hfull = bars + 1;   // [2]
+    uint64_t* mma_done = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster = cluster_id_x();
+    const int dir = cluster / line_groups;
+    const int line0 = (cluster - dir * line_groups) * kLines;
+    const int npass = planes == 2 ? 3 : 1;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tmW);
+        ptx::mbar_init(wfull, 1);
+        ptx::mbar_init(&hfull[0], 1);
+        ptx::mbar_init(&hfull[1], 1);
+        ptx::mbar_init(mma_done, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0) ptx::tmem_alloc<32>(tmem_slot);
+    // h_{-1} = 0: zero both B buffers
+    for (int i = tid; i < 2 * planes * kHPlane / 16; i += kThreads)
+        reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    cluster_sync_all();  // peers' barriers are initialised before anybody signals them
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        ptx::mbar_expect_tx(wfull, planes * kWPlane);
+        for (int pl = 0; pl < planes; ++pl)
+            for (int kc = 0; kc < 4; ++kc)
+                ptx::tma_load_2d(sW + pl * kWPlane + kc * 16384, &tmW, wfull, kc * 64,
+                                 ((dir * planes + pl) * kCl + rank) * 128);
+    }
+
+    // epilogue-2 role of this thread: line nl, units [8*ug, 8*ug+8) of this CTA's 32
+    const int nl = tid >> 2, ug = tid & 3;
+    const int line = line0 + nl;
+    const bool line_ok = line < n_lines;
+    const int unit0 = rank * kUnits + ug * 8;  // hidden-unit index within the direction
+    float c_state[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) c_state[e] = 0.f;
+    const uint32_t slice_off = (rank * 4 + ug) * 512 + (nl >> 3) * 128 + (nl & 7) * 16;  // inside a B plane
+
+    ptx::mbar_wait(wfull, 0);
+    uint32_t hphase[2] = {0, 0};
+    uint32_t mphase = 0;
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? (T - 1 - s) : s;
+        const int b = s & 1, nb = b ^ 1;
+        // prefetch this step's pre-gates (i,f,g,o x 8 units) while the MMA runs
+        float pg[4][8];
+        const size_t row = static_cast<size_t>(line_ok ? line : 0) * T + t;
+        {
+            const float* pr = pre + row * (8 * kH) + dir * 4 * kH + unit0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (line_ok) {
+                    v0 = __ldg(reinterpret_cast<const float4*>(pr + g * kH));
+                    v1 = __ldg(reinterpret_cast<const float4*>(pr + g * kH + 4));
+                }
+                pg[g][0] = v0.x; pg[g][1] = v0.y; pg[g][2] = v0.z; pg[g][3] = v0.w;
+                pg[g][4] = v1.x; pg[g][5] = v1.y; pg[g][6] = v1.z; pg[g][7] = v1.w;
+            }
+        }
+        if (s > 0) {
+            if (tid == 0) {
+                ptx::mbar_wait(&hfull[b], hphase[b]);
+                hphase[b] ^= 1;
+                ptx::tc_fence_after();
+                constexpr uint32_t idesc = ptx::idesc_f16_f32(128, kLines);
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int pw = (pass == 2) ? 1 : 0;  // W plane
+                    const int ph = (pass == 1) ? 1 : 0;  // h plane
+                    const uint32_t wa = ptx::smem_u32(sW + pw * kWPlane);
+                    const uint32_t ha = ptx::smem_u32(sH + (b * planes + ph) * kHPlane);
+#pragma unroll
+                    for (int k16 = 0; k16 < 16; ++k16) {
+                        const uint64_t a_desc = ptx::smem_desc_sw128(wa + (k16 >> 2) * 16384) + 2 * (k16 & 3);
+                        const uint64_t b_desc = smem_desc_nosw(ha + k16 * 2 * 512, 512, 128);
+                        ptx::mma_f16_ss(tmem_base, a_desc, b_desc, idesc, (pass | k16) != 0);
+                    }
+                }
+                ptx::mma_commit(mma_done);
+            }
+            ptx::mbar_wait(mma_done, mphase);
+            mphase ^= 1;
+            ptx::tc_fence_after();
+            // phase 1: TMEM lane = gate row (warp = gate type, lane = unit), column = line
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), r);
+            ptx::tmem_ld_wait();
+            float* g_row = sG + (warp * 32 + lane) * kGStride;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g_row[j] = __uint_as_float(r[j]);
+            ptx::tc_fence_before();
+        }
+        __syncthreads();
+        // phase 2: gates for (line nl, units 8ug..8ug+7)
+        float hv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int u = ug * 8 + e;
+            float gi = pg[0][e], gf = pg[1][e], gg = pg[2][e], go = pg[3][e];
+            if (s > 0) {
+                gi += sG[(0 * 32 + u) * kGStride + nl];
+                gf += sG[(1 * 32 + u) * kGStride + nl];
+                gg += sG[(2 * 32 + u) * kGStride + nl];
+                go += sG[(3 * 32 + u) * kGStride + nl];
+            }
+            const float ig = sigm(gi), fg = sigm(gf), cg = tanh_(gg), og = sigm(go);
+            c_state[e] = fg * c_state[e] + ig * cg;
+            hv[e] = og * tanh_(c_state[e]);
+        }
+        uint32_t hi_w[4], lo_w[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const __half2 h2 = __floats2half2_rn(hv[e], hv[e + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(hv[e] - hf.x, hv[e + 1] - hf.y);
+            hi_w[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo_w[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        if (line_ok) {
+            __half* o = out + row * (planes * 2 * kH) + dir * kH + unit0;
+            *reinterpret_cast<uint4*>(o) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+            if (planes == 2) *reinterpret_cast<uint4*>(o + 2 * kH) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+        }
+        if (s + 1 < T) {
+            uint8_t* hb = sH + nb * planes * kHPlane;
+            *reinterpret_cast<uint4*>(hb + slice_off) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+            if (planes == 2)
+                *reinterpret_cast<uint4*>(hb + kHPlane + slice_off) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                ptx::mbar_expect_tx(&hfull[nb], (kCl - 1) * planes * kSliceBytes);
+                for (int pl = 0; pl < planes; ++pl) {
+                    const uint32_t src = ptx::smem_u32(hb + pl * kHPlane + rank * kSliceBytes);
+                    const uint32_t bar = ptx::smem_u32(&hfull[nb]);
+                    for (uint32_t peer = 0; peer < kCl; ++peer) {
+                        if (peer == rank) continue;
+                        bulk_copy_to_peer(mapa(src, peer), src, kSliceBytes, mapa(bar, peer));
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    cluster_sync_all();  // nobody leaves while a peer may still push into its shared memory
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<32>(tmem_base);
+    }
+}
+
+}  // namespace
+
+size_t lstm_tc_smem_bytes(int planes) {
+    return static_cast<size_t>(planes) * kWPlane + 2 * static_cast<size_t>(planes) * kHPlane +
+           128 * kGStride * sizeof(float) + 64 + 1024;
+}
+
+cudaError_t launch_lstm_tc(const CUtensorMap& tmW, const float* pre, __half* out, int n_lines, int T, int H, int planes,
+                           cudaStream_t stream) {
+    if (H != kH) return cudaErrorInvalidValue;
+    const size_t smem = lstm_tc_smem_bytes(planes);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int line_groups = (n_lines + kLines - 1) / kLines;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * line_groups * kCl);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, lstm_tc_kernel, tmW, pre, out, n_lines, T, planes, line_groups);
+}

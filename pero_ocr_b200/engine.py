@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's line-OCR engine surface, driving libb200_lineocr.so.
+
+Replaces (same names, argument meaning and return types):
+  * ``BaseEngineLineOCR.__init__`` / ``process_lines``   pero_ocr/ocr_engine/line_ocr_engine.py:17-55, 57-177
+  * ``PytorchEngineLineOCR.__init__`` / ``run_ocr``      pero_ocr/ocr_engine/pytorch_ocr_engine.py:37-74
+  * ``greedy_decode_ctc``'s id -> string join            pero_ocr/ocr_engine/pytorch_ocr_engine.py:28-34
+  * ``PageParser.compute_line_confidence``               pero_ocr/document_ocr/page_parser.py:486-496 (fused, optional)
+
+PyTorch appears only as the owner of device/pinned buffers and of the CUDA stream.
+"""
+import ctypes as C
+import json
+import math
+from os.path import dirname, isabs, join, realpath
+
+import numpy as np
+
+from . import _lib, netdesc
+
+
+class LineRecognizer:
+    """Thin handle over one native engine (one per device, not thread-safe -- like the reference engines)."""
+
+    def __init__(self, layers, precision='fp16x3', line_height=40, device=0):
+        import torch
+        self._lib = _lib.load_library()
+        if not torch.cuda.is_available():
+            raise _lib.B200Error('no CUDA device: the B200 line recogniser has no CPU fallback')
+        self.torch = torch
+        self.device = torch.device('cuda', device)
+        self.precision = precision
+        self.line_height = line_height
+        desc, keep = netdesc.to_ctypes(layers, precision, line_height, device)
+        handle = C.c_void_p()
+        torch.cuda.set_device(self.device)
+        _lib.check(self._lib.b200ocr_create(C.byref(desc), C.byref(handle)))
+        del keep
+        self._h = handle
+        self.num_classes = [l for l in layers if l['kind'] == _lib.CTC_HEAD][-1]['cout'] if any(
+            l['kind'] == _lib.CTC_HEAD for l in layers) else None
+        self._reserved = (0, 0)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.b200ocr_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reserve(self, max_lines, max_width):
+        if max_lines > self._reserved[0] or max_width > self._reserved[1]:
+            n, w = max(max_lines, self._reserved[0]), max(max_width, self._reserved[1])
+            _lib.check(self._lib.b200ocr_reserve(self._h, n, w), self._h)
+            self._reserved = (n, w)
+
+    def use_reference_kernels(self, on):
+        _lib.check(self._lib.b200ocr_debug_use_reference_kernels(self._h, 1 if on else 0), self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.b200ocr_launch_count(self._h))
+
+    def flops(self, n, w):
+        g = C.c_double()
+        total = self._lib.b200ocr_forward_flops(self._h, n, w, C.byref(g))
+        return float(total), float(g.value)
+
+    def forward(self, crops, want_logits=True, want_confidence=False, want_best_path=False, out=None):
+        """crops: CUDA uint8 tensor [N,H,W,3] (contiguous).  Returns dict of CUDA tensors; stream-ordered on torch's
+        current stream, no synchronisation."""
+        torch = self.torch
+        assert crops.is_cuda and crops.dtype == torch.uint8 and crops.is_contiguous() and crops.dim() == 4
+        n, h, w, ch = crops.shape
+        if ch != 3:
+            raise ValueError('line crops need three colour channels')
+        self.reserve(n, w)
+        T = w // 4
+        o = out if out is not None else {}
+        dev = crops.device
+        if 'labels' not in o or o['labels'].shape != (n, T):
+            o['labels'] = torch.empty((n, T), dtype=torch.int32, device=dev)
+            o['lengths'] = torch.empty((n,), dtype=torch.int32, device=dev)
+        if want_logits and ('logits' not in o or o['logits'].shape != (n, T, self.num_classes)):
+            o['logits'] = torch.empty((n, T, self.num_classes), dtype=torch.float32, device=dev)
+        if want_confidence and ('confidence' not in o or o['confidence'].shape != (n,)):
+            o['confidence'] = torch.empty((n,), dtype=torch.float32, device=dev)
+        if want_best_path and ('best_path' not in o or o['best_path'].shape != (n, T)):
+            o['best_path'] = torch.empty((n, T), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self._lib.b200ocr_forward(
+            self._h, crops.data_ptr(), n, h, w,
+            o['logits'].data_ptr() if want_logits else None,
+            o['labels'].data_ptr(), o['lengths'].data_ptr(),
+            o['confidence'].data_ptr() if want_confidence else None,
+            o['best_path'].data_ptr() if want_best_path else None,
+            C.c_void_p(stream)), self._h)
+        return o
+
+    def debug_forward_prefix(self, crops, n_layers):
+        n, h, w, _ = crops.shape
+        self.reserve(n, w)
+        cap = n * h * w * 64 * 2
+        buf = np.empty(cap, dtype=np.float32)
+        written = C.c_int64()
+        shape = (C.c_int32 * 4)()
+        stream = self.torch.cuda.current_stream(crops.device).cuda_stream
+        _lib.check(self._lib.b200ocr_debug_forward_prefix(
+            self._h, crops.data_ptr(), n, h, w, n_layers, buf.ctypes.data_as(C.c_void_p), cap, C.byref(written),
+            shape, C.c_void_p(stream)), self._h)
+        return buf[:written.value].reshape(tuple(shape)).copy()
+
+
+def softmax(x, axis):
+    """Numerically-stable softmax used for logit sparsification (role of pero_ocr/ocr_engine/softmax.py, theta=1)."""
+    e = np.exp(x - np.max(x, axis=axis, keepdims=True))
+    return e / np.sum(e, axis=axis, keepdims=True)
+
+
+class B200EngineLineOCR:
+    """Drop-in for ``PytorchEngineLineOCR(json_def, device, batch_size)``.
+
+    The engine JSON is the reference's (keys ``line_px_height, line_vertical_scale, checkpoint, characters,
+    net_name``; optional ``max_line_width``); ``checkpoint`` is the same TorchScript file the reference loads
+    (the ``.cpu`` suffix rule does not apply -- the weights are read once on the host and packed for the GPU).
+    Embedding-conditioned nets (``embed_id``) are not supported and raise at construction.
+    """
+
+    def __init__(self, json_def, device=None, batch_size=8, precision='fp16x3', module=None):
+        import torch
+        with open(json_def, 'r', encoding='utf8') as f:
+            self.config = json.load(f)
+        self.line_px_height = self.config['line_px_height']
+        self.line_vertical_scale = self.config['line_vertical_scale']
+        ck = self.config['checkpoint']
+        self.checkpoint = ck if isabs(ck) else realpath(join(dirname(json_def), ck))
+        self.characters = list(self.config['characters']) + [u'​']   # pytorch_ocr_engine.py:42
+        self.net_name = self.config['net_name']
+        self.embed_num = int(self.config['embed_num']) if 'embed_num' in self.config else None
+        self.embed_id = self.config.get('embed_id')
+        if self.embed_id is not None:
+            raise NotImplementedError('embedding-conditioned recognisers (embed_id) are outside the B200 path')
+        self.max_line_width = int(self.config.get('max_line_width', 1e10))
+        self.model_type = 'ctc'
+        self.device = device if device is not None else torch.device('cuda', 0)
+        if self.device.type != 'cuda':
+            raise _lib.B200Error('B200EngineLineOCR runs on a CUDA device only (no CPU fallback)')
+        self.batch_size = batch_size
+        self.line_padding_px = 32                                           # line_ocr_engine.py:54
+        self.max_input_horizontal_pixels = 480 * batch_size                 # line_ocr_engine.py:55
+        self.net_subsampling = 4                                            # pytorch_ocr_engine.py:41
+        if module is None:
+            module = torch.jit.load(self.checkpoint, map_location='cpu')
+        layers, n_classes = netdesc.describe_line_net(module)
+        if n_classes != len(self.characters) + 1:
+            raise ValueError(f'net emits {n_classes} classes, engine JSON implies {len(self.characters) + 1}')
+        self.model = LineRecognizer(layers, precision=precision, line_height=self.line_px_height,
+                                    device=self.device.index or 0)
+        self._pinned = None
+        self._dev_in = None
+        self._outs = {}
+        self.want_confidence = False
+        self.last_confidences = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---- device step --------------------------------------------------------------------------------------
+    def _stage(self, batch_data):
+        """Host u8 batch -> pinned staging buffer -> device (async on the current stream)."""
+        torch = self.model.torch
+        n_bytes = batch_data.size
+        if self._pinned is None or self._pinned.numel() < n_bytes:
+            self._pinned = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+            self._dev_in = torch.empty(n_bytes, dtype=torch.uint8, device=self.device)
+        pin = self._pinned[:n_bytes].view(batch_data.shape)
+        pin.numpy()[...] = batch_data
+        dev = self._dev_in[:n_bytes].view(batch_data.shape)
+        dev.copy_(pin, non_blocking=True)
+        self.h2d_bytes += n_bytes
+        return dev
+
+    def _decode_ids(self, labels, lengths):
+        chars = self.characters
+        return [''.join(chars[c] for c in row[:ln]) for row, ln in zip(labels, lengths)]
+
+    def run_ocr(self, batch_data, no_logits=False):
+        """np.uint8 [N,H,W,3] -> (list[str], np.float32 [N,T,C])   (pytorch_ocr_engine.py:59-74)."""
+        torch = self.model.torch
+        with torch.cuda.device(self.device):
+            dev = self._stage(np.ascontiguousarray(batch_data))
+            o = self.model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence,
+                                   out=self._outs)
+            self._outs = o
+            labels = o['labels'].cpu().numpy()
+            lengths = o['lengths'].cpu().numpy()
+            self.d2h_bytes += labels.nbytes + lengths.nbytes
+            logits = None
+            if not no_logits:
+                logits = o['logits'].cpu().numpy()
+                self.d2h_bytes += logits.nbytes
+            if self.want_confidence:
+                self.last_confidences = o['confidence'].cpu().numpy()
+        return self._decode_ids(labels, lengths), logits
+
+    # ---- batching ------------------------------------------------------------------------------------------
+    def process_lines(self, lines, sparse_logits=True, tight_crop_logits=False, no_logits=False):
+        """list of [H,w,3] uint8 crops -> (transcriptions, logits, logit_coords); semantics of
+        line_ocr_engine.py:57-177 for model_type 'ctc': widest-first batches under a pixel budget, 32 px zero
+        padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4."""
+        from scipy import sparse
+        count = len(lines)
+        transcriptions = [None] * count
+        logits_out = [None] * count
+        coords_out = [None] * count
+        confidences = [None] * count
+        pad, sub = self.line_padding_px, self.net_subsampling
+        pending = sorted(range(count), key=lambda i: -lines[i].shape[1])     # stable: ties keep input order
+        while pending:
+            widest = int(math.ceil(lines[pending[0]].shape[1] / 32.0) * 32)
+            take = max(1, self.max_input_horizontal_pixels // widest)
+            chunk, pending = pending[:take], pending[take:]
+            batch = np.zeros((len(chunk), self.line_px_height, widest + 2 * pad, 3), dtype=np.uint8)
+            for slot, idx in enumerate(chunk):
+                batch[slot, :, pad:pad + lines[idx].shape[1], :] = lines[idx]
+            if batch.shape[2] > self.max_input_horizontal_pixels:
+                print(f'WARNING: Line too long for OCR engine. Cropping from {batch.shape[2]} px down to '
+                      f'{self.max_input_horizontal_pixels}.')
+                batch = batch[:, :, :self.max_input_horizontal_pixels]
+            texts, dense = self.run_ocr(batch, no_logits=no_logits)
+            for slot, idx in enumerate(chunk):
+                transcriptions[idx] = texts[slot]
+                if self.want_confidence:
+                    confidences[idx] = float(self.last_confidences[slot])
+                if no_logits:
+                    continue
+                line_logits = dense[slot]
+                lo, hi = int(pad // sub), int((pad + lines[idx].shape[1]) // sub)
+                if tight_crop_logits:
+                    line_logits = line_logits[lo:hi]
+                    coords_out[idx] = [None, None]
+                else:
+                    coords_out[idx] = [lo, hi]
+                if sparse_logits:
+                    line_logits = line_logits.copy()
+                    line_logits[softmax(line_logits, axis=1) < 0.0001] = 0
+                    line_logits = sparse.csc_matrix(line_logits)
+                logits_out[idx] = line_logits
+        self.last_line_confidences = confidences if self.want_confidence else None
+        return transcriptions, logits_out, coords_out
