@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: text-lines/sec on synthetic 40x1280 crops (BASELINE.json config 2: batch 256, random-init
+CNN+BiLSTM recogniser), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16x3|fp16] [--net lstm]
+
+A step = one pass of the hot path (pad/255 -> conv stack -> BiLSTM x2 -> CTC head + greedy collapse) over one batch
+of 256 lines.  `value` is device-resident throughput (crops already in HBM; CUDA events, max over ranks);
+`e2e` runs the same lines through B200EngineLineOCR.process_lines (host uint8 crops -> padded pinned batch -> H2D ->
+forward -> D2H of label ids -> strings), double-buffered, and for N>1 ends with the NCCL gather of label ids.
+`--impl reference` times the reference's algorithm on the host cores (torch-CPU oracle port: the reference ships
+no recogniser weights or definition, so `oracle/nets.py` hosted by the reference's own engine logic is its CPU path).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 256
+WIDTH = 1280
+PADDED = WIDTH + 64
+METRIC = 'text-lines/sec (40x1280 crops)'
+UNIT = 'lines/s'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get('bf16_tflops_sustained', 1342.1), p.get('hbm_gbs', 6552.6), 'measured (MEASURED_PEAKS.json, bf16 sustained)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+                getattr(pynvml, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+                getattr(pynvml, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+                getattr(pynvml, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+                getattr(pynvml, 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown', 0x80): 'hw_power_brake',
+            }
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as exc:  # NVML missing: report that instead of failing the bench
+            self.reasons.add(f'nvml_unavailable:{type(exc).__name__}')
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def make_net(kind):
+    from pero_ocr_b200.synthetic import make_net as mk
+    return mk(kind, 120, seed=0, out_gain=6.0 if kind == 'lstm' else 2.5, **({'layers': 2} if kind == 'transformer' else {}))
+
+
+def cpu_reference_lines_per_s(kind, n_lines, threads=None):
+    """The reference algorithm on the host: torch-CPU recogniser + the reference's greedy CTC collapse."""
+    import torch
+    from oracle import cases
+    from oracle.forward_oracle import OracleEngine
+    if threads:
+        torch.set_num_threads(threads)
+    net = make_net(kind)
+    eng = OracleEngine(dict(net.state_dict()), cases.json_characters(118), kind=kind)
+    eng.model = lambda x: net(x)
+    eng.max_input_horizontal_pixels = BATCH * WIDTH
+    lines = list(cases.bench_crops(n_lines, WIDTH, seed=0))
+    with torch.no_grad():
+        eng.process_lines(lines[:1], no_logits=True)          # warm-up (thread pool, allocator)
+        t0 = time.perf_counter()
+        eng.process_lines(lines, no_logits=True)
+        dt = time.perf_counter() - t0
+    return n_lines / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = max(1, args.ref_lines)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_lines_per_s(args.net, 1, cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        r, dt, used = cpu_reference_lines_per_s(args.net, sample, cores)
+        rates.append(r)
+        t_all += dt
+    value = sample * args.steps / t_all
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'config2: {sample}-line sample of the batch-256 40x1280 workload, random-init CNN+BiLSTM '
+                               f'(reference algorithm on host cores)', 'net': args.net, 'lines_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port',
+                         'sample': f'{sample} lines x {args.steps} steps, torch-CPU fp32, {used} threads'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16'])
+    ap.add_argument('--net', default='lstm', choices=['lstm', 'transformer'])
+    ap.add_argument('--ref-lines', type=int, default=4, help='lines per step of the CPU reference arm')
+    ap.add_argument('--cpu-baseline-lines', type=int, default=16)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-out', default=None, help='write the per-layer kernel table (JSON) here')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pero_ocr_b200 import synthetic as cases
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    from pero_ocr_b200.sharding import gather_ids
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---- engine through the reference-facing constructor (engine JSON + module)
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    js = os.path.join(tmp, 'ocr.json')
+    with open(js, 'w', encoding='utf8') as f:
+        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'unused.pt',
+                   'characters': cases.json_characters(118), 'net_name': 'B200_BENCH'}, f)
+    net = make_net(args.net)
+    engine = B200EngineLineOCR(js, dev, batch_size=8, precision=args.precision, module=net)
+    engine.max_input_horizontal_pixels = BATCH * WIDTH          # as user_scripts/select_embed_id.py:54-55 does
+    rec = engine.model
+    rec.reserve(BATCH, PADDED)
+
+    # ---- synthetic inputs: 4 distinct resident batches (165 MB > L2), seeded per rank
+    n_rot = 4
+    host_lines = cases.bench_crops(BATCH * n_rot, WIDTH, seed=rank)         # [n,40,1280,3] u8
+    resident = []
+    for r in range(n_rot):
+        b = torch.zeros((BATCH, 40, PADDED, 3), dtype=torch.uint8, device=dev)
+        b[:, :, 32:32 + WIDTH] = torch.from_numpy(host_lines[r * BATCH:(r + 1) * BATCH]).to(dev)
+        resident.append(b)
+    outs = {}
+
+    def step(i):
+        rec.forward(resident[i % n_rot], want_logits=False, out=outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = rec.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    launches = rec.launch_count - launches0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
+    value = world * BATCH * args.steps / (ms_dev / 1e3)
+
+    # ---- end to end through process_lines (host crops in, strings out), then the gather of label ids
+    e2e_lines = [host_lines[i % (BATCH * n_rot)] for i in range(BATCH * args.steps)]
+    engine.process_lines(e2e_lines[:BATCH * 2], no_logits=True)             # warm-up: pinned buffers, slots
+    engine.h2d_bytes = engine.d2h_bytes = 0
+    barrier()
+    t0 = time.perf_counter()
+    ids, _, _ = engine.process_lines(e2e_lines, no_logits=True, return_ids=True)
+    gathered = 0
+    if world > 1:
+        _, gathered = gather_ids(ids, [rank * len(ids) + i for i in range(len(ids))], world * len(ids))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * len(e2e_lines) / float(t.item())
+    e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': engine.h2d_bytes // args.steps,
+           'd2h_bytes_per_step': engine.d2h_bytes // args.steps, 'gather_bytes_total': gathered,
+           'api': 'B200EngineLineOCR.process_lines(lines, no_logits=True)'}
+
+    # ---- roofline leg: per-launch CUDA-event timing of the same step (separate from the timed region)
+    rec.profile(True)
+    prof_steps = 3
+    for i in range(prof_steps):
+        step(i)
+    tags, lidx, pms = rec.profile_read()
+    rec.profile(False)
+    total_flops, gemm_flops = rec.flops(BATCH, PADDED)
+    igemm_ms = float(pms[tags == 1].sum()) / prof_steps
+    lstm_ms = float(pms[tags == 2].sum()) / prof_steps
+    first_ms = float(pms[tags == 0].sum()) / prof_steps
+    other_ms = float(pms[tags == 3].sum()) / prof_steps
+    n_igemm = int((tags == 1).sum()) // prof_steps
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved = gemm_flops / (igemm_ms / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': 'igemm_tc_kernel (tcgen05 implicit-GEMM conv/GEMM)',
+                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'peak_source': peak_src, 'traffic': None,
+                'algorithmic_gflop_per_line': gemm_flops / BATCH / 1e9,
+                'launches_per_step': n_igemm, 'avg_launch_ms': igemm_ms / max(n_igemm, 1),
+                'share_of_step': igemm_ms / (igemm_ms + lstm_ms + first_ms + other_ms),
+                'step_breakdown_ms': {'igemm_tc': igemm_ms, 'lstm_tc': lstm_ms, 'conv_first': first_ms, 'other': other_ms},
+                'executed_mma_passes': 3 if args.precision == 'fp16x3' else 1}
+    if args.profile_out and rank == 0:
+        per_layer = {}
+        for tg, li, m in zip(tags, lidx, pms):
+            key = f'layer{int(li):02d}_tag{int(tg)}'
+            per_layer[key] = per_layer.get(key, 0.0) + float(m) / prof_steps
+        with open(args.profile_out, 'w') as f:
+            json.dump({'precision': args.precision, 'per_layer_ms': per_layer, 'roofline': roofline}, f, indent=1)
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16x3 (fp16 hi/lo split operands, fp32 accumulate)' if args.precision == 'fp16x3' else 'f16 (fp32 accumulate)',
+        'data': 'synthetic',
+        'config': {'workload': 'config2: ocr_engine line recognizer, batch=256 synthetic 40x1280 gray crops (40x1344 padded), '
+                               'random-init CNN+BiLSTM, C=120' if args.net == 'lstm' else
+                               'config3 forward: Transformer-encoder variant, batch=256 synthetic 40x1280 crops',
+                   'net': args.net, 'lines_per_step': BATCH, 'precision': args.precision,
+                   'l2_policy': f'{n_rot} distinct resident input batches (165 MB) rotated; per-step activations (>3 GB) exceed L2',
+                   'parallelism': f'batch-parallel x{world}, no data-path collective'},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, dt_cpu, used = cpu_reference_lines_per_s(args.net, args.cpu_baseline_lines)
+        line['cpu_baseline'] = {'value': r, 'unit': UNIT, 'cores': used, 'kind': 'port',
+                                'sample': f'{args.cpu_baseline_lines} lines of the same workload in {dt_cpu:.1f} s, torch-CPU fp32'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

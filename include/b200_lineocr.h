@@ -146,6 +146,14 @@ int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int
 int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
                             int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream);
 
+/* Per-launch device timing for bench.py's roofline leg: while on, every kernel launched by b200ocr_forward is
+ * bracketed by CUDA events on its stream.  b200ocr_profile_read synchronises the device, returns one record per
+ * launch (tag 0 = first conv, 1 = tcgen05 implicit GEMM, 2 = tcgen05 LSTM recurrence, 3 = other; index of the layer;
+ * milliseconds) and clears the list.  Never on inside a timed throughput region. */
+int b200ocr_profile(b200ocr_engine_t* e, int32_t on);
+int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, int32_t* layers, float* ms,
+                         int32_t* count);
+
 /* ---- debug / test hooks (not used by the product path) ------------------------------------------------- */
 /* Route every implicit-GEMM layer through a naive one-thread-per-output CUDA-core kernel (same packed fp16
  * operands, fp32 accumulate) so the tcgen05 path can be checked on a GPU box where the reference is absent. */

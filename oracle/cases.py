@@ -6,6 +6,8 @@ so the GPU box regenerates bit-identical inputs and weights without shipping the
 import numpy as np
 from scipy.special import log_softmax
 
+from pero_ocr_b200.synthetic import bench_crops, json_characters  # noqa: F401
+
 BLANK = '<BLANK>'
 
 # Recogniser cases hosted by the reference engine in make_golden.py.  `engine_batch_size` is the constructor
@@ -21,11 +23,6 @@ PARSENET_CASE = dict(seed=5, downsample=2, height=250, width=330)
 CONFIG1_BEAM_LINES = 6
 
 
-def json_characters(n):
-    """`n` distinct printable characters for the engine JSON (the engine appends U+200B and blank is last)."""
-    return [chr(0x100 + i) for i in range(n)]
-
-
 def line_crop(rng, width, height=40):
     """One synthetic "gray" crop [H,W,3] u8: equal channels."""
     g = rng.integers(0, 256, (height, width), dtype=np.uint8)
@@ -39,13 +36,6 @@ def engine_lines(kind):
     # one genuinely coloured line: the net sees 3 distinct channels
     lines[1] = rng.integers(0, 256, lines[1].shape, dtype=np.uint8)
     return lines
-
-
-def bench_crops(n, width=1280, seed=0, height=40):
-    """BASELINE.json configs 2/3/5: n gray 40 x width crops, default_rng(seed)."""
-    rng = np.random.default_rng(seed)
-    g = rng.integers(0, 256, (n, height, width), dtype=np.uint8)
-    return np.repeat(g[:, :, :, None], 3, axis=3)
 
 
 def config1_logits():

@@ -1,209 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- synthetic random-init recogniser nets (oracle side).
-
-The reference ships no CNN+BiLSTM definition: the recogniser is an opaque
-TorchScript blob loaded at ``pero_ocr/ocr_engine/pytorch_ocr_engine.py:52-57``
-and called as ``model(x: f32[N,3,40,W]) -> f32[N,C,W/4]`` (``:64-69``).  The
-modules below are *our* seeded stand-ins with that contract; they are scripted
-and hosted by the unmodified reference engine to produce golden vectors
-(``oracle/make_golden.py``) and are the torch-CPU fp32 oracle for the CUDA path.
-
-The convolutional frontend restates the layer list the reference builds in
-``pero_ocr/ocr_engine/transformer.py:75-148`` (VGG16 ``features[:17]`` with the
-pool strides rewritten for subsampling (8, 4), then a 256->512->512 LeakyReLU
-block, BatchNorm2d(512)) and ``:335-363`` (5x1 aggregation conv + LeakyReLU).
-``make_golden.py`` checks this restatement against the reference's own
-``ConvolutionalEncoder`` loaded with the same weights.
-
-Weights are drawn from ``numpy.random.default_rng(seed)`` (PCG64 -- stable across
-numpy/torch versions and machines) in a fixed order, so the GPU box can rebuild
-the exact same parameters without shipping 100 MB of floats.
-"""
-import math
-from collections import OrderedDict
-
-import numpy as np
-import torch
-from torch import nn
-
-# (cin, cout, act, pool_after)   act: 'relu' | 'lrelu'
-VGG_FRONTEND = [
-    (3, 64, 'relu', None),
-    (64, 64, 'relu', (2, 2)),
-    (64, 128, 'relu', None),
-    (128, 128, 'relu', (2, 2)),
-    (128, 256, 'relu', None),
-    (256, 256, 'relu', None),
-    (256, 256, 'relu', (2, 1)),
-    (256, 512, 'lrelu', None),
-    (512, 512, 'lrelu', None),
-]
-LINE_HEIGHT = 40
-AGG_HEIGHT = LINE_HEIGHT // 8
-D_MODEL = 512
-
-
-def build_frontend_modules():
-    layers = []
-    for cin, cout, act, pool in VGG_FRONTEND:
-        layers.append(nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1))
-        layers.append(nn.ReLU() if act == 'relu' else nn.LeakyReLU())
-        if pool is not None:
-            layers.append(nn.MaxPool2d(kernel_size=pool, stride=pool))
-    layers.append(nn.BatchNorm2d(512))
-    return nn.Sequential(*layers)
-
-
-class LineNetLSTM(nn.Module):
-    """VGG frontend -> 2-layer BiLSTM -> linear CTC head.  f32[N,3,40,W] -> f32[N,C,W/4]."""
-
-    def __init__(self, num_classes: int = 120, hidden: int = 256, lstm_layers: int = 2):
-        super().__init__()
-        self.conv = build_frontend_modules()
-        self.agg = nn.Conv2d(512, D_MODEL, kernel_size=(AGG_HEIGHT, 1))
-        self.agg_act = nn.LeakyReLU()
-        self.lstm = nn.LSTM(D_MODEL, hidden, num_layers=lstm_layers, bidirectional=True)
-        self.out = nn.Linear(2 * hidden, num_classes)
-
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.agg_act(self.agg(self.conv(x)))      # [N,512,1,T]
-        y = y.squeeze(2).permute(2, 0, 1)             # [T,N,512]
-        y, _ = self.lstm(y)                           # [T,N,2H]
-        y = self.out(y)                               # [T,N,C]
-        return y.permute(1, 2, 0)                     # [N,C,T]
-
-
-class LineNetTransformer(nn.Module):
-    """VGG frontend -> LayerNorm + sinusoid PE + post-LN TransformerEncoder -> linear CTC head.
-
-    Encoder half of the reference's ``TransformerOCR`` (``transformer.py:366-385, 548-555``)
-    with a CTC head in place of the autoregressive decoder.
-    """
-
-    def __init__(self, num_classes: int = 120, layers: int = 2, heads: int = 8, dim_ff: int = 2048,
-                 max_len: int = 2000):
-        super().__init__()
-        self.conv = build_frontend_modules()
-        self.agg = nn.Conv2d(512, D_MODEL, kernel_size=(AGG_HEIGHT, 1))
-        self.agg_act = nn.LeakyReLU()
-        self.input_norm = nn.LayerNorm(D_MODEL, eps=1e-5)
-        enc_layer = nn.TransformerEncoderLayer(D_MODEL, heads, dim_feedforward=dim_ff, dropout=0.0)
-        self.trans_encoder = nn.TransformerEncoder(enc_layer, num_layers=layers, enable_nested_tensor=False)
-        pe = torch.zeros(max_len, D_MODEL)
-        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
-        div_term = torch.exp(torch.arange(0, D_MODEL, 2).float() * (-math.log(10000.0) / D_MODEL))
-        pe[:, 0::2] = torch.sin(position * div_term)
-        pe[:, 1::2] = torch.cos(position * div_term)
-        self.register_buffer('pe', pe.unsqueeze(1), persistent=False)
-        self.out = nn.Linear(D_MODEL, num_classes)
-
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.agg_act(self.agg(self.conv(x)))
-        y = y.squeeze(2).permute(2, 0, 1)             # [T,N,512]
-        y = self.input_norm(y)
-        y = y + self.pe[:y.size(0)]
-        y = self.trans_encoder(y)
-        y = self.out(y)
-        return y.permute(1, 2, 0)
-
-
-class ParseNetStandIn(nn.Module):
-    """Conv-only stand-in for the opaque ParseNet blob (``layout_engines/torch_parsenet.py:11-15, 51-53``):
-    f32[1,3,H,W] (H, W multiples of 64) -> (f32[1,5,H,W], aux).  Encoder: 3 conv+pool levels, decoder:
-    nearest upsampling + conv, 5 output maps (``cnn_layout_engine.py:129-131``)."""
-
-    def __init__(self, base: int = 64):
-        super().__init__()
-        b = base
-        self.e1 = nn.Conv2d(3, b, 3, padding=1)
-        self.e2 = nn.Conv2d(b, b, 3, padding=1)
-        self.e3 = nn.Conv2d(b, 2 * b, 3, padding=1)
-        self.e4 = nn.Conv2d(2 * b, 2 * b, 3, padding=1)
-        self.d1 = nn.Conv2d(2 * b, b, 3, padding=1)
-        self.d2 = nn.Conv2d(b, b, 3, padding=1)
-        self.head = nn.Conv2d(b, 5, 3, padding=1)
-        self.pool = nn.MaxPool2d(2, 2)
-        self.act = nn.ReLU()
-
-    def forward(self, x: torch.Tensor):
-        y = self.act(self.e1(x))
-        y = self.pool(self.act(self.e2(y)))           # /2
-        y = self.act(self.e3(y))
-        y = self.pool(self.act(self.e4(y)))           # /4
-        y = self.act(self.d1(y))
-        y = self.act(self.d2(y))
-        y = self.head(y)                               # [1,5,H/4,W/4]
-        y = torch.nn.functional.interpolate(y, scale_factor=4.0, mode='nearest')
-        return y, y[:, :1]
-
-
-# --------------------------------------------------------------------------------------------
-# Seeded parameters (numpy PCG64) -- same dict feeds the oracle modules and the CUDA engine.
-# --------------------------------------------------------------------------------------------
-
-def _fan_in(shape):
-    f = 1
-    for s in shape[1:]:
-        f *= s
-    return f
-
-
-def seeded_state_dict(module: nn.Module, seed: int = 0, out_gain: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
-    """Draw every parameter/buffer of ``module`` from default_rng(seed) in state_dict order.
-
-    conv / linear weights: He-uniform (gain sqrt(2)) so activations stay O(1) through the ReLU stack;
-    biases U(-0.1, 0.1); BatchNorm: gamma U(0.5,1.5), beta U(-0.2,0.2), mean U(-0.2,0.2), var U(0.5,1.5);
-    LayerNorm gamma U(0.8,1.2), beta U(-0.1,0.1); LSTM / attention in_proj: U(-1/sqrt(fan_in), ..).
-    ``out_gain`` scales the CTC head ('out.weight') so the top-2 logit margin is well above numeric error.
-    """
-    rng = np.random.default_rng(seed)
-    sd = OrderedDict()
-    for name, ref in module.state_dict().items():
-        shape = tuple(ref.shape)
-        leaf = name.split('.')[-1]
-        if leaf == 'num_batches_tracked':
-            sd[name] = torch.zeros((), dtype=torch.long)
-            continue
-        is_bn = leaf in ('running_mean', 'running_var') or (
-            len(shape) == 1 and name.rsplit('.', 1)[0] + '.running_mean' in module.state_dict())
-        is_ln = ('norm' in name) and len(shape) == 1 and not is_bn
-        if leaf == 'running_var':
-            a = rng.uniform(0.5, 1.5, shape)
-        elif leaf == 'running_mean':
-            a = rng.uniform(-0.2, 0.2, shape)
-        elif is_bn and leaf == 'weight':
-            a = rng.uniform(0.5, 1.5, shape)
-        elif is_bn and leaf == 'bias':
-            a = rng.uniform(-0.2, 0.2, shape)
-        elif is_ln and leaf == 'weight':
-            a = rng.uniform(0.8, 1.2, shape)
-        elif is_ln and leaf == 'bias':
-            a = rng.uniform(-0.1, 0.1, shape)
-        elif name.startswith('lstm.') or 'in_proj' in name:
-            if len(shape) >= 2:
-                b = 1.0 / math.sqrt(shape[1])
-            else:
-                b = 0.05
-            a = rng.uniform(-b, b, shape)
-        elif len(shape) >= 2:
-            gain = math.sqrt(2.0)
-            b = gain * math.sqrt(3.0 / _fan_in(shape))
-            if name == 'out.weight':
-                b = out_gain * math.sqrt(3.0 / _fan_in(shape))
-            a = rng.uniform(-b, b, shape)
-        else:
-            a = rng.uniform(-0.1, 0.1, shape)
-        sd[name] = torch.from_numpy(a.astype(np.float32))
-    return sd
-
-
-def make_net(kind: str = 'lstm', num_classes: int = 120, seed: int = 0, out_gain: float = 1.0, **kw) -> nn.Module:
-    if kind == 'lstm':
-        net = LineNetLSTM(num_classes, **kw)
-    elif kind == 'transformer':
-        net = LineNetTransformer(num_classes, **kw)
-    elif kind == 'parsenet':
-        net = ParseNetStandIn(**kw)
-    else:
-        raise ValueError(kind)
-    net.load_state_dict(seeded_state_dict(net, seed, out_gain))
-    return net.eval()
+"""TEST INFRASTRUCTURE ONLY -- the synthetic net definitions live in pero_ocr_b200/synthetic.py (shared with
+bench.py and smoke()); re-exported here for the oracle modules."""
+from pero_ocr_b200.synthetic import *  # noqa: F401,F403
+from pero_ocr_b200.synthetic import VGG_FRONTEND, make_net, seeded_state_dict  # noqa: F401

@@ -54,6 +54,9 @@ EXPORTS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'b200ocr_ctc_prefix_beam': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'b200ocr_profile': (C.c_int, [C.c_void_p, C.c_int32]),
+    'b200ocr_profile_read': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_int32)]),
     'b200ocr_debug_use_reference_kernels': (C.c_int, [C.c_void_p, C.c_int32]),
     'b200ocr_debug_forward_prefix': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),

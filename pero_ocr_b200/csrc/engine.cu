@@ -83,6 +83,10 @@ struct b200ocr_engine {
     size_t frames_cap = 0;
     int64_t launches = 0;
     std::string err;
+    bool profiling = false;
+    int cur_layer = -1;
+    struct ProfRec { int tag, layer; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -97,6 +101,29 @@ int fail(b200ocr_engine* e, int status, const char* fmt, ...) {
     else g_create_error = buf;
     return status;
 }
+
+// Brackets one kernel launch with CUDA events on its own stream when profiling is on (bench.py's roofline leg).
+struct ProfScope {
+    b200ocr_engine* e;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int tag;
+    bool on;
+    ProfScope(b200ocr_engine* e_, cudaStream_t st_, int tag_) : e(e_), st(st_), tag(tag_), on(e_->profiling) {
+        if (on) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(b, st);
+            e->prof.push_back({tag, e->cur_layer, a, b});
+        }
+    }
+};
+enum { PROF_CONV_FIRST = 0, PROF_IGEMM = 1, PROF_LSTM = 2, PROF_OTHER = 3 };
 
 #define CU_TRY(e, call)                                                                                   \
     do {                                                                                                  \
@@ -219,7 +246,10 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     }
     CUtensorMap tmA;
     if (int s = make_map_act(e, &tmA, in, in_s.n, in_s.h, in_s.w, e->planes * g.cin, p.th)) return s;
-    CU_TRY(e, launch_igemm_tc(p, tmA, g.tmB, g.bn, e->num_sms, st));
+    {
+        ProfScope ps(e, st, PROF_IGEMM);
+        CU_TRY(e, launch_igemm_tc(p, tmA, g.tmB, g.bn, e->num_sms, st));
+    }
     e->launches++;
     return 0;
 }
@@ -257,6 +287,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
     const int L = std::min<int>(n_layers, e->layers.size());
     for (int li = 0; li < L; ++li) {
         LayerRT& ly = e->layers[li];
+        e->cur_layer = li;
         const int next_kind = li + 1 < (int)e->layers.size() ? e->layers[li + 1].kind : 0;
         switch (ly.kind) {
             case B200OCR_CONV_FIRST: {
@@ -265,6 +296,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                 if (dry) dry->hn(slot, hbytes(e, os));
                 else {
                     if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    ProfScope ps(e, st, PROF_CONV_FIRST);
                     CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
                                                 e->planes, static_cast<__half*>(e->hbuf[slot]), st));
                     e->launches++;
@@ -334,6 +366,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     if (e->use_ref) {
                         CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->planes, e->planes == 1, o, st));
                     } else {
+                        ProfScope ps(e, st, PROF_LSTM);
                         CU_TRY(e, launch_lstm_tc(ly.tmW, eo.out_f32, o, cur.n, T, H, e->planes, st));
                     }
                     e->launches++;
@@ -387,12 +420,12 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     EpiOut eo;
                     eo.epi = EPI_F32; eo.out_f32 = qkv;
                     if (int s = run_gemm(e, ly.g_in, xh, rows, 0, 1, 1, eo, st, nullptr)) return s;
-                    CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->planes, st));
+                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->planes, st)); }
                     e->launches++;
                     EpiOut er;
                     er.epi = EPI_RES_F32; er.out_f32 = tmp; er.residual = x;
                     if (int s = run_gemm(e, ly.g_out, ah, rows, 0, 1, 1, er, st, nullptr)) return s;
-                    CU_TRY(e, launch_layernorm(tmp, R, D, ly.n1w, ly.n1b, 1e-5f, 0, x, xh, e->planes, st));
+                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_layernorm(tmp, R, D, ly.n1w, ly.n1b, 1e-5f, 0, x, xh, e->planes, st)); }
                     e->launches++;
                     EpiOut ef;
                     ef.epi = EPI_ACT_F16; ef.out_h = fh;
@@ -400,7 +433,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     Shape ffrows{1, 1, R, ly.dim_ff};
                     er.out_f32 = tmp; er.residual = x;
                     if (int s = run_gemm(e, ly.g_l2, fh, ffrows, 0, 1, 1, er, st, nullptr)) return s;
-                    CU_TRY(e, launch_layernorm(tmp, R, D, ly.n2w, ly.n2b, 1e-5f, 0, x, xh, e->planes, st));
+                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_layernorm(tmp, R, D, ly.n2w, ly.n2b, 1e-5f, 0, x, xh, e->planes, st)); }
                     e->launches++;
                 }
                 break;
@@ -435,6 +468,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                         if (int s = run_gemm(e, ly.g, cur_h, rows, 0, 1, 1, eo, st, nullptr)) return s;
                     }
                     if (out.labels) {
+                        ProfScope ps(e, st, PROF_OTHER);
                         CU_TRY(e, launch_ctc_collapse(best, out.confidence ? e->fprob : nullptr, cur.n, T, C - 1,
                                                       out.labels, out.lengths, out.confidence, st));
                         e->launches++;
@@ -751,6 +785,30 @@ int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_
     cudaError_t err = launch_ctc_prefix_beam(logprobs, n, t, c, k, out_labels, out_lengths, out_scores, status, ws, st);
     cudaFreeAsync(ws, st);
     if (err != cudaSuccess) return fail(nullptr, B200OCR_E_CUDA, "prefix beam launch failed: %s", cudaGetErrorString(err));
+    return B200OCR_OK;
+}
+
+int b200ocr_profile(b200ocr_engine_t* e, int32_t on) {
+    if (!e) return B200OCR_E_INVALID;
+    for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.clear();
+    e->profiling = on != 0;
+    return B200OCR_OK;
+}
+
+int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, int32_t* layers, float* ms,
+                         int32_t* count) {
+    if (!e || !count) return B200OCR_E_INVALID;
+    CU_TRY(e, cudaDeviceSynchronize());
+    const int n = static_cast<int>(e->prof.size());
+    *count = n;
+    for (int i = 0; i < n && i < capacity; ++i) {
+        float t = 0.f;
+        CU_TRY(e, cudaEventElapsedTime(&t, e->prof[i].a, e->prof[i].b));
+        tags[i] = e->prof[i].tag; layers[i] = e->prof[i].layer; ms[i] = t;
+    }
+    for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.clear();
     return B200OCR_OK;
 }
 

@@ -96,6 +96,20 @@ class LineRecognizer:
             C.c_void_p(stream)), self._h)
         return o
 
+    def profile(self, on):
+        _lib.check(self._lib.b200ocr_profile(self._h, 1 if on else 0), self._h)
+
+    def profile_read(self, capacity=4096):
+        tags = np.zeros(capacity, dtype=np.int32)
+        layers = np.zeros(capacity, dtype=np.int32)
+        ms = np.zeros(capacity, dtype=np.float32)
+        count = C.c_int32()
+        _lib.check(self._lib.b200ocr_profile_read(self._h, capacity, tags.ctypes.data_as(C.c_void_p),
+                                                  layers.ctypes.data_as(C.c_void_p), ms.ctypes.data_as(C.c_void_p),
+                                                  C.byref(count)), self._h)
+        k = min(count.value, capacity)
+        return tags[:k], layers[:k], ms[:k]
+
     def debug_forward_prefix(self, crops, n_layers):
         n, h, w, _ = crops.shape
         self.reserve(n, w)
@@ -155,28 +169,64 @@ class B200EngineLineOCR:
             raise ValueError(f'net emits {n_classes} classes, engine JSON implies {len(self.characters) + 1}')
         self.model = LineRecognizer(layers, precision=precision, line_height=self.line_px_height,
                                     device=self.device.index or 0)
-        self._pinned = None
-        self._dev_in = None
-        self._outs = {}
+        self._slots = None
+        self._copy_stream = None
         self.want_confidence = False
         self.last_confidences = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def _device_ctx(self):
+        return self.model.torch.cuda.device(self.device)
+
     # ---- device step --------------------------------------------------------------------------------------
-    def _stage(self, batch_data):
-        """Host u8 batch -> pinned staging buffer -> device (async on the current stream)."""
+    def _slot(self, k):
+        """Per-slot pinned staging, device input and output buffers (two slots: batch i+1 is staged on the host
+        and copied on a side stream while batch i computes)."""
+        if self._slots is None:
+            torch = self.model.torch
+            self._slots = [dict(pin=None, dev=None, outs={}, host={}, done=torch.cuda.Event(), h2d=torch.cuda.Event())
+                           for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(self.device)
+        return self._slots[k]
+
+    def _submit(self, k, shape, fill, no_logits):
+        """Stage one padded uint8 batch of `shape` (filled in place by `fill(view)`), copy it to the device on the
+        side stream, run the forward on the current stream and start the device->host copies of the results."""
         torch = self.model.torch
-        n_bytes = batch_data.size
-        if self._pinned is None or self._pinned.numel() < n_bytes:
-            self._pinned = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
-            self._dev_in = torch.empty(n_bytes, dtype=torch.uint8, device=self.device)
-        pin = self._pinned[:n_bytes].view(batch_data.shape)
-        pin.numpy()[...] = batch_data
-        dev = self._dev_in[:n_bytes].view(batch_data.shape)
-        dev.copy_(pin, non_blocking=True)
+        sl = self._slot(k)
+        n_bytes = int(np.prod(shape))
+        if sl['pin'] is None or sl['pin'].numel() < n_bytes:
+            sl['pin'] = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+            sl['dev'] = torch.empty(n_bytes, dtype=torch.uint8, device=self.device)
+        pin = sl['pin'][:n_bytes].view(shape)
+        fill(pin.numpy())
+        dev = sl['dev'][:n_bytes].view(shape)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            dev.copy_(pin, non_blocking=True)
+            sl['h2d'].record(self._copy_stream)
+        main.wait_event(sl['h2d'])
         self.h2d_bytes += n_bytes
-        return dev
+        o = self.model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence, out=sl['outs'])
+        sl['outs'] = o
+        names = ['labels', 'lengths'] + ([] if no_logits else ['logits']) + (['confidence'] if self.want_confidence else [])
+        for name in names:
+            t = o[name]
+            h = sl['host'].get(name)
+            if h is None or h.shape != t.shape:
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                sl['host'][name] = h
+            h.copy_(t, non_blocking=True)
+            self.d2h_bytes += h.numel() * h.element_size()
+        sl['done'].record(main)
+        return k, names
+
+    def _collect(self, ticket):
+        k, names = ticket
+        sl = self._slots[k]
+        sl['done'].synchronize()
+        return {name: sl['host'][name].numpy() for name in names}
 
     def _decode_ids(self, labels, lengths):
         chars = self.characters
@@ -184,55 +234,55 @@ class B200EngineLineOCR:
 
     def run_ocr(self, batch_data, no_logits=False):
         """np.uint8 [N,H,W,3] -> (list[str], np.float32 [N,T,C])   (pytorch_ocr_engine.py:59-74)."""
-        torch = self.model.torch
-        with torch.cuda.device(self.device):
-            dev = self._stage(np.ascontiguousarray(batch_data))
-            o = self.model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence,
-                                   out=self._outs)
-            self._outs = o
-            labels = o['labels'].cpu().numpy()
-            lengths = o['lengths'].cpu().numpy()
-            self.d2h_bytes += labels.nbytes + lengths.nbytes
-            logits = None
-            if not no_logits:
-                logits = o['logits'].cpu().numpy()
-                self.d2h_bytes += logits.nbytes
-            if self.want_confidence:
-                self.last_confidences = o['confidence'].cpu().numpy()
-        return self._decode_ids(labels, lengths), logits
+        batch_data = np.asarray(batch_data)
+        if batch_data.ndim != 4 or batch_data.shape[3] != 3:
+            raise ValueError('line crops need three colour channels')
+        with self._device_ctx():
+            def fill(view):
+                view[...] = batch_data
+            res = self._collect(self._submit(0, batch_data.shape, fill, no_logits))
+        if self.want_confidence:
+            self.last_confidences = res['confidence'].copy()
+        logits = None if no_logits else res['logits'].copy()
+        return self._decode_ids(res['labels'], res['lengths']), logits
 
     # ---- batching ------------------------------------------------------------------------------------------
-    def process_lines(self, lines, sparse_logits=True, tight_crop_logits=False, no_logits=False):
+    def _batches(self, lines):
+        """Widest-first batches under the pixel budget (line_ocr_engine.py:79-90)."""
+        pending = sorted(range(len(lines)), key=lambda i: -lines[i].shape[1])     # stable: ties keep input order
+        while pending:
+            widest = int(math.ceil(lines[pending[0]].shape[1] / 32.0) * 32)
+            take = max(1, self.max_input_horizontal_pixels // widest)
+            chunk, pending = pending[:take], pending[take:]
+            yield chunk, widest
+
+    def process_lines(self, lines, sparse_logits=True, tight_crop_logits=False, no_logits=False, return_ids=False):
         """list of [H,w,3] uint8 crops -> (transcriptions, logits, logit_coords); semantics of
         line_ocr_engine.py:57-177 for model_type 'ctc': widest-first batches under a pixel budget, 32 px zero
-        padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4."""
+        padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4.
+        Batches are double-buffered: batch i+1 is padded and uploaded while batch i runs on the GPU."""
         from scipy import sparse
         count = len(lines)
         transcriptions = [None] * count
         logits_out = [None] * count
         coords_out = [None] * count
         confidences = [None] * count
-        pad, sub = self.line_padding_px, self.net_subsampling
-        pending = sorted(range(count), key=lambda i: -lines[i].shape[1])     # stable: ties keep input order
-        while pending:
-            widest = int(math.ceil(lines[pending[0]].shape[1] / 32.0) * 32)
-            take = max(1, self.max_input_horizontal_pixels // widest)
-            chunk, pending = pending[:take], pending[take:]
-            batch = np.zeros((len(chunk), self.line_px_height, widest + 2 * pad, 3), dtype=np.uint8)
-            for slot, idx in enumerate(chunk):
-                batch[slot, :, pad:pad + lines[idx].shape[1], :] = lines[idx]
-            if batch.shape[2] > self.max_input_horizontal_pixels:
-                print(f'WARNING: Line too long for OCR engine. Cropping from {batch.shape[2]} px down to '
-                      f'{self.max_input_horizontal_pixels}.')
-                batch = batch[:, :, :self.max_input_horizontal_pixels]
-            texts, dense = self.run_ocr(batch, no_logits=no_logits)
+        pad, sub, height = self.line_padding_px, self.net_subsampling, self.line_px_height
+        budget = self.max_input_horizontal_pixels
+
+        def finish(chunk, res):
+            labels, lengths = res['labels'], res['lengths']
+            if return_ids:
+                texts = [labels[s, :lengths[s]].copy() for s in range(len(chunk))]
+            else:
+                texts = self._decode_ids(labels, lengths)
             for slot, idx in enumerate(chunk):
                 transcriptions[idx] = texts[slot]
                 if self.want_confidence:
-                    confidences[idx] = float(self.last_confidences[slot])
+                    confidences[idx] = float(res['confidence'][slot])
                 if no_logits:
                     continue
-                line_logits = dense[slot]
+                line_logits = res['logits'][slot]
                 lo, hi = int(pad // sub), int((pad + lines[idx].shape[1]) // sub)
                 if tight_crop_logits:
                     line_logits = line_logits[lo:hi]
@@ -243,6 +293,35 @@ class B200EngineLineOCR:
                     line_logits = line_logits.copy()
                     line_logits[softmax(line_logits, axis=1) < 0.0001] = 0
                     line_logits = sparse.csc_matrix(line_logits)
+                else:
+                    line_logits = line_logits.copy()
                 logits_out[idx] = line_logits
+
+        in_flight = None
+        with self._device_ctx():
+            for bi, (chunk, widest) in enumerate(self._batches(lines)):
+                full_w = widest + 2 * pad
+                width = full_w
+                if full_w > budget:
+                    print(f'WARNING: Line too long for OCR engine. Cropping from {full_w} px down to {budget}.')
+                    width = budget
+
+                def fill(view, chunk=chunk, width=width):
+                    for slot, idx in enumerate(chunk):
+                        line = lines[idx]
+                        if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
+                            raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
+                        end = min(width, pad + line.shape[1])
+                        view[slot, :, :pad] = 0
+                        if end > pad:
+                            view[slot, :, pad:end] = line[:, :end - pad]
+                        view[slot, :, end:] = 0
+
+                ticket = self._submit(bi & 1, (len(chunk), height, width, 3), fill, no_logits)
+                if in_flight is not None:
+                    finish(in_flight[0], self._collect(in_flight[1]))
+                in_flight = (chunk, ticket)
+            if in_flight is not None:
+                finish(in_flight[0], self._collect(in_flight[1]))
         self.last_line_confidences = confidences if self.want_confidence else None
         return transcriptions, logits_out, coords_out

@@ -1,0 +1,172 @@
+"""GPU parity: the CUDA recogniser behind B200EngineLineOCR against (1) outputs of the unmodified reference
+PytorchEngineLineOCR stored in tests/golden/engine_*.npz and (2) the torch-CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star: "bit-exact CTC argmax indices; logits within 1e-3 fp32"):
+  * precision 'fp16x3' (default): |logit - reference| <= 1e-3 absolute; per-frame argmax identical on every frame
+    whose reference top-2 margin exceeds 2e-3 (closer calls are numerically undecidable between any two fp32
+    implementations); transcriptions identical.
+  * precision 'fp16' (single-pass, same 10-bit mantissa as the reference's own cuDNN-TF32 GPU path): 3e-3 * max|logit|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.forward_oracle import OracleEngine, dense_logits, greedy_ctc_indices, line_confidence, sparsify_logits
+from tests.util import load_golden, make_case_net, write_engine_json
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+MARGIN = 2e-3
+
+
+def _engine(tmp_path, kind, precision='fp16x3', batch_size=None):
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    spec = cases.ENGINE_CASES[kind]
+    js = write_engine_json(tmp_path, kind)
+    return B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=batch_size or spec['engine_batch_size'],
+                             precision=precision, module=make_case_net(kind))
+
+
+@pytest.mark.parametrize('kind', ['lstm', 'transformer'])
+def test_process_lines_matches_reference_golden(tmp_path, golden_dir, kind):
+    gold = load_golden(golden_dir, f'engine_{kind}.npz')
+    eng = _engine(tmp_path, kind)
+    lines = cases.engine_lines(kind)
+    tr, lg, co = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+    assert eng.characters == list(gold['chars'])
+    worst = 0.0
+    for i in range(len(lines)):
+        ref = gold[f'logits_{i}']
+        assert lg[i].shape == ref.shape and lg[i].dtype == np.float32
+        worst = max(worst, float(np.abs(lg[i] - ref).max()))
+        assert list(co[i]) == list(gold[f'coords_{i}'])
+        # bit-exact argmax wherever the reference's own decision is numerically meaningful
+        srt = np.sort(ref, axis=1)
+        decided = (srt[:, -1] - srt[:, -2]) > MARGIN
+        assert np.array_equal(lg[i].argmax(axis=1)[decided], ref.argmax(axis=1)[decided])
+    assert worst <= TOL, worst
+    assert tr == list(gold['transcriptions'])
+    # tight crop / no-logits variants (line_ocr_engine.py:145-150, 143-144)
+    tr2, lg2, co2 = eng.process_lines([l.copy() for l in lines], sparse_logits=False, tight_crop_logits=True)
+    for i in range(len(lines)):
+        assert co2[i] == [None, None]
+        assert np.abs(lg2[i] - gold[f'tight_{i}']).max() <= TOL
+    tr3, lg3, co3 = eng.process_lines([l.copy() for l in lines], no_logits=True)
+    assert tr3 == tr and all(x is None for x in lg3) and all(x is None for x in co3)
+
+
+@pytest.mark.parametrize('kind', ['lstm', 'transformer'])
+def test_sparse_logits_match_reference_golden(tmp_path, golden_dir, kind):
+    from scipy import sparse
+    gold = load_golden(golden_dir, f'engine_{kind}.npz')
+    eng = _engine(tmp_path, kind)
+    lines = cases.engine_lines(kind)
+    _, lg, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=True)
+    for i in range(len(lines)):
+        assert sparse.issparse(lg[i]) and lg[i].format == 'csc'
+        ref = sparse.csc_matrix((gold[f'csc_data_{i}'], gold[f'csc_indices_{i}'], gold[f'csc_indptr_{i}']),
+                                shape=lg[i].shape).toarray()
+        got = lg[i].toarray()
+        both = (ref != 0) & (got != 0)
+        assert np.abs(got[both] - ref[both]).max() <= TOL
+        # the keep/drop pattern may differ only for probabilities within rounding of the 1e-4 threshold
+        assert ((ref != 0) != (got != 0)).mean() < 1e-3
+
+
+def test_checkpoint_file_route(tmp_path, golden_dir):
+    """Same TorchScript checkpoint file the reference engine loads (pytorch_ocr_engine.py:52-57)."""
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    net = make_case_net('lstm')
+    torch.jit.script(net).save(str(tmp_path / 'ck.pt'))
+    js = write_engine_json(tmp_path, 'lstm', checkpoint='ck.pt')
+    eng = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=1)
+    gold = load_golden(golden_dir, 'engine_lstm.npz')
+    tr, _, _ = eng.process_lines(cases.engine_lines('lstm'), no_logits=True)
+    assert tr == list(gold['transcriptions'])
+
+
+def test_single_pass_fp16_mode(tmp_path, golden_dir):
+    gold = load_golden(golden_dir, 'engine_lstm.npz')
+    eng = _engine(tmp_path, 'lstm', precision='fp16')
+    lines = cases.engine_lines('lstm')
+    tr, lg, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+    scale = max(float(np.abs(gold[f'logits_{i}']).max()) for i in range(len(lines)))
+    agree = total = 0
+    for i in range(len(lines)):
+        ref = gold[f'logits_{i}']
+        assert np.abs(lg[i] - ref).max() <= 3e-3 * scale
+        agree += int((lg[i].argmax(axis=1) == ref.argmax(axis=1)).sum())
+        total += ref.shape[0]
+    assert agree / total > 0.97
+
+
+@pytest.mark.parametrize('kind', ['lstm', 'transformer'])
+def test_tensor_core_kernels_match_cuda_core_cross_check(kind):
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    net = make_case_net(kind)
+    layers, _ = netdesc.describe_line_net(net)
+    eng = LineRecognizer(layers, precision='fp16x3')
+    rng = np.random.default_rng(3)
+    crops = torch.from_numpy(rng.integers(0, 256, (5, 40, 328, 3), dtype=np.uint8)).cuda()
+    a = eng.forward(crops, want_logits=True, want_best_path=True)
+    a = {k: v.clone() for k, v in a.items()}
+    eng.use_reference_kernels(True)
+    b = eng.forward(crops, want_logits=True, want_best_path=True, out={})
+    torch.cuda.synchronize()
+    assert (a['logits'] - b['logits']).abs().max().item() <= TOL
+
+
+def test_fused_confidence_matches_reference_chain(tmp_path):
+    """confidence output == PageParser.compute_line_confidence on the engine's own sparsified logits."""
+    eng = _engine(tmp_path, 'lstm', batch_size=8)
+    eng.want_confidence = True
+    lines = cases.engine_lines('lstm')
+    _, lg, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=True)
+    for i in range(len(lines)):
+        want = line_confidence(dense_logits(lg[i]))
+        assert eng.last_line_confidences[i] == pytest.approx(want, rel=2e-4)
+
+
+def test_error_behaviour(tmp_path):
+    from pero_ocr_b200 import B200Error
+    eng = _engine(tmp_path, 'lstm')
+    with pytest.raises(B200Error):
+        eng.run_ocr(np.zeros((1, 32, 64, 3), dtype=np.uint8))        # wrong line height
+    with pytest.raises(ValueError):
+        eng.run_ocr(np.zeros((1, 40, 64, 1), dtype=np.uint8))        # not 3 channels
+    tr, lg, co = eng.process_lines([])
+    assert tr == [] and lg == [] and co == []
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 size (256 x 40 x 1344): determinism and batch independence -- a line's result must
+    not depend on which other lines share its batch (the reference has the same property by construction)."""
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    net = make_case_net('lstm')
+    layers, _ = netdesc.describe_line_net(net)
+    eng = LineRecognizer(layers, precision='fp16x3')
+    crops = np.zeros((256, 40, 1344, 3), dtype=np.uint8)
+    crops[:, :, 32:-32] = cases.bench_crops(256, 1280, seed=0)
+    d = torch.from_numpy(crops).cuda()
+    a = {k: v.clone() for k, v in eng.forward(d, want_logits=True).items()}
+    b = {k: v.clone() for k, v in eng.forward(d, want_logits=True, out={}).items()}
+    assert torch.equal(a['labels'], b['labels']) and torch.equal(a['logits'], b['logits'])
+    sub = eng.forward(d[100:107].contiguous(), want_logits=True, out={})
+    torch.cuda.synchronize()
+    assert torch.equal(sub['labels'], a['labels'][100:107])
+    assert (sub['logits'] - a['logits'][100:107]).abs().max().item() <= 1e-5
+    # oracle on a bounded sample of the same batch
+    with torch.no_grad():
+        x = torch.from_numpy(crops[:2]).float().div(255.0).permute(0, 3, 1, 2)
+        ref = net(x).numpy()
+    got = a['logits'][:2].cpu().numpy()
+    assert np.abs(got - ref.transpose(0, 2, 1)).max() <= TOL
+    want = greedy_ctc_indices(ref)
+    lab, ln = a['labels'][:2].cpu().numpy(), a['lengths'][:2].cpu().numpy()
+    srt = np.sort(ref, axis=1)
+    if ((srt[:, -1] - srt[:, -2]) > MARGIN).all():
+        assert [list(lab[i, :ln[i]]) for i in range(2)] == [list(w) for w in want]

@@ -1,0 +1,105 @@
+"""CPU: host-side logic of the engine mirror (batching, padding, cropping, logit_coords, sparsification, ordering)
+with the device step replaced by the torch-CPU oracle -- compared with the unmodified reference's outputs."""
+import contextlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.forward_oracle import greedy_ctc_indices
+from tests.util import load_golden, make_case_net
+
+
+def _host_only_engine(kind):
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    spec = cases.ENGINE_CASES[kind]
+    net = make_case_net(kind)
+    eng = object.__new__(B200EngineLineOCR)
+    eng.line_px_height = 40
+    eng.line_padding_px = 32
+    eng.net_subsampling = 4
+    eng.batch_size = spec['engine_batch_size']
+    eng.max_input_horizontal_pixels = 480 * eng.batch_size
+    eng.characters = cases.json_characters(spec['classes'] - 2) + [u'​']
+    eng.want_confidence = False
+    eng.h2d_bytes = eng.d2h_bytes = 0
+    eng._device_ctx = contextlib.nullcontext
+    store = {}
+
+    def submit(k, shape, fill, no_logits):
+        batch = np.empty(shape, dtype=np.uint8)
+        batch[...] = 0xAB                      # stale garbage: fill() must overwrite every byte
+        fill(batch)
+        with torch.no_grad():
+            logits = net(torch.from_numpy(batch).float().div(255.0).permute(0, 3, 1, 2)).numpy()
+        ids = greedy_ctc_indices(logits)
+        T = logits.shape[2]
+        labels = np.full((shape[0], T), -1, dtype=np.int32)
+        for i, v in enumerate(ids):
+            labels[i, :len(v)] = v
+        store[k] = dict(labels=labels, lengths=np.array([len(v) for v in ids], dtype=np.int32),
+                        logits=np.ascontiguousarray(logits.transpose(0, 2, 1)))
+        return k, None
+
+    eng._submit = submit
+    eng._collect = lambda ticket: store[ticket[0]]
+    return eng
+
+
+@pytest.mark.parametrize('kind', ['lstm', 'transformer'])
+def test_process_lines_host_logic_matches_reference(golden_dir, kind):
+    gold = load_golden(golden_dir, f'engine_{kind}.npz')
+    eng = _host_only_engine(kind)
+    lines = cases.engine_lines(kind)
+    tr, lg, co = eng.process_lines(lines, sparse_logits=False)
+    assert tr == list(gold['transcriptions'])
+    for i in range(len(lines)):
+        np.testing.assert_allclose(lg[i], gold[f'logits_{i}'], atol=2e-5)
+        assert list(co[i]) == list(gold[f'coords_{i}'])
+    _, lg2, _ = eng.process_lines(lines, sparse_logits=True)
+    for i in range(len(lines)):
+        assert np.array_equal(lg2[i].indptr, gold[f'csc_indptr_{i}'])
+        assert np.array_equal(lg2[i].indices, gold[f'csc_indices_{i}'])
+    _, lg3, co3 = eng.process_lines(lines, sparse_logits=False, tight_crop_logits=True)
+    for i in range(len(lines)):
+        np.testing.assert_allclose(lg3[i], gold[f'tight_{i}'], atol=2e-5)
+        assert co3[i] == [None, None]
+    ids, _, _ = eng.process_lines(lines, no_logits=True, return_ids=True)
+    assert [''.join(eng.characters[c] for c in v) for v in ids] == tr
+
+
+def test_library_exports_every_declared_symbol():
+    """include/b200_lineocr.h and libb200_lineocr.so agree (no compute call: there is no GPU here)."""
+    from pero_ocr_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, 'include', 'b200_lineocr.h')).read()
+    declared = set(re.findall(r'\b(b200ocr_[a-z_0-9]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_product_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from pero_ocr_b200 import B200Error, netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    from pero_ocr_b200.decoders import GreedyDecoder
+    layers, _ = netdesc.describe_line_net(make_case_net('lstm'))
+    with pytest.raises(B200Error):
+        LineRecognizer(layers)
+    with pytest.raises(B200Error):
+        GreedyDecoder(['a', '<BLANK>'])(np.log(np.array([[0.5, 0.5]])))
+
+
+def test_product_package_does_not_import_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, 'pero_ocr_b200')
+    for name in os.listdir(pkg):
+        if name.endswith('.py'):
+            src = open(os.path.join(pkg, name)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), name
