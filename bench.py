@@ -48,7 +48,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                 getattr(pynvml, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
                 getattr(pynvml, 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown', 0x80): 'hw_power_brake',
             }
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f'nvml_unavailable:{type(exc).__name__}')
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}

@@ -548,8 +548,8 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
         int s = 0;
         switch (d.kind) {
             case B200OCR_CONV_FIRST: {
-                if (d.cin != 3 || d.kh != 3 || d.kw != 3 || d.cout > 64 || (d.cout % 8))
-                    return bail(fail(e, B200OCR_E_INVALID, "layer %d: first conv must be 3x3, 3 -> <=64 channels", i));
+                if (d.cin != 3 || d.kh != 3 || d.kw != 3 || (d.cout != 64 && d.cout != 32 && d.cout != 16))
+                    return bail(fail(e, B200OCR_E_INVALID, "layer %d: first conv must be 3x3, 3 -> 16/32/64 channels", i));
                 std::vector<float> wt(27 * d.cout);
                 for (int o = 0; o < d.cout; ++o)
                     for (int c = 0; c < 3; ++c)

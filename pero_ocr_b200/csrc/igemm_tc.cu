@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 fp16
 
 template <int BN>
@@ -69,6 +69,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull = bars + 2 * C::kStages;    // [2]
     uint64_t* tempty = bars + 2 * C::kStages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+    // per-channel epilogue vectors (bias | post_scale | post_shift), cout_pad floats each, 16-byte aligned
+    float* s_vec = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -86,91 +88,103 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull[i], 1);
-            ptx::mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tempty[i], 8);  // one arrive per epilogue warp
         }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
+        s_vec[i] = p.bias ? p.bias[i] : 0.f;
+        s_vec[p.cout_pad + i] = p.post_scale ? p.post_scale[i] : 1.f;
+        s_vec[2 * p.cout_pad + i] = p.post_shift ? p.post_shift[i] : 0.f;
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.tiles_n;
-                const int nt = tile - mt * p.tiles_n;
-                SegCoord sc[4];
+        // The whole warp runs the (warp-uniform) loop nest so that coordinates live in uniform registers; one
+        // elected lane issues.
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.tiles_n;
+            const int nt = tile - mt * p.tiles_n;
+            SegCoord sc[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sc[q] = seg_coord(p, mt * 4 + q);
-                for (int pass = 0; pass < p.npass; ++pass) {
-                    const int pa = (pass == 2) ? 1 : 0;  // activation plane
-                    const int pb = (pass == 1) ? 1 : 0;  // weight plane
-                    for (int tap = 0; tap < taps; ++tap) {
-                        const int r = tap / p.kw;
-                        const int s = tap - r * p.kw;
-                        const int brow = (pb * taps + tap) * p.cout_pad + nt * BN;
-                        for (int kc = 0; kc < kchunks; ++kc) {
-                            ptx::mbar_wait(&empty[stage], phase ^ 1);
-                            uint8_t* sA = smem + stage * C::kStageBytes;
-                            uint8_t* sB = sA + kABytes;
-                            ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
+            for (int q = 0; q < 4; ++q) sc[q] = seg_coord(p, mt * 4 + q);
+            for (int pass = 0; pass < p.npass; ++pass) {
+                const int pa = (pass == 2) ? 1 : 0;  // activation plane
+                const int pb = (pass == 1) ? 1 : 0;  // weight plane
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int r = tap / p.kw;
+                    const int s = tap - r * p.kw;
+                    const int brow = (pb * taps + tap) * p.cout_pad + nt * BN;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * C::kStageBytes;
+                        uint8_t* sB = sA + kABytes;
+                        ptx::mbar_expect_tx_pred(&full[stage], C::kStageBytes, leader);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                ptx::tma_load_4d(sA + q * 4096, &tmA, &full[stage], pa * p.cin + kc * 64,
-                                                 sc[q].w0 + s - p.pad_w, sc[q].h0 + r - p.pad_h, sc[q].img);
-                            ptx::tma_load_2d(sB, &tmB, &full[stage], kc * 64, brow);
-                            if (++stage == C::kStages) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
+                        for (int q = 0; q < 4; ++q)
+                            ptx::tma_load_4d_pred(sA + q * 4096, &tmA, &full[stage], pa * p.cin + kc * 64,
+                                                  sc[q].w0 + s - p.pad_w, sc[q].h0 + r - p.pad_h, sc[q].img, leader);
+                        ptx::tma_load_2d_pred(sB, &tmB, &full[stage], kc * 64, brow, leader);
+                        if (++stage == C::kStages) {
+                            stage = 0;
+                            phase ^= 1;
                         }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase[2] = {0, 0};
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                ptx::mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);
+        // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
+        constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase0 = 0, acc_phase1 = 0;
+        const uint32_t smem_base = ptx::smem_u32(smem);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int it = 0; it < k_iters; ++it) {
+                ptx::mbar_wait(&full[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int it = 0; it < k_iters; ++it) {
-                    ptx::mbar_wait(&full[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem + stage * C::kStageBytes);
-                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr);
-                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + kABytes);
+                const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+                const uint64_t a_desc = ptx::smem_desc_sw128(a_addr);
+                const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + kABytes);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)  // 4 x K=16 inside the 128-byte swizzle atom: +32 B per step
-                        ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
-                    ptx::mma_commit(&empty[stage]);
-                    if (++stage == C::kStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                for (int k = 0; k < 4; ++k)  // 4 x K=16 inside the 128-byte swizzle atom: +32 B per step
+                    ptx::mma_f16_ss_pred(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0, leader);
+                ptx::mma_commit_pred(&empty[stage], leader);
+                if (++stage == C::kStages) {
+                    stage = 0;
+                    phase ^= 1;
                 }
-                ptx::mma_commit(&tfull[acc]);
-                acc_phase[acc] ^= 1;
-                acc ^= 1;
             }
+            ptx::mma_commit_pred(&tfull[acc], leader);
+            if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+            acc ^= 1;
         }
+        __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp handles (fp16 / f32 paths)
         const int segw = 32 / p.th;
         const int dh = lane / segw;
         const int dw = lane - dh * segw;
+        const float* s_bias = s_vec;
+        const float* s_scale = s_vec + p.cout_pad;
+        const float* s_shift = s_vec + 2 * p.cout_pad;
+        const bool has_affine = p.post_scale != nullptr;
         int acc = 0;
         uint32_t acc_phase[2] = {0, 0};
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -182,6 +196,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(&tfull[acc], acc_phase[acc]);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+            const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
 
             if (p.epi == EPI_ACT_F16) {
                 const bool writer = valid && (dh % p.pool_h == 0) && (dw % p.pool_w == 0);
@@ -189,33 +204,51 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int Hp = p.h_out / p.pool_h, Wp = p.w_out / p.pool_w;
                 __half* orow = p.out_h + (static_cast<size_t>(sc.img) * Hp * Wp + static_cast<size_t>(hp) * Wp + wp) *
                                              p.out_cstride;
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     const int n0 = nt * BN + c0;
                     if (n0 >= p.cout) break;  // warp-uniform
                     uint32_t r[32];
                     ptx::tmem_ld_32x32b_x32(t_addr + c0, r);
                     ptx::tmem_ld_wait();
-                    uint32_t ph[16], pl[16];
+                    // max-pool first (bias + monotone activation commute with max), then bias/act once
+                    if (p.pool_w == 2) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float v[2];
+                        for (int j = 0; j < 32; ++j)
+                            r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]),
+                                                         __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 1)));
+                    }
+                    if (p.pool_h == 2) {
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            float x = __uint_as_float(r[j + e]) + (p.bias ? __ldg(p.bias + n0 + j + e) : 0.f);
-                            x = apply_act(x, p.act);
-                            if (p.pool_w == 2) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-                            if (p.pool_h == 2) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, segw));
-                            if (p.post_scale)
-                                x = x * __ldg(p.post_scale + n0 + j + e) + __ldg(p.post_shift + n0 + j + e);
-                            v[e] = x;
-                        }
-                        const __half2 h2 = __floats2half2_rn(v[0], v[1]);
-                        const float2 hf = __half22float2(h2);
-                        const __half2 l2 = __floats2half2_rn(v[0] - hf.x, v[1] - hf.y);
-                        ph[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                        pl[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                        for (int j = 0; j < 32; ++j)
+                            r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]),
+                                                         __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), segw)));
                     }
                     if (writer) {
+                        uint32_t ph[16], pl[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+                            float v[4] = {__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
+                                          __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act);
+                            if (has_affine) {
+                                const float4 a4 = *reinterpret_cast<const float4*>(s_scale + n0 + j);
+                                const float4 s4 = *reinterpret_cast<const float4*>(s_shift + n0 + j);
+                                v[0] = fmaf(v[0], a4.x, s4.x); v[1] = fmaf(v[1], a4.y, s4.y);
+                                v[2] = fmaf(v[2], a4.z, s4.z); v[3] = fmaf(v[3], a4.w, s4.w);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                const __half2 h2 = __floats2half2_rn(v[e], v[e + 1]);
+                                ph[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                                if (p.out_lo_off >= 0) {
+                                    const float2 hf = __half22float2(h2);
+                                    const __half2 l2 = __floats2half2_rn(v[e] - hf.x, v[e + 1] - hf.y);
+                                    pl[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                                }
+                            }
+                        }
                         uint4* dst = reinterpret_cast<uint4*>(orow + n0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -229,6 +262,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             } else if (p.epi == EPI_CTC) {
+              if (half == 0) {
                 // one frame per thread: running first-max argmax (torch.argmax: NaN counts as maximal),
                 // online logsumexp
                 const size_t pix = (static_cast<size_t>(sc.img) * p.h_out + ho) * p.w_out + wo;
@@ -244,7 +278,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int j = 0; j < 32; ++j) {
                         const int n = c0 + j;
                         if (n < p.cout) {
-                            const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                            const float v = __uint_as_float(r[j]) + s_bias[n];
                             r[j] = __float_as_uint(v);
                             if (!best_nan) {
                                 if (v != v) {
@@ -298,7 +332,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int j = 0; j < 32; ++j) {
                             const int n = c0 + j;
                             if (n < p.cout) {
-                                const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                                const float v = __uint_as_float(r[j]) + s_bias[n];
                                 const float e = __expf(v - run_m);
                                 if (e < thr || v == 0.f) ++dropped;
                                 else kept += e;
@@ -308,9 +342,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     kept += dropped * __expf(-80.f - run_m);
                     if (valid) p.fprob[pix] = __expf(best_v - run_m) / kept;
                 }
+              }
             } else {  // EPI_F32 / EPI_RES_F32
                 const size_t pix = (static_cast<size_t>(sc.img) * p.h_out + ho) * p.w_out + wo;
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     const int n0 = nt * BN + c0;
                     if (n0 >= p.cout) break;
                     uint32_t r[32];
@@ -325,8 +360,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if (n0 + j < p.cout) {
                                     float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                                    if (p.bias) {
-                                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                                    {
+                                        const float4 b = *reinterpret_cast<const float4*>(s_bias + n0 + j);
                                         v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                                     }
                                     v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
@@ -342,7 +377,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 if (n0 + j < p.cout) {
-                                    float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+                                    float v = __uint_as_float(r[j]) + s_bias[n0 + j];
                                     v = apply_act(v, p.act);
                                     if (res) v += __ldg(res + j);
                                     dst[j] = v;
@@ -375,14 +410,16 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::kSmemBytes);
+                                             227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float);
+    if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
     const int total_tiles = p.m_tiles * p.tiles_n;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    igemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+    igemm_tc_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 

@@ -14,18 +14,17 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 
 // ------------------------------------------------------------------------------------------------ first conv
 // One CTA = 128 consecutive output pixels of one image row.  The 3 x 130 x 3 input patch is staged in shared
-// memory as fp32 (x / 255, zero outside the image), each thread computes one pixel x 64 channels in fp32 and the
-// fp16 (hi | lo) pixel records are written back through shared memory so global stores are fully coalesced.
+// memory as fp32 (x / 255, zero outside the image); each thread computes one pixel x COUT channels in fp32
+// (weights broadcast from shared memory as float4) and stores its fp16 (hi | lo) pixel record with 16-byte stores.
 constexpr int CF_PX = 128;
 
+template <int COUT>
 __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                           const float* __restrict__ w_t, const float* __restrict__ bias,
-                                                          int cout, int act, int planes, __half* __restrict__ out) {
+                                                          int act, int planes, __half* __restrict__ out) {
     __shared__ float s_in[3][CF_PX + 2][3];
-    __shared__ float s_w[27 * 64];
-    __shared__ float s_b[64];
-    extern __shared__ __align__(16) unsigned char s_dyn[];  // [CF_PX][planes*cout] fp16 staging
-    __half* s_out = reinterpret_cast<__half*>(s_dyn);
+    __shared__ __align__(16) float s_w[27 * COUT];
+    __shared__ __align__(16) float s_b[COUT];
 
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
     const int tw = blockIdx.x % tiles_w;
@@ -33,8 +32,8 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
     const int img = blockIdx.x / (tiles_w * h);
     const int w0 = tw * CF_PX;
 
-    for (int i = threadIdx.x; i < 27 * cout; i += CF_PX) s_w[i] = w_t[i];
-    for (int i = threadIdx.x; i < cout; i += CF_PX) s_b[i] = bias ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 27 * COUT; i += CF_PX) s_w[i] = w_t[i];
+    for (int i = threadIdx.x; i < COUT; i += CF_PX) s_b[i] = bias ? bias[i] : 0.f;
     for (int i = threadIdx.x; i < 3 * (CF_PX + 2) * 3; i += CF_PX) {
         const int c = i % 3;
         const int x = (i / 3) % (CF_PX + 2);
@@ -47,10 +46,10 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
     }
     __syncthreads();
 
-    float acc[64];
+    float acc[COUT];
 #pragma unroll
-    for (int o = 0; o < 64; ++o) acc[o] = 0.f;
-    // PyTorch weight [cout][c][r][s]; w_t index ((r*3+s)*3+c)*cout + o
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    // PyTorch weight [cout][c][r][s]; w_t index ((r*3+s)*3+c)*COUT + o
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -58,29 +57,35 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float x = s_in[r][threadIdx.x + s][c];
-                const float* wr = &s_w[((r * 3 + s) * 3 + c) * cout];
+                const float4* wr = reinterpret_cast<const float4*>(&s_w[((r * 3 + s) * 3 + c) * COUT]);
 #pragma unroll
-                for (int o = 0; o < 64; ++o)
-                    if (o < cout) acc[o] = fmaf(x, wr[o], acc[o]);
+                for (int o = 0; o < COUT / 4; ++o) {
+                    const float4 wv = wr[o];
+                    acc[4 * o + 0] = fmaf(x, wv.x, acc[4 * o + 0]);
+                    acc[4 * o + 1] = fmaf(x, wv.y, acc[4 * o + 1]);
+                    acc[4 * o + 2] = fmaf(x, wv.z, acc[4 * o + 2]);
+                    acc[4 * o + 3] = fmaf(x, wv.w, acc[4 * o + 3]);
+                }
             }
-    const int rec = planes * cout;
-    __half* my = s_out + threadIdx.x * rec;
+    if (w0 + static_cast<int>(threadIdx.x) >= w) return;
+    const int rec = planes * COUT;
+    __half* dst = out + ((static_cast<size_t>(img) * h + row) * w + w0 + threadIdx.x) * rec;
 #pragma unroll
-    for (int o = 0; o < 64; ++o) {
-        if (o < cout) {
-            const float v = act_fn(acc[o] + s_b[o], act);
-            const __half hi = __float2half_rn(v);
-            my[o] = hi;
-            if (planes == 2) my[cout + o] = __float2half_rn(v - __half2float(hi));
+    for (int o = 0; o < COUT; o += 8) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const float v0 = act_fn(acc[o + e] + s_b[o + e], act);
+            const float v1 = act_fn(acc[o + e + 1] + s_b[o + e + 1], act);
+            const __half2 h2 = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
         }
+        *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (planes == 2) *reinterpret_cast<uint4*>(dst + COUT + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
-    __syncthreads();
-    const int npx = min(CF_PX, w - w0);
-    const size_t base = ((static_cast<size_t>(img) * h + row) * w + w0) * rec;
-    const int total16 = npx * rec / 8;  // uint4 = 8 halves; rec is a multiple of 8
-    const uint4* src = reinterpret_cast<const uint4*>(s_out);
-    uint4* dst = reinterpret_cast<uint4*>(out + base);
-    for (int i = threadIdx.x; i < total16; i += CF_PX) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------ frame stats
@@ -396,10 +401,14 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
 
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
                               int act, int planes, __half* out, cudaStream_t stream) {
-    if (cout > 64 || (cout * planes) % 8) return cudaErrorInvalidValue;
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
-    const size_t dyn = static_cast<size_t>(CF_PX) * planes * cout * sizeof(__half);
-    conv_first_kernel<<<n * h * tiles_w, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, cout, act, planes, out);
+    const int grid = n * h * tiles_w;
+    switch (cout) {
+        case 64: conv_first_kernel<64><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        case 32: conv_first_kernel<32><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        case 16: conv_first_kernel<16><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

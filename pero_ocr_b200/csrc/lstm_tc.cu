@@ -23,11 +23,12 @@ constexpr int kH = 256;          // hidden units per direction
 constexpr int kCl = 8;           // CTAs per cluster
 constexpr int kUnits = kH / kCl; // 32 hidden units per CTA
 constexpr int kLines = 32;       // lines per cluster (MMA N)
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kWPlane = 128 * kH * 2;        // 64 KB: 4 K-chunks of [128 rows][64 fp16]
 constexpr int kHPlane = kLines * kH * 2;     // 16 KB: [k/8][n/8][n%8][k%8]
 constexpr int kSliceBytes = kUnits * kLines * 2;  // 2 KB: this CTA's k range inside a B plane
 constexpr int kGStride = 33;
+constexpr int kAccs = 4;          // independent TMEM accumulators (K split) so dependent MMAs do not serialise
 
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -48,12 +49,13 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
     asm volatile("mov.u32 %0, %%clusterid.x;\n" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
-                                                  uint32_t mbar_cluster_addr) {
+__device__ __forceinline__ void bulk_copy_to_peer_pred(uint32_t dst_cluster_addr, uint32_t src_cta_addr,
+                                                       uint32_t bytes, uint32_t mbar_cluster_addr, uint32_t pred) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+        "@q cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n" ::"r"(
             dst_cluster_addr),
-        "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+        "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr), "r"(pred)
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -68,12 +70,12 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t addr, uint32_t lbo, 
     d |= static_cast<uint64_t>(1) << 46;
     return d;
 }
-__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_(float x) {
     // tanh(x) = 1 - 2 / (exp(2x) + 1): full fp32 accuracy up to the __expf error (2 ulp), no cancellation blow-up
     // for |x| >~ 1e-2; below that the relative error of the result is still < 1e-5.
     const float e = __expf(2.f * x);
-    return 1.f - 2.f / (e + 1.f);
+    return 1.f - 2.f * __fdividef(1.f, e + 1.f);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -105,7 +107,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
         ptx::mbar_init(mma_done, 1);
         ptx::fence_mbar_init();
     }
-    if (warp == 0) ptx::tmem_alloc<32>(tmem_slot);
+    if (warp == 0) ptx::tmem_alloc<kAccs * kLines>(tmem_slot);
     // h_{-1} = 0: zero both B buffers
     for (int i = tid; i < 2 * planes * kHPlane / 16; i += kThreads)
         reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
@@ -124,77 +126,92 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
                                  ((dir * planes + pl) * kCl + rank) * 128);
     }
 
-    // epilogue-2 role of this thread: line nl, units [8*ug, 8*ug+8) of this CTA's 32
-    const int nl = tid >> 2, ug = tid & 3;
+    // epilogue-2 role of this thread: line nl, units [4*ug, 4*ug+4) of this CTA's 32
+    const int nl = tid >> 3, ug = tid & 7;
     const int line = line0 + nl;
     const bool line_ok = line < n_lines;
-    const int unit0 = rank * kUnits + ug * 8;  // hidden-unit index within the direction
-    float c_state[8];
+    const int unit0 = rank * kUnits + ug * 4;  // hidden-unit index within the direction
+    float c_state[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) c_state[e] = 0.f;
-    const uint32_t slice_off = (rank * 4 + ug) * 512 + (nl >> 3) * 128 + (nl & 7) * 16;  // inside a B plane
+    for (int e = 0; e < 4; ++e) c_state[e] = 0.f;
+    // byte offset of (line nl, units unit0..unit0+3) inside a B plane: [k/8][n/8][n%8][k%8]
+    const uint32_t slice_off = (rank * 4 + (ug >> 1)) * 512 + (nl >> 3) * 128 + (nl & 7) * 16 + (ug & 1) * 8;
+    const uint32_t leader = (warp == 0 && ptx::elect_one()) ? 1u : 0u;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
     ptx::mbar_wait(wfull, 0);
-    uint32_t hphase[2] = {0, 0};
+    uint32_t hphase0 = 0, hphase1 = 0;
     uint32_t mphase = 0;
 
     for (int s = 0; s < T; ++s) {
         const int t = dir ? (T - 1 - s) : s;
         const int b = s & 1, nb = b ^ 1;
-        // prefetch this step's pre-gates (i,f,g,o x 8 units) while the MMA runs
-        float pg[4][8];
+        // prefetch this step's pre-gates (i,f,g,o x 4 units) while the MMA runs
+        float pg[4][4];
         const size_t row = static_cast<size_t>(line_ok ? line : 0) * T + t;
         {
             const float* pr = pre + row * (8 * kH) + dir * 4 * kH + unit0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (line_ok) {
-                    v0 = __ldg(reinterpret_cast<const float4*>(pr + g * kH));
-                    v1 = __ldg(reinterpret_cast<const float4*>(pr + g * kH + 4));
-                }
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (line_ok) v0 = __ldg(reinterpret_cast<const float4*>(pr + g * kH));
                 pg[g][0] = v0.x; pg[g][1] = v0.y; pg[g][2] = v0.z; pg[g][3] = v0.w;
-                pg[g][4] = v1.x; pg[g][5] = v1.y; pg[g][6] = v1.z; pg[g][7] = v1.w;
             }
         }
         if (s > 0) {
-            if (tid == 0) {
-                ptx::mbar_wait(&hfull[b], hphase[b]);
-                hphase[b] ^= 1;
+            if (warp == 0) {  // whole warp runs the uniform issue code; one elected lane issues
+                ptx::mbar_wait(b ? &hfull[1] : &hfull[0], b ? hphase1 : hphase0);
+                if (b) hphase1 ^= 1; else hphase0 ^= 1;
                 ptx::tc_fence_after();
                 constexpr uint32_t idesc = ptx::idesc_f16_f32(128, kLines);
+                const uint32_t w_base = ptx::smem_u32(sW);
+                const uint32_t h_base = ptx::smem_u32(sH) + b * planes * kHPlane;
                 for (int pass = 0; pass < npass; ++pass) {
-                    const int pw = (pass == 2) ? 1 : 0;  // W plane
-                    const int ph = (pass == 1) ? 1 : 0;  // h plane
-                    const uint32_t wa = ptx::smem_u32(sW + pw * kWPlane);
-                    const uint32_t ha = ptx::smem_u32(sH + (b * planes + ph) * kHPlane);
+                    const uint32_t wa = w_base + ((pass == 2) ? kWPlane : 0);   // W plane
+                    const uint32_t ha = h_base + ((pass == 1) ? kHPlane : 0);   // h plane
 #pragma unroll
                     for (int k16 = 0; k16 < 16; ++k16) {
                         const uint64_t a_desc = ptx::smem_desc_sw128(wa + (k16 >> 2) * 16384) + 2 * (k16 & 3);
                         const uint64_t b_desc = smem_desc_nosw(ha + k16 * 2 * 512, 512, 128);
-                        ptx::mma_f16_ss(tmem_base, a_desc, b_desc, idesc, (pass | k16) != 0);
+                        ptx::mma_f16_ss_pred(tmem_u + (k16 & (kAccs - 1)) * kLines, a_desc, b_desc, idesc,
+                                             (pass != 0 || k16 >= kAccs) ? 1u : 0u, leader);
                     }
                 }
-                ptx::mma_commit(mma_done);
+                ptx::mma_commit_pred(mma_done, leader);
             }
             ptx::mbar_wait(mma_done, mphase);
             mphase ^= 1;
             ptx::tc_fence_after();
-            // phase 1: TMEM lane = gate row (warp = gate type, lane = unit), column = line
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), r);
-            ptx::tmem_ld_wait();
-            float* g_row = sG + (warp * 32 + lane) * kGStride;
+            // phase 1: TMEM lane = gate row (lane quarter = gate type, lane = unit), column = line;
+            // warps 0-3 take lines 0-15, warps 4-7 lines 16-31
+            const int q = warp & 3, half = warp >> 2;
+            float sum[16];
+            {
+                uint32_t r[16];
+                ptx::tmem_ld_32x32b_x16(tmem_u + (static_cast<uint32_t>(q * 32) << 16) + half * 16, r);
+                ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g_row[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(r[j]);
+            }
+#pragma unroll
+            for (int a = 1; a < kAccs; ++a) {
+                uint32_t r[16];
+                ptx::tmem_ld_32x32b_x16(tmem_u + (static_cast<uint32_t>(q * 32) << 16) + a * kLines + half * 16, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(r[j]);
+            }
+            float* g_row = sG + (q * 32 + lane) * kGStride + half * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g_row[j] = sum[j];
             ptx::tc_fence_before();
         }
         __syncthreads();
-        // phase 2: gates for (line nl, units 8ug..8ug+7)
-        float hv[8];
+        // phase 2: gates for (line nl, units 4ug..4ug+3)
+        float hv[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int u = ug * 8 + e;
+        for (int e = 0; e < 4; ++e) {
+            const int u = ug * 4 + e;
             float gi = pg[0][e], gf = pg[1][e], gg = pg[2][e], go = pg[3][e];
             if (s > 0) {
                 gi += sG[(0 * 32 + u) * kGStride + nl];
@@ -206,9 +223,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
             c_state[e] = fg * c_state[e] + ig * cg;
             hv[e] = og * tanh_(c_state[e]);
         }
-        uint32_t hi_w[4], lo_w[4];
+        uint32_t hi_w[2], lo_w[2];
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
+        for (int e = 0; e < 4; e += 2) {
             const __half2 h2 = __floats2half2_rn(hv[e], hv[e + 1]);
             const float2 hf = __half22float2(h2);
             const __half2 l2 = __floats2half2_rn(hv[e] - hf.x, hv[e + 1] - hf.y);
@@ -217,24 +234,25 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
         }
         if (line_ok) {
             __half* o = out + row * (planes * 2 * kH) + dir * kH + unit0;
-            *reinterpret_cast<uint4*>(o) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
-            if (planes == 2) *reinterpret_cast<uint4*>(o + 2 * kH) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+            *reinterpret_cast<uint2*>(o) = make_uint2(hi_w[0], hi_w[1]);
+            if (planes == 2) *reinterpret_cast<uint2*>(o + 2 * kH) = make_uint2(lo_w[0], lo_w[1]);
         }
         if (s + 1 < T) {
             uint8_t* hb = sH + nb * planes * kHPlane;
-            *reinterpret_cast<uint4*>(hb + slice_off) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
-            if (planes == 2)
-                *reinterpret_cast<uint4*>(hb + kHPlane + slice_off) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+            *reinterpret_cast<uint2*>(hb + slice_off) = make_uint2(hi_w[0], hi_w[1]);
+            if (planes == 2) *reinterpret_cast<uint2*>(hb + kHPlane + slice_off) = make_uint2(lo_w[0], lo_w[1]);
             fence_proxy_async_smem();
             __syncthreads();
-            if (tid == 0) {
-                ptx::mbar_expect_tx(&hfull[nb], (kCl - 1) * planes * kSliceBytes);
+            if (warp == 0) {
+                uint64_t* hbar = nb ? &hfull[1] : &hfull[0];
+                ptx::mbar_expect_tx_pred(hbar, (kCl - 1) * planes * kSliceBytes, leader);
+                const uint32_t bar = ptx::smem_u32(hbar);
                 for (int pl = 0; pl < planes; ++pl) {
                     const uint32_t src = ptx::smem_u32(hb + pl * kHPlane + rank * kSliceBytes);
-                    const uint32_t bar = ptx::smem_u32(&hfull[nb]);
-                    for (uint32_t peer = 0; peer < kCl; ++peer) {
-                        if (peer == rank) continue;
-                        bulk_copy_to_peer(mapa(src, peer), src, kSliceBytes, mapa(bar, peer));
+#pragma unroll
+                    for (uint32_t d = 1; d < kCl; ++d) {
+                        const uint32_t peer = (rank + d) & (kCl - 1);
+                        bulk_copy_to_peer_pred(mapa(src, peer), src, kSliceBytes, mapa(bar, peer), leader);
                     }
                 }
             }
@@ -245,7 +263,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     cluster_sync_all();  // nobody leaves while a peer may still push into its shared memory
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<32>(tmem_base);
+        ptx::tmem_dealloc<kAccs * kLines>(tmem_u);
     }
 }
 

@@ -123,6 +123,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // K-major operand tile in the canonical 128-byte-swizzled layout (rows of 64 fp16 = 128 B, 8-row groups 1024 B apart):
@@ -143,6 +152,52 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+
+// ---------------------------------------------------------------- predicated single-issue forms
+// Executed by ALL lanes of a converged warp with warp-uniform operands (so ptxas keeps them in uniform registers
+// and emits no per-instruction R2UR); `pred` is non-zero in exactly one lane (elect_one()).
+__device__ __forceinline__ void mbar_expect_tx_pred(uint64_t* bar, uint32_t bytes, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(bytes), "r"(pred)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pred(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(pred)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pred(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pred(uint64_t* bar, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(pred)
+        : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
