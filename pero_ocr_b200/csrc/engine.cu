@@ -367,7 +367,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                         CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->planes, e->planes == 1, o, st));
                     } else {
                         ProfScope ps(e, st, PROF_LSTM);
-                        CU_TRY(e, launch_lstm_tc(ly.tmW, eo.out_f32, o, cur.n, T, H, e->planes, st));
+                        CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->planes, st));
                     }
                     e->launches++;
                     cur_h = o;

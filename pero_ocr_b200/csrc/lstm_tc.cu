@@ -6,14 +6,17 @@
 //
 // One thread-block cluster of 8 CTAs owns 32 lines of one direction for all T steps:
 //   * CTA j keeps the W_hh rows of hidden units [32j, 32j+32) (4 gates x 32 units = 128 rows x K=256, fp16 hi
-//     (+lo)) resident in shared memory for the whole kernel -- loaded once by TMA, 128B-swizzled, operand A;
+//     (+lo)) resident in TENSOR MEMORY for the whole kernel (tcgen05.st once; 128 columns per plane) as operand A
+//     of TS-mode MMAs -- with N = 32 an A operand in shared memory would make every MMA pay a 4 KB smem fetch;
 //   * h_{t-1} of the 32 lines (N=32 x K=256, fp16 hi (+lo)) is operand B in the no-swizzle core-matrix layout,
 //     double-buffered; one elected thread issues the 16 (x3) tcgen05.mma (M=128,N=32,K=16) of the step into TMEM;
 //   * epilogue: tcgen05.ld -> shared-memory transpose so that one thread holds i,f,g,o of (line, 8 units),
 //     gates + cell update in fp32 (cell state lives in registers for all T steps), h_t is written to HBM (fp16
-//     hi|lo, next layer's GEMM operand) and into the CTA's own slice of the next B buffer, which is then pushed to
-//     the 7 peer CTAs with cp.async.bulk (shared::cta -> shared::cluster) completing on the peers' mbarriers:
-//     no cluster-wide barrier inside the time loop.
+//     hi|lo, next layer's GEMM operand) and into the CTA's own slice of the next B buffer (hi and lo planes of a
+//     slice contiguous), which is then pushed to the 7 peer CTAs with ONE cp.async.bulk (shared::cta ->
+//     shared::cluster) each, completing on the peers' mbarriers: no cluster-wide barrier inside the time loop.
+//     (Measured alternatives: plain st.shared::cluster stores + remote mbarrier arrives were 2x slower; separate
+//     copies per plane doubled the step time -- a bulk push costs ~0.5 us and pushes serialise.)
 #include "lstm_tc.cuh"
 #include "ptx.cuh"
 
@@ -24,11 +27,12 @@ constexpr int kCl = 8;           // CTAs per cluster
 constexpr int kUnits = kH / kCl; // 32 hidden units per CTA
 constexpr int kLines = 32;       // lines per cluster (MMA N)
 constexpr int kThreads = 256;
-constexpr int kWPlane = 128 * kH * 2;        // 64 KB: 4 K-chunks of [128 rows][64 fp16]
-constexpr int kHPlane = kLines * kH * 2;     // 16 KB: [k/8][n/8][n%8][k%8]
-constexpr int kSliceBytes = kUnits * kLines * 2;  // 2 KB: this CTA's k range inside a B plane
+constexpr int kHPlane = kLines * kH * 2;     // 16 KB per plane; a B buffer is [slice j][plane][k/8 - 4j][n/8][n%8][k%8]
+constexpr int kSliceBytes = kUnits * kLines * 2;  // 2 KB: one CTA's k range of one plane
 constexpr int kGStride = 33;
-constexpr int kAccs = 4;          // independent TMEM accumulators (K split) so dependent MMAs do not serialise
+constexpr int kAccs = 4;          // K split over independent TMEM accumulators (summed in the epilogue)
+constexpr int kWCol0 = 128;       // TMEM column of W plane 0 (plane p at kWCol0 + 128 p); accumulator at column 0
+constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -79,12 +83,11 @@ __device__ __forceinline__ float tanh_(float x) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ pre, __half* __restrict__ out,
+lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, __half* __restrict__ out,
                int n_lines, int T, int planes, int line_groups) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sW = smem;                                  // planes * 64 KB
-    uint8_t* sH = sW + planes * kWPlane;                 // 2 buffers * planes * 16 KB
+    uint8_t* sH = smem;                                  // 2 buffers * planes * 16 KB
     float* sG = reinterpret_cast<float*>(sH + 2 * planes * kHPlane);   // [128][33]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 128 * kGStride);
     uint64_t* wfull = bars;
@@ -100,14 +103,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     const int npass = planes == 2 ? 3 : 1;
 
     if (tid == 0) {
-        ptx::prefetch_tmap(&tmW);
         ptx::mbar_init(wfull, 1);
         ptx::mbar_init(&hfull[0], 1);
         ptx::mbar_init(&hfull[1], 1);
         ptx::mbar_init(mma_done, 1);
         ptx::fence_mbar_init();
     }
-    if (warp == 0) ptx::tmem_alloc<kAccs * kLines>(tmem_slot);
+    if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
     // h_{-1} = 0: zero both B buffers
     for (int i = tid; i < 2 * planes * kHPlane / 16; i += kThreads)
         reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
@@ -118,12 +120,30 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     cluster_sync_all();  // peers' barriers are initialised before anybody signals them
     const uint32_t tmem_base = *tmem_slot;
 
-    if (tid == 0) {
-        ptx::mbar_expect_tx(wfull, planes * kWPlane);
-        for (int pl = 0; pl < planes; ++pl)
-            for (int kc = 0; kc < 4; ++kc)
-                ptx::tma_load_2d(sW + pl * kWPlane + kc * 16384, &tmW, wfull, kc * 64,
-                                 ((dir * planes + pl) * kCl + rank) * 128);
+    // W_hh slice -> TMEM: thread (row = lane quarter * 32 + lane, plane = warp / 4) copies its 256-element row
+    // (512 B, packed k-pairs = 128 32-bit columns).
+    {
+        const int pl = warp >> 2;
+        if (pl < planes) {
+            const int rowi = (warp & 3) * 32 + lane;
+            const uint4* src = reinterpret_cast<const uint4*>(
+                w_rec + ((static_cast<size_t>(dir * planes + pl) * kCl + rank) * 128 + rowi) * kH);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kWCol0 + pl * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const uint4 x = __ldg(src + c * 8 + v);
+                    r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                }
+                ptx::tmem_st_32x32b_x32(taddr + c * 32, r);
+            }
+            ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        ptx::tc_fence_after();
     }
 
     // epilogue-2 role of this thread: line nl, units [4*ug, 4*ug+4) of this CTA's 32
@@ -134,12 +154,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     float c_state[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) c_state[e] = 0.f;
-    // byte offset of (line nl, units unit0..unit0+3) inside a B plane: [k/8][n/8][n%8][k%8]
-    const uint32_t slice_off = (rank * 4 + (ug >> 1)) * 512 + (nl >> 3) * 128 + (nl & 7) * 16 + (ug & 1) * 8;
+    // byte offset of (line nl, units unit0..unit0+3) of plane 0 inside a B buffer (plane 1 at + kSliceBytes)
+    const uint32_t slice_off = rank * planes * kSliceBytes + (ug >> 1) * 512 + (nl >> 3) * 128 + (nl & 7) * 16 + (ug & 1) * 8;
     const uint32_t leader = (warp == 0 && ptx::elect_one()) ? 1u : 0u;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-    ptx::mbar_wait(wfull, 0);
     uint32_t hphase0 = 0, hphase1 = 0;
     uint32_t mphase = 0;
 
@@ -164,16 +183,15 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
                 if (b) hphase1 ^= 1; else hphase0 ^= 1;
                 ptx::tc_fence_after();
                 constexpr uint32_t idesc = ptx::idesc_f16_f32(128, kLines);
-                const uint32_t w_base = ptx::smem_u32(sW);
                 const uint32_t h_base = ptx::smem_u32(sH) + b * planes * kHPlane;
                 for (int pass = 0; pass < npass; ++pass) {
-                    const uint32_t wa = w_base + ((pass == 2) ? kWPlane : 0);   // W plane
-                    const uint32_t ha = h_base + ((pass == 1) ? kHPlane : 0);   // h plane
+                    const uint32_t wa = tmem_u + kWCol0 + ((pass == 2) ? 128 : 0);   // W plane (TMEM columns)
+                    const uint32_t ha = h_base + ((pass == 1) ? kSliceBytes : 0);   // h plane inside each slice block
 #pragma unroll
                     for (int k16 = 0; k16 < 16; ++k16) {
-                        const uint64_t a_desc = ptx::smem_desc_sw128(wa + (k16 >> 2) * 16384) + 2 * (k16 & 3);
-                        const uint64_t b_desc = smem_desc_nosw(ha + k16 * 2 * 512, 512, 128);
-                        ptx::mma_f16_ss_pred(tmem_u + (k16 & (kAccs - 1)) * kLines, a_desc, b_desc, idesc,
+                        const uint64_t b_desc =
+                            smem_desc_nosw(ha + (k16 >> 1) * planes * kSliceBytes + (k16 & 1) * 1024, 512, 128);
+                        ptx::mma_f16_ts_pred(tmem_u + (k16 & (kAccs - 1)) * kLines, wa + k16 * 8, b_desc, idesc,
                                              (pass != 0 || k16 >= kAccs) ? 1u : 0u, leader);
                     }
                 }
@@ -238,22 +256,23 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
             if (planes == 2) *reinterpret_cast<uint2*>(o + 2 * kH) = make_uint2(lo_w[0], lo_w[1]);
         }
         if (s + 1 < T) {
+            // own slice (hi | lo contiguous) of the next B buffer, then ONE bulk push per peer: a cp.async.bulk
+            // shared::cta -> shared::cluster costs ~0.5 us and they serialise, so planes share a copy
             uint8_t* hb = sH + nb * planes * kHPlane;
             *reinterpret_cast<uint2*>(hb + slice_off) = make_uint2(hi_w[0], hi_w[1]);
-            if (planes == 2) *reinterpret_cast<uint2*>(hb + kHPlane + slice_off) = make_uint2(lo_w[0], lo_w[1]);
+            if (planes == 2) *reinterpret_cast<uint2*>(hb + slice_off + kSliceBytes) = make_uint2(lo_w[0], lo_w[1]);
             fence_proxy_async_smem();
             __syncthreads();
             if (warp == 0) {
                 uint64_t* hbar = nb ? &hfull[1] : &hfull[0];
-                ptx::mbar_expect_tx_pred(hbar, (kCl - 1) * planes * kSliceBytes, leader);
+                const uint32_t bytes = planes * kSliceBytes;
+                ptx::mbar_expect_tx_pred(hbar, (kCl - 1) * bytes, leader);
                 const uint32_t bar = ptx::smem_u32(hbar);
-                for (int pl = 0; pl < planes; ++pl) {
-                    const uint32_t src = ptx::smem_u32(hb + pl * kHPlane + rank * kSliceBytes);
+                const uint32_t src = ptx::smem_u32(hb + rank * bytes);
 #pragma unroll
-                    for (uint32_t d = 1; d < kCl; ++d) {
-                        const uint32_t peer = (rank + d) & (kCl - 1);
-                        bulk_copy_to_peer_pred(mapa(src, peer), src, kSliceBytes, mapa(bar, peer), leader);
-                    }
+                for (uint32_t d = 1; d < kCl; ++d) {
+                    const uint32_t peer = (rank + d) & (kCl - 1);
+                    bulk_copy_to_peer_pred(mapa(src, peer), src, bytes, mapa(bar, peer), leader);
                 }
             }
         }
@@ -263,18 +282,18 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict_
     cluster_sync_all();  // nobody leaves while a peer may still push into its shared memory
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<kAccs * kLines>(tmem_u);
+        ptx::tmem_dealloc<kTmemCols>(tmem_u);
     }
 }
 
 }  // namespace
 
 size_t lstm_tc_smem_bytes(int planes) {
-    return static_cast<size_t>(planes) * kWPlane + 2 * static_cast<size_t>(planes) * kHPlane +
+    return 2 * static_cast<size_t>(planes) * kHPlane +
            128 * kGStride * sizeof(float) + 64 + 1024;
 }
 
-cudaError_t launch_lstm_tc(const CUtensorMap& tmW, const float* pre, __half* out, int n_lines, int T, int H, int planes,
+cudaError_t launch_lstm_tc(const __half* w_rec, const float* pre, __half* out, int n_lines, int T, int H, int planes,
                            cudaStream_t stream) {
     if (H != kH) return cudaErrorInvalidValue;
     const size_t smem = lstm_tc_smem_bytes(planes);
@@ -297,5 +316,5 @@ cudaError_t launch_lstm_tc(const CUtensorMap& tmW, const float* pre, __half* out
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, lstm_tc_kernel, tmW, pre, out, n_lines, T, planes, line_groups);
+    return cudaLaunchKernelEx(&cfg, lstm_tc_kernel, w_rec, pre, out, n_lines, T, planes, line_groups);
 }

@@ -5,9 +5,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
-// tmW: 2-D map over the packed recurrent weights, fp16 [2 dirs][planes][8 CTAs][128 rows = gate*32 + unit][K = 256],
-//      box (64, 128), 128B swizzle.
+// w_rec: packed recurrent weights, fp16 [2 dirs][planes][8 CTAs][128 rows = gate*32 + unit][K = 256].
 // pre: fp32 [n_lines*T][2*4H] pre-gates; out: fp16 [n_lines*T][planes*2H].
-cudaError_t launch_lstm_tc(const CUtensorMap& tmW, const float* pre, __half* out, int n_lines, int T, int H, int planes,
+cudaError_t launch_lstm_tc(const __half* w_rec, const float* pre, __half* out, int n_lines, int T, int H, int planes,
                            cudaStream_t stream);
 size_t lstm_tc_smem_bytes(int planes);
