@@ -57,6 +57,7 @@ EXPORTS = {
     'b200ocr_profile': (C.c_int, [C.c_void_p, C.c_int32]),
     'b200ocr_profile_read': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_int32)]),
+    'b200ocr_debug_set_flag': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     'b200ocr_debug_use_reference_kernels': (C.c_int, [C.c_void_p, C.c_int32]),
     'b200ocr_debug_forward_prefix': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),

@@ -45,6 +45,8 @@ struct Gemm {  // one dense contraction: packed fp16 weights [plane][tap][cout_p
     float* post_scale = nullptr;
     float* post_shift = nullptr;
     CUtensorMap tmB;
+    int bn_halo = 0;       // tile N of the halo-reuse kernel (0 = not applicable)
+    CUtensorMap tmB_halo;
 };
 
 struct LayerRT {
@@ -71,6 +73,7 @@ struct Shape {
 struct b200ocr_engine {
     int device = 0, num_sms = 148, precision = 0, planes = 1, npass = 1, line_height = 40;
     bool use_ref = false;
+    bool use_halo = true;
     std::vector<LayerRT> layers;
     std::vector<void*> owned;
     // workspace
@@ -155,12 +158,13 @@ int make_map_2d(b200ocr_engine* e, CUtensorMap* m, const void* base, uint64_t in
     return 0;
 }
 
-int make_map_act(b200ocr_engine* e, CUtensorMap* m, const void* base, int n, int h, int w, int c_total, int th) {
+int make_map_act(b200ocr_engine* e, CUtensorMap* m, const void* base, int n, int h, int w, int c_total, int box_w,
+                 int box_h) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)c_total, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c_total * 2, (cuuint64_t)w * c_total * 2, (cuuint64_t)h * w * c_total * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(32 / th), (cuuint32_t)th, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -202,6 +206,10 @@ int build_gemm(b200ocr_engine* e, Gemm& g, const float* weight, const float* bia
         std::copy(post_shift, post_shift + cout, b.begin());
         if (int s = upload(e, a.data(), a.size(), &g.post_scale)) return s;
         if (int s = upload(e, b.data(), b.size(), &g.post_shift)) return s;
+    }
+    if (kh == 3 && kw == 3 && pad_h == 1 && pad_w == 1 && cin <= 128 && cout <= 256 && (cout % 32) == 0) {
+        g.bn_halo = cout > 64 ? 128 : 64;
+        if (int s = make_map_2d(e, &g.tmB_halo, g.w, cin, rows, g.bn_halo)) return s;
     }
     return make_map_2d(e, &g.tmB, g.w, cin, rows, g.bn);
 }
@@ -245,7 +253,20 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
         return 0;
     }
     CUtensorMap tmA;
-    if (int s = make_map_act(e, &tmA, in, in_s.n, in_s.h, in_s.w, e->planes * g.cin, p.th)) return s;
+    if (e->use_halo && g.bn_halo) {
+        IgemmParams ph = p;
+        ph.tiles_n = (g.cout + g.bn_halo - 1) / g.bn_halo;
+        if (ph.tiles_n * g.bn_halo == g.cout_pad && igemm_halo_supported(ph, g.bn_halo)) {
+            if (int s = make_map_act(e, &tmA, in, in_s.n, in_s.h, in_s.w, e->planes * g.cin, 130, 4)) return s;
+            {
+                ProfScope ps(e, st, PROF_IGEMM);
+                CU_TRY(e, launch_igemm_halo(ph, tmA, g.tmB_halo, g.bn_halo, e->num_sms, st));
+            }
+            e->launches++;
+            return 0;
+        }
+    }
+    if (int s = make_map_act(e, &tmA, in, in_s.n, in_s.h, in_s.w, e->planes * g.cin, 32 / p.th, p.th)) return s;
     {
         ProfScope ps(e, st, PROF_IGEMM);
         CU_TRY(e, launch_igemm_tc(p, tmA, g.tmB, g.bn, e->num_sms, st));
@@ -809,6 +830,13 @@ int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, i
     }
     for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     e->prof.clear();
+    return B200OCR_OK;
+}
+
+int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
+    if (!e) return B200OCR_E_INVALID;
+    if (flag == 1) e->use_halo = value != 0;
+    else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }
 

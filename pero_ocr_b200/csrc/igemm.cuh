@@ -63,3 +63,9 @@ cudaError_t launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmA, const 
 
 // Naive CUDA-core kernel with identical semantics (debug / cross-check only).
 cudaError_t launch_igemm_ref(const IgemmParams& p, const __half* in, const __half* w_packed, cudaStream_t stream);
+
+// Halo-reuse variant for 3x3 / pad 1 convolutions with cin <= 128 (igemm_halo.cu).  tmA_halo: 4-D map over the
+// input activation with box (64, 130, 4, 1); tmB: 2-D weight map with box (64, bn), bn in {64, 128}.
+bool igemm_halo_supported(const IgemmParams& p, int bn);
+cudaError_t launch_igemm_halo(const IgemmParams& p, const CUtensorMap& tmA_halo, const CUtensorMap& tmB, int bn,
+                              int num_sms, cudaStream_t stream);

@@ -1,0 +1,342 @@
+// tcgen05 3x3 convolution with shared-memory halo reuse, for the wide / shallow layers of the frontend
+// (conv1_2, conv2_1, conv2_2, conv3_1 of the layer list in pero_ocr/ocr_engine/transformer.py:75-148).
+//
+// igemm_tc.cu reloads the activation tile once per filter tap; for 64/128-channel layers that makes the kernel
+// L2->SM-bandwidth bound (profiles/: 9 x re-reads, ~10 TB/s).  Here one CTA computes 2 output rows x 128 output
+// columns and loads the (2+2) x (128+2) pixel halo of a 64-channel chunk ONCE (one 4-D TMA box, 128B swizzle); the
+// nine taps are nine shifted views of that buffer: a K-major swizzle-128B operand is 128 consecutive pixel rows of
+// 128 B, so a tap (r, s) is just a different descriptor start address ((r*130 + s) * 128 B further).  Weights stream
+// through their own ring.  Two accumulators (one per output row) make the 2x2 / 2x1 max-pool a per-thread max
+// plus one shuffle.
+//
+// Warps: 0 = halo (A) producer, 1 = weight (B) producer, 2 = MMA issuer, 3-10 = epilogue (two per TMEM lane quarter).
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kThreads = 352;
+constexpr int kHaloW = 130, kHaloH = 4;
+constexpr int kHaloBytes = kHaloH * kHaloW * 128;             // 66,560
+constexpr int kHaloStage = ((kHaloBytes + 1023) / 1024) * 1024;  // 66,560 -> 66,560 (65 KB) multiple of 1024
+constexpr int kAStages = 2;
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kBStages = BN == 64 ? 8 : 4;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kBarOff = kAStages * kHaloStage + kBStages * kBBytes;
+    static constexpr int kSmemBytes = kBarOff + 256 + 1024;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    return v;
+}
+
+struct Tile {
+    int img, h0, w0, nt;
+};
+
+__device__ __forceinline__ Tile tile_coord(const IgemmParams& p, int tile, int tiles_w, int tiles_h) {
+    Tile t;
+    t.nt = tile % p.tiles_n;
+    int m = tile / p.tiles_n;
+    const int tw = m % tiles_w;
+    m /= tiles_w;
+    t.h0 = (m % tiles_h) * 2;
+    t.img = m / tiles_h;
+    t.w0 = tw * 128;
+    return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const IgemmParams p, int tiles_w, int tiles_h, int total_tiles) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + kAStages * kHaloStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+    uint64_t* a_full = bars;                              // [kAStages]
+    uint64_t* a_empty = a_full + kAStages;                // [kAStages]
+    uint64_t* b_full = a_empty + kAStages;                // [kBStages]
+    uint64_t* b_empty = b_full + C::kBStages;             // [kBStages]
+    uint64_t* tfull = b_empty + C::kBStages;              // [2]
+    uint64_t* tempty = tfull + 2;                         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_vec = reinterpret_cast<float*>(smem + C::kBarOff + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int kchunks = p.cin >> 6;
+    const int planes = p.npass == 3 ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < kAStages; ++i) {
+            ptx::mbar_init(&a_full[i], 1);
+            ptx::mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < C::kBStages; ++i) {
+            ptx::mbar_init(&b_full[i], 1);
+            ptx::mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull[i], 1);
+            ptx::mbar_init(&tempty[i], 8);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
+        s_vec[i] = p.bias ? p.bias[i] : 0.f;
+        s_vec[p.cout_pad + i] = p.post_scale ? p.post_scale[i] : 1.f;
+        s_vec[2 * p.cout_pad + i] = p.post_shift ? p.post_shift[i] : 0.f;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (*tmem_slot != 0) __trap();
+    constexpr uint32_t tmem_base = 0;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ halo (A) producer
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
+            for (int kc = 0; kc < kchunks; ++kc)
+                for (int ap = 0; ap < planes; ++ap) {
+                    ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+                    ptx::mbar_expect_tx_pred(&a_full[stage], kHaloBytes, leader);
+                    ptx::tma_load_4d_pred(sA + stage * kHaloStage, &tmA, &a_full[stage], ap * p.cin + kc * 64,
+                                          t.w0 - 1, t.h0 - 1, t.img, leader);
+                    if (++stage == kAStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ weight (B) producer
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
+            for (int kc = 0; kc < kchunks; ++kc)
+                for (int ap = 0; ap < planes; ++ap) {
+                    const int nbp = (ap == 0) ? planes : 1;   // A_hi meets B_hi (and B_lo); A_lo meets B_hi only
+                    for (int bp = 0; bp < nbp; ++bp)
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(&b_empty[stage], phase ^ 1);
+                            ptx::mbar_expect_tx_pred(&b_full[stage], C::kBBytes, leader);
+                            ptx::tma_load_2d_pred(sB + stage * C::kBBytes, &tmB, &b_full[stage], kc * 64,
+                                                  (bp * 9 + tap) * p.cout_pad + t.nt * BN, leader);
+                            if (++stage == C::kBStages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+        const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
+        int as = 0, bs = 0, acc = 0;
+        uint32_t aph = 0, bph = 0, acc_phase0 = 0, acc_phase1 = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d0 = tmem_base + acc * 2 * BN;
+            uint32_t started = 0;
+            for (int kc = 0; kc < kchunks; ++kc)
+                for (int ap = 0; ap < planes; ++ap) {
+                    ptx::mbar_wait(&a_full[as], aph);
+                    const uint32_t halo = sA_u + as * kHaloStage;
+                    const int nbp = (ap == 0) ? planes : 1;
+                    for (int bp = 0; bp < nbp; ++bp)
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(&b_full[bs], bph);
+                            ptx::tc_fence_after();
+                            const int tr = tap / 3, ts = tap - tr * 3;
+                            const uint64_t b_desc = ptx::smem_desc_sw128(sB_u + bs * C::kBBytes);
+                            if (ptx::elect_one()) {
+#pragma unroll
+                                for (int r = 0; r < 2; ++r) {
+                                    const uint64_t a_desc =
+                                        ptx::smem_desc_sw128(halo + ((r + tr) * kHaloW + ts) * 128);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                                        (started | k) != 0 ? 1u : 0u);
+                                }
+                                ptx::mma_commit(&b_empty[bs]);
+                            }
+                            __syncwarp();
+                            started = 1;
+                            if (++bs == C::kBStages) {
+                                bs = 0;
+                                bph ^= 1;
+                            }
+                        }
+                    if (ptx::elect_one()) ptx::mma_commit(&a_empty[as]);
+                    __syncwarp();
+                    if (++as == kAStages) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                }
+            if (ptx::elect_one()) ptx::mma_commit(&tfull[acc]);
+            __syncwarp();
+            if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+            acc ^= 1;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 3..10)
+        const int q = warp & 3;
+        const int half = (warp - 3) >> 2;
+        const float* s_bias = s_vec;
+        const float* s_scale = s_vec + p.cout_pad;
+        const float* s_shift = s_vec + 2 * p.cout_pad;
+        const bool has_affine = p.post_scale != nullptr;
+        const int Hp = p.h_out / p.pool_h, Wp = p.w_out / p.pool_w;
+        int acc = 0;
+        uint32_t acc_phase0 = 0, acc_phase1 = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
+            const int wo = t.w0 + q * 32 + lane;
+            ptx::mbar_wait(&tfull[acc], acc ? acc_phase1 : acc_phase0);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * 2 * BN + (static_cast<uint32_t>(q * 32) << 16);
+            const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
+            const bool col_ok = wo < p.w_out;
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                const int n0 = t.nt * BN + c0;
+                if (n0 >= p.cout) break;
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32b_x32(t_addr + c0, r0);
+                ptx::tmem_ld_32x32b_x32(t_addr + BN + c0, r1);
+                ptx::tmem_ld_wait();
+                if (p.pool_h == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        r0[j] = __float_as_uint(fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])));
+                }
+                if (p.pool_w == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        r0[j] = __float_as_uint(fmaxf(__uint_as_float(r0[j]),
+                                                      __shfl_xor_sync(0xffffffffu, __uint_as_float(r0[j]), 1)));
+                    if (p.pool_h == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            r1[j] = __float_as_uint(fmaxf(__uint_as_float(r1[j]),
+                                                          __shfl_xor_sync(0xffffffffu, __uint_as_float(r1[j]), 1)));
+                    }
+                }
+                const bool writer = col_ok && (p.pool_w == 1 || (lane & 1) == 0);
+                const int rows = p.pool_h == 2 ? 1 : 2;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    if (rr >= rows) break;
+                    const int ho = t.h0 + rr;
+                    if (!writer || ho >= p.h_out) continue;
+                    const uint32_t* src = rr == 0 ? r0 : r1;
+                    __half* orow = p.out_h + (static_cast<size_t>(t.img) * Hp * Wp +
+                                              static_cast<size_t>(ho / p.pool_h) * Wp + wo / p.pool_w) * p.out_cstride;
+                    uint32_t ph[16], pl[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+                        float v[4] = {__uint_as_float(src[j]) + b4.x, __uint_as_float(src[j + 1]) + b4.y,
+                                      __uint_as_float(src[j + 2]) + b4.z, __uint_as_float(src[j + 3]) + b4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act);
+                        if (has_affine) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(s_scale + n0 + j);
+                            const float4 s4 = *reinterpret_cast<const float4*>(s_shift + n0 + j);
+                            v[0] = fmaf(v[0], a4.x, s4.x); v[1] = fmaf(v[1], a4.y, s4.y);
+                            v[2] = fmaf(v[2], a4.z, s4.z); v[3] = fmaf(v[3], a4.w, s4.w);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; e += 2) {
+                            const __half2 h2 = __floats2half2_rn(v[e], v[e + 1]);
+                            ph[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                            if (p.out_lo_off >= 0) {
+                                const float2 hf = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(v[e] - hf.x, v[e + 1] - hf.y);
+                                pl[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                        }
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(orow + n0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dst[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                    if (p.out_lo_off >= 0) {
+                        uint4* dl = reinterpret_cast<uint4*>(orow + p.out_lo_off + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+            if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+            acc ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BN>
+cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                      cudaStream_t stream) {
+    using C = Cfg<BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float);
+    if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
+    const int tiles_w = (p.w_out + 127) / 128, tiles_h = (p.h_out + 1) / 2;
+    const int total_tiles = p.n_img * tiles_h * tiles_w * p.tiles_n;
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    igemm_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p, tiles_w, tiles_h, total_tiles);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool igemm_halo_supported(const IgemmParams& p, int bn) {
+    return p.epi == EPI_ACT_F16 && p.kh == 3 && p.kw == 3 && p.pad_h == 1 && p.pad_w == 1 && (bn == 64 || bn == 128) &&
+           p.cin <= 128 && (p.h_out % 2) == 0 && (p.cout % 32) == 0;
+}
+
+cudaError_t launch_igemm_halo(const IgemmParams& p, const CUtensorMap& tmA_halo, const CUtensorMap& tmB, int bn,
+                              int num_sms, cudaStream_t stream) {
+    if (bn == 64) return launch_bn<64>(p, tmA_halo, tmB, num_sms, stream);
+    if (bn == 128) return launch_bn<128>(p, tmA_halo, tmB, num_sms, stream);
+    return cudaErrorInvalidValue;
+}

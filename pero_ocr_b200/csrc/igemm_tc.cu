@@ -25,7 +25,7 @@ struct Cfg {
     static constexpr int kBBytes = BN * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes;
-    static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;  // two accumulators
+    static constexpr int kTmemCols = 512;  // whole TMEM (1 CTA/SM): base address is 0 => warp-uniform operands
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -101,7 +101,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    if (*tmem_slot != 0) __trap();
+    constexpr uint32_t tmem_base = 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer

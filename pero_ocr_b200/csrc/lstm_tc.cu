@@ -157,7 +157,10 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
     // byte offset of (line nl, units unit0..unit0+3) of plane 0 inside a B buffer (plane 1 at + kSliceBytes)
     const uint32_t slice_off = rank * planes * kSliceBytes + (ug >> 1) * 512 + (nl >> 3) * 128 + (nl & 7) * 16 + (ug & 1) * 8;
     const uint32_t leader = (warp == 0 && ptx::elect_one()) ? 1u : 0u;
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // The kernel owns all 512 TMEM columns, so the allocation starts at address 0; using the literal keeps every
+    // tcgen05 operand warp-uniform (no per-MMA R2UR / BRA.U.ANY sequences in the issue loop).
+    if (tmem_base != 0) __trap();
+    constexpr uint32_t tmem_u = 0;
 
     uint32_t hphase0 = 0, hphase1 = 0;
     uint32_t mphase = 0;
@@ -184,18 +187,21 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
                 ptx::tc_fence_after();
                 constexpr uint32_t idesc = ptx::idesc_f16_f32(128, kLines);
                 const uint32_t h_base = ptx::smem_u32(sH) + b * planes * kHPlane;
-                for (int pass = 0; pass < npass; ++pass) {
-                    const uint32_t wa = tmem_u + kWCol0 + ((pass == 2) ? 128 : 0);   // W plane (TMEM columns)
-                    const uint32_t ha = h_base + ((pass == 1) ? kSliceBytes : 0);   // h plane inside each slice block
+                if (ptx::elect_one()) {
+                    for (int pass = 0; pass < npass; ++pass) {
+                        const uint32_t wa = tmem_u + kWCol0 + ((pass == 2) ? 128 : 0);   // W plane (TMEM columns)
+                        const uint32_t ha = h_base + ((pass == 1) ? kSliceBytes : 0);    // h plane inside each slice block
 #pragma unroll
-                    for (int k16 = 0; k16 < 16; ++k16) {
-                        const uint64_t b_desc =
-                            smem_desc_nosw(ha + (k16 >> 1) * planes * kSliceBytes + (k16 & 1) * 1024, 512, 128);
-                        ptx::mma_f16_ts_pred(tmem_u + (k16 & (kAccs - 1)) * kLines, wa + k16 * 8, b_desc, idesc,
-                                             (pass != 0 || k16 >= kAccs) ? 1u : 0u, leader);
+                        for (int k16 = 0; k16 < 16; ++k16) {
+                            const uint64_t b_desc =
+                                smem_desc_nosw(ha + (k16 >> 1) * planes * kSliceBytes + (k16 & 1) * 1024, 512, 128);
+                            ptx::mma_f16_ts(tmem_u + (k16 & (kAccs - 1)) * kLines, wa + k16 * 8, b_desc, idesc,
+                                            (pass != 0 || k16 >= kAccs) ? 1u : 0u);
+                        }
                     }
+                    ptx::mma_commit(mma_done);
                 }
-                ptx::mma_commit_pred(mma_done, leader);
+                __syncwarp();
             }
             ptx::mbar_wait(mma_done, mphase);
             mphase ^= 1;

@@ -56,6 +56,9 @@ class LineRecognizer:
     def use_reference_kernels(self, on):
         _lib.check(self._lib.b200ocr_debug_use_reference_kernels(self._h, 1 if on else 0), self._h)
 
+    def set_flag(self, flag, value):
+        _lib.check(self._lib.b200ocr_debug_set_flag(self._h, int(flag), int(value)), self._h)
+
     @property
     def launch_count(self):
         return int(self._lib.b200ocr_launch_count(self._h))
