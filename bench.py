@@ -105,6 +105,49 @@ def cpu_reference_lines_per_s(kind, n_lines, threads=None):
     return n_lines / dt, dt, torch.get_num_threads()
 
 
+def ctc_decode_times(dev, with_cpu):
+    """BASELINE.json metric part 2, 'CTC decode us/line': device-resident greedy (config 1: 128 x 256 x 120) and
+    prefix beam k=16 (256 x 336 x 120 peaky log-probs), next to the reference algorithm on one host core."""
+    import torch
+    from oracle import cases
+    from pero_ocr_b200.decoders import greedy_ids_device, prefix_beam_device
+    raw, lp, letters = cases.config1_logits()
+    x = torch.from_numpy(np.ascontiguousarray(lp)).to(dev)
+    rng = np.random.default_rng(9)
+    beam_np = cases.peaky_logprobs(rng, 8, 336, 120, sharp=11.0)
+    xb = torch.from_numpy(np.ascontiguousarray(np.tile(beam_np, (32, 1, 1)))).to(dev)     # 256 lines
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms = timed(lambda: greedy_ids_device(x, 'ntc'), 20)
+    out['greedy_us_per_line'] = 1e3 * ms / x.shape[0]
+    ms = timed(lambda: prefix_beam_device(xb, 16), 3)
+    out['prefix_beam_k16_us_per_line'] = 1e3 * ms / xb.shape[0]
+    out['shapes'] = {'greedy': list(x.shape), 'prefix_beam': list(xb.shape)}
+    if with_cpu:
+        from oracle.decoders_oracle import greedy, prefix_beam
+        t0 = time.perf_counter()
+        for m in lp[:64]:
+            greedy(m, letters)
+        out['cpu_greedy_us_per_line'] = 1e6 * (time.perf_counter() - t0) / 64
+        t0 = time.perf_counter()
+        for m in beam_np[:2]:
+            prefix_beam(m, 16)
+        out['cpu_prefix_beam_k16_us_per_line'] = 1e6 * (time.perf_counter() - t0) / 2
+        out['cpu_note'] = 'numpy restatement of pero_ocr.decoding on one host core (64 / 2 lines)'
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -285,6 +328,8 @@ def main():
                    'parallelism': f'batch-parallel x{world}, no data-path collective'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
     }
+    if rank == 0:
+        line['ctc_decode'] = ctc_decode_times(dev, with_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, dt_cpu, used = cpu_reference_lines_per_s(args.net, args.cpu_baseline_lines)
         line['cpu_baseline'] = {'value': r, 'unit': UNIT, 'cores': used, 'kind': 'port',

@@ -149,57 +149,59 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 2) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
-        const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
-        int as = 0, bs = 0, acc = 0;
-        uint32_t aph = 0, bph = 0, acc_phase0 = 0, acc_phase1 = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t d0 = tmem_base + acc * 2 * BN;
-            uint32_t started = 0;
-            for (int kc = 0; kc < kchunks; ++kc)
-                for (int ap = 0; ap < planes; ++ap) {
-                    ptx::mbar_wait(&a_full[as], aph);
-                    const uint32_t halo = sA_u + as * kHaloStage;
-                    const int nbp = (ap == 0) ? planes : 1;
-                    for (int bp = 0; bp < nbp; ++bp)
-                        for (int tap = 0; tap < 9; ++tap) {
-                            ptx::mbar_wait(&b_full[bs], bph);
-                            ptx::tc_fence_after();
-                            const int tr = tap / 3, ts = tap - tr * 3;
-                            const uint64_t b_desc = ptx::smem_desc_sw128(sB_u + bs * C::kBBytes);
-                            if (ptx::elect_one()) {
+        // One elected thread runs the whole role (waits included): no per-stage reconvergence, every operand in
+        // uniform registers, tap loop fully unrolled so the shifted-view offsets are immediates.
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+            const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
+            const uint64_t desc_hi = ptx::smem_desc_sw128(0);   // descriptor with a zero start-address field
+            int as = 0, bs = 0, acc = 0;
+            uint32_t aph = 0, bph = 0, acc_phase0 = 0, acc_phase1 = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d0 = tmem_base + acc * 2 * BN;
+                uint32_t started = 0;
+                for (int kc = 0; kc < kchunks; ++kc)
+                    for (int ap = 0; ap < planes; ++ap) {
+                        ptx::mbar_wait(&a_full[as], aph);
+                        const uint64_t a_base = desc_hi + ((sA_u + as * kHaloStage) >> 4);
+                        const int nbp = (ap == 0) ? planes : 1;
+                        for (int bp = 0; bp < nbp; ++bp) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                ptx::mbar_wait(&b_full[bs], bph);
+                                ptx::tc_fence_after();
+                                const uint64_t b_desc = desc_hi + ((sB_u + bs * C::kBBytes) >> 4);
 #pragma unroll
                                 for (int r = 0; r < 2; ++r) {
-                                    const uint64_t a_desc =
-                                        ptx::smem_desc_sw128(halo + ((r + tr) * kHaloW + ts) * 128);
+                                    // pixel ((r + tap/3) * 130 + tap%3) of the halo, 128 B per pixel, >>4 encoded
+                                    const uint64_t a_desc = a_base + (((r + tap / 3) * kHaloW + tap % 3) * 8);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                         ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                                        (started | k) != 0 ? 1u : 0u);
+                                                        (tap | k) != 0 ? 1u : started);
                                 }
                                 ptx::mma_commit(&b_empty[bs]);
+                                if (++bs == C::kBStages) {
+                                    bs = 0;
+                                    bph ^= 1;
+                                }
                             }
-                            __syncwarp();
                             started = 1;
-                            if (++bs == C::kBStages) {
-                                bs = 0;
-                                bph ^= 1;
-                            }
                         }
-                    if (ptx::elect_one()) ptx::mma_commit(&a_empty[as]);
-                    __syncwarp();
-                    if (++as == kAStages) {
-                        as = 0;
-                        aph ^= 1;
+                        ptx::mma_commit(&a_empty[as]);
+                        if (++as == kAStages) {
+                            as = 0;
+                            aph ^= 1;
+                        }
                     }
-                }
-            if (ptx::elect_one()) ptx::mma_commit(&tfull[acc]);
-            __syncwarp();
-            if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-            acc ^= 1;
+                ptx::mma_commit(&tfull[acc]);
+                if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+                acc ^= 1;
+            }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 3..10)
         const int q = warp & 3;

@@ -143,36 +143,38 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
-        constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
-        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase0 = 0, acc_phase1 = 0;
-        const uint32_t smem_base = ptx::smem_u32(smem);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int it = 0; it < k_iters; ++it) {
-                ptx::mbar_wait(&full[stage], phase);
+        // ------------------------------------------------------------------ MMA issuer: one elected thread runs the role
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+            const uint64_t desc_hi = ptx::smem_desc_sw128(0);
+            const uint32_t smem_base = ptx::smem_u32(smem);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase0 = 0, acc_phase1 = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * C::kStageBytes;
-                const uint64_t a_desc = ptx::smem_desc_sw128(a_addr);
-                const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + kABytes);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int it = 0; it < k_iters; ++it) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+                    const uint64_t a_desc = desc_hi + (a_addr >> 4);
+                    const uint64_t b_desc = desc_hi + ((a_addr + kABytes) >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)  // 4 x K=16 inside the 128-byte swizzle atom: +32 B per step
-                    ptx::mma_f16_ss_pred(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0, leader);
-                ptx::mma_commit_pred(&empty[stage], leader);
-                if (++stage == C::kStages) {
-                    stage = 0;
-                    phase ^= 1;
+                    for (int k = 0; k < 4; ++k)  // 4 x K=16 inside the 128-byte swizzle atom: +32 B per step
+                        ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+                    ptx::mma_commit(&empty[stage]);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+                ptx::mma_commit(&tfull[acc]);
+                if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+                acc ^= 1;
             }
-            ptx::mma_commit_pred(&tfull[acc], leader);
-            if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-            acc ^= 1;
         }
         __syncwarp();
     } else {

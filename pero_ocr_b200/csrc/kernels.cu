@@ -13,78 +13,91 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 }
 
 // ------------------------------------------------------------------------------------------------ first conv
-// One CTA = 128 consecutive output pixels of one image row.  The 3 x 130 x 3 input patch is staged in shared
-// memory as fp32 (x / 255, zero outside the image); each thread computes one pixel x COUT channels in fp32
-// (weights broadcast from shared memory as float4) and stores its fp16 (hi | lo) pixel record with 16-byte stores.
+// One CTA = CF_ROWS image rows x 128 consecutive output pixels.  The (CF_ROWS+2) x 130 x 3 input patch is staged in
+// shared memory as fp32 through a 256-entry table of k / 255.0f (the reference's `/255`, pytorch_ocr_engine.py:61,
+// bit-exact and without a division per byte; zero outside the image); each thread computes one pixel x COUT
+// channels per row in fp32 (weights broadcast from shared memory as float4) and stores its fp16 (hi | lo) pixel
+// record with 16-byte stores.
 constexpr int CF_PX = 128;
+constexpr int CF_ROWS = 4;
 
 template <int COUT>
 __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                           const float* __restrict__ w_t, const float* __restrict__ bias,
                                                           int act, int planes, __half* __restrict__ out) {
-    __shared__ float s_in[3][CF_PX + 2][3];
+    __shared__ float s_in[CF_ROWS + 2][CF_PX + 2][3];
     __shared__ __align__(16) float s_w[27 * COUT];
     __shared__ __align__(16) float s_b[COUT];
+    __shared__ float s_lut[256];
 
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
+    const int tiles_h = (h + CF_ROWS - 1) / CF_ROWS;
     const int tw = blockIdx.x % tiles_w;
-    const int row = (blockIdx.x / tiles_w) % h;
-    const int img = blockIdx.x / (tiles_w * h);
+    const int row0 = ((blockIdx.x / tiles_w) % tiles_h) * CF_ROWS;
+    const int img = blockIdx.x / (tiles_w * tiles_h);
     const int w0 = tw * CF_PX;
 
+    for (int i = threadIdx.x; i < 256; i += CF_PX) s_lut[i] = static_cast<float>(i) / 255.0f;
     for (int i = threadIdx.x; i < 27 * COUT; i += CF_PX) s_w[i] = w_t[i];
     for (int i = threadIdx.x; i < COUT; i += CF_PX) s_b[i] = bias ? bias[i] : 0.f;
-    for (int i = threadIdx.x; i < 3 * (CF_PX + 2) * 3; i += CF_PX) {
-        const int c = i % 3;
-        const int x = (i / 3) % (CF_PX + 2);
-        const int r = i / (3 * (CF_PX + 2));
-        const int yy = row + r - 1, xx = w0 + x - 1;
+    __syncthreads();
+    constexpr int kRowBytes = (CF_PX + 2) * 3;
+    for (int i = threadIdx.x; i < (CF_ROWS + 2) * kRowBytes; i += CF_PX) {
+        const int r = i / kRowBytes;
+        const int b = i - r * kRowBytes;  // byte inside the staged row: pixel b / 3, channel b % 3
+        const int yy = row0 + r - 1;
+        const int xb = (w0 - 1) * 3 + b;  // byte offset inside the image row
         float v = 0.f;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w)
-            v = static_cast<float>(in[((static_cast<size_t>(img) * h + yy) * w + xx) * 3 + c]) / 255.0f;
-        s_in[r][x][c] = v;
+        if (yy >= 0 && yy < h && xb >= 0 && xb < w * 3)
+            v = s_lut[in[(static_cast<size_t>(img) * h + yy) * w * 3 + xb]];
+        (&s_in[r][0][0])[b] = v;
     }
     __syncthreads();
 
-    float acc[COUT];
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-    // PyTorch weight [cout][c][r][s]; w_t index ((r*3+s)*3+c)*COUT + o
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float x = s_in[r][threadIdx.x + s][c];
-                const float4* wr = reinterpret_cast<const float4*>(&s_w[((r * 3 + s) * 3 + c) * COUT]);
-#pragma unroll
-                for (int o = 0; o < COUT / 4; ++o) {
-                    const float4 wv = wr[o];
-                    acc[4 * o + 0] = fmaf(x, wv.x, acc[4 * o + 0]);
-                    acc[4 * o + 1] = fmaf(x, wv.y, acc[4 * o + 1]);
-                    acc[4 * o + 2] = fmaf(x, wv.z, acc[4 * o + 2]);
-                    acc[4 * o + 3] = fmaf(x, wv.w, acc[4 * o + 3]);
-                }
-            }
-    if (w0 + static_cast<int>(threadIdx.x) >= w) return;
+    const bool px_ok = w0 + static_cast<int>(threadIdx.x) < w;
     const int rec = planes * COUT;
-    __half* dst = out + ((static_cast<size_t>(img) * h + row) * w + w0 + threadIdx.x) * rec;
+    for (int rr = 0; rr < CF_ROWS; ++rr) {
+        const int row = row0 + rr;
+        if (row >= h) break;
+        float acc[COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; o += 8) {
-        uint32_t ph[4], pl[4];
+        for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+        // PyTorch weight [cout][c][r][s]; w_t index ((r*3+s)*3+c)*COUT + o
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-            const float v0 = act_fn(acc[o + e] + s_b[o + e], act);
-            const float v1 = act_fn(acc[o + e + 1] + s_b[o + e + 1], act);
-            const __half2 h2 = __floats2half2_rn(v0, v1);
-            const float2 hf = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-            ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-            pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float x = s_in[rr + r][threadIdx.x + s][c];
+                    const float4* wr = reinterpret_cast<const float4*>(&s_w[((r * 3 + s) * 3 + c) * COUT]);
+#pragma unroll
+                    for (int o = 0; o < COUT / 4; ++o) {
+                        const float4 wv = wr[o];
+                        acc[4 * o + 0] = fmaf(x, wv.x, acc[4 * o + 0]);
+                        acc[4 * o + 1] = fmaf(x, wv.y, acc[4 * o + 1]);
+                        acc[4 * o + 2] = fmaf(x, wv.z, acc[4 * o + 2]);
+                        acc[4 * o + 3] = fmaf(x, wv.w, acc[4 * o + 3]);
+                    }
+                }
+        if (!px_ok) continue;
+        __half* dst = out + ((static_cast<size_t>(img) * h + row) * w + w0 + threadIdx.x) * rec;
+#pragma unroll
+        for (int o = 0; o < COUT; o += 8) {
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const float v0 = act_fn(acc[o + e] + s_b[o + e], act);
+                const float v1 = act_fn(acc[o + e + 1] + s_b[o + e + 1], act);
+                const __half2 h2 = __floats2half2_rn(v0, v1);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            if (planes == 2) *reinterpret_cast<uint4*>(dst + COUT + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
-        *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        if (planes == 2) *reinterpret_cast<uint4*>(dst + COUT + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
 }
 
@@ -402,7 +415,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
                               int act, int planes, __half* out, cudaStream_t stream) {
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
-    const int grid = n * h * tiles_w;
+    const int grid = n * ((h + CF_ROWS - 1) / CF_ROWS) * tiles_w;
     switch (cout) {
         case 64: conv_first_kernel<64><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
         case 32: conv_first_kernel<32><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;

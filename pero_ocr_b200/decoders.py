@@ -82,6 +82,47 @@ def _stream(torch, device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def greedy_ids_device(x, layout='ntc', want_confidence=False):
+    """Device-resident form: x is a contiguous CUDA float32 tensor; returns CUDA tensors, no synchronisation."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = x.device
+    if layout == 'ntc':
+        n, t, c = x.shape
+        lay = 0
+    else:
+        n, c, t = x.shape
+        lay = 1
+    out = dict(labels=torch.empty((n, t), dtype=torch.int32, device=dev),
+               lengths=torch.empty((n,), dtype=torch.int32, device=dev),
+               best_path=torch.empty((n, t), dtype=torch.int32, device=dev),
+               frame_max=torch.empty((n, t), dtype=torch.float32, device=dev),
+               frame_lse=torch.empty((n, t), dtype=torch.float32, device=dev))
+    if want_confidence:
+        out['confidence'] = torch.empty((n,), dtype=torch.float32, device=dev)
+    _lib.check(lib.b200ocr_ctc_greedy(x.data_ptr(), n, t, c, lay, out['labels'].data_ptr(), out['lengths'].data_ptr(),
+                                      out['confidence'].data_ptr() if want_confidence else None,
+                                      out['best_path'].data_ptr(), out['frame_max'].data_ptr(),
+                                      out['frame_lse'].data_ptr(), _stream(torch, dev)))
+    return out
+
+
+def prefix_beam_device(x, k):
+    """x: contiguous CUDA float64 [N,T,C] normalised log-probs -> CUDA (labels [N,k,T], lengths [N,k], scores [N,k],
+    status [N]); no synchronisation."""
+    torch = _torch()
+    lib = _lib.load_library()
+    n, t, c = x.shape
+    dev = x.device
+    labels = torch.empty((n, k, t), dtype=torch.int32, device=dev)
+    lengths = torch.empty((n, k), dtype=torch.int32, device=dev)
+    scores = torch.empty((n, k), dtype=torch.float64, device=dev)
+    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.check(lib.b200ocr_ctc_prefix_beam(x.data_ptr(), n, t, c, k, labels.data_ptr(), lengths.data_ptr(),
+                                           scores.data_ptr(), status.data_ptr(), _stream(torch, dev)))
+    return labels, lengths, scores, status
+
+
 def greedy_ids(scores, layout='ntc', want_confidence=False, device=None):
     """scores: np.ndarray or CUDA tensor, [N,T,C] ('ntc') or [N,C,T] ('nct'), blank = last class.
     -> dict(labels [N,T] i32 left-packed -1 padded, lengths [N], best_path [N,T], frame_max, frame_lse[, confidence])
