@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
     __shared__ __align__(16) float s_w[27 * COUT];
     __shared__ __align__(16) float s_b[COUT];
     __shared__ float s_lut[256];
+    extern __shared__ uint4 s_stage[];   // [CF_PX][planes * COUT / 8]: one row of pixel records (hi | lo)
 
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
     const int tiles_h = (h + CF_ROWS - 1) / CF_ROWS;
@@ -54,7 +55,6 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
     }
     __syncthreads();
 
-    const bool px_ok = w0 + static_cast<int>(threadIdx.x) < w;
     const int rec = planes * COUT;
     for (int rr = 0; rr < CF_ROWS; ++rr) {
         const int row = row0 + rr;
@@ -80,23 +80,39 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
                         acc[4 * o + 3] = fmaf(x, wv.w, acc[4 * o + 3]);
                     }
                 }
-        if (!px_ok) continue;
-        __half* dst = out + ((static_cast<size_t>(img) * h + row) * w + w0 + threadIdx.x) * rec;
+        // pixel records -> shared memory (16-byte chunks, XOR-swizzled by pixel so that both the per-pixel writes
+        // and the per-record reads are bank-conflict free) -> fully coalesced 16-byte global stores
+        const int chunks = rec / 8;                 // 16-byte chunks per pixel record
+        __syncthreads();                            // previous row's staging has been read
+        {
+            uint4* my = s_stage + threadIdx.x * chunks;
 #pragma unroll
-        for (int o = 0; o < COUT; o += 8) {
-            uint32_t ph[4], pl[4];
+            for (int o = 0; o < COUT; o += 8) {
+                uint32_t ph[4], pl[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                const float v0 = act_fn(acc[o + e] + s_b[o + e], act);
-                const float v1 = act_fn(acc[o + e + 1] + s_b[o + e + 1], act);
-                const __half2 h2 = __floats2half2_rn(v0, v1);
-                const float2 hf = __half22float2(h2);
-                const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                for (int e = 0; e < 8; e += 2) {
+                    const float v0 = act_fn(acc[o + e] + s_b[o + e], act);
+                    const float v1 = act_fn(acc[o + e + 1] + s_b[o + e + 1], act);
+                    const __half2 h2 = __floats2half2_rn(v0, v1);
+                    const float2 hf = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                    ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                const int c_hi = o / 8, c_lo = COUT / 8 + o / 8;
+                my[c_hi ^ (threadIdx.x & (chunks - 1))] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                if (planes == 2)
+                    my[c_lo ^ (threadIdx.x & (chunks - 1))] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
-            *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            if (planes == 2) *reinterpret_cast<uint4*>(dst + COUT + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+        __syncthreads();
+        {
+            const int npx = min(CF_PX, w - w0);
+            uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row) * w + w0) * rec);
+            for (int i = threadIdx.x; i < npx * chunks; i += CF_PX) {
+                const int px = i / chunks, c = i - px * chunks;
+                dst[i] = s_stage[px * chunks + (c ^ (px & (chunks - 1)))];
+            }
         }
     }
 }
@@ -416,10 +432,18 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
                               int act, int planes, __half* out, cudaStream_t stream) {
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
     const int grid = n * ((h + CF_ROWS - 1) / CF_ROWS) * tiles_w;
+    const size_t dyn = static_cast<size_t>(CF_PX) * planes * cout * sizeof(__half);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_first_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(conv_first_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(conv_first_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
+    }
     switch (cout) {
-        case 64: conv_first_kernel<64><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
-        case 32: conv_first_kernel<32><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
-        case 16: conv_first_kernel<16><<<grid, CF_PX, 0, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        case 64: conv_first_kernel<64><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        case 32: conv_first_kernel<32><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        case 16: conv_first_kernel<16><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

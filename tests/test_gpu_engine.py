@@ -170,3 +170,22 @@ def test_full_size_properties():
     srt = np.sort(ref, axis=1)
     if ((srt[:, -1] - srt[:, -2]) > MARGIN).all():
         assert [list(lab[i, :ln[i]]) for i in range(2)] == [list(w) for w in want]
+
+
+@pytest.mark.parametrize('width', [136, 264, 520])
+def test_halo_kernel_matches_per_tap_kernel(width):
+    """The halo-reuse 3x3 kernel (shifted swizzle-128B views) and the per-tap TMA kernel are two implementations of
+    the same contraction: identical operands, fp32 accumulation in a different order."""
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    net = make_case_net('lstm')
+    layers, _ = netdesc.describe_line_net(net)
+    eng = LineRecognizer(layers, precision='fp16x3')
+    rng = np.random.default_rng(width)
+    crops = torch.from_numpy(rng.integers(0, 256, (3, 40, width, 3), dtype=np.uint8)).cuda()
+    a = {k: v.clone() for k, v in eng.forward(crops, want_logits=True).items()}
+    eng.set_flag(1, 0)
+    b = eng.forward(crops, want_logits=True, out={})
+    torch.cuda.synchronize()
+    assert (a['logits'] - b['logits']).abs().max().item() <= 2e-4
+    assert torch.equal(a['labels'], b['labels'])
