@@ -80,6 +80,19 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
+def ncu_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed
+    `ncu --set full` capture of one step (profiles/r01_ncu_step_<precision>.json, tools/ncu_summary.py)."""
+    path = os.path.join(ROOT, 'profiles', f'r01_ncu_step_{precision}.json')
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        d = json.load(f)
+    ks = [v for k, v in d['by_kernel'].items() if 'igemm' in k]
+    n = sum(v['launches'] for v in ks)
+    return (sum(v['traffic_bytes'] for v in ks) / n if n else None), os.path.relpath(path, ROOT)
+
+
 def make_net(kind):
     from pero_ocr_b200.synthetic import make_net as mk
     return mk(kind, 120, seed=0, out_gain=6.0 if kind == 'lstm' else 2.5, **({'layers': 2} if kind == 'transformer' else {}))
@@ -95,7 +108,7 @@ def cpu_reference_lines_per_s(kind, n_lines, threads=None):
     net = make_net(kind)
     eng = OracleEngine(dict(net.state_dict()), cases.json_characters(118), kind=kind)
     eng.model = lambda x: net(x)
-    eng.max_input_horizontal_pixels = BATCH * WIDTH
+    eng.max_input_horizontal_pixels = 32 * WIDTH          # 32-line host batches (a 256-line fp32 batch needs >10 GB)
     lines = list(cases.bench_crops(n_lines, WIDTH, seed=0))
     with torch.no_grad():
         eng.process_lines(lines[:1], no_logits=True)          # warm-up (thread pool, allocator)
@@ -185,8 +198,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16'])
     ap.add_argument('--net', default='lstm', choices=['lstm', 'transformer'])
-    ap.add_argument('--ref-lines', type=int, default=4, help='lines per step of the CPU reference arm')
-    ap.add_argument('--cpu-baseline-lines', type=int, default=16)
+    ap.add_argument('--ref-lines', type=int, default=96, help='lines per step of the CPU reference arm')
+    ap.add_argument('--cpu-baseline-lines', type=int, default=512, help='bounded CPU sample (about 10-20 s of host work)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-layer kernel table (JSON) here')
     args = ap.parse_args()
@@ -307,6 +320,9 @@ def main():
                 'share_of_step': igemm_ms / (igemm_ms + lstm_ms + first_ms + other_ms),
                 'step_breakdown_ms': {'igemm_tc': igemm_ms, 'lstm_tc': lstm_ms, 'conv_first': first_ms, 'other': other_ms},
                 'executed_mma_passes': 3 if args.precision == 'fp16x3' else 1}
+    traffic, traffic_src = ncu_traffic(args.precision) if args.net == 'lstm' else (None, None)
+    roofline['traffic'] = traffic
+    roofline['traffic_source'] = traffic_src
     if args.profile_out and rank == 0:
         per_layer = {}
         for tg, li, m in zip(tags, lidx, pms):
