@@ -2,7 +2,7 @@
 """Headline benchmark: text-lines/sec on synthetic 40x1280 crops (BASELINE.json config 2: batch 256, random-init
 CNN+BiLSTM recogniser), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16x3|fp16] [--net lstm]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16x3|fp16f8|fp16] [--net lstm]
 
 A step = one pass of the hot path (pad/255 -> conv stack -> BiLSTM x2 -> CTC head + greedy collapse) over one batch
 of 256 lines.  `value` is device-resident throughput (crops already in HBM; CUDA events, max over ranks);
@@ -196,7 +196,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16'])
+    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16f8', 'fp16'])
     ap.add_argument('--net', default='lstm', choices=['lstm', 'transformer'])
     ap.add_argument('--ref-lines', type=int, default=96, help='lines per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-lines', type=int, default=512, help='bounded CPU sample (about 10-20 s of host work)')
@@ -319,7 +319,7 @@ def main():
                 'launches_per_step': n_igemm, 'avg_launch_ms': igemm_ms / max(n_igemm, 1),
                 'share_of_step': igemm_ms / (igemm_ms + lstm_ms + first_ms + other_ms),
                 'step_breakdown_ms': {'igemm_tc': igemm_ms, 'lstm_tc': lstm_ms, 'conv_first': first_ms, 'other': other_ms},
-                'executed_mma_passes': 3 if args.precision == 'fp16x3' else 1}
+                'executed_mma_passes': {'fp16x3': 3, 'fp16f8': 2, 'fp16': 1}[args.precision]}
     traffic, traffic_src = ncu_traffic(args.precision) if args.net == 'lstm' else (None, None)
     roofline['traffic'] = traffic
     roofline['traffic_source'] = traffic_src
@@ -334,7 +334,9 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16x3 (fp16 hi/lo split operands, fp32 accumulate)' if args.precision == 'fp16x3' else 'f16 (fp32 accumulate)',
+        'dtype': {'fp16x3': 'f16x3 (fp16 hi/lo split operands, fp32 accumulate)',
+                  'fp16f8': 'f16+e5m2 (fp16 pass + e5m2 first-order correction pass, fp32 accumulate)',
+                  'fp16': 'f16 (fp32 accumulate)'}[args.precision],
         'data': 'synthetic',
         'config': {'workload': 'config2: ocr_engine line recognizer, batch=256 synthetic 40x1280 gray crops (40x1344 padded), '
                                'random-init CNN+BiLSTM, C=120' if args.net == 'lstm' else

@@ -42,7 +42,9 @@ enum b200ocr_act { B200OCR_ACT_NONE = 0, B200OCR_ACT_RELU = 1, B200OCR_ACT_LEAKY
 
 enum b200ocr_precision {
     B200OCR_PREC_FP16 = 0,  /* fp16 operands, fp32 accumulate (same 10-bit mantissa as cuDNN's default TF32 convs) */
-    B200OCR_PREC_FP16X3 = 1 /* hi/lo fp16 split of both operands, 3 MMAs per product: ~fp32-faithful */
+    B200OCR_PREC_FP16X3 = 1, /* hi/lo fp16 split of both operands, 3 MMAs per product: ~fp32-faithful */
+    B200OCR_PREC_FP16F8 = 2  /* fp16 hi*hi pass + the two first-order correction terms (lo*hi + hi*lo) as ONE e5m2
+                                tensor-core pass at twice the fp16 rate: 2 pass-equivalents, logits within ~1e-4 */
 };
 
 /* One layer.  All weight pointers are HOST pointers to fp32 arrays in PyTorch's native layouts; the library

@@ -8,8 +8,8 @@ _LIB = None
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_NO_DEVICE = 0, 1, 2, 3, 4
 CONV_FIRST, CONV, BILSTM, CTC_HEAD, UPSAMPLE, LN_PE, TRANSFORMER_LAYER = 1, 2, 3, 4, 5, 6, 7
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
-PREC_FP16, PREC_FP16X3 = 0, 1
-PRECISIONS = {'fp16': PREC_FP16, 'fp16x3': PREC_FP16X3}
+PREC_FP16, PREC_FP16X3, PREC_FP16F8 = 0, 1, 2
+PRECISIONS = {'fp16': PREC_FP16, 'fp16x3': PREC_FP16X3, 'fp16f8': PREC_FP16F8}
 
 _FP = C.POINTER(C.c_float)
 

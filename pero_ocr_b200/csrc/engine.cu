@@ -72,6 +72,8 @@ struct Shape {
 
 struct b200ocr_engine {
     int device = 0, num_sms = 148, precision = 0, planes = 1, npass = 1, line_height = 40;
+    int fmt = ACT_F16;        // activation record format between layers (actfmt.cuh)
+    int lstm_planes = 1;      // arithmetic of the LSTM recurrence (1 = fp16, 2 = fp16x3)
     bool use_ref = false;
     bool use_halo = true;
     std::vector<LayerRT> layers;
@@ -184,15 +186,29 @@ int build_gemm(b200ocr_engine* e, Gemm& g, const float* weight, const float* bia
     const int taps = kh * kw;
     const size_t rows = static_cast<size_t>(g.planes) * taps * g.cout_pad;
     std::vector<__half> packed(rows * cin, __float2half(0.f));
+    const bool f8 = e->fmt == ACT_F16_F8;
     for (int o = 0; o < cout; ++o)
         for (int c = 0; c < cin; ++c)
             for (int t = 0; t < taps; ++t) {
                 const float v = weight[(static_cast<size_t>(o) * cin + c) * taps + t];
                 const __half hi = __float2half_rn(v);
-                packed[(static_cast<size_t>(t) * g.cout_pad + o) * cin + c] = hi;
-                if (g.planes == 2)
-                    packed[((static_cast<size_t>(taps) + t) * g.cout_pad + o) * cin + c] =
-                        __float2half_rn(v - __half2float(hi));
+                const float lo = v - __half2float(hi);
+                const size_t row0 = (static_cast<size_t>(t) * g.cout_pad + o) * cin;
+                const size_t row1 = ((static_cast<size_t>(taps) + t) * g.cout_pad + o) * cin;
+                if (f8) {
+                    // plane 0: fp16(w) * 2^11 (accumulators live at scale 2^11); plane 1: 2*cin e5m2 bytes
+                    // [e5m2(hi) x cin | e5m2(lo * 2^11) x cin], the K-concatenated partner of [lo' | hi8] (actfmt.cuh)
+                    const float scaled = __half2float(hi) * kF8Scale;
+                    if (!(std::fabs(scaled) <= 65504.f))
+                        return fail(e, B200OCR_E_INVALID, "fp16f8 precision needs |weight| < 32 (got %g)", v);
+                    packed[row0 + c] = __float2half_rn(scaled);
+                    uint8_t* b = reinterpret_cast<uint8_t*>(&packed[row1]);
+                    b[c] = f32_to_e5m2(__half2float(hi));
+                    b[cin + c] = f32_to_e5m2(lo * kF8Scale);
+                } else {
+                    packed[row0 + c] = hi;
+                    if (g.planes == 2) packed[row1 + c] = __float2half_rn(lo);
+                }
             }
     if (int s = upload(e, packed.data(), packed.size(), &g.w)) return s;
     if (bias) {
@@ -240,6 +256,8 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     p.epi = o.epi;
     p.bias = g.bias; p.post_scale = g.post_scale; p.post_shift = g.post_shift; p.residual = o.residual;
     p.out_h = o.out_h; p.out_cstride = g.cout * e->planes; p.out_lo_off = e->planes == 2 ? g.cout : -1;
+    p.out_fmt = e->fmt;
+    p.acc_scale = e->fmt == ACT_F16_F8 ? 1.f / kF8Scale : 1.f;
     p.out_f32 = o.out_f32; p.best = o.best; p.fmax = o.fmax; p.flse = o.flse; p.fprob = o.fprob;
     if (o.epi == EPI_ACT_F16 && (g.cout % 32))
         return fail(e, B200OCR_E_INVALID, "fp16 activation output needs cout %% 32 == 0 (got %d)", g.cout);
@@ -319,7 +337,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
                     ProfScope ps(e, st, PROF_CONV_FIRST);
                     CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
-                                                e->planes, static_cast<__half*>(e->hbuf[slot]), st));
+                                                e->fmt, static_cast<__half*>(e->hbuf[slot]), st));
                     e->launches++;
                     cur_h = static_cast<__half*>(e->hbuf[slot]);
                 }
@@ -385,10 +403,10 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     if (int s = run_gemm(e, ly.g, cur_h, rows, 0, 1, 1, eo, st, nullptr)) return s;
                     __half* o = static_cast<__half*>(e->hbuf[slot]);
                     if (e->use_ref) {
-                        CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->planes, e->planes == 1, o, st));
+                        CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->fmt, e->planes == 1, o, st));
                     } else {
                         ProfScope ps(e, st, PROF_LSTM);
-                        CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->planes, st));
+                        CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->lstm_planes, e->fmt, st));
                     }
                     e->launches++;
                     cur_h = o;
@@ -409,7 +427,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                         return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
                     CU_TRY(e, launch_layernorm(cur_f, cur.n * T, cur.c, ly.n1w, ly.n1b, 1e-5f, T,
                                                static_cast<float*>(e->fbuf[2]), static_cast<__half*>(e->hbuf[0]),
-                                               e->planes, st));
+                                               e->fmt, st));
                     e->launches++;
                     cur_f = static_cast<float*>(e->fbuf[2]);
                     cur_h = static_cast<__half*>(e->hbuf[0]);
@@ -441,12 +459,12 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     EpiOut eo;
                     eo.epi = EPI_F32; eo.out_f32 = qkv;
                     if (int s = run_gemm(e, ly.g_in, xh, rows, 0, 1, 1, eo, st, nullptr)) return s;
-                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->planes, st)); }
+                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->fmt, st)); }
                     e->launches++;
                     EpiOut er;
                     er.epi = EPI_RES_F32; er.out_f32 = tmp; er.residual = x;
                     if (int s = run_gemm(e, ly.g_out, ah, rows, 0, 1, 1, er, st, nullptr)) return s;
-                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_layernorm(tmp, R, D, ly.n1w, ly.n1b, 1e-5f, 0, x, xh, e->planes, st)); }
+                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_layernorm(tmp, R, D, ly.n1w, ly.n1b, 1e-5f, 0, x, xh, e->fmt, st)); }
                     e->launches++;
                     EpiOut ef;
                     ef.epi = EPI_ACT_F16; ef.out_h = fh;
@@ -454,7 +472,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     Shape ffrows{1, 1, R, ly.dim_ff};
                     er.out_f32 = tmp; er.residual = x;
                     if (int s = run_gemm(e, ly.g_l2, fh, ffrows, 0, 1, 1, er, st, nullptr)) return s;
-                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_layernorm(tmp, R, D, ly.n2w, ly.n2b, 1e-5f, 0, x, xh, e->planes, st)); }
+                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_layernorm(tmp, R, D, ly.n2w, ly.n2b, 1e-5f, 0, x, xh, e->fmt, st)); }
                     e->launches++;
                 }
                 break;
@@ -556,8 +574,12 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
     cudaGetDeviceProperties(&prop, e->device);
     e->num_sms = prop.multiProcessorCount;
     e->precision = desc->precision;
-    e->planes = desc->precision == B200OCR_PREC_FP16X3 ? 2 : 1;
-    e->npass = e->planes == 2 ? 3 : 1;
+    switch (desc->precision) {
+        case B200OCR_PREC_FP16: e->fmt = ACT_F16; e->planes = 1; e->npass = 1; e->lstm_planes = 1; break;
+        case B200OCR_PREC_FP16X3: e->fmt = ACT_F16_HILO; e->planes = 2; e->npass = 3; e->lstm_planes = 2; break;
+        case B200OCR_PREC_FP16F8: e->fmt = ACT_F16_F8; e->planes = 2; e->npass = 2; e->lstm_planes = 2; break;
+        default: return bail(fail(e, B200OCR_E_INVALID, "unknown precision %d", desc->precision));
+    }
     e->line_height = desc->line_height;
     e->layers.resize(desc->n_layers);
     for (int i = 0; i < desc->n_layers; ++i) {
@@ -602,7 +624,7 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                     return bail(s);
                 ly.hidden = H;
                 // recurrent weights for the tcgen05 kernel: [dir][plane][cta j][row = gate*32 + u][k]
-                const int P = e->planes;
+                const int P = e->lstm_planes;
                 std::vector<__half> rec(static_cast<size_t>(2) * P * 8 * 128 * H);
                 std::vector<float> wt(static_cast<size_t>(2) * H * 4 * H);
                 for (int dir = 0; dir < 2; ++dir)
@@ -865,7 +887,7 @@ int b200ocr_debug_forward_prefix(b200ocr_engine_t* e, const uint8_t* crops, int3
     } else {
         float* tmp = nullptr;
         CU_TRY(e, cudaMalloc(reinterpret_cast<void**>(&tmp), count * 4));
-        CU_TRY(e, launch_h2f(static_cast<const __half*>(ptr), fs.n * fs.h * fs.w, fs.c, e->planes, tmp, st));
+        CU_TRY(e, launch_h2f(static_cast<const __half*>(ptr), fs.n * fs.h * fs.w, fs.c, e->fmt, tmp, st));
         CU_TRY(e, cudaMemcpyAsync(out, tmp, count * 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(e, cudaStreamSynchronize(st));
         cudaFree(tmp);

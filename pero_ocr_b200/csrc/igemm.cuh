@@ -9,6 +9,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "actfmt.cuh"
+
 enum IgemmEpilogue : int {
     EPI_ACT_F16 = 0,  // bias + act (+pool) (+affine) -> fp16 NHWC (hi plane, optional lo plane)
     EPI_F32 = 1,      // bias (+act) -> fp32 [pixel][cout]
@@ -17,7 +19,8 @@ enum IgemmEpilogue : int {
 };
 
 struct IgemmParams {
-    // input activation: fp16 NHWC [n_img][h_in][w_in][cin * planes]; plane 0 = hi, plane 1 = lo (x3 mode)
+    // input activation: NHWC records [n_img][h_in][w_in][cin * planes fp16-sized slots] (actfmt.cuh): plane 0 = fp16
+    // hi, plane 1 = fp16 lo (npass 3) or the 2*cin e5m2 bytes lo' | hi8 (npass 2)
     int n_img, h_in, w_in, cin;
     int cout;      // real output channels
     int cout_pad;  // rows per tap in the packed weight matrix (= tiles_n * BN)
@@ -25,7 +28,9 @@ struct IgemmParams {
     int h_out, w_out;  // conv output geometry before pooling
     int pool_h, pool_w;
     int act;
-    int npass;  // 1 (fp16) or 3 (fp16x3: hi*hi + hi*lo + lo*hi)
+    int npass;  // 1 (fp16), 3 (fp16x3: hi*hi + hi*lo + lo*hi) or 2 (fp16 hi*hi + one e5m2 correction pass, actfmt.cuh)
+    float acc_scale;  // epilogue multiplies the accumulator by this before the bias (2^-11 when npass == 2, else 1)
+    int out_fmt;      // ActFormat of the EPI_ACT_F16 output
     int th;     // rows per segment (1 or 2); a segment is th x (32/th) output pixels = one TMEM lane quarter
     int segs_per_row, row_groups, total_segs, m_tiles, tiles_n;
     int epi;

@@ -30,12 +30,6 @@ struct Cfg {
     static constexpr int kSmemBytes = kBarOff + 256 + 1024;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : 0.01f * v;
-    return v;
-}
-
 struct Tile {
     int img, h0, w0, nt;
 };
@@ -52,7 +46,7 @@ __device__ __forceinline__ Tile tile_coord(const IgemmParams& p, int tile, int t
     return t;
 }
 
-template <int BN>
+template <int BN, int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmParams p, int tiles_w, int tiles_h, int total_tiles) {
@@ -74,7 +68,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int kchunks = p.cin >> 6;
-    const int planes = p.npass == 3 ? 2 : 1;
+    // FMT (compile time) = operand format of the input AND record format of the output (one format per engine)
+    constexpr int planes = FMT == ACT_F16 ? 1 : 2;
+    constexpr bool f8 = FMT == ACT_F16_F8;   // plane 1 = e5m2 correction operands: A plane ap meets B plane ap only
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -133,13 +129,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
             for (int kc = 0; kc < kchunks; ++kc)
                 for (int ap = 0; ap < planes; ++ap) {
-                    const int nbp = (ap == 0) ? planes : 1;   // A_hi meets B_hi (and B_lo); A_lo meets B_hi only
+                    // fp16x3: A_hi meets B_hi and B_lo, A_lo meets B_hi only; fp16+fp8: A plane ap meets B plane ap
+                    const int nbp = (ap == 0 && !f8) ? planes : 1;
                     for (int bp = 0; bp < nbp; ++bp)
                         for (int tap = 0; tap < 9; ++tap) {
                             ptx::mbar_wait(&b_empty[stage], phase ^ 1);
                             ptx::mbar_expect_tx_pred(&b_full[stage], C::kBBytes, leader);
                             ptx::tma_load_2d_pred(sB + stage * C::kBBytes, &tmB, &b_full[stage], kc * 64,
-                                                  (bp * 9 + tap) * p.cout_pad + t.nt * BN, leader);
+                                                  ((f8 ? ap : bp) * 9 + tap) * p.cout_pad + t.nt * BN, leader);
                             if (++stage == C::kBStages) {
                                 stage = 0;
                                 phase ^= 1;
@@ -153,6 +150,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // uniform registers, tap loop fully unrolled so the shifted-view offsets are immediates.
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+            constexpr uint32_t idesc8 = ptx::idesc_e5m2_f32(128, BN);
             const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
             const uint64_t desc_hi = ptx::smem_desc_sw128(0);   // descriptor with a zero start-address field
             int as = 0, bs = 0, acc = 0;
@@ -166,7 +164,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int ap = 0; ap < planes; ++ap) {
                         ptx::mbar_wait(&a_full[as], aph);
                         const uint64_t a_base = desc_hi + ((sA_u + as * kHaloStage) >> 4);
-                        const int nbp = (ap == 0) ? planes : 1;
+                        const int nbp = (ap == 0 && !f8) ? planes : 1;
+                        const bool e5m2 = f8 && ap == 1;
                         for (int bp = 0; bp < nbp; ++bp) {
 #pragma unroll
                             for (int tap = 0; tap < 9; ++tap) {
@@ -177,10 +176,16 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 for (int r = 0; r < 2; ++r) {
                                     // pixel ((r + tap/3) * 130 + tap%3) of the halo, 128 B per pixel, >>4 encoded
                                     const uint64_t a_desc = a_base + (((r + tap / 3) * kHaloW + tap % 3) * 8);
+                                    if (e5m2) {
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                                        (tap | k) != 0 ? 1u : started);
+                                        for (int k = 0; k < 4; ++k)
+                                            ptx::mma_f8_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1u);
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                                            (tap | k) != 0 ? 1u : started);
+                                    }
                                 }
                                 ptx::mma_commit(&b_empty[bs]);
                                 if (++bs == C::kBStages) {
@@ -252,44 +257,10 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (rr >= rows) break;
                     const int ho = t.h0 + rr;
                     if (!writer || ho >= p.h_out) continue;
-                    const uint32_t* src = rr == 0 ? r0 : r1;
                     __half* orow = p.out_h + (static_cast<size_t>(t.img) * Hp * Wp +
                                               static_cast<size_t>(ho / p.pool_h) * Wp + wo / p.pool_w) * p.out_cstride;
-                    uint32_t ph[16], pl[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + j);
-                        float v[4] = {__uint_as_float(src[j]) + b4.x, __uint_as_float(src[j + 1]) + b4.y,
-                                      __uint_as_float(src[j + 2]) + b4.z, __uint_as_float(src[j + 3]) + b4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act);
-                        if (has_affine) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(s_scale + n0 + j);
-                            const float4 s4 = *reinterpret_cast<const float4*>(s_shift + n0 + j);
-                            v[0] = fmaf(v[0], a4.x, s4.x); v[1] = fmaf(v[1], a4.y, s4.y);
-                            v[2] = fmaf(v[2], a4.z, s4.z); v[3] = fmaf(v[3], a4.w, s4.w);
-                        }
-#pragma unroll
-                        for (int e = 0; e < 4; e += 2) {
-                            const __half2 h2 = __floats2half2_rn(v[e], v[e + 1]);
-                            ph[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                            if (p.out_lo_off >= 0) {
-                                const float2 hf = __half22float2(h2);
-                                const __half2 l2 = __floats2half2_rn(v[e] - hf.x, v[e + 1] - hf.y);
-                                pl[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-                            }
-                        }
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(orow + n0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dst[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                    if (p.out_lo_off >= 0) {
-                        uint4* dl = reinterpret_cast<uint4*>(orow + p.out_lo_off + n0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    }
+                    epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow,
+                                p.cout, FMT);
                 }
             }
             ptx::tc_fence_before();
@@ -308,13 +279,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-template <int BN>
+template <int BN, int FMT>
 cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                       cudaStream_t stream) {
     using C = Cfg<BN>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -325,8 +296,19 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
     const int total_tiles = p.n_img * tiles_h * tiles_w * p.tiles_n;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    igemm_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p, tiles_w, tiles_h, total_tiles);
+    igemm_halo_kernel<BN, FMT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p, tiles_w, tiles_h, total_tiles);
     return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_fmt(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                       cudaStream_t stream) {
+    switch (p.npass) {
+        case 1: return launch_bn<BN, ACT_F16>(p, tmA, tmB, num_sms, stream);
+        case 3: return launch_bn<BN, ACT_F16_HILO>(p, tmA, tmB, num_sms, stream);
+        case 2: return launch_bn<BN, ACT_F16_F8>(p, tmA, tmB, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace
@@ -338,7 +320,7 @@ bool igemm_halo_supported(const IgemmParams& p, int bn) {
 
 cudaError_t launch_igemm_halo(const IgemmParams& p, const CUtensorMap& tmA_halo, const CUtensorMap& tmB, int bn,
                               int num_sms, cudaStream_t stream) {
-    if (bn == 64) return launch_bn<64>(p, tmA_halo, tmB, num_sms, stream);
-    if (bn == 128) return launch_bn<128>(p, tmA_halo, tmB, num_sms, stream);
+    if (bn == 64) return launch_fmt<64>(p, tmA_halo, tmB, num_sms, stream);
+    if (bn == 128) return launch_fmt<128>(p, tmA_halo, tmB, num_sms, stream);
     return cudaErrorInvalidValue;
 }

@@ -56,7 +56,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-template <int BN>
+template <int BN, int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const IgemmParams p) {
@@ -76,7 +76,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int taps = p.kh * p.kw;
     const int kchunks = p.cin >> 6;
-    const int k_iters = p.npass * taps * kchunks;
+    // FMT (compile time) = operand format of the input AND record format of an EPI_ACT_F16 output
+    constexpr int npass = FMT == ACT_F16 ? 1 : (FMT == ACT_F16_HILO ? 3 : 2);
+    const int k_iters = npass * taps * kchunks;
     const int total_tiles = p.m_tiles * p.tiles_n;
 
     if (threadIdx.x == 0) {
@@ -117,9 +119,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             SegCoord sc[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) sc[q] = seg_coord(p, mt * 4 + q);
-            for (int pass = 0; pass < p.npass; ++pass) {
-                const int pa = (pass == 2) ? 1 : 0;  // activation plane
-                const int pb = (pass == 1) ? 1 : 0;  // weight plane
+            for (int pass = 0; pass < npass; ++pass) {
+                // fp16x3: (A hi, B hi), (A hi, B lo), (A lo, B hi); fp16+fp8: (A hi, B hi*2^11), (A e5m2, B e5m2)
+                const int pa = (npass == 2) ? pass : ((pass == 2) ? 1 : 0);  // activation plane
+                const int pb = (npass == 2) ? pass : ((pass == 1) ? 1 : 0);  // weight plane
                 for (int tap = 0; tap < taps; ++tap) {
                     const int r = tap / p.kw;
                     const int s = tap - r * p.kw;
@@ -146,8 +149,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ------------------------------------------------------------------ MMA issuer: one elected thread runs the role
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
+            constexpr uint32_t idesc8 = ptx::idesc_e5m2_f32(128, BN);
             const uint64_t desc_hi = ptx::smem_desc_sw128(0);
             const uint32_t smem_base = ptx::smem_u32(smem);
+            // iterations [0, k16_iters) are fp16 passes; the rest (npass == 2 only) is the e5m2 correction pass
+            const int k16_iters = (npass == 2) ? taps * kchunks : k_iters;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -156,7 +162,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int it = 0; it < k_iters; ++it) {
+                for (int it = 0; it < k16_iters; ++it) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * C::kStageBytes;
@@ -165,6 +171,21 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; ++k)  // 4 x K=16 inside the 128-byte swizzle atom: +32 B per step
                         ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+                    ptx::mma_commit(&empty[stage]);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                for (int it = k16_iters; it < k_iters; ++it) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+                    const uint64_t a_desc = desc_hi + (a_addr >> 4);
+                    const uint64_t b_desc = desc_hi + ((a_addr + kABytes) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)  // 4 x K=32 e5m2 inside the 128-byte swizzle atom: +32 B per step
+                        ptx::mma_f8_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1u);
                     ptx::mma_commit(&empty[stage]);
                     if (++stage == C::kStages) {
                         stage = 0;
@@ -226,43 +247,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]),
                                                          __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), segw)));
                     }
-                    if (writer) {
-                        uint32_t ph[16], pl[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + j);
-                            float v[4] = {__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
-                                          __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act);
-                            if (has_affine) {
-                                const float4 a4 = *reinterpret_cast<const float4*>(s_scale + n0 + j);
-                                const float4 s4 = *reinterpret_cast<const float4*>(s_shift + n0 + j);
-                                v[0] = fmaf(v[0], a4.x, s4.x); v[1] = fmaf(v[1], a4.y, s4.y);
-                                v[2] = fmaf(v[2], a4.z, s4.z); v[3] = fmaf(v[3], a4.w, s4.w);
-                            }
-#pragma unroll
-                            for (int e = 0; e < 4; e += 2) {
-                                const __half2 h2 = __floats2half2_rn(v[e], v[e + 1]);
-                                ph[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                                if (p.out_lo_off >= 0) {
-                                    const float2 hf = __half22float2(h2);
-                                    const __half2 l2 = __floats2half2_rn(v[e] - hf.x, v[e + 1] - hf.y);
-                                    pl[(j + e) >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-                                }
-                            }
-                        }
-                        uint4* dst = reinterpret_cast<uint4*>(orow + n0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                        if (p.out_lo_off >= 0) {
-                            uint4* dl = reinterpret_cast<uint4*>(orow + p.out_lo_off + n0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                        }
-                    }
+                    if (writer)
+                        epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
                 }
             } else if (p.epi == EPI_CTC) {
               if (half == 0) {
@@ -281,7 +267,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int j = 0; j < 32; ++j) {
                         const int n = c0 + j;
                         if (n < p.cout) {
-                            const float v = __uint_as_float(r[j]) + s_bias[n];
+                            const float v = fmaf(__uint_as_float(r[j]), p.acc_scale, s_bias[n]);
                             r[j] = __float_as_uint(v);
                             if (!best_nan) {
                                 if (v != v) {
@@ -335,7 +321,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int j = 0; j < 32; ++j) {
                             const int n = c0 + j;
                             if (n < p.cout) {
-                                const float v = __uint_as_float(r[j]) + s_bias[n];
+                                const float v = fmaf(__uint_as_float(r[j]), p.acc_scale, s_bias[n]);
                                 const float e = __expf(v - run_m);
                                 if (e < thr || v == 0.f) ++dropped;
                                 else kept += e;
@@ -361,11 +347,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (n0 + j < p.cout) {
-                                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                                    float4 v;
                                     {
                                         const float4 b = *reinterpret_cast<const float4*>(s_bias + n0 + j);
-                                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                        v.x = fmaf(__uint_as_float(r[j]), p.acc_scale, b.x);
+                                        v.y = fmaf(__uint_as_float(r[j + 1]), p.acc_scale, b.y);
+                                        v.z = fmaf(__uint_as_float(r[j + 2]), p.acc_scale, b.z);
+                                        v.w = fmaf(__uint_as_float(r[j + 3]), p.acc_scale, b.w);
                                     }
                                     v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
                                     v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
@@ -380,7 +368,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 if (n0 + j < p.cout) {
-                                    float v = __uint_as_float(r[j]) + s_bias[n0 + j];
+                                    float v = fmaf(__uint_as_float(r[j]), p.acc_scale, s_bias[n0 + j]);
                                     v = apply_act(v, p.act);
                                     if (res) v += __ldg(res + j);
                                     dst[j] = v;
@@ -406,13 +394,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
-template <int BN>
+template <int BN, int FMT>
 cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                       cudaStream_t stream) {
     using C = Cfg<BN>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -422,8 +410,19 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
     const int total_tiles = p.m_tiles * p.tiles_n;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    igemm_tc_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    igemm_tc_kernel<BN, FMT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
     return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_fmt(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                       cudaStream_t stream) {
+    switch (p.npass) {
+        case 1: return launch_bn<BN, ACT_F16>(p, tmA, tmB, num_sms, stream);
+        case 3: return launch_bn<BN, ACT_F16_HILO>(p, tmA, tmB, num_sms, stream);
+        case 2: return launch_bn<BN, ACT_F16_F8>(p, tmA, tmB, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace
@@ -431,9 +430,9 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
 cudaError_t launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int num_sms,
                             cudaStream_t stream) {
     switch (bn) {
-        case 64: return launch_bn<64>(p, tmA, tmB, num_sms, stream);
-        case 128: return launch_bn<128>(p, tmA, tmB, num_sms, stream);
-        case 256: return launch_bn<256>(p, tmA, tmB, num_sms, stream);
+        case 64: return launch_fmt<64>(p, tmA, tmB, num_sms, stream);
+        case 128: return launch_fmt<128>(p, tmA, tmB, num_sms, stream);
+        case 256: return launch_fmt<256>(p, tmA, tmB, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -24,7 +24,8 @@ constexpr int CF_ROWS = 4;
 template <int COUT>
 __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                           const float* __restrict__ w_t, const float* __restrict__ bias,
-                                                          int act, int planes, __half* __restrict__ out) {
+                                                          int act, int fmt, __half* __restrict__ out) {
+    const int planes = act_planes(fmt);
     __shared__ float s_in[CF_ROWS + 2][CF_PX + 2][3];
     __shared__ __align__(16) float s_w[27 * COUT];
     __shared__ __align__(16) float s_b[COUT];
@@ -86,23 +87,39 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
         __syncthreads();                            // previous row's staging has been read
         {
             uint4* my = s_stage + threadIdx.x * chunks;
+            const int sw = threadIdx.x & (chunks - 1);
 #pragma unroll
-            for (int o = 0; o < COUT; o += 8) {
-                uint32_t ph[4], pl[4];
+            for (int o = 0; o < COUT; o += 16) {
+                uint32_t ph[8], pl[8];   // pl: 8 words fp16 lo (HILO) or 4 words lo' + 4 words hi8 (F8)
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    const float v0 = act_fn(acc[o + e] + s_b[o + e], act);
-                    const float v1 = act_fn(acc[o + e + 1] + s_b[o + e + 1], act);
-                    const __half2 h2 = __floats2half2_rn(v0, v1);
-                    const float2 hf = __half22float2(h2);
-                    const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                    ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                    pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                for (int e = 0; e < 16; e += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = act_fn(acc[o + e + q] + s_b[o + e + q], act);
+                    const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
+                    ph[(e >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    if (fmt == ACT_F16_HILO) {
+                        const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y);
+                        const __half2 l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+                        pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l01);
+                        pl[(e >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                    } else if (fmt == ACT_F16_F8) {
+                        pl[e >> 2] = pack_e5m2x4((v[0] - f01.x) * kF8Scale, (v[1] - f01.y) * kF8Scale,
+                                                 (v[2] - f23.x) * kF8Scale, (v[3] - f23.y) * kF8Scale);
+                        pl[4 + (e >> 2)] = pack_e5m2x4(f01.x, f01.y, f23.x, f23.y);
+                    }
                 }
-                const int c_hi = o / 8, c_lo = COUT / 8 + o / 8;
-                my[c_hi ^ (threadIdx.x & (chunks - 1))] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                if (planes == 2)
-                    my[c_lo ^ (threadIdx.x & (chunks - 1))] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                my[(o / 8) ^ sw] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                my[(o / 8 + 1) ^ sw] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                if (fmt == ACT_F16_HILO) {
+                    my[(COUT / 8 + o / 8) ^ sw] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    my[(COUT / 8 + o / 8 + 1) ^ sw] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                } else if (fmt == ACT_F16_F8) {
+                    my[(COUT / 8 + o / 16) ^ sw] = make_uint4(pl[0], pl[1], pl[2], pl[3]);              // lo' bytes
+                    my[(COUT / 8 + COUT / 16 + o / 16) ^ sw] = make_uint4(pl[4], pl[5], pl[6], pl[7]);  // hi8 bytes
+                }
             }
         }
         __syncthreads();
@@ -219,7 +236,8 @@ constexpr int LR_LINES = 4;
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void lstm_ref_kernel(const float* __restrict__ pre, const float* __restrict__ w_hh_t, int n, int T, int H,
-                                int planes, int round_fp16, __half* __restrict__ out) {
+                                int fmt, int round_fp16, __half* __restrict__ out) {
+    const int planes = act_planes(fmt);
     extern __shared__ float s_h[];  // [LR_LINES][H]
     const int dir = blockIdx.y;
     const int line0 = blockIdx.x * LR_LINES;
@@ -256,11 +274,8 @@ __global__ void lstm_ref_kernel(const float* __restrict__ pre, const float* __re
             const float go = sigmoidf_(a[3][l] + pr[3 * H + j]);
             c[l] = gf * c[l] + gi * gg;
             const float hv = go * tanhf(c[l]);
-            const __half hi = __float2half_rn(hv);
-            __half* o = out + row * (planes * 2 * H) + dir * H + j;
-            o[0] = hi;
-            if (planes == 2) o[2 * H] = __float2half_rn(hv - __half2float(hi));
-            s_h[l * H + j] = round_fp16 ? __half2float(hi) : hv;
+            act_store(out + row * (planes * 2 * H), 2 * H, dir * H + j, hv, fmt);
+            s_h[l * H + j] = round_fp16 ? __half2float(__float2half_rn(hv)) : hv;
         }
         __syncthreads();
     }
@@ -279,7 +294,7 @@ __global__ void igemm_ref_kernel(const IgemmParams p, const __half* __restrict__
     const int hq = static_cast<int>((pix / Wp) % Hp);
     const int img = static_cast<int>(pix / (static_cast<long>(Wp) * Hp));
     const int taps = p.kh * p.kw;
-    const int planes = p.npass == 3 ? 2 : 1;
+    const int planes = p.npass == 1 ? 1 : 2;
     const int cstride = planes * p.cin;
     float result = -INFINITY;
     for (int ph = 0; ph < p.pool_h; ++ph)
@@ -287,7 +302,7 @@ __global__ void igemm_ref_kernel(const IgemmParams p, const __half* __restrict__
             const int ho = hq * p.pool_h + ph, wo = wq * p.pool_w + pw;
             float acc = 0.f;
             for (int pass = 0; pass < p.npass; ++pass) {
-                const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                const int pa = p.npass == 2 ? pass : (pass == 2 ? 1 : 0), pb = p.npass == 2 ? pass : (pass == 1 ? 1 : 0);
                 for (int tap = 0; tap < taps; ++tap) {
                     const int r = tap / p.kw, s = tap % p.kw;
                     const int hi_ = ho + r - p.pad_h, wi = wo + s - p.pad_w;
@@ -295,20 +310,23 @@ __global__ void igemm_ref_kernel(const IgemmParams p, const __half* __restrict__
                     const __half* a = in + ((static_cast<size_t>(img) * p.h_in + hi_) * p.w_in + wi) * cstride +
                                       pa * p.cin;
                     const __half* b = wp + (static_cast<size_t>(pb * taps + tap) * p.cout_pad + co) * p.cin;
-                    for (int k = 0; k < p.cin; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
+                    if (p.npass == 2 && pass == 1) {   // e5m2 correction operands: 2 * cin bytes each
+                        const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a);
+                        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(b);
+                        for (int k = 0; k < 2 * p.cin; ++k) acc = fmaf(e5m2_to_f32(a8[k]), e5m2_to_f32(b8[k]), acc);
+                    } else {
+                        for (int k = 0; k < p.cin; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
+                    }
                 }
             }
-            float v = acc + (p.bias ? p.bias[co] : 0.f);
+            float v = fmaf(acc, p.acc_scale, p.bias ? p.bias[co] : 0.f);
             if (p.epi != EPI_RES_F32) v = act_fn(v, p.act);
             result = fmaxf(result, v);
         }
     const size_t opix = (static_cast<size_t>(img) * Hp + hq) * Wp + wq;
     if (p.epi == EPI_ACT_F16) {
         if (p.post_scale) result = result * p.post_scale[co] + p.post_shift[co];
-        const __half hi = __float2half_rn(result);
-        p.out_h[opix * p.out_cstride + co] = hi;
-        if (p.out_lo_off >= 0)
-            p.out_h[opix * p.out_cstride + p.out_lo_off + co] = __float2half_rn(result - __half2float(hi));
+        act_store(p.out_h + opix * p.out_cstride, p.cout, co, result, p.out_fmt);
     } else {
         if (p.epi == EPI_RES_F32) result += p.residual[opix * p.cout + co];
         p.out_f32[opix * p.cout + co] = result;
@@ -331,7 +349,8 @@ __global__ void upsample_nchw_kernel(const float* __restrict__ in, int n, int h,
 // one warp per row
 __global__ void layernorm_kernel(const float* __restrict__ in, int rows, int d, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, int pe_T, float* out_f32, __half* out_h,
-                                 int planes) {
+                                 int fmt) {
+    const int planes = act_planes(fmt);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -358,26 +377,21 @@ __global__ void layernorm_kernel(const float* __restrict__ in, int rows, int d, 
             y += (i & 1) ? cosf(ang) : sinf(ang);
         }
         if (out_f32) out_f32[static_cast<size_t>(row) * d + i] = y;
-        if (out_h) {
-            const __half hi = __float2half_rn(y);
-            out_h[static_cast<size_t>(row) * planes * d + i] = hi;
-            if (planes == 2) out_h[static_cast<size_t>(row) * planes * d + d + i] = __float2half_rn(y - __half2float(hi));
-        }
+        if (out_h) act_store(out_h + static_cast<size_t>(row) * planes * d, d, i, y, fmt);
     }
 }
 
-__global__ void h2f_kernel(const __half* __restrict__ in, long rows, int d, int planes, float* out) {
+__global__ void h2f_kernel(const __half* __restrict__ in, long rows, int d, int fmt, float* out) {
     const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
     if (idx >= rows * d) return;
     const long r = idx / d;
     const int i = static_cast<int>(idx % d);
-    float v = __half2float(in[r * planes * d + i]);
-    if (planes == 2) v += __half2float(in[r * planes * d + d + i]);
-    out[idx] = v;
+    out[idx] = act_load(in + r * act_planes(fmt) * d, d, i, fmt);
 }
 
 // One CTA per (line, head); K and V of the head staged in shared memory as fp32, one warp per query row.
-__global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, int D, int heads, __half* out, int planes) {
+__global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, int D, int heads, __half* out, int fmt) {
+    const int planes = act_planes(fmt);
     extern __shared__ float s_att[];
     const int dh = D / heads;
     float* sK = s_att;                 // [T][dh+1]
@@ -418,9 +432,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
             for (int tk = 0; tk < T; ++tk) acc = fmaf(p[tk], sV[tk * (dh + 1) + e], acc);
             acc *= inv;
             const size_t row = static_cast<size_t>(line) * T + tq;
-            const __half hi = __float2half_rn(acc);
-            out[row * planes * D + head * dh + e] = hi;
-            if (planes == 2) out[row * planes * D + D + head * dh + e] = __float2half_rn(acc - __half2float(hi));
+            act_store(out + row * planes * D, D, head * dh + e, acc, fmt);
         }
         __syncwarp();
     }
@@ -429,7 +441,8 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
 }  // namespace
 
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
-                              int act, int planes, __half* out, cudaStream_t stream) {
+                              int act, int fmt, __half* out, cudaStream_t stream) {
+    const int planes = act_planes(fmt);
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
     const int grid = n * ((h + CF_ROWS - 1) / CF_ROWS) * tiles_w;
     const size_t dyn = static_cast<size_t>(CF_PX) * planes * cout * sizeof(__half);
@@ -441,9 +454,9 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
         attr_done = true;
     }
     switch (cout) {
-        case 64: conv_first_kernel<64><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
-        case 32: conv_first_kernel<32><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
-        case 16: conv_first_kernel<16><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, planes, out); break;
+        case 64: conv_first_kernel<64><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
+        case 32: conv_first_kernel<32><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
+        case 16: conv_first_kernel<16><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -469,10 +482,10 @@ cudaError_t launch_ctc_collapse(const int32_t* best, const float* fprob, int n, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_lstm_ref(const float* pre, const float* w_hh_t, int n, int T, int H, int planes, int round_fp16,
+cudaError_t launch_lstm_ref(const float* pre, const float* w_hh_t, int n, int T, int H, int fmt, int round_fp16,
                             __half* out, cudaStream_t stream) {
     dim3 grid((n + LR_LINES - 1) / LR_LINES, 2);
-    lstm_ref_kernel<<<grid, H, LR_LINES * H * sizeof(float), stream>>>(pre, w_hh_t, n, T, H, planes, round_fp16, out);
+    lstm_ref_kernel<<<grid, H, LR_LINES * H * sizeof(float), stream>>>(pre, w_hh_t, n, T, H, fmt, round_fp16, out);
     return cudaGetLastError();
 }
 
@@ -490,19 +503,19 @@ cudaError_t launch_upsample_nchw(const float* in, int n, int h, int w, int c, in
 }
 
 cudaError_t launch_layernorm(const float* in, int rows, int d, const float* gamma, const float* beta, float eps,
-                             int pe_T, float* out_f32, __half* out_h, int planes, cudaStream_t stream) {
+                             int pe_T, float* out_f32, __half* out_h, int fmt, cudaStream_t stream) {
     layernorm_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(in, rows, d, gamma, beta, eps, pe_T, out_f32, out_h,
-                                                                  planes);
+                                                                  fmt);
     return cudaGetLastError();
 }
 
-cudaError_t launch_h2f(const __half* in, int rows, int d, int planes, float* out, cudaStream_t stream) {
+cudaError_t launch_h2f(const __half* in, int rows, int d, int fmt, float* out, cudaStream_t stream) {
     const long total = static_cast<long>(rows) * d;
-    h2f_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, rows, d, planes, out);
+    h2f_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, rows, d, fmt, out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int planes,
+cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int fmt,
                              cudaStream_t stream) {
     const int dh = D / heads;
     const int warps = 8;
@@ -514,6 +527,6 @@ cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, _
         attr_done = true;
     }
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
-    attention_kernel<<<n * heads, warps * 32, smem, stream>>>(qkv, n, T, D, heads, out, planes);
+    attention_kernel<<<n * heads, warps * 32, smem, stream>>>(qkv, n, T, D, heads, out, fmt);
     return cudaGetLastError();
 }

@@ -4,11 +4,13 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "actfmt.cuh"   // `fmt` arguments below are ActFormat values
+
 // u8 NHWC [n][h][w][3] -> x/255 -> 3x3 conv (pad 1) + bias + act -> fp16 NHWC [n][h][w][planes*cout]
 // (replaces the `/255` + permute of run_ocr, pytorch_ocr_engine.py:61-62, and the first conv of the blob).
 // w_t: fp32 [27][cout] (tap-major: (r*3+s)*3+c), cout <= 64.
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
-                              int act, int planes, __half* out, cudaStream_t stream);
+                              int act, int fmt, __half* out, cudaStream_t stream);
 
 // Per-frame argmax (first maximal index, NaN maximal) / max / logsumexp / sparsified-softmax best prob over
 // materialised scores.  layout 0 = [n][t][c], 1 = [n][c][t].
@@ -23,7 +25,7 @@ cudaError_t launch_ctc_collapse(const int32_t* best, const float* fprob, int n, 
 
 // CUDA-core bidirectional LSTM layer (cross-check path).  pre: fp32 [n*T][2*4H] (x W_ih^T + b_ih + b_hh, forward
 // gates then reverse gates, PyTorch order i,f,g,o); w_hh_t: fp32 [2][H][4H]; out: fp16 [n*T][planes*2H].
-cudaError_t launch_lstm_ref(const float* pre, const float* w_hh_t, int n, int T, int H, int planes, int round_fp16,
+cudaError_t launch_lstm_ref(const float* pre, const float* w_hh_t, int n, int T, int H, int fmt, int round_fp16,
                             __half* out, cudaStream_t stream);
 
 // nearest-neighbour upsampling fp32 [n][h][w][c] (NHWC) -> fp32 [n][c][h*f][w*f] (NCHW)  (ParseNet tail)
@@ -32,13 +34,13 @@ cudaError_t launch_upsample_nchw(const float* in, int n, int h, int w, int c, in
 // LayerNorm over channels (+ optional sinusoidal positional encoding indexed by t = row % T) of fp32 rows
 // [rows][d] -> fp32 [rows][d] and fp16 hi/lo [rows][planes*d]  (transformer.py:316-332, 378-381).
 cudaError_t launch_layernorm(const float* in, int rows, int d, const float* gamma, const float* beta, float eps,
-                             int pe_T, float* out_f32, __half* out_h, int planes, cudaStream_t stream);
+                             int pe_T, float* out_f32, __half* out_h, int fmt, cudaStream_t stream);
 
 // fp16 hi/lo NHWC [rows][planes*d] -> fp32 [rows][d]
-cudaError_t launch_h2f(const __half* in, int rows, int d, int planes, float* out, cudaStream_t stream);
+cudaError_t launch_h2f(const __half* in, int rows, int d, int fmt, float* out, cudaStream_t stream);
 
 // Multi-head self-attention over one line: qkv fp32 [n*T][3*D] (q | k | v), heads of D/heads -> fp16 hi/lo
 // [n*T][planes*D].  softmax(q k^T / sqrt(dh)) v, fp32 math  (nn.MultiheadAttention inside
 // nn.TransformerEncoderLayer, transformer.py:371-373).
-cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int planes,
+cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int fmt,
                              cudaStream_t stream);

@@ -18,6 +18,7 @@
 //     (Measured alternatives: plain st.shared::cluster stores + remote mbarrier arrives were 2x slower; separate
 //     copies per plane doubled the step time -- a bulk push costs ~0.5 us and pushes serialise.)
 #include "lstm_tc.cuh"
+#include "actfmt.cuh"
 #include "ptx.cuh"
 
 namespace {
@@ -84,7 +85,7 @@ __device__ __forceinline__ float tanh_(float x) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, __half* __restrict__ out,
-               int n_lines, int T, int planes, int line_groups) {
+               int n_lines, int T, int planes, int out_fmt, int line_groups) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sH = smem;                                  // 2 buffers * planes * 16 KB
@@ -248,6 +249,7 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
             hv[e] = og * tanh_(c_state[e]);
         }
         uint32_t hi_w[2], lo_w[2];
+        float hf4[4];
 #pragma unroll
         for (int e = 0; e < 4; e += 2) {
             const __half2 h2 = __floats2half2_rn(hv[e], hv[e + 1]);
@@ -255,11 +257,22 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
             const __half2 l2 = __floats2half2_rn(hv[e] - hf.x, hv[e + 1] - hf.y);
             hi_w[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
             lo_w[e >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+            hf4[e] = hf.x;
+            hf4[e + 1] = hf.y;
         }
         if (line_ok) {
-            __half* o = out + row * (planes * 2 * kH) + dir * kH + unit0;
+            // next layer's GEMM operand record (actfmt.cuh): [2H fp16 hi][second plane]
+            __half* rec = out + row * (act_planes(out_fmt) * 2 * kH);
+            __half* o = rec + dir * kH + unit0;
             *reinterpret_cast<uint2*>(o) = make_uint2(hi_w[0], hi_w[1]);
-            if (planes == 2) *reinterpret_cast<uint2*>(o + 2 * kH) = make_uint2(lo_w[0], lo_w[1]);
+            if (out_fmt == ACT_F16_HILO) {
+                *reinterpret_cast<uint2*>(o + 2 * kH) = make_uint2(lo_w[0], lo_w[1]);
+            } else if (out_fmt == ACT_F16_F8) {
+                uint8_t* b = reinterpret_cast<uint8_t*>(rec + 2 * kH) + dir * kH + unit0;
+                *reinterpret_cast<uint32_t*>(b) = pack_e5m2x4((hv[0] - hf4[0]) * kF8Scale, (hv[1] - hf4[1]) * kF8Scale,
+                                                              (hv[2] - hf4[2]) * kF8Scale, (hv[3] - hf4[3]) * kF8Scale);
+                *reinterpret_cast<uint32_t*>(b + 2 * kH) = pack_e5m2x4(hf4[0], hf4[1], hf4[2], hf4[3]);
+            }
         }
         if (s + 1 < T) {
             // own slice (hi | lo contiguous) of the next B buffer, then ONE bulk push per peer: a cp.async.bulk
@@ -300,7 +313,7 @@ size_t lstm_tc_smem_bytes(int planes) {
 }
 
 cudaError_t launch_lstm_tc(const __half* w_rec, const float* pre, __half* out, int n_lines, int T, int H, int planes,
-                           cudaStream_t stream) {
+                           int out_fmt, cudaStream_t stream) {
     if (H != kH) return cudaErrorInvalidValue;
     const size_t smem = lstm_tc_smem_bytes(planes);
     static bool attr_done = false;
@@ -322,5 +335,5 @@ cudaError_t launch_lstm_tc(const __half* w_rec, const float* pre, __half* out, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, lstm_tc_kernel, w_rec, pre, out, n_lines, T, planes, line_groups);
+    return cudaLaunchKernelEx(&cfg, lstm_tc_kernel, w_rec, pre, out, n_lines, T, planes, out_fmt, line_groups);
 }

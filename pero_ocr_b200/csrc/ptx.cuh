@@ -104,6 +104,16 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T, 8-bit float operands (K = 32 per instruction), fp32 accumulate, one CTA.
+__device__ __forceinline__ void mma_f8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
@@ -154,6 +164,12 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+
+// kind::f8f6f4 instruction descriptor: e5m2 A/B (format 1), fp32 accumulate, both operands K-major, dense.
+__host__ __device__ constexpr uint32_t idesc_e5m2_f32(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
 
 // ---------------------------------------------------------------- predicated single-issue forms
 // Executed by ALL lanes of a converged warp with warp-uniform operands (so ptxas keeps them in uniform registers

@@ -5,6 +5,7 @@ Tolerances (BASELINE.json north_star: "bit-exact CTC argmax indices; logits with
   * precision 'fp16x3' (default): |logit - reference| <= 1e-3 absolute; per-frame argmax identical on every frame
     whose reference top-2 margin exceeds 2e-3 (closer calls are numerically undecidable between any two fp32
     implementations); transcriptions identical.
+  * precision 'fp16f8' (fp16 pass + e5m2 first-order correction pass, 2 pass-equivalents): the same bars as 'fp16x3'.
   * precision 'fp16' (single-pass, same 10-bit mantissa as the reference's own cuDNN-TF32 GPU path): 3e-3 * max|logit|.
 """
 import numpy as np
@@ -29,10 +30,11 @@ def _engine(tmp_path, kind, precision='fp16x3', batch_size=None):
                              precision=precision, module=make_case_net(kind))
 
 
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16f8'])
 @pytest.mark.parametrize('kind', ['lstm', 'transformer'])
-def test_process_lines_matches_reference_golden(tmp_path, golden_dir, kind):
+def test_process_lines_matches_reference_golden(tmp_path, golden_dir, kind, precision):
     gold = load_golden(golden_dir, f'engine_{kind}.npz')
-    eng = _engine(tmp_path, kind)
+    eng = _engine(tmp_path, kind, precision=precision)
     lines = cases.engine_lines(kind)
     tr, lg, co = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
     assert eng.characters == list(gold['chars'])
@@ -102,13 +104,14 @@ def test_single_pass_fp16_mode(tmp_path, golden_dir):
     assert agree / total > 0.97
 
 
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16f8'])
 @pytest.mark.parametrize('kind', ['lstm', 'transformer'])
-def test_tensor_core_kernels_match_cuda_core_cross_check(kind):
+def test_tensor_core_kernels_match_cuda_core_cross_check(kind, precision):
     from pero_ocr_b200 import netdesc
     from pero_ocr_b200.engine import LineRecognizer
     net = make_case_net(kind)
     layers, _ = netdesc.describe_line_net(net)
-    eng = LineRecognizer(layers, precision='fp16x3')
+    eng = LineRecognizer(layers, precision=precision)
     rng = np.random.default_rng(3)
     crops = torch.from_numpy(rng.integers(0, 256, (5, 40, 328, 3), dtype=np.uint8)).cuda()
     a = eng.forward(crops, want_logits=True, want_best_path=True)
@@ -172,15 +175,16 @@ def test_full_size_properties():
         assert [list(lab[i, :ln[i]]) for i in range(2)] == [list(w) for w in want]
 
 
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16f8'])
 @pytest.mark.parametrize('width', [136, 264, 520])
-def test_halo_kernel_matches_per_tap_kernel(width):
+def test_halo_kernel_matches_per_tap_kernel(width, precision):
     """The halo-reuse 3x3 kernel (shifted swizzle-128B views) and the per-tap TMA kernel are two implementations of
     the same contraction: identical operands, fp32 accumulation in a different order."""
     from pero_ocr_b200 import netdesc
     from pero_ocr_b200.engine import LineRecognizer
     net = make_case_net('lstm')
     layers, _ = netdesc.describe_line_net(net)
-    eng = LineRecognizer(layers, precision='fp16x3')
+    eng = LineRecognizer(layers, precision=precision)
     rng = np.random.default_rng(width)
     crops = torch.from_numpy(rng.integers(0, 256, (3, 40, width, 3), dtype=np.uint8)).cuda()
     a = {k: v.clone() for k, v in eng.forward(crops, want_logits=True).items()}

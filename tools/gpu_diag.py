@@ -51,7 +51,7 @@ def main():
         ref_logits = net(x).permute(0, 2, 1).numpy()     # [N,T,C]
     dcrops = torch.from_numpy(crops).cuda()
     n_front = sum(1 for l in layers if l['kind'] in (1, 2))
-    for prec in ('fp16x3', 'fp16'):
+    for prec in (sys.argv[2].split(',') if len(sys.argv) > 2 else ('fp16x3', 'fp16f8', 'fp16')):
         print(f'===== {kind} precision {prec}', flush=True)
         try:
             eng = LineRecognizer(layers, precision=prec)
