@@ -196,7 +196,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16f8', 'fp16'])
+    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16f8'), choices=['fp16x3', 'fp16f8', 'fp16'])
     ap.add_argument('--net', default='lstm', choices=['lstm', 'transformer'])
     ap.add_argument('--ref-lines', type=int, default=96, help='lines per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-lines', type=int, default=512, help='bounded CPU sample (about 10-20 s of host work)')

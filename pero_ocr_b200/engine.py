@@ -16,12 +16,13 @@ from os.path import dirname, isabs, join, realpath
 import numpy as np
 
 from . import _lib, netdesc
+from ._lib import DEFAULT_PRECISION
 
 
 class LineRecognizer:
     """Thin handle over one native engine (one per device, not thread-safe -- like the reference engines)."""
 
-    def __init__(self, layers, precision='fp16x3', line_height=40, device=0):
+    def __init__(self, layers, precision=DEFAULT_PRECISION, line_height=40, device=0):
         import torch
         self._lib = _lib.load_library()
         if not torch.cuda.is_available():
@@ -142,7 +143,7 @@ class B200EngineLineOCR:
     Embedding-conditioned nets (``embed_id``) are not supported and raise at construction.
     """
 
-    def __init__(self, json_def, device=None, batch_size=8, precision='fp16x3', module=None):
+    def __init__(self, json_def, device=None, batch_size=8, precision=DEFAULT_PRECISION, module=None):
         import torch
         with open(json_def, 'r', encoding='utf8') as f:
             self.config = json.load(f)

@@ -10,11 +10,12 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, netdesc
+from ._lib import DEFAULT_PRECISION
 
 
 class B200ParseNet:
     def __init__(self, model_path, device=None, downsample=4, max_mp=5, detection_threshold=0.2,
-                 adaptive_downsample=True, precision='fp16x3', module=None):
+                 adaptive_downsample=True, precision=DEFAULT_PRECISION, module=None):
         import torch
         import cv2  # noqa: F401  (host-side resize, as in the reference)
         if not torch.cuda.is_available():
