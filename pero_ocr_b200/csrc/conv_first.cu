@@ -1,0 +1,232 @@
+// First convolution of the recogniser (3 -> COUT channels, 3x3, pad 1) fused with the reference's `/255` and
+// NHWC -> NCHW permute (pero_ocr/ocr_engine/pytorch_ocr_engine.py:61-62) -- the bytes of the padded crop batch are
+// the operand.
+//
+// K = 27 is far too short for a tcgen05 pipeline (one 128 x 64 x 32 MMA per 128 pixels against 32 KB of output),
+// and on CUDA cores the layer was issue-bound at ~30 % of the FMA peak (1728 FMAs per pixel fed by shared-memory
+// weight broadcasts).  Here it runs on warp-level mma.sync (m16n8k16, fp16 operands, fp32 accumulate):
+//   * the uint8 pixels are exact in fp16, so the A operand is the raw byte value and the 1/255 moves to the epilogue;
+//   * the weights are normalised per output channel by a power of two s_n (largest |w| in [0.5, 1)) and split
+//     w / s_n = hi + lo into two fp16 operands -- both products accumulate into the same fp32 registers, so the layer
+//     keeps fp32-grade accuracy (|lo| error <= 2^-25 of the channel's largest weight);
+//   * K is laid out as k = 10 r + (3 s + c) (slots 9, 19, 29, 30, 31 are zero weights), so that an A-fragment
+//     register (two consecutive k) is two consecutive fp16 of one row of the staged input patch;
+//   * epilogue: acc * (s_n / 255) + bias -> activation -> activation record (actfmt.cuh) staged in shared memory
+//     (16-byte chunks XOR-swizzled by pixel: conflict-free fragment writes and conflict-free record reads) ->
+//     fully coalesced 16-byte stores.  The kernel is bound by that store stream (the 64-channel hi|lo records of
+//     a 256 x 40 x 1344 batch are 3.5 GB).
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int CFM_PX = 128;      // output pixels per CTA row (4 warps x 32)
+constexpr int CFM_ROWS = 4;      // image rows per CTA
+constexpr int CFM_PSTRIDE = 392; // fp16 per staged patch row: 130 pixels x 3 channels + 2 pad
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float cfm_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t ld_pair(const __half* p) {   // two consecutive fp16 at any 2-byte alignment
+    const uint32_t lo = *reinterpret_cast<const unsigned short*>(p);
+    const uint32_t hi = *reinterpret_cast<const unsigned short*>(p + 1);
+    return lo | (hi << 16);
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(CFM_PX, 3) conv_first_mma_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
+                                                              const uint2* __restrict__ wfrag,
+                                                              const float* __restrict__ oscale,
+                                                              const float* __restrict__ bias, int act, int fmt,
+                                                              __half* __restrict__ out) {
+    constexpr int NT = COUT / 8;
+    const int planes = act_planes(fmt);
+    __shared__ __align__(16) __half s_p[(CFM_ROWS + 2) * CFM_PSTRIDE];
+    __shared__ float s_sc[COUT], s_b[COUT];
+    extern __shared__ uint4 s_stage[];   // [CFM_PX][planes * COUT / 8]: one image row of pixel records
+
+    const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
+    const int tiles_h = (h + CFM_ROWS - 1) / CFM_ROWS;
+    const int tw = blockIdx.x % tiles_w;
+    const int row0 = ((blockIdx.x / tiles_w) % tiles_h) * CFM_ROWS;
+    const int img = blockIdx.x / (tiles_w * tiles_h);
+    const int w0 = tw * CFM_PX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+
+    // weight fragments: registers for the whole kernel ([plane][k step][n tile] x {b0b1, b2b3})
+    uint2 bf[2][2][NT];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bf[p][ks][nt] = __ldg(wfrag + ((p * 2 + ks) * NT + nt) * 32 + lane);
+    for (int i = threadIdx.x; i < COUT; i += CFM_PX) {
+        s_sc[i] = oscale[i];
+        s_b[i] = bias ? bias[i] : 0.f;
+    }
+    // input patch (rows row0-1 .. row0+CFM_ROWS, pixels w0-1 .. w0+128) as fp16 byte values, zero outside the image
+    constexpr int kRowVals = (CFM_PX + 2) * 3;
+    for (int i = threadIdx.x; i < (CFM_ROWS + 2) * CFM_PSTRIDE; i += CFM_PX) {
+        const int r = i / CFM_PSTRIDE;
+        const int b = i - r * CFM_PSTRIDE;
+        const int yy = row0 + r - 1;
+        const int xb = (w0 - 1) * 3 + b;
+        unsigned short v = 0;
+        if (b < kRowVals && yy >= 0 && yy < h && xb >= 0 && xb < w * 3)
+            v = in[(static_cast<size_t>(img) * h + yy) * w * 3 + xb];
+        s_p[i] = __ushort2half_rn(v);
+    }
+    // patch offsets of this thread's A-fragment columns: k = 16 ks + 2 tig (+ 8) -> row r = k / 10, value j = k % 10
+    int aoff[2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int k = ks * 16 + tig * 2 + 8 * hh;
+            aoff[ks][hh] = k < 30 ? (k / 10) * CFM_PSTRIDE + (k % 10) : 0;   // k >= 30: zero weights, any finite value
+        }
+    __syncthreads();
+
+    const int rec = planes * COUT;
+    const int chunks = rec / 8;                 // 16-byte chunks per pixel record
+    for (int rr = 0; rr < CFM_ROWS; ++rr) {
+        const int row = row0 + rr;
+        if (row >= h) break;
+        if (rr) __syncthreads();                // previous row's staging has been read
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int pb = warp * 32 + mt * 16;
+            const __half* p0 = s_p + rr * CFM_PSTRIDE + 3 * (pb + gid);
+            const __half* p1 = p0 + 3 * 8;
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t a[4];
+                a[0] = ld_pair(p0 + aoff[ks][0]);
+                a[1] = ld_pair(p1 + aoff[ks][0]);
+                a[2] = ld_pair(p0 + aoff[ks][1]);
+                a[3] = ld_pair(p1 + aoff[ks][1]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma16816(acc[nt], a, bf[0][ks][nt].x, bf[0][ks][nt].y);
+                    mma16816(acc[nt], a, bf[1][ks][nt].x, bf[1][ks][nt].y);
+                }
+            }
+            // fragment -> staged records: rows (pixels) pb+gid and pb+gid+8, channels 8 nt + 2 tig + {0, 1}
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int px = pb + gid + 8 * half;
+                uint4* my = s_stage + px * chunks;
+                const int sw = px & (chunks - 1);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int ch = nt * 8 + tig * 2;
+                    const float v0 = cfm_act(fmaf(acc[nt][2 * half], s_sc[ch], s_b[ch]), act);
+                    const float v1 = cfm_act(fmaf(acc[nt][2 * half + 1], s_sc[ch + 1], s_b[ch + 1]), act);
+                    const __half2 h2 = __floats2half2_rn(v0, v1);
+                    reinterpret_cast<uint32_t*>(my + (nt ^ sw))[tig] = *reinterpret_cast<const uint32_t*>(&h2);
+                    if (fmt != ACT_F16) {
+                        const float2 hf = __half22float2(h2);
+                        if (fmt == ACT_F16_HILO) {
+                            const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                            reinterpret_cast<uint32_t*>(my + ((NT + nt) ^ sw))[tig] = *reinterpret_cast<const uint32_t*>(&l2);
+                        } else {
+                            const unsigned short lo8 =
+                                static_cast<unsigned short>(pack_e5m2x2((v0 - hf.x) * kF8Scale, (v1 - hf.y) * kF8Scale));
+                            const unsigned short hi8 = static_cast<unsigned short>(pack_e5m2x2(hf.x, hf.y));
+                            const int sub = (nt & 1) * 4 + tig;   // 16-bit slot inside the 16-byte chunk
+                            reinterpret_cast<unsigned short*>(my + ((NT + (nt >> 1)) ^ sw))[sub] = lo8;
+                            reinterpret_cast<unsigned short*>(my + ((NT + NT / 2 + (nt >> 1)) ^ sw))[sub] = hi8;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int npx = min(CFM_PX, w - w0);
+            uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row) * w + w0) * rec);
+            for (int i = threadIdx.x; i < npx * chunks; i += CFM_PX) {
+                const int px = i / chunks, c = i - px * chunks;
+                dst[i] = s_stage[px * chunks + (c ^ (px & (chunks - 1)))];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t conv_first_wfrag_words(int cout) { return static_cast<size_t>(2) * 2 * (cout / 8) * 32 * 2; }
+
+void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* oscale) {
+    // weight: PyTorch [cout][3][3][3] (o, c, r, s).  K slot k = 10 r + 3 s + c.
+    for (int o = 0; o < cout; ++o) {
+        float m = 0.f;
+        for (int i = 0; i < 27; ++i) m = fmaxf(m, fabsf(weight[o * 27 + i]));
+        int ex = 0;
+        if (m > 0.f) frexpf(m, &ex);             // m = f * 2^ex, f in [0.5, 1)
+        oscale[o] = ldexpf(1.f, ex) / 255.0f;    // folded with the reference's /255
+    }
+    auto wk = [&](int o, int k, int plane) -> __half {
+        if (k >= 30 || k % 10 == 9) return __float2half_rn(0.f);
+        const int r = k / 10, j = k % 10, s = j / 3, c = j % 3;
+        int ex = 0;
+        float m = 0.f;
+        for (int i = 0; i < 27; ++i) m = fmaxf(m, fabsf(weight[o * 27 + i]));
+        if (m > 0.f) frexpf(m, &ex);
+        const float v = ldexpf(weight[((o * 3 + c) * 3 + r) * 3 + s], -ex);
+        const __half hi = __float2half_rn(v);
+        return plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    };
+    const int NT = cout / 8;
+    for (int p = 0; p < 2; ++p)
+        for (int ks = 0; ks < 2; ++ks)
+            for (int nt = 0; nt < NT; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int gid = lane >> 2, tig = lane & 3, o = nt * 8 + gid;
+                    for (int q = 0; q < 2; ++q) {
+                        const int k = ks * 16 + tig * 2 + 8 * q;
+                        const __half a = wk(o, k, p), b = wk(o, k + 1, p);
+                        const uint32_t lo = *reinterpret_cast<const unsigned short*>(&a);
+                        const uint32_t hi = *reinterpret_cast<const unsigned short*>(&b);
+                        wfrag[((((p * 2 + ks) * NT + nt) * 32) + lane) * 2 + q] = lo | (hi << 16);
+                    }
+                }
+}
+
+cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
+                                  const float* bias, int cout, int act, int fmt, __half* out, cudaStream_t stream) {
+    const int planes = act_planes(fmt);
+    const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
+    const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
+    const size_t dyn = static_cast<size_t>(CFM_PX) * planes * cout * sizeof(__half);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_first_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(conv_first_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(conv_first_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
+    }
+    const uint2* wf = reinterpret_cast<const uint2*>(wfrag);
+    switch (cout) {
+        case 64: conv_first_mma_kernel<64><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out); break;
+        case 32: conv_first_mma_kernel<32><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out); break;
+        case 16: conv_first_mma_kernel<16><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}

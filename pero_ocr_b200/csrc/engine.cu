@@ -54,6 +54,8 @@ struct LayerRT {
     Gemm g;                  // CONV / CTC_HEAD / BILSTM input projection
     float* w_t = nullptr;    // CONV_FIRST: fp32 [27][cout]
     float* bias0 = nullptr;  // CONV_FIRST
+    uint32_t* wfrag0 = nullptr;   // CONV_FIRST: mma.sync weight fragments (conv_first.cu)
+    float* oscale0 = nullptr;     // CONV_FIRST: per-channel power-of-two weight scale / 255
     int cout0 = 0;
     int hidden = 0;          // BILSTM
     __half* w_rec = nullptr;
@@ -336,8 +338,13 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                 else {
                     if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
                     ProfScope ps(e, st, PROF_CONV_FIRST);
-                    CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
-                                                e->fmt, static_cast<__half*>(e->hbuf[slot]), st));
+                    if (e->use_ref)   // CUDA-core fp32 cross-check kernel
+                        CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
+                                                    e->fmt, static_cast<__half*>(e->hbuf[slot]), st));
+                    else
+                        CU_TRY(e, launch_conv_first_mma(crops, cur.n, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
+                                                        ly.cout0, ly.act, e->fmt, static_cast<__half*>(e->hbuf[slot]),
+                                                        st));
                     e->launches++;
                     cur_h = static_cast<__half*>(e->hbuf[slot]);
                 }
@@ -602,6 +609,11 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                 ly.cout0 = d.cout;
                 if ((s = upload(e, wt.data(), wt.size(), &ly.w_t))) return bail(s);
                 if (d.bias && (s = upload(e, d.bias, (size_t)d.cout, &ly.bias0))) return bail(s);
+                std::vector<uint32_t> wf(conv_first_wfrag_words(d.cout));
+                std::vector<float> osc(d.cout);
+                conv_first_pack(d.weight, d.cout, wf.data(), osc.data());
+                if ((s = upload(e, wf.data(), wf.size(), &ly.wfrag0))) return bail(s);
+                if ((s = upload(e, osc.data(), osc.size(), &ly.oscale0))) return bail(s);
                 break;
             }
             case B200OCR_CONV:

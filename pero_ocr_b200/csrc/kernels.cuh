@@ -12,6 +12,14 @@
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
                               int act, int fmt, __half* out, cudaStream_t stream);
 
+// The same layer on warp-level tensor cores (conv_first.cu; the product path -- the kernel above is the fp32
+// cross-check).  conv_first_pack turns the PyTorch weight [cout][3][3][3] into per-lane mma.sync fragments
+// (conv_first_wfrag_words(cout) 32-bit words) and the per-channel epilogue scale (power-of-two weight scale / 255).
+cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
+                                  const float* bias, int cout, int act, int fmt, __half* out, cudaStream_t stream);
+size_t conv_first_wfrag_words(int cout);
+void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* oscale);
+
 // Per-frame argmax (first maximal index, NaN maximal) / max / logsumexp / sparsified-softmax best prob over
 // materialised scores.  layout 0 = [n][t][c], 1 = [n][c][t].
 cudaError_t launch_frame_stats(const float* scores, int n, int t, int c, int layout, int32_t* best, float* fmax,

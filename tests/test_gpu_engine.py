@@ -193,3 +193,30 @@ def test_halo_kernel_matches_per_tap_kernel(width, precision):
     torch.cuda.synchronize()
     assert (a['logits'] - b['logits']).abs().max().item() <= 2e-4
     assert torch.equal(a['labels'], b['labels'])
+
+
+@pytest.mark.parametrize('width', [40, 136, 264])
+def test_first_conv_tensor_core_kernel_is_fp32_grade(width):
+    """conv_first.cu (mma.sync, weights split hi+lo per channel scale, 1/255 in the epilogue) against torch fp32
+    conv2d(x / 255) and against the CUDA-core fp32 cross-check kernel, read back after the first layer.  The fp16x3
+    record (hi + lo) resolves ~2^-22 of the value, so the bar is a few fp32 ulps of the largest activation."""
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    net = make_case_net('lstm')
+    layers, _ = netdesc.describe_line_net(net)
+    eng = LineRecognizer(layers, precision='fp16x3')
+    rng = np.random.default_rng(width)
+    crops = rng.integers(0, 256, (3, 40, width, 3), dtype=np.uint8)
+    crops[0, :, :7] = 255                                   # saturated block at the left edge
+    crops[1] = 0                                            # all-zero line: output = act(bias)
+    d = torch.from_numpy(crops).cuda()
+    got = eng.debug_forward_prefix(d, 1)                    # [n, h, w, 64] fp32
+    eng.use_reference_kernels(True)
+    ref_kernel = eng.debug_forward_prefix(d, 1)
+    conv = net.conv[0]
+    with torch.no_grad():
+        x = torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)
+        want = torch.relu(conv(x)).permute(0, 2, 3, 1).numpy()
+    scale = float(np.abs(want).max())
+    assert np.abs(ref_kernel - want).max() <= 4e-6 * max(scale, 1.0)
+    assert np.abs(got - want).max() <= 4e-6 * max(scale, 1.0)
