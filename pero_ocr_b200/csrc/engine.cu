@@ -261,6 +261,10 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     p.out_fmt = e->fmt;
     p.acc_scale = e->fmt == ACT_F16_F8 ? 1.f / kF8Scale : 1.f;
     p.out_f32 = o.out_f32; p.best = o.best; p.fmax = o.fmax; p.flse = o.flse; p.fprob = o.fprob;
+    {
+        static const int dbg = getenv("B200OCR_IGEMM_DBG") ? atoi(getenv("B200OCR_IGEMM_DBG")) : 0;   // bring-up only
+        p.dbg = dbg;
+    }
     if (o.epi == EPI_ACT_F16 && (g.cout % 32))
         return fail(e, B200OCR_E_INVALID, "fp16 activation output needs cout %% 32 == 0 (got %d)", g.cout);
     if (o.epi == EPI_CTC && p.tiles_n != 1)

@@ -46,6 +46,7 @@ struct IgemmParams {
     float* fmax;
     float* flse;
     float* fprob;             // best-class probability under the reference's sparsified softmax (or null)
+    int dbg;                  // bring-up switches (B200OCR_IGEMM_DBG): 1 = skip epilogue stores, 2 = skip MMA issue
 };
 
 inline void igemm_fill_geometry(IgemmParams& p, int bn) {

@@ -19,14 +19,20 @@ constexpr int kThreads = 352;
 constexpr int kHaloW = 130, kHaloH = 4;
 constexpr int kHaloBytes = kHaloH * kHaloW * 128;             // 66,560
 constexpr int kHaloStage = ((kHaloBytes + 1023) / 1024) * 1024;  // 66,560 -> 66,560 (65 KB) multiple of 1024
-constexpr int kAStages = 2;
 
 template <int BN>
 struct Cfg {
     static constexpr int kBBytes = BN * 128;
-    static constexpr int kBStages = BN == 64 ? 8 : 4;
+    // An N = 64 MMA lasts 32 clocks, so with one filter tap per weight stage (8 MMAs) the single issuing thread spent
+    // longer on the per-stage wait / commit / ring bookkeeping than the tensor pipe on the MMAs (ncu: pipe 41 %
+    // busy, issuer never blocked on a barrier).  BN = 64 therefore streams a whole filter ROW (3 taps, 24 MMAs) per
+    // stage.  (A third halo stage instead made no difference: the halo loads are not the limiter.)
+    static constexpr int kTapsPerStage = BN == 64 ? 3 : 1;
+    static constexpr int kAStages = 2;
+    static constexpr int kBStages = BN == 64 ? 3 : 4;
+    static constexpr int kBStageBytes = kTapsPerStage * kBBytes;
     static constexpr int kTmemCols = 512;
-    static constexpr int kBarOff = kAStages * kHaloStage + kBStages * kBBytes;
+    static constexpr int kBarOff = kAStages * kHaloStage + kBStages * kBStageBytes;
     static constexpr int kSmemBytes = kBarOff + 256 + 1024;
 };
 
@@ -54,11 +60,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = smem + kAStages * kHaloStage;
+    uint8_t* sB = smem + C::kAStages * kHaloStage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
     uint64_t* a_full = bars;                              // [kAStages]
-    uint64_t* a_empty = a_full + kAStages;                // [kAStages]
-    uint64_t* b_full = a_empty + kAStages;                // [kBStages]
+    uint64_t* a_empty = a_full + C::kAStages;             // [kAStages]
+    uint64_t* b_full = a_empty + C::kAStages;                // [kBStages]
     uint64_t* b_empty = b_full + C::kBStages;             // [kBStages]
     uint64_t* tfull = b_empty + C::kBStages;              // [2]
     uint64_t* tempty = tfull + 2;                         // [2]
@@ -75,7 +81,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
-        for (int i = 0; i < kAStages; ++i) {
+        for (int i = 0; i < C::kAStages; ++i) {
             ptx::mbar_init(&a_full[i], 1);
             ptx::mbar_init(&a_empty[i], 1);
         }
@@ -114,7 +120,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     ptx::mbar_expect_tx_pred(&a_full[stage], kHaloBytes, leader);
                     ptx::tma_load_4d_pred(sA + stage * kHaloStage, &tmA, &a_full[stage], ap * p.cin + kc * 64,
                                           t.w0 - 1, t.h0 - 1, t.img, leader);
-                    if (++stage == kAStages) {
+                    if (++stage == C::kAStages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -132,11 +138,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     // fp16x3: A_hi meets B_hi and B_lo, A_lo meets B_hi only; fp16+fp8: A plane ap meets B plane ap
                     const int nbp = (ap == 0 && !f8) ? planes : 1;
                     for (int bp = 0; bp < nbp; ++bp)
-                        for (int tap = 0; tap < 9; ++tap) {
+                        for (int tap = 0; tap < 9; tap += C::kTapsPerStage) {
                             ptx::mbar_wait(&b_empty[stage], phase ^ 1);
-                            ptx::mbar_expect_tx_pred(&b_full[stage], C::kBBytes, leader);
-                            ptx::tma_load_2d_pred(sB + stage * C::kBBytes, &tmB, &b_full[stage], kc * 64,
-                                                  ((f8 ? ap : bp) * 9 + tap) * p.cout_pad + t.nt * BN, leader);
+                            ptx::mbar_expect_tx_pred(&b_full[stage], C::kBStageBytes, leader);
+#pragma unroll
+                            for (int tt = 0; tt < C::kTapsPerStage; ++tt)
+                                ptx::tma_load_2d_pred(sB + stage * C::kBStageBytes + tt * C::kBBytes, &tmB, &b_full[stage],
+                                                      kc * 64, ((f8 ? ap : bp) * 9 + tap + tt) * p.cout_pad + t.nt * BN,
+                                                      leader);
                             if (++stage == C::kBStages) {
                                 stage = 0;
                                 phase ^= 1;
@@ -146,45 +155,56 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 2) {
         // ------------------------------------------------------------------ MMA issuer
-        // One elected thread runs the whole role (waits included): no per-stage reconvergence, every operand in
-        // uniform registers, tap loop fully unrolled so the shifted-view offsets are immediates.
+        // One elected thread runs the whole role (waits included): no per-stage reconvergence; the plane and tap loops
+        // are unrolled, so the operand kind is a compile-time fact and the shifted-view offsets are immediates.
+        // (Running the loop nest warp-wide with lane-predicated MMAs was tried: ptxas then emits an R2UR + VOTEU pair
+        // per operand of every MMA.)
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::idesc_f16_f32(128, BN);
             constexpr uint32_t idesc8 = ptx::idesc_e5m2_f32(128, BN);
             const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
             const uint64_t desc_hi = ptx::smem_desc_sw128(0);   // descriptor with a zero start-address field
+            const bool skip_mma = (p.dbg & 2) != 0;             // bring-up: time the pipeline without tensor work
             int as = 0, bs = 0, acc = 0;
             uint32_t aph = 0, bph = 0, acc_phase0 = 0, acc_phase1 = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d0 = tmem_base + acc * 2 * BN;
-                uint32_t started = 0;
-                for (int kc = 0; kc < kchunks; ++kc)
+                for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
                     for (int ap = 0; ap < planes; ++ap) {
                         ptx::mbar_wait(&a_full[as], aph);
                         const uint64_t a_base = desc_hi + ((sA_u + as * kHaloStage) >> 4);
                         const int nbp = (ap == 0 && !f8) ? planes : 1;
                         const bool e5m2 = f8 && ap == 1;
-                        for (int bp = 0; bp < nbp; ++bp) {
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
+                        for (int bp = 0; bp < nbp; ++bp) {
+                            // the very first MMA of a tile overwrites the accumulators
+                            const uint32_t started = (ap | bp) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+#pragma unroll
+                            for (int tap0 = 0; tap0 < 9; tap0 += C::kTapsPerStage) {
                                 ptx::mbar_wait(&b_full[bs], bph);
                                 ptx::tc_fence_after();
-                                const uint64_t b_desc = desc_hi + ((sB_u + bs * C::kBBytes) >> 4);
+                                if (!skip_mma) {
 #pragma unroll
-                                for (int r = 0; r < 2; ++r) {
-                                    // pixel ((r + tap/3) * 130 + tap%3) of the halo, 128 B per pixel, >>4 encoded
-                                    const uint64_t a_desc = a_base + (((r + tap / 3) * kHaloW + tap % 3) * 8);
-                                    if (e5m2) {
+                                    for (int tt = 0; tt < C::kTapsPerStage; ++tt) {
+                                        const int tap = tap0 + tt;
+                                        const uint64_t b_desc =
+                                            desc_hi + ((sB_u + bs * C::kBStageBytes + tt * C::kBBytes) >> 4);
 #pragma unroll
-                                        for (int k = 0; k < 4; ++k)
-                                            ptx::mma_f8_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1u);
-                                    } else {
+                                        for (int r = 0; r < 2; ++r) {
+                                            // pixel ((r + tap/3) * 130 + tap%3) of the halo, 128 B per pixel, >>4 encoded
+                                            const uint64_t a_desc = a_base + (((r + tap / 3) * kHaloW + tap % 3) * 8);
 #pragma unroll
-                                        for (int k = 0; k < 4; ++k)
-                                            ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                                            (tap | k) != 0 ? 1u : started);
+                                            for (int k = 0; k < 4; ++k) {
+                                                if (e5m2)
+                                                    ptx::mma_f8_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1u);
+                                                else
+                                                    ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                                                    (tap | k) != 0 ? 1u : started);
+                                            }
+                                        }
                                     }
                                 }
                                 ptx::mma_commit(&b_empty[bs]);
@@ -193,14 +213,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     bph ^= 1;
                                 }
                             }
-                            started = 1;
                         }
                         ptx::mma_commit(&a_empty[as]);
-                        if (++as == kAStages) {
+                        if (++as == C::kAStages) {
                             as = 0;
                             aph ^= 1;
                         }
                     }
+                }
                 ptx::mma_commit(&tfull[acc]);
                 if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
                 acc ^= 1;
@@ -259,8 +279,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (!writer || ho >= p.h_out) continue;
                     __half* orow = p.out_h + (static_cast<size_t>(t.img) * Hp * Wp +
                                               static_cast<size_t>(ho / p.pool_h) * Wp + wo / p.pool_w) * p.out_cstride;
-                    epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow,
-                                p.cout, FMT);
+                    if (!(p.dbg & 1))   // bring-up: time the pipeline without the global stores
+                        epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow,
+                                    p.cout, FMT);
                 }
             }
             ptx::tc_fence_before();

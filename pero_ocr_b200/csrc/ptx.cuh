@@ -208,6 +208,15 @@ __device__ __forceinline__ void mma_f16_ss_pred(uint32_t d_tmem, uint64_t a_desc
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
         : "memory");
 }
+__device__ __forceinline__ void mma_f8_ss_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]^T : A (M x K, 16-bit pairs packed per 32-bit column, lane = row) stays in TMEM.
 __device__ __forceinline__ void mma_f16_ts_pred(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                                 uint32_t accumulate, uint32_t pred) {
