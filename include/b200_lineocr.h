@@ -140,6 +140,22 @@ int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int
                        int32_t* lengths, float* confidence, int32_t* best_path, float* frame_max, float* frame_lse,
                        void* cuda_stream);
 
+/* Replaces the per-line logit sparsification of BaseEngineLineOCR.process_lines
+ * (pero_ocr/ocr_engine/line_ocr_engine.py:168-172: softmax, zero raw logits with p < 1e-4, scipy CSC) together with
+ * the optional tight crop of the frame range (:152-156), on the device, so that only the surviving entries cross PCIe.
+ *   logits   device f32 [n][t][c] (b200ocr_forward's `logits`)
+ *   t_lo/hi  device i32 [n] or NULL: frame range [lo, hi) kept per line (NULL = [0, t))
+ *   indptr   device i32 [n][c+1]   CSC column pointers of each line's [hi-lo][c] matrix, relative to base[line]
+ *   nnz      device i32 [n]        entries per line
+ *   base     device i64 [n+1]      offset of each line's first entry in indices/data; base[n] = total
+ *   indices  device i32 [capacity] frame index minus lo, ascending inside a column
+ *   data     device f32 [capacity] the raw logit
+ * Entries beyond `capacity` are counted but not written (n*t*c always suffices).  A raw logit equal to 0.0 is
+ * never stored, as in the reference (scipy drops zeros; core/layout.py:65-68 maps them back to -80). */
+int b200ocr_sparsify_logits(const float* logits, int32_t n, int32_t t, int32_t c, const int32_t* t_lo,
+                            const int32_t* t_hi, int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices,
+                            float* data, int64_t capacity, void* cuda_stream);
+
 /* Replaces CTCPrefixLogRawNumpyDecoder.__call__ without LM (pero_ocr/decoding/decoders.py:220-299).
  *   logprobs  device f64 [n][t][c] normalised log-probabilities, blank last
  *   out_labels device i32 [n][k][t], out_lengths i32 [n][k] (-1 = unused beam slot), out_scores f64 [n][k]

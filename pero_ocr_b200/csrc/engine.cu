@@ -831,6 +831,17 @@ int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int
     return B200OCR_OK;
 }
 
+int b200ocr_sparsify_logits(const float* logits, int32_t n, int32_t t, int32_t c, const int32_t* t_lo,
+                            const int32_t* t_hi, int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices,
+                            float* data, int64_t capacity, void* cuda_stream) {
+    if (!logits || n < 0 || t <= 0 || c <= 0 || !indptr || !nnz || !base || !indices || !data || capacity < 0)
+        return fail(nullptr, B200OCR_E_INVALID, "bad sparsify_logits arguments");
+    if (n == 0) return B200OCR_OK;
+    CU_TRY(nullptr, launch_sparsify(logits, n, t, c, t_lo, t_hi, indptr, nnz, base, indices, data, capacity,
+                                    static_cast<cudaStream_t>(cuda_stream)));
+    return B200OCR_OK;
+}
+
 int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
                             int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream) {
     if (!logprobs || n < 0 || t <= 0 || c <= 1 || k < 1 || !out_labels || !out_lengths || !out_scores || !status)

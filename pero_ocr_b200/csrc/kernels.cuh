@@ -25,6 +25,11 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
 cudaError_t launch_frame_stats(const float* scores, int n, int t, int c, int layout, int32_t* best, float* fmax,
                                float* flse, float* fprob, cudaStream_t stream);
 
+// Logit sparsification (sparsify.cu): softmax threshold 1e-4 + CSC of every line (line_ocr_engine.py:168-172).
+cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int32_t* t_lo, const int32_t* t_hi,
+                            int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices, float* data,
+                            int64_t capacity, cudaStream_t stream);
+
 // greedy_decode_ctc's collapse (pytorch_ocr_engine.py:19-27) on per-frame argmax ids: drop repeats (frame 0 is
 // compared with a virtual blank), drop blanks; left-packed labels (-1 padded) + lengths; optional line
 // confidence = get_prob (page_parser.py:437-450) over fprob.

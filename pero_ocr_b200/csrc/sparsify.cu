@@ -1,0 +1,148 @@
+// Logit sparsification on the device.
+//
+// Replaces the per-line NumPy pass of BaseEngineLineOCR.process_lines
+//     line_probs = softmax(line_logits, axis=1); line_logits[line_probs < 0.0001] = 0
+//     line_logits = sparse.csc_matrix(line_logits)            (pero_ocr/ocr_engine/line_ocr_engine.py:168-172)
+// including the optional tight crop of the frame range (:152-156), so that PageOCR.process_page
+// (document_ocr/page_parser.py:423-430), which always asks for logits, ships a few CSC entries per frame instead of
+// the dense [T][C] fp32 matrix and runs no per-line softmax on the host.
+//
+// Output is scipy's canonical CSC of the [hi-lo][C] matrix of every line, concatenated:
+//   indptr  i32 [n][C+1]   per-line column pointers (relative to the line's first entry)
+//   base    i64 [n+1]      first entry of each line in indices / data (base[n] = total entries)
+//   indices i32 [total]    frame index (relative to the line's lo), ascending inside a column
+//   data    f32 [total]    the raw logit (bit pattern of the input)
+// Semantics mirrored exactly: softmax in fp32 as p = exp(v - max) / sum; an entry is dropped when
+// (double)p < 0.0001 (NumPy compares the fp32 probability with a Python float) or when the raw logit is 0.0 (CSC
+// never stores zeros -- the reference loses genuine zero logits by design, core/layout.py:65-68); NaN survives.
+// exp and the order of the sum are CUDA's, not NumPy's: an entry whose probability is within a few fp32 ulps of
+// 1e-4 may fall on the other side (tests/test_gpu_sparsify.py bounds that band).
+//
+// One CTA per line.  Phase 0: per-frame max and sum (thread per frame).  Phase 1: thread per class scans the frames
+// (coalesced across classes) and counts kept entries; an exclusive scan over classes gives indptr.  A one-CTA scan
+// over lines gives base.  Phase 2 repeats the scan of phase 1 and writes entries at base + indptr.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int SP_THREADS = 256;
+
+__device__ __forceinline__ bool sp_keep(float v, float mx, float sum) {
+    const float p = __fdiv_rn(expf(v - mx), sum);
+    return !(static_cast<double>(p) < 0.0001) && v != 0.0f;
+}
+
+__device__ void sp_frame_stats(const float* __restrict__ L, int lo, int hi, int C, float* s_mx, float* s_sum) {
+    for (int t = lo + threadIdx.x; t < hi; t += SP_THREADS) {
+        const float* row = L + static_cast<size_t>(t) * C;
+        float mx = row[0];
+        bool nan = mx != mx;
+        for (int c = 1; c < C; ++c) {
+            const float v = row[c];
+            if (v != v) nan = true;
+            mx = fmaxf(mx, v);
+        }
+        if (nan) mx = __int_as_float(0x7fc00000);   // np.max propagates NaN
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+        s_mx[t - lo] = mx;
+        s_sum[t - lo] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS) sparsify_count_kernel(const float* __restrict__ logits, int T, int C,
+                                                                    const int32_t* __restrict__ t_lo,
+                                                                    const int32_t* __restrict__ t_hi,
+                                                                    int32_t* __restrict__ indptr,
+                                                                    int32_t* __restrict__ nnz) {
+    extern __shared__ float s_dyn[];
+    const int line = blockIdx.x;
+    const int lo = t_lo ? max(0, min(T, t_lo[line])) : 0;
+    const int hi = t_hi ? max(lo, min(T, t_hi[line])) : T;
+    float* s_mx = s_dyn;
+    float* s_sum = s_dyn + T;
+    int32_t* s_cnt = reinterpret_cast<int32_t*>(s_dyn + 2 * T);   // [C]
+    const float* L = logits + static_cast<size_t>(line) * T * C;
+    sp_frame_stats(L, lo, hi, C, s_mx, s_sum);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += SP_THREADS) {
+        int cnt = 0;
+        for (int t = lo; t < hi; ++t) cnt += sp_keep(L[static_cast<size_t>(t) * C + c], s_mx[t - lo], s_sum[t - lo]) ? 1 : 0;
+        s_cnt[c] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t* ip = indptr + static_cast<size_t>(line) * (C + 1);
+        int run = 0;
+        for (int c = 0; c < C; ++c) {
+            ip[c] = run;
+            run += s_cnt[c];
+        }
+        ip[C] = run;
+        nnz[line] = run;
+    }
+}
+
+__global__ void sparsify_scan_kernel(const int32_t* __restrict__ nnz, int n, int64_t* __restrict__ base) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < n; ++i) {
+            base[i] = run;
+            run += nnz[i];
+        }
+        base[n] = run;
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS) sparsify_fill_kernel(const float* __restrict__ logits, int T, int C,
+                                                                   const int32_t* __restrict__ t_lo,
+                                                                   const int32_t* __restrict__ t_hi,
+                                                                   const int32_t* __restrict__ indptr,
+                                                                   const int64_t* __restrict__ base, int64_t capacity,
+                                                                   int32_t* __restrict__ indices,
+                                                                   float* __restrict__ data) {
+    extern __shared__ float s_dyn[];
+    const int line = blockIdx.x;
+    const int lo = t_lo ? max(0, min(T, t_lo[line])) : 0;
+    const int hi = t_hi ? max(lo, min(T, t_hi[line])) : T;
+    float* s_mx = s_dyn;
+    float* s_sum = s_dyn + T;
+    const float* L = logits + static_cast<size_t>(line) * T * C;
+    sp_frame_stats(L, lo, hi, C, s_mx, s_sum);
+    __syncthreads();
+    const int32_t* ip = indptr + static_cast<size_t>(line) * (C + 1);
+    const int64_t b0 = base[line];
+    for (int c = threadIdx.x; c < C; c += SP_THREADS) {
+        int64_t at = b0 + ip[c];
+        for (int t = lo; t < hi; ++t) {
+            const float v = L[static_cast<size_t>(t) * C + c];
+            if (sp_keep(v, s_mx[t - lo], s_sum[t - lo])) {
+                if (at < capacity) {
+                    indices[at] = t - lo;
+                    data[at] = v;
+                }
+                ++at;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int32_t* t_lo, const int32_t* t_hi,
+                            int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices, float* data,
+                            int64_t capacity, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const size_t dyn = (2 * static_cast<size_t>(T) + C) * sizeof(float);
+    if (dyn > 200 * 1024) return cudaErrorInvalidValue;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(sparsify_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(sparsify_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    sparsify_count_kernel<<<n, SP_THREADS, dyn, stream>>>(logits, T, C, t_lo, t_hi, indptr, nnz);
+    sparsify_scan_kernel<<<1, 32, 0, stream>>>(nnz, n, base);
+    sparsify_fill_kernel<<<n, SP_THREADS, dyn, stream>>>(logits, T, C, t_lo, t_hi, indptr, base, capacity, indices, data);
+    return cudaGetLastError();
+}

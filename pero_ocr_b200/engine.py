@@ -17,6 +17,7 @@ import numpy as np
 
 from . import _lib, netdesc
 from ._lib import DEFAULT_PRECISION
+from .sparse_logits import csc_lines, sparsify_device
 
 
 class LineRecognizer:
@@ -128,12 +129,6 @@ class LineRecognizer:
         return buf[:written.value].reshape(tuple(shape)).copy()
 
 
-def softmax(x, axis):
-    """Numerically-stable softmax used for logit sparsification (role of pero_ocr/ocr_engine/softmax.py, theta=1)."""
-    e = np.exp(x - np.max(x, axis=axis, keepdims=True))
-    return e / np.sum(e, axis=axis, keepdims=True)
-
-
 class B200EngineLineOCR:
     """Drop-in for ``PytorchEngineLineOCR(json_def, device, batch_size)``.
 
@@ -194,7 +189,7 @@ class B200EngineLineOCR:
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._slots[k]
 
-    def _submit(self, k, shape, fill, no_logits):
+    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None):
         """Stage one padded uint8 batch of `shape` (filled in place by `fill(view)`), copy it to the device on the
         side stream, run the forward on the current stream and start the device->host copies of the results."""
         torch = self.model.torch
@@ -214,7 +209,15 @@ class B200EngineLineOCR:
         self.h2d_bytes += n_bytes
         o = self.model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence, out=sl['outs'])
         sl['outs'] = o
-        names = ['labels', 'lengths'] + ([] if no_logits else ['logits']) + (['confidence'] if self.want_confidence else [])
+        sl['sparse'] = None
+        dense = not no_logits and sparse_ranges is None
+        if not no_logits and sparse_ranges is not None:
+            # softmax threshold + CSC on the device (line_ocr_engine.py:152-156, 168-172): only the surviving entries
+            # are copied back, in _collect
+            lo, hi = sparse_ranges
+            sl['sparse'] = sparsify_device(o['logits'], lo, hi, out=sl.get('sparse_buf'))
+            sl['sparse_buf'] = sl['sparse']
+        names = ['labels', 'lengths'] + (['logits'] if dense else []) + (['confidence'] if self.want_confidence else [])
         for name in names:
             t = o[name]
             h = sl['host'].get(name)
@@ -230,7 +233,13 @@ class B200EngineLineOCR:
         k, names = ticket
         sl = self._slots[k]
         sl['done'].synchronize()
-        return {name: sl['host'][name].numpy() for name in names}
+        res = {name: sl['host'][name].numpy() for name in names}
+        if sl.get('sparse') is not None:
+            fetched = sl['sparse'].fetch(self._copy_stream)
+            self._copy_stream.synchronize()
+            self.d2h_bytes += sum(int(a.nbytes) for a in fetched)
+            res['sparse'] = csc_lines(sl['sparse'], fetched)
+        return res
 
     def _decode_ids(self, labels, lengths):
         chars = self.characters
@@ -265,7 +274,6 @@ class B200EngineLineOCR:
         line_ocr_engine.py:57-177 for model_type 'ctc': widest-first batches under a pixel budget, 32 px zero
         padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4.
         Batches are double-buffered: batch i+1 is padded and uploaded while batch i runs on the GPU."""
-        from scipy import sparse
         count = len(lines)
         transcriptions = [None] * count
         logits_out = [None] * count
@@ -286,20 +294,18 @@ class B200EngineLineOCR:
                     confidences[idx] = float(res['confidence'][slot])
                 if no_logits:
                     continue
-                line_logits = res['logits'][slot]
                 lo, hi = int(pad // sub), int((pad + lines[idx].shape[1]) // sub)
+                if sparse_logits:
+                    coords_out[idx] = [None, None] if tight_crop_logits else [lo, hi]
+                    logits_out[idx] = res['sparse'][slot]
+                    continue
+                line_logits = res['logits'][slot]
                 if tight_crop_logits:
                     line_logits = line_logits[lo:hi]
                     coords_out[idx] = [None, None]
                 else:
                     coords_out[idx] = [lo, hi]
-                if sparse_logits:
-                    line_logits = line_logits.copy()
-                    line_logits[softmax(line_logits, axis=1) < 0.0001] = 0
-                    line_logits = sparse.csc_matrix(line_logits)
-                else:
-                    line_logits = line_logits.copy()
-                logits_out[idx] = line_logits
+                logits_out[idx] = line_logits.copy()
 
         in_flight = None
         with self._device_ctx():
@@ -321,7 +327,14 @@ class B200EngineLineOCR:
                             view[slot, :, pad:end] = line[:, :end - pad]
                         view[slot, :, end:] = 0
 
-                ticket = self._submit(bi & 1, (len(chunk), height, width, 3), fill, no_logits)
+                ranges = None
+                if sparse_logits and not no_logits:
+                    t_all = width // sub
+                    if tight_crop_logits:
+                        ranges = ([pad // sub] * len(chunk), [(pad + lines[i].shape[1]) // sub for i in chunk])
+                    else:
+                        ranges = ([0] * len(chunk), [t_all] * len(chunk))
+                ticket = self._submit(bi & 1, (len(chunk), height, width, 3), fill, no_logits, ranges)
                 if in_flight is not None:
                     finish(in_flight[0], self._collect(in_flight[1]))
                 in_flight = (chunk, ticket)

@@ -1,0 +1,81 @@
+"""Device-side logit sparsification: the host mirror of ``b200ocr_sparsify_logits``.
+
+Replaces the per-line NumPy pass at the end of ``BaseEngineLineOCR.process_lines``
+(pero_ocr/ocr_engine/line_ocr_engine.py:152-156 tight crop, :168-172 softmax threshold 1e-4 + ``scipy.sparse.csc_matrix``)
+so that ``TextLine.logits`` (pero_ocr/core/layout.py:41-72) is built from a few surviving entries per frame instead of
+a dense [T, C] matrix copied over PCIe and soft-maxed on one host core per line.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class SparseLogits:
+    """CSC parts of a batch of lines, still on the device.  ``fetch()`` copies exactly the used prefix to the host."""
+
+    def __init__(self, torch, n, t, c):
+        self.torch, self.n, self.t, self.c = torch, n, t, c
+        self.indptr = self.nnz = self.base = self.indices = self.data = None
+        self.rows = None          # host int array [n]: rows (frames) of every line's matrix
+        self._host = {}
+
+    def fetch(self, stream=None):
+        """-> (indptr int32 [n, C+1], base int64 [n+1], indices int32 [total], data float32 [total]) as NumPy arrays.
+        Two small copies first (indptr, base), then the used prefix of indices / data."""
+        torch = self.torch
+        stream = stream or torch.cuda.current_stream(self.indptr.device)
+        with torch.cuda.stream(stream):
+            indptr = self.indptr.cpu()
+            base = self.base.cpu()
+            total = int(base[self.n])
+            indices = self.indices[:total].cpu()
+            data = self.data[:total].cpu()
+        return indptr.numpy(), base.numpy(), indices.numpy(), data.numpy()
+
+
+def sparsify_device(logits, t_lo=None, t_hi=None, out=None):
+    """logits: CUDA float32 [N, T, C] (contiguous).  t_lo / t_hi: optional int arrays [N] (host) giving the frame range
+    kept per line (the reference's tight crop).  Stream-ordered on torch's current stream; returns SparseLogits."""
+    import torch
+    lib = _lib.load_library()
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 3
+    n, t, c = logits.shape
+    dev = logits.device
+    sp = out if isinstance(out, SparseLogits) and (out.n, out.t, out.c) == (n, t, c) else SparseLogits(torch, n, t, c)
+    if sp.indptr is None:
+        sp.indptr = torch.empty((n, c + 1), dtype=torch.int32, device=dev)
+        sp.nnz = torch.empty((n,), dtype=torch.int32, device=dev)
+        sp.base = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+        sp.indices = torch.empty((n * t * c,), dtype=torch.int32, device=dev)
+        sp.data = torch.empty((n * t * c,), dtype=torch.float32, device=dev)
+    lo_d = hi_d = None
+    if t_lo is not None:
+        lo = np.ascontiguousarray(t_lo, dtype=np.int32)
+        hi = np.ascontiguousarray(t_hi, dtype=np.int32)
+        lo_d = torch.from_numpy(lo).to(dev, non_blocking=False)
+        hi_d = torch.from_numpy(hi).to(dev, non_blocking=False)
+        sp.rows = np.maximum(np.minimum(hi, t) - np.clip(lo, 0, t), 0)
+    else:
+        sp.rows = np.full((n,), t, dtype=np.int64)
+    sp._keep = (lo_d, hi_d)      # alive until the kernels have run
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.b200ocr_sparsify_logits(
+        logits.data_ptr(), n, t, c,
+        lo_d.data_ptr() if lo_d is not None else None, hi_d.data_ptr() if hi_d is not None else None,
+        sp.indptr.data_ptr(), sp.nnz.data_ptr(), sp.base.data_ptr(), sp.indices.data_ptr(), sp.data.data_ptr(),
+        n * t * c, C.c_void_p(stream)))
+    return sp
+
+
+def csc_lines(sp, fetched=None):
+    """list of scipy.sparse.csc_matrix [rows_i, C] float32 -- the value ``process_lines`` stores in ``TextLine.logits``."""
+    from scipy import sparse
+    indptr, base, indices, data = fetched if fetched is not None else sp.fetch()
+    out = []
+    for i in range(sp.n):
+        b0, b1 = int(base[i]), int(base[i + 1])
+        out.append(sparse.csc_matrix((data[b0:b1].copy(), indices[b0:b1].copy(), indptr[i].copy()),
+                                     shape=(int(sp.rows[i]), sp.c)))
+    return out

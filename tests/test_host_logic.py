@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import cases
-from oracle.forward_oracle import greedy_ctc_indices
+from oracle.forward_oracle import greedy_ctc_indices, sparsify_logits
 from tests.util import load_golden, make_case_net
 
 
@@ -29,7 +29,7 @@ def _host_only_engine(kind):
     eng._device_ctx = contextlib.nullcontext
     store = {}
 
-    def submit(k, shape, fill, no_logits):
+    def submit(k, shape, fill, no_logits, sparse_ranges=None):
         batch = np.empty(shape, dtype=np.uint8)
         batch[...] = 0xAB                      # stale garbage: fill() must overwrite every byte
         fill(batch)
@@ -42,6 +42,9 @@ def _host_only_engine(kind):
             labels[i, :len(v)] = v
         store[k] = dict(labels=labels, lengths=np.array([len(v) for v in ids], dtype=np.int32),
                         logits=np.ascontiguousarray(logits.transpose(0, 2, 1)))
+        if sparse_ranges is not None:           # the device sparsifier's role, played by the oracle's NumPy pass
+            lo, hi = sparse_ranges
+            store[k]['sparse'] = [sparsify_logits(store[k]['logits'][i, lo[i]:hi[i]]) for i in range(shape[0])]
         return k, None
 
     eng._submit = submit
