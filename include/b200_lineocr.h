@@ -140,6 +140,18 @@ int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int
                        int32_t* lengths, float* confidence, int32_t* best_path, float* frame_max, float* frame_lse,
                        void* cuda_stream);
 
+/* Replaces EngineLineCropper.fast_remap (pero_ocr/core/crop_engine.py:146-163: cv2.remap, INTER_LINEAR,
+ * BORDER_CONSTANT 0, 8-bit fixed-point bilinear) for all lines of a page in one launch, writing straight into the
+ * zero-padded batch that BaseEngineLineOCR.process_lines builds on the host (line_ocr_engine.py:121-123).
+ *   image     device u8 [img_h][img_w][3]   the page (img_h, img_w <= 32767, OpenCV's own limit for this path)
+ *   coords    device f32: per line a [line_h][w_i][2] map of source (x, y), i.e. get_crop_inputs' result
+ *             (crop_engine.py:54-99), concatenated; coord_off device i64 [n] = offset of line i in floats
+ *   widths    device i32 [n]  w_i
+ *   out       device u8 [n][line_h][out_w][3]: line i occupies columns [pad, pad + w_i) (cut at out_w), the rest is 0 */
+int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, const float* coords,
+                        const int64_t* coord_off, const int32_t* widths, int32_t n, int32_t line_h, uint8_t* out,
+                        int32_t out_w, int32_t pad, void* cuda_stream);
+
 /* Replaces the per-line logit sparsification of BaseEngineLineOCR.process_lines
  * (pero_ocr/ocr_engine/line_ocr_engine.py:168-172: softmax, zero raw logits with p < 1e-4, scipy CSC) together with
  * the optional tight crop of the frame range (:152-156), on the device, so that only the surviving entries cross PCIe.

@@ -11,6 +11,7 @@ What is executed from the reference (nothing is copied; the tree is imported rea
     the same seeded weights, to pin oracle/nets.py's restatement of that architecture
   * pero_ocr.decoding.decoders.GreedyDecoder / CTCPrefixLogRawNumpyDecoder
   * pero_ocr.layout_engines.torch_parsenet.TorchParseNet.get_maps
+  * pero_ocr.core.crop_engine.EngineLineCropper.crop / get_crop_inputs (cv2.remap underneath)
   * pero_ocr.document_ocr.page_parser.PageParser.compute_line_confidence / line_confident_enough and
     pero_ocr.core.layout.TextLine.get_dense_logits / get_full_logprobs (imported behind stub modules for the
     absent lxml / shapely / skimage / arabic_reshaper packages -- SURVEY.md appendix A.4)
@@ -18,6 +19,7 @@ What is executed from the reference (nothing is copied; the tree is imported rea
 Inputs and weights are regenerated from seeds by the tests; only reference OUTPUTS are stored.
 """
 import contextlib
+import hashlib
 import io
 import json
 import os
@@ -246,6 +248,29 @@ def golden_parsenet(tmp):
     return {'maps_shape': list(maps.shape), 'absmax': float(np.abs(maps).max())}
 
 
+def golden_cropper():
+    """EngineLineCropper.crop on a seeded noise page: coordinate maps (get_crop_inputs) and crops (cv2.remap)."""
+    from pero_ocr.core.crop_engine import EngineLineCropper
+    from oracle.crop_oracle import CROP_CASES, page_image
+    img = page_image()
+    out, info = {}, {}
+    for name, kw, baseline, heights in CROP_CASES:
+        cropper = EngineLineCropper(**kw)
+        crop = cropper.crop(img, baseline, heights)
+        out[f'crop_{name}'] = crop
+        try:
+            full = cropper.get_crop_inputs(baseline, heights, cropper.line_height)
+            out[f'map_{name}'] = full[:, ::4]          # every 4th column + a digest of the whole map (fixture size)
+            out[f'mapsha_{name}'] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(full).tobytes()).digest(),
+                                                   dtype=np.uint8)
+            out[f'mapshape_{name}'] = np.array(full.shape)
+        except Exception as exc:                       # the reference's crop() swallows this and returns zeros
+            info[name] = f'geometry fails: {type(exc).__name__}'
+        info.setdefault(name, list(crop.shape))
+    np.savez_compressed(os.path.join(GOLDEN, 'cropper.npz'), **out)
+    return info
+
+
 def main():
     sys.path.insert(0, REF)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -253,13 +278,19 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     report = {'reference': 'DCGM/pero-ocr v0.7.0 @ /root/reference', 'torch': torch.__version__,
               'numpy': np.__version__}
+    only = set(sys.argv[1:])                    # e.g. `python -m oracle.make_golden cropper` refreshes one part
+    if only:
+        with open(os.path.join(GOLDEN, 'REPORT.json')) as f:
+            report = json.load(f)
     with tempfile.TemporaryDirectory() as tmp:
-        report['architecture_check'] = check_reference_architecture()
-        report['decoders'] = golden_decoders()
-        report['engine_lstm'] = golden_engine('lstm', tmp)
-        report['engine_transformer'] = golden_engine('transformer', tmp)
-        report['parsenet'] = golden_parsenet(tmp)
-        report['confidence'] = golden_confidence()
+        parts = [('architecture_check', check_reference_architecture), ('decoders', golden_decoders),
+                 ('engine_lstm', lambda: golden_engine('lstm', tmp)),
+                 ('engine_transformer', lambda: golden_engine('transformer', tmp)),
+                 ('parsenet', lambda: golden_parsenet(tmp)), ('confidence', golden_confidence),
+                 ('cropper', golden_cropper)]
+        for name, fn in parts:
+            if not only or name in only:
+                report[name] = fn()
     with open(os.path.join(GOLDEN, 'REPORT.json'), 'w') as f:
         json.dump(report, f, indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))

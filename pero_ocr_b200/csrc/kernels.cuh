@@ -25,6 +25,11 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
 cudaError_t launch_frame_stats(const float* scores, int n, int t, int c, int layout, int32_t* best, float* fmax,
                                float* flse, float* fprob, cudaStream_t stream);
 
+// Bilinear 8-bit remap of all lines of a page into the padded recogniser batch (remap.cu; crop_engine.py:146-163).
+cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
+                               const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,
+                               cudaStream_t stream);
+
 // Logit sparsification (sparsify.cu): softmax threshold 1e-4 + CSC of every line (line_ocr_engine.py:168-172).
 cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int32_t* t_lo, const int32_t* t_hi,
                             int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices, float* data,

@@ -1,0 +1,72 @@
+// Baseline-following line crops on the device.
+//
+// Replaces EngineLineCropper.fast_remap (pero_ocr/core/crop_engine.py:146-163), i.e. cv2.remap(img, map_x, map_y,
+// INTER_LINEAR, BORDER_CONSTANT) per text line on one host core, and the zero padding + stacking of the crops into
+// the recogniser's batch (BaseEngineLineOCR.process_lines, pero_ocr/ocr_engine/line_ocr_engine.py:121-123): the page
+// image is uploaded once, every line of the page is resampled by one launch and lands directly in the padded
+// [n][line_h][out_w][3] batch that b200ocr_forward reads.
+//
+// The arithmetic is OpenCV's 8-bit bilinear remap (opencv-python, un-pinned dependency of the reference; pinned here
+// against 4.13.0 outputs, tests/golden/cropper.npz), restated:
+//   sx = cvRound(x * 32), sy = cvRound(y * 32)            (INTER_BITS = 5; round half to even)
+//   ix = saturate<short>(sx >> 5), fx = sx & 31            (same for y)
+//   w00 = (32-fx)(32-fy)*32, w01 = fx(32-fy)*32, w10 = (32-fx)fy*32, w11 = fx*fy*32     (sum = 2^15)
+//   dst = (p00*w00 + p01*w01 + p10*w10 + p11*w11 + 2^14) >> 15, a neighbour outside the image counts as 0.
+// (OpenCV's table holds 32767 / 1 instead of 32768 / 0 for fx = fy = 0; the result is the same byte for every input.)
+// Both branches of fast_remap -- whole image with a constant border, or the bounding-box crop with shifted
+// coordinates -- produce exactly these bytes: subtracting the integer box origin from a float32 coordinate is exact.
+#include "kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ int cv_round_x32(float v) {
+    // cvRound(v * 32): SSE cvtss2si semantics -- NaN and out-of-range give INT_MIN ("integer indefinite")
+    const float s = v * 32.0f;
+    if (!(fabsf(s) < 2147483648.0f)) return INT_MIN;
+    return __float2int_rn(s);
+}
+
+__global__ void __launch_bounds__(256) remap_lines_kernel(const uint8_t* __restrict__ img, int img_h, int img_w,
+                                                          const float* __restrict__ coords,
+                                                          const int64_t* __restrict__ coord_off,
+                                                          const int32_t* __restrict__ widths, int line_h,
+                                                          uint8_t* __restrict__ out, int out_w, int pad) {
+    const int line = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= out_w) return;
+    uint8_t* dst = out + ((static_cast<size_t>(line) * line_h + y) * out_w + x) * 3;
+    const int w = widths[line];
+    const int cx = x - pad;                       // column inside the line's own crop
+    if (cx < 0 || cx >= w) {                      // padding (and lines cut at the batch width keep their left part)
+        dst[0] = dst[1] = dst[2] = 0;
+        return;
+    }
+    const float2 xy = *reinterpret_cast<const float2*>(coords + coord_off[line] + (static_cast<size_t>(y) * w + cx) * 2);
+    const int sx = cv_round_x32(xy.x), sy = cv_round_x32(xy.y);
+    const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));
+    const int fx = sx & 31, fy = sy & 31;
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+    const bool x0 = ix >= 0 && ix < img_w, x1 = ix + 1 >= 0 && ix + 1 < img_w;
+    const bool y0 = iy >= 0 && iy < img_h, y1 = iy + 1 >= 0 && iy + 1 < img_h;
+    const uint8_t* r0 = img + (static_cast<size_t>(y0 ? iy : 0) * img_w) * 3;
+    const uint8_t* r1 = img + (static_cast<size_t>(y1 ? iy + 1 : 0) * img_w) * 3;
+    const int o0 = (x0 ? ix : 0) * 3, o1 = (x1 ? ix + 1 : 0) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int p00 = (y0 && x0) ? r0[o0 + c] : 0, p01 = (y0 && x1) ? r0[o1 + c] : 0;
+        const int p10 = (y1 && x0) ? r1[o0 + c] : 0, p11 = (y1 && x1) ? r1[o1 + c] : 0;
+        dst[c] = static_cast<uint8_t>((p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
+                               const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,
+                               cudaStream_t stream) {
+    if (n <= 0 || out_w <= 0) return cudaSuccess;
+    if (n > 65535 || line_h > 65535) return cudaErrorInvalidValue;
+    dim3 grid((out_w + 255) / 256, line_h, n);
+    remap_lines_kernel<<<grid, 256, 0, stream>>>(img, img_h, img_w, coords, coord_off, widths, line_h, out, out_w, pad);
+    return cudaGetLastError();
+}

@@ -189,24 +189,30 @@ class B200EngineLineOCR:
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._slots[k]
 
-    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None):
-        """Stage one padded uint8 batch of `shape` (filled in place by `fill(view)`), copy it to the device on the
-        side stream, run the forward on the current stream and start the device->host copies of the results."""
+    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None, device_fill=None):
+        """Stage one padded uint8 batch of `shape` (filled in place by `fill(view)` in pinned host memory and copied
+        to the device on the side stream -- or produced on the device by `device_fill(dev_batch)`), run the forward
+        on the current stream and start the device->host copies of the results."""
         torch = self.model.torch
         sl = self._slot(k)
         n_bytes = int(np.prod(shape))
-        if sl['pin'] is None or sl['pin'].numel() < n_bytes:
-            sl['pin'] = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+        if sl['dev'] is None or sl['dev'].numel() < n_bytes:
             sl['dev'] = torch.empty(n_bytes, dtype=torch.uint8, device=self.device)
-        pin = sl['pin'][:n_bytes].view(shape)
-        fill(pin.numpy())
+            sl['pin'] = None
         dev = sl['dev'][:n_bytes].view(shape)
         main = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self._copy_stream):
-            dev.copy_(pin, non_blocking=True)
-            sl['h2d'].record(self._copy_stream)
-        main.wait_event(sl['h2d'])
-        self.h2d_bytes += n_bytes
+        if device_fill is not None:
+            self.h2d_bytes += int(device_fill(dev))
+        else:
+            if sl['pin'] is None or sl['pin'].numel() < n_bytes:
+                sl['pin'] = torch.empty(sl['dev'].numel(), dtype=torch.uint8, pin_memory=True)
+            pin = sl['pin'][:n_bytes].view(shape)
+            fill(pin.numpy())
+            with torch.cuda.stream(self._copy_stream):
+                dev.copy_(pin, non_blocking=True)
+                sl['h2d'].record(self._copy_stream)
+            main.wait_event(sl['h2d'])
+            self.h2d_bytes += n_bytes
         o = self.model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence, out=sl['outs'])
         sl['outs'] = o
         sl['sparse'] = None
@@ -260,21 +266,19 @@ class B200EngineLineOCR:
         return self._decode_ids(res['labels'], res['lengths']), logits
 
     # ---- batching ------------------------------------------------------------------------------------------
-    def _batches(self, lines):
+    def _batches(self, widths):
         """Widest-first batches under the pixel budget (line_ocr_engine.py:79-90)."""
-        pending = sorted(range(len(lines)), key=lambda i: -lines[i].shape[1])     # stable: ties keep input order
+        pending = sorted(range(len(widths)), key=lambda i: -widths[i])     # stable: ties keep input order
         while pending:
-            widest = int(math.ceil(lines[pending[0]].shape[1] / 32.0) * 32)
+            widest = int(math.ceil(widths[pending[0]] / 32.0) * 32)
             take = max(1, self.max_input_horizontal_pixels // widest)
             chunk, pending = pending[:take], pending[take:]
             yield chunk, widest
 
-    def process_lines(self, lines, sparse_logits=True, tight_crop_logits=False, no_logits=False, return_ids=False):
-        """list of [H,w,3] uint8 crops -> (transcriptions, logits, logit_coords); semantics of
-        line_ocr_engine.py:57-177 for model_type 'ctc': widest-first batches under a pixel budget, 32 px zero
-        padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4.
-        Batches are double-buffered: batch i+1 is padded and uploaded while batch i runs on the GPU."""
-        count = len(lines)
+    def _run_batches(self, widths, stager, sparse_logits, tight_crop_logits, no_logits, return_ids):
+        """Common driver of process_lines / process_line_maps.  `stager(chunk, width)` returns the keyword arguments
+        (`fill=` host stager or `device_fill=` device stager) that produce the padded batch of `chunk`."""
+        count = len(widths)
         transcriptions = [None] * count
         logits_out = [None] * count
         coords_out = [None] * count
@@ -294,7 +298,7 @@ class B200EngineLineOCR:
                     confidences[idx] = float(res['confidence'][slot])
                 if no_logits:
                     continue
-                lo, hi = int(pad // sub), int((pad + lines[idx].shape[1]) // sub)
+                lo, hi = int(pad // sub), int((pad + widths[idx]) // sub)
                 if sparse_logits:
                     coords_out[idx] = [None, None] if tight_crop_logits else [lo, hi]
                     logits_out[idx] = res['sparse'][slot]
@@ -309,32 +313,22 @@ class B200EngineLineOCR:
 
         in_flight = None
         with self._device_ctx():
-            for bi, (chunk, widest) in enumerate(self._batches(lines)):
+            for bi, (chunk, widest) in enumerate(self._batches(widths)):
                 full_w = widest + 2 * pad
                 width = full_w
                 if full_w > budget:
                     print(f'WARNING: Line too long for OCR engine. Cropping from {full_w} px down to {budget}.')
                     width = budget
-
-                def fill(view, chunk=chunk, width=width):
-                    for slot, idx in enumerate(chunk):
-                        line = lines[idx]
-                        if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
-                            raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
-                        end = min(width, pad + line.shape[1])
-                        view[slot, :, :pad] = 0
-                        if end > pad:
-                            view[slot, :, pad:end] = line[:, :end - pad]
-                        view[slot, :, end:] = 0
-
                 ranges = None
                 if sparse_logits and not no_logits:
                     t_all = width // sub
                     if tight_crop_logits:
-                        ranges = ([pad // sub] * len(chunk), [(pad + lines[i].shape[1]) // sub for i in chunk])
+                        ranges = ([pad // sub] * len(chunk), [(pad + widths[i]) // sub for i in chunk])
                     else:
                         ranges = ([0] * len(chunk), [t_all] * len(chunk))
-                ticket = self._submit(bi & 1, (len(chunk), height, width, 3), fill, no_logits, ranges)
+                kw = stager(chunk, width)
+                ticket = self._submit(bi & 1, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
+                                      device_fill=kw.get('device_fill'))
                 if in_flight is not None:
                     finish(in_flight[0], self._collect(in_flight[1]))
                 in_flight = (chunk, ticket)
@@ -342,3 +336,47 @@ class B200EngineLineOCR:
                 finish(in_flight[0], self._collect(in_flight[1]))
         self.last_line_confidences = confidences if self.want_confidence else None
         return transcriptions, logits_out, coords_out
+
+    def process_lines(self, lines, sparse_logits=True, tight_crop_logits=False, no_logits=False, return_ids=False):
+        """list of [H,w,3] uint8 crops -> (transcriptions, logits, logit_coords); semantics of
+        line_ocr_engine.py:57-177 for model_type 'ctc': widest-first batches under a pixel budget, 32 px zero
+        padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4.
+        Batches are double-buffered: batch i+1 is padded and uploaded while batch i runs on the GPU."""
+        pad, height = self.line_padding_px, self.line_px_height
+
+        def stager(chunk, width):
+            def fill(view):
+                for slot, idx in enumerate(chunk):
+                    line = lines[idx]
+                    if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
+                        raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
+                    end = min(width, pad + line.shape[1])
+                    view[slot, :, :pad] = 0
+                    if end > pad:
+                        view[slot, :, pad:end] = line[:, :end - pad]
+                    view[slot, :, end:] = 0
+            return {'fill': fill}
+
+        return self._run_batches([l.shape[1] for l in lines], stager, sparse_logits, tight_crop_logits, no_logits,
+                                 return_ids)
+
+    def process_line_maps(self, page, maps, sparse_logits=True, tight_crop_logits=False, no_logits=False,
+                          return_ids=False):
+        """Lines given as sampling maps instead of pixels: `page` is a cropper.DevicePage (the page image, uploaded
+        once), `maps` a list of float32 [H, w, 2] source-coordinate maps (B200LineCropper.get_crop_inputs, i.e.
+        crop_engine.py:54-99).  Each batch is resampled on the device straight into the padded recogniser batch
+        (b200ocr_remap_lines) -- LineCropper.process_page (page_parser.py:384-393) + process_lines without the host
+        crops, their padding copy and their upload.  Results are those of process_lines on the reference's crops."""
+        from .cropper import remap_into
+        height = self.line_px_height
+        for m in maps:
+            if m.ndim != 3 or m.shape[0] != height or m.shape[2] != 2:
+                raise ValueError(f'line maps must be [{height}, w, 2] float32, got {m.shape}')
+
+        def stager(chunk, width):
+            def device_fill(dev_batch):
+                return remap_into(page, [maps[i] for i in chunk], dev_batch, self.line_padding_px)
+            return {'device_fill': device_fill}
+
+        return self._run_batches([m.shape[1] for m in maps], stager, sparse_logits, tight_crop_logits, no_logits,
+                                 return_ids)

@@ -1,0 +1,70 @@
+"""GPU parity of the line cropper's device resampling (b200ocr_remap_lines) against crops produced by the unmodified
+reference EngineLineCropper (tests/golden/cropper.npz) and against the oracle's restatement of cv2.remap on seeded
+maps.  Bar: byte-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.crop_oracle import CROP_CASES, page_image, remap_bilinear_u8
+from tests.util import load_golden, make_case_net, write_engine_json
+
+pytestmark = pytest.mark.gpu
+
+
+def test_crops_match_reference_golden(golden_dir):
+    from pero_ocr_b200.cropper import B200LineCropper
+    gold = load_golden(golden_dir, 'cropper.npz')
+    img = page_image()
+    for name, kw, baseline, heights in CROP_CASES:
+        crop = B200LineCropper(**kw).crop(img, baseline, heights)
+        want = gold[f'crop_{name}']
+        assert crop.dtype == np.uint8 and crop.shape == want.shape, name
+        assert np.array_equal(crop, want), name
+
+
+def test_whole_page_launch_matches_oracle_on_random_maps():
+    """One launch, ragged widths, maps that leave the page on every side, exact-pixel / half-step / NaN / huge
+    coordinates; written into a padded batch like the recogniser's (pad 32, zero fill)."""
+    from pero_ocr_b200.cropper import DevicePage, remap_into
+    rng = np.random.default_rng(17)
+    img = rng.integers(0, 256, (211, 333, 3), dtype=np.uint8)
+    widths = [1, 37, 256, 300, 0, 129]
+    maps = []
+    for w in widths:
+        m = np.stack([rng.random((40, w)) * 360 - 14, rng.random((40, w)) * 240 - 14], axis=2).astype(np.float32)
+        maps.append(m)
+    maps[2][0, :8, 0] = [0.0, 332.0, 331.999, -1.0, 64.5, 64.015625, np.nan, 3e9]
+    maps[2][0, :8, 1] = [0.0, 210.0, 209.5, 3.0, 0.5, 7.984375, 5.0, 5.0]
+    page = DevicePage(img)
+    out = torch.full((len(maps), 40, 320, 3), 0xAB, dtype=torch.uint8, device='cuda')   # stale bytes must vanish
+    remap_into(page, maps, out, 32)
+    got = out.cpu().numpy()
+    for i, (w, m) in enumerate(zip(widths, maps)):
+        keep = min(w, 320 - 32)
+        want = np.zeros((40, 320, 3), dtype=np.uint8)
+        if keep:
+            want[:, 32:32 + keep] = remap_bilinear_u8(img, m)[:, :keep]
+        assert np.array_equal(got[i], want), i
+
+
+def test_process_line_maps_equals_process_lines_on_reference_crops(tmp_path, golden_dir):
+    """Cropping on the device straight into the recogniser batch gives exactly what the reference pipeline gives:
+    LineCropper.process_page crops (golden) -> process_lines."""
+    from pero_ocr_b200.cropper import B200LineCropper, DevicePage
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    gold = load_golden(golden_dir, 'cropper.npz')
+    js = write_engine_json(tmp_path, 'lstm')
+    eng = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=4, module=make_case_net('lstm'))
+    use = [c for c in CROP_CASES if c[1]['line_height'] == 40 and c[0] != 'degenerate_single_point']
+    cropper = B200LineCropper(line_height=40)
+    maps = []
+    for name, kw, baseline, heights in use:
+        c = B200LineCropper(**kw)
+        maps.append(c.get_crop_inputs(baseline, heights, 40))
+    page = DevicePage(page_image())
+    tr_a, lg_a, co_a = eng.process_line_maps(page, maps, sparse_logits=False)
+    tr_b, lg_b, co_b = eng.process_lines([gold[f'crop_{n}'] for n, *_ in use], sparse_logits=False)
+    assert tr_a == tr_b and co_a == co_b
+    for a, b in zip(lg_a, lg_b):
+        assert np.array_equal(a, b)                    # identical input bytes -> identical logits
