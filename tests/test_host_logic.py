@@ -29,7 +29,7 @@ def _host_only_engine(kind):
     eng._device_ctx = contextlib.nullcontext
     store = {}
 
-    def submit(k, shape, fill, no_logits, sparse_ranges=None):
+    def submit(k, shape, fill, no_logits, sparse_ranges=None, device_fill=None):
         batch = np.empty(shape, dtype=np.uint8)
         batch[...] = 0xAB                      # stale garbage: fill() must overwrite every byte
         fill(batch)
