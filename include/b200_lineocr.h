@@ -140,6 +140,23 @@ int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int
                        int32_t* lengths, float* confidence, int32_t* best_path, float* frame_max, float* frame_lse,
                        void* cuda_stream);
 
+/* Replaces force_align / align_text (pero_ocr/core/force_alignment.py:13-35, 152-165): Viterbi alignment of a
+ * transcription to the frames of a CTC output, for a batch of lines.
+ *   neg_logprobs  device f32 (is_f64 = 0) or f64 (1) [n][t][c] NEGATIVE log-probabilities; n_frames device i32 [n] or
+ *                 NULL = frames actually used per line (<= t)
+ *   labels        device i32 [n][l_max] symbol ids (blank excluded), lengths device i32 [n]; blank = blank class id
+ *   out_symbols   device i32 [n][t] or NULL: the most probable path as symbols incl. blanks (force_align's default)
+ *   out_positions device i32 [n][t] or NULL: the path as character indices, -1 on blank frames
+ *                 (return_seq_positions=True)
+ *   char_positions device i32 [n][l_max] or NULL: align_text's result, one frame per character (needs out_positions)
+ *   status        device i32 [n]: 0 ok, 1 no finite-cost alignment exists (reference: ValueError, :146-147),
+ *                 2 empty transcription / blank or out-of-range symbol in it (reference: ValueError, :41-43, :64-68)
+ * Unused tails of the outputs are -1.  Costs accumulate in float64 as in the reference. */
+int b200ocr_force_align(const void* neg_logprobs, int32_t is_f64, int32_t n, int32_t t, int32_t c,
+                        const int32_t* n_frames, const int32_t* labels, int32_t l_max, const int32_t* lengths,
+                        int32_t blank, int32_t* out_symbols, int32_t* out_positions, int32_t* char_positions,
+                        int32_t* status, void* cuda_stream);
+
 /* Replaces EngineLineCropper.fast_remap (pero_ocr/core/crop_engine.py:146-163: cv2.remap, INTER_LINEAR,
  * BORDER_CONSTANT 0, 8-bit fixed-point bilinear) for all lines of a page in one launch, writing straight into the
  * zero-padded batch that BaseEngineLineOCR.process_lines builds on the host (line_ocr_engine.py:121-123).

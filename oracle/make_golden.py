@@ -11,6 +11,7 @@ What is executed from the reference (nothing is copied; the tree is imported rea
     the same seeded weights, to pin oracle/nets.py's restatement of that architecture
   * pero_ocr.decoding.decoders.GreedyDecoder / CTCPrefixLogRawNumpyDecoder
   * pero_ocr.layout_engines.torch_parsenet.TorchParseNet.get_maps
+  * pero_ocr.core.force_alignment.force_align / align_text
   * pero_ocr.core.crop_engine.EngineLineCropper.crop / get_crop_inputs (cv2.remap underneath)
   * pero_ocr.document_ocr.page_parser.PageParser.compute_line_confidence / line_confident_enough and
     pero_ocr.core.layout.TextLine.get_dense_logits / get_full_logprobs (imported behind stub modules for the
@@ -271,6 +272,20 @@ def golden_cropper():
     return info
 
 
+def golden_align():
+    """force_align / align_text of the unmodified reference on the seeded cases of oracle/align_oracle.py."""
+    from pero_ocr.core.force_alignment import align_text, force_align
+    from oracle.align_oracle import align_cases
+    out, info = {}, {}
+    for name, neg, labels, blank in align_cases():
+        out[f'sym_{name}'] = np.asarray(force_align(neg, labels, blank), dtype=np.int32)
+        out[f'pos_{name}'] = np.asarray(force_align(neg, labels, blank, return_seq_positions=True), dtype=np.int32)
+        out[f'chr_{name}'] = np.asarray(align_text(neg, np.array(labels), blank), dtype=np.int32)
+        info[name] = [int(neg.shape[0]), len(labels), str(neg.dtype)]
+    np.savez_compressed(os.path.join(GOLDEN, 'align.npz'), **out)
+    return info
+
+
 def main():
     sys.path.insert(0, REF)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -287,7 +302,7 @@ def main():
                  ('engine_lstm', lambda: golden_engine('lstm', tmp)),
                  ('engine_transformer', lambda: golden_engine('transformer', tmp)),
                  ('parsenet', lambda: golden_parsenet(tmp)), ('confidence', golden_confidence),
-                 ('cropper', golden_cropper)]
+                 ('cropper', golden_cropper), ('align', golden_align)]
         for name, fn in parts:
             if not only or name in only:
                 report[name] = fn()

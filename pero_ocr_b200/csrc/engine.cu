@@ -831,6 +831,24 @@ int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int
     return B200OCR_OK;
 }
 
+int b200ocr_force_align(const void* neg_logprobs, int32_t is_f64, int32_t n, int32_t t, int32_t c,
+                        const int32_t* n_frames, const int32_t* labels, int32_t l_max, const int32_t* lengths,
+                        int32_t blank, int32_t* out_symbols, int32_t* out_positions, int32_t* char_positions,
+                        int32_t* status, void* cuda_stream) {
+    if (!neg_logprobs || n < 0 || t <= 0 || c <= 1 || !labels || l_max < 1 || !lengths || blank < 0 || blank >= c ||
+        !status || (char_positions && !out_positions))
+        return fail(nullptr, B200OCR_E_INVALID, "bad force_align arguments");
+    if (n == 0) return B200OCR_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    uint8_t* ws = nullptr;
+    CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&ws), force_align_workspace_bytes(n, t, l_max), st));
+    cudaError_t err = launch_force_align(neg_logprobs, is_f64, n, t, c, n_frames, labels, l_max, lengths, blank, ws,
+                                         out_symbols, out_positions, char_positions, status, st);
+    cudaFreeAsync(ws, st);
+    CU_TRY(nullptr, err);
+    return B200OCR_OK;
+}
+
 int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, const float* coords,
                         const int64_t* coord_off, const int32_t* widths, int32_t n, int32_t line_h, uint8_t* out,
                         int32_t out_w, int32_t pad, void* cuda_stream) {

@@ -25,6 +25,13 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
 cudaError_t launch_frame_stats(const float* scores, int n, int t, int c, int layout, int32_t* best, float* fmax,
                                float* flse, float* fprob, cudaStream_t stream);
 
+// CTC forced alignment (force_align.cu; core/force_alignment.py).  bp_ws: force_align_workspace_bytes(n, t, l_max).
+cudaError_t launch_force_align(const void* neg, int is_f64, int n, int t_max, int C, const int32_t* n_frames,
+                               const int32_t* labels, int l_max, const int32_t* lengths, int blank, uint8_t* bp_ws,
+                               int32_t* out_symbols, int32_t* out_positions, int32_t* char_pos, int32_t* status,
+                               cudaStream_t stream);
+size_t force_align_workspace_bytes(int n, int t_max, int l_max);
+
 // Bilinear 8-bit remap of all lines of a page into the padded recogniser batch (remap.cu; crop_engine.py:146-163).
 cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
                                const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,
