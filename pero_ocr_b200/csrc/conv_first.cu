@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t ld_pair(const __half* p) {   // two consecut
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(CFM_PX, 3) conv_first_mma_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
+__global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                               const uint2* __restrict__ wfrag,
                                                               const float* __restrict__ oscale,
                                                               const float* __restrict__ bias, int act, int fmt,
@@ -64,14 +64,11 @@ __global__ void __launch_bounds__(CFM_PX, 3) conv_first_mma_kernel(const uint8_t
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
 
-    // weight fragments: registers for the whole kernel ([plane][k step][n tile] x {b0b1, b2b3})
-    uint2 bf[2][2][NT];
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) bf[p][ks][nt] = __ldg(wfrag + ((p * 2 + ks) * NT + nt) * 32 + lane);
+    // weight fragments ([plane][k step][n tile][lane] x {b0b1, b2b3}) live in shared memory: in registers they cost
+    // 64 of 168 and held the kernel at 3 warps per scheduler (ncu: latency-bound, 7 cycles per issued instruction);
+    // a lane reads its own 8 bytes, consecutive lanes consecutive words: conflict-free
+    __shared__ uint2 s_bf[2 * 2 * NT * 32];
+    for (int i = threadIdx.x; i < 2 * 2 * NT * 32; i += CFM_PX) s_bf[i] = __ldg(wfrag + i);
     for (int i = threadIdx.x; i < COUT; i += CFM_PX) {
         s_sc[i] = oscale[i];
         s_b[i] = bias ? bias[i] : 0.f;
@@ -122,8 +119,10 @@ __global__ void __launch_bounds__(CFM_PX, 3) conv_first_mma_kernel(const uint8_t
                 a[3] = ld_pair(p1 + aoff[ks][1]);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    mma16816(acc[nt], a, bf[0][ks][nt].x, bf[0][ks][nt].y);
-                    mma16816(acc[nt], a, bf[1][ks][nt].x, bf[1][ks][nt].y);
+                    const uint2 bh = s_bf[((0 * 2 + ks) * NT + nt) * 32 + lane];
+                    const uint2 bl = s_bf[((1 * 2 + ks) * NT + nt) * 32 + lane];
+                    mma16816(acc[nt], a, bh.x, bh.y);
+                    mma16816(acc[nt], a, bl.x, bl.y);
                 }
             }
             // fragment -> staged records: rows (pixels) pb+gid and pb+gid+8, channels 8 nt + 2 tig + {0, 1}
