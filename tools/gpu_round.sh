@@ -1,15 +1,15 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench lines (both precisions), the ncu launch list of the bench command and one
-# `ncu --set full` capture of a single device-resident step.  Outputs land in gpurun_out/<tag>_*.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r01'
+# One GPU-box pass: parity tests, bench lines (default precision + fp16x3 + the reference arm), the ncu launch list of
+# the bench command and one `ncu --set full` capture of a single device-resident step.  Outputs: gpurun_out/<tag>_*.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r01e'
 tag=${1:-r01}
-prec=${2:-fp16x3}
+prec=${2:-fp16f8}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/${tag}_smi.txt 2>&1
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
-python bench.py --precision fp16x3 --profile-out $out/${tag}_per_layer_fp16x3.json > $out/${tag}_bench_fp16x3.json 2> $out/${tag}_bench_fp16x3.err
-python bench.py --precision fp16 --no-cpu-baseline --profile-out $out/${tag}_per_layer_fp16.json > $out/${tag}_bench_fp16.json 2> $out/${tag}_bench_fp16.err
+python bench.py --precision $prec --profile-out $out/${tag}_per_layer_${prec}.json > $out/${tag}_bench_${prec}.json 2> $out/${tag}_bench_${prec}.err
+python bench.py --precision fp16x3 --no-cpu-baseline --profile-out $out/${tag}_per_layer_fp16x3.json > $out/${tag}_bench_fp16x3.json 2> $out/${tag}_bench_fp16x3.err
 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 # launch list of the bench command itself (per-launch times are cold-cache and serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
