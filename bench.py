@@ -214,6 +214,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep stdout to the one JSON line whatever NCCL_DEBUG is
     import torch
     import torch.distributed as dist
     from pero_ocr_b200 import synthetic as cases
