@@ -1,0 +1,165 @@
+"""Measurement of the SURVEY 8(f) rows built next to the hot path: line cropper, logit sparsification, forced alignment.
+
+    python -m tests.aux_bench > profiles/<round>_aux_bench.json      (lives under tests/: it runs the oracle as the CPU side)
+
+For each: device time of the kernel(s) by CUDA events on the launching stream (inputs resident, warm-up first),
+algorithmic bytes moved against the measured HBM copy bandwidth (all three are byte/integer work bound by memory or
+by a sequential chain, not by the tensor pipe), and the reference algorithm on one host core beside it (cv2.remap
+itself when importable -- it is the reference's own callee -- else the NumPy oracle; the oracle ports otherwise).
+One JSON object per line on stdout.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import cases                                                     # noqa: E402
+from oracle.align_oracle import force_align as oracle_force_align            # noqa: E402
+from oracle.crop_oracle import remap_bilinear_u8                             # noqa: E402
+from oracle.forward_oracle import sparsify_logits                            # noqa: E402
+from pero_ocr_b200.cropper import B200LineCropper, DevicePage, remap_into     # noqa: E402
+from pero_ocr_b200.force_alignment import force_align_batch                  # noqa: E402
+from pero_ocr_b200.sparse_logits import csc_lines, sparsify_device           # noqa: E402
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get('hbm_gbs', 6450.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def bench_cropper(peak):
+    """BASELINE config-4 shaped: one 3000 x 4000 page, 60 baselines of ~1280 output pixels, line height 40."""
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8)
+    cropper = B200LineCropper(line_height=40, poly=2, scale=1)
+    lines = []
+    for i in range(60):
+        y = 60 + i * 48
+        lines.append(([[100, y], [1400, y + rng.integers(-6, 7)], [2700, y + rng.integers(-6, 7)]], [26, 14]))
+    t0 = time.perf_counter()
+    maps = [cropper.get_crop_inputs(b, h, 40) for b, h in lines]
+    geom_ms = 1e3 * (time.perf_counter() - t0)
+    page = DevicePage(img)
+    width = int(np.ceil(max(m.shape[1] for m in maps) / 32.0) * 32) + 64
+    out = torch.empty((len(maps), 40, width, 3), dtype=torch.uint8, device='cuda')
+    coords, offs, widths, _ = page.stage_maps(maps)
+    from pero_ocr_b200 import _lib
+    import ctypes as C
+    lib = _lib.load_library()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def kernel():
+        _lib.check(lib.b200ocr_remap_lines(page.image.data_ptr(), 3000, 4000, coords.data_ptr(), offs.data_ptr(),
+                                           widths.data_ptr(), len(maps), 40, out.data_ptr(), width, 32,
+                                           C.c_void_p(stream)))
+    ms = timed(kernel, reps=20)
+    px = sum(40 * m.shape[1] for m in maps)
+    algo_bytes = px * (8 + 3 + 3) + (out.numel() - px * 3)      # map read + source pixel (each used ~once) + store; padding
+    e2e_ms = timed(lambda: remap_into(page, maps, out, 32), reps=5)
+    # CPU: the reference's callee on one core
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        t0 = time.perf_counter()
+        for m in maps[:20]:
+            cv2.remap(img, m[..., 0], m[..., 1], interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+        cpu_ms, cpu_kind = 1e3 * (time.perf_counter() - t0) / 20, 'cv2.remap 4.x, 1 thread (the reference\'s callee)'
+    except ImportError:
+        t0 = time.perf_counter()
+        for m in maps[:4]:
+            remap_bilinear_u8(img, m)
+        cpu_ms, cpu_kind = 1e3 * (time.perf_counter() - t0) / 4, 'NumPy oracle, 1 core'
+    got = out.cpu().numpy()
+    ok = bool(np.array_equal(got[7, :, 32:32 + maps[7].shape[1]], remap_bilinear_u8(img, maps[7])))
+    return {'op': 'line cropper (b200ocr_remap_lines)', 'workload': '60 lines x 40 x ~1300 px from one 3000x4000 page',
+            'gpu_ms_per_page': ms, 'gpu_us_per_line': 1e3 * ms / len(maps),
+            'gpu_ms_per_page_with_map_upload': e2e_ms, 'host_geometry_ms_per_page': geom_ms,
+            'cpu_ms_per_line': cpu_ms, 'cpu_kind': cpu_kind,
+            'roofline': {'bound': 'hbm', 'achieved': algo_bytes / (ms * 1e-3) / 1e9, 'peak': peak[0], 'unit': 'GB/s',
+                         'frac': algo_bytes / (ms * 1e-3) / 1e9 / peak[0], 'peak_source': peak[1],
+                         'algorithmic_bytes_per_pixel': 14},
+            'parity_spot_check_vs_oracle': ok}
+
+
+def bench_sparsify(peak):
+    """256 lines x 336 frames x 120 classes of trained-net-like (peaky) logits."""
+    rng = np.random.default_rng(2)
+    lp = cases.peaky_logprobs(rng, 16, 336, 120, sharp=11.0).astype(np.float32)
+    raw = np.tile(lp, (16, 1, 1)) + 3.0                       # raw logits: log-probs shifted (softmax invariant)
+    x = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+    sp = sparsify_device(x)
+    ms = timed(lambda: sparsify_device(x, out=sp), reps=10)
+    total = int(sp.base.cpu()[-1])
+    algo_bytes = 2 * x.numel() * 4 + total * 8 + sp.indptr.numel() * 4
+    t0 = time.perf_counter()
+    host = [sparsify_logits(raw[i]) for i in range(16)]
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / 16
+    got = csc_lines(sp)
+    same = all((got[i] != host[i]).nnz <= 2 for i in range(16))
+    return {'op': 'logit sparsification (b200ocr_sparsify_logits)', 'workload': '256 x 336 x 120 peaky logits',
+            'gpu_ms_per_batch': ms, 'gpu_us_per_line': 1e3 * ms / 256, 'entries_kept_per_frame': total / (256 * 336),
+            'd2h_bytes_per_line_sparse': (total * 8 + sp.indptr.numel() * 4) / 256, 'd2h_bytes_per_line_dense': 336 * 120 * 4,
+            'cpu_ms_per_line': cpu_ms, 'cpu_kind': 'NumPy + scipy.sparse oracle (the reference\'s pass), 1 core',
+            'roofline': {'bound': 'hbm', 'achieved': algo_bytes / (ms * 1e-3) / 1e9, 'peak': peak[0], 'unit': 'GB/s',
+                         'frac': algo_bytes / (ms * 1e-3) / 1e9 / peak[0], 'peak_source': peak[1],
+                         'algorithmic_bytes_per_line': algo_bytes / 256},
+            'parity_spot_check_vs_oracle': bool(same)}
+
+
+def bench_align(peak):
+    """256 lines x 336 frames x 120 classes, transcriptions = the greedy text of each line (~40-60 symbols)."""
+    rng = np.random.default_rng(3)
+    lp = cases.peaky_logprobs(rng, 32, 336, 120, sharp=10.0).astype(np.float32)
+    neg = np.ascontiguousarray(np.tile(-lp, (8, 1, 1)))
+    labels = []
+    for i in range(256):
+        best = lp[i % 32].argmax(axis=1)
+        labels.append([int(v) for k, v in enumerate(best) if v != 119 and (k == 0 or best[k - 1] != v)] or [1])
+    x = torch.from_numpy(neg).cuda()
+    res = force_align_batch(x, labels, 119, want_char_positions=True)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        force_align_batch(x, labels, 119, want_char_positions=True)
+    wall_ms = 1e3 * (time.perf_counter() - t0) / 3               # includes label upload + result download
+    t0 = time.perf_counter()
+    want = [oracle_force_align(neg[i], labels[i], 119) for i in range(2)]
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / 2
+    ok = all(list(res['symbols'][i]) == want[i] for i in range(2)) and int(res['status'].max()) == 0
+    mean_len = float(np.mean([len(l) for l in labels]))
+    return {'op': 'CTC forced alignment (b200ocr_force_align)', 'workload': f'256 lines x 336 frames x 120 classes, mean text length {mean_len:.0f}',
+            'gpu_ms_per_batch_incl_transfers': wall_ms, 'gpu_us_per_line': 1e3 * wall_ms / 256,
+            'cpu_ms_per_line': cpu_ms, 'cpu_kind': 'pure-Python oracle restatement of force_alignment.py, 1 core',
+            'bound': 'latency of the T sequential frames (one CTA per line; 256 lines = 2 waves)',
+            'parity_spot_check_vs_oracle': bool(ok)}
+
+
+def main():
+    assert torch.cuda.is_available()
+    peak = hbm_peak()
+    for fn in (bench_cropper, bench_sparsify, bench_align):
+        print(json.dumps(fn(peak)), flush=True)
+
+
+if __name__ == '__main__':
+    main()
