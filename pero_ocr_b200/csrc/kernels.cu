@@ -389,21 +389,36 @@ __global__ void h2f_kernel(const __half* __restrict__ in, long rows, int d, int 
     out[idx] = act_load(in + r * act_planes(fmt) * d, d, i, fmt);
 }
 
-// One CTA per (line, head); K and V of the head staged in shared memory as fp32, one warp per query row.
+// One CTA per (line, head), one warp per query row.  SMEM_KV: K and V of the head are staged in shared memory as
+// fp32 (T <= ~400 frames for 64-wide heads); otherwise (very long lines) they are read in place from the L2-resident
+// qkv tensor with the same arithmetic in the same order.
+template <bool SMEM_KV>
 __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, int D, int heads, __half* out, int fmt) {
     const int planes = act_planes(fmt);
     extern __shared__ float s_att[];
     const int dh = D / heads;
-    float* sK = s_att;                 // [T][dh+1]
-    float* sV = sK + T * (dh + 1);     // [T][dh+1]
-    float* sP = sV + T * (dh + 1);     // [warps][T]
     const int line = blockIdx.x / heads, head = blockIdx.x % heads;
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* base = qkv + static_cast<size_t>(line) * T * 3 * D;
-    for (int i = threadIdx.x; i < T * dh; i += blockDim.x) {
-        const int t = i / dh, e = i % dh;
-        sK[t * (dh + 1) + e] = base[static_cast<size_t>(t) * 3 * D + D + head * dh + e];
-        sV[t * (dh + 1) + e] = base[static_cast<size_t>(t) * 3 * D + 2 * D + head * dh + e];
+    const float* sK;                   // row tk of the head's K at sK + tk * kv_stride
+    const float* sV;
+    float* sP;                         // [warps][T]
+    int kv_stride;
+    if (SMEM_KV) {
+        float* k = s_att;              // [T][dh+1]
+        float* v = k + T * (dh + 1);   // [T][dh+1]
+        sP = v + T * (dh + 1);
+        for (int i = threadIdx.x; i < T * dh; i += blockDim.x) {
+            const int t = i / dh, e = i % dh;
+            k[t * (dh + 1) + e] = base[static_cast<size_t>(t) * 3 * D + D + head * dh + e];
+            v[t * (dh + 1) + e] = base[static_cast<size_t>(t) * 3 * D + 2 * D + head * dh + e];
+        }
+        sK = k; sV = v; kv_stride = dh + 1;
+    } else {
+        sP = s_att;
+        sK = base + D + head * dh;
+        sV = base + 2 * D + head * dh;
+        kv_stride = 3 * D;
     }
     __syncthreads();
     const float scale = rsqrtf(static_cast<float>(dh));
@@ -413,7 +428,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
         float m = -INFINITY;
         for (int tk = lane; tk < T; tk += 32) {
             float s = 0.f;
-            for (int e = 0; e < dh; ++e) s = fmaf(q[e] * scale, sK[tk * (dh + 1) + e], s);
+            for (int e = 0; e < dh; ++e) s = fmaf(q[e] * scale, sK[static_cast<size_t>(tk) * kv_stride + e], s);
             p[tk] = s;
             m = fmaxf(m, s);
         }
@@ -429,7 +444,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
         const float inv = 1.f / sum;
         for (int e = lane; e < dh; e += 32) {
             float acc = 0.f;
-            for (int tk = 0; tk < T; ++tk) acc = fmaf(p[tk], sV[tk * (dh + 1) + e], acc);
+            for (int tk = 0; tk < T; ++tk) acc = fmaf(p[tk], sV[static_cast<size_t>(tk) * kv_stride + e], acc);
             acc *= inv;
             const size_t row = static_cast<size_t>(line) * T + tq;
             act_store(out + row * planes * D, D, head * dh + e, acc, fmt);
@@ -519,14 +534,21 @@ cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, _
                              cudaStream_t stream) {
     const int dh = D / heads;
     const int warps = 8;
-    const size_t smem = (2 * static_cast<size_t>(T) * (dh + 1) + static_cast<size_t>(warps) * T) * sizeof(float);
+    const size_t smem_kv = (2 * static_cast<size_t>(T) * (dh + 1) + static_cast<size_t>(warps) * T) * sizeof(float);
+    const size_t smem_p = static_cast<size_t>(warps) * T * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    if (smem > 220 * 1024) return cudaErrorInvalidValue;
-    attention_kernel<<<n * heads, warps * 32, smem, stream>>>(qkv, n, T, D, heads, out, fmt);
+    if (smem_kv <= 220 * 1024)
+        attention_kernel<true><<<n * heads, warps * 32, smem_kv, stream>>>(qkv, n, T, D, heads, out, fmt);
+    else if (smem_p <= 220 * 1024)
+        attention_kernel<false><<<n * heads, warps * 32, smem_p, stream>>>(qkv, n, T, D, heads, out, fmt);
+    else
+        return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

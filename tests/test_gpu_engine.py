@@ -220,3 +220,26 @@ def test_first_conv_tensor_core_kernel_is_fp32_grade(width):
     scale = float(np.abs(want).max())
     assert np.abs(ref_kernel - want).max() <= 4e-6 * max(scale, 1.0)
     assert np.abs(got - want).max() <= 4e-6 * max(scale, 1.0)
+
+
+def test_transformer_variant_on_a_very_long_line():
+    """A 2016 px line (T = 520 frames) exceeds what the attention kernel can keep of K / V in shared memory; the
+    in-place variant must give the oracle's logits too (same bars as the other engine tests)."""
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    net = make_case_net('transformer')
+    layers, _ = netdesc.describe_line_net(net)
+    eng = LineRecognizer(layers)
+    rng = np.random.default_rng(77)
+    crops = np.zeros((2, 40, 2080, 3), dtype=np.uint8)
+    crops[:, :, 32:-32] = np.repeat(rng.integers(0, 256, (2, 40, 2016, 1), dtype=np.uint8), 3, axis=3)
+    with torch.no_grad():
+        ref = net(torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)).numpy()       # [N, C, T]
+    out = eng.forward(torch.from_numpy(crops).cuda(), want_logits=True, want_best_path=True)
+    torch.cuda.synchronize()
+    got = out['logits'].cpu().numpy()
+    assert got.shape == (2, 520, 120)
+    assert np.abs(got - ref.transpose(0, 2, 1)).max() <= TOL
+    srt = np.sort(ref, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > MARGIN                                                # [N, T]
+    assert np.array_equal(out['best_path'].cpu().numpy()[decided], ref.argmax(axis=1)[decided])
