@@ -28,6 +28,7 @@ WIDTH = 1280
 PADDED = WIDTH + 64
 METRIC = 'text-lines/sec (40x1280 crops)'
 UNIT = 'lines/s'
+RESULT_OUT = sys.stdout
 
 
 def peaks():
@@ -189,10 +190,15 @@ def run_reference(args, rank, world):
                          'sample': f'{sample} lines x {args.steps} steps, torch-CPU fp32, {used} threads'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner, warnings) are sent to
+    # stderr by swapping the file descriptors; the JSON line goes to the saved original
+    global RESULT_OUT
+    RESULT_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -214,7 +220,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep stdout to the one JSON line whatever NCCL_DEBUG is
     import torch
     import torch.distributed as dist
     from pero_ocr_b200 import synthetic as cases
@@ -371,7 +376,7 @@ def main():
         line['cpu_baseline'] = {'value': r, 'unit': UNIT, 'cores': used, 'kind': 'port',
                                 'sample': f'{args.cpu_baseline_lines} lines of the same workload in {dt_cpu:.1f} s, torch-CPU fp32'}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

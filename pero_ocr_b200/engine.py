@@ -170,6 +170,8 @@ class B200EngineLineOCR:
                                     device=self.device.index or 0)
         self._slots = None
         self._copy_stream = None
+        self.host_threads = 4            # host threads that pad a batch into pinned memory (process_lines)
+        self._executor = None
         self.want_confidence = False
         self.last_confidences = None
         self.h2d_bytes = 0
@@ -177,6 +179,12 @@ class B200EngineLineOCR:
 
     def _device_ctx(self):
         return self.model.torch.cuda.device(self.device)
+
+    def _pool(self):
+        if getattr(self, '_executor', None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._executor = ThreadPoolExecutor(max_workers=max(1, self.host_threads))
+        return self._executor
 
     # ---- device step --------------------------------------------------------------------------------------
     def _slot(self, k):
@@ -345,9 +353,9 @@ class B200EngineLineOCR:
         pad, height = self.line_padding_px, self.line_px_height
 
         def stager(chunk, width):
-            def fill(view):
-                for slot, idx in enumerate(chunk):
-                    line = lines[idx]
+            def fill_range(view, lo, hi):
+                for slot in range(lo, hi):
+                    line = lines[chunk[slot]]
                     if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
                         raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
                     end = min(width, pad + line.shape[1])
@@ -355,6 +363,18 @@ class B200EngineLineOCR:
                     if end > pad:
                         view[slot, :, pad:end] = line[:, :end - pad]
                     view[slot, :, end:] = 0
+
+            def fill(view):
+                # padding a batch is a 40 MB strided copy at config 2: a few host threads share it (NumPy releases
+                # the GIL inside large copies)
+                n = len(chunk)
+                workers = min(self.host_threads, max(1, n // 16))
+                if workers <= 1:
+                    return fill_range(view, 0, n)
+                step = (n + workers - 1) // workers
+                jobs = [self._pool().submit(fill_range, view, lo, min(n, lo + step)) for lo in range(0, n, step)]
+                for j in jobs:
+                    j.result()
             return {'fill': fill}
 
         return self._run_batches([l.shape[1] for l in lines], stager, sparse_logits, tight_crop_logits, no_logits,

@@ -25,6 +25,8 @@ def _host_only_engine(kind):
     eng.max_input_horizontal_pixels = 480 * eng.batch_size
     eng.characters = cases.json_characters(spec['classes'] - 2) + [u'​']
     eng.want_confidence = False
+    eng.host_threads = 3
+    eng._executor = None
     eng.h2d_bytes = eng.d2h_bytes = 0
     eng._device_ctx = contextlib.nullcontext
     store = {}
@@ -106,3 +108,18 @@ def test_product_package_does_not_import_the_oracle():
         if name.endswith('.py'):
             src = open(os.path.join(pkg, name)).read()
             assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), name
+
+
+def test_threaded_batch_padding_is_equivalent():
+    """process_lines pads large batches with several host threads: same batch bytes, hence same results."""
+    rng = np.random.default_rng(8)
+    lines = [cases.line_crop(rng, int(w)) for w in rng.integers(20, 97, 70)]
+    outs = []
+    for threads in (1, 3):
+        eng = _host_only_engine('lstm')
+        eng.host_threads = threads
+        eng.max_input_horizontal_pixels = 96 * 80          # one batch holds all 70 lines
+        outs.append(eng.process_lines(lines, sparse_logits=False))
+    assert outs[0][0] == outs[1][0] and outs[0][2] == outs[1][2]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b)
