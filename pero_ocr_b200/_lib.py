@@ -75,7 +75,8 @@ EXPORTS = {
 
 
 def library_path():
-    return os.path.join(_HERE, 'libb200_lineocr.so')
+    # B200OCR_LIB: bring-up override used to A/B two builds of the library inside one GPU session
+    return os.environ.get('B200OCR_LIB') or os.path.join(_HERE, 'libb200_lineocr.so')
 
 
 def load_library():

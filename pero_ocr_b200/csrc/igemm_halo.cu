@@ -29,8 +29,12 @@ struct Cfg {
     // stage.  (A third halo stage instead made no difference: the halo loads are not the limiter.)
     static constexpr int kTapsPerStage = BN == 64 ? 3 : 1;
     static constexpr int kAStages = 2;
-    static constexpr int kBStages = BN == 64 ? 3 : 4;
+    // BN = 128 stores through the staged epilogue (actfmt.cuh: epi_store32_staged; the un-pooled 128-channel layer
+    // spent 0.5 of its 1.4 ms on sector-splitting stores): its 32 KB come out of the weight ring (4 -> 3 stages)
+    static constexpr bool kStagedEpi = BN == 128;
+    static constexpr int kBStages = 3;
     static constexpr int kBStageBytes = kTapsPerStage * kBBytes;
+    static constexpr int kEpiStageBytes = kStagedEpi ? 8 * 4096 : 0;
     static constexpr int kTmemCols = 512;
     static constexpr int kBarOff = kAStages * kHaloStage + kBStages * kBStageBytes;
     static constexpr int kSmemBytes = kBarOff + 256 + 1024;
@@ -70,6 +74,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tempty = tfull + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_vec = reinterpret_cast<float*>(smem + C::kBarOff + 256);
+    uint4* s_epi = reinterpret_cast<uint4*>(s_vec + 3 * p.cout_pad);   // kStagedEpi: 256 uint4 per epilogue warp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -276,10 +281,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int rr = 0; rr < 2; ++rr) {
                     if (rr >= rows) break;
                     const int ho = t.h0 + rr;
-                    if (!writer || ho >= p.h_out) continue;
+                    if (ho >= p.h_out) continue;            // warp-uniform
                     __half* orow = p.out_h + (static_cast<size_t>(t.img) * Hp * Wp +
                                               static_cast<size_t>(ho / p.pool_h) * Wp + wo / p.pool_w) * p.out_cstride;
-                    if (!(p.dbg & 1))   // bring-up: time the pipeline without the global stores
+                    if (p.dbg & 1) continue;                // bring-up: time the pipeline without the global stores
+                    if (C::kStagedEpi)
+                        epi_store32_staged(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine,
+                                           p.act, orow, writer, p.cout, FMT, s_epi + (warp - 3) * 256, lane);
+                    else if (writer)
                         epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow,
                                     p.cout, FMT);
                 }
@@ -311,7 +320,7 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float);
+    const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float) + C::kEpiStageBytes;
     if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
     const int tiles_w = (p.w_out + 127) / 128, tiles_h = (p.h_out + 1) / 2;
     const int total_tiles = p.n_img * tiles_h * tiles_w * p.tiles_n;
