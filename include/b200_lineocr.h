@@ -157,6 +157,17 @@ int b200ocr_force_align(const void* neg_logprobs, int32_t is_f64, int32_t n, int
                         int32_t blank, int32_t* out_symbols, int32_t* out_positions, int32_t* char_positions,
                         int32_t* status, void* cuda_stream);
 
+/* Replaces the per-character loop of get_line_confidence (pero_ocr/core/confidence_estimation.py:73-104) for a batch
+ * of lines: confidence of character i = max(0, p[a_i, label_i] - the largest probability of any OTHER non-blank
+ * class (neighbouring labels excluded too) between the borders half-way to the neighbouring characters' frames).
+ *   log_probs      device f32 [n][t][c] log-probabilities (TextLine.get_full_logprobs, core/layout.py:70-72), blank LAST
+ *   n_frames       device i32 [n] or NULL; labels device i32 [n][l_max]; lengths device i32 [n]
+ *   char_positions device i32 [n][l_max]  align_text's frames (b200ocr_force_align); a negative entry gives 0
+ *   confidences    device f32 [n][l_max]  (entries past a line's length are 0) */
+int b200ocr_char_confidence(const float* log_probs, int32_t n, int32_t t, int32_t c, const int32_t* n_frames,
+                            const int32_t* labels, int32_t l_max, const int32_t* lengths,
+                            const int32_t* char_positions, float* confidences, void* cuda_stream);
+
 /* Replaces EngineLineCropper.fast_remap (pero_ocr/core/crop_engine.py:146-163: cv2.remap, INTER_LINEAR,
  * BORDER_CONSTANT 0, 8-bit fixed-point bilinear) for all lines of a page in one launch, writing straight into the
  * zero-padded batch that BaseEngineLineOCR.process_lines builds on the host (line_ocr_engine.py:121-123).

@@ -281,6 +281,12 @@ def golden_align():
         out[f'sym_{name}'] = np.asarray(force_align(neg, labels, blank), dtype=np.int32)
         out[f'pos_{name}'] = np.asarray(force_align(neg, labels, blank, return_seq_positions=True), dtype=np.int32)
         out[f'chr_{name}'] = np.asarray(align_text(neg, np.array(labels), blank), dtype=np.int32)
+        if blank == neg.shape[1] - 1 and name != 'all_ties':
+            # get_line_confidence (confidence_estimation.py:73-104) on the same line: blank must be the last class
+            from pero_ocr.core.confidence_estimation import get_line_confidence
+            line = types.SimpleNamespace(logits=np.zeros(neg.shape, dtype=np.float32))
+            lp = (-neg).astype(np.float32)
+            out[f'conf_{name}'] = np.asarray(get_line_confidence(line, np.array(labels), log_probs=lp), dtype=np.float64)
         info[name] = [int(neg.shape[0]), len(labels), str(neg.dtype)]
     np.savez_compressed(os.path.join(GOLDEN, 'align.npz'), **out)
     return info

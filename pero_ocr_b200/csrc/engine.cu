@@ -849,6 +849,17 @@ int b200ocr_force_align(const void* neg_logprobs, int32_t is_f64, int32_t n, int
     return B200OCR_OK;
 }
 
+int b200ocr_char_confidence(const float* log_probs, int32_t n, int32_t t, int32_t c, const int32_t* n_frames,
+                            const int32_t* labels, int32_t l_max, const int32_t* lengths,
+                            const int32_t* char_positions, float* confidences, void* cuda_stream) {
+    if (!log_probs || n < 0 || t <= 0 || c <= 1 || !labels || l_max < 1 || !lengths || !char_positions || !confidences)
+        return fail(nullptr, B200OCR_E_INVALID, "bad char_confidence arguments");
+    if (n == 0) return B200OCR_OK;
+    CU_TRY(nullptr, launch_char_conf(log_probs, n, t, c, n_frames, labels, l_max, lengths, char_positions, confidences,
+                                     static_cast<cudaStream_t>(cuda_stream)));
+    return B200OCR_OK;
+}
+
 int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, const float* coords,
                         const int64_t* coord_off, const int32_t* widths, int32_t n, int32_t line_h, uint8_t* out,
                         int32_t out_w, int32_t pad, void* cuda_stream) {

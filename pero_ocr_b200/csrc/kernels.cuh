@@ -32,6 +32,11 @@ cudaError_t launch_force_align(const void* neg, int is_f64, int n, int t_max, in
                                cudaStream_t stream);
 size_t force_align_workspace_bytes(int n, int t_max, int l_max);
 
+// Per-character confidences (char_conf.cu; core/confidence_estimation.py:73-104).
+cudaError_t launch_char_conf(const float* logp, int n, int t_max, int C, const int32_t* n_frames, const int32_t* labels,
+                             int l_max, const int32_t* lengths, const int32_t* char_pos, float* conf,
+                             cudaStream_t stream);
+
 // Bilinear 8-bit remap of all lines of a page into the padded recogniser batch (remap.cu; crop_engine.py:146-163).
 cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
                                const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,

@@ -70,3 +70,43 @@ def test_batch_of_ragged_lines_matches_oracle():
         assert list(res['positions'][i, :frames[i]]) == oracle_force_align(x, labels[i], c - 1, True), i
         assert (res['symbols'][i, frames[i]:] == -1).all()
         assert np.array_equal(res['char_positions'][i, :len(labels[i])], oracle_align_text(x, labels[i], c - 1)), i
+
+
+def test_char_confidences_match_reference_golden(golden_dir):
+    """b200ocr_char_confidence against get_line_confidence of the unmodified reference.  float32 arithmetic with CUDA's
+    expf instead of NumPy's: 2e-6 absolute on probabilities in [0, 1]."""
+    from pero_ocr_b200.confidence_estimation import get_line_confidence, line_confidences_batch
+    gold = load_golden(golden_dir, 'align.npz')
+    import types
+    seen = 0
+    for name, neg, labels, blank in align_cases():
+        if f'conf_{name}' not in gold.files:
+            continue
+        lp = (-neg).astype(np.float32)
+        line = types.SimpleNamespace(logits=np.zeros(lp.shape, dtype=np.float32))
+        got = get_line_confidence(line, np.array(labels), log_probs=lp)
+        assert got.shape == gold[f'conf_{name}'].shape
+        assert np.abs(got - gold[f'conf_{name}']).max() <= 2e-6, name
+        # with the alignment handed in (the reference's aligned_letters argument)
+        got2 = get_line_confidence(line, np.array(labels), aligned_letters=gold[f'chr_{name}'], log_probs=lp)
+        assert np.abs(got2 - gold[f'conf_{name}']).max() <= 2e-6, name
+        seen += 1
+    assert seen >= 6
+
+
+def test_char_confidences_batch_matches_oracle():
+    from oracle.confidence_oracle import line_confidence
+    from pero_ocr_b200.confidence_estimation import line_confidences_batch
+    rng = np.random.default_rng(41)
+    n, t, c = 12, 200, 60
+    lp = cases.peaky_logprobs(rng, n, t, c, sharp=10.0).astype(np.float32)
+    frames = rng.integers(60, t + 1, n)
+    labels = []
+    for i in range(n):
+        best = lp[i, :frames[i]].argmax(axis=1)
+        labels.append([int(v) for k, v in enumerate(best) if v != c - 1 and (k == 0 or best[k - 1] != v)] or [3])
+    conf, status = line_confidences_batch(lp, labels, n_frames=frames)
+    assert (status == 0).all()
+    for i in range(n):
+        want = line_confidence(lp[i, :frames[i]], labels[i])
+        assert np.abs(conf[i] - want).max() <= 2e-6, i

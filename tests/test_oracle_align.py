@@ -25,3 +25,17 @@ def test_oracle_matches_reference_golden(golden_dir):
         assert force_align(neg, labels, blank) == list(gold[f'sym_{name}']), name
         assert force_align(neg, labels, blank, return_seq_positions=True) == list(gold[f'pos_{name}']), name
         assert np.array_equal(align_text(neg, np.array(labels), blank), gold[f'chr_{name}']), name
+
+
+def test_char_confidence_oracle_matches_reference_golden(golden_dir):
+    """oracle/confidence_oracle.py restates get_line_confidence (confidence_estimation.py:73-104)."""
+    from oracle.confidence_oracle import line_confidence
+    gold = load_golden(golden_dir, 'align.npz')
+    seen = 0
+    for name, neg, labels, blank in align_cases():
+        if f'conf_{name}' not in gold.files:
+            continue
+        got = line_confidence((-neg).astype(np.float32), labels)
+        assert np.array_equal(got, gold[f'conf_{name}']), name
+        seen += 1
+    assert seen >= 6
