@@ -204,6 +204,20 @@ int b200ocr_sparsify_logits(const float* logits, int32_t n, int32_t t, int32_t c
 int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
                             int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream);
 
+/* b200ocr_ctc_prefix_beam on a frame range per line: t_lo / t_hi device i32 [n] (both or neither), the slice
+ * `logprobs[logit_coords[0]:logit_coords[1]]` that PageDecoder.decode_line takes before calling the decoder
+ * (pero_ocr/document_ocr/page_parser.py:133-135).  Lets a page's lines of different widths share one launch. */
+int b200ocr_ctc_prefix_beam_ranges(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k,
+                                   const int32_t* t_lo, const int32_t* t_hi, int32_t* out_labels, int32_t* out_lengths,
+                                   double* out_scores, int32_t* status, void* cuda_stream);
+
+/* Replaces, on the device, the chain that turns the recogniser's raw logits into the decoders' input: sparsification
+ * (line_ocr_engine.py:168-172) -> TextLine.get_dense_logits (zeros -> -80) -> get_full_logprobs (float32 log-softmax)
+ * (pero_ocr/core/layout.py:65-72).
+ *   logits    device f32 [n][t][c] (b200ocr_forward's `logits`)
+ *   logprobs  device f64 [n][t][c] (the decoders' working type) */
+int b200ocr_full_logprobs(const float* logits, int32_t n, int32_t t, int32_t c, double* logprobs, void* cuda_stream);
+
 /* Per-launch device timing for bench.py's roofline leg: while on, every kernel launched by b200ocr_forward is
  * bracketed by CUDA events on its stream.  b200ocr_profile_read synchronises the device, returns one record per
  * launch (tag 0 = first conv, 1 = tcgen05 implicit GEMM, 2 = tcgen05 LSTM recurrence, 3 = other; index of the layer;

@@ -65,6 +65,9 @@ EXPORTS = {
                                           C.c_void_p]),
     'b200ocr_ctc_prefix_beam': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+   'b200ocr_ctc_prefix_beam_ranges': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'b200ocr_full_logprobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'b200ocr_profile': (C.c_int, [C.c_void_p, C.c_int32]),
     'b200ocr_profile_read': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_int32)]),

@@ -44,7 +44,8 @@ __device__ bool same_string(const int* parent, const int* chr, int a, int b) {
 
 __global__ void __launch_bounds__(kThreads)
 prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32_t* out_labels, int32_t* out_lengths,
-                   double* out_scores, int32_t* status, int* ws_parent, int* ws_char, int nodes_per_line) {
+                   double* out_scores, int32_t* status, int* ws_parent, int* ws_char, int nodes_per_line,
+                   const int32_t* __restrict__ t_lo, const int32_t* __restrict__ t_hi) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int cols_max = C + 1;  // S + 2 <= (C - 1) + 2
     double* table = reinterpret_cast<double*>(dyn);              // [K][cols_max]
@@ -63,6 +64,10 @@ prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32
     __shared__ int s_S, s_flag, s_nkeep;
 
     const int line = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // frames [f_lo, f_hi) of the line are decoded (PageDecoder slices the log-probs by logit_coords,
+    // document_ocr/page_parser.py:133-135); the whole matrix when no ranges are given
+    const int f_lo = t_lo ? max(0, min(T, t_lo[line])) : 0;
+    const int f_hi = t_hi ? max(f_lo, min(T, t_hi[line])) : T;
     const double* lp = lp_all + static_cast<size_t>(line) * T * C;
     int* parent = ws_parent + static_cast<size_t>(line) * nodes_per_line;
     int* chr = ws_char + static_cast<size_t>(line) * nodes_per_line;
@@ -71,7 +76,7 @@ prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32
     // normalisation gate (decoders.py:223-224): max_t |sum_c exp(lp) - 1| <= 1e-5
     if (tid == 0) s_flag = 0;
     __syncthreads();
-    for (int t = tid; t < T; t += kThreads) {
+    for (int t = f_lo + tid; t < f_hi; t += kThreads) {
         double s = 0;
         for (int c = 0; c < C; ++c) s += exp(lp[static_cast<size_t>(t) * C + c]);
         if (!(fabs(s - 1.0) <= 1e-5)) s_flag = 1;
@@ -98,7 +103,7 @@ prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32
     int nb = 1, cur = 0, next_node = 1;
     __syncthreads();
 
-    for (int t = 0; t < T; ++t) {
+    for (int t = f_lo; t < f_hi; ++t) {
         const double* row = lp + static_cast<size_t>(t) * C;
         Beam& B = beams[cur];
         Beam& N = beams[cur ^ 1];
@@ -291,9 +296,9 @@ size_t ctc_beam_workspace_bytes(int n, int t, int c, int k) {
     return static_cast<size_t>(n) * nodes * 2 * sizeof(int);
 }
 
-cudaError_t launch_ctc_prefix_beam(const double* logprobs, int n, int t, int c, int k, int32_t* out_labels,
-                                   int32_t* out_lengths, double* out_scores, int32_t* status, void* workspace,
-                                   cudaStream_t stream) {
+cudaError_t launch_ctc_prefix_beam(const double* logprobs, int n, int t, int c, int k, const int32_t* t_lo,
+                                   const int32_t* t_hi, int32_t* out_labels, int32_t* out_lengths, double* out_scores,
+                                   int32_t* status, void* workspace, cudaStream_t stream) {
     const int nodes = t * k + 1;
     int* ws_parent = static_cast<int*>(workspace);
     int* ws_char = ws_parent + static_cast<size_t>(n) * nodes;
@@ -303,6 +308,6 @@ cudaError_t launch_ctc_prefix_beam(const double* logprobs, int n, int t, int c, 
         if (e != cudaSuccess) return e;
     }
     prefix_beam_kernel<<<n, kThreads, dyn, stream>>>(logprobs, t, c, k, out_labels, out_lengths, out_scores, status,
-                                                     ws_parent, ws_char, nodes);
+                                                     ws_parent, ws_char, nodes, t_lo, t_hi);
     return cudaGetLastError();
 }

@@ -883,9 +883,11 @@ int b200ocr_sparsify_logits(const float* logits, int32_t n, int32_t t, int32_t c
     return B200OCR_OK;
 }
 
-int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
-                            int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream) {
-    if (!logprobs || n < 0 || t <= 0 || c <= 1 || k < 1 || !out_labels || !out_lengths || !out_scores || !status)
+int b200ocr_ctc_prefix_beam_ranges(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k,
+                                   const int32_t* t_lo, const int32_t* t_hi, int32_t* out_labels, int32_t* out_lengths,
+                                   double* out_scores, int32_t* status, void* cuda_stream) {
+    if (!logprobs || n < 0 || t <= 0 || c <= 1 || k < 1 || !out_labels || !out_lengths || !out_scores || !status ||
+        ((t_lo == nullptr) != (t_hi == nullptr)))
         return fail(nullptr, B200OCR_E_INVALID, "bad ctc_prefix_beam arguments");
     if (n == 0) return B200OCR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -893,9 +895,24 @@ int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_
     const size_t ws_bytes = ctc_beam_workspace_bytes(n, t, c, k);
     if (ws_bytes == 0) return fail(nullptr, B200OCR_E_INVALID, "beam size / class count not supported (k <= 64, c <= 1024)");
     CU_TRY(nullptr, cudaMallocAsync(&ws, ws_bytes, st));
-    cudaError_t err = launch_ctc_prefix_beam(logprobs, n, t, c, k, out_labels, out_lengths, out_scores, status, ws, st);
+    cudaError_t err = launch_ctc_prefix_beam(logprobs, n, t, c, k, t_lo, t_hi, out_labels, out_lengths, out_scores, status,
+                                             ws, st);
     cudaFreeAsync(ws, st);
     if (err != cudaSuccess) return fail(nullptr, B200OCR_E_CUDA, "prefix beam launch failed: %s", cudaGetErrorString(err));
+    return B200OCR_OK;
+}
+
+int b200ocr_ctc_prefix_beam(const double* logprobs, int32_t n, int32_t t, int32_t c, int32_t k, int32_t* out_labels,
+                            int32_t* out_lengths, double* out_scores, int32_t* status, void* cuda_stream) {
+    return b200ocr_ctc_prefix_beam_ranges(logprobs, n, t, c, k, nullptr, nullptr, out_labels, out_lengths, out_scores,
+                                          status, cuda_stream);
+}
+
+int b200ocr_full_logprobs(const float* logits, int32_t n, int32_t t, int32_t c, double* logprobs, void* cuda_stream) {
+    if (!logits || n < 0 || t <= 0 || c <= 0 || !logprobs)
+        return fail(nullptr, B200OCR_E_INVALID, "bad full_logprobs arguments");
+    if (n == 0) return B200OCR_OK;
+    CU_TRY(nullptr, launch_full_logprobs(logits, n, t, c, logprobs, static_cast<cudaStream_t>(cuda_stream)));
     return B200OCR_OK;
 }
 

@@ -47,6 +47,9 @@ cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int3
                             int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices, float* data,
                             int64_t capacity, cudaStream_t stream);
 
+// Dense log-probabilities as seen through the sparsify -> get_full_logprobs round trip (sparsify.cu).
+cudaError_t launch_full_logprobs(const float* logits, int n, int T, int C, double* out, cudaStream_t stream);
+
 // greedy_decode_ctc's collapse (pytorch_ocr_engine.py:19-27) on per-frame argmax ids: drop repeats (frame 0 is
 // compared with a virtual blank), drop blanks; left-packed labels (-1 padded) + lengths; optional line
 // confidence = get_prob (page_parser.py:437-450) over fprob.

@@ -127,7 +127,58 @@ __global__ void __launch_bounds__(SP_THREADS) sparsify_fill_kernel(const float* 
     }
 }
 
+// What a consumer of TextLine.logits sees after the sparsify -> CSC -> get_full_logprobs round trip
+// (line_ocr_engine.py:168-172, core/layout.py:65-72), computed straight from the dense logits on the device: entries
+// the sparsification drops (softmax p < 1e-4, or a raw 0.0) become -80, then a float32 log-softmax per frame (the
+// reference's x - np.logaddexp.reduce(x) of core/layout.py:32-34, evaluated as x - max - log(sum(exp(x - max))): equal
+// up to float32 rounding, ~1e-6); written as float64, the decoders' working type.
+__global__ void full_logprobs_kernel(const float* __restrict__ logits, long frames, int C, double* __restrict__ out) {
+    const long f = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= frames) return;
+    const float* row = logits + f * C;
+    double* o = out + f * C;
+    float mx = row[0];
+    bool nan = mx != mx;
+    for (int c = 1; c < C; ++c) {
+        const float v = row[c];
+        if (v != v) nan = true;
+        mx = fmaxf(mx, v);
+    }
+    if (nan) mx = __int_as_float(0x7fc00000);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+    // second softmax: over the densified values
+    float mx2 = -INFINITY;
+    bool nan2 = false;
+    for (int c = 0; c < C; ++c) {
+        const float v = row[c];
+        const float d = sp_keep(v, mx, sum) ? v : -80.f;
+        if (d != d) nan2 = true;
+        mx2 = fmaxf(mx2, d);
+    }
+    if (nan2) mx2 = __int_as_float(0x7fc00000);
+    float sum2 = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float v = row[c];
+        const float d = sp_keep(v, mx, sum) ? v : -80.f;
+        sum2 += expf(d - mx2);
+    }
+    const float lse = logf(sum2);
+    for (int c = 0; c < C; ++c) {
+        const float v = row[c];
+        const float d = sp_keep(v, mx, sum) ? v : -80.f;
+        o[c] = static_cast<double>((d - mx2) - lse);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_full_logprobs(const float* logits, int n, int T, int C, double* out, cudaStream_t stream) {
+    const long frames = static_cast<long>(n) * T;
+    if (frames <= 0) return cudaSuccess;
+    full_logprobs_kernel<<<static_cast<unsigned>((frames + 127) / 128), 128, 0, stream>>>(logits, frames, C, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int32_t* t_lo, const int32_t* t_hi,
                             int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices, float* data,

@@ -123,6 +123,34 @@ def prefix_beam_device(x, k):
     return labels, lengths, scores, status
 
 
+def full_logprobs_device(logits):
+    """logits: contiguous CUDA float32 [N,T,C] raw recogniser outputs -> CUDA float64 [N,T,C]: what
+    ``TextLine.get_full_logprobs()`` returns after the engine's sparsification (line_ocr_engine.py:168-172,
+    core/layout.py:65-72), computed on the device; no synchronisation."""
+    torch = _torch()
+    lib = _lib.load_library()
+    n, t, c = logits.shape
+    out = torch.empty((n, t, c), dtype=torch.float64, device=logits.device)
+    _lib.check(lib.b200ocr_full_logprobs(logits.data_ptr(), n, t, c, out.data_ptr(), _stream(torch, logits.device)))
+    return out
+
+
+def prefix_beam_device_ranges(x, k, t_lo, t_hi):
+    """prefix_beam_device on the frame range [t_lo[i], t_hi[i]) of every line (CUDA int32 [N] tensors)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    n, t, c = x.shape
+    dev = x.device
+    labels = torch.empty((n, k, t), dtype=torch.int32, device=dev)
+    lengths = torch.empty((n, k), dtype=torch.int32, device=dev)
+    scores = torch.empty((n, k), dtype=torch.float64, device=dev)
+    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.check(lib.b200ocr_ctc_prefix_beam_ranges(x.data_ptr(), n, t, c, k, t_lo.data_ptr(), t_hi.data_ptr(),
+                                                  labels.data_ptr(), lengths.data_ptr(), scores.data_ptr(),
+                                                  status.data_ptr(), _stream(torch, dev)))
+    return labels, lengths, scores, status
+
+
 def greedy_ids(scores, layout='ntc', want_confidence=False, device=None):
     """scores: np.ndarray or CUDA tensor, [N,T,C] ('ntc') or [N,C,T] ('nct'), blank = last class.
     -> dict(labels [N,T] i32 left-packed -1 padded, lengths [N], best_path [N,T], frame_max, frame_lse[, confidence])
@@ -244,20 +272,27 @@ class CTCPrefixLogRawNumpyDecoder:
             status = torch.empty((n,), dtype=torch.int32, device=dev)
             _lib.check(lib.b200ocr_ctc_prefix_beam(x.data_ptr(), n, t, c, k, labels.data_ptr(), lengths.data_ptr(),
                                                    scores.data_ptr(), status.data_ptr(), _stream(torch, dev)))
-            labels, lengths = labels.cpu().numpy(), lengths.cpu().numpy()
-            scores, status = scores.cpu().numpy(), status.cpu().numpy()
-            for row, i in enumerate(idxs):
-                if status[row] != 0:
-                    raise ValueError('Expected properly normalized logits')
-                bag = BagOfHypotheses()
-                for b in range(k):
-                    ln = lengths[row, b]
-                    if ln < 0:
-                        continue
-                    text = self.symbol_separator.join(self._letters[j] for j in labels[row, b, :ln])
-                    bag.add(text, float(scores[row, b]), 0)
-                bag.sort()
-                bags[i] = bag
+            for row, bag in enumerate(self.bags_from_device(labels, lengths, scores, status)):
+                bags[idxs[row]] = bag
+        return bags
+
+    def bags_from_device(self, labels, lengths, scores, status):
+        """Device results of b200ocr_ctc_prefix_beam[_ranges] -> list of BagOfHypotheses (one per line)."""
+        labels, lengths = labels.cpu().numpy(), lengths.cpu().numpy()
+        scores, status = scores.cpu().numpy(), status.cpu().numpy()
+        bags = []
+        for row in range(labels.shape[0]):
+            if status[row] != 0:
+                raise ValueError('Expected properly normalized logits')
+            bag = BagOfHypotheses()
+            for b in range(labels.shape[1]):
+                ln = lengths[row, b]
+                if ln < 0:
+                    continue
+                text = self.symbol_separator.join(self._letters[j] for j in labels[row, b, :ln])
+                bag.add(text, float(scores[row, b]), 0)
+            bag.sort()
+            bags.append(bag)
         return bags
 
     def __call__(self, logits, model_eos=False, max_unnormalization=1e-5, return_h=False, init_h=None):

@@ -380,6 +380,45 @@ class B200EngineLineOCR:
         return self._run_batches([l.shape[1] for l in lines], stager, sparse_logits, tight_crop_logits, no_logits,
                                  return_ids)
 
+    def decode_lines(self, lines, decoder):
+        """Recognise and beam-decode in one pass on the device: the work of PageOCR.process_page followed by
+        PageDecoder.process_page with a CTC prefix decoder without LM (page_parser.py:418-430 and 108-142) --
+        raw logits -> sparsification semantics -> -80 fill -> log-softmax (core/layout.py:65-72) -> the slice
+        [logit_coords[0]:logit_coords[1]] -> prefix beam search -- without the logits ever leaving the GPU.
+        `decoder`: pero_ocr_b200.decoders.CTCPrefixLogRawNumpyDecoder built on `self.characters + ['<BLANK>']`.
+        -> list of BagOfHypotheses, one per line (what `decoder(logprobs)` returns in the reference chain)."""
+        from .decoders import CTCPrefixLogRawNumpyDecoder, full_logprobs_device, prefix_beam_device_ranges
+        if not isinstance(decoder, CTCPrefixLogRawNumpyDecoder):
+            raise TypeError('decode_lines fuses the GPU prefix beam decoder (CTCPrefixLogRawNumpyDecoder, lm=None)')
+        if len(decoder._letters) != len(self.characters) + 1:
+            raise ValueError('decoder letters must be the engine characters plus the blank symbol')
+        torch = self.model.torch
+        pad, sub, height = self.line_padding_px, self.net_subsampling, self.line_px_height
+        budget = self.max_input_horizontal_pixels
+        widths = [l.shape[1] for l in lines]
+        bags = [None] * len(lines)
+        with self._device_ctx():
+            for chunk, widest in self._batches(widths):
+                width = min(widest + 2 * pad, budget)
+                batch = np.zeros((len(chunk), height, width, 3), dtype=np.uint8)
+                for slot, idx in enumerate(chunk):
+                    line = lines[idx]
+                    if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
+                        raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
+                    end = min(width, pad + line.shape[1])
+                    if end > pad:
+                        batch[slot, :, pad:end] = line[:, :end - pad]
+                dev = torch.from_numpy(batch).to(self.device)
+                self.h2d_bytes += batch.nbytes
+                out = self.model.forward(dev, want_logits=True)
+                lp = full_logprobs_device(out['logits'])
+                lo = torch.full((len(chunk),), pad // sub, dtype=torch.int32, device=self.device)
+                hi = torch.tensor([(pad + widths[i]) // sub for i in chunk], dtype=torch.int32, device=self.device)
+                res = prefix_beam_device_ranges(lp, decoder._k, lo, hi)
+                for slot, bag in enumerate(decoder.bags_from_device(*res)):
+                    bags[chunk[slot]] = bag
+        return bags
+
     def process_line_maps(self, page, maps, sparse_logits=True, tight_crop_logits=False, no_logits=False,
                           return_ids=False):
         """Lines given as sampling maps instead of pixels: `page` is a cropper.DevicePage (the page image, uploaded

@@ -130,3 +130,35 @@ def test_prefix_beam_full_size_vs_oracle_and_mass():
     bag = CTCPrefixLogRawNumpyDecoder(LETTERS, 64)(small)
     want = prefix_beam(small, 64)
     np.testing.assert_allclose(sorted(h.vis_sc for h in bag), sorted(s for _, s in want), rtol=1e-9)
+
+
+@pytest.mark.parametrize('kind', ['transformer', 'lstm'])
+def test_recognise_and_beam_decode_on_device_matches_reference_chain(tmp_path, kind):
+    """BASELINE config 3 chain (Transformer-encoder variant + CTC prefix beam, k = 16), device-resident:
+    B200EngineLineOCR.decode_lines against the reference chain restated by the oracles -- process_lines (sparse
+    logits) -> get_full_logprobs -> [logit_coords] slice -> CTCPrefixLogRawNumpyDecoder(k) (page_parser.py:108-142,
+    418-430).  Bar: same best hypothesis, vis_sc within rtol 1e-4."""
+    import torch
+    from oracle.forward_oracle import OracleEngine, full_logprobs
+    from pero_ocr_b200.decoders import BLANK_SYMBOL, CTCPrefixLogRawNumpyDecoder
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    from tests.util import make_case_net, write_engine_json
+    spec = cases.ENGINE_CASES[kind]
+    net = make_case_net(kind)
+    eng = B200EngineLineOCR(write_engine_json(tmp_path, kind), torch.device('cuda', 0), batch_size=4, module=net)
+    letters = eng.characters + [BLANK_SYMBOL]
+    lines = cases.engine_lines(kind)
+    bags = eng.decode_lines([l.copy() for l in lines], CTCPrefixLogRawNumpyDecoder(letters, 16))
+    ref = OracleEngine(dict(net.state_dict()), cases.json_characters(spec['classes'] - 2), kind=kind)
+    ref.model = lambda x: net(x)
+    ref.batch_size = 4
+    ref.max_input_horizontal_pixels = 480 * 4
+    with torch.no_grad():
+        _, sparse_logits, coords = ref.process_lines([l.copy() for l in lines], sparse_logits=True)
+    for i in range(len(lines)):
+        lp = full_logprobs(sparse_logits[i])[coords[i][0]:coords[i][1]]
+        want = prefix_beam(lp.astype(np.float64), 16)
+        best = max(want, key=lambda h: h[1])
+        got = max(bags[i], key=lambda h: h.vis_sc)
+        assert got.transcript == ''.join(letters[j] for j in best[0]), i
+        assert abs(got.vis_sc - best[1]) <= 1e-4 * max(1.0, abs(best[1])), i
