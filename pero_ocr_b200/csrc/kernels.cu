@@ -453,6 +453,116 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
     }
 }
 
+// Tiled self-attention for 64-wide heads: one CTA per (line, head, 64-query tile), 16 x 16 threads each owning a
+// 4 x 4 block; K / V stream through shared memory in 64-key tiles with the running-maximum ("online") softmax, so the
+// line length is unbounded and every value read from shared memory feeds 4 (S = q k^T) or 16 (O += P v) FMAs.  Same
+// fp32 arithmetic as attention_kernel up to the order of the softmax sums (the row-per-warp kernel above spent
+// 12.5 ms per encoder layer at config 3, this one is bound by the FMA pipe).
+constexpr int FA_T = 64;          // queries per CTA = keys per tile = head width
+constexpr int FA_LD = FA_T + 4;   // padded row (keeps float4 alignment, spreads banks)
+
+__global__ void __launch_bounds__(256) attention_tiled_kernel(const float* __restrict__ qkv, int n, int T, int D,
+                                                              int heads, __half* __restrict__ out, int fmt) {
+    const int planes = act_planes(fmt);
+    extern __shared__ __align__(16) float s_fa[];
+    float (*sQt)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa);                         // [d][query]  (scaled)
+    float (*sKt)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + FA_T * FA_LD);          // [d][key]
+    float (*sV)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + 2 * FA_T * FA_LD);       // [key][d]
+    float (*sP)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + 3 * FA_T * FA_LD);       // [query][key]
+    const int line = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int q0 = blockIdx.y * FA_T;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* base = qkv + static_cast<size_t>(line) * T * 3 * D + head * FA_T;
+    const float scale = rsqrtf(static_cast<float>(FA_T));
+    for (int i = threadIdx.x; i < FA_T * FA_T; i += 256) {
+        const int r = i >> 6, d = i & 63;
+        sQt[d][r] = q0 + r < T ? base[static_cast<size_t>(q0 + r) * 3 * D + d] * scale : 0.f;
+    }
+    float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m_run[i] = -INFINITY;
+        l_run[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    }
+    for (int k0 = 0; k0 < T; k0 += FA_T) {
+        __syncthreads();                              // previous tile fully consumed (and sQt written)
+        for (int i = threadIdx.x; i < FA_T * FA_T; i += 256) {
+            const int r = i >> 6, d = i & 63;
+            const bool ok = k0 + r < T;
+            const float* row = base + static_cast<size_t>(k0 + r) * 3 * D;
+            sKt[d][r] = ok ? row[D + d] : 0.f;
+            sV[r][d] = ok ? row[2 * D + d] : 0.f;
+        }
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < FA_T; ++d) {
+            const float4 a = *reinterpret_cast<const float4*>(&sQt[d][4 * ty]);
+            const float4 b = *reinterpret_cast<const float4*>(&sKt[d][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+        }
+        // running softmax per query row (the 16 threads of a row are 16 consecutive lanes)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + 4 * tx + j >= T) s[i][j] = -INFINITY;
+                mx = fmaxf(mx, s[i][j]);
+            }
+#pragma unroll
+            for (int w = 1; w < 16; w <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, w));
+            const float m_new = fmaxf(m_run[i], mx);
+            const float corr = expf(m_run[i] - m_new);       // 0 on the first tile (m_run = -inf)
+            float ps = 0.f;
+            float pv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                pv[j] = expf(s[i][j] - m_new);
+                ps += pv[j];
+            }
+#pragma unroll
+            for (int w = 1; w < 16; w <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, w);
+            l_run[i] = l_run[i] * corr + ps;
+            m_run[i] = m_new;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+            *reinterpret_cast<float4*>(&sP[4 * ty + i][4 * tx]) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < FA_T; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(&sV[k][4 * tx]);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float p = sP[4 * ty + i][k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[i][j] = fmaf(p, vv[j], o[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int tq = q0 + 4 * ty + i;
+        if (tq >= T) continue;
+        const float inv = 1.f / l_run[i];
+        const size_t row = static_cast<size_t>(line) * T + tq;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) act_store(out + row * planes * D, D, head * FA_T + 4 * tx + j, o[i][j] * inv, fmt);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
@@ -533,6 +643,17 @@ cudaError_t launch_h2f(const __half* in, int rows, int d, int fmt, float* out, c
 cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int fmt,
                              cudaStream_t stream) {
     const int dh = D / heads;
+    if (dh == FA_T && heads * dh == D) {
+        const size_t smem = 4 * static_cast<size_t>(FA_T) * FA_LD * sizeof(float);
+        static bool fa_attr = false;
+        if (!fa_attr) {
+            cudaError_t e = cudaFuncSetAttribute(attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e != cudaSuccess) return e;
+            fa_attr = true;
+        }
+        attention_tiled_kernel<<<dim3(n * heads, (T + FA_T - 1) / FA_T), 256, smem, stream>>>(qkv, n, T, D, heads, out, fmt);
+        return cudaGetLastError();
+    }
     const int warps = 8;
     const size_t smem_kv = (2 * static_cast<size_t>(T) * (dh + 1) + static_cast<size_t>(warps) * T) * sizeof(float);
     const size_t smem_p = static_cast<size_t>(warps) * T * sizeof(float);

@@ -154,10 +154,42 @@ def bench_align(peak):
             'parity_spot_check_vs_oracle': bool(ok)}
 
 
+def bench_config3(peak):
+    """BASELINE config 3: Transformer-encoder variant + CTC prefix beam (k = 16), batch = 256 synthetic 40x1280 crops,
+    through engine.decode_lines (host crops in, BagOfHypotheses out; logits never leave the GPU)."""
+    import tempfile
+    from pero_ocr_b200 import synthetic
+    from pero_ocr_b200.decoders import BLANK_SYMBOL, CTCPrefixLogRawNumpyDecoder
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    net = synthetic.make_net('transformer', 120, seed=0, out_gain=2.5, layers=2)
+    tmp = tempfile.mkdtemp()
+    js = os.path.join(tmp, 'ocr.json')
+    with open(js, 'w', encoding='utf8') as f:
+        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'unused.pt',
+                   'characters': synthetic.json_characters(118), 'net_name': 'B200_AUX'}, f)
+    eng = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=8, module=net)
+    eng.max_input_horizontal_pixels = 256 * 1280
+    dec = CTCPrefixLogRawNumpyDecoder(eng.characters + [BLANK_SYMBOL], 16)
+    lines = list(synthetic.bench_crops(512, 1280, seed=0))
+    eng.decode_lines(lines[:256], dec)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    bags = eng.decode_lines(lines, dec)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.process_lines(lines, no_logits=True)
+    dt_fwd = time.perf_counter() - t0
+    return {'op': 'config 3: Transformer-encoder variant (2 layers) + CTC prefix beam k=16, decode_lines',
+            'workload': '512 lines of 40x1280 in batches of 256', 'lines_per_s': len(lines) / dt,
+            'ms_per_256_lines': 1e3 * dt / 2, 'forward_only_lines_per_s (process_lines, greedy)': len(lines) / dt_fwd,
+            'hypotheses_per_line': float(np.mean([len(b) for b in bags]))}
+
+
 def main():
     assert torch.cuda.is_available()
     peak = hbm_peak()
-    for fn in (bench_cropper, bench_sparsify, bench_align):
+    for fn in (bench_cropper, bench_sparsify, bench_align, bench_config3):
         print(json.dumps(fn(peak)), flush=True)
 
 
