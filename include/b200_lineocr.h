@@ -180,6 +180,28 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
                         const int64_t* coord_off, const int32_t* widths, int32_t n, int32_t line_h, uint8_t* out,
                         int32_t out_w, int32_t pad, void* cuda_stream);
 
+/* One text line for b200ocr_remap_poly_lines: what the host keeps of EngineLineCropper.get_crop_inputs
+ * (crop_engine.py:54-73) for the `poly` > 0 configurations -- the fitted baseline polynomial in the rotated frame and
+ * the arc-length resampling constants; the device evaluates the rest (:74-99). */
+typedef struct b200ocr_poly_line {
+    double coef[4];   /* np.polyfit coefficients, highest power first; `ncoef` of them are used */
+    double x_first;   /* xs[0]  = left end of the rotated baseline */
+    double x_last;    /* xs[-1] = last sample of np.arange(left, right) */
+    double total;     /* arc length of the sampled baseline (mapping_x_to_line_pos[-1]) */
+    double step;      /* total / (n_out - 1): np.linspace's step (unused when n_out == 1) */
+    double rot[4];    /* rotation back to page coordinates, row-major r00 r01 r10 r11 */
+    int32_t ncoef;    /* 0 = geometry failed: the reference's all-zero crop (crop_engine.py:16-22) */
+    int32_t n_out;    /* crop width in pixels */
+} b200ocr_poly_line_t;
+
+/* b200ocr_remap_lines with the sampling maps computed on the device from per-line parameters instead of uploaded:
+ *   lines    device b200ocr_poly_line_t [n]
+ *   offsets  device f64 [n][line_h]: np.linspace(-heights[0]*scale, heights[1]*scale, line_h) (crop_engine.py:91)
+ * Output bytes are those of b200ocr_remap_lines on the reference's own float32 maps. */
+int b200ocr_remap_poly_lines(const uint8_t* image, int32_t img_h, int32_t img_w, const b200ocr_poly_line_t* lines,
+                             const double* offsets, int32_t n, int32_t line_h, uint8_t* out, int32_t out_w,
+                             int32_t pad, void* cuda_stream);
+
 /* Replaces the per-line logit sparsification of BaseEngineLineOCR.process_lines
  * (pero_ocr/ocr_engine/line_ocr_engine.py:168-172: softmax, zero raw logits with p < 1e-4, scipy CSC) together with
  * the optional tight crop of the frame range (:152-156), on the device, so that only the surviving entries cross PCIe.

@@ -34,6 +34,12 @@ class Layer(C.Structure):
     ]
 
 
+class PolyLine(C.Structure):
+    """b200ocr_poly_line_t (include/b200_lineocr.h)."""
+    _fields_ = [('coef', C.c_double * 4), ('x_first', C.c_double), ('x_last', C.c_double), ('total', C.c_double),
+                ('step', C.c_double), ('rot', C.c_double * 4), ('ncoef', C.c_int32), ('n_out', C.c_int32)]
+
+
 class NetDesc(C.Structure):
     _fields_ = [('n_layers', C.c_int32), ('layers', C.POINTER(Layer)), ('precision', C.c_int32),
                 ('line_height', C.c_int32), ('device', C.c_int32)]
@@ -60,6 +66,8 @@ EXPORTS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'b200ocr_remap_lines': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    'b200ocr_remap_poly_lines': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'b200ocr_sparsify_logits': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p]),

@@ -85,6 +85,27 @@ def remap_into(page, maps, out, pad):
     return nbytes
 
 
+def remap_poly_into(page, params, offsets, out, pad):
+    """Like remap_into, with the sampling maps evaluated on the device: `params` is a list of _lib.PolyLine,
+    `offsets` a float64 array [n, line_h] (B200LineCropper.poly_params).  Returns the bytes uploaded."""
+    torch = page.torch
+    lib = _lib.load_library()
+    n, line_h, out_w, ch = out.shape
+    assert ch == 3 and out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and n == len(params)
+    if n == 0:
+        return 0
+    arr = (_lib.PolyLine * n)(*params)
+    raw = np.frombuffer(arr, dtype=np.uint8).copy()
+    d_par = torch.from_numpy(raw).to(page.device)
+    d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.float64)).to(page.device)
+    stream = torch.cuda.current_stream(page.device).cuda_stream
+    _lib.check(lib.b200ocr_remap_poly_lines(page.image.data_ptr(), page.shape[0], page.shape[1], d_par.data_ptr(),
+                                            d_off.data_ptr(), n, line_h, out.data_ptr(), out_w, pad,
+                                            C.c_void_p(stream)))
+    page._keep = (d_par, d_off)            # alive until the kernel has run (stream-ordered free on the next call)
+    return raw.nbytes + d_off.numel() * 8
+
+
 class B200LineCropper:
     """Drop-in for ``EngineLineCropper(correct_slant, line_height, poly, scale, blend_border)``.
 
@@ -144,6 +165,44 @@ class B200LineCropper:
         map_y = ny.reshape(1, -1) * offsets + out_y.reshape(1, -1)
         return np.dot(np.stack((map_x, map_y), axis=2), rot).astype(np.float32)
 
+    def poly_params(self, baseline, line_heights, target_height=None):
+        """The host half of get_crop_inputs for `poly` > 0 (crop_engine.py:54-73): rotated baseline, polynomial fit,
+        arc length, crop width.  -> (_lib.PolyLine, float64 offsets [target_height]); the device evaluates the rest
+        (b200ocr_remap_poly_lines).  A geometry failure yields the reference's fallback, a 32 px all-zero crop."""
+        if not self.poly:
+            raise ValueError('poly_params needs a polynomial baseline fit (poly > 0); use get_crop_inputs otherwise')
+        target_height = target_height or self.line_height
+        line = _lib.PolyLine()
+        try:
+            above, below = line_heights[0] * self.scale, line_heights[1] * self.scale
+            pts = np.asarray(baseline).copy().astype(int)
+            angle = math.atan2(pts[-1, 1] - pts[0, 1], pts[-1, 0] - pts[0, 0])
+            rot = np.array([[np.cos(angle), np.sin(angle)], [-np.sin(angle), np.cos(angle)]])
+            pts = np.dot(pts, np.linalg.inv(rot))
+            degree = self.poly if pts.shape[0] > 2 else 1
+            coef = np.polyfit(pts[:, 0], pts[:, 1], degree)
+            xs = np.arange(pts[:, 0].min(), pts[:, 0].max())
+            ys = np.poly1d(coef)(xs)
+            seg = ((xs[:-1] - xs[1:]) ** 2 + (ys[:-1] - ys[1:]) ** 2) ** 0.5
+            total = np.concatenate([np.zeros(1), np.cumsum(seg)])[-1]
+            n_out = int(total * (target_height / (above + below)))
+            if n_out < 1 or len(coef) > 4 or not np.isfinite(total):
+                raise ValueError('empty crop')
+            offsets = np.linspace(-above, below, target_height)
+            for i, v in enumerate(coef):
+                line.coef[i] = float(v)
+            line.ncoef, line.n_out = len(coef), n_out
+            line.x_first, line.x_last, line.total = float(xs[0]), float(xs[-1]), float(total)
+            line.step = float(total / (n_out - 1)) if n_out > 1 else 0.0
+            line.rot[0], line.rot[1], line.rot[2], line.rot[3] = (float(rot[0, 0]), float(rot[0, 1]), float(rot[1, 0]),
+                                                                  float(rot[1, 1]))
+            return line, offsets
+        except Exception:
+            print('ERROR: line crop failed.', line_heights, baseline)
+            line = _lib.PolyLine()
+            line.ncoef, line.n_out = 0, 32
+            return line, np.zeros(target_height)
+
     @staticmethod
     def _reverse_line_mapping(forward_mapping, sample_positions, sampled_values):
         """crop_engine.py:101-110, quirk preserved: the reference's search loop advances only while the cumulative
@@ -174,6 +233,17 @@ class B200LineCropper:
             self._page = DevicePage(img, self.device)
             self._page_key = key
         return self._page
+
+    def crop_page_poly(self, img, lines):
+        """crop_page with the maps evaluated on the device (poly > 0 only): one launch, ~200 bytes uploaded per line."""
+        page = img if isinstance(img, DevicePage) else self.page(img)
+        params, offs = zip(*[self.poly_params(b, h) for b, h in lines]) if lines else ((), ())
+        torch = page.torch
+        width = max([p.n_out for p in params] + [1])
+        out = torch.empty((len(params), self.line_height, width, 3), dtype=torch.uint8, device=page.device)
+        remap_poly_into(page, list(params), np.stack(offs) if offs else np.zeros((0, self.line_height)), out, 0)
+        host = out.cpu().numpy()
+        return [host[i, :, :p.n_out].copy() for i, p in enumerate(params)]
 
     def crop_page(self, img, lines):
         """`lines`: iterable of (baseline, heights).  -> list of uint8 [line_height, w, 3] crops (the reference's

@@ -872,6 +872,18 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
     return B200OCR_OK;
 }
 
+int b200ocr_remap_poly_lines(const uint8_t* image, int32_t img_h, int32_t img_w, const b200ocr_poly_line_t* lines,
+                             const double* offsets, int32_t n, int32_t line_h, uint8_t* out, int32_t out_w,
+                             int32_t pad, void* cuda_stream) {
+    if (!image || img_h <= 0 || img_w <= 0 || img_h > 32767 || img_w > 32767 || n < 0 || line_h <= 0 || !out ||
+        out_w <= 0 || pad < 0 || (n > 0 && (!lines || !offsets)))
+        return fail(nullptr, B200OCR_E_INVALID, "bad remap_poly_lines arguments");
+    if (n == 0) return B200OCR_OK;
+    CU_TRY(nullptr, launch_remap_poly_lines(image, img_h, img_w, lines, offsets, n, line_h, out, out_w, pad,
+                                            static_cast<cudaStream_t>(cuda_stream)));
+    return B200OCR_OK;
+}
+
 int b200ocr_sparsify_logits(const float* logits, int32_t n, int32_t t, int32_t c, const int32_t* t_lo,
                             const int32_t* t_hi, int32_t* indptr, int32_t* nnz, int64_t* base, int32_t* indices,
                             float* data, int64_t capacity, void* cuda_stream) {

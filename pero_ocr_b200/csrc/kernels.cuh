@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "actfmt.cuh"   // `fmt` arguments below are ActFormat values
+#include "../../include/b200_lineocr.h"   // b200ocr_poly_line_t
 
 // u8 NHWC [n][h][w][3] -> x/255 -> 3x3 conv (pad 1) + bias + act -> fp16 NHWC [n][h][w][planes*cout]
 // (replaces the `/255` + permute of run_ocr, pytorch_ocr_engine.py:61-62, and the first conv of the blob).
@@ -41,6 +42,10 @@ cudaError_t launch_char_conf(const float* logp, int n, int t_max, int C, const i
 cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
                                const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,
                                cudaStream_t stream);
+
+cudaError_t launch_remap_poly_lines(const uint8_t* img, int img_h, int img_w, const b200ocr_poly_line_t* lines,
+                                    const double* offsets, int n, int line_h, uint8_t* out, int out_w, int pad,
+                                    cudaStream_t stream);
 
 // Logit sparsification (sparsify.cu): softmax threshold 1e-4 + CSC of every line (line_ocr_engine.py:168-172).
 cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int32_t* t_lo, const int32_t* t_hi,

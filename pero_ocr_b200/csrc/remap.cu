@@ -26,23 +26,10 @@ __device__ __forceinline__ int cv_round_x32(float v) {
     return __float2int_rn(s);
 }
 
-__global__ void __launch_bounds__(256) remap_lines_kernel(const uint8_t* __restrict__ img, int img_h, int img_w,
-                                                          const float* __restrict__ coords,
-                                                          const int64_t* __restrict__ coord_off,
-                                                          const int32_t* __restrict__ widths, int line_h,
-                                                          uint8_t* __restrict__ out, int out_w, int pad) {
-    const int line = blockIdx.z, y = blockIdx.y;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= out_w) return;
-    uint8_t* dst = out + ((static_cast<size_t>(line) * line_h + y) * out_w + x) * 3;
-    const int w = widths[line];
-    const int cx = x - pad;                       // column inside the line's own crop
-    if (cx < 0 || cx >= w) {                      // padding (and lines cut at the batch width keep their left part)
-        dst[0] = dst[1] = dst[2] = 0;
-        return;
-    }
-    const float2 xy = *reinterpret_cast<const float2*>(coords + coord_off[line] + (static_cast<size_t>(y) * w + cx) * 2);
-    const int sx = cv_round_x32(xy.x), sy = cv_round_x32(xy.y);
+// One output pixel of cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) at source position (x, y).
+__device__ __forceinline__ void remap_pixel(const uint8_t* __restrict__ img, int img_h, int img_w, float x, float y,
+                                            uint8_t* __restrict__ dst) {
+    const int sx = cv_round_x32(x), sy = cv_round_x32(y);
     const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));
     const int fx = sx & 31, fy = sy & 31;
     const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
@@ -59,7 +46,80 @@ __global__ void __launch_bounds__(256) remap_lines_kernel(const uint8_t* __restr
     }
 }
 
+__global__ void __launch_bounds__(256) remap_lines_kernel(const uint8_t* __restrict__ img, int img_h, int img_w,
+                                                          const float* __restrict__ coords,
+                                                          const int64_t* __restrict__ coord_off,
+                                                          const int32_t* __restrict__ widths, int line_h,
+                                                          uint8_t* __restrict__ out, int out_w, int pad) {
+    const int line = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= out_w) return;
+    uint8_t* dst = out + ((static_cast<size_t>(line) * line_h + y) * out_w + x) * 3;
+    const int w = widths[line];
+    const int cx = x - pad;                       // column inside the line's own crop
+    if (cx < 0 || cx >= w) {                      // padding (and lines cut at the batch width keep their left part)
+        dst[0] = dst[1] = dst[2] = 0;
+        return;
+    }
+    const float2 xy = *reinterpret_cast<const float2*>(coords + coord_off[line] + (static_cast<size_t>(y) * w + cx) * 2);
+    remap_pixel(img, img_h, img_w, xy.x, xy.y, dst);
+}
+
+// The same resampling with the sampling map computed in flight from the fitted baseline polynomial (the tail of
+// get_crop_inputs, crop_engine.py:74-99, for the `poly` > 0 configurations): per output column the arc-length sample,
+// the baseline point, the unit normal from a 0.1 px forward difference, per pixel the offset along the normal and the
+// rotation back to page coordinates.  Every float64 operation is the one NumPy performs, in NumPy's order, spelled
+// with explicit rounding intrinsics so that nvcc cannot contract them -- except the final rotation, where np.dot's
+// BLAS kernel computes fma(y, r1, x * r0) (pinned by tests/test_oracle_cropper.py on this container's BLAS): the
+// float32 maps are bit-identical to the reference's, so are the crops.  25 MB of maps per page shrink to ~10 KB of
+// line parameters, and the host no longer evaluates 40 x w float64 maps in NumPy (5 of its 8 ms per line).
+__device__ __forceinline__ double poly_eval(const b200ocr_poly_line_t& L, double x) {
+    double y = 0.0;
+    for (int i = 0; i < L.ncoef; ++i) y = __dadd_rn(__dmul_rn(y, x), L.coef[i]);   // np.polyval: y = y * x + p[i]
+    return y;
+}
+
+__global__ void __launch_bounds__(256) remap_poly_lines_kernel(const uint8_t* __restrict__ img, int img_h, int img_w,
+                                                               const b200ocr_poly_line_t* __restrict__ lines,
+                                                               const double* __restrict__ offsets, int line_h,
+                                                               uint8_t* __restrict__ out, int out_w, int pad) {
+    const int line = blockIdx.z, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= out_w) return;
+    uint8_t* dst = out + ((static_cast<size_t>(line) * line_h + y) * out_w + x) * 3;
+    const b200ocr_poly_line_t& L = lines[line];
+    const int cx = x - pad;
+    if (cx < 0 || cx >= L.n_out || L.ncoef <= 0) {        // padding; ncoef == 0: the reference's all-zero fallback crop
+        dst[0] = dst[1] = dst[2] = 0;
+        return;
+    }
+    // np.linspace(0, total, n_out)[cx]
+    const double smp = L.n_out == 1 ? 0.0 : (cx == L.n_out - 1 ? L.total : __dmul_rn(static_cast<double>(cx), L.step));
+    // reverse_line_mapping (its search loop never advances): blend between xs[-1] and xs[0]
+    const double da = __ddiv_rn(__dsub_rn(smp, L.total), __dsub_rn(0.0, L.total));
+    const double ox = __dadd_rn(__dmul_rn(__dsub_rn(1.0, da), L.x_last), __dmul_rn(da, L.x_first));
+    const double oy = poly_eval(L, ox);
+    const double dy = __dsub_rn(oy, poly_eval(L, __dadd_rn(ox, 0.1)));
+    const double len = __dsqrt_rn(__dadd_rn(__dmul_rn(0.1, 0.1), __dmul_rn(dy, dy)));
+    const double nx = __ddiv_rn(-dy, len), ny = __ddiv_rn(0.1, len);
+    const double off = offsets[static_cast<size_t>(line) * line_h + y];
+    const double mx = __dadd_rn(__dmul_rn(nx, off), ox), my = __dadd_rn(__dmul_rn(ny, off), oy);
+    const float fx = __double2float_rn(__fma_rn(my, L.rot[2], __dmul_rn(mx, L.rot[0])));
+    const float fy = __double2float_rn(__fma_rn(my, L.rot[3], __dmul_rn(mx, L.rot[1])));
+    remap_pixel(img, img_h, img_w, fx, fy, dst);
+}
+
 }  // namespace
+
+cudaError_t launch_remap_poly_lines(const uint8_t* img, int img_h, int img_w, const b200ocr_poly_line_t* lines,
+                                    const double* offsets, int n, int line_h, uint8_t* out, int out_w, int pad,
+                                    cudaStream_t stream) {
+    if (n <= 0 || out_w <= 0) return cudaSuccess;
+    if (n > 65535 || line_h > 65535) return cudaErrorInvalidValue;
+    dim3 grid((out_w + 255) / 256, line_h, n);
+    remap_poly_lines_kernel<<<grid, 256, 0, stream>>>(img, img_h, img_w, lines, offsets, line_h, out, out_w, pad);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
                                const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,

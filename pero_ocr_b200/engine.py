@@ -380,6 +380,27 @@ class B200EngineLineOCR:
         return self._run_batches([l.shape[1] for l in lines], stager, sparse_logits, tight_crop_logits, no_logits,
                                  return_ids)
 
+    def process_baselines(self, page, lines, cropper, sparse_logits=True, tight_crop_logits=False, no_logits=False,
+                          return_ids=False):
+        """The page path end to end on the device: `lines` = [(baseline, heights), ...] of one page (`page` a
+        cropper.DevicePage), `cropper` a B200LineCropper with a polynomial baseline fit (poly > 0).  Only ~200 bytes
+        of line parameters per line are uploaded; the sampling maps, the bilinear resampling, the padding of the
+        batch and the recogniser all run on the GPU.  Results are those of LineCropper.process_page followed by
+        process_lines (page_parser.py:384-393, 418-430) on the reference's crops."""
+        from .cropper import remap_poly_into
+        if cropper.line_height != self.line_px_height:
+            raise ValueError('cropper and recogniser disagree on the line height')
+        prepared = [cropper.poly_params(b, h) for b, h in lines]
+
+        def stager(chunk, width):
+            def device_fill(dev_batch):
+                return remap_poly_into(page, [prepared[i][0] for i in chunk], np.stack([prepared[i][1] for i in chunk]),
+                                       dev_batch, self.line_padding_px)
+            return {'device_fill': device_fill}
+
+        return self._run_batches([p[0].n_out for p in prepared], stager, sparse_logits, tight_crop_logits, no_logits,
+                                 return_ids)
+
     def decode_lines(self, lines, decoder):
         """Recognise and beam-decode in one pass on the device: the work of PageOCR.process_page followed by
         PageDecoder.process_page with a CTC prefix decoder without LM (page_parser.py:418-430 and 108-142) --

@@ -92,9 +92,20 @@ def bench_cropper(peak):
         cpu_ms, cpu_kind = 1e3 * (time.perf_counter() - t0) / 4, 'NumPy oracle, 1 core'
     got = out.cpu().numpy()
     ok = bool(np.array_equal(got[7, :, 32:32 + maps[7].shape[1]], remap_bilinear_u8(img, maps[7])))
+    # the same page with the maps evaluated on the device (b200ocr_remap_poly_lines): host fits the polynomial only
+    from pero_ocr_b200.cropper import remap_poly_into
+    t0 = time.perf_counter()
+    prepared = [cropper.poly_params(b, h) for b, h in lines]
+    params_ms = 1e3 * (time.perf_counter() - t0)
+    par, offs_ = [p for p, _ in prepared], np.stack([o for _, o in prepared])
+    out2 = torch.empty_like(out)
+    poly_ms = timed(lambda: remap_poly_into(page, par, offs_, out2, 32), reps=10)
+    same = bool(torch.equal(out, out2))
     return {'op': 'line cropper (b200ocr_remap_lines)', 'workload': '60 lines x 40 x ~1300 px from one 3000x4000 page',
             'gpu_ms_per_page': ms, 'gpu_us_per_line': 1e3 * ms / len(maps),
             'gpu_ms_per_page_with_map_upload': e2e_ms, 'host_geometry_ms_per_page': geom_ms,
+            'device_geometry': {'gpu_ms_per_page_incl_param_upload': poly_ms, 'host_polyfit_ms_per_page': params_ms,
+                                'bytes_uploaded_per_line': 112 + 40 * 8, 'identical_to_map_path': same},
             'cpu_ms_per_line': cpu_ms, 'cpu_kind': cpu_kind,
             'roofline': {'bound': 'hbm', 'achieved': algo_bytes / (ms * 1e-3) / 1e9, 'peak': peak[0], 'unit': 'GB/s',
                          'frac': algo_bytes / (ms * 1e-3) / 1e9 / peak[0], 'peak_source': peak[1],

@@ -68,3 +68,37 @@ def test_process_line_maps_equals_process_lines_on_reference_crops(tmp_path, gol
     assert tr_a == tr_b and co_a == co_b
     for a, b in zip(lg_a, lg_b):
         assert np.array_equal(a, b)                    # identical input bytes -> identical logits
+
+
+def test_device_geometry_crops_match_reference_golden(golden_dir):
+    """b200ocr_remap_poly_lines: the sampling maps are evaluated on the device from the fitted polynomial (float64, in
+    NumPy's order of operations) -- the crops must still be the reference's, byte for byte."""
+    from pero_ocr_b200.cropper import B200LineCropper
+    gold = load_golden(golden_dir, 'cropper.npz')
+    img = page_image()
+    seen = 0
+    for name, kw, baseline, heights in CROP_CASES:
+        if not kw['poly']:
+            continue
+        crop = B200LineCropper(**kw).crop_page_poly(img, [(baseline, heights)])[0]
+        want = gold[f'crop_{name}']
+        assert crop.shape == want.shape and np.array_equal(crop, want), name
+        seen += 1
+    assert seen >= 5
+
+
+def test_process_baselines_equals_process_lines_on_reference_crops(tmp_path, golden_dir):
+    from pero_ocr_b200.cropper import B200LineCropper, DevicePage
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    gold = load_golden(golden_dir, 'cropper.npz')
+    js = write_engine_json(tmp_path, 'lstm')
+    eng = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=4, module=make_case_net('lstm'))
+    use = [c for c in CROP_CASES if c[1] == dict(line_height=40, poly=2, scale=1)]
+    assert len(use) >= 3                      # includes the degenerate baseline -> the reference's zero crop
+    cropper = B200LineCropper(line_height=40, poly=2, scale=1)
+    page = DevicePage(page_image())
+    tr_a, lg_a, co_a = eng.process_baselines(page, [(b, h) for _, _, b, h in use], cropper, sparse_logits=False)
+    tr_b, lg_b, co_b = eng.process_lines([gold[f'crop_{n}'] for n, *_ in use], sparse_logits=False)
+    assert tr_a == tr_b and co_a == co_b
+    for a, b in zip(lg_a, lg_b):
+        assert np.array_equal(a, b)
