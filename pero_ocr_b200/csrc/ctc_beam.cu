@@ -18,6 +18,9 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kMaxK = 64;
 constexpr int kMaxC = 1024;
+constexpr int kSelPerLane = 16;                     // candidates a lane keeps in registers for the warp-level top-k
+constexpr int kSurvMax = 512;                       // survivors of the top-k prefilter kept in shared memory
+constexpr int kSelMax = kThreads * kSelPerLane;   // 2048: beyond that the block-wide rounds are used
 #define kNegInf (-CUDART_INF)
 
 __device__ __forceinline__ double lae(double a, double b) {  // logaddexp
@@ -61,6 +64,10 @@ prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32
     __shared__ double red_v[kThreads / 32];
     __shared__ int red_i[kThreads / 32];
     __shared__ int pick_r[kMaxK], pick_c[kMaxK];
+    __shared__ double s_lmax[kThreads], surv_v[kSurvMax], s_thr;
+    __shared__ int surv_i[kSurvMax], s_m;
+    __shared__ double cand_v[(kThreads / 32) * kMaxK];
+    __shared__ int cand_i[(kThreads / 32) * kMaxK];
     __shared__ int s_S, s_flag, s_nkeep;
 
     const int line = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -196,7 +203,143 @@ prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32
         }
         __syncthreads();
         const int n_keep = s_nkeep;
-        // ---- top-k: n_keep rounds of block arg-max (value desc, flat index asc)
+        // ---- top-k (value desc, flat index asc)
+        const int M = nb * cols;
+        if (M <= kSelMax) {
+            // two-level selection without block barriers in the pick loop: every lane keeps its <= 16 candidates
+            // (flat index tid + 128 e) in registers, each warp extracts the n_keep best of its 32 x 16 by n_keep
+            // shuffle arg-max rounds, then warp 0 merges the 4 x n_keep survivors the same way.  (n_keep block-wide
+            // arg-max rounds with two barriers each were half of the per-frame time at k = 16.)
+            double lv[kSelPerLane];
+#pragma unroll
+            for (int e = 0; e < kSelPerLane; ++e) {
+                const int i = tid + e * kThreads;
+                double v = kNegInf;
+                if (i < M) {
+                    const int p = i / cols, j = i - p * cols;
+                    v = score[p * cols_max + j];
+                    if (v != v) v = kNegInf;
+                }
+                lv[e] = v;
+            }
+            // prefilter: the n_keep-th largest of the 128 per-thread maxima is a lower bound of the n_keep-th best
+            // candidate, so only candidates at or above it can be picked (typically 16-40 of ~1500); they are
+            // compacted into shared memory and ranked exactly (value desc, flat index asc)
+            double lmax = kNegInf;
+#pragma unroll
+            for (int e = 0; e < kSelPerLane; ++e) lmax = fmax(lmax, lv[e]);
+            s_lmax[tid] = lmax;
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            {
+                int rank = 0;
+                for (int j2 = 0; j2 < kThreads; ++j2) {
+                    const double o = s_lmax[j2];
+                    rank += (o > lmax || (o == lmax && j2 < tid)) ? 1 : 0;
+                }
+                if (rank == n_keep - 1) s_thr = lmax;
+            }
+            __syncthreads();
+            const double thr = s_thr;
+#pragma unroll
+            for (int e = 0; e < kSelPerLane; ++e)
+                if (lv[e] != kNegInf && lv[e] >= thr) {
+                    const int at = atomicAdd(&s_m, 1);
+                    if (at < kSurvMax) {
+                        surv_v[at] = lv[e];
+                        surv_i[at] = tid + e * kThreads;
+                    }
+                }
+            __syncthreads();
+            const int m = s_m;
+            if (m <= kSurvMax) {
+                for (int q = tid; q < m; q += kThreads) {
+                    const double v = surv_v[q];
+                    const int i = surv_i[q];
+                    int rank = 0;
+                    for (int q2 = 0; q2 < m; ++q2) {
+                        const double v2 = surv_v[q2];
+                        rank += (v2 > v || (v2 == v && surv_i[q2] < i)) ? 1 : 0;
+                    }
+                    if (rank < n_keep) {
+                        const int p = i / cols;
+                        pick_r[rank] = p;
+                        pick_c[rank] = i - p * cols;
+                    }
+                }
+                __syncthreads();
+            } else {
+            // (ties at the threshold overflowed the survivor list: exact two-level warp selection)
+            unsigned taken = 0;
+            for (int r = 0; r < n_keep; ++r) {
+                double bv = kNegInf;
+                int be = -1;
+#pragma unroll
+                for (int e = 0; e < kSelPerLane; ++e)
+                    if (!((taken >> e) & 1u) && lv[e] > bv) {
+                        bv = lv[e];
+                        be = e;
+                    }
+                const int mine = be >= 0 ? tid + be * kThreads : 0x7fffffff;
+                int bi = mine;
+                for (int o = 16; o; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) {
+                        bv = ov;
+                        bi = oi;
+                    }
+                }
+                if (be >= 0 && bi == mine) taken |= 1u << be;
+                if (lane == 0) {
+                    cand_v[warp * kMaxK + r] = bv;
+                    cand_i[warp * kMaxK + r] = bi;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                constexpr int kPer = (kThreads / 32) * kMaxK / 32;      // merged candidates per lane
+                double mv[kPer];
+                int mi[kPer];
+#pragma unroll
+                for (int e = 0; e < kPer; ++e) {
+                    const int slot = lane + e * 32;
+                    const int w2 = slot / kMaxK, r2 = slot - w2 * kMaxK;
+                    const bool ok = r2 < n_keep;
+                    mv[e] = ok ? cand_v[slot] : kNegInf;
+                    mi[e] = ok ? cand_i[slot] : 0x7fffffff;
+                }
+                unsigned tk = 0;
+                for (int r = 0; r < n_keep; ++r) {
+                    double bv = kNegInf;
+                    int bi = 0x7fffffff, be = -1;
+#pragma unroll
+                    for (int e = 0; e < kPer; ++e)
+                        if (!((tk >> e) & 1u) && (mv[e] > bv || (mv[e] == bv && mv[e] != kNegInf && mi[e] < bi))) {
+                            bv = mv[e];
+                            bi = mi[e];
+                            be = e;
+                        }
+                    const int mine = bi;
+                    for (int o = 16; o; o >>= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) {
+                            bv = ov;
+                            bi = oi;
+                        }
+                    }
+                    if (be >= 0 && bi == mine) tk |= 1u << be;
+                    if (lane == 0) {
+                        const int p = bi / cols;
+                        pick_r[r] = p;
+                        pick_c[r] = bi - p * cols;
+                    }
+                }
+            }
+            __syncthreads();
+            }
+        } else
         for (int round = 0; round < n_keep; ++round) {
             double bv = kNegInf;
             int bi = 0x7fffffff;
@@ -303,9 +446,11 @@ cudaError_t launch_ctc_prefix_beam(const double* logprobs, int n, int t, int c, 
     int* ws_parent = static_cast<int*>(workspace);
     int* ws_char = ws_parent + static_cast<size_t>(n) * nodes;
     const size_t dyn = dyn_bytes(c, k);
-    if (dyn > 40 * 1024) {
+    static bool attr_done = false;   // static + dynamic shared memory exceeds the 48 KB default already at k = 16, c = 120
+    if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
         if (e != cudaSuccess) return e;
+        attr_done = true;
     }
     prefix_beam_kernel<<<n, kThreads, dyn, stream>>>(logprobs, t, c, k, out_labels, out_lengths, out_scores, status,
                                                      ws_parent, ws_char, nodes, t_lo, t_hi);
