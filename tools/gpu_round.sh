@@ -7,6 +7,7 @@ prec=${2:-fp16f8}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/${tag}_smi.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> $out/${tag}_smoke.log
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
 python bench.py --precision $prec --profile-out $out/${tag}_per_layer_${prec}.json > $out/${tag}_bench_${prec}.json 2> $out/${tag}_bench_${prec}.err
 python bench.py --precision fp16x3 --no-cpu-baseline --profile-out $out/${tag}_per_layer_fp16x3.json > $out/${tag}_bench_fp16x3.json 2> $out/${tag}_bench_fp16x3.err
@@ -19,4 +20,5 @@ nl=16
 ncu --set full --clock-control none --import-source on -k 'regex:igemm|lstm_tc|conv_first|ctc_collapse' -s ${nl} -c ${nl} -o $out/${tag}_step_${prec} -f \
     python tools/prof_step.py lstm $prec 2 > $out/${tag}_ncu_full.log 2>&1
 ncu -i $out/${tag}_step_${prec}.ncu-rep --page raw --csv > $out/${tag}_step_${prec}_raw.csv 2>/dev/null
+timeout 600 python -m tests.aux_bench > $out/${tag}_aux_bench.json 2> $out/${tag}_aux_bench.err
 echo done
