@@ -256,8 +256,24 @@ class B200EngineLineOCR:
         return res
 
     def _decode_ids(self, labels, lengths):
+        """label ids -> strings (the join of greedy_decode_ctc, pytorch_ocr_engine.py:28-34).  A 256-line batch is
+        ~50k symbols: a per-symbol Python loop costs ~10 ms per batch on the thread that also feeds the GPU, so
+        single-code-point alphabets go through one NumPy gather + UTF-32 decode per line."""
         chars = self.characters
-        return [''.join(chars[c] for c in row[:ln]) for row, ln in zip(labels, lengths)]
+        table = getattr(self, '_codepoints', None)
+        if table is None or len(table) != len(chars):
+            table = (np.array([ord(c) for c in chars], dtype=np.uint32)
+                     if all(isinstance(c, str) and len(c) == 1 for c in chars) else False)
+            self._codepoints = table
+        lens = np.asarray(lengths).tolist()
+        if table is not False:
+            codes = table[np.asarray(labels).clip(0)]                      # unused tail entries are -1
+            try:
+                return [codes[i, :ln].tobytes().decode('utf-32-le') for i, ln in enumerate(lens)]
+            except UnicodeDecodeError:                                     # lone surrogates in the alphabet
+                pass
+        get = chars.__getitem__
+        return [''.join(map(get, row[:ln])) for row, ln in zip(np.asarray(labels).tolist(), lens)]
 
     def run_ocr(self, batch_data, no_logits=False):
         """np.uint8 [N,H,W,3] -> (list[str], np.float32 [N,T,C])   (pytorch_ocr_engine.py:59-74)."""
