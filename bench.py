@@ -289,6 +289,7 @@ def main():
     e2e_lines = [host_lines[i % (BATCH * n_rot)] for i in range(BATCH * args.steps)]
     engine.process_lines(e2e_lines[:BATCH * 2], no_logits=True)             # warm-up: pinned buffers, slots
     engine.h2d_bytes = engine.d2h_bytes = 0
+    engine.host_ms = {k: 0.0 for k in engine.host_ms}
     barrier()
     t0 = time.perf_counter()
     ids, _, _ = engine.process_lines(e2e_lines, no_logits=True, return_ids=True)
@@ -303,7 +304,9 @@ def main():
     e2e_value = world * len(e2e_lines) / float(t.item())
     e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': engine.h2d_bytes // args.steps,
            'd2h_bytes_per_step': engine.d2h_bytes // args.steps, 'gather_bytes_total': gathered,
-           'api': 'B200EngineLineOCR.process_lines(lines, no_logits=True)'}
+           'api': 'B200EngineLineOCR.process_lines(lines, no_logits=True)',
+           'host_ms_per_step_rank0': {k: v / args.steps for k, v in engine.host_ms.items()},
+           'host_threads': engine.host_threads}
 
     # ---- the same call with logits (what PageOCR.process_page asks for), reported on stderr only: the random-init
     # bench net keeps every class of every frame (p ~ 1/120 > 1e-4), which is the degenerate worst case of the sparse

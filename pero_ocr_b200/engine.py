@@ -11,6 +11,7 @@ PyTorch appears only as the owner of device/pinned buffers and of the CUDA strea
 import ctypes as C
 import json
 import math
+import time
 from os.path import dirname, isabs, join, realpath
 
 import numpy as np
@@ -170,7 +171,12 @@ class B200EngineLineOCR:
                                     device=self.device.index or 0)
         self._slots = None
         self._copy_stream = None
-        self.host_threads = 4            # host threads that pad a batch into pinned memory (process_lines)
+        # host threads that pad a batch into pinned memory (process_lines): a few when the process has the cores for
+        # it, none when several ranks share the host (torchrun exports LOCAL_WORLD_SIZE)
+        import os
+        ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+        self.host_threads = max(1, min(4, (os.cpu_count() or 2) // (4 * ranks)))
+        self.host_ms = {'stage': 0.0, 'wait': 0.0, 'finish': 0.0}      # where process_lines spends host time
         self._executor = None
         self.want_confidence = False
         self.last_confidences = None
@@ -215,7 +221,9 @@ class B200EngineLineOCR:
             if sl['pin'] is None or sl['pin'].numel() < n_bytes:
                 sl['pin'] = torch.empty(sl['dev'].numel(), dtype=torch.uint8, pin_memory=True)
             pin = sl['pin'][:n_bytes].view(shape)
+            t0 = time.perf_counter()
             fill(pin.numpy())
+            self.host_ms['stage'] += 1e3 * (time.perf_counter() - t0)
             with torch.cuda.stream(self._copy_stream):
                 dev.copy_(pin, non_blocking=True)
                 sl['h2d'].record(self._copy_stream)
@@ -246,7 +254,9 @@ class B200EngineLineOCR:
     def _collect(self, ticket):
         k, names = ticket
         sl = self._slots[k]
+        t0 = time.perf_counter()
         sl['done'].synchronize()
+        self.host_ms['wait'] += 1e3 * (time.perf_counter() - t0)
         res = {name: sl['host'][name].numpy() for name in names}
         if sl.get('sparse') is not None:
             fetched = sl['sparse'].fetch(self._copy_stream)
@@ -354,7 +364,10 @@ class B200EngineLineOCR:
                 ticket = self._submit(bi & 1, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
                                       device_fill=kw.get('device_fill'))
                 if in_flight is not None:
-                    finish(in_flight[0], self._collect(in_flight[1]))
+                    res = self._collect(in_flight[1])
+                    t0 = time.perf_counter()
+                    finish(in_flight[0], res)
+                    self.host_ms['finish'] += 1e3 * (time.perf_counter() - t0)
                 in_flight = (chunk, ticket)
             if in_flight is not None:
                 finish(in_flight[0], self._collect(in_flight[1]))

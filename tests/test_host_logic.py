@@ -26,6 +26,7 @@ def _host_only_engine(kind):
     eng.characters = cases.json_characters(spec['classes'] - 2) + [u'​']
     eng.want_confidence = False
     eng.host_threads = 3
+    eng.host_ms = {'stage': 0.0, 'wait': 0.0, 'finish': 0.0}
     eng._executor = None
     eng.h2d_bytes = eng.d2h_bytes = 0
     eng._device_ctx = contextlib.nullcontext
