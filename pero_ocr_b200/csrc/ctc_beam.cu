@@ -176,7 +176,7 @@ prefix_beam_kernel(const double* __restrict__ lp_all, int T, int C, int K, int32
                 joinq[p] = q;
         }
         __syncthreads();
-        if (tid < nb && joinq[tid] >= 0) {
+        if (tid < nb && joinq[tid] >= 0 && rlast[tid] < S) {   // column S is the all -inf dummy: nothing to move
             const int q = joinq[tid];
             double& mine = table[tid * cols_max + S + 1];
             double& theirs = table[q * cols_max + rlast[tid]];

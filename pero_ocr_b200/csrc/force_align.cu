@@ -54,15 +54,15 @@ __global__ void __launch_bounds__(FA_THREADS) force_align_kernel(const T* __rest
     }
     if (o_chr) for (int i = threadIdx.x; i < l_max; i += FA_THREADS) o_chr[i] = -1;
     __syncthreads();
-    if (!s_bad) {
+    const bool shape_ok = s_bad == 0;
+    bool sym_bad = false;
+    if (shape_ok)
         for (int i = threadIdx.x; i < L; i += FA_THREADS) {
             const int c = lab[i];
-            if (c == blank || c < 0 || c >= C) s_bad = 2;
+            sym_bad |= (c == blank || c < 0 || c >= C);
         }
-    }
-    __syncthreads();
-    if (s_bad) {
-        if (threadIdx.x == 0) status[line] = s_bad;
+    if (__syncthreads_or(sym_bad ? 1 : 0) || !shape_ok) {
+        if (threadIdx.x == 0) status[line] = 2;
         return;
     }
     double* cur = s_cost;
