@@ -62,3 +62,37 @@ CROP_CASES = [
     ('tall_line_height48', dict(line_height=48, poly=2, scale=1), [[25, 100], [190, 103], [400, 97]], [35, 14]),
     ('degenerate_single_point', dict(line_height=40, poly=2, scale=1), [[150, 150], [150, 150]], [20, 8]),
 ]
+
+
+def poly_map_columns(line, offsets, columns):
+    """What b200ocr_remap_poly_lines evaluates per output pixel (pero_ocr_b200/csrc/remap.cu: remap_poly_lines_kernel),
+    restated operation by operation in IEEE float64 (Python floats; the fused multiply-add of the final rotation by
+    exact rational arithmetic) for the given output columns.  `line` is the _lib.PolyLine produced by
+    B200LineCropper.poly_params.  -> float32 [len(offsets), len(columns), 2]; must equal the reference's
+    get_crop_inputs map (crop_engine.py:74-99) bit for bit."""
+    import math
+    from fractions import Fraction
+
+    def fma(a, b, c):
+        return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+    def poly(x):
+        y = 0.0
+        for i in range(line.ncoef):
+            y = y * x + line.coef[i]
+        return y
+
+    out = np.zeros((len(offsets), len(columns), 2), dtype=np.float32)
+    for k, cx in enumerate(columns):
+        smp = 0.0 if line.n_out == 1 else (line.total if cx == line.n_out - 1 else cx * line.step)
+        da = (smp - line.total) / (0.0 - line.total)
+        ox = (1.0 - da) * line.x_last + da * line.x_first
+        oy = poly(ox)
+        dy = oy - poly(ox + 0.1)
+        length = math.sqrt(0.1 * 0.1 + dy * dy)
+        nx, ny = -dy / length, 0.1 / length
+        for i, off in enumerate(offsets):
+            mx, my = nx * off + ox, ny * off + oy
+            out[i, k, 0] = np.float32(fma(my, line.rot[2], mx * line.rot[0]))
+            out[i, k, 1] = np.float32(fma(my, line.rot[3], mx * line.rot[1]))
+    return out

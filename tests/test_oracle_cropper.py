@@ -60,3 +60,33 @@ def test_oracle_remap_against_cv2_on_random_maps():
     want = cv2.remap(img, coords[..., 0], coords[..., 1], interpolation=cv2.INTER_LINEAR,
                      borderMode=cv2.BORDER_CONSTANT)
     assert np.array_equal(remap_bilinear_u8(img, coords), want)
+
+
+@pytest.mark.parametrize('case', [c for c in CROP_CASES if c[1]['poly'] and c[0] != 'degenerate_single_point'],
+                         ids=lambda c: c[0])
+def test_device_geometry_formulas_reproduce_reference_maps(golden_dir, case):
+    """The per-pixel float64 arithmetic of b200ocr_remap_poly_lines (restated in oracle.crop_oracle.poly_map_columns)
+    on the parameters B200LineCropper.poly_params hands to the device reproduces the reference's float32 map bit for
+    bit -- checked on every 4th column (the columns stored in the fixture) and on the last one."""
+    from oracle.crop_oracle import poly_map_columns
+    from pero_ocr_b200.cropper import B200LineCropper
+    name, kw, baseline, heights = case
+    gold = load_golden(golden_dir, 'cropper.npz')
+    c = B200LineCropper(**kw)
+    line, offsets = c.poly_params(baseline, heights)
+    shape = list(gold[f'mapshape_{name}'])
+    assert [len(offsets), line.n_out, 2] == shape
+    cols = list(range(0, line.n_out, 4))
+    got = poly_map_columns(line, offsets, cols[::3] + [cols[-1]])
+    want = gold[f'map_{name}'][:, list(range(len(cols)))[::3] + [len(cols) - 1]]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    full = _geometry(kw, baseline, heights)
+    last = poly_map_columns(line, offsets, [line.n_out - 1])
+    assert np.array_equal(last[:, 0].view(np.uint32), full[:, -1].view(np.uint32))
+
+
+def test_poly_params_of_a_degenerate_baseline_is_the_zero_crop():
+    from pero_ocr_b200.cropper import B200LineCropper
+    name, kw, baseline, heights = [c for c in CROP_CASES if c[0] == 'degenerate_single_point'][0]
+    line, offsets = B200LineCropper(**kw).poly_params(baseline, heights)
+    assert line.ncoef == 0 and line.n_out == 32 and not offsets.any()
