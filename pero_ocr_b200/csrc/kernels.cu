@@ -453,34 +453,36 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int n, int T, in
     }
 }
 
-// Tiled self-attention for 64-wide heads: one CTA per (line, head, 64-query tile), 16 x 16 threads each owning a
-// 4 x 4 block; K / V stream through shared memory in 64-key tiles with the running-maximum ("online") softmax, so the
+// Tiled self-attention for 64-wide heads: one CTA per (line, head, 64-query tile), 8 x 16 threads each owning an
+// 8 x 4 block; K / V stream through shared memory in 64-key tiles with the running-maximum ("online") softmax, so the
 // line length is unbounded and every value read from shared memory feeds 4 (S = q k^T) or 16 (O += P v) FMAs.  Same
 // fp32 arithmetic as attention_kernel up to the order of the softmax sums (the row-per-warp kernel above spent
 // 12.5 ms per encoder layer at config 3, this one is bound by the FMA pipe).
 constexpr int FA_T = 64;          // queries per CTA = keys per tile = head width
 constexpr int FA_LD = FA_T + 4;   // padded row (keeps float4 alignment, spreads banks)
 
-__global__ void __launch_bounds__(256) attention_tiled_kernel(const float* __restrict__ qkv, int n, int T, int D,
+__global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __restrict__ qkv, int n, int T, int D,
                                                               int heads, __half* __restrict__ out, int fmt) {
+    // 128 threads = 8 (ty) x 16 (tx); a thread owns 8 queries (ty + 8 i) x 4 keys / head dims (4 tx .. 4 tx + 3):
+    // 32 FMAs per three 16-byte shared-memory reads in both products.
     const int planes = act_planes(fmt);
     extern __shared__ __align__(16) float s_fa[];
     float (*sQt)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa);                         // [d][query]  (scaled)
     float (*sKt)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + FA_T * FA_LD);          // [d][key]
     float (*sV)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + 2 * FA_T * FA_LD);       // [key][d]
-    float (*sP)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + 3 * FA_T * FA_LD);       // [query][key]
+    float (*sPt)[FA_LD] = reinterpret_cast<float (*)[FA_LD]>(s_fa + 3 * FA_T * FA_LD);      // [key][query]
     const int line = blockIdx.x / heads, head = blockIdx.x % heads;
     const int q0 = blockIdx.y * FA_T;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // ty in [0, 8): queries 8 ty .. 8 ty + 7
     const float* base = qkv + static_cast<size_t>(line) * T * 3 * D + head * FA_T;
     const float scale = rsqrtf(static_cast<float>(FA_T));
-    for (int i = threadIdx.x; i < FA_T * FA_T; i += 256) {
+    for (int i = threadIdx.x; i < FA_T * FA_T; i += 128) {
         const int r = i >> 6, d = i & 63;
         sQt[d][r] = q0 + r < T ? base[static_cast<size_t>(q0 + r) * 3 * D + d] * scale : 0.f;
     }
-    float m_run[4], l_run[4], o[4][4];
+    float m_run[8], l_run[8], o[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
         m_run[i] = -INFINITY;
         l_run[i] = 0.f;
 #pragma unroll
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(256) attention_tiled_kernel(const float* __res
     }
     for (int k0 = 0; k0 < T; k0 += FA_T) {
         __syncthreads();                              // previous tile fully consumed (and sQt written)
-        for (int i = threadIdx.x; i < FA_T * FA_T; i += 256) {
+        for (int i = threadIdx.x; i < FA_T * FA_T; i += 128) {
             const int r = i >> 6, d = i & 63;
             const bool ok = k0 + r < T;
             const float* row = base + static_cast<size_t>(k0 + r) * 3 * D;
@@ -496,24 +498,25 @@ __global__ void __launch_bounds__(256) attention_tiled_kernel(const float* __res
             sV[r][d] = ok ? row[2 * D + d] : 0.f;
         }
         __syncthreads();
-        float s[4][4];
+        float s[8][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-#pragma unroll 8
+#pragma unroll 4
         for (int d = 0; d < FA_T; ++d) {
-            const float4 a = *reinterpret_cast<const float4*>(&sQt[d][4 * ty]);
+            const float4 a0 = *reinterpret_cast<const float4*>(&sQt[d][8 * ty]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sQt[d][8 * ty + 4]);
             const float4 b = *reinterpret_cast<const float4*>(&sKt[d][4 * tx]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
         }
         // running softmax per query row (the 16 threads of a row are 16 consecutive lanes)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -525,11 +528,11 @@ __global__ void __launch_bounds__(256) attention_tiled_kernel(const float* __res
             const float m_new = fmaxf(m_run[i], mx);
             const float corr = expf(m_run[i] - m_new);       // 0 on the first tile (m_run = -inf)
             float ps = 0.f;
-            float pv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                pv[j] = expf(s[i][j] - m_new);
-                ps += pv[j];
+                const float pv = expf(s[i][j] - m_new);
+                ps += pv;
+                sPt[4 * tx + j][((8 * ty) ^ (8 * (tx & 7))) + i] = pv;   // 8-query blocks XOR-swizzled by key group
             }
 #pragma unroll
             for (int w = 1; w < 16; w <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, w);
@@ -537,24 +540,24 @@ __global__ void __launch_bounds__(256) attention_tiled_kernel(const float* __res
             m_run[i] = m_new;
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[i][j] *= corr;
-            *reinterpret_cast<float4*>(&sP[4 * ty + i][4 * tx]) = make_float4(pv[0], pv[1], pv[2], pv[3]);
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int k = 0; k < FA_T; ++k) {
             const float4 v = *reinterpret_cast<const float4*>(&sV[k][4 * tx]);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
+            const int qb = (8 * ty) ^ (8 * ((k >> 2) & 7));
+            const float4 p0 = *reinterpret_cast<const float4*>(&sPt[k][qb]);
+            const float4 p1 = *reinterpret_cast<const float4*>(&sPt[k][qb + 4]);
+            const float vv[4] = {v.x, v.y, v.z, v.w}, pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float p = sP[4 * ty + i][k];
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[i][j] = fmaf(p, vv[j], o[i][j]);
-            }
+                for (int j = 0; j < 4; ++j) o[i][j] = fmaf(pp[i], vv[j], o[i][j]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int tq = q0 + 4 * ty + i;
+    for (int i = 0; i < 8; ++i) {
+        const int tq = q0 + 8 * ty + i;
         if (tq >= T) continue;
         const float inv = 1.f / l_run[i];
         const size_t row = static_cast<size_t>(line) * T + tq;
@@ -651,7 +654,7 @@ cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, _
             if (e != cudaSuccess) return e;
             fa_attr = true;
         }
-        attention_tiled_kernel<<<dim3(n * heads, (T + FA_T - 1) / FA_T), 256, smem, stream>>>(qkv, n, T, D, heads, out, fmt);
+        attention_tiled_kernel<<<dim3(n * heads, (T + FA_T - 1) / FA_T), 128, smem, stream>>>(qkv, n, T, D, heads, out, fmt);
         return cudaGetLastError();
     }
     const int warps = 8;
