@@ -113,3 +113,20 @@ def parsenet_image():
     spec = PARSENET_CASE
     rng = np.random.default_rng(500 + spec['seed'])
     return rng.integers(0, 256, (spec['height'], spec['width'], 3), dtype=np.uint8)
+
+
+# autoregressive Transformer decoding: seeded encoder (pero_ocr_b200/synthetic.py) + seeded decoder
+# (oracle/ar_oracle.py); classes = symbols + sentence boundary + ignore symbol (transformer_ocr_engine.py:16-19)
+AR_CASE = dict(encoder_seed=3, decoder_seed=5, decoder_layers=2, classes=32, lines=3, width=1088)
+
+
+def ar_inputs():
+    """uint8 [N, 3, 40, W]: what TransformerEngineLineOCR.run_ocr hands to transcribe_batch (after its NHWC -> NCHW
+    transpose and the centre padding to 1088 px, transformer_ocr_engine.py:33-40)."""
+    rng = np.random.default_rng(77)
+    n, w = AR_CASE['lines'], AR_CASE['width']
+    x = np.zeros((n, 3, 40, w), dtype=np.uint8)
+    for i, wi in enumerate([1088, 700, 420][:n]):
+        s = (w - wi) // 2
+        x[i, :, :, s:s + wi] = rng.integers(0, 256, (1, 40, wi), dtype=np.uint8)
+    return x

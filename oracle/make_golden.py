@@ -11,6 +11,7 @@ What is executed from the reference (nothing is copied; the tree is imported rea
     the same seeded weights, to pin oracle/nets.py's restatement of that architecture
   * pero_ocr.decoding.decoders.GreedyDecoder / CTCPrefixLogRawNumpyDecoder
   * pero_ocr.layout_engines.torch_parsenet.TorchParseNet.get_maps
+  * pero_ocr.ocr_engine.transformer_ocr_engine.TransformerEngineLineOCR.transcribe_batch (autoregressive decoder)
   * pero_ocr.core.force_alignment.force_align / align_text
   * pero_ocr.core.crop_engine.EngineLineCropper.crop / get_crop_inputs (cv2.remap underneath)
   * pero_ocr.document_ocr.page_parser.PageParser.compute_line_confidence / line_confident_enough and
@@ -292,6 +293,52 @@ def golden_align():
     return info
 
 
+def golden_ar_decoder():
+    """TransformerEngineLineOCR.transcribe_batch (autoregressive greedy decoding with the cached decoder) of the
+    unmodified reference, hosting the seeded encoder of oracle/nets.py and the seeded decoder of oracle/ar_oracle.py."""
+    import torchvision
+    from pero_ocr.ocr_engine import transformer as ref_tr
+    from pero_ocr.ocr_engine.transformer_ocr_engine import TransformerEngineLineOCR
+    from oracle.ar_oracle import ar_decoder_state
+    spec = cases.AR_CASE
+    orig = torchvision.models.vgg16
+    torchvision.models.vgg16 = lambda pretrained=False, **k: orig(weights=None)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = ref_tr.build_net({'dim_model': 512, 'dim_ff': 2048, 'heads': 8, 'encoder_layers': 2,
+                                    'decoder_layers': spec['decoder_layers'], 'conv_subsampling': [8, 4]},
+                                   input_height=40, input_channels=3, nb_output_symbols=spec['classes'] - 2).eval()
+    finally:
+        torchvision.models.vgg16 = orig
+    ours = make_net('transformer', 120, seed=spec['encoder_seed'], layers=2)
+    ref_front = ref.encoder_frontend
+    for r, o in zip([m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.Conv2d)],
+                    [m for m in ours.conv if isinstance(m, torch.nn.Conv2d)]):
+        r.load_state_dict(o.state_dict())
+    [m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.BatchNorm2d)][0].load_state_dict(
+        [m for m in ours.conv if isinstance(m, torch.nn.BatchNorm2d)][0].state_dict())
+    ref_front.aggregation_conv[0].load_state_dict(ours.agg.state_dict())
+    ref.encoder.input_norm.load_state_dict(ours.input_norm.state_dict())
+    ref.encoder.trans_encoder.load_state_dict(ours.trans_encoder.state_dict())
+    dec = ar_decoder_state(seed=spec['decoder_seed'], layers=spec['decoder_layers'], classes=spec['classes'])
+    missing, unexpected = ref.load_state_dict({k: torch.from_numpy(v) for k, v in dec.items()}, strict=False)
+    assert not unexpected and not [k for k in missing if k.startswith(('trans_decoder', 'dec_'))], (missing, unexpected)
+    fake = types.SimpleNamespace(net=ref, device=torch.device('cpu'), sentence_boundary_ind=spec['classes'] - 2,
+                                 ignore_ind=spec['classes'] - 1)
+    fake.postprocess_decoded = lambda *a: TransformerEngineLineOCR.postprocess_decoded(fake, *a)
+    inputs = cases.ar_inputs()                                   # uint8 [N, 3, 40, W]
+    with torch.no_grad():
+        outs, logits = TransformerEngineLineOCR.transcribe_batch(fake, inputs, is_cached=True)
+    n = len(outs)
+    width = max([len(o) for o in outs] + [1])
+    toks = np.full((n, width), -1, dtype=np.int64)
+    for i, o in enumerate(outs):
+        toks[i, :len(o)] = o.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, 'ar_decoder.npz'), tokens=toks,
+                        lengths=np.array([len(o) for o in outs]), logits=logits.numpy().astype(np.float32))
+    return {'lines': n, 'steps': int(logits.shape[1]), 'lengths': [len(o) for o in outs]}
+
+
 def main():
     sys.path.insert(0, REF)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -308,7 +355,7 @@ def main():
                  ('engine_lstm', lambda: golden_engine('lstm', tmp)),
                  ('engine_transformer', lambda: golden_engine('transformer', tmp)),
                  ('parsenet', lambda: golden_parsenet(tmp)), ('confidence', golden_confidence),
-                 ('cropper', golden_cropper), ('align', golden_align)]
+                 ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder)]
         for name, fn in parts:
             if not only or name in only:
                 report[name] = fn()
