@@ -240,6 +240,57 @@ int b200ocr_ctc_prefix_beam_ranges(const double* logprobs, int32_t n, int32_t t,
  *   logprobs  device f64 [n][t][c] (the decoders' working type) */
 int b200ocr_full_logprobs(const float* logits, int32_t n, int32_t t, int32_t c, double* logprobs, void* cuda_stream);
 
+/* ---- autoregressive Transformer decoder (the reference's `pytorch_ocr-transformer` engine) ------------------- */
+/* One DecoderLayer (pero_ocr/ocr_engine/transformer.py:388-462): cached self-attention, encoder-decoder attention,
+ * ReLU feed-forward, post-LN.  HOST fp32 pointers in PyTorch's layouts (state-dict entries
+ * trans_decoder.layers.i.{self_attn,multihead_attn}.{in_proj_weight,in_proj_bias,out_proj.*}, linear1/2, norm1-3). */
+typedef struct b200ocr_ar_layer {
+    const float *self_in_w, *self_in_b;     /* [3D][D], [3D] */
+    const float *self_out_w, *self_out_b;   /* [D][D], [D] */
+    const float *cross_in_w, *cross_in_b;   /* [3D][D], [3D]: rows 0..D-1 project the query, D..3D-1 the memory K | V */
+    const float *cross_out_w, *cross_out_b;
+    const float *lin1_w, *lin1_b;           /* [dim_ff][D] */
+    const float *lin2_w, *lin2_b;           /* [D][dim_ff] */
+    const float *norm1_w, *norm1_b, *norm2_w, *norm2_b, *norm3_w, *norm3_b;
+} b200ocr_ar_layer_t;
+
+typedef struct b200ocr_ar_desc {
+    int32_t n_layers, heads, dim_ff;
+    int32_t classes;                 /* TransformerOCR.num_classes = output symbols + 2 (transformer.py:39) */
+    const b200ocr_ar_layer_t* layers;
+    const float* embed;              /* dec_embeder.weight [classes][D] (transformer.py:512) */
+    const float* out_w;              /* dec_out_proj.weight [classes][D] (:513) */
+    const float* out_b;              /* [classes] */
+} b200ocr_ar_desc_t;
+
+/* Attaches the decoder half of TransformerOCR (transformer.py:489-546) to an engine whose layer list is the encoder
+ * half (conv frontend, B200OCR_LN_PE, B200OCR_TRANSFORMER_LAYER x L -- no CTC head): TransformerOCR.encode (:548-555)
+ * is then b200ocr's layer walk and its output stays in the engine's workspace as the decoder's memory.
+ * Replaces the decoder part of TransformerEngineLineOCR.__init__ (transformer_ocr_engine.py:21-31). */
+int b200ocr_ar_attach(b200ocr_engine_t* e, const b200ocr_ar_desc_t* desc);
+
+/* Workspace for b200ocr_ar_transcribe: batches up to max_lines x max_width_px, up to max_steps decoded positions
+ * (also calls b200ocr_reserve for the encoder). */
+int b200ocr_ar_reserve(b200ocr_engine_t* e, int32_t max_lines, int32_t max_width_px, int32_t max_steps);
+
+/* Replaces TransformerEngineLineOCR.transcribe_batch(inputs, is_cached=True) (transformer_ocr_engine.py:49-89) up to
+ * (not including) postprocess_decoded: `/255`, encode, then greedy decoding one position per step with cached
+ * self-attention keys / values (Decoder.infer / DecoderLayer.infer / CustomMultiheadAttention.cached_forward,
+ * transformer.py:183-305, 418-486) -- the whole token loop runs inside this call.
+ *   crops        device u8 [n][h][w][3] (run_ocr's batch, already centre-padded to >= 1088 px by the caller, :36-40)
+ *   start_token  the sentence-boundary symbol (:17): first input token of every line and the stop symbol
+ *   max_steps    bound on decoded positions; the reference stops after w/4 + 1 (:79-82)
+ *   check_every  the alive mask is read back (one 8-byte copy + a stream synchronisation) every this many steps; the
+ *                reference synchronises at every step (:75).  Positions decoded past the stop are never reported.
+ *   tokens       device i32 [max_steps][n]: greedy choice of every line at every executed step (row s = `samples`
+ *                of step s; the reference's partial_transcripts[1:] are rows 0 .. *steps - 2)
+ *   logits       device f32 [n][max_steps][classes] or NULL: the reference's second result, rows 0 .. *steps - 1 valid
+ *   steps        HOST i32: number of steps the reference loop executes on this batch (its `len(logits)`)
+ * Unlike b200ocr_forward this call synchronises `cuda_stream` (it returns a host value), as the reference loop does. */
+int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_t h, int32_t w,
+                          int32_t start_token, int32_t max_steps, int32_t check_every, int32_t* tokens, float* logits,
+                          int32_t* steps, void* cuda_stream);
+
 /* Per-launch device timing for bench.py's roofline leg: while on, every kernel launched by b200ocr_forward is
  * bracketed by CUDA events on its stream.  b200ocr_profile_read synchronises the device, returns one record per
  * launch (tag 0 = first conv, 1 = tcgen05 implicit GEMM, 2 = tcgen05 LSTM recurrence, 3 = other; index of the layer;

@@ -130,3 +130,68 @@ def ar_inputs():
         s = (w - wi) // 2
         x[i, :, :, s:s + wi] = rng.integers(0, 256, (1, 40, wi), dtype=np.uint8)
     return x
+
+AR_NET_CONFIG = {'dim_model': 512, 'dim_ff': 2048, 'heads': 8, 'encoder_layers': 2,
+                 'decoder_layers': AR_CASE['decoder_layers'], 'conv_subsampling': [8, 4]}   # transformer.build_net keys
+
+
+def ar_state_dict():
+    """The TransformerOCR checkpoint (reference key names) of AR_CASE: seeded encoder + seeded decoder."""
+    from oracle.ar_oracle import ar_decoder_state
+    from pero_ocr_b200.synthetic import make_net, transformer_ocr_state
+    net = make_net('transformer', 120, seed=AR_CASE['encoder_seed'], layers=AR_NET_CONFIG['encoder_layers'])
+    dec = ar_decoder_state(seed=AR_CASE['decoder_seed'], layers=AR_CASE['decoder_layers'], classes=AR_CASE['classes'])
+    return net, dec, transformer_ocr_state(net, dec)
+
+
+def write_ar_engine_json(tmpdir, max_line_width=None):
+    import json
+    import os
+    path = os.path.join(str(tmpdir), 'ar_engine.json')
+    cfg = {'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'ar.pt',
+           'characters': json_characters(AR_CASE['classes'] - 2), 'net_name': AR_NET_CONFIG}
+    if max_line_width is not None:
+        cfg['max_line_width'] = max_line_width
+    with open(path, 'w', encoding='utf8') as f:
+        json.dump(cfg, f)
+    return path
+
+
+# host logic of process_lines for model_type "transformer" (line_ocr_engine.py:57-211): a deterministic stand-in for
+# run_ocr whose transcription is a function of the pixel columns, so overlapping parts of a split line agree on
+# their overlap the way a real recogniser's do.
+AR_HOST_CASE = dict(max_line_width=256, batch_size=2, widths=[700, 256, 90, 257, 1000, 33], block=16, classes=12)
+
+
+def ar_host_lines():
+    rng = np.random.default_rng(91)
+    out = []
+    for w in AR_HOST_CASE['widths']:
+        cols = rng.integers(1, 256, (1, w, 1), dtype=np.uint8)
+        out.append(np.repeat(np.repeat(cols, 40, axis=0), 3, axis=2))
+    return out
+
+
+def ar_host_fake_run_ocr(characters):
+    """-> run_ocr(batch_data) for the stand-in: one character per 16-px block that holds ink, chosen by the block's
+    pixel sum; logits = seeded noise [len + 3, classes]."""
+    import zlib
+    block, classes = AR_HOST_CASE['block'], AR_HOST_CASE['classes']
+
+    def run_ocr(batch_data):
+        texts, logits = [], []
+        longest = 0
+        for line in batch_data:
+            row = line[0, :, 0].astype(np.int64)
+            chars = []
+            for b in range(0, row.shape[0] - block + 1, block):
+                s = int(row[b:b + block].sum())
+                if s:
+                    chars.append(characters[s % (classes - 2)])
+            texts.append(''.join(chars))
+            longest = max(longest, len(chars))
+        for t in texts:
+            rng = np.random.default_rng(zlib.crc32(t.encode('utf8')))
+            logits.append((rng.standard_normal((longest + 3, classes)) * 4).astype(np.float32))
+        return texts, np.stack(logits)
+    return run_ocr

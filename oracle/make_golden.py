@@ -12,6 +12,8 @@ What is executed from the reference (nothing is copied; the tree is imported rea
   * pero_ocr.decoding.decoders.GreedyDecoder / CTCPrefixLogRawNumpyDecoder
   * pero_ocr.layout_engines.torch_parsenet.TorchParseNet.get_maps
   * pero_ocr.ocr_engine.transformer_ocr_engine.TransformerEngineLineOCR.transcribe_batch (autoregressive decoder)
+  * pero_ocr.ocr_engine.line_ocr_engine.BaseEngineLineOCR.process_lines (model_type "transformer": split / merge of
+    long lines) and find_best_overlap, around a deterministic run_ocr stand-in
   * pero_ocr.core.force_alignment.force_align / align_text
   * pero_ocr.core.crop_engine.EngineLineCropper.crop / get_crop_inputs (cv2.remap underneath)
   * pero_ocr.document_ocr.page_parser.PageParser.compute_line_confidence / line_confident_enough and
@@ -339,6 +341,54 @@ def golden_ar_decoder():
     return {'lines': n, 'steps': int(logits.shape[1]), 'lengths': [len(o) for o in outs]}
 
 
+def golden_ar_host(tmp):
+    """BaseEngineLineOCR.process_lines with model_type "transformer" (line_ocr_engine.py:57-211: split of lines wider
+    than max_line_width, merge on the best overlap, logit_coords [0, len]) of the unmodified reference around the
+    deterministic run_ocr stand-in of oracle/cases.py; plus the key / shape list of the state dict that the unmodified
+    transformer.build_net produces (the checkpoint format of TransformerEngineLineOCR)."""
+    import torchvision
+    from pero_ocr.ocr_engine import transformer as ref_tr
+    from pero_ocr.ocr_engine.line_ocr_engine import BaseEngineLineOCR, find_best_overlap
+    spec = cases.AR_HOST_CASE
+    chars = cases.json_characters(spec['classes'] - 2)
+    js = os.path.join(tmp, 'ar_host.json')
+    with open(js, 'w', encoding='utf8') as f:
+        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'none.pt', 'characters': chars,
+                   'net_name': 'x', 'max_line_width': spec['max_line_width']}, f)
+    eng = BaseEngineLineOCR(js, torch.device('cpu'), batch_size=spec['batch_size'], model_type='transformer')
+    eng.run_ocr = cases.ar_host_fake_run_ocr(chars)
+    eng.net_subsampling = 4      # TransformerEngineLineOCR never sets it: tight_crop_logits raises AttributeError there
+    lines = cases.ar_host_lines()
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr, lg, co = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+        tr_t, lg_t, co_t = eng.process_lines([l.copy() for l in lines], sparse_logits=False, tight_crop_logits=True)
+        tr_s, lg_s, co_s = eng.process_lines([l.copy() for l in lines], sparse_logits=True)
+    out['transcriptions'] = np.array(tr)
+    for i in range(len(lines)):
+        out[f'logits_{i}'] = lg[i]
+        out[f'coords_{i}'] = np.array(co[i])
+        out[f'tight_{i}'] = lg_t[i]
+        out[f'sparse_{i}'] = lg_s[i].toarray()
+    pairs = [('hello world', 'world peace'), ('abcabc', 'bcabcd'), ('xyz', 'abc'), ('aaaa', 'aa'), ('a', 'b'),
+             ('', 'abc'), ('same', 'same')]
+    out['overlap_pairs'] = np.array([list(p) for p in pairs])
+    out['overlaps'] = np.array([find_best_overlap(a, b) for a, b in pairs])
+    np.savez_compressed(os.path.join(GOLDEN, 'ar_host.npz'), **out)
+    orig = torchvision.models.vgg16
+    torchvision.models.vgg16 = lambda pretrained=False, **k: orig(weights=None)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = ref_tr.build_net(cases.AR_NET_CONFIG, input_height=40, input_channels=3,
+                                   nb_output_symbols=cases.AR_CASE['classes'] - 2)
+    finally:
+        torchvision.models.vgg16 = orig
+    keys = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    with open(os.path.join(GOLDEN, 'transformer_ocr_keys.json'), 'w') as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+    return {'lines': len(lines), 'transcriptions': tr, 'state_dict_keys': len(keys)}
+
+
 def main():
     sys.path.insert(0, REF)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -355,7 +405,8 @@ def main():
                  ('engine_lstm', lambda: golden_engine('lstm', tmp)),
                  ('engine_transformer', lambda: golden_engine('transformer', tmp)),
                  ('parsenet', lambda: golden_parsenet(tmp)), ('confidence', golden_confidence),
-                 ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder)]
+                 ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder),
+                 ('ar_host', lambda: golden_ar_host(tmp))]
         for name, fn in parts:
             if not only or name in only:
                 report[name] = fn()

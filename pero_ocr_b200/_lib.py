@@ -40,6 +40,19 @@ class PolyLine(C.Structure):
                 ('step', C.c_double), ('rot', C.c_double * 4), ('ncoef', C.c_int32), ('n_out', C.c_int32)]
 
 
+class ArLayer(C.Structure):
+    """b200ocr_ar_layer_t (include/b200_lineocr.h)."""
+    _fields_ = [(k, _FP) for k in (
+        'self_in_w', 'self_in_b', 'self_out_w', 'self_out_b', 'cross_in_w', 'cross_in_b', 'cross_out_w', 'cross_out_b',
+        'lin1_w', 'lin1_b', 'lin2_w', 'lin2_b', 'norm1_w', 'norm1_b', 'norm2_w', 'norm2_b', 'norm3_w', 'norm3_b')]
+
+
+class ArDesc(C.Structure):
+    """b200ocr_ar_desc_t (include/b200_lineocr.h)."""
+    _fields_ = [('n_layers', C.c_int32), ('heads', C.c_int32), ('dim_ff', C.c_int32), ('classes', C.c_int32),
+                ('layers', C.POINTER(ArLayer)), ('embed', _FP), ('out_w', _FP), ('out_b', _FP)]
+
+
 class NetDesc(C.Structure):
     _fields_ = [('n_layers', C.c_int32), ('layers', C.POINTER(Layer)), ('precision', C.c_int32),
                 ('line_height', C.c_int32), ('device', C.c_int32)]
@@ -76,6 +89,10 @@ EXPORTS = {
    'b200ocr_ctc_prefix_beam_ranges': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'b200ocr_full_logprobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    'b200ocr_ar_attach': (C.c_int, [C.c_void_p, C.POINTER(ArDesc)]),
+    'b200ocr_ar_reserve': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    'b200ocr_ar_transcribe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     'b200ocr_profile': (C.c_int, [C.c_void_p, C.c_int32]),
     'b200ocr_profile_read': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_int32)]),

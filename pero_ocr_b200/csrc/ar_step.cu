@@ -1,0 +1,245 @@
+// Step kernels of the autoregressive Transformer decoder: the per-token work of
+// TransformerEngineLineOCR.transcribe_batch (pero_ocr/ocr_engine/transformer_ocr_engine.py:49-89) that is not a GEMM.
+//   * embed_pe:        dec_embeder(token) + PositionalEncoding row of the position   (transformer.py:316-332, 512-513)
+//   * step_attention:  one query position per (line, head) against S cached key / value positions -- the cached
+//                      self-attention (S = tokens so far) and the encoder-decoder attention (S = T memory frames) of
+//                      CustomMultiheadAttention.cached_forward (transformer.py:183-305); fp32, softmax over all S
+//   * linear_f32:      the per-step projections (M = lines in the batch <= a few hundred rows: in-proj, out-proj,
+//                      feed-forward, class projection) as a tiled fp32 CUDA-core GEMM with fused bias / ReLU /
+//                      residual; these are weight-streaming bound at M <= 256 and keep the greedy argmax in fp32.
+//                      The large contraction of the decoder (memory K / V projection, M = lines x frames) goes
+//                      through the tcgen05 kernel instead (engine.cu)
+//   * argmax_alive:    torch.argmax over the classes (first maximum) + alive-mask update + stop detection
+//                      (transformer_ocr_engine.py:72-77)
+#include "kernels.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace {
+
+// tokens == nullptr: every line starts from `start_token` (position 0).
+__global__ void embed_pe_kernel(const float* __restrict__ table, const int32_t* __restrict__ tokens, int start_token,
+                                int n, int d, int pos, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d) return;
+    const int line = i / d, c = i - line * d;
+    const int tok = tokens ? tokens[line] : start_token;
+    // pe[pos, 2m] = sin(pos * exp(2m * -ln(1e4)/d)), pe[pos, 2m+1] = cos(same)   (transformer.py:321-328)
+    const int m2 = c & ~1;
+    const float div = expf(static_cast<float>(m2) * (-logf(10000.0f) / d));
+    const float ang = static_cast<float>(pos) * div;
+    out[i] = table[static_cast<size_t>(tok) * d + c] + ((c & 1) ? cosf(ang) : sinf(ang));
+}
+
+// one warp per (line, head); head width a multiple of 4, <= 128.  q: [n][q_ls]; k, v: position p of line l at
+// + p * ps + l * ls (16-byte aligned rows).  Scores of the S positions live in shared memory.
+__global__ void step_attention_kernel(const float* __restrict__ q, long q_ls, const float* __restrict__ k,
+                                      const float* __restrict__ v, long ps, long ls, int n, int S, int d, int heads,
+                                      float* __restrict__ out) {
+    extern __shared__ float s_w[];                    // [warps][S] scores, then [warps][128] scaled query
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * warps + warp;
+    if (unit >= n * heads) return;
+    const int line = unit / heads, head = unit - line * heads;
+    const int hd = d / heads;
+    const float scale = powf(static_cast<float>(hd), -0.5f);
+    float* w = s_w + static_cast<size_t>(warp) * S;
+    float* qs = s_w + static_cast<size_t>(warps) * S + warp * 128;
+    for (int e = lane; e < hd; e += 32) qs[e] = q[line * q_ls + head * hd + e] * scale;   // q scaled first (:268-271)
+    __syncwarp();
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    float mx = -INFINITY;
+    for (int p = lane; p < S; p += 32) {
+        const float4* kp = reinterpret_cast<const float4*>(k + p * ps + line * ls + head * hd);
+        float s = 0.f;
+        for (int e = 0; e < hd / 4; ++e) {
+            const float4 kk = kp[e], qq = q4[e];
+            s = fmaf(qq.x, kk.x, s); s = fmaf(qq.y, kk.y, s); s = fmaf(qq.z, kk.z, s); s = fmaf(qq.w, kk.w, s);
+        }
+        w[p] = s;
+        mx = fmaxf(mx, s);
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int p = lane; p < S; p += 32) {
+        const float e = expf(w[p] - mx);
+        w[p] = e;
+        sum += e;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int e = lane; e < hd; e += 32) {
+        const float* vp = v + line * ls + head * hd + e;
+        float acc = 0.f;
+        for (int p = 0; p < S; ++p) acc = fmaf(w[p], vp[p * ps], acc);
+        out[static_cast<size_t>(line) * d + head * hd + e] = acc * inv;
+    }
+}
+
+// out[m][o] = act(sum_k x[m][k] * w[o][k] + bias[o]) (+ res[m][o]);  x rows ldx apart, w = PyTorch Linear weight
+// [O][K] (K contiguous), out rows ldo apart.  32 x 32 output tile per CTA, 64 threads x (4 x 4), K in chunks of 32.
+constexpr int LBM = 32, LBN = 32, LBK = 32, LLD = 33;
+
+__global__ void __launch_bounds__(64) linear_f32_kernel(const float* __restrict__ x, long ldx,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        const float* __restrict__ res, long ldr,
+                                                        float* __restrict__ out, long ldo, int M, int O, int K,
+                                                        int relu) {
+    __shared__ float xs[LBK][LLD];   // [k][m]
+    __shared__ float ws[LBK][LLD];   // [k][o]
+    const int m0 = blockIdx.y * LBM, o0 = blockIdx.x * LBN;
+    const int tid = threadIdx.x, tm = tid >> 3, tn = tid & 7;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += LBK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 64;          // 256 float4 per operand tile
+            const int r = idx >> 3, k4 = (idx & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), u = v;
+            if (m0 + r < M) v = *reinterpret_cast<const float4*>(x + static_cast<long>(m0 + r) * ldx + k0 + k4);
+            if (o0 + r < O) u = *reinterpret_cast<const float4*>(w + static_cast<size_t>(o0 + r) * K + k0 + k4);
+            xs[k4 + 0][r] = v.x; xs[k4 + 1][r] = v.y; xs[k4 + 2][r] = v.z; xs[k4 + 3][r] = v.w;
+            ws[k4 + 0][r] = u.x; ws[k4 + 1][r] = u.y; ws[k4 + 2][r] = u.z; ws[k4 + 3][r] = u.w;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < LBK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = xs[k][tm * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = ws[k][tn * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + tm * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + tn * 4 + j;
+            if (o >= O) continue;
+            float v = acc[i][j] + (bias ? bias[o] : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            if (res) v += res[static_cast<long>(m) * ldr + o];
+            out[static_cast<long>(m) * ldo + o] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ bool score_better(float v, int i, float bv, int bi) {
+    // torch.argmax: NaN counts as the maximum; among equal values the lowest index wins
+    const bool vn = v != v, bn = bv != bv;
+    if (vn != bn) return vn;
+    if (!vn && v != bv) return v > bv;
+    return i < bi;
+}
+
+// One CTA for the whole batch (a few hundred lines x a few hundred classes): warp per line.
+// state[0] = lines still alive after this step, state[1] = first step after which none was (-1 until then).
+__global__ void argmax_alive_kernel(const float* __restrict__ logits, long ld, int n, int C, int stop_token, int step,
+                                    int32_t* __restrict__ tokens_out, int32_t* __restrict__ alive,
+                                    int32_t* __restrict__ state) {
+    __shared__ int total;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int line = warp; line < n; line += warps) {
+        const float* row = logits + static_cast<long>(line) * ld;
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = row[c];
+            if (bi == 0x7fffffff || score_better(v, c, bv, bi)) { bv = v; bi = c; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || score_better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            tokens_out[line] = bi;
+            const int a = (alive[line] != 0 && bi != stop_token) ? 1 : 0;
+            alive[line] = a;
+            mine += a;
+        }
+    }
+    if (lane == 0 && mine) atomicAdd(&total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        state[0] = total;
+        if (total == 0 && state[1] < 0) state[1] = step;
+    }
+}
+
+__global__ void ar_init_kernel(int32_t* alive, int n, int32_t* state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) alive[i] = 1;
+    if (i == 0) { state[0] = n; state[1] = -1; }
+}
+
+}  // namespace
+
+cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start_token, int n, int d, int pos,
+                            float* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    embed_pe_kernel<<<(n * d + 255) / 256, 256, 0, stream>>>(table, tokens, start_token, n, d, pos, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
+                              float* out, long ldo, int M, int O, int K, int relu, cudaStream_t stream) {
+    if (M <= 0 || O <= 0) return cudaSuccess;
+    if (K <= 0 || (K % LBK) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
+        return cudaErrorInvalidValue;
+    const dim3 grid((O + LBN - 1) / LBN, (M + LBM - 1) / LBM);
+    linear_f32_kernel<<<grid, 64, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_argmax_alive(const float* logits, long ld, int n, int C, int stop_token, int step,
+                                int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    argmax_alive_kernel<<<1, 256, 0, stream>>>(logits, ld, n, C, stop_token, step, tokens_out, alive, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ar_init(int32_t* alive, int n, int32_t* state, cudaStream_t stream) {
+    ar_init_kernel<<<(std::max(n, 1) + 255) / 256, 256, 0, stream>>>(alive, n, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
+                                  int S, int d, int heads, float* out, cudaStream_t stream) {
+    if (n <= 0 || S <= 0) return cudaSuccess;
+    const int hd = heads > 0 ? d / heads : 0;
+    if (heads <= 0 || hd * heads != d || (hd % 4) || hd > 128 || (ps % 4) || (ls % 4) ||
+        (reinterpret_cast<uintptr_t>(k) & 15))
+        return cudaErrorInvalidValue;
+    const int warps = 4;
+    const size_t smem = static_cast<size_t>(warps) * (S + 128) * sizeof(float);
+    if (smem > 160 * 1024) return cudaErrorInvalidValue;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(step_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int units = n * heads;
+    step_attention_kernel<<<(units + warps - 1) / warps, warps * 32, smem, stream>>>(q, q_ls, k, v, ps, ls, n, S, d, heads,
+                                                                                    out);
+    return cudaGetLastError();
+}

@@ -70,6 +70,31 @@ struct Shape {
     int n, h, w, c;
 };
 
+// Decoder half of TransformerOCR (b200ocr_ar_attach): fp32 weights of the per-step projections, the tcgen05 GEMM of
+// the memory K | V projection, and the decode workspace.
+struct ArLayer {
+    float *self_in_w = nullptr, *self_in_b = nullptr, *self_out_w = nullptr, *self_out_b = nullptr;
+    float *cross_q_w = nullptr, *cross_q_b = nullptr, *cross_out_w = nullptr, *cross_out_b = nullptr;
+    float *l1w = nullptr, *l1b = nullptr, *l2w = nullptr, *l2b = nullptr;
+    float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr, *n3w = nullptr, *n3b = nullptr;
+    Gemm g_memkv;   // rows D..3D-1 of the encoder-decoder in_proj: memory -> K | V
+};
+
+struct ArState {
+    bool attached = false;
+    int heads = 0, dim_ff = 0, classes = 0, D = 0;
+    std::vector<ArLayer> layers;
+    float *embed = nullptr, *out_w = nullptr, *out_b = nullptr;
+    // workspace (b200ocr_ar_reserve)
+    int cap_lines = 0, cap_T = 0, cap_steps = 0;
+    float* memkv = nullptr;    // [layer][cap_lines * cap_T][2D]   K | V of the memory frames
+    float* selfkv = nullptr;   // [layer][cap_steps][lines][2D]    K | V of the decoded positions
+    float *x = nullptr, *q = nullptr, *a = nullptr, *t = nullptr, *f = nullptr, *lg = nullptr;
+    int32_t *alive = nullptr, *state = nullptr;
+    int32_t* h_state = nullptr;   // pinned host copy of `state`
+    std::vector<void*> ws;
+};
+
 }  // namespace
 
 struct b200ocr_engine {
@@ -94,6 +119,7 @@ struct b200ocr_engine {
     int cur_layer = -1;
     struct ProfRec { int tag, layer; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
+    ArState ar;
 };
 
 namespace {
@@ -767,6 +793,8 @@ void b200ocr_destroy(b200ocr_engine_t* e) {
         if (e->fbuf[i]) cudaFree(e->fbuf[i]);
     }
     if (e->best) { cudaFree(e->best); cudaFree(e->fmax); cudaFree(e->flse); cudaFree(e->fprob); }
+    for (void* p : e->ar.ws) cudaFree(p);
+    if (e->ar.h_state) cudaFreeHost(e->ar.h_state);
     delete e;
 }
 
@@ -925,6 +953,188 @@ int b200ocr_full_logprobs(const float* logits, int32_t n, int32_t t, int32_t c, 
         return fail(nullptr, B200OCR_E_INVALID, "bad full_logprobs arguments");
     if (n == 0) return B200OCR_OK;
     CU_TRY(nullptr, launch_full_logprobs(logits, n, t, c, logprobs, static_cast<cudaStream_t>(cuda_stream)));
+    return B200OCR_OK;
+}
+
+int b200ocr_ar_attach(b200ocr_engine_t* e, const b200ocr_ar_desc_t* d) {
+    if (!e) return B200OCR_E_INVALID;
+    if (!d || d->n_layers <= 0 || !d->layers || d->heads <= 0 || d->dim_ff <= 0 || d->classes <= 1 || !d->embed ||
+        !d->out_w || !d->out_b)
+        return fail(e, B200OCR_E_INVALID, "bad decoder descriptor");
+    if (e->ar.attached) return fail(e, B200OCR_E_INVALID, "a decoder is already attached to this engine");
+    if (e->layers.empty() || e->layers.back().kind != B200OCR_TRANSFORMER_LAYER)
+        return fail(e, B200OCR_E_INVALID, "the decoder attaches to an engine that ends in the Transformer encoder");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int D = e->layers.back().g_out.cout;
+    const int hd = D / d->heads;
+    if (hd * d->heads != D || (hd % 4) || hd > 128 || (D % 32) || (d->dim_ff % 32))
+        return fail(e, B200OCR_E_INVALID, "decoder needs head width %% 4 == 0 (<= 128) and D, dim_ff %% 32 == 0");
+    ArState& ar = e->ar;
+    ar.heads = d->heads; ar.dim_ff = d->dim_ff; ar.classes = d->classes; ar.D = D;
+    ar.layers.resize(d->n_layers);
+    const size_t DD = static_cast<size_t>(D) * D;
+    for (int i = 0; i < d->n_layers; ++i) {
+        const b200ocr_ar_layer_t& src = d->layers[i];
+        ArLayer& L = ar.layers[i];
+        const float* all[] = {src.self_in_w, src.self_in_b, src.self_out_w, src.self_out_b, src.cross_in_w,
+                              src.cross_in_b, src.cross_out_w, src.cross_out_b, src.lin1_w, src.lin1_b, src.lin2_w,
+                              src.lin2_b, src.norm1_w, src.norm1_b, src.norm2_w, src.norm2_b, src.norm3_w, src.norm3_b};
+        for (const float* p : all)
+            if (!p) return fail(e, B200OCR_E_INVALID, "decoder layer %d: missing parameter", i);
+        int s = 0;
+        if ((s = upload(e, src.self_in_w, 3 * DD, &L.self_in_w))) return s;
+        if ((s = upload(e, src.self_in_b, (size_t)3 * D, &L.self_in_b))) return s;
+        if ((s = upload(e, src.self_out_w, DD, &L.self_out_w))) return s;
+        if ((s = upload(e, src.self_out_b, (size_t)D, &L.self_out_b))) return s;
+        if ((s = upload(e, src.cross_in_w, DD, &L.cross_q_w))) return s;          // query rows only
+        if ((s = upload(e, src.cross_in_b, (size_t)D, &L.cross_q_b))) return s;
+        if ((s = upload(e, src.cross_out_w, DD, &L.cross_out_w))) return s;
+        if ((s = upload(e, src.cross_out_b, (size_t)D, &L.cross_out_b))) return s;
+        if ((s = upload(e, src.lin1_w, (size_t)d->dim_ff * D, &L.l1w))) return s;
+        if ((s = upload(e, src.lin1_b, (size_t)d->dim_ff, &L.l1b))) return s;
+        if ((s = upload(e, src.lin2_w, (size_t)d->dim_ff * D, &L.l2w))) return s;
+        if ((s = upload(e, src.lin2_b, (size_t)D, &L.l2b))) return s;
+        if ((s = upload(e, src.norm1_w, (size_t)D, &L.n1w))) return s;
+        if ((s = upload(e, src.norm1_b, (size_t)D, &L.n1b))) return s;
+        if ((s = upload(e, src.norm2_w, (size_t)D, &L.n2w))) return s;
+        if ((s = upload(e, src.norm2_b, (size_t)D, &L.n2b))) return s;
+        if ((s = upload(e, src.norm3_w, (size_t)D, &L.n3w))) return s;
+        if ((s = upload(e, src.norm3_b, (size_t)D, &L.n3b))) return s;
+        if ((s = build_gemm(e, L.g_memkv, src.cross_in_w + DD, src.cross_in_b + D, nullptr, nullptr, D, 2 * D, 1, 1, 0, 0)))
+            return s;
+    }
+    int s = 0;
+    if ((s = upload(e, d->embed, (size_t)d->classes * D, &ar.embed))) return s;
+    if ((s = upload(e, d->out_w, (size_t)d->classes * D, &ar.out_w))) return s;
+    if ((s = upload(e, d->out_b, (size_t)d->classes, &ar.out_b))) return s;
+    CU_TRY(e, cudaMallocHost(reinterpret_cast<void**>(&ar.h_state), 2 * sizeof(int32_t)));
+    ar.attached = true;
+    return B200OCR_OK;
+}
+
+int b200ocr_ar_reserve(b200ocr_engine_t* e, int32_t max_lines, int32_t max_width_px, int32_t max_steps) {
+    if (!e) return B200OCR_E_INVALID;
+    if (!e->ar.attached) return fail(e, B200OCR_E_INVALID, "no decoder attached (b200ocr_ar_attach)");
+    if (max_lines <= 0 || max_width_px <= 0 || max_steps <= 0) return fail(e, B200OCR_E_INVALID, "bad reserve arguments");
+    if (int s = b200ocr_reserve(e, max_lines, max_width_px)) return s;
+    Need need;
+    Outputs none;
+    Shape fs;
+    if (int s = walk(e, nullptr, max_lines, e->line_height, max_width_px, 1 << 30, none, nullptr, &need, &fs, nullptr,
+                     nullptr))
+        return s;
+    ArState& ar = e->ar;
+    if (fs.h != 1 || fs.c != ar.D) return fail(e, B200OCR_E_INVALID, "encoder output is not a [n][1][T][%d] sequence", ar.D);
+    if (max_lines <= ar.cap_lines && fs.w <= ar.cap_T && max_steps <= ar.cap_steps) return B200OCR_OK;
+    const int N = std::max(max_lines, ar.cap_lines), T = std::max(fs.w, ar.cap_T), S = std::max(max_steps, ar.cap_steps);
+    for (void* p : ar.ws) cudaFree(p);
+    ar.ws.clear();
+    ar.cap_lines = ar.cap_T = ar.cap_steps = 0;
+    const size_t L = ar.layers.size(), D = ar.D;
+    auto grab = [&](size_t bytes, void** out) -> cudaError_t {
+        cudaError_t err = cudaMalloc(out, std::max<size_t>(bytes, 16));
+        if (err == cudaSuccess) ar.ws.push_back(*out);
+        return err;
+    };
+    CU_TRY(e, grab(L * N * T * 2 * D * sizeof(float), reinterpret_cast<void**>(&ar.memkv)));
+    CU_TRY(e, grab(L * S * N * 2 * D * sizeof(float), reinterpret_cast<void**>(&ar.selfkv)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.x)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.q)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.a)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.t)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * ar.dim_ff * sizeof(float), reinterpret_cast<void**>(&ar.f)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * ar.classes * sizeof(float), reinterpret_cast<void**>(&ar.lg)));
+    CU_TRY(e, grab(static_cast<size_t>(N) * sizeof(int32_t), reinterpret_cast<void**>(&ar.alive)));
+    CU_TRY(e, grab(2 * sizeof(int32_t), reinterpret_cast<void**>(&ar.state)));
+    ar.cap_lines = N; ar.cap_T = T; ar.cap_steps = S;
+    return B200OCR_OK;
+}
+
+int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, int32_t h, int32_t w,
+                          int32_t start_token, int32_t max_steps, int32_t check_every, int32_t* tokens, float* logits,
+                          int32_t* steps, void* cuda_stream) {
+    if (!e) return B200OCR_E_INVALID;
+    ArState& ar = e->ar;
+    if (!ar.attached) return fail(e, B200OCR_E_INVALID, "no decoder attached (b200ocr_ar_attach)");
+    if (!crops || n <= 0 || h != e->line_height || w <= 0 || (w % 8) || !tokens || !steps || max_steps <= 0 ||
+        start_token < 0 || start_token >= ar.classes)
+        return fail(e, B200OCR_E_INVALID, "bad ar_transcribe arguments (n=%d h=%d w=%d max_steps=%d)", n, h, w, max_steps);
+    if (check_every <= 0) check_every = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // TransformerOCR.encode (transformer.py:548-555): the layer walk; memory = records in hbuf[0], rows n*T + t
+    Outputs none;
+    Shape fs;
+    const void* mem = nullptr;
+    bool mem_f32 = false;
+    if (int s = walk(e, crops, n, h, w, 1 << 30, none, st, nullptr, &fs, &mem, &mem_f32)) return s;
+    const int D = ar.D, T = fs.w, C = ar.classes, FF = ar.dim_ff;
+    if (mem_f32 || !mem || fs.h != 1 || fs.c != D) return fail(e, B200OCR_E_INVALID, "encoder output is not a [n][1][T][%d] sequence", D);
+    if (n > ar.cap_lines || T > ar.cap_T || max_steps > ar.cap_steps)
+        return fail(e, B200OCR_E_WORKSPACE, "workspace too small: call b200ocr_ar_reserve first");
+    const int L = static_cast<int>(ar.layers.size());
+    const size_t memkv_layer = static_cast<size_t>(ar.cap_lines) * ar.cap_T * 2 * D;
+    const size_t selfkv_layer = static_cast<size_t>(ar.cap_steps) * ar.cap_lines * 2 * D;
+#define AR_LAUNCH(call)      \
+    do {                     \
+        CU_TRY(e, call);     \
+        e->launches++;       \
+    } while (0)
+    // K | V of the memory for every layer, once per batch (cached_forward's static branch, transformer.py:239-249)
+    for (int i = 0; i < L; ++i) {
+        EpiOut eo;
+        eo.epi = EPI_F32;
+        eo.out_f32 = ar.memkv + i * memkv_layer;
+        e->cur_layer = static_cast<int>(e->layers.size()) + i;
+        if (int s = run_gemm(e, ar.layers[i].g_memkv, static_cast<const __half*>(mem), Shape{1, 1, n * T, D}, 0, 1, 1, eo,
+                             st, nullptr))
+            return s;
+    }
+    AR_LAUNCH(launch_ar_init(ar.alive, n, ar.state, st));
+    int done_steps = -1;
+    for (int s = 0; s < max_steps; ++s) {
+        AR_LAUNCH(launch_embed_pe(ar.embed, s == 0 ? nullptr : tokens + static_cast<size_t>(s - 1) * n, start_token, n, D,
+                                  s, ar.x, st));
+        for (int i = 0; i < L; ++i) {
+            const ArLayer& ly = ar.layers[i];
+            float* kv = ar.selfkv + i * selfkv_layer;                       // position p at + p * n * 2D
+            float* kv_s = kv + static_cast<size_t>(s) * n * 2 * D;
+            const float* mkv = ar.memkv + i * memkv_layer;                  // row (line * T + t) * 2D
+            // cached self-attention over positions 0..s (DecoderLayer.infer, transformer.py:431-435)
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w + static_cast<size_t>(D) * D, ly.self_in_b + D, nullptr, 0,
+                                        kv_s, 2 * D, n, 2 * D, D, 0, st));
+            AR_LAUNCH(launch_step_attention(ar.q, D, kv, kv + D, static_cast<long>(n) * 2 * D, 2 * D, n, s + 1, D,
+                                            ar.heads, ar.a, st));
+            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.self_out_w, ly.self_out_b, ar.x, D, ar.t, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n1w, ly.n1b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+            // encoder-decoder attention over the T memory frames (:438-447)
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_step_attention(ar.q, D, mkv, mkv + D, 2 * D, static_cast<long>(T) * 2 * D, n, T, D, ar.heads,
+                                            ar.a, st));
+            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.cross_out_w, ly.cross_out_b, ar.x, D, ar.t, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n2w, ly.n2b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+            // feed-forward (:449-450)
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, st));
+            AR_LAUNCH(launch_linear_f32(ar.f, FF, ly.l2w, ly.l2b, ar.x, D, ar.t, D, n, D, FF, 0, st));
+            AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n3w, ly.n3b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+        }
+        // dec_out_proj + argmax + alive mask (transformer_ocr_engine.py:69-75)
+        float* lg = logits ? logits + static_cast<size_t>(s) * C : ar.lg;
+        const long lg_ld = logits ? static_cast<long>(max_steps) * C : C;
+        AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, st));
+        AR_LAUNCH(launch_argmax_alive(lg, lg_ld, n, C, start_token, s, tokens + static_cast<size_t>(s) * n, ar.alive,
+                                      ar.state, st));
+        if ((s + 1) % check_every == 0 || s + 1 == max_steps) {
+            CU_TRY(e, cudaMemcpyAsync(ar.h_state, ar.state, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(e, cudaStreamSynchronize(st));
+            if (ar.h_state[1] >= 0) {
+                done_steps = ar.h_state[1] + 1;
+                break;
+            }
+        }
+    }
+#undef AR_LAUNCH
+    *steps = done_steps >= 0 ? done_steps : max_steps;
     return B200OCR_OK;
 }
 

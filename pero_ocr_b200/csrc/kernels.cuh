@@ -33,6 +33,21 @@ cudaError_t launch_force_align(const void* neg, int is_f64, int n, int t_max, in
                                cudaStream_t stream);
 size_t force_align_workspace_bytes(int n, int t_max, int l_max);
 
+// Autoregressive decoder step kernels (ar_step.cu; transformer_ocr_engine.py:49-89, transformer.py:183-305, 418-462).
+// embed_pe: out[line][:] = table[tokens ? tokens[line] : start_token][:] + sinusoid(pos)   (fp32 [n][d])
+cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start_token, int n, int d, int pos,
+                            float* out, cudaStream_t stream);
+// out[m][o] = act(x[m][:] . w[o][:] + bias[o]) (+ res[m][o]); fp32, w = Linear weight [O][K], K % 32 == 0.
+cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
+                              float* out, long ldo, int M, int O, int K, int relu, cudaStream_t stream);
+// one query position per (line, head) against S key / value positions (position p of line l at + p*ps + l*ls).
+cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
+                                  int S, int d, int heads, float* out, cudaStream_t stream);
+// greedy choice + alive mask + stop detection; state = {alive lines, first step after which none was alive or -1}.
+cudaError_t launch_argmax_alive(const float* logits, long ld, int n, int C, int stop_token, int step,
+                                int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream);
+cudaError_t launch_ar_init(int32_t* alive, int n, int32_t* state, cudaStream_t stream);
+
 // Per-character confidences (char_conf.cu; core/confidence_estimation.py:73-104).
 cudaError_t launch_char_conf(const float* logp, int n, int t_max, int C, const int32_t* n_frames, const int32_t* labels,
                              int l_max, const int32_t* lengths, const int32_t* char_pos, float* conf,

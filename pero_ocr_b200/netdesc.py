@@ -10,8 +10,15 @@ loads is walked here and turned into the flat layer list of ``include/b200_lineo
                     ``input_norm`` + ``trans_encoder`` (post-LN nn.TransformerEncoder, ReLU), then ``out`` (Linear).
   page detector:    ``e1 e2 | pool | e3 e4 | pool | d1 d2 | head`` 3x3 convs + nearest x4 upsampling.
 
+  TransformerOCR:   the state dict ``TransformerEngineLineOCR`` loads (transformer_ocr_engine.py:21-29) plus the
+                    ``net_name`` config of ``transformer.build_net`` (transformer.py:12-48) -> encoder layer list
+                    (no CTC head) + decoder description for ``b200ocr_ar_attach`` (``describe_transformer_ocr``).
+
 Anything else raises -- there is no generic fallback executor.
 """
+import json
+import re
+
 import numpy as np
 
 from . import _lib
@@ -22,6 +29,8 @@ def _name(m):
 
 
 def _f32(t):
+    if not hasattr(t, 'detach'):
+        return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
     return np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32))
 
 
@@ -134,6 +143,142 @@ def describe_line_net(module):
     ow, ob = _f32(sd['out.weight']), _f32(sd['out.bias'])
     layers.append(dict(kind=_lib.CTC_HEAD, cin=feat, cout=ow.shape[0], kh=1, kw=1, weight=ow, bias=ob))
     return layers, ow.shape[0]
+
+
+def describe_transformer_ocr(state_dict, net_config, line_height=40):
+    """State dict of the reference's ``TransformerOCR`` (transformer.py:489-546) + the ``net_name`` config that
+    ``build_net`` reads (:12-20) -> (encoder layer specs for b200ocr_create, decoder spec for b200ocr_ar_attach).
+
+    The convolutional frontend is rebuilt from the key structure the way ``VGG_conv_module.__init__`` builds it
+    (:75-148): convolutions directly in ``blocks_2d`` come from VGG16 (ReLU), a gap of four module indices after one
+    means a (max-pool, dropout) pair follows it, nested ``Sequential`` blocks are ``create_vgg_block_2d(norm='none')``
+    (:51-72: conv + LeakyReLU twice, then a max-pool) followed by a BatchNorm2d; pool strides replay the subsampling
+    bookkeeping (:104-139) from ``conv_subsampling``."""
+    cfg = json.loads(net_config) if isinstance(net_config, str) else dict(net_config)
+    sd = {k: _f32(v) for k, v in state_dict.items() if not k.endswith('num_batches_tracked')}
+    d_model, dim_ff, heads = int(cfg['dim_model']), int(cfg['dim_ff']), int(cfg['heads'])
+    sub_v, sub_h = cfg['conv_subsampling']
+    prefix = 'encoder_frontend.blocks_2d.blocks_2d.'
+    mods = {}                                   # (idx,) or (idx, sub) -> module key prefix
+    for k in sd:
+        if k.startswith(prefix):
+            m = re.match(r'(\d+)(?:\.(\d+))?\.(weight|bias|running_mean|running_var)$', k[len(prefix):])
+            if not m:
+                raise ValueError(f'unexpected frontend parameter {k}')
+            key = (int(m.group(1)),) if m.group(2) is None else (int(m.group(1)), int(m.group(2)))
+            mods[key] = prefix + '.'.join(str(i) for i in key)
+    top = sorted({k[0] for k in mods})
+    layers = []
+    cur_v = cur_h = 1
+
+    def next_stride():
+        nonlocal cur_v, cur_h
+        sv = 2 if (sub_v is None or cur_v < sub_v) else 1           # transformer.py:106-114 / 128-136
+        sh = 2 if cur_h < sub_h else 1
+        cur_v, cur_h = cur_v * sv, cur_h * sh
+        return sv, sh
+
+    def set_pool(spec, stride):
+        if stride == (1, 1):
+            return
+        if spec['kind'] == _lib.CONV_FIRST or stride[0] not in (1, 2) or stride[1] not in (1, 2):
+            raise ValueError('max-pool must be 2x2 / 2x1 / 1x2 and follow a tensor-core convolution')
+        spec['pool_h'], spec['pool_w'] = stride
+
+    for pos, idx in enumerate(top):
+        nested = sorted(k for k in mods if k[0] == idx and len(k) == 2)
+        nxt = top[pos + 1] if pos + 1 < len(top) else None
+        if nested:                                                   # create_vgg_block_2d(norm='none')
+            for key in nested:
+                spec = _conv_spec(sd, mods[key], first=False)
+                spec['act'] = _lib.ACT_LEAKY_RELU
+                layers.append(spec)
+            set_pool(layers[-1], next_stride())
+        elif mods[(idx,)] + '.running_mean' in sd:                   # BatchNorm2d after a block (:141-144)
+            key = mods[(idx,)]
+            g, b, mu, var = (sd[key + s].astype(np.float64) for s in ('.weight', '.bias', '.running_mean', '.running_var'))
+            scale = g / np.sqrt(var + 1e-5)
+            if not layers or layers[-1]['kind'] == _lib.CONV_FIRST or 'post_scale' in layers[-1]:
+                raise ValueError('BatchNorm must follow a tensor-core convolution')
+            layers[-1]['post_scale'] = scale.astype(np.float32)
+            layers[-1]['post_shift'] = (b - mu * scale).astype(np.float32)
+        else:                                                        # VGG16 conv + ReLU
+            spec = _conv_spec(sd, mods[(idx,)], first=not layers)
+            spec['act'] = _lib.ACT_RELU
+            layers.append(spec)
+            if nxt is not None and nxt - idx == 4:                   # conv, ReLU, MaxPool2d, Dropout
+                set_pool(spec, next_stride())
+            elif nxt is not None and nxt - idx != 2:
+                raise ValueError(f'unexpected module spacing in the VGG frontend at index {idx}')
+    for spec in layers:
+        if (spec['kh'], spec['kw']) != (3, 3):
+            raise ValueError('frontend convolutions must be 3x3')
+    if (sub_v is not None and cur_v != sub_v) or cur_h != sub_h:
+        raise ValueError(f'frontend subsampling ({cur_v}, {cur_h}) does not reach conv_subsampling {cfg["conv_subsampling"]}')
+    agg = _conv_spec(sd, 'encoder_frontend.aggregation_conv.0', first=False)
+    if agg['kh'] != line_height // cur_v or agg['kw'] != 1 or agg['cout'] != d_model:
+        raise ValueError('aggregation convolution does not match line height / subsampling / dim_model')
+    agg['pad_h'] = agg['pad_w'] = 0
+    agg['act'] = _lib.ACT_LEAKY_RELU
+    layers.append(agg)
+    layers.append(dict(kind=_lib.LN_PE, cin=d_model, norm1_w=sd['encoder.input_norm.weight'],
+                       norm1_b=sd['encoder.input_norm.bias']))
+    for i in range(int(cfg['encoder_layers'])):
+        p = f'encoder.trans_encoder.layers.{i}.'
+        layers.append(dict(
+            kind=_lib.TRANSFORMER_LAYER, cin=d_model, heads=heads, dim_ff=sd[p + 'linear1.weight'].shape[0],
+            in_proj_w=sd[p + 'self_attn.in_proj_weight'], in_proj_b=sd[p + 'self_attn.in_proj_bias'],
+            out_proj_w=sd[p + 'self_attn.out_proj.weight'], out_proj_b=sd[p + 'self_attn.out_proj.bias'],
+            lin1_w=sd[p + 'linear1.weight'], lin1_b=sd[p + 'linear1.bias'],
+            lin2_w=sd[p + 'linear2.weight'], lin2_b=sd[p + 'linear2.bias'],
+            norm1_w=sd[p + 'norm1.weight'], norm1_b=sd[p + 'norm1.bias'],
+            norm2_w=sd[p + 'norm2.weight'], norm2_b=sd[p + 'norm2.bias']))
+    if f'encoder.trans_encoder.layers.{int(cfg["encoder_layers"])}.linear1.weight' in sd:
+        raise ValueError('state dict has more encoder layers than the net config')
+    dec_layers = []
+    for i in range(int(cfg['decoder_layers'])):
+        p = f'trans_decoder.layers.{i}.'
+        dec_layers.append(dict(
+            self_in_w=sd[p + 'self_attn.in_proj_weight'], self_in_b=sd[p + 'self_attn.in_proj_bias'],
+            self_out_w=sd[p + 'self_attn.out_proj.weight'], self_out_b=sd[p + 'self_attn.out_proj.bias'],
+            cross_in_w=sd[p + 'multihead_attn.in_proj_weight'], cross_in_b=sd[p + 'multihead_attn.in_proj_bias'],
+            cross_out_w=sd[p + 'multihead_attn.out_proj.weight'], cross_out_b=sd[p + 'multihead_attn.out_proj.bias'],
+            lin1_w=sd[p + 'linear1.weight'], lin1_b=sd[p + 'linear1.bias'],
+            lin2_w=sd[p + 'linear2.weight'], lin2_b=sd[p + 'linear2.bias'],
+            norm1_w=sd[p + 'norm1.weight'], norm1_b=sd[p + 'norm1.bias'],
+            norm2_w=sd[p + 'norm2.weight'], norm2_b=sd[p + 'norm2.bias'],
+            norm3_w=sd[p + 'norm3.weight'], norm3_b=sd[p + 'norm3.bias']))
+    if f'trans_decoder.layers.{int(cfg["decoder_layers"])}.linear1.weight' in sd:
+        raise ValueError('state dict has more decoder layers than the net config')
+    for i, ly in enumerate(dec_layers):
+        if ly['lin1_w'].shape != (dim_ff, d_model) or ly['self_in_w'].shape != (3 * d_model, d_model):
+            raise ValueError(f'decoder layer {i}: parameter shapes do not match the net config')
+    classes = sd['dec_embeder.weight'].shape[0]
+    if sd['dec_out_proj.weight'].shape != (classes, d_model):
+        raise ValueError('dec_out_proj does not match dec_embeder')
+    decoder = dict(layers=dec_layers, heads=heads, dim_ff=dim_ff, classes=classes, d_model=d_model,
+                   embed=sd['dec_embeder.weight'], out_w=sd['dec_out_proj.weight'], out_b=sd['dec_out_proj.bias'])
+    return layers, decoder
+
+
+def ar_to_ctypes(decoder):
+    """Decoder spec of describe_transformer_ocr -> (ArDesc, keepalive list) for b200ocr_ar_attach."""
+    import ctypes as C
+    keep = []
+
+    def ptr(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_float))
+
+    arr = (_lib.ArLayer * len(decoder['layers']))()
+    for i, spec in enumerate(decoder['layers']):
+        for key, _ in _lib.ArLayer._fields_:
+            setattr(arr[i], key, ptr(spec[key]))
+    desc = _lib.ArDesc(len(decoder['layers']), int(decoder['heads']), int(decoder['dim_ff']), int(decoder['classes']),
+                       arr, ptr(decoder['embed']), ptr(decoder['out_w']), ptr(decoder['out_b']))
+    keep.append(arr)
+    return desc, keep
 
 
 def describe_parsenet(module):

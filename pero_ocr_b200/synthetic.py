@@ -217,3 +217,43 @@ def bench_crops(n, width=1280, seed=0, height=40):
     rng = np.random.default_rng(seed)
     g = rng.integers(0, 256, (n, height, width), dtype=np.uint8)
     return np.repeat(g[:, :, :, None], 3, axis=3)
+
+
+def transformer_ocr_state(encoder_net: "LineNetTransformer", decoder_state) -> "OrderedDict[str, torch.Tensor]":
+    """Re-keys the encoder half of a ``LineNetTransformer`` + a decoder state (reference names already:
+    ``trans_decoder.layers.i.*``, ``dec_embeder.weight``, ``dec_out_proj.*``) into the state dict of the reference's
+    ``TransformerOCR`` as ``transformer.build_net`` lays it out (``pero_ocr/ocr_engine/transformer.py:75-148,
+    335-385``): VGG convolutions directly in ``encoder_frontend.blocks_2d.blocks_2d`` (each followed by its ReLU, a
+    pool by a Dropout), the 256->512->512 block as a nested Sequential, then the BatchNorm.  This is the checkpoint
+    format ``TransformerEngineLineOCR`` loads (``transformer_ocr_engine.py:29``); tests/golden/transformer_ocr_keys.json
+    holds the key / shape list of the unmodified reference for it."""
+    src = encoder_net.state_dict()
+    convs = [k[:-len('.weight')] for k, v in src.items() if k.startswith('conv.') and k.endswith('.weight') and v.dim() == 4]
+    bn = [k[:-len('.running_mean')] for k in src if k.startswith('conv.') and k.endswith('.running_mean')]
+    assert len(convs) == len(VGG_FRONTEND) and len(bn) == 1
+    out = OrderedDict()
+    prefix = 'encoder_frontend.blocks_2d.blocks_2d.'
+    idx = 0
+    block = None
+    for name, (cin, cout, act, pool) in zip(convs, VGG_FRONTEND):
+        if act == 'relu':
+            dst = f'{prefix}{idx}'
+            idx += 4 if pool is not None else 2          # conv, ReLU (, MaxPool2d, Dropout)
+        else:
+            if block is None:
+                block = [idx, 0]
+            dst = f'{prefix}{block[0]}.{block[1]}'
+            block[1] += 2                                # conv, LeakyReLU inside create_vgg_block_2d
+        out[dst + '.weight'] = src[name + '.weight']
+        out[dst + '.bias'] = src[name + '.bias']
+    bn_dst = f'{prefix}{block[0] + 1}'
+    for leaf in ('weight', 'bias', 'running_mean', 'running_var', 'num_batches_tracked'):
+        out[f'{bn_dst}.{leaf}'] = src[f'{bn[0]}.{leaf}']
+    out['encoder_frontend.aggregation_conv.0.weight'] = src['agg.weight']
+    out['encoder_frontend.aggregation_conv.0.bias'] = src['agg.bias']
+    for k, v in src.items():
+        if k.startswith('trans_encoder.') or k.startswith('input_norm.'):
+            out['encoder.' + k] = v
+    for k, v in decoder_state.items():
+        out[k] = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))
+    return out

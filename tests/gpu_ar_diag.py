@@ -1,0 +1,69 @@
+"""Bring-up diagnostics + timing of the autoregressive decoder on a GPU box (not a test; uses the oracle as the
+checker).  `python -m tests.gpu_ar_diag [out.json]`: stage-wise errors against the reference golden (encoder memory,
+per-step logits) and the time of b200ocr_ar_transcribe on the golden batch and on a larger synthetic batch."""
+import json
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+from oracle import cases
+from tests.util import load_golden
+from tests.conftest import GOLDEN
+
+
+def main():
+    from pero_ocr_b200.transformer_engine import B200TransformerEngineLineOCR
+    out = {}
+    net, dec, sd = cases.ar_state_dict()
+    with tempfile.TemporaryDirectory() as tmp:
+        eng = B200TransformerEngineLineOCR(cases.write_ar_engine_json(tmp), torch.device('cuda', 0), state_dict=sd)
+    gold = load_golden(GOLDEN, 'ar_decoder.npz')
+    x = cases.ar_inputs()
+    try:
+        nhwc = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 3, 1))).cuda()
+        mem = eng.net.debug_forward_prefix(nhwc, 1 << 20)                        # [n][1][T][D]
+        with torch.no_grad():
+            xf = torch.from_numpy(x).float() / 255.0
+            y = net.agg_act(net.agg(net.conv(xf))).squeeze(2).permute(2, 0, 1)
+            ref_mem = net.trans_encoder(net.input_norm(y) + net.pe[:y.size(0)]).numpy()   # [T][n][D]
+        out['memory_max_abs_err'] = float(np.abs(mem[:, 0].transpose(1, 0, 2) - ref_mem).max())
+        out['memory_max_abs'] = float(np.abs(ref_mem).max())
+    except Exception as e:                                                        # noqa: BLE001
+        out['memory_error'] = repr(e)
+    t0 = time.perf_counter()
+    outs, logits = eng.transcribe_batch(x)
+    out['golden_batch_first_call_s'] = time.perf_counter() - t0
+    steps = min(logits.shape[1], gold['logits'].shape[1])
+    diff = np.abs(logits[:, :steps] - gold['logits'][:, :steps]).max(axis=2)     # [n][steps]
+    out['steps'] = [int(logits.shape[1]), int(gold['logits'].shape[1])]
+    out['logit_err_step0'] = diff[:, 0].tolist()
+    out['logit_err_step1'] = diff[:, 1].tolist() if steps > 1 else None
+    out['logit_err_max_per_line'] = diff.max(axis=1).tolist()
+    out['first_step_over_2e-3'] = [int(np.argmax(d > 2e-3)) if (d > 2e-3).any() else -1 for d in diff]
+    out['argmax_equal_steps'] = (logits[:, :steps].argmax(2) == gold['logits'][:, :steps].argmax(2)).sum(axis=1).tolist()
+    out['lengths'] = [[len(o) for o in outs], gold['lengths'].tolist()]
+    # timing: golden batch again (warm), then 64 lines x 1088 px
+    for name, n in (('n3', 3), ('n64', 64)):
+        rng = np.random.default_rng(5)
+        b = rng.integers(0, 256, (n, 3, 40, 1088), dtype=np.uint8) if n != 3 else x
+        eng.transcribe_batch(b, no_logits=True)
+        l0 = eng.net.launch_count
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o, _ = eng.transcribe_batch(b, no_logits=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[f'time_{name}'] = {'seconds': dt, 'lines_per_s': n / dt, 'launches': eng.net.launch_count - l0,
+                               'mean_len': float(np.mean([len(t) for t in o]))}
+    text = json.dumps(out, indent=1)
+    print(text)
+    if len(sys.argv) > 1:
+        with open(sys.argv[1], 'w') as f:
+            f.write(text)
+
+
+if __name__ == '__main__':
+    main()
