@@ -303,7 +303,8 @@ int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, i
 /* Route every implicit-GEMM layer through a naive one-thread-per-output CUDA-core kernel (same packed fp16
  * operands, fp32 accumulate) so the tcgen05 path can be checked on a GPU box where the reference is absent. */
 int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
-/* A/B switches for kernel variants (tests, profiling).  flag 1: halo-reuse 3x3 kernel for cin <= 128 (default on). */
+/* A/B switches for kernel variants (tests, profiling).  flag 1: halo-reuse 3x3 kernel for cin <= 128 (default on);
+ * flag 2: split-K kernel for the per-step projections of b200ocr_ar_transcribe (default on; 0 = one K walker per tile). */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

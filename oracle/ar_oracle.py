@@ -10,8 +10,8 @@ self-attention accumulate in a cache, keys / values of the encoder-decoder atten
 Pinned: tests/golden/ar_decoder.npz holds token sequences and logits produced by the UNMODIFIED reference classes
 (``transformer.build_net`` + ``TransformerEngineLineOCR.transcribe_batch``) hosting the seeded weights of
 ``ar_decoder_state`` / ``pero_ocr_b200.synthetic`` (oracle/make_golden.py: golden_ar_decoder); tests/test_oracle_ar.py
-checks this restatement against them.  The GPU implementation of this row is not built yet: this oracle is its
-parity reference for the next round.
+checks this restatement against them; tests/test_zz_gpu_ar_decoder.py checks the device path
+(b200ocr_ar_transcribe behind B200TransformerEngineLineOCR) against the same golden and against this oracle.
 """
 import math
 from collections import OrderedDict

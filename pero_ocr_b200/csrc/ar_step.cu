@@ -139,6 +139,97 @@ __global__ void __launch_bounds__(64) linear_f32_kernel(const float* __restrict_
     }
 }
 
+// Latency-oriented variant of the same contraction for the token loop, where M (lines in the batch) is small and the
+// K loop of the kernel above is a serial chain of global-load round trips: 256 threads = KG groups of 64, group g
+// takes the K chunks c = g (mod KG) into its own shared-memory tiles (64-thread named barriers), the next chunk's
+// global loads are issued into registers before the current chunk is multiplied, and the KG partial tiles are summed
+// in a fixed order (deterministic) by group 0 before the same epilogue.
+constexpr int LKG = 4;
+
+__device__ __forceinline__ void group_barrier(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(64) : "memory");
+}
+
+__global__ void __launch_bounds__(64 * LKG) linear_f32_splitk_kernel(const float* __restrict__ x, long ldx,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias,
+                                                                     const float* __restrict__ res, long ldr,
+                                                                     float* __restrict__ out, long ldo, int M, int O,
+                                                                     int K, int relu) {
+    __shared__ float xs[LKG][LBK][LLD];   // [group][k][m]; afterwards [group][m][o] partial sums
+    __shared__ float ws[LKG][LBK][LLD];   // [group][k][o]
+    const int m0 = blockIdx.y * LBM, o0 = blockIdx.x * LBN;
+    const int g = threadIdx.x >> 6, t = threadIdx.x & 63, tm = t >> 3, tn = t & 7;
+    const int chunks = K / LBK;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 xv[4], wv[4];
+    auto fetch = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + i * 64;
+            const int r = idx >> 3, k4 = (idx & 7) * 4;
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[i] = xv[i];
+            if (m0 + r < M) xv[i] = *reinterpret_cast<const float4*>(x + static_cast<long>(m0 + r) * ldx + c * LBK + k4);
+            if (o0 + r < O) wv[i] = *reinterpret_cast<const float4*>(w + static_cast<size_t>(o0 + r) * K + c * LBK + k4);
+        }
+    };
+    int c = g;
+    if (c < chunks) fetch(c);
+    for (; c < chunks; c += LKG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + i * 64;
+            const int r = idx >> 3, k4 = (idx & 7) * 4;
+            xs[g][k4 + 0][r] = xv[i].x; xs[g][k4 + 1][r] = xv[i].y; xs[g][k4 + 2][r] = xv[i].z; xs[g][k4 + 3][r] = xv[i].w;
+            ws[g][k4 + 0][r] = wv[i].x; ws[g][k4 + 1][r] = wv[i].y; ws[g][k4 + 2][r] = wv[i].z; ws[g][k4 + 3][r] = wv[i].w;
+        }
+        group_barrier(g);
+        if (c + LKG < chunks) fetch(c + LKG);      // in flight while this chunk is multiplied
+#pragma unroll 8
+        for (int k = 0; k < LBK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = xs[g][k][tm * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = ws[g][k][tn * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        group_barrier(g);
+    }
+    // partial tiles -> shared memory (each group's own region: its last reads are behind its last barrier)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xs[g][tm * 4 + i][tn * 4 + j] = acc[i][j];
+    __syncthreads();
+    if (g != 0) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + tm * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + tn * 4 + j;
+            if (o >= O) continue;
+            float v = xs[0][tm * 4 + i][tn * 4 + j];
+#pragma unroll
+            for (int q = 1; q < LKG; ++q) v += xs[q][tm * 4 + i][tn * 4 + j];
+            v += bias ? bias[o] : 0.f;
+            if (relu) v = fmaxf(v, 0.f);
+            if (res) v += res[static_cast<long>(m) * ldr + o];
+            out[static_cast<long>(m) * ldo + o] = v;
+        }
+    }
+}
+
 __device__ __forceinline__ bool score_better(float v, int i, float bv, int bi) {
     // torch.argmax: NaN counts as the maximum; among equal values the lowest index wins
     const bool vn = v != v, bn = bv != bv;
@@ -201,12 +292,15 @@ cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start
 }
 
 cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
-                              float* out, long ldo, int M, int O, int K, int relu, cudaStream_t stream) {
+                              float* out, long ldo, int M, int O, int K, int relu, int variant, cudaStream_t stream) {
     if (M <= 0 || O <= 0) return cudaSuccess;
     if (K <= 0 || (K % LBK) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
         return cudaErrorInvalidValue;
     const dim3 grid((O + LBN - 1) / LBN, (M + LBM - 1) / LBM);
-    linear_f32_kernel<<<grid, 64, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
+    if (variant == 1)
+        linear_f32_splitk_kernel<<<grid, 64 * LKG, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
+    else
+        linear_f32_kernel<<<grid, 64, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
     return cudaGetLastError();
 }
 

@@ -82,6 +82,7 @@ struct ArLayer {
 
 struct ArState {
     bool attached = false;
+    int linear_variant = 1;   // launch_linear_f32 variant of the token loop: split-K (b200ocr_debug_set_flag 2, 0 = tiled)
     int heads = 0, dim_ff = 0, classes = 0, D = 0;
     std::vector<ArLayer> layers;
     float *embed = nullptr, *out_w = nullptr, *out_b = nullptr;
@@ -1100,28 +1101,28 @@ int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, 
             float* kv_s = kv + static_cast<size_t>(s) * n * 2 * D;
             const float* mkv = ar.memkv + i * memkv_layer;                  // row (line * T + t) * 2D
             // cached self-attention over positions 0..s (DecoderLayer.infer, transformer.py:431-435)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, ar.linear_variant, st));
             AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w + static_cast<size_t>(D) * D, ly.self_in_b + D, nullptr, 0,
-                                        kv_s, 2 * D, n, 2 * D, D, 0, st));
+                                        kv_s, 2 * D, n, 2 * D, D, 0, ar.linear_variant, st));
             AR_LAUNCH(launch_step_attention(ar.q, D, kv, kv + D, static_cast<long>(n) * 2 * D, 2 * D, n, s + 1, D,
                                             ar.heads, ar.a, st));
-            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.self_out_w, ly.self_out_b, ar.x, D, ar.t, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.self_out_w, ly.self_out_b, ar.x, D, ar.t, D, n, D, D, 0, ar.linear_variant, st));
             AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n1w, ly.n1b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
             // encoder-decoder attention over the T memory frames (:438-447)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, ar.linear_variant, st));
             AR_LAUNCH(launch_step_attention(ar.q, D, mkv, mkv + D, 2 * D, static_cast<long>(T) * 2 * D, n, T, D, ar.heads,
                                             ar.a, st));
-            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.cross_out_w, ly.cross_out_b, ar.x, D, ar.t, D, n, D, D, 0, st));
+            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.cross_out_w, ly.cross_out_b, ar.x, D, ar.t, D, n, D, D, 0, ar.linear_variant, st));
             AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n2w, ly.n2b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
             // feed-forward (:449-450)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, st));
-            AR_LAUNCH(launch_linear_f32(ar.f, FF, ly.l2w, ly.l2b, ar.x, D, ar.t, D, n, D, FF, 0, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, ar.linear_variant, st));
+            AR_LAUNCH(launch_linear_f32(ar.f, FF, ly.l2w, ly.l2b, ar.x, D, ar.t, D, n, D, FF, 0, ar.linear_variant, st));
             AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n3w, ly.n3b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
         }
         // dec_out_proj + argmax + alive mask (transformer_ocr_engine.py:69-75)
         float* lg = logits ? logits + static_cast<size_t>(s) * C : ar.lg;
         const long lg_ld = logits ? static_cast<long>(max_steps) * C : C;
-        AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, st));
+        AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, ar.linear_variant, st));
         AR_LAUNCH(launch_argmax_alive(lg, lg_ld, n, C, start_token, s, tokens + static_cast<size_t>(s) * n, ar.alive,
                                       ar.state, st));
         if ((s + 1) % check_every == 0 || s + 1 == max_steps) {
@@ -1165,6 +1166,7 @@ int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, i
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     if (!e) return B200OCR_E_INVALID;
     if (flag == 1) e->use_halo = value != 0;
+    else if (flag == 2) e->ar.linear_variant = value != 0 ? 1 : 0;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

@@ -38,8 +38,9 @@ size_t force_align_workspace_bytes(int n, int t_max, int l_max);
 cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start_token, int n, int d, int pos,
                             float* out, cudaStream_t stream);
 // out[m][o] = act(x[m][:] . w[o][:] + bias[o]) (+ res[m][o]); fp32, w = Linear weight [O][K], K % 32 == 0.
+// variant 0: one 64-thread group walks K; 1: four groups split K (register prefetch, fixed-order reduction).
 cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
-                              float* out, long ldo, int M, int O, int K, int relu, cudaStream_t stream);
+                              float* out, long ldo, int M, int O, int K, int relu, int variant, cudaStream_t stream);
 // one query position per (line, head) against S key / value positions (position p of line l at + p*ps + l*ls).
 cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
                                   int S, int d, int heads, float* out, cudaStream_t stream);

@@ -36,6 +36,9 @@ class ARLineRecognizer(LineRecognizer):
         del keep
         self.num_classes = int(decoder['classes'])
         self._ar_reserved = (0, 0, 0)
+        import os
+        if os.environ.get('B200OCR_AR_LINEAR'):        # bring-up override: A/B of the step-projection kernels
+            self.set_flag(2, int(os.environ['B200OCR_AR_LINEAR']))
 
     def reserve_ar(self, max_lines, max_width, max_steps):
         r = self._ar_reserved

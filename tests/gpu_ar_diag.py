@@ -45,19 +45,46 @@ def main():
     out['first_step_over_2e-3'] = [int(np.argmax(d > 2e-3)) if (d > 2e-3).any() else -1 for d in diff]
     out['argmax_equal_steps'] = (logits[:, :steps].argmax(2) == gold['logits'][:, :steps].argmax(2)).sum(axis=1).tolist()
     out['lengths'] = [[len(o) for o in outs], gold['lengths'].tolist()]
-    # timing: golden batch again (warm), then 64 lines x 1088 px
-    for name, n in (('n3', 3), ('n64', 64)):
-        rng = np.random.default_rng(5)
-        b = rng.integers(0, 256, (n, 3, 40, 1088), dtype=np.uint8) if n != 3 else x
-        eng.transcribe_batch(b, no_logits=True)
-        l0 = eng.net.launch_count
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        o, _ = eng.transcribe_batch(b, no_logits=True)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        out[f'time_{name}'] = {'seconds': dt, 'lines_per_s': n / dt, 'launches': eng.net.launch_count - l0,
-                               'mean_len': float(np.mean([len(t) for t in o]))}
+    # the split-K variant of the step projections (b200ocr_debug_set_flag 2): same checks against the golden
+    eng.net.set_flag(2, 1)
+    outs_v, logits_v = eng.transcribe_batch(x)
+    steps_v = min(logits_v.shape[1], gold['logits'].shape[1])
+    diff_v = np.abs(logits_v[:, :steps_v] - gold['logits'][:, :steps_v]).max(axis=2)
+    out['splitk'] = {
+        'steps': int(logits_v.shape[1]), 'logit_err_max_per_line': diff_v.max(axis=1).tolist(),
+        'argmax_equal_steps': (logits_v[:, :steps_v].argmax(2) == gold['logits'][:, :steps_v].argmax(2)).sum(axis=1).tolist(),
+        'lengths': [len(o) for o in outs_v],
+        'tokens_equal_default': bool(all(np.array_equal(a, b) for a, b in zip(outs, outs_v))),
+        'max_abs_diff_to_default': float(np.abs(logits_v[:, :steps] - logits[:, :steps]).max()) if logits_v.shape == logits.shape else None}
+    # timing of both variants, crops resident on the device: golden batch (warm), 64 and 256 lines x 1088 px
+    sb = cases.AR_CASE['classes'] - 2
+    for variant in (0, 1):
+        eng.net.set_flag(2, variant)
+        for name, n in (('n3', 3), ('n64', 64), ('n256', 256)):
+            rng = np.random.default_rng(5)
+            b = rng.integers(0, 256, (n, 3, 40, 1088), dtype=np.uint8) if n != 3 else x
+            dev = torch.from_numpy(np.ascontiguousarray(b.transpose(0, 2, 3, 1))).cuda()
+            eng.net.transcribe(dev, sb, want_logits=False)
+            l0 = eng.net.launch_count
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, _, k = eng.net.transcribe(dev, sb, want_logits=False)      # synchronises (returns the step count)
+            dt = time.perf_counter() - t0
+            out[f'time_v{variant}_{name}'] = {'seconds': dt, 'lines_per_s': n / dt, 'steps': k,
+                                             'ms_per_step': 1e3 * dt / k, 'launches': eng.net.launch_count - l0}
+    # the same work on the host cores: torch-CPU encoder + NumPy decoder loop of the oracle (golden batch, 3 lines)
+    from oracle.ar_oracle import greedy_transcribe
+    sb = cases.AR_CASE['classes'] - 2
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        xf = torch.from_numpy(x).float() / 255.0
+        y = net.agg_act(net.agg(net.conv(xf))).squeeze(2).permute(2, 0, 1)
+        m = net.trans_encoder(net.input_norm(y) + net.pe[:y.size(0)]).numpy()
+    t1 = time.perf_counter()
+    greedy_transcribe(m, dec, cases.AR_CASE['decoder_layers'], 8, sb, x.shape[3])
+    t2 = time.perf_counter()
+    out['cpu_oracle_n3'] = {'encoder_s': t1 - t0, 'decoder_s': t2 - t1, 'lines_per_s': 3 / (t2 - t0),
+                            'threads': torch.get_num_threads()}
     text = json.dumps(out, indent=1)
     print(text)
     if len(sys.argv) > 1:

@@ -1,6 +1,6 @@
 """CPU: oracle/ar_oracle.py (restatement of the reference's autoregressive Transformer decoding)
 against the output of the unmodified TransformerEngineLineOCR.transcribe_batch stored in tests/golden/ar_decoder.npz.
-The GPU implementation of this row is not built yet; this pins its parity reference."""
+This pins the parity reference of the device path (tests/test_zz_gpu_ar_decoder.py)."""
 import numpy as np
 import torch
 
