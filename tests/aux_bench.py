@@ -197,11 +197,78 @@ def bench_config3(peak):
             'hypotheses_per_line': float(np.mean([len(b) for b in bags]))}
 
 
+def bench_config4(peak, pages=16):
+    """BASELINE config 4: synthetic 4000x3000 pages through the ParseNet forward (conv-only stand-in, DOWNSAMPLE = 4 ->
+    net input [1,3,768,1024]) + line OCR of an injected fixed layout of 60 baselines per page (random-init
+    maps give arbitrary line counts, so the layout is fixed), the lines cropped on the device from the uploaded page
+    (process_baselines: polynomial fit on the host, maps + resampling + recogniser on the GPU).  The CPU geometry
+    between the two (cnn_layout_engine.py, shapely) is outside the path and not timed."""
+    import tempfile
+    from pero_ocr_b200 import synthetic
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    from pero_ocr_b200.parsenet import B200ParseNet
+    dev = torch.device('cuda', 0)
+    pn = B200ParseNet(None, dev, downsample=4, adaptive_downsample=False, module=synthetic.make_net('parsenet', seed=1))
+    net = synthetic.make_net('lstm', 120, seed=0, out_gain=2.5)
+    tmp = tempfile.mkdtemp()
+    js = os.path.join(tmp, 'ocr.json')
+    with open(js, 'w', encoding='utf8') as f:
+        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'unused.pt',
+                   'characters': synthetic.json_characters(118), 'net_name': 'B200_AUX'}, f)
+    eng = B200EngineLineOCR(js, dev, batch_size=8, module=net)
+    eng.max_input_horizontal_pixels = 64 * 1408
+    cropper = B200LineCropper(line_height=40, poly=2, scale=1)
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8) for _ in range(2)]     # alternated: 36 MB each
+    lines = []
+    for i in range(60):
+        y = 60 + i * 48
+        lines.append(([[100, y], [1400, y + rng.integers(-6, 7)], [2700, y + rng.integers(-6, 7)]], [26, 14]))
+    t = {'parsenet': 0.0, 'upload': 0.0, 'ocr': 0.0}
+
+    def one_page(img):
+        t0 = time.perf_counter()
+        maps = pn.get_maps(img, 4)                      # INTER_AREA resize on the host + conv forward + D2H of 5 maps
+        t1 = time.perf_counter()
+        page = DevicePage(img)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        tr, _, _ = eng.process_baselines(page, lines, cropper, no_logits=True)
+        t3 = time.perf_counter()
+        t['parsenet'] += t1 - t0; t['upload'] += t2 - t1; t['ocr'] += t3 - t2
+        return maps.shape, len(tr)
+
+    one_page(imgs[0])
+    one_page(imgs[1])
+    for k in t:
+        t[k] = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(pages):
+        shape, n_lines = one_page(imgs[i & 1])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # device time of the two forwards alone
+    canvas = np.zeros((1, 768, 1024, 3), dtype=np.uint8)
+    canvas[0, :750, :1000] = imgs[0][::4, ::4][:750, :1000]
+    pn_ms = timed(lambda: pn.net(canvas), reps=5)
+    return {'op': 'config 4: page pipeline (ParseNet forward + device cropper + line OCR)',
+            'workload': f'{pages} synthetic 3000x4000 pages, ParseNet stand-in at downsample 4 (maps {list(shape)}), '
+                        f'{n_lines} injected baselines per page -> 40 x ~1300 px crops, CNN+BiLSTM recogniser',
+            'pages_per_s': pages / dt, 'lines_per_s': pages * n_lines / dt, 'ms_per_page': 1e3 * dt / pages,
+            'ms_per_page_parsenet_get_maps (host resize + upload + conv forward + D2H)': 1e3 * t['parsenet'] / pages,
+            'ms_per_page_parsenet_forward_incl_canvas_upload': pn_ms,
+            'ms_per_page_upload_page_image': 1e3 * t['upload'] / pages,
+            'ms_per_page_crop_and_ocr (process_baselines)': 1e3 * t['ocr'] / pages}
+
+
 def main():
     assert torch.cuda.is_available()
     peak = hbm_peak()
-    for fn in (bench_cropper, bench_sparsify, bench_align, bench_config3):
-        print(json.dumps(fn(peak)), flush=True)
+    benches = {'cropper': bench_cropper, 'sparsify': bench_sparsify, 'align': bench_align, 'config3': bench_config3,
+               'config4': bench_config4}
+    for name in (sys.argv[1:] or list(benches)):             # e.g. `python -m tests.aux_bench config4`
+        print(json.dumps(benches[name](peak)), flush=True)
 
 
 if __name__ == '__main__':
