@@ -11,6 +11,7 @@
 //                      through the tcgen05 kernel instead (engine.cu)
 //   * argmax_alive:    torch.argmax over the classes (first maximum) + alive-mask update + stop detection
 //                      (transformer_ocr_engine.py:72-77)
+#include "once.cuh"
 #include "kernels.cuh"
 
 #include <math.h>
@@ -326,11 +327,11 @@ cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, con
     const int warps = 4;
     const size_t smem = static_cast<size_t>(warps) * (S + 128) * sizeof(float);
     if (smem > 160 * 1024) return cudaErrorInvalidValue;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(step_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.mark();
     }
     const int units = n * heads;
     step_attention_kernel<<<(units + warps - 1) / warps, warps * 32, smem, stream>>>(q, q_ls, k, v, ps, ls, n, S, d, heads,

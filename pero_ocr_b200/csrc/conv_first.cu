@@ -15,6 +15,7 @@
 //     (16-byte chunks XOR-swizzled by pixel: conflict-free fragment writes and conflict-free record reads) ->
 //     fully coalesced 16-byte stores.  The kernel is bound by that store stream (the 64-channel hi|lo records of
 //     a 256 x 40 x 1344 batch are 3.5 GB).
+#include "once.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -213,12 +214,12 @@ cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const 
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
     const size_t dyn = static_cast<size_t>(CFM_PX) * planes * cout * sizeof(__half);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaFuncSetAttribute(conv_first_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(conv_first_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(conv_first_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     const uint2* wf = reinterpret_cast<const uint2*>(wfrag);
     switch (cout) {

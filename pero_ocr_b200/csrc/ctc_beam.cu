@@ -8,6 +8,7 @@
 //   compute_Pb (:207-208), top_k (multisort.py:4-15) -> k rounds of block arg-max (ties: lower flat index)
 //   find_new_prefixes (:116-131)       -> new trie nodes
 // and BagOfHypotheses.sort (bag_of_hypotheses.py:19-20) for the output order.
+#include "once.cuh"
 #include "ctc_beam.cuh"
 
 #include <math.h>
@@ -446,11 +447,11 @@ cudaError_t launch_ctc_prefix_beam(const double* logprobs, int n, int t, int c, 
     int* ws_parent = static_cast<int*>(workspace);
     int* ws_char = ws_parent + static_cast<size_t>(n) * nodes;
     const size_t dyn = dyn_bytes(c, k);
-    static bool attr_done = false;   // static + dynamic shared memory exceeds the 48 KB default already at k = 16, c = 120
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;   // static + dynamic shared memory exceeds the 48 KB default already at k = 16, c = 120
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.mark();
     }
     prefix_beam_kernel<<<n, kThreads, dyn, stream>>>(logprobs, t, c, k, out_labels, out_lengths, out_scores, status,
                                                      ws_parent, ws_char, nodes, t_lo, t_hi);

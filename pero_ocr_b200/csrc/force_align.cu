@@ -16,6 +16,7 @@
 //     the transcription or an empty transcription -> status 2 (:41-43, :64-68);
 //   * align_text (:152-165): for every character the frame, among those aligned to it, with the largest per-frame
 //     maximum probability (first such frame).
+#include "once.cuh"
 #include "kernels.cuh"
 
 #include <math.h>
@@ -170,11 +171,11 @@ cudaError_t launch_force_align(const void* neg, int is_f64, int n, int t_max, in
     const size_t S = 2 * static_cast<size_t>(l_max) + 1;
     const size_t dyn = sizeof(double) * (2 * S > static_cast<size_t>(t_max) ? 2 * S : static_cast<size_t>(t_max));
     if (dyn > 200 * 1024) return cudaErrorInvalidValue;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaFuncSetAttribute(force_align_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(force_align_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     if (is_f64)
         force_align_kernel<double><<<n, FA_THREADS, dyn, stream>>>(static_cast<const double*>(neg), t_max, C, n_frames,

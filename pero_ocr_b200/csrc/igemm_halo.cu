@@ -10,6 +10,7 @@
 // plus one shuffle.
 //
 // Warps: 0 = halo (A) producer, 1 = weight (B) producer, 2 = MMA issuer, 3-10 = epilogue (two per TMEM lane quarter).
+#include "once.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -313,12 +314,12 @@ template <int BN, int FMT>
 cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                       cudaStream_t stream) {
     using C = Cfg<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.mark();
     }
     const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float) + C::kEpiStageBytes;
     if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;

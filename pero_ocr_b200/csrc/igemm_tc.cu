@@ -12,6 +12,7 @@
 //              fused CTC epilogue (per-frame argmax / max / logsumexp; logits optional)
 // A tile is 4 segments of 32 output pixels (th x 32/th); segment q feeds TMEM lanes [32q, 32q+32), so a 2x2 or
 // 2x1 max-pool never leaves the warp.
+#include "once.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -398,12 +399,12 @@ template <int BN, int FMT>
 cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                       cudaStream_t stream) {
     using C = Cfg<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.mark();
     }
     const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float);
     if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;

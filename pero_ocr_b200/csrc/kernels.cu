@@ -1,4 +1,5 @@
 // Non-GEMM kernels of the line-recognition path (sm_100a) + CUDA-core cross-check kernels.
+#include "once.cuh"
 #include "kernels.cuh"
 #include "igemm.cuh"
 
@@ -574,12 +575,12 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
     const int grid = n * ((h + CF_ROWS - 1) / CF_ROWS) * tiles_w;
     const size_t dyn = static_cast<size_t>(CF_PX) * planes * cout * sizeof(__half);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaFuncSetAttribute(conv_first_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(conv_first_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(conv_first_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     switch (cout) {
         case 64: conv_first_kernel<64><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
@@ -648,11 +649,11 @@ cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, _
     const int dh = D / heads;
     if (dh == FA_T && heads * dh == D) {
         const size_t smem = 4 * static_cast<size_t>(FA_T) * FA_LD * sizeof(float);
-        static bool fa_attr = false;
-        if (!fa_attr) {
+        static PerDeviceOnce fa_attr;
+        if (fa_attr.pending()) {
             cudaError_t e = cudaFuncSetAttribute(attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) return e;
-            fa_attr = true;
+            fa_attr.mark();
         }
         attention_tiled_kernel<<<dim3(n * heads, (T + FA_T - 1) / FA_T), 128, smem, stream>>>(qkv, n, T, D, heads, out, fmt);
         return cudaGetLastError();
@@ -660,13 +661,13 @@ cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, _
     const int warps = 8;
     const size_t smem_kv = (2 * static_cast<size_t>(T) * (dh + 1) + static_cast<size_t>(warps) * T) * sizeof(float);
     const size_t smem_p = static_cast<size_t>(warps) * T * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.mark();
     }
     if (smem_kv <= 220 * 1024)
         attention_kernel<true><<<n * heads, warps * 32, smem_kv, stream>>>(qkv, n, T, D, heads, out, fmt);

@@ -21,6 +21,7 @@
 // One CTA per line.  Phase 0: per-frame max and sum (thread per frame).  Phase 1: thread per class scans the frames
 // (coalesced across classes) and counts kept entries; an exclusive scan over classes gives indptr.  A one-CTA scan
 // over lines gives base.  Phase 2 repeats the scan of phase 1 and writes entries at base + indptr.
+#include "once.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -186,11 +187,11 @@ cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int3
     if (n <= 0) return cudaSuccess;
     const size_t dyn = (2 * static_cast<size_t>(T) + C) * sizeof(float);
     if (dyn > 200 * 1024) return cudaErrorInvalidValue;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
         cudaFuncSetAttribute(sparsify_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(sparsify_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     sparsify_count_kernel<<<n, SP_THREADS, dyn, stream>>>(logits, T, C, t_lo, t_hi, indptr, nnz);
     sparsify_scan_kernel<<<1, 32, 0, stream>>>(nnz, n, base);
