@@ -55,6 +55,15 @@ def test_find_best_overlap_and_levenshtein_match_reference(golden_dir):
     assert levenshtein_distance([], list('abc')) == 3 and levenshtein_distance(list('abc'), []) == 3
 
 
+@pytest.mark.parametrize('a, b, want', [
+    # the reference's known answers for levenshtein_distance (test/test_sequence_alignment.py:9-48)
+    ([1], [1], 0), ([1], [2], 1), ([1], [2, 1], 1), ([1, 2], [1], 1), ([1, 2, 3], [1, -1, -2, 3], 2),
+    ([1, -1, -2, 3], [1, 2, 3], 2), ([1, 2, 3], [], 3), ([], [1, 2, 3], 3)])
+def test_levenshtein_distance_reference_known_answers(a, b, want):
+    from pero_ocr_b200.transformer_engine import levenshtein_distance
+    assert levenshtein_distance(a, b) == want
+
+
 def test_postprocess_decoded_matches_oracle():
     from oracle.ar_oracle import postprocess_decoded as oracle_pp
     from pero_ocr_b200.transformer_engine import postprocess_decoded
