@@ -124,3 +124,27 @@ def test_threaded_batch_padding_is_equivalent():
     assert outs[0][0] == outs[1][0] and outs[0][2] == outs[1][2]
     for a, b in zip(outs[0][1], outs[1][1]):
         assert np.array_equal(a, b)
+
+
+def test_process_lines_edge_cases_follow_the_reference():
+    """Empty input -> three empty lists; a zero-width crop divides by zero in the batch-size computation exactly as
+    in the reference (line_ocr_engine.py:84: `max_input_horizontal_pixels // max_width`); a 1-px line is one batch."""
+    eng = _host_only_engine('lstm')
+    assert eng.process_lines([]) == ([], [], [])
+    with pytest.raises(ZeroDivisionError):
+        eng.process_lines([np.zeros((40, 0, 3), dtype=np.uint8)])
+    tr, lg, co = eng.process_lines([np.zeros((40, 1, 3), dtype=np.uint8)], sparse_logits=False)
+    assert len(tr) == 1 and lg[0].shape[0] == (32 + 64) // 4 and co[0] == [8, 8]
+    with pytest.raises(ValueError):
+        eng.process_lines([np.zeros((39, 50, 3), dtype=np.uint8)])
+
+
+def test_ar_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from pero_ocr_b200 import B200Error, netdesc
+    from pero_ocr_b200.transformer_engine import ARLineRecognizer
+    net, dec, sd = cases.ar_state_dict()
+    layers, decoder = netdesc.describe_transformer_ocr(sd, cases.AR_NET_CONFIG, 40)
+    with pytest.raises(B200Error):
+        ARLineRecognizer(layers, decoder)
