@@ -178,7 +178,7 @@ def ar_host_fake_run_ocr(characters):
     import zlib
     block, classes = AR_HOST_CASE['block'], AR_HOST_CASE['classes']
 
-    def run_ocr(batch_data):
+    def run_ocr(batch_data, no_logits=False):
         texts, logits = [], []
         longest = 0
         for line in batch_data:
@@ -193,5 +193,5 @@ def ar_host_fake_run_ocr(characters):
         for t in texts:
             rng = np.random.default_rng(zlib.crc32(t.encode('utf8')))
             logits.append((rng.standard_normal((longest + 3, classes)) * 4).astype(np.float32))
-        return texts, np.stack(logits)
+        return texts, (None if no_logits else np.stack(logits))
     return run_ocr

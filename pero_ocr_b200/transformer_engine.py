@@ -247,7 +247,11 @@ class B200TransformerEngineLineOCR:
                 print(f'WARNING: Line too long for OCR engine. Cropping from {batch_data.shape[2]} px down to '
                       f'{self.max_input_horizontal_pixels}.')
                 batch_data = batch_data[:, :, :self.max_input_horizontal_pixels]
-            out_transcriptions, out_logits = self.run_ocr(batch_data)
+            if no_logits:            # the logits are only sliced along the text by the merge: skip computing / copying them
+                out_transcriptions, _ = self.run_ocr(batch_data, no_logits=True)
+                out_logits = [np.zeros((len(t), 0), dtype=np.float32) for t in out_transcriptions]
+            else:
+                out_transcriptions, out_logits = self.run_ocr(batch_data)
             merged_transcriptions, merged_logits = [], []
             start = 0
             for span in spans:
