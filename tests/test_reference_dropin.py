@@ -70,3 +70,40 @@ def test_engine_object_drops_into_the_unmodified_page_parser(tmp_path):
         np.testing.assert_allclose(a.logits.data, b.logits.data, atol=2e-5)
         np.testing.assert_allclose(a.get_full_logprobs(), b.get_full_logprobs(), atol=2e-5)
         assert abs(a.transcription_confidence - b.transcription_confidence) <= 1e-5
+
+
+def test_parsenet_host_logic_matches_the_unmodified_torch_parsenet(tmp_path):
+    """B5 seam: B200ParseNet's host side -- INTER_AREA downscale, x64 canvas, crop back, the adaptive
+    second pass and its `last_downsample` state (torch_parsenet.py:37-93) -- against the unmodified TorchParseNet, both
+    around the same deterministic stand-in for the conv forward."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from pero_ocr.layout_engines.torch_parsenet import TorchParseNet
+    from pero_ocr_b200.parsenet import B200ParseNet
+    ck = os.path.join(str(tmp_path), 'pn.pt')
+    torch.jit.script(make_case_net('lstm').agg_act).save(ck + '.cpu')          # any loadable blob: replaced below
+
+    def fake(x):                       # f32 [1,3,H,W] in [0,1] -> ([1,5,H,W], aux); line height 30 px, lines where bright
+        g = x.mean(dim=1, keepdim=True)
+        return torch.cat([g * 0 + 30.0, g * 0 + 5.0, (g > 0.45).float(), g, 1 - g], dim=1), None
+
+    ref = TorchParseNet(ck, torch.device('cpu'), downsample=2, max_mp=5, detection_threshold=0.2)
+    ref.net = fake
+    ours = B200ParseNet.__new__(B200ParseNet)                                  # host logic only: no device here
+    for name in ('max_megapixels', 'detection_threshold', 'adaptive_downsample', 'init_downsample', 'last_downsample',
+                 'downsample_line_pixel_adapt_threshold', 'min_line_processing_height', 'max_line_processing_height',
+                 'optimal_line_processing_height', 'min_downsample', 'max_downsample'):
+        setattr(ours, name, getattr(ref, name))
+    ours.net = lambda canvas: fake(torch.from_numpy(canvas).float().permute(0, 3, 1, 2) * (1 / 255.))[0]
+    rng = np.random.default_rng(3)
+    for shape in ((333, 517, 3), (640, 256, 3), (100, 90, 3)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want_map, want_ds = ref.get_maps_with_optimal_resolution(img)
+            plain = ref.get_maps(img, 3)
+        got_map, got_ds = ours.get_maps_with_optimal_resolution(img)
+        assert got_ds == want_ds and ours.last_downsample == ref.last_downsample
+        assert got_map.shape == want_map.shape and np.array_equal(got_map, want_map)
+        assert np.array_equal(ours.get_maps(img, 3), plain)
+        assert ours.get_med_height(got_map) == ref.get_med_height(want_map)
+    assert ref.last_downsample != 2                        # the adaptive second pass did run and moved the state
