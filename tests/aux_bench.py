@@ -262,11 +262,61 @@ def bench_config4(peak, pages=16):
             'ms_per_page_crop_and_ocr (process_baselines)': 1e3 * t['ocr'] / pages}
 
 
+def bench_incumbent(peak, steps=10):
+    """The reference's own GPU path as the incumbent: what PytorchEngineLineOCR(json, cuda).run_ocr
+    executes on a 256 x 40 x 1344 batch -- H2D of the uint8 batch, `/255`, NHWC -> NCHW, the module in PyTorch eager
+    (cuDNN convolutions with TF32 allowed: torch's default, cuDNN LSTM, cuBLAS), greedy_decode_ctc's tensor part and its
+    `.cpu()` (pytorch_ocr_engine.py:13-34, 59-74) -- restated here around the same seeded nn.Module, because the
+    reference package itself cannot travel to the GPU box.  Library code on purpose: this is the baseline, not the
+    product.  `with_logits` adds run_ocr's second result (the [N,C,T] -> [N,T,C] logits download, :72)."""
+    from pero_ocr_b200 import synthetic
+    net = synthetic.make_net('lstm', 120, seed=0, out_gain=2.5).cuda()
+    crops = synthetic.bench_crops(256, 1280, seed=0)
+    batch = np.zeros((256, 40, 1344, 3), dtype=np.uint8)
+    batch[:, :, 32:32 + 1280] = crops
+    host = torch.from_numpy(batch).pin_memory()
+    chars = synthetic.json_characters(118) + ['\u200b']
+
+    def run_ocr(with_logits):
+        with torch.no_grad():
+            x = host.to('cuda', non_blocking=True).float()
+            x /= 255.0
+            logits = net(x.permute(0, 3, 1, 2))                                   # [N,C,T]
+            sp = torch.cat((logits[:, :, 0:1], logits), dim=2)                    # greedy_decode_ctc, :19-27
+            sp[:, :, 0] = -1000
+            sp[:, -1, 0] = 1000
+            best = torch.argmax(sp, 1) + 1
+            mask = best[:, :-1] == best[:, 1:]
+            best = best[:, 1:]
+            best[mask] = 0
+            best[best == sp.shape[1]] = 0
+            best = best.cpu().numpy() - 1
+            out = [''.join(chars[c] for c in line[np.nonzero(line >= 0)]) for line in best]
+            lg = logits.permute(0, 2, 1).cpu().numpy() if with_logits else None
+        return out, lg
+
+    res = {}
+    for name, with_logits in (('no_logits', False), ('with_logits', True)):
+        for _ in range(3):
+            run_ocr(with_logits)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run_ocr(with_logits)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res[name] = {'lines_per_s': 256 * steps / dt, 'ms_per_256_lines': 1e3 * dt / steps}
+    return {'op': 'incumbent: the reference\'s GPU path (PyTorch eager run_ocr on the same net, cuDNN/cuBLAS)',
+            'workload': 'config 2: 256 x 40 x 1344 uint8 batch from pinned host memory per step',
+            'torch': torch.__version__, 'cudnn_allow_tf32': bool(torch.backends.cudnn.allow_tf32),
+            'matmul_allow_tf32': bool(torch.backends.cuda.matmul.allow_tf32), **res}
+
+
 def main():
     assert torch.cuda.is_available()
     peak = hbm_peak()
     benches = {'cropper': bench_cropper, 'sparsify': bench_sparsify, 'align': bench_align, 'config3': bench_config3,
-               'config4': bench_config4}
+               'config4': bench_config4, 'incumbent': bench_incumbent}
     for name in (sys.argv[1:] or list(benches)):             # e.g. `python -m tests.aux_bench config4`
         print(json.dumps(benches[name](peak)), flush=True)
 
