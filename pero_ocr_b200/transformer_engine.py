@@ -221,25 +221,23 @@ class B200TransformerEngineLineOCR:
             max_width = min(max_width, self.max_line_width + 2 * pad)
             batch_size = int(max(1, self.max_input_horizontal_pixels // max_width))
             batch_line_ids, line_ids = line_ids[:batch_size], line_ids[batch_size:]
-            overlap = self.max_line_width // 4
+            # lines wider than max_line_width become windows of that width advancing by three quarters of it; the last
+            # window is the first one that reaches the end of the line (line_ocr_engine.py:95-117)
+            window = self.max_line_width
+            stride = window - window // 4
             batch_images, spans = [], []
             for i in batch_line_ids:
                 image = lines[i]
                 if image.shape[0] != self.line_px_height or image.ndim != 3 or image.shape[2] != 3:
                     raise ValueError(f'line crops must be [{self.line_px_height}, w, 3] uint8, got {image.shape}')
-                if image.shape[1] > self.max_line_width:
-                    parts = []
-                    start, end = 0, self.max_line_width
-                    while end < image.shape[1]:
-                        parts.append(image[:, start:end, :])
-                        start += self.max_line_width - overlap
-                        end += self.max_line_width - overlap
-                    parts.append(image[:, start:end, :])
-                    batch_images += parts
-                    spans.append(len(parts))
+                starts = [0]
+                if image.shape[1] > window:
+                    while starts[-1] + window < image.shape[1]:
+                        starts.append(starts[-1] + stride)
+                    batch_images += [image[:, s:s + window, :] for s in starts]
                 else:
                     batch_images.append(image)
-                    spans.append(1)
+                spans.append(len(starts))
             batch_data = np.zeros([len(batch_images), self.line_px_height, int(max_width) + 2 * pad, 3], dtype=np.uint8)
             for data, image in zip(batch_data, batch_images):
                 data[:, pad:pad + image.shape[1], :] = image
