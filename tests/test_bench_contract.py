@@ -22,3 +22,15 @@ def test_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']
+
+
+def test_product_arm_fails_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device the default arm exits non-zero and prints no result line."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '3'],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode != 0
+    assert not [l for l in proc.stdout.splitlines() if l.strip().startswith('{')], proc.stdout
