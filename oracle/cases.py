@@ -117,39 +117,49 @@ def parsenet_image():
 
 # autoregressive Transformer decoding: seeded encoder (pero_ocr_b200/synthetic.py) + seeded decoder
 # (oracle/ar_oracle.py); classes = symbols + sentence boundary + ignore symbol (transformer_ocr_engine.py:16-19)
-AR_CASE = dict(encoder_seed=3, decoder_seed=5, decoder_layers=2, classes=32, lines=3, width=1088)
+AR_CASE = dict(encoder_seed=3, decoder_seed=5, decoder_layers=2, classes=32, lines=3, width=1088,
+               line_widths=[1088, 700, 420], input_seed=77, golden='ar_decoder.npz')
+# a realistic alphabet (class count not a multiple of the kernels' 32-wide tiles) and a deeper decoder
+AR_CASE_WIDE = dict(encoder_seed=4, decoder_seed=9, decoder_layers=3, classes=122, lines=2, width=1152,
+                    line_widths=[1152, 777], input_seed=78, golden='ar_decoder_wide.npz')
+AR_CASES = {'small': AR_CASE, 'wide': AR_CASE_WIDE}
 
 
-def ar_inputs():
+def ar_inputs(spec=AR_CASE):
     """uint8 [N, 3, 40, W]: what TransformerEngineLineOCR.run_ocr hands to transcribe_batch (after its NHWC -> NCHW
     transpose and the centre padding to 1088 px, transformer_ocr_engine.py:33-40)."""
-    rng = np.random.default_rng(77)
-    n, w = AR_CASE['lines'], AR_CASE['width']
+    rng = np.random.default_rng(spec['input_seed'])
+    n, w = spec['lines'], spec['width']
     x = np.zeros((n, 3, 40, w), dtype=np.uint8)
-    for i, wi in enumerate([1088, 700, 420][:n]):
+    for i, wi in enumerate(spec['line_widths'][:n]):
         s = (w - wi) // 2
         x[i, :, :, s:s + wi] = rng.integers(0, 256, (1, 40, wi), dtype=np.uint8)
     return x
 
-AR_NET_CONFIG = {'dim_model': 512, 'dim_ff': 2048, 'heads': 8, 'encoder_layers': 2,
-                 'decoder_layers': AR_CASE['decoder_layers'], 'conv_subsampling': [8, 4]}   # transformer.build_net keys
+def ar_net_config(spec=AR_CASE):
+    """transformer.build_net's config keys (transformer.py:12-20)."""
+    return {'dim_model': 512, 'dim_ff': 2048, 'heads': 8, 'encoder_layers': 2,
+            'decoder_layers': spec['decoder_layers'], 'conv_subsampling': [8, 4]}
 
 
-def ar_state_dict():
-    """The TransformerOCR checkpoint (reference key names) of AR_CASE: seeded encoder + seeded decoder."""
+AR_NET_CONFIG = ar_net_config()
+
+
+def ar_state_dict(spec=AR_CASE):
+    """The TransformerOCR checkpoint (reference key names) of an AR case: seeded encoder + seeded decoder."""
     from oracle.ar_oracle import ar_decoder_state
     from pero_ocr_b200.synthetic import make_net, transformer_ocr_state
-    net = make_net('transformer', 120, seed=AR_CASE['encoder_seed'], layers=AR_NET_CONFIG['encoder_layers'])
-    dec = ar_decoder_state(seed=AR_CASE['decoder_seed'], layers=AR_CASE['decoder_layers'], classes=AR_CASE['classes'])
+    net = make_net('transformer', 120, seed=spec['encoder_seed'], layers=2)
+    dec = ar_decoder_state(seed=spec['decoder_seed'], layers=spec['decoder_layers'], classes=spec['classes'])
     return net, dec, transformer_ocr_state(net, dec)
 
 
-def write_ar_engine_json(tmpdir, max_line_width=None):
+def write_ar_engine_json(tmpdir, max_line_width=None, spec=AR_CASE):
     import json
     import os
     path = os.path.join(str(tmpdir), 'ar_engine.json')
     cfg = {'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'ar.pt',
-           'characters': json_characters(AR_CASE['classes'] - 2), 'net_name': AR_NET_CONFIG}
+           'characters': json_characters(spec['classes'] - 2), 'net_name': ar_net_config(spec)}
     if max_line_width is not None:
         cfg['max_line_width'] = max_line_width
     with open(path, 'w', encoding='utf8') as f:

@@ -297,48 +297,52 @@ def golden_align():
 
 def golden_ar_decoder():
     """TransformerEngineLineOCR.transcribe_batch (autoregressive greedy decoding with the cached decoder) of the
-    unmodified reference, hosting the seeded encoder of oracle/nets.py and the seeded decoder of oracle/ar_oracle.py."""
+    unmodified reference, hosting the seeded encoder of oracle/nets.py and the seeded decoder of oracle/ar_oracle.py;
+    one golden file per case of cases.AR_CASES."""
     import torchvision
     from pero_ocr.ocr_engine import transformer as ref_tr
     from pero_ocr.ocr_engine.transformer_ocr_engine import TransformerEngineLineOCR
     from oracle.ar_oracle import ar_decoder_state
-    spec = cases.AR_CASE
-    orig = torchvision.models.vgg16
-    torchvision.models.vgg16 = lambda pretrained=False, **k: orig(weights=None)
-    try:
-        with contextlib.redirect_stdout(io.StringIO()):
-            ref = ref_tr.build_net({'dim_model': 512, 'dim_ff': 2048, 'heads': 8, 'encoder_layers': 2,
-                                    'decoder_layers': spec['decoder_layers'], 'conv_subsampling': [8, 4]},
-                                   input_height=40, input_channels=3, nb_output_symbols=spec['classes'] - 2).eval()
-    finally:
-        torchvision.models.vgg16 = orig
-    ours = make_net('transformer', 120, seed=spec['encoder_seed'], layers=2)
-    ref_front = ref.encoder_frontend
-    for r, o in zip([m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.Conv2d)],
-                    [m for m in ours.conv if isinstance(m, torch.nn.Conv2d)]):
-        r.load_state_dict(o.state_dict())
-    [m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.BatchNorm2d)][0].load_state_dict(
-        [m for m in ours.conv if isinstance(m, torch.nn.BatchNorm2d)][0].state_dict())
-    ref_front.aggregation_conv[0].load_state_dict(ours.agg.state_dict())
-    ref.encoder.input_norm.load_state_dict(ours.input_norm.state_dict())
-    ref.encoder.trans_encoder.load_state_dict(ours.trans_encoder.state_dict())
-    dec = ar_decoder_state(seed=spec['decoder_seed'], layers=spec['decoder_layers'], classes=spec['classes'])
-    missing, unexpected = ref.load_state_dict({k: torch.from_numpy(v) for k, v in dec.items()}, strict=False)
-    assert not unexpected and not [k for k in missing if k.startswith(('trans_decoder', 'dec_'))], (missing, unexpected)
-    fake = types.SimpleNamespace(net=ref, device=torch.device('cpu'), sentence_boundary_ind=spec['classes'] - 2,
-                                 ignore_ind=spec['classes'] - 1)
-    fake.postprocess_decoded = lambda *a: TransformerEngineLineOCR.postprocess_decoded(fake, *a)
-    inputs = cases.ar_inputs()                                   # uint8 [N, 3, 40, W]
-    with torch.no_grad():
-        outs, logits = TransformerEngineLineOCR.transcribe_batch(fake, inputs, is_cached=True)
-    n = len(outs)
-    width = max([len(o) for o in outs] + [1])
-    toks = np.full((n, width), -1, dtype=np.int64)
-    for i, o in enumerate(outs):
-        toks[i, :len(o)] = o.numpy()
-    np.savez_compressed(os.path.join(GOLDEN, 'ar_decoder.npz'), tokens=toks,
-                        lengths=np.array([len(o) for o in outs]), logits=logits.numpy().astype(np.float32))
-    return {'lines': n, 'steps': int(logits.shape[1]), 'lengths': [len(o) for o in outs]}
+    report = {}
+    for name, spec in cases.AR_CASES.items():
+        orig = torchvision.models.vgg16
+        torchvision.models.vgg16 = lambda pretrained=False, **k: orig(weights=None)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = ref_tr.build_net(cases.ar_net_config(spec), input_height=40, input_channels=3,
+                                       nb_output_symbols=spec['classes'] - 2).eval()
+        finally:
+            torchvision.models.vgg16 = orig
+        ours = make_net('transformer', 120, seed=spec['encoder_seed'], layers=2)
+        ref_front = ref.encoder_frontend
+        for r, o in zip([m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.Conv2d)],
+                        [m for m in ours.conv if isinstance(m, torch.nn.Conv2d)]):
+            r.load_state_dict(o.state_dict())
+        [m for m in ref_front.blocks_2d.modules() if isinstance(m, torch.nn.BatchNorm2d)][0].load_state_dict(
+            [m for m in ours.conv if isinstance(m, torch.nn.BatchNorm2d)][0].state_dict())
+        ref_front.aggregation_conv[0].load_state_dict(ours.agg.state_dict())
+        ref.encoder.input_norm.load_state_dict(ours.input_norm.state_dict())
+        ref.encoder.trans_encoder.load_state_dict(ours.trans_encoder.state_dict())
+        dec = ar_decoder_state(seed=spec['decoder_seed'], layers=spec['decoder_layers'], classes=spec['classes'])
+        missing, unexpected = ref.load_state_dict({k: torch.from_numpy(v) for k, v in dec.items()}, strict=False)
+        assert not unexpected and not [k for k in missing if k.startswith(('trans_decoder', 'dec_'))], (missing, unexpected)
+        fake = types.SimpleNamespace(net=ref, device=torch.device('cpu'), sentence_boundary_ind=spec['classes'] - 2,
+                                     ignore_ind=spec['classes'] - 1)
+        fake.postprocess_decoded = lambda *a, fake=fake: TransformerEngineLineOCR.postprocess_decoded(fake, *a)
+        inputs = cases.ar_inputs(spec)                               # uint8 [N, 3, 40, W]
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            outs, logits = TransformerEngineLineOCR.transcribe_batch(fake, inputs, is_cached=True)
+        n = len(outs)
+        width = max([len(o) for o in outs] + [1])
+        toks = np.full((n, width), -1, dtype=np.int64)
+        for i, o in enumerate(outs):
+            toks[i, :len(o)] = o.numpy()
+        np.savez_compressed(os.path.join(GOLDEN, spec['golden']), tokens=toks,
+                            lengths=np.array([len(o) for o in outs]), logits=logits.numpy().astype(np.float32))
+        srt = np.sort(logits.numpy(), axis=2)
+        report[name] = {'lines': n, 'steps': int(logits.shape[1]), 'lengths': [len(o) for o in outs],
+                        'top2_margin_min': float((srt[..., -1] - srt[..., -2]).min())}
+    return report
 
 
 def golden_ar_host(tmp):

@@ -72,6 +72,28 @@ def main():
             dt = time.perf_counter() - t0
             out[f'time_v{variant}_{name}'] = {'seconds': dt, 'lines_per_s': n / dt, 'steps': k,
                                              'ms_per_step': 1e3 * dt / k, 'launches': eng.net.launch_count - l0}
+    # second golden case (not yet part of the GPU test-suite): 3 decoder layers, 122 classes (partial 32-wide output
+    # tiles, several argmax passes per warp), no line stops -> the loop ends on the length limit after W/4 + 1 steps
+    try:
+        spec = cases.AR_CASES['wide']
+        gold_w = load_golden(GOLDEN, spec['golden'])
+        _, _, sd_w = cases.ar_state_dict(spec)
+        with tempfile.TemporaryDirectory() as tmp:
+            eng_w = B200TransformerEngineLineOCR(cases.write_ar_engine_json(tmp, spec=spec), torch.device('cuda', 0),
+                                                 state_dict=sd_w)
+        outs_w, logits_w = eng_w.transcribe_batch(cases.ar_inputs(spec))
+        k = min(logits_w.shape[1], gold_w['logits'].shape[1])
+        d = np.abs(logits_w[:, :k] - gold_w['logits'][:, :k]).max(axis=2)
+        same = logits_w[:, :k].argmax(2) == gold_w['logits'][:, :k].argmax(2)
+        first_diff = [int(np.argmin(r)) if not r.all() else -1 for r in same]
+        out['wide_case'] = {'steps': [int(logits_w.shape[1]), int(gold_w['logits'].shape[1])],
+                            'lengths': [[len(o) for o in outs_w], gold_w['lengths'].tolist()],
+                            'first_step_with_other_argmax': first_diff,
+                            'logit_err_max_before_divergence': [float(d[i, :(f if f >= 0 else k)].max()) if (f != 0) else None
+                                                                for i, f in enumerate(first_diff)]}
+        eng_w.net.close()
+    except Exception as e:                                                        # noqa: BLE001
+        out['wide_case_error'] = repr(e)
     # the same work on the host cores: torch-CPU encoder + NumPy decoder loop of the oracle (golden batch, 3 lines)
     from oracle.ar_oracle import greedy_transcribe
     sb = cases.AR_CASE['classes'] - 2

@@ -99,6 +99,9 @@ def test_describe_transformer_ocr_reads_the_reference_checkpoint_layout(golden_d
         assert np.array_equal(ly['cross_in_w'], dec[f'trans_decoder.layers.{i}.multihead_attn.in_proj_weight'])
     desc, keep = netdesc.ar_to_ctypes(decoder)
     assert desc.n_layers == 2 and desc.heads == 8 and desc.dim_ff == 2048 and desc.classes == 32
+    _, _, sd_wide = cases.ar_state_dict(cases.AR_CASES['wide'])
+    _, dec_wide = netdesc.describe_transformer_ocr(sd_wide, cases.ar_net_config(cases.AR_CASES['wide']), 40)
+    assert len(dec_wide['layers']) == 3 and dec_wide['classes'] == 122
     bad = dict(sd)
     bad.pop('trans_decoder.layers.1.norm3.bias')
     with pytest.raises(KeyError):

@@ -1,7 +1,11 @@
 """CPU: oracle/ar_oracle.py (restatement of the reference's autoregressive Transformer decoding)
-against the output of the unmodified TransformerEngineLineOCR.transcribe_batch stored in tests/golden/ar_decoder.npz.
-This pins the parity reference of the device path (tests/test_zz_gpu_ar_decoder.py)."""
+against the output of the unmodified TransformerEngineLineOCR.transcribe_batch stored in tests/golden/ar_decoder*.npz
+(oracle/make_golden.py: golden_ar_decoder).  This pins the parity reference of the device path
+(tests/test_zz_gpu_ar_decoder.py).  Case 'small': 2 decoder layers, 32 classes, every line stops by itself; case
+'wide': 3 decoder layers, 122 classes, no line ever emits the sentence boundary, so the loop ends on the length limit
+(transformer_ocr_engine.py:79-82)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import cases
@@ -10,11 +14,12 @@ from oracle.nets import make_net
 from tests.util import load_golden
 
 
-def test_ar_greedy_decoding_matches_reference_golden(golden_dir):
-    gold = load_golden(golden_dir, 'ar_decoder.npz')
-    spec = cases.AR_CASE
+@pytest.mark.parametrize('case', ['small', 'wide'])
+def test_ar_greedy_decoding_matches_reference_golden(golden_dir, case):
+    spec = cases.AR_CASES[case]
+    gold = load_golden(golden_dir, spec['golden'])
     net = make_net('transformer', 120, seed=spec['encoder_seed'], layers=2)
-    x = torch.from_numpy(cases.ar_inputs()).float() / 255.0
+    x = torch.from_numpy(cases.ar_inputs(spec)).float() / 255.0
     with torch.no_grad():                                     # TransformerOCR.encode (transformer.py:548-555)
         y = net.agg_act(net.agg(net.conv(x))).squeeze(2).permute(2, 0, 1)
         memory = net.trans_encoder(net.input_norm(y) + net.pe[:y.size(0)]).numpy()
@@ -29,3 +34,5 @@ def test_ar_greedy_decoding_matches_reference_golden(golden_dir):
     outs = postprocess_decoded(tokens, spec['classes'] - 1, spec['classes'] - 2)
     for i, o in enumerate(outs):
         assert o == list(gold['tokens'][i, :gold['lengths'][i]]), i
+    if case == 'wide':                                        # ended by the length limit, not by the alive mask
+        assert logits.shape[1] == spec['width'] // 4 + 1 and all(len(o) == spec['width'] // 4 for o in outs)
