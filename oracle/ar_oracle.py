@@ -7,7 +7,7 @@ Follows ``TransformerEngineLineOCR.transcribe_batch`` / ``postprocess_decoded``
 projection of ``TransformerOCR`` (:489-546).  One token position is processed per step; keys / values of the
 self-attention accumulate in a cache, keys / values of the encoder-decoder attention are projected once.
 
-Pinned: tests/golden/ar_decoder.npz holds token sequences and logits produced by the UNMODIFIED reference classes
+Pinned: tests/golden/ar_decoder.npz and ar_decoder_wide.npz hold token sequences and logits produced by the UNMODIFIED reference classes
 (``transformer.build_net`` + ``TransformerEngineLineOCR.transcribe_batch``) hosting the seeded weights of
 ``ar_decoder_state`` / ``pero_ocr_b200.synthetic`` (oracle/make_golden.py: golden_ar_decoder); tests/test_oracle_ar.py
 checks this restatement against them; tests/test_zz_gpu_ar_decoder.py checks the device path
