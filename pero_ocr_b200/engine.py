@@ -102,6 +102,20 @@ class LineRecognizer:
             C.c_void_p(stream)), self._h)
         return o
 
+    @staticmethod
+    def bytes_from_unit_floats(x):
+        """f32 [N,3,H,W] in [0,1] (what run_ocr feeds the blob: uint8 / 255, NCHW, pytorch_ocr_engine.py:61-62) ->
+        the uint8 [N,H,W,3] batch it came from.  Exact for every k / 255: the engine's input IS the byte batch, the
+        `/255` happens inside the first convolution."""
+        import torch
+        return (x * 255.0).round_().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+    def __call__(self, x):
+        """The B1 seam of SURVEY.md 8(b): a stand-in for the TorchScript blob, `model(x: f32[N,3,H,W] in [0,1], CUDA)
+        -> f32[N,C,T]` raw logits with the blank last (pytorch_ocr_engine.py:64-69).  Stream-ordered, no sync."""
+        out = self.forward(self.bytes_from_unit_floats(x), want_logits=True)
+        return out['logits'].permute(0, 2, 1)
+
     def profile(self, on):
         _lib.check(self._lib.b200ocr_profile(self._h, 1 if on else 0), self._h)
 

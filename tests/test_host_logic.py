@@ -148,3 +148,20 @@ def test_ar_engine_fails_loudly_without_gpu():
     layers, decoder = netdesc.describe_transformer_ocr(sd, cases.AR_NET_CONFIG, 40)
     with pytest.raises(B200Error):
         ARLineRecognizer(layers, decoder)
+
+
+def test_model_seam_recovers_the_byte_batch_exactly():
+    """B1 seam (LineRecognizer.__call__): run_ocr's float input uint8 / 255 maps back to the same bytes for all 256
+    values, in the NHWC layout the engine consumes."""
+    from pero_ocr_b200.engine import LineRecognizer
+    rng = np.random.default_rng(0)
+    batch = rng.integers(0, 256, (2, 5, 64, 3), dtype=np.uint8)
+    batch[0, 0, :, 0] = np.arange(64) * 4
+    batch[0, 1, :, 1] = 255 - np.arange(64) * 4
+    batch[1, 0, :64, 2] = np.arange(192, 256)
+    x = torch.from_numpy(batch).float()
+    x /= 255.0                                                   # pytorch_ocr_engine.py:61-62
+    back = LineRecognizer.bytes_from_unit_floats(x.permute(0, 3, 1, 2))
+    assert back.dtype == torch.uint8 and back.is_contiguous() and np.array_equal(back.numpy(), batch)
+    every = torch.arange(256, dtype=torch.float32).div(255.0).view(1, 1, 1, 256).expand(1, 3, 1, 256)
+    assert np.array_equal(LineRecognizer.bytes_from_unit_floats(every)[0, 0, :, 0].numpy(), np.arange(256))
