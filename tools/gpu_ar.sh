@@ -17,5 +17,5 @@ ncu -i $out/${tag}_ar_step.ncu-rep --page raw --csv > $out/${tag}_ar_step_raw.cs
 # compute-sanitizer over the token loop (3 lines keep the encoder short under instrumentation)
 compute-sanitizer --tool memcheck python -m tests.prof_ar 3 1 > $out/${tag}_ar_memcheck.log 2>&1
 compute-sanitizer --tool racecheck python -m tests.prof_ar 3 1 > $out/${tag}_ar_racecheck.log 2>&1
-python -m tests.aux_bench config4 incumbent > $out/${tag}_config4_page_pipeline.json 2> $out/${tag}_config4.err
+python -m tests.aux_bench config4 incumbent > $out/${tag}_aux_config4_incumbent.json 2> $out/${tag}_aux_config4_incumbent.err
 echo done
