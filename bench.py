@@ -121,6 +121,118 @@ def cpu_reference_lines_per_s(kind, n_lines, threads=None):
     return n_lines / dt, dt, torch.get_num_threads()
 
 
+def incumbent_gpu(kind, dev, steps=5, ours=None):
+    """The reference's own GPU path on this device -- the incumbent: what
+    PytorchEngineLineOCR(json, cuda).run_ocr executes (pero_ocr/ocr_engine/pytorch_ocr_engine.py:59-74, 13-34): H2D of
+    the padded uint8 batch, `.float() / 255`, NHWC -> NCHW view, the module as a TorchScript blob (cuDNN convolutions
+    with TF32 allowed and fp32 cuBLAS matmuls: torch's defaults, which the reference does not touch; cuDNN LSTM),
+    greedy_decode_ctc's tensor part + `.cpu()` + string join, and the [N,T,C] logits download run_ocr always performs
+    (:72).  Restated around the same seeded module because the reference package (lxml, shapely, ... at import) cannot
+    travel to the GPU box; every kernel on this path is library code -- it is the baseline, never the product.
+    Variants: the stock path, strict fp32 (TF32 off), and two tuned library paths the reference does not use (bf16 /
+    fp16 autocast with cudnn.benchmark) as an upper bound on what the libraries give.  Each reports device-resident
+    lines/s (CUDA events, uint8 batch already in HBM, like `value`), end-to-end lines/s from pinned host memory to
+    strings (+ the logits download, like `e2e`), and its max logit error against the torch-CPU fp32 module on a 4-line
+    sample -- printed beside ours on the same sample."""
+    import torch
+    from pero_ocr_b200 import synthetic
+    net = make_net(kind).to(dev)
+    hosted = 'torch.jit.script (the blob format torch.jit.load hosts)'
+    try:
+        mod = torch.jit.script(net)
+    except Exception:                                                           # noqa: BLE001
+        mod, hosted = net, 'eager nn.Module'
+    chars = synthetic.json_characters(118) + ['\u200b']
+    crops = synthetic.bench_crops(BATCH, WIDTH, seed=0)
+    batch = np.zeros((BATCH, 40, PADDED, 3), dtype=np.uint8)
+    batch[:, :, 32:32 + WIDTH] = crops
+    host = torch.from_numpy(batch).pin_memory()
+    resident = host.to(dev)
+    rng = np.random.default_rng(7)
+    small = rng.integers(0, 256, (4, 40, 256, 3), dtype=np.uint8)
+    with torch.no_grad():
+        want = make_net(kind)(torch.from_numpy(small).float().div(255.0).permute(0, 3, 1, 2)).numpy()   # CPU fp32 [N,C,T]
+
+    def forward(u8, autocast):
+        x = u8.float() / 255.0                                                  # :61
+        x = x.permute(0, 3, 1, 2)                                               # :62
+        if autocast is None:
+            return mod(x)
+        with torch.autocast('cuda', dtype=autocast):
+            return net(x).float()
+
+    def greedy_tensor(logits):                                                  # greedy_decode_ctc, :19-27
+        sp = torch.cat((logits[:, :, 0:1], logits), dim=2)
+        sp[:, :, 0] = -1000
+        sp[:, -1, 0] = 1000
+        best = torch.argmax(sp, 1) + 1
+        mask = best[:, :-1] == best[:, 1:]
+        best = best[:, 1:]
+        best[mask] = 0
+        best[best == sp.shape[1]] = 0
+        return best
+
+    def run_ocr(src, autocast, with_logits):
+        with torch.no_grad():
+            logits = forward(src.to(dev, non_blocking=True), autocast)
+            best = greedy_tensor(logits).cpu().numpy() - 1                      # :28-34
+            out = [''.join(chars[c] for c in line[np.nonzero(line >= 0)]) for line in best]
+            lg = logits.permute(0, 2, 1).cpu().numpy() if with_logits else None  # :72
+        return out, lg
+
+    variants = [('stock_tf32', dict(tf32=True, autocast=None, benchmark=False)),
+                ('strict_fp32', dict(tf32=False, autocast=None, benchmark=False)),
+                ('tuned_bf16_autocast', dict(tf32=True, autocast=torch.bfloat16, benchmark=True)),
+                ('tuned_fp16_autocast', dict(tf32=True, autocast=torch.float16, benchmark=True))]
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    res = {}
+    for name, v in variants:
+        torch.backends.cudnn.allow_tf32 = v['tf32']
+        torch.backends.cudnn.benchmark = v['benchmark']
+        try:
+            with torch.no_grad():
+                got = forward(torch.from_numpy(small).to(dev), v['autocast']).float().cpu().numpy()
+                err = float(np.abs(got - want).max())
+                for _ in range(3):
+                    greedy_tensor(forward(resident, v['autocast']))
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(steps):
+                    greedy_tensor(forward(resident, v['autocast']))
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / steps
+            r = {'lines_per_s': BATCH / (ms / 1e3), 'ms_per_step': ms, 'logit_max_abs_err_vs_fp32': err}
+            for key, with_logits in (('e2e_lines_per_s', True), ('e2e_no_logits_lines_per_s', False)):
+                run_ocr(host, v['autocast'], with_logits)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    run_ocr(host, v['autocast'], with_logits)
+                torch.cuda.synchronize()
+                r[key] = BATCH * steps / (time.perf_counter() - t0)
+            res[name] = r
+        except Exception as exc:                                                # noqa: BLE001
+            res[name] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = saved
+    stock = res.get('stock_tf32', {})
+    out = {'what': "the reference's GPU path: PyTorch run_ocr on the same module, same batch (pytorch_ocr_engine.py:59-74)",
+           'kernels': 'library (cuDNN / cuBLAS / ATen)', 'hosted_as': hosted, 'torch': torch.__version__,
+           'cudnn': torch.backends.cudnn.version(), 'allow_tf32': True, 'steps': steps,
+           'lines_per_s': stock.get('lines_per_s'), 'e2e_lines_per_s': stock.get('e2e_lines_per_s'),
+           'logit_max_abs_err_vs_fp32': stock.get('logit_max_abs_err_vs_fp32'), 'variants': res}
+    if ours is not None:
+        with torch.no_grad():
+            o = ours.forward(torch.from_numpy(small).to(dev), want_logits=True)
+            torch.cuda.synchronize()
+            out['ours_logit_max_abs_err_vs_fp32'] = float(np.abs(o['logits'].cpu().numpy() - want.transpose(0, 2, 1)).max())
+    del mod, net, resident, host
+    torch.cuda.empty_cache()
+    return out
+
+
 def ctc_decode_times(dev, with_cpu):
     """BASELINE.json metric part 2, 'CTC decode us/line': device-resident greedy (config 1: 128 x 256 x 120) and
     prefix beam k=16 (256 x 336 x 120 peaky log-probs), next to the reference algorithm on one host core."""
@@ -209,6 +321,8 @@ def main():
     ap.add_argument('--ref-lines', type=int, default=96, help='lines per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-lines', type=int, default=512, help='bounded CPU sample (about 10-20 s of host work)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-incumbent', action='store_true', help="skip the reference's GPU eager path (N=1 only)")
+    ap.add_argument('--incumbent-steps', type=int, default=5)
     ap.add_argument('--profile-out', default=None, help='write the per-layer kernel table (JSON) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -378,6 +492,13 @@ def main():
         r, dt_cpu, used = cpu_reference_lines_per_s(args.net, args.cpu_baseline_lines)
         line['cpu_baseline'] = {'value': r, 'unit': UNIT, 'cores': used, 'kind': 'port',
                                 'sample': f'{args.cpu_baseline_lines} lines of the same workload in {dt_cpu:.1f} s, torch-CPU fp32'}
+    if rank == 0 and world == 1 and not args.no_incumbent:
+        # the reference's GPU path on the same device, right after the timed region (library kernels: the baseline)
+        inc = incumbent_gpu(args.net, dev, steps=args.incumbent_steps, ours=rec)
+        if inc.get('lines_per_s'):
+            inc['value_over_incumbent'] = value / inc['lines_per_s']
+            inc['e2e_over_incumbent_e2e'] = e2e_value / inc['e2e_lines_per_s'] if inc.get('e2e_lines_per_s') else None
+        line['incumbent_gpu'] = inc
     if rank == 0:
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:

@@ -15,7 +15,6 @@ ncu --set full --clock-control none --import-source on -k 'regex:linear_f32|step
     -s 1085 -c 27 -o $out/${tag}_ar_step -f python -m tests.prof_ar 64 1 > $out/${tag}_ar_ncu_full.log 2>&1
 ncu -i $out/${tag}_ar_step.ncu-rep --page raw --csv > $out/${tag}_ar_step_raw.csv 2>/dev/null
 # compute-sanitizer over the token loop (3 lines keep the encoder short under instrumentation)
-compute-sanitizer --tool memcheck python -m tests.prof_ar 3 1 > $out/${tag}_ar_memcheck.log 2>&1
-compute-sanitizer --tool racecheck python -m tests.prof_ar 3 1 > $out/${tag}_ar_racecheck.log 2>&1
-python -m tests.aux_bench config4 incumbent > $out/${tag}_aux_config4_incumbent.json 2> $out/${tag}_aux_config4_incumbent.err
+timeout 420 compute-sanitizer --tool memcheck python -m tests.prof_ar 3 1 > $out/${tag}_ar_memcheck.log 2>&1
+timeout 420 compute-sanitizer --tool racecheck python -m tests.prof_ar 3 1 > $out/${tag}_ar_racecheck.log 2>&1
 echo done
