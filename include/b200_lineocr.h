@@ -43,9 +43,16 @@ enum b200ocr_act { B200OCR_ACT_NONE = 0, B200OCR_ACT_RELU = 1, B200OCR_ACT_LEAKY
 enum b200ocr_precision {
     B200OCR_PREC_FP16 = 0,  /* fp16 operands, fp32 accumulate (same 10-bit mantissa as cuDNN's default TF32 convs) */
     B200OCR_PREC_FP16X3 = 1, /* hi/lo fp16 split of both operands, 3 MMAs per product: ~fp32-faithful */
-    B200OCR_PREC_FP16F8 = 2  /* fp16 hi*hi pass + the two first-order correction terms (lo*hi + hi*lo) as ONE e5m2
+    B200OCR_PREC_FP16F8 = 2, /* fp16 hi*hi pass + the two first-order correction terms (lo*hi + hi*lo) as ONE e5m2
                                 tensor-core pass at twice the fp16 rate: 2 pass-equivalents, logits within ~1e-4 */
+    B200OCR_PREC_FP16F8W = 3 /* FP16F8 with b200ocr_set_layer_correction(layer, B200OCR_CORR_WEIGHT) preset on the 3x3
+                                convolutions with >= 256 input channels (the tensor-pipe-bound layers) */
 };
+
+/* B200OCR_PREC_FP16F8: which first-order correction terms the e5m2 pass of ONE layer evaluates.  The pass contracts
+ * [a_lo | a_hi] . [w_hi | w_lo]; WEIGHT walks the second half only (a_hi . w_lo: the fp16 rounding of the weights,
+ * the larger and static error term) for 1.5 instead of 2 pass-equivalents, NONE leaves plain fp16. */
+enum b200ocr_correction { B200OCR_CORR_BOTH = 0, B200OCR_CORR_WEIGHT = 1, B200OCR_CORR_NONE = 2 };
 
 /* One layer.  All weight pointers are HOST pointers to fp32 arrays in PyTorch's native layouts; the library
  * packs them (fp16, tap-major, K-major) into device memory it owns.  Unused fields are 0 / NULL. */
@@ -130,6 +137,17 @@ int64_t b200ocr_launch_count(const b200ocr_engine_t* e);
 
 /* Algorithmic FLOPs (2*MACs) of one forward at (n, w) and the share of the implicit-GEMM conv kernel. */
 double b200ocr_forward_flops(const b200ocr_engine_t* e, int32_t n, int32_t w, double* conv_gemm_flops);
+
+/* Per-layer arithmetic of a B200OCR_PREC_FP16F8 engine (the reference has one arithmetic: whatever torch dispatches
+ * for `self.model`, pytorch_ocr_engine.py:64-69 -- cuDNN TF32 convolutions by default).  `layer` indexes the
+ * descriptor's layer list; layers without a tensor-core contraction are rejected.  Takes effect at the next forward.
+ * pero_ocr_b200.engine.LineRecognizer.autotune_precision chooses the modes by measured logit error. */
+int b200ocr_set_layer_correction(b200ocr_engine_t* e, int32_t layer, int32_t mode);
+
+/* FLOP-weighted tensor-core pass-equivalents the GEMM layers execute per algorithmic FLOP at (n, w) (1 = fp16,
+ * 2 = fp16f8, 3 = fp16x3, in between with per-layer corrections); per_layer (HOST f32 [capacity], may be NULL)
+ * receives the figure of each layer (0 for layers without a contraction). */
+double b200ocr_executed_passes(const b200ocr_engine_t* e, int32_t n, int32_t w, int32_t capacity, float* per_layer);
 
 /* Replaces greedy_decode_ctc (pytorch_ocr_engine.py:13-34) and decoding.decoders.GreedyDecoder.__call__
  * (pero_ocr/decoding/decoders.py:42-62) on materialised scores.

@@ -8,8 +8,9 @@ _LIB = None
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_NO_DEVICE = 0, 1, 2, 3, 4
 CONV_FIRST, CONV, BILSTM, CTC_HEAD, UPSAMPLE, LN_PE, TRANSFORMER_LAYER = 1, 2, 3, 4, 5, 6, 7
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
-PREC_FP16, PREC_FP16X3, PREC_FP16F8 = 0, 1, 2
-PRECISIONS = {'fp16': PREC_FP16, 'fp16x3': PREC_FP16X3, 'fp16f8': PREC_FP16F8}
+PREC_FP16, PREC_FP16X3, PREC_FP16F8, PREC_FP16F8W = 0, 1, 2, 3
+PRECISIONS = {'fp16': PREC_FP16, 'fp16x3': PREC_FP16X3, 'fp16f8': PREC_FP16F8, 'fp16f8w': PREC_FP16F8W}
+CORR_BOTH, CORR_WEIGHT, CORR_NONE = 0, 1, 2
 DEFAULT_PRECISION = 'fp16f8'   # fp16 pass + e5m2 correction pass: logits within 1e-4 of the fp32 oracle at 2 pass-equivalents
 
 _FP = C.POINTER(C.c_float)
@@ -70,6 +71,8 @@ EXPORTS = {
     'b200ocr_last_error': (C.c_char_p, [C.c_void_p]),
     'b200ocr_launch_count': (C.c_int64, [C.c_void_p]),
     'b200ocr_forward_flops': (C.c_double, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    'b200ocr_set_layer_correction': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    'b200ocr_executed_passes': (C.c_double, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'b200ocr_ctc_greedy': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'b200ocr_force_align': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -47,6 +47,7 @@ struct Gemm {  // one dense contraction: packed fp16 weights [plane][tap][cout_p
     CUtensorMap tmB;
     int bn_halo = 0;       // tile N of the halo-reuse kernel (0 = not applicable)
     CUtensorMap tmB_halo;
+    int corr = CORR_BOTH;  // fp16f8 only: correction terms of the e5m2 pass (b200ocr_set_layer_correction)
 };
 
 struct LayerRT {
@@ -278,6 +279,7 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     p.h_out = in_s.h + 2 * g.pad_h - g.kh + 1;
     p.w_out = in_s.w + 2 * g.pad_w - g.kw + 1;
     p.pool_h = pool_h; p.pool_w = pool_w; p.act = act; p.npass = e->npass;
+    p.corr_mode = e->fmt == ACT_F16_F8 ? g.corr : CORR_BOTH;
     if (p.h_out <= 0 || p.w_out <= 0) return fail(e, B200OCR_E_INVALID, "empty convolution output");
     if (p.h_out % pool_h || p.w_out % pool_w)
         return fail(e, B200OCR_E_INVALID, "pooled layer needs even output (%d x %d)", p.h_out, p.w_out);
@@ -579,6 +581,24 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
     return 0;
 }
 
+// The engine-less entry points (decoders, cropper, sparsification, alignment) launch on the stream they are given; a
+// stream and the per-device kernel attributes belong to ONE device, which need not be the calling thread's current
+// one (a tensor on cuda:1 while cuda:0 is current).  Makes the device that owns `ptr` current for the call.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const void* ptr) {
+        cudaPointerAttributes at;
+        int cur = 0;
+        if (ptr && cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+            cudaGetDevice(&cur) == cudaSuccess && cur != at.device && cudaSetDevice(at.device) == cudaSuccess)
+            prev = cur;
+        cudaGetLastError();   // a host pointer is not an error here
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 int check_device(b200ocr_engine* e, int device) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= device)
@@ -615,7 +635,8 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
     switch (desc->precision) {
         case B200OCR_PREC_FP16: e->fmt = ACT_F16; e->planes = 1; e->npass = 1; e->lstm_planes = 1; break;
         case B200OCR_PREC_FP16X3: e->fmt = ACT_F16_HILO; e->planes = 2; e->npass = 3; e->lstm_planes = 2; break;
-        case B200OCR_PREC_FP16F8: e->fmt = ACT_F16_F8; e->planes = 2; e->npass = 2; e->lstm_planes = 2; break;
+        case B200OCR_PREC_FP16F8:
+        case B200OCR_PREC_FP16F8W: e->fmt = ACT_F16_F8; e->planes = 2; e->npass = 2; e->lstm_planes = 2; break;
         default: return bail(fail(e, B200OCR_E_INVALID, "unknown precision %d", desc->precision));
     }
     e->line_height = desc->line_height;
@@ -712,6 +733,9 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                 return bail(fail(e, B200OCR_E_INVALID, "layer %d: unknown kind %d", i, d.kind));
         }
     }
+    if (desc->precision == B200OCR_PREC_FP16F8W)   // preset: weight-side correction only in the deep 3x3 layers
+        for (LayerRT& ly : e->layers)
+            if (ly.kind == B200OCR_CONV && ly.g.kh * ly.g.kw == 9 && ly.g.cin >= 256) ly.g.corr = CORR_WEIGHT;
     *out = e;
     return B200OCR_OK;
 }
@@ -845,12 +869,71 @@ double b200ocr_forward_flops(const b200ocr_engine_t* e, int32_t n, int32_t w, do
     return total;
 }
 
+int b200ocr_set_layer_correction(b200ocr_engine_t* e, int32_t layer, int32_t mode) {
+    if (!e) return B200OCR_E_INVALID;
+    if (layer < 0 || layer >= (int)e->layers.size() || mode < CORR_BOTH || mode > CORR_NONE)
+        return fail(e, B200OCR_E_INVALID, "bad layer correction (layer %d, mode %d)", layer, mode);
+    LayerRT& ly = e->layers[layer];
+    switch (ly.kind) {
+        case B200OCR_CONV: case B200OCR_CTC_HEAD: case B200OCR_BILSTM: ly.g.corr = mode; break;
+        case B200OCR_TRANSFORMER_LAYER: ly.g_in.corr = ly.g_out.corr = ly.g_l1.corr = ly.g_l2.corr = mode; break;
+        default: return fail(e, B200OCR_E_INVALID, "layer %d has no tensor-core contraction", layer);
+    }
+    return B200OCR_OK;
+}
+
+double b200ocr_executed_passes(const b200ocr_engine_t* e, int32_t n, int32_t w, int32_t capacity, float* per_layer) {
+    if (!e) return 0.0;
+    // tensor-core pass-equivalents a contraction executes: 1 (fp16), 3 (fp16x3), or 1 + the share of the 2*cin-byte
+    // e5m2 operand the correction pass walks (igemm_tc.cu: whole 128-byte chunks, starting at chunk kchunks/2 for the
+    // weight-side-only mode; an e5m2 MMA of K = 32 takes as long as an fp16 MMA of K = 16)
+    auto passes = [&](const Gemm& g) -> double {
+        if (e->fmt == ACT_F16) return 1.0;
+        if (e->fmt == ACT_F16_HILO) return 3.0;
+        const int kchunks = g.cin / 64;
+        if (g.corr == CORR_NONE) return 1.0;
+        if (g.corr == CORR_WEIGHT) {
+            if (g.bn_halo && kchunks == 1) return 1.5;       // halo kernel, cin = 64: upper two K steps of the chunk
+            return 1.0 + static_cast<double>(kchunks - (kchunks >> 1)) / kchunks;
+        }
+        return 2.0;
+    };
+    double flops = 0.0, weighted = 0.0;
+    int h = e->line_height, cw = w, li = 0;
+    for (const LayerRT& ly : e->layers) {
+        auto gf = [&](const Gemm& g, double pixels) { return 2.0 * pixels * g.cout * g.cin * g.kh * g.kw; };
+        double f = 0.0, fw = 0.0;
+        switch (ly.kind) {
+            case B200OCR_CONV: {
+                const int ho = h + 2 * ly.g.pad_h - ly.g.kh + 1, wo = cw + 2 * ly.g.pad_w - ly.g.kw + 1;
+                f = gf(ly.g, static_cast<double>(n) * ho * wo); fw = f * passes(ly.g);
+                h = ho / ly.pool_h; cw = wo / ly.pool_w;
+                break;
+            }
+            case B200OCR_BILSTM: case B200OCR_CTC_HEAD:
+                f = gf(ly.g, static_cast<double>(n) * cw); fw = f * passes(ly.g);
+                break;
+            case B200OCR_TRANSFORMER_LAYER: {
+                const double px = static_cast<double>(n) * cw;
+                for (const Gemm* g : {&ly.g_in, &ly.g_out, &ly.g_l1, &ly.g_l2}) { f += gf(*g, px); fw += gf(*g, px) * passes(*g); }
+                break;
+            }
+            default: break;
+        }
+        if (per_layer && li < capacity) per_layer[li] = f > 0.0 ? static_cast<float>(fw / f) : 0.f;
+        flops += f; weighted += fw;
+        ++li;
+    }
+    return flops > 0.0 ? weighted / flops : 0.0;
+}
+
 int b200ocr_ctc_greedy(const float* scores, int32_t n, int32_t t, int32_t c, int32_t layout, int32_t* labels,
                        int32_t* lengths, float* confidence, int32_t* best_path, float* frame_max, float* frame_lse,
                        void* cuda_stream) {
     if (!scores || n < 0 || t <= 0 || c <= 1 || !labels || !lengths || !best_path || (layout != 0 && layout != 1))
         return fail(nullptr, B200OCR_E_INVALID, "bad ctc_greedy arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(scores);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     float* fprob = nullptr;
     if (confidence) CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&fprob), static_cast<size_t>(n) * t * 4, st));
@@ -868,6 +951,7 @@ int b200ocr_force_align(const void* neg_logprobs, int32_t is_f64, int32_t n, int
         !status || (char_positions && !out_positions))
         return fail(nullptr, B200OCR_E_INVALID, "bad force_align arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(neg_logprobs);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     uint8_t* ws = nullptr;
     CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&ws), force_align_workspace_bytes(n, t, l_max), st));
@@ -884,6 +968,7 @@ int b200ocr_char_confidence(const float* log_probs, int32_t n, int32_t t, int32_
     if (!log_probs || n < 0 || t <= 0 || c <= 1 || !labels || l_max < 1 || !lengths || !char_positions || !confidences)
         return fail(nullptr, B200OCR_E_INVALID, "bad char_confidence arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(log_probs);
     CU_TRY(nullptr, launch_char_conf(log_probs, n, t, c, n_frames, labels, l_max, lengths, char_positions, confidences,
                                      static_cast<cudaStream_t>(cuda_stream)));
     return B200OCR_OK;
@@ -896,6 +981,7 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
         out_w <= 0 || pad < 0 || (n > 0 && (!coords || !coord_off || !widths)))
         return fail(nullptr, B200OCR_E_INVALID, "bad remap_lines arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(out);
     CU_TRY(nullptr, launch_remap_lines(image, img_h, img_w, coords, coord_off, widths, n, line_h, out, out_w, pad,
                                        static_cast<cudaStream_t>(cuda_stream)));
     return B200OCR_OK;
@@ -908,6 +994,7 @@ int b200ocr_remap_poly_lines(const uint8_t* image, int32_t img_h, int32_t img_w,
         out_w <= 0 || pad < 0 || (n > 0 && (!lines || !offsets)))
         return fail(nullptr, B200OCR_E_INVALID, "bad remap_poly_lines arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(out);
     CU_TRY(nullptr, launch_remap_poly_lines(image, img_h, img_w, lines, offsets, n, line_h, out, out_w, pad,
                                             static_cast<cudaStream_t>(cuda_stream)));
     return B200OCR_OK;
@@ -919,6 +1006,7 @@ int b200ocr_sparsify_logits(const float* logits, int32_t n, int32_t t, int32_t c
     if (!logits || n < 0 || t <= 0 || c <= 0 || !indptr || !nnz || !base || !indices || !data || capacity < 0)
         return fail(nullptr, B200OCR_E_INVALID, "bad sparsify_logits arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(logits);
     CU_TRY(nullptr, launch_sparsify(logits, n, t, c, t_lo, t_hi, indptr, nnz, base, indices, data, capacity,
                                     static_cast<cudaStream_t>(cuda_stream)));
     return B200OCR_OK;
@@ -931,6 +1019,7 @@ int b200ocr_ctc_prefix_beam_ranges(const double* logprobs, int32_t n, int32_t t,
         ((t_lo == nullptr) != (t_hi == nullptr)))
         return fail(nullptr, B200OCR_E_INVALID, "bad ctc_prefix_beam arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(logprobs);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     void* ws = nullptr;
     const size_t ws_bytes = ctc_beam_workspace_bytes(n, t, c, k);
@@ -953,6 +1042,7 @@ int b200ocr_full_logprobs(const float* logits, int32_t n, int32_t t, int32_t c, 
     if (!logits || n < 0 || t <= 0 || c <= 0 || !logprobs)
         return fail(nullptr, B200OCR_E_INVALID, "bad full_logprobs arguments");
     if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(logits);
     CU_TRY(nullptr, launch_full_logprobs(logits, n, t, c, logprobs, static_cast<cudaStream_t>(cuda_stream)));
     return B200OCR_OK;
 }

@@ -11,6 +11,8 @@
 
 #include "actfmt.cuh"
 
+enum IgemmCorrection : int { CORR_BOTH = 0, CORR_WEIGHT = 1, CORR_NONE = 2 };
+
 enum IgemmEpilogue : int {
     EPI_ACT_F16 = 0,  // bias + act (+pool) (+affine) -> fp16 NHWC (hi plane, optional lo plane)
     EPI_F32 = 1,      // bias (+act) -> fp32 [pixel][cout]
@@ -30,6 +32,11 @@ struct IgemmParams {
     int act;
     int npass;  // 1 (fp16), 3 (fp16x3: hi*hi + hi*lo + lo*hi) or 2 (fp16 hi*hi + one e5m2 correction pass, actfmt.cuh)
     float acc_scale;  // epilogue multiplies the accumulator by this before the bias (2^-11 when npass == 2, else 1)
+    // npass == 2 only: which first-order correction terms the e5m2 pass evaluates.  The pass contracts the
+    // K-concatenated operands [al*2^11 | ah] . [wh | wl*2^11] (actfmt.cuh); CORR_BOTH walks all 2*cin bytes,
+    // CORR_WEIGHT only the second half (ah . wl: the rounding of the WEIGHTS, the larger and the static error term;
+    // 1.5 pass-equivalents instead of 2), CORR_NONE skips the pass (the layer runs plain fp16).
+    int corr_mode;
     int out_fmt;      // ActFormat of the EPI_ACT_F16 output
     int th;     // rows per segment (1 or 2); a segment is th x (32/th) output pixels = one TMEM lane quarter
     int segs_per_row, row_groups, total_segs, m_tiles, tiles_n;

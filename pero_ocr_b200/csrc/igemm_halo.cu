@@ -83,6 +83,12 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // FMT (compile time) = operand format of the input AND record format of the output (one format per engine)
     constexpr int planes = FMT == ACT_F16 ? 1 : 2;
     constexpr bool f8 = FMT == ACT_F16_F8;   // plane 1 = e5m2 correction operands: A plane ap meets B plane ap only
+    // IgemmParams::corr_mode: the e5m2 plane of a pixel is [lo'(cin) | hi8(cin)] bytes = kchunks 128-byte chunks.
+    // CORR_WEIGHT keeps the hi8 half only: with cin = 128 that is chunk 1, with cin = 64 the upper two K = 32 steps
+    // of the single chunk; CORR_NONE skips the plane.
+    const int corr = p.corr_mode;
+    auto skip_f8 = [&](int kc) { return corr == CORR_NONE || (corr == CORR_WEIGHT && kchunks == 2 && kc == 0); };
+    const int f8_k0 = (corr == CORR_WEIGHT && kchunks == 1) ? 2 : 0;
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -122,6 +128,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
             for (int kc = 0; kc < kchunks; ++kc)
                 for (int ap = 0; ap < planes; ++ap) {
+                    if (f8 && ap == 1 && skip_f8(kc)) continue;
                     ptx::mbar_wait(&a_empty[stage], phase ^ 1);
                     ptx::mbar_expect_tx_pred(&a_full[stage], kHaloBytes, leader);
                     ptx::tma_load_4d_pred(sA + stage * kHaloStage, &tmA, &a_full[stage], ap * p.cin + kc * 64,
@@ -141,6 +148,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
             for (int kc = 0; kc < kchunks; ++kc)
                 for (int ap = 0; ap < planes; ++ap) {
+                    if (f8 && ap == 1 && skip_f8(kc)) continue;
                     // fp16x3: A_hi meets B_hi and B_lo, A_lo meets B_hi only; fp16+fp8: A plane ap meets B plane ap
                     const int nbp = (ap == 0 && !f8) ? planes : 1;
                     for (int bp = 0; bp < nbp; ++bp)
@@ -180,6 +188,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kc = 0; kc < kchunks; ++kc) {
 #pragma unroll
                     for (int ap = 0; ap < planes; ++ap) {
+                        if (f8 && ap == 1 && skip_f8(kc)) continue;
                         ptx::mbar_wait(&a_full[as], aph);
                         const uint64_t a_base = desc_hi + ((sA_u + as * kHaloStage) >> 4);
                         const int nbp = (ap == 0 && !f8) ? planes : 1;
@@ -204,9 +213,10 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                             const uint64_t a_desc = a_base + (((r + tap / 3) * kHaloW + tap % 3) * 8);
 #pragma unroll
                                             for (int k = 0; k < 4; ++k) {
-                                                if (e5m2)
-                                                    ptx::mma_f8_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1u);
-                                                else
+                                                if (e5m2) {
+                                                    if (k >= f8_k0)
+                                                        ptx::mma_f8_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc8, 1u);
+                                                } else
                                                     ptx::mma_f16_ss(d0 + r * BN, a_desc + 2 * k, b_desc + 2 * k, idesc,
                                                                     (tap | k) != 0 ? 1u : started);
                                             }

@@ -79,7 +79,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int kchunks = p.cin >> 6;
     // FMT (compile time) = operand format of the input AND record format of an EPI_ACT_F16 output
     constexpr int npass = FMT == ACT_F16 ? 1 : (FMT == ACT_F16_HILO ? 3 : 2);
-    const int k_iters = npass * taps * kchunks;
+    // first 64-slot chunk of the e5m2 pass (IgemmParams::corr_mode): 0 = both corrections, kchunks/2 = weight side only
+    const int f8_kc0 = (npass != 2 || p.corr_mode == CORR_BOTH) ? 0 : (p.corr_mode == CORR_WEIGHT ? (kchunks >> 1) : kchunks);
+    const int k_iters = (npass == 2) ? taps * (2 * kchunks - f8_kc0) : npass * taps * kchunks;
     const int total_tiles = p.m_tiles * p.tiles_n;
 
     if (threadIdx.x == 0) {
@@ -128,7 +130,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int r = tap / p.kw;
                     const int s = tap - r * p.kw;
                     const int brow = (pb * taps + tap) * p.cout_pad + nt * BN;
-                    for (int kc = 0; kc < kchunks; ++kc) {
+                    for (int kc = (npass == 2 && pass == 1) ? f8_kc0 : 0; kc < kchunks; ++kc) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * C::kStageBytes;
                         uint8_t* sB = sA + kABytes;

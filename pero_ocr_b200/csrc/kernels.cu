@@ -314,7 +314,8 @@ __global__ void igemm_ref_kernel(const IgemmParams p, const __half* __restrict__
                     if (p.npass == 2 && pass == 1) {   // e5m2 correction operands: 2 * cin bytes each
                         const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a);
                         const uint8_t* b8 = reinterpret_cast<const uint8_t*>(b);
-                        for (int k = 0; k < 2 * p.cin; ++k) acc = fmaf(e5m2_to_f32(a8[k]), e5m2_to_f32(b8[k]), acc);
+                        const int k0 = p.corr_mode == CORR_BOTH ? 0 : (p.corr_mode == CORR_WEIGHT ? p.cin : 2 * p.cin);
+                        for (int k = k0; k < 2 * p.cin; ++k) acc = fmaf(e5m2_to_f32(a8[k]), e5m2_to_f32(b8[k]), acc);
                     } else {
                         for (int k = 0; k < p.cin; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
                     }

@@ -42,6 +42,12 @@ class LineRecognizer:
         self.num_classes = [l for l in layers if l['kind'] == _lib.CTC_HEAD][-1]['cout'] if any(
             l['kind'] == _lib.CTC_HEAD for l in layers) else None
         self._reserved = (0, 0)
+        self._layers = layers
+        self._kinds = [l['kind'] for l in layers]
+        self.corrections = {}
+        if precision == 'fp16f8w':       # the library's preset (engine.cu: b200ocr_create)
+            self.corrections = {i: _lib.CORR_WEIGHT for i, l in enumerate(layers)
+                                if l['kind'] == _lib.CONV and (l.get('kh') or 1) * (l.get('kw') or 1) == 9 and l['cin'] >= 256}
 
     def close(self):
         if getattr(self, '_h', None):
@@ -70,6 +76,74 @@ class LineRecognizer:
         g = C.c_double()
         total = self._lib.b200ocr_forward_flops(self._h, n, w, C.byref(g))
         return float(total), float(g.value)
+
+    def set_layer_correction(self, layer, mode):
+        """fp16f8 engines: correction terms of one layer's e5m2 pass (_lib.CORR_BOTH / CORR_WEIGHT / CORR_NONE)."""
+        _lib.check(self._lib.b200ocr_set_layer_correction(self._h, int(layer), int(mode)), self._h)
+        self.corrections[int(layer)] = int(mode)
+
+    def executed_passes(self, n, w):
+        """(FLOP-weighted tensor-core pass-equivalents of the GEMM layers, per-layer list)."""
+        per = np.zeros(len(self._kinds), dtype=np.float32)
+        total = self._lib.b200ocr_executed_passes(self._h, n, w, len(per), per.ctypes.data_as(C.c_void_p))
+        return float(total), per.tolist()
+
+    def autotune_precision(self, budget=3e-4, sample=None, candidates=None):
+        """Chooses, per layer, how much of the fp16f8 correction pass to execute, by MEASURED logit error: the
+        calibration batch is run with both correction terms everywhere (the parity-grade arithmetic, ~1e-4 of the
+        fp32 oracle), then layers are switched to the weight-side-only correction one at a time -- most tensor-core
+        work first -- and a switch is kept while max |logits - full-correction logits| over the calibration batch stays
+        within `budget` (absolute, in logit units).  `sample`: CUDA uint8 [n,H,w,3] crops representative of the
+        workload (default: 8 seeded noise lines of 512 px, the bench's input statistics).  Returns a dict with the
+        chosen modes, the measured deviation and the executed pass-equivalents.  Plain device work through the C ABI:
+        nothing here consults the oracle."""
+        torch = self.torch
+        if self.precision not in ('fp16f8', 'fp16f8w'):
+            raise ValueError('per-layer corrections exist in the fp16f8 precision only')
+        if sample is None:
+            g = torch.Generator(device='cpu').manual_seed(1234)
+            gray = torch.randint(0, 256, (8, self.line_height, 512, 1), generator=g, dtype=torch.uint8)
+            sample = gray.expand(-1, -1, -1, 3).contiguous().to(self.device)
+        n, _, w, _ = sample.shape
+        if candidates is None:
+            _, per = self.executed_passes(n, w)
+            flops = self.layer_gemm_flops(n, w)
+            candidates = [i for i in np.argsort(flops)[::-1].tolist() if flops[i] > 0 and self._kinds[i] == _lib.CONV]
+        for i in self.corrections:
+            self.set_layer_correction(i, _lib.CORR_BOTH)
+        base = self.forward(sample, want_logits=True)['logits'].clone()
+        chosen, worst = [], 0.0
+        for i in candidates:
+            self.set_layer_correction(i, _lib.CORR_WEIGHT)
+            dev = float((self.forward(sample, want_logits=True)['logits'] - base).abs().max().item())
+            if dev <= budget:
+                chosen.append(i)
+                worst = dev
+            else:
+                self.set_layer_correction(i, _lib.CORR_BOTH)
+        total, per = self.executed_passes(n, w)
+        return {'weight_only_layers': sorted(chosen), 'max_abs_dev_vs_full_correction': worst, 'budget': budget,
+                'executed_passes': total, 'per_layer_passes': per, 'calibration': [int(n), int(w)]}
+
+    def layer_gemm_flops(self, n, w):
+        """Algorithmic GEMM FLOPs of each layer at (n, w) (0 for layers without a contraction)."""
+        out, h, cw = [], self.line_height, w
+        for l in self._layers:
+            k = l['kind']
+            if k == _lib.CONV:
+                kh, kw_ = l.get('kh', 1) or 1, l.get('kw', 1) or 1
+                ho, wo = h + 2 * l.get('pad_h', 0) - kh + 1, cw + 2 * l.get('pad_w', 0) - kw_ + 1
+                out.append(2.0 * n * ho * wo * l['cin'] * l['cout'] * kh * kw_)
+                h, cw = ho // max(1, l.get('pool_h', 1) or 1), wo // max(1, l.get('pool_w', 1) or 1)
+            elif k == _lib.BILSTM:
+                out.append(2.0 * n * cw * l['cin'] * 8 * l['hidden'])
+            elif k == _lib.CTC_HEAD:
+                out.append(2.0 * n * cw * l['cin'] * l['cout'])
+            else:
+                if k == _lib.CONV_FIRST:
+                    pass
+                out.append(0.0)
+        return out
 
     def forward(self, crops, want_logits=True, want_confidence=False, want_best_path=False, out=None):
         """crops: CUDA uint8 tensor [N,H,W,3] (contiguous).  Returns dict of CUDA tensors; stream-ordered on torch's
@@ -179,8 +253,16 @@ class B200EngineLineOCR:
         if module is None:
             module = torch.jit.load(self.checkpoint, map_location='cpu')
         layers, n_classes = netdesc.describe_line_net(module)
-        if n_classes != len(self.characters) + 1:
-            raise ValueError(f'net emits {n_classes} classes, engine JSON implies {len(self.characters) + 1}')
+        # The blank is the LAST class (greedy_decode_ctc, pytorch_ocr_engine.py:27) and `characters` must name every
+        # other one.  pero checkpoints emit len(JSON characters) + 1 classes -- decoder_factory's letters are the JSON
+        # characters + '<BLANK>' (decoding_itf.py:49-50), so the U+200B appended at :42 sits in the blank's slot and is
+        # never emitted; a net with one class more (U+200B as a real symbol, blank after it) decodes through the same
+        # table.  The reference itself checks nothing (a too-small table is an IndexError in the join at :33).
+        if not (len(self.characters) <= n_classes <= len(self.characters) + 1):
+            raise ValueError(f'net emits {n_classes} classes; the engine JSON names {len(self.characters) - 1} characters '
+                             f'(+ U+200B), which fits {len(self.characters)} or {len(self.characters) + 1} classes with '
+                             f'the blank last')
+        self.num_classes = n_classes
         self.model = LineRecognizer(layers, precision=precision, line_height=self.line_px_height,
                                     device=self.device.index or 0)
         self._slots = None
@@ -454,8 +536,9 @@ class B200EngineLineOCR:
         from .decoders import CTCPrefixLogRawNumpyDecoder, full_logprobs_device, prefix_beam_device_ranges
         if not isinstance(decoder, CTCPrefixLogRawNumpyDecoder):
             raise TypeError('decode_lines fuses the GPU prefix beam decoder (CTCPrefixLogRawNumpyDecoder, lm=None)')
-        if len(decoder._letters) != len(self.characters) + 1:
-            raise ValueError('decoder letters must be the engine characters plus the blank symbol')
+        if len(decoder._letters) != self.num_classes:
+            raise ValueError(f'decoder has {len(decoder._letters)} letters (blank included), the net emits '
+                             f'{self.num_classes} classes')
         torch = self.model.torch
         pad, sub, height = self.line_padding_px, self.net_subsampling, self.line_px_height
         budget = self.max_input_horizontal_pixels

@@ -24,6 +24,7 @@ from ._lib import DEFAULT_PRECISION
 from .engine import LineRecognizer
 
 MIN_WIDTH = 1088          # transformer_ocr_engine.py:36-40
+MAX_SEQ_LEN = 2000        # transformer.py:12 (build_net's default, which the reference engine never overrides)
 
 
 class ARLineRecognizer(LineRecognizer):
@@ -150,6 +151,11 @@ class B200TransformerEngineLineOCR:
         self.max_line_width = 1e10                                              # line_ocr_engine.py:44-46
         if 'max_line_width' in self.config:
             self.max_line_width = int(self.config['max_line_width'])
+            # batches of split lines are max_line_width + 128 px wide (process_lines below); the recogniser takes
+            # widths that are multiples of 8 (16-byte pixel rows).  The reference accepts any value: fail here, with
+            # the reason, rather than at the first over-wide line
+            if self.max_line_width % 8:
+                raise ValueError(f'max_line_width must be a multiple of 8 for the B200 engine (got {self.max_line_width})')
         self.model_type = 'transformer'
         self.device = device if device is not None else torch.device('cuda', 0)
         if self.device.type != 'cuda':
@@ -177,6 +183,9 @@ class B200TransformerEngineLineOCR:
         signature compatibility; the uncached path computes the same function)."""
         torch = self.net.torch
         nhwc = np.ascontiguousarray(np.transpose(np.asarray(inputs), (0, 2, 3, 1)))
+        # the reference's cached attention holds max_seq_len = 2000 positions (transformer.py:12, 241): longer memories
+        # (lines of 8000 px and more) fail its assertion
+        assert nhwc.shape[2] // 4 < MAX_SEQ_LEN, f'MHA: Sequence longer than {MAX_SEQ_LEN} logits'
         with torch.cuda.device(self.device):
             dev = torch.from_numpy(nhwc).to(self.device)
             self.h2d_bytes += nhwc.nbytes

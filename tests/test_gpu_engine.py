@@ -243,3 +243,81 @@ def test_transformer_variant_on_a_very_long_line():
     srt = np.sort(ref, axis=1)
     decided = (srt[:, -1] - srt[:, -2]) > MARGIN                                                # [N, T]
     assert np.array_equal(out['best_path'].cpu().numpy()[decided], ref.argmax(axis=1)[decided])
+
+
+# ---- per-layer correction modes of the fp16f8 precision (b200ocr_set_layer_correction) ---------------------------
+
+def _case_recognizer(kind='lstm', precision='fp16f8'):
+    from pero_ocr_b200 import netdesc
+    from pero_ocr_b200.engine import LineRecognizer
+    layers, _ = netdesc.describe_line_net(make_case_net(kind))
+    return LineRecognizer(layers, precision=precision), layers
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+def test_layer_correction_modes_match_cuda_core_cross_check(mode):
+    """Weight-side-only (1) and no (2) e5m2 correction in EVERY contraction -- the halo kernel's chunk / K-step skips
+    (cin = 64 and 128) and the per-tap kernel's shortened e5m2 pass -- against the CUDA-core kernel walking the same
+    operand bytes."""
+    from pero_ocr_b200 import _lib
+    eng, layers = _case_recognizer()
+    for i, l in enumerate(layers):
+        if l['kind'] in (_lib.CONV, _lib.BILSTM, _lib.CTC_HEAD):
+            eng.set_layer_correction(i, mode)
+    rng = np.random.default_rng(11)
+    crops = torch.from_numpy(rng.integers(0, 256, (5, 40, 328, 3), dtype=np.uint8)).cuda()
+    a = {k: v.clone() for k, v in eng.forward(crops, want_logits=True).items()}
+    eng.use_reference_kernels(True)
+    b = eng.forward(crops, want_logits=True, out={})
+    torch.cuda.synchronize()
+    assert (a['logits'] - b['logits']).abs().max().item() <= 2e-4
+    total, per = eng.executed_passes(5, 328)
+    assert total == pytest.approx(1.5 if mode == 1 else 1.0)
+
+
+def test_no_correction_equals_single_pass_fp16():
+    """CORR_NONE leaves the fp16 hi * hi pass: the arithmetic of precision 'fp16' (accumulator at scale 2^11: exact)."""
+    from pero_ocr_b200 import _lib
+    eng, layers = _case_recognizer()
+    for i, l in enumerate(layers):
+        if l['kind'] in (_lib.CONV, _lib.BILSTM, _lib.CTC_HEAD):
+            eng.set_layer_correction(i, _lib.CORR_NONE)
+    plain, _ = _case_recognizer(precision='fp16')
+    rng = np.random.default_rng(12)
+    crops = torch.from_numpy(rng.integers(0, 256, (3, 40, 264, 3), dtype=np.uint8)).cuda()
+    a = eng.forward(crops, want_logits=True)['logits']
+    b = plain.forward(crops, want_logits=True)['logits']
+    torch.cuda.synchronize()
+    # same convolution arithmetic; the BiLSTM recurrence differs (three-pass split vs single fp16 pass)
+    assert (a - b).abs().max().item() <= 1.5e-3
+
+
+def test_weight_only_preset_holds_the_parity_bar(tmp_path, golden_dir):
+    """precision 'fp16f8w' (weight-side correction only in the deep 3x3 layers) against the unmodified reference's
+    outputs: the same 1e-3 logit bar and identical transcriptions; 1.7 instead of 2 pass-equivalents."""
+    gold = load_golden(golden_dir, 'engine_lstm.npz')
+    eng = _engine(tmp_path, 'lstm', precision='fp16f8w')
+    lines = cases.engine_lines('lstm')
+    tr, lg, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+    worst = max(float(np.abs(lg[i] - gold[f'logits_{i}']).max()) for i in range(len(lines)))
+    print(f'fp16f8w: worst |logit - reference| = {worst:.2e}')
+    assert worst <= TOL, worst
+    assert tr == list(gold['transcriptions'])
+    total, _ = eng.model.executed_passes(8, 512)
+    assert 1.6 < total < 1.8
+
+
+def test_autotune_precision_respects_its_budget():
+    eng, layers = _case_recognizer()
+    rep = eng.autotune_precision(budget=3e-4)
+    assert rep['max_abs_dev_vs_full_correction'] <= 3e-4
+    assert rep['executed_passes'] <= 2.0
+    rng = np.random.default_rng(13)
+    crops = torch.from_numpy(rng.integers(0, 256, (4, 40, 264, 3), dtype=np.uint8)).cuda()
+    net = make_case_net('lstm')
+    with torch.no_grad():
+        ref = net(torch.from_numpy(crops.cpu().numpy()).float().div(255.0).permute(0, 3, 1, 2)).numpy()
+    got = eng.forward(crops, want_logits=True)['logits'].cpu().numpy()
+    assert np.abs(got - ref.transpose(0, 2, 1)).max() <= TOL
+    strict = eng.autotune_precision(budget=0.0)
+    assert strict['weight_only_layers'] == [] and strict['executed_passes'] == pytest.approx(2.0)

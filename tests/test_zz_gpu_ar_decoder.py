@@ -135,3 +135,24 @@ def test_process_lines_splits_and_merges_on_the_device_path(tmp_path):
     assert tr[1] == t_parts[3] and np.array_equal(lg[1], l_parts[3][:len(t_parts[3])])
     sp_tr, sp_lg, _ = eng.process_lines(lines, sparse_logits=True)
     assert sp_tr == tr and sp_lg[0].shape == lg[0].shape
+
+
+def test_wide_case_matches_reference_golden(tmp_path, golden_dir):
+    """Second golden of the unmodified TransformerEngineLineOCR.transcribe_batch: 3 decoder layers, 122 classes
+    (partial 32-wide output tiles, several argmax passes per warp), no line emits the stop symbol, so the loop ends on
+    the length limit after W/4 + 1 = 289 steps (transformer_ocr_engine.py:79-82)."""
+    from pero_ocr_b200.transformer_engine import B200TransformerEngineLineOCR
+    spec = cases.AR_CASES['wide']
+    gold = load_golden(golden_dir, spec['golden'])
+    _, _, sd = cases.ar_state_dict(spec)
+    eng = B200TransformerEngineLineOCR(cases.write_ar_engine_json(tmp_path, spec=spec), torch.device('cuda', 0),
+                                       state_dict=sd)
+    outs, logits = eng.transcribe_batch(cases.ar_inputs(spec), is_cached=True)
+    assert logits.shape[1] == gold['logits'].shape[1] == spec['width'] // 4 + 1
+    worst, compared = _compare(logits, gold['logits'])
+    assert worst <= TOL, worst
+    if min(compared) == gold['logits'].shape[1]:
+        for i, o in enumerate(outs):
+            assert list(o) == list(gold['tokens'][i, :gold['lengths'][i]]), i
+    else:
+        assert min(compared) >= 40, compared
