@@ -6,9 +6,12 @@ CNN+BiLSTM recogniser), one process per GPU.
 
 A step = one pass of the hot path (pad/255 -> conv stack -> BiLSTM x2 -> CTC head + greedy collapse) over one batch
 of 256 lines.  `value` is device-resident throughput (crops already in HBM; CUDA events, max over ranks);
-`e2e` runs the same lines through B200EngineLineOCR.process_lines (host uint8 crops -> padded pinned batch -> H2D ->
-forward -> D2H of label ids -> strings), double-buffered, and for N>1 ends with the NCCL gather of label ids.
-`--impl reference` times the reference's algorithm on the host cores (torch-CPU oracle port: the reference ships
+`e2e` is the reference caller's own call, B200EngineLineOCR.process_lines(lines) with its default arguments
+(pero_ocr/document_ocr/page_parser.py:423: strings + sparse logits + logit_coords back on the host; host uint8 crops
+-> packed pinned staging -> H2D -> device pad -> forward -> device sparsification -> D2H), double-buffered, and for
+N>1 it ends with the NCCL gather of label ids; `e2e.no_logits` is the same with no_logits=True (strings only).
+At N=1 the same JSON line also carries BASELINE.json configs 3 and 4 (`config3`, `config4`) and the reference's own
+GPU path measured in this process (`incumbent_gpu`).  `--impl reference` times the reference's algorithm on the host cores (torch-CPU oracle port: the reference ships
 no recogniser weights or definition, so the seeded net of pero_ocr_b200/synthetic.py hosted by the oracle's restatement of the reference's engine logic is its CPU path).
 """
 import argparse
@@ -27,6 +30,9 @@ BATCH = 256
 WIDTH = 1280
 PADDED = WIDTH + 64
 METRIC = 'text-lines/sec (40x1280 crops)'
+WORKLOAD = {'lstm': 'config2: ocr_engine line recognizer, batch=256 synthetic 40x1280 gray crops (40x1344 padded), '
+                    'random-init CNN+BiLSTM, C=120',
+            'transformer': 'config3 forward: Transformer-encoder variant, batch=256 synthetic 40x1280 crops'}
 UNIT = 'lines/s'
 RESULT_OUT = sys.stdout
 
@@ -237,7 +243,7 @@ def ctc_decode_times(dev, with_cpu):
     """BASELINE.json metric part 2, 'CTC decode us/line': device-resident greedy (config 1: 128 x 256 x 120) and
     prefix beam k=16 (256 x 336 x 120 peaky log-probs), next to the reference algorithm on one host core."""
     import torch
-    from oracle import cases
+    from pero_ocr_b200 import synthetic as cases
     from pero_ocr_b200.decoders import greedy_ids_device, prefix_beam_device
     raw, lp, letters = cases.config1_logits()
     x = torch.from_numpy(np.ascontiguousarray(lp)).to(dev)
@@ -296,13 +302,177 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'config2: {sample}-line sample of the batch-256 40x1280 workload, random-init CNN+BiLSTM '
-                               f'(reference algorithm on host cores)', 'net': args.net, 'lines_per_step': sample},
+        'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'lines_per_step': sample,
+                   'sample': f'{sample} of the 256 lines of a step per timed step, in 32-line host batches '
+                             f'(a 256-line fp32 batch needs > 10 GB of host activations); same net, same arithmetic'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port',
                          'sample': f'{sample} lines x {args.steps} steps, torch-CPU fp32, {used} threads'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), file=RESULT_OUT, flush=True)
+
+
+def write_engine_json(n_chars=118):
+    import tempfile
+    from pero_ocr_b200 import synthetic
+    js = os.path.join(tempfile.mkdtemp(), 'ocr.json')
+    with open(js, 'w', encoding='utf8') as f:
+        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'unused.pt',
+                   'characters': synthetic.json_characters(n_chars), 'net_name': 'B200_BENCH'}, f)
+    return js
+
+
+def bench_config3(dev, peak_tf, with_cpu, lines_total=512):
+    """BASELINE.json config 3: Transformer-encoder variant + CTC prefix beam (k = 16), batch = 256 synthetic 40x1280
+    crops, through engine.decode_lines (host crops in, BagOfHypotheses out; the logits never leave the GPU)."""
+    import torch
+    from pero_ocr_b200 import synthetic
+    from pero_ocr_b200.decoders import BLANK_SYMBOL, CTCPrefixLogRawNumpyDecoder
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    net = make_net('transformer')
+    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=net)
+    eng.max_input_horizontal_pixels = BATCH * WIDTH
+    dec = CTCPrefixLogRawNumpyDecoder(eng.characters + [BLANK_SYMBOL], 16)
+    lines = list(synthetic.bench_crops(lines_total, WIDTH, seed=0))
+    eng.decode_lines(lines[:BATCH], dec)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    bags = eng.decode_lines(lines, dec)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # device-resident forward alone (CUDA events) for the roofline of this net
+    rec = eng.model
+    batch = torch.zeros((BATCH, 40, PADDED, 3), dtype=torch.uint8, device=dev)
+    batch[:, :, 32:32 + WIDTH] = torch.from_numpy(synthetic.bench_crops(BATCH, WIDTH, seed=1)).to(dev)
+    outs = {}
+    for _ in range(3):
+        rec.forward(batch, want_logits=False, out=outs)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        rec.forward(batch, want_logits=False, out=outs)
+    b.record()
+    torch.cuda.synchronize()
+    fwd_ms = a.elapsed_time(b) / 5
+    total_flops, gemm_flops = rec.flops(BATCH, PADDED)
+    ach = total_flops / (fwd_ms / 1e3) / 1e12
+    out = {'workload': 'config3: ocr_engine Transformer-encoder variant (2 encoder layers) + CTC prefix-beam (beam=16), '
+                       'batch=256 synthetic 40x1280 crops', 'metric': 'text-lines/sec incl. beam decode',
+           'value': lines_total / dt, 'unit': UNIT, 'lines': lines_total, 'ms_per_256_lines': 1e3 * dt * BATCH / lines_total,
+           'api': 'B200EngineLineOCR.decode_lines(lines, CTCPrefixLogRawNumpyDecoder(k=16))',
+           'forward_only': {'lines_per_s': BATCH / (fwd_ms / 1e3), 'ms_per_step': fwd_ms},
+           'hypotheses_per_line': float(np.mean([len(x) for x in bags])),
+           'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
+                        'algorithmic_gflop_per_line': total_flops / BATCH / 1e9, 'of': 'device-resident forward'}}
+    if with_cpu:
+        from oracle.decoders_oracle import prefix_beam
+        from oracle.forward_oracle import full_logprobs, sparsify_logits
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_cpu = 8
+        x = torch.from_numpy(np.ascontiguousarray(batch[:n_cpu].cpu().numpy())).float().div(255.0).permute(0, 3, 1, 2)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            lg = net(x).permute(0, 2, 1).numpy()
+        t_fwd = (time.perf_counter() - t0) / n_cpu
+        t0 = time.perf_counter()
+        for i in range(2):
+            prefix_beam(full_logprobs(sparsify_logits(lg[i]))[8:328].astype(np.float64), 16)
+        t_beam = (time.perf_counter() - t0) / 2
+        out['cpu_baseline'] = {'value': 1.0 / (t_fwd + t_beam), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                               'sample': f'{n_cpu} lines torch-CPU forward ({1e3 * t_fwd:.0f} ms/line, all cores) + 2 lines '
+                                         f'NumPy prefix beam ({1e3 * t_beam:.0f} ms/line, 1 core)'}
+    eng.model.close()
+    return out
+
+
+def bench_config4(dev, with_cpu, pages=16):
+    """BASELINE.json config 4: synthetic 4000x3000 pages through the ParseNet forward (conv-only stand-in, DOWNSAMPLE = 4
+    -> net input [1,3,768,1024]) + line OCR of an injected fixed layout of 60 baselines per page (random-
+    init maps give arbitrary line counts), the lines cropped on the device from the uploaded page.  The CPU geometry
+    between the two (cnn_layout_engine.py, shapely) is outside the path and not timed."""
+    import torch
+    from pero_ocr_b200 import synthetic
+    from pero_ocr_b200.cropper import B200LineCropper, DevicePage
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    from pero_ocr_b200.parsenet import B200ParseNet
+    pn = B200ParseNet(None, dev, downsample=4, adaptive_downsample=False, module=synthetic.make_net('parsenet', seed=1))
+    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=make_net('lstm'))
+    eng.max_input_horizontal_pixels = 64 * 1408
+    cropper = B200LineCropper(line_height=40, poly=2, scale=1)
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8) for _ in range(2)]     # alternated: 36 MB each
+    lines = []
+    for i in range(60):
+        y = 60 + i * 48
+        lines.append(([[100, y], [1400, y + rng.integers(-6, 7)], [2700, y + rng.integers(-6, 7)]], [26, 14]))
+    t = {'parsenet': 0.0, 'upload': 0.0, 'ocr': 0.0}
+
+    def one_page(img):
+        t0 = time.perf_counter()
+        maps = pn.get_maps(img, 4)                      # INTER_AREA resize on the host + conv forward + D2H of 5 maps
+        t1 = time.perf_counter()
+        page = DevicePage(img)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        tr, _, _ = eng.process_baselines(page, lines, cropper, no_logits=True)
+        t3 = time.perf_counter()
+        t['parsenet'] += t1 - t0; t['upload'] += t2 - t1; t['ocr'] += t3 - t2
+        return maps.shape, len(tr)
+
+    one_page(imgs[0])
+    one_page(imgs[1])
+    for k in t:
+        t[k] = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(pages):
+        shape, n_lines = one_page(imgs[i & 1])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {'workload': f'config4: {pages} synthetic 4000x3000 pages: ParseNet stand-in forward at downsample 4 (maps '
+                       f'{list(shape)}) + {n_lines} injected baselines per page cropped on the device (40 x ~1300 px) + '
+                       f'CNN+BiLSTM line OCR', 'metric': 'pages/sec', 'value': pages / dt, 'unit': 'pages/s',
+           'lines_per_s': pages * n_lines / dt, 'ms_per_page': 1e3 * dt / pages,
+           'ms_per_page_breakdown': {'parsenet_get_maps (host INTER_AREA resize + upload + conv forward + D2H)': 1e3 * t['parsenet'] / pages,
+                                     'upload_page_image': 1e3 * t['upload'] / pages,
+                                     'crop_and_ocr (process_baselines)': 1e3 * t['ocr'] / pages},
+           'api': 'B200ParseNet.get_maps + B200EngineLineOCR.process_baselines(DevicePage, baselines, B200LineCropper)'}
+    if with_cpu:
+        try:
+            import cv2
+            cv2.setNumThreads(os.cpu_count() or 1)
+            torch.set_num_threads(os.cpu_count() or 1)
+            net, pnet = make_net('lstm'), synthetic.make_net('parsenet', seed=1)
+            t0 = time.perf_counter()
+            small = cv2.resize(imgs[0], (0, 0), fx=0.25, fy=0.25, interpolation=cv2.INTER_AREA)
+            canvas = np.zeros((1, 768, 1024, 3), dtype=np.uint8)
+            canvas[0, :small.shape[0], :small.shape[1]] = small
+            with torch.no_grad():
+                pnet(torch.from_numpy(canvas).float().permute(0, 3, 1, 2) * (1 / 255.))
+            t_pn = time.perf_counter() - t0
+            maps = [cropper.get_crop_inputs(bl, hh, 40) for bl, hh in lines[:8]]
+            t0 = time.perf_counter()
+            crops = [cv2.remap(imgs[0], m[..., 0], m[..., 1], interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+                     for m in maps]
+            t_crop = (time.perf_counter() - t0) / len(maps)
+            w = max(c.shape[1] for c in crops)
+            batch = np.zeros((len(crops), 40, (w + 31) // 32 * 32 + 64, 3), dtype=np.uint8)
+            for i, c in enumerate(crops):
+                batch[i, :, 32:32 + c.shape[1]] = c
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                net(torch.from_numpy(batch).float().div(255.0).permute(0, 3, 1, 2))
+            t_ocr = (time.perf_counter() - t0) / len(crops)
+            per_page = t_pn + n_lines * (t_crop + t_ocr)
+            out['cpu_baseline'] = {'value': 1.0 / per_page, 'unit': 'pages/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                   'sample': f'1 page ParseNet stand-in torch-CPU ({1e3 * t_pn:.0f} ms) + 8 of {n_lines} lines: '
+                                             f'cv2.remap {1e3 * t_crop:.1f} ms/line + torch-CPU recogniser {1e3 * t_ocr:.0f} ms/line, '
+                                             f'extrapolated to {n_lines} lines'}
+        except ImportError as exc:
+            out['cpu_baseline'] = {'unavailable': str(exc)}
+    eng.model.close()
+    pn.close()
+    return out
 
 
 def main():
@@ -316,13 +486,18 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16f8'), choices=['fp16x3', 'fp16f8', 'fp16'])
+    ap.add_argument('--precision', default=os.environ.get('B200OCR_PRECISION', 'fp16f8'),
+                    choices=['fp16x3', 'fp16f8', 'fp16f8w', 'fp16'])
+    ap.add_argument('--autotune-budget', type=float, default=float(os.environ.get('B200OCR_AUTOTUNE_BUDGET', '3e-4')),
+                    help='fp16f8 only: per-layer weight-side-only correction while the measured logit deviation from '
+                         'the full correction stays within this (0 = full correction everywhere)')
     ap.add_argument('--net', default='lstm', choices=['lstm', 'transformer'])
     ap.add_argument('--ref-lines', type=int, default=96, help='lines per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-lines', type=int, default=512, help='bounded CPU sample (about 10-20 s of host work)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-incumbent', action='store_true', help="skip the reference's GPU eager path (N=1 only)")
     ap.add_argument('--incumbent-steps', type=int, default=5)
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 3 and 4 (N=1 only)')
     ap.add_argument('--profile-out', default=None, help='write the per-layer kernel table (JSON) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -334,10 +509,20 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # several ranks on one host: give each its own cores (the staging threads of 8 ranks otherwise share one
+    # affinity mask and migrate over each other)
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', str(world)))
+    if local_world > 1:
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // local_world)
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+        except (AttributeError, OSError):
+            pass
+
     import torch
     import torch.distributed as dist
     from pero_ocr_b200 import synthetic as cases
-    from pero_ocr_b200 import netdesc
     from pero_ocr_b200.engine import B200EngineLineOCR
     from pero_ocr_b200.sharding import gather_ids
 
@@ -347,17 +532,15 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     # ---- engine through the reference-facing constructor (engine JSON + module)
-    import tempfile
-    tmp = tempfile.mkdtemp()
-    js = os.path.join(tmp, 'ocr.json')
-    with open(js, 'w', encoding='utf8') as f:
-        json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': 'unused.pt',
-                   'characters': cases.json_characters(118), 'net_name': 'B200_BENCH'}, f)
     net = make_net(args.net)
-    engine = B200EngineLineOCR(js, dev, batch_size=8, precision=args.precision, module=net)
+    engine = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, precision=args.precision, module=net)
     engine.max_input_horizontal_pixels = BATCH * WIDTH          # as user_scripts/select_embed_id.py:54-55 does
     rec = engine.model
     rec.reserve(BATCH, PADDED)
+    tuned = None
+    if args.precision == 'fp16f8' and args.autotune_budget > 0:
+        tuned = rec.autotune_precision(budget=args.autotune_budget)
+    passes_total, passes_per_layer = rec.executed_passes(BATCH, PADDED)
 
     # ---- synthetic inputs: 4 distinct resident batches (165 MB > L2), seeded per rank
     n_rot = 4
@@ -377,6 +560,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -391,51 +580,60 @@ def main():
     ev1.record()
     barrier()
     launches = rec.launch_count - launches0
-    ms = ev0.elapsed_time(ev1)
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev = float(t.item())
     value = world * BATCH * args.steps / (ms_dev / 1e3)
 
-    # ---- end to end through process_lines (host crops in, strings out), then the gather of label ids
-    e2e_lines = [host_lines[i % (BATCH * n_rot)] for i in range(BATCH * args.steps)]
-    engine.process_lines(e2e_lines[:BATCH * 2], no_logits=True)             # warm-up: pinned buffers, slots
-    engine.h2d_bytes = engine.d2h_bytes = 0
-    engine.host_ms = {k: 0.0 for k in engine.host_ms}
-    barrier()
-    t0 = time.perf_counter()
-    ids, _, _ = engine.process_lines(e2e_lines, no_logits=True, return_ids=True)
-    gathered = 0
+    # ---- multi-GPU correctness on the hardware: every rank recognises the SAME batch (rank 0's first one); the
+    # gathered label ids of all ranks must be identical, line by line
+    parity = None
     if world > 1:
-        _, gathered = gather_ids(ids, [rank * len(ids) + i for i in range(len(ids))], world * len(ids))
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * len(e2e_lines) / float(t.item())
-    e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': engine.h2d_bytes // args.steps,
-           'd2h_bytes_per_step': engine.d2h_bytes // args.steps, 'gather_bytes_total': gathered,
-           'api': 'B200EngineLineOCR.process_lines(lines, no_logits=True)',
-           'host_ms_per_step_rank0': {k: v / args.steps for k, v in engine.host_ms.items()},
-           'host_threads': engine.host_threads}
+        common = list(cases.bench_crops(BATCH, WIDTH, seed=0))
+        ids, _, _ = engine.process_lines(common, no_logits=True, return_ids=True)
+        full, _ = gather_ids(ids, [rank * BATCH + i for i in range(BATCH)], world * BATCH)
+        same = all(np.array_equal(full[r * BATCH + i], full[i]) for r in range(1, world) for i in range(BATCH))
+        parity = {'ranks_agree_on_rank0_batch': bool(same), 'lines_compared': BATCH * (world - 1)}
+        if not same:
+            raise SystemExit('bench: ranks disagree on the label ids of the same batch')
 
-    # ---- the same call with logits (what PageOCR.process_page asks for), reported on stderr only: the random-init
-    # bench net keeps every class of every frame (p ~ 1/120 > 1e-4), which is the degenerate worst case of the sparse
-    # path (a trained recogniser keeps a handful of classes per frame)
-    if os.environ.get('B200OCR_BENCH_SPARSE'):
-        sp_lines = e2e_lines[:BATCH * 4]
-        engine.process_lines(sp_lines[:BATCH], sparse_logits=True)
+    # ---- end to end through process_lines, then the gather of label ids.  BASELINE config 5 at 8 GPUs: 100k lines.
+    total_lines = max(world * BATCH * args.steps, 100000 if world == 8 else 0)
+    per_rank = (total_lines + world * BATCH - 1) // (world * BATCH) * BATCH
+    e2e_lines = [host_lines[i % (BATCH * n_rot)] for i in range(per_rank)]
+    e2e_steps = per_rank // BATCH
+
+    def e2e_leg(**kw):
+        engine.process_lines(e2e_lines[:BATCH * 2], **kw)                   # warm-up: pinned buffers, slots
+        engine.h2d_bytes = engine.d2h_bytes = 0
+        engine.host_ms = {k: 0.0 for k in engine.host_ms}
         barrier()
         t0 = time.perf_counter()
-        _, sp_logits, _ = engine.process_lines(sp_lines, sparse_logits=True)
+        tr, lg, _ = engine.process_lines(e2e_lines, **kw)
+        gathered = 0
+        if world > 1:
+            ids = [np.frombuffer(t.encode('utf-32-le'), dtype=np.uint32).astype(np.int32) for t in tr]   # code points
+            _, gathered = gather_ids(ids, [rank * len(ids) + i for i in range(len(ids))], world * len(ids))
         torch.cuda.synchronize()
-        dt_sp = time.perf_counter() - t0
-        print(f'process_lines with sparse logits: {world * len(sp_lines) / dt_sp:.0f} lines/s, '
-              f'{np.mean([m.nnz / m.shape[0] for m in sp_logits[:8]]):.1f} entries kept per frame', file=sys.stderr)
-        del sp_logits
+        dt = max_over_ranks(time.perf_counter() - t0)
+        kept = float(np.mean([m.nnz / max(1, m.shape[0]) for m in lg[:8]])) if lg and lg[0] is not None else None
+        del lg
+        return {'value': world * len(e2e_lines) / dt, 'unit': UNIT, 'h2d_bytes_per_step': engine.h2d_bytes // e2e_steps,
+                'd2h_bytes_per_step': engine.d2h_bytes // e2e_steps, 'gather_bytes_total': gathered,
+                'host_ms_per_step_rank0': {k: v / e2e_steps for k, v in engine.host_ms.items()},
+                'logit_entries_kept_per_frame': kept}
+
+    e2e = e2e_leg()                                                         # the reference caller's call: defaults
+    e2e['api'] = 'B200EngineLineOCR.process_lines(lines)  [strings + sparse logits + logit_coords, page_parser.py:423]'
+    e2e['lines_total'] = world * len(e2e_lines)
+    e2e['host_threads'] = engine.host_threads
+    if e2e.get('logit_entries_kept_per_frame') and e2e['logit_entries_kept_per_frame'] > 60:
+        e2e['note'] = ('the random-init bench net keeps every class of every frame (p ~ 1/120 > 1e-4): the degenerate '
+                       'worst case of the sparse path (a trained recogniser keeps a handful of classes per frame)')
+    no_lg = e2e_leg(no_logits=True)
+    e2e['no_logits'] = {k: no_lg[k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'host_ms_per_step_rank0')}
+    e2e['no_logits']['api'] = 'B200EngineLineOCR.process_lines(lines, no_logits=True)  [strings only]'
+    if parity:
+        e2e['multi_gpu_parity'] = parity
 
     # ---- roofline leg: per-launch CUDA-event timing of the same step (separate from the timed region)
     rec.profile(True)
@@ -452,52 +650,89 @@ def main():
     n_igemm = int((tags == 1).sum()) // prof_steps
     peak_tf, peak_hbm, peak_src = peaks()
     achieved = gemm_flops / (igemm_ms / 1e3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'igemm_tc_kernel (tcgen05 implicit-GEMM conv/GEMM)',
+    roofline = {'bound': 'tensor', 'kernel': 'igemm_tc_kernel + igemm_halo_kernel (tcgen05 implicit-GEMM conv/GEMM)',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                 'peak_source': peak_src, 'traffic': None,
                 'algorithmic_gflop_per_line': gemm_flops / BATCH / 1e9,
                 'launches_per_step': n_igemm, 'avg_launch_ms': igemm_ms / max(n_igemm, 1),
                 'share_of_step': igemm_ms / (igemm_ms + lstm_ms + first_ms + other_ms),
                 'step_breakdown_ms': {'igemm_tc': igemm_ms, 'lstm_tc': lstm_ms, 'conv_first': first_ms, 'other': other_ms},
-                'executed_mma_passes': {'fp16x3': 3, 'fp16f8': 2, 'fp16': 1}[args.precision]}
+                'executed_mma_passes': passes_total,
+                'executed_mma_passes_per_layer': [round(x, 3) for x in passes_per_layer],
+                'executed_tflops': achieved * passes_total,
+                'whole_step': {'achieved': total_flops / (ms_dev / args.steps / 1e3) / 1e12,
+                               'frac': total_flops / (ms_dev / args.steps / 1e3) / 1e12 / peak_tf}}
     traffic, traffic_src = ncu_traffic(args.precision) if args.net == 'lstm' else (None, None)
     roofline['traffic'] = traffic
     roofline['traffic_source'] = traffic_src
+    per_layer = {}
+    for tg, li, m in zip(tags, lidx, pms):
+        key = f'layer{int(li):02d}_tag{int(tg)}'
+        per_layer[key] = per_layer.get(key, 0.0) + float(m) / prof_steps
+    roofline['per_layer_ms'] = {k: round(v, 4) for k, v in per_layer.items()}
     if args.profile_out and rank == 0:
-        per_layer = {}
-        for tg, li, m in zip(tags, lidx, pms):
-            key = f'layer{int(li):02d}_tag{int(tg)}'
-            per_layer[key] = per_layer.get(key, 0.0) + float(m) / prof_steps
         with open(args.profile_out, 'w') as f:
-            json.dump({'precision': args.precision, 'per_layer_ms': per_layer, 'roofline': roofline}, f, indent=1)
+            json.dump({'precision': args.precision, 'autotune': tuned, 'per_layer_ms': per_layer, 'roofline': roofline}, f, indent=1)
+
+    # ---- the same step under the other arithmetic choices of this engine (device-resident, 5 steps each)
+    variants = None
+    if rank == 0 and args.precision == 'fp16f8' and args.net == 'lstm':
+        from pero_ocr_b200 import _lib as L
+        variants = {}
+        gemm_layers = [i for i, k in enumerate(rec._kinds) if k in (L.CONV, L.BILSTM, L.CTC_HEAD)]
+        saved = dict(rec.corrections)
+        for name, mode in (('full_correction_everywhere (2 passes)', L.CORR_BOTH),
+                           ('no_correction = plain fp16, the mantissa of the incumbent\'s TF32 (1 pass)', L.CORR_NONE)):
+            for i in gemm_layers:
+                rec.set_layer_correction(i, mode)
+            for i in range(2):
+                step(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(5):
+                step(i)
+            b.record()
+            torch.cuda.synchronize()
+            variants[name] = {'lines_per_s': BATCH * 5 / (a.elapsed_time(b) / 1e3), 'ms_per_step': a.elapsed_time(b) / 5}
+        for i in gemm_layers:
+            rec.set_layer_correction(i, saved.get(i, L.CORR_BOTH))
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': {'fp16x3': 'f16x3 (fp16 hi/lo split operands, fp32 accumulate)',
                   'fp16f8': 'f16+e5m2 (fp16 pass + e5m2 first-order correction pass, fp32 accumulate)',
+                  'fp16f8w': 'f16+e5m2 (fp16 pass + e5m2 correction pass, weight side only in the deep layers)',
                   'fp16': 'f16 (fp32 accumulate)'}[args.precision],
         'data': 'synthetic',
-        'config': {'workload': 'config2: ocr_engine line recognizer, batch=256 synthetic 40x1280 gray crops (40x1344 padded), '
-                               'random-init CNN+BiLSTM, C=120' if args.net == 'lstm' else
-                               'config3 forward: Transformer-encoder variant, batch=256 synthetic 40x1280 crops',
+        'config': {'workload': WORKLOAD[args.net],
                    'net': args.net, 'lines_per_step': BATCH, 'precision': args.precision,
+                   'precision_autotune': tuned,
                    'l2_policy': f'{n_rot} distinct resident input batches (165 MB) rotated; per-step activations (>3 GB) exceed L2',
                    'parallelism': f'batch-parallel x{world}, no data-path collective'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
     }
+    if variants:
+        line['precision_variants'] = variants
     if rank == 0:
         line['ctc_decode'] = ctc_decode_times(dev, with_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, dt_cpu, used = cpu_reference_lines_per_s(args.net, args.cpu_baseline_lines)
         line['cpu_baseline'] = {'value': r, 'unit': UNIT, 'cores': used, 'kind': 'port',
                                 'sample': f'{args.cpu_baseline_lines} lines of the same workload in {dt_cpu:.1f} s, torch-CPU fp32'}
+    if rank == 0 and world == 1 and not args.no_configs:
+        for key, fn in (('config3', lambda: bench_config3(dev, peak_tf, not args.no_cpu_baseline)),
+                        ('config4', lambda: bench_config4(dev, not args.no_cpu_baseline))):
+            try:
+                line[key] = fn()
+            except Exception as exc:                                        # noqa: BLE001  (never lose the headline)
+                line[key] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
     if rank == 0 and world == 1 and not args.no_incumbent:
         # the reference's GPU path on the same device, right after the timed region (library kernels: the baseline)
         inc = incumbent_gpu(args.net, dev, steps=args.incumbent_steps, ours=rec)
         if inc.get('lines_per_s'):
             inc['value_over_incumbent'] = value / inc['lines_per_s']
-            inc['e2e_over_incumbent_e2e'] = e2e_value / inc['e2e_lines_per_s'] if inc.get('e2e_lines_per_s') else None
+            inc['e2e_over_incumbent_e2e'] = e2e['value'] / inc['e2e_lines_per_s'] if inc.get('e2e_lines_per_s') else None
         line['incumbent_gpu'] = inc
     if rank == 0:
         print(json.dumps(line), file=RESULT_OUT, flush=True)

@@ -198,6 +198,15 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
                         const int64_t* coord_off, const int32_t* widths, int32_t n, int32_t line_h, uint8_t* out,
                         int32_t out_w, int32_t pad, void* cuda_stream);
 
+/* Replaces the zero padding + stacking of BaseEngineLineOCR.process_lines (pero_ocr/ocr_engine/line_ocr_engine.py:
+ * 121-127: `batch_data[i, :, 32:32 + w_i] = line_i`, lines beyond the batch width cut) on the device, so that the host
+ * stages each crop with ONE contiguous copy and no padding bytes cross PCIe.
+ *   packed    device u8: the crops back to back, crop i = [line_h][w_i][3] at byte offset line_off[i] (device i64 [n])
+ *   widths    device i32 [n]  w_i
+ *   out       device u8 [n][line_h][out_w][3] (out_w a multiple of 4): columns [pad, pad + w_i) hold crop i, the rest 0 */
+int b200ocr_pad_lines(const uint8_t* packed, const int64_t* line_off, const int32_t* widths, int32_t n, int32_t line_h,
+                      uint8_t* out, int32_t out_w, int32_t pad, void* cuda_stream);
+
 /* One text line for b200ocr_remap_poly_lines: what the host keeps of EngineLineCropper.get_crop_inputs
  * (crop_engine.py:54-73) for the `poly` > 0 configurations -- the fitted baseline polynomial in the rotated frame and
  * the arc-length resampling constants; the device evaluates the rest (:74-99). */
@@ -322,7 +331,9 @@ int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, i
  * operands, fp32 accumulate) so the tcgen05 path can be checked on a GPU box where the reference is absent. */
 int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
 /* A/B switches for kernel variants (tests, profiling).  flag 1: halo-reuse 3x3 kernel for cin <= 128 (default on);
- * flag 2: split-K kernel for the per-step projections of b200ocr_ar_transcribe (default on; 0 = one K walker per tile). */
+ * flag 2: split-K kernel for the per-step projections of b200ocr_ar_transcribe (default on; 0 = one K walker per tile);
+ * flag 3: the BiLSTM recurrence also multiplies the fp16 rounding residual of h_t (three passes and twice the SM-to-SM
+ * exchange per step; default on only in B200OCR_PREC_FP16X3). */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

@@ -6,7 +6,7 @@ so the GPU box regenerates bit-identical inputs and weights without shipping the
 import numpy as np
 from scipy.special import log_softmax
 
-from pero_ocr_b200.synthetic import bench_crops, json_characters  # noqa: F401
+from pero_ocr_b200.synthetic import bench_crops, config1_logits, json_characters, peaky_logprobs  # noqa: F401
 
 BLANK = '<BLANK>'
 
@@ -36,36 +36,6 @@ def engine_lines(kind):
     # one genuinely coloured line: the net sees 3 distinct channels
     lines[1] = rng.integers(0, 256, lines[1].shape, dtype=np.uint8)
     return lines
-
-
-def config1_logits():
-    """BASELINE.json config 1: 128 lines x T=256 x C=120, blank last."""
-    rng = np.random.default_rng(1234)
-    raw = (rng.standard_normal((128, 256, 120)) * 4).astype(np.float32)
-    lp = log_softmax(raw, axis=2)
-    letters = [chr(0x100 + i) for i in range(119)] + [BLANK]
-    return raw, lp, letters
-
-
-def peaky_logprobs(rng, n, t, c, sharp=9.0, p_blank=0.55, p_repeat=0.3):
-    """Log-probabilities shaped like a trained CTC net's: one dominant class per frame, blank-heavy,
-    with repeats, plus low-level noise so that a few classes pass the decoder's > -10 relevance gate."""
-    out = np.empty((n, t, c), dtype=np.float64)
-    for i in range(n):
-        raw = rng.standard_normal((t, c)) * 1.5
-        prev = c - 1
-        for f in range(t):
-            u = rng.random()
-            if u < p_blank:
-                k = c - 1
-            elif u < p_blank + p_repeat and prev != c - 1:
-                k = prev
-            else:
-                k = int(rng.integers(0, c - 1))
-            raw[f, k] += sharp * rng.uniform(0.4, 1.0)
-            prev = k
-        out[i] = log_softmax(raw, axis=1)
-    return out
 
 
 def peaky_cases():

@@ -82,6 +82,8 @@ EXPORTS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'b200ocr_remap_lines': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    'b200ocr_pad_lines': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
     'b200ocr_remap_poly_lines': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'b200ocr_sparsify_logits': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -102,7 +102,8 @@ struct ArState {
 struct b200ocr_engine {
     int device = 0, num_sms = 148, precision = 0, planes = 1, npass = 1, line_height = 40;
     int fmt = ACT_F16;        // activation record format between layers (actfmt.cuh)
-    int lstm_planes = 1;      // arithmetic of the LSTM recurrence (1 = fp16, 2 = fp16x3)
+    int lstm_planes = 1;      // fp16 planes of W_hh in the LSTM recurrence (1 = fp16, 2 = hi + lo)
+    int lstm_hplanes = 1;     // planes of h_t exchanged and multiplied per step (<= lstm_planes; lstm_tc.cuh)
     bool use_ref = false;
     bool use_halo = true;
     std::vector<LayerRT> layers;
@@ -446,7 +447,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                         CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->fmt, e->planes == 1, o, st));
                     } else {
                         ProfScope ps(e, st, PROF_LSTM);
-                        CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->lstm_planes, e->fmt, st));
+                        CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->lstm_planes, e->lstm_hplanes, e->fmt, st));
                     }
                     e->launches++;
                     cur_h = o;
@@ -634,7 +635,7 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
     e->precision = desc->precision;
     switch (desc->precision) {
         case B200OCR_PREC_FP16: e->fmt = ACT_F16; e->planes = 1; e->npass = 1; e->lstm_planes = 1; break;
-        case B200OCR_PREC_FP16X3: e->fmt = ACT_F16_HILO; e->planes = 2; e->npass = 3; e->lstm_planes = 2; break;
+        case B200OCR_PREC_FP16X3: e->fmt = ACT_F16_HILO; e->planes = 2; e->npass = 3; e->lstm_planes = e->lstm_hplanes = 2; break;
         case B200OCR_PREC_FP16F8:
         case B200OCR_PREC_FP16F8W: e->fmt = ACT_F16_F8; e->planes = 2; e->npass = 2; e->lstm_planes = 2; break;
         default: return bail(fail(e, B200OCR_E_INVALID, "unknown precision %d", desc->precision));
@@ -987,6 +988,17 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
     return B200OCR_OK;
 }
 
+int b200ocr_pad_lines(const uint8_t* packed, const int64_t* line_off, const int32_t* widths, int32_t n, int32_t line_h,
+                      uint8_t* out, int32_t out_w, int32_t pad, void* cuda_stream) {
+    if (n < 0 || line_h <= 0 || !out || out_w <= 0 || (out_w % 4) || pad < 0 || (n > 0 && (!packed || !line_off || !widths)))
+        return fail(nullptr, B200OCR_E_INVALID, "bad pad_lines arguments");
+    if (n == 0) return B200OCR_OK;
+    DeviceGuard guard(out);
+    CU_TRY(nullptr, launch_pad_lines(packed, line_off, widths, n, line_h, out, out_w, pad,
+                                     static_cast<cudaStream_t>(cuda_stream)));
+    return B200OCR_OK;
+}
+
 int b200ocr_remap_poly_lines(const uint8_t* image, int32_t img_h, int32_t img_w, const b200ocr_poly_line_t* lines,
                              const double* offsets, int32_t n, int32_t line_h, uint8_t* out, int32_t out_w,
                              int32_t pad, void* cuda_stream) {
@@ -1257,6 +1269,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     if (!e) return B200OCR_E_INVALID;
     if (flag == 1) e->use_halo = value != 0;
     else if (flag == 2) e->ar.linear_variant = value != 0 ? 1 : 0;
+    else if (flag == 3) e->lstm_hplanes = (value != 0 && e->lstm_planes == 2) ? 2 : 1;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

@@ -54,6 +54,9 @@ cudaError_t launch_char_conf(const float* logp, int n, int t_max, int C, const i
                              int l_max, const int32_t* lengths, const int32_t* char_pos, float* conf,
                              cudaStream_t stream);
 
+// Packed host crops -> zero-padded recogniser batch (remap.cu; line_ocr_engine.py:121-127).
+cudaError_t launch_pad_lines(const uint8_t* packed, const int64_t* line_off, const int32_t* widths, int n, int line_h,
+                             uint8_t* out, int out_w, int pad, cudaStream_t stream);
 // Bilinear 8-bit remap of all lines of a page into the padded recogniser batch (remap.cu; crop_engine.py:146-163).
 cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
                                const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,

@@ -25,6 +25,7 @@
 //     copies per plane doubled the step time; staging h_t in L2 and bringing it back with one multicast
 //     cp.async.bulk per CTA cost 370 cycles/step more than the pushes -- the generic->async proxy fence on global
 //     memory alone is ~900 cycles.)
+#include "once.cuh"
 #include "lstm_tc.cuh"
 #include "actfmt.cuh"
 #include "ptx.cuh"
@@ -105,14 +106,14 @@ __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
 template <bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, __half* __restrict__ out,
-               int n_lines, int T, int planes, int out_fmt, int pair_groups, long long* __restrict__ dbg) {
+               int n_lines, int T, int planes, int hplanes, int out_fmt, int pair_groups, long long* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp = tid >> 8;              // which line group this half of the CTA serves
     const int gt = tid & (kGThreads - 1);  // thread index within the half
     const int gwarp = gt >> 5;
-    const int group_bytes = 2 * planes * kHPlane;      // two B buffers
+    const int group_bytes = 2 * hplanes * kHPlane;     // two B buffers
     uint8_t* sH = smem + grp * group_bytes;
     float* sG = reinterpret_cast<float*>(smem + kGroups * group_bytes) + grp * 128 * kGStride;   // [128][33]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGroups * group_bytes + kGroups * 128 * kGStride * 4);
@@ -125,7 +126,12 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
     const int dir = cluster / pair_groups;
     const int line0 = ((cluster - dir * pair_groups) * kGroups + grp) * kLines;
     const bool active = line0 < n_lines;   // the same in every CTA of the cluster
-    const int npass = planes == 2 ? 3 : 1;
+    // planes = fp16 planes of W_hh in TMEM (hi, lo), hplanes = planes of h_t that are exchanged and multiplied:
+    //   (2, 2) W_hi h_hi + W_hi h_lo + W_lo h_hi   (fp16x3)
+    //   (2, 1) W_hi h_hi + W_lo h_hi               h_t rounded to fp16 once per step, weights exact to ~2^-22: the
+    //          logits move by 3e-5 (tools/emulate_mixed_precision.py) and the exchange -- the kernel's bound -- halves
+    //   (1, 1) W_hi h_hi                           (fp16)
+    const int npass = planes == 2 ? (hplanes == 2 ? 3 : 2) : 1;
 
     if (tid == 0) {
         for (int i = 0; i < kGroups * kBarsPerGroup; ++i) ptx::mbar_init(&bars[i], 1);
@@ -181,7 +187,7 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
 #pragma unroll
     for (int e = 0; e < 4; ++e) c_state[e] = 0.f;
     // byte offset of (line nl, units unit0..unit0+3) of plane 0 inside a B buffer (plane 1 at + kSliceBytes)
-    const uint32_t slice_off = rank * planes * kSliceBytes + (ug >> 1) * 512 + (nl >> 3) * 128 + (nl & 7) * 16 + (ug & 1) * 8;
+    const uint32_t slice_off = rank * hplanes * kSliceBytes + (ug >> 1) * 512 + (nl >> 3) * 128 + (nl & 7) * 16 + (ug & 1) * 8;
     uint32_t mphase = 0;
 
     // optional per-phase cycle counters of CTA 0 / thread 0 (bring-up: B200OCR_LSTM_DBG=1)
@@ -212,17 +218,18 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
                 PROBE(0);
                 ptx::tc_fence_after();
                 constexpr uint32_t idesc = ptx::idesc_f16_f32(128, kLines);
-                const uint32_t h_base = ptx::smem_u32(sH) + b * planes * kHPlane;
+                const uint32_t h_base = ptx::smem_u32(sH) + b * hplanes * kHPlane;
                 if (ptx::elect_one()) {
                     // fully unrolled with compile-time offsets: runtime-indexed descriptors cost ~100 cycles per MMA in
                     // uniform-datapath address arithmetic (profiles/r01c_lstm_phases.log)
                     for (int pass = 0; pass < npass; ++pass) {
-                        const uint32_t wa = kWCol0 + ((pass == 2) ? 128 : 0);            // W plane (TMEM columns)
-                        const uint32_t ha = h_base + ((pass == 1) ? kSliceBytes : 0);    // h plane inside each slice block
+                        const bool w_lo = hplanes == 2 ? pass == 2 : pass == 1;
+                        const uint32_t wa = kWCol0 + (w_lo ? 128 : 0);                   // W plane (TMEM columns)
+                        const uint32_t ha = h_base + ((hplanes == 2 && pass == 1) ? kSliceBytes : 0);   // h plane inside each slice block
 #pragma unroll
                         for (int k16 = 0; k16 < 16; ++k16) {
                             const uint64_t b_desc =
-                                smem_desc_nosw(ha + (k16 >> 1) * planes * kSliceBytes + (k16 & 1) * 1024, 512, 128);
+                                smem_desc_nosw(ha + (k16 >> 1) * hplanes * kSliceBytes + (k16 & 1) * 1024, 512, 128);
                             ptx::mma_f16_ts(acc_u + (k16 & (kAccs - 1)) * kLines, wa + k16 * 8, b_desc, idesc,
                                             (pass != 0 || k16 >= kAccs) ? 1u : 0u);
                         }
@@ -298,9 +305,9 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
         if (s + 1 < T) {
             // own slice (hi | lo contiguous) of the next B buffer, then ONE bulk push per peer: a cp.async.bulk
             // shared::cta -> shared::cluster costs ~0.5 us and they serialise, so planes share a copy
-            uint8_t* hb = sH + nb * planes * kHPlane;
+            uint8_t* hb = sH + nb * hplanes * kHPlane;
             *reinterpret_cast<uint2*>(hb + slice_off) = make_uint2(hi_w[0], hi_w[1]);
-            if (planes == 2) *reinterpret_cast<uint2*>(hb + slice_off + kSliceBytes) = make_uint2(lo_w[0], lo_w[1]);
+            if (hplanes == 2) *reinterpret_cast<uint2*>(hb + slice_off + kSliceBytes) = make_uint2(lo_w[0], lo_w[1]);
             fence_proxy_async_smem();
             ptx::named_bar_sync(1 + grp, kGThreads);
             PROBE(3);
@@ -309,7 +316,7 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
                 // seven per-slice mbarriers so that the MMAs of a slice can start as it lands, they were slower: with
                 // two groups per SM the exchange runs at the SM-to-SM network's ~20 B/clk per SM
                 // (profiles/r01c_lstm_phases.log)
-                const uint32_t bytes = planes * kSliceBytes;
+                const uint32_t bytes = hplanes * kSliceBytes;
                 const uint32_t lead = ptx::elect_one() ? 1u : 0u;
                 ptx::mbar_expect_tx_pred(&hfull[nb], (kCl - 1) * bytes, lead);
                 const uint32_t bar = ptx::smem_u32(&hfull[nb]);
@@ -354,23 +361,23 @@ lstm_tc_kernel(const __half* __restrict__ w_rec, const float* __restrict__ pre, 
 
 }  // namespace
 
-size_t lstm_tc_smem_bytes(int planes) {
-    return kGroups * (2 * static_cast<size_t>(planes) * kHPlane + 128 * kGStride * sizeof(float)) + 128 + 1024;
+size_t lstm_tc_smem_bytes(int hplanes) {
+    return kGroups * (2 * static_cast<size_t>(hplanes) * kHPlane + 128 * kGStride * sizeof(float)) + 128 + 1024;
 }
 
 cudaError_t launch_lstm_tc(const __half* w_rec, const float* pre, __half* out, int n_lines, int T, int H, int planes,
-                           int out_fmt, cudaStream_t stream) {
-    if (H != kH) return cudaErrorInvalidValue;
-    const size_t smem = lstm_tc_smem_bytes(planes);
-    static int init = 0;
+                           int hplanes, int out_fmt, cudaStream_t stream) {
+    if (H != kH || hplanes < 1 || hplanes > planes) return cudaErrorInvalidValue;
+    const size_t smem = lstm_tc_smem_bytes(hplanes);
+    static PerDeviceOnce init;
     static long long* dbg = nullptr;   // bring-up only (B200OCR_LSTM_DBG=1): per-phase cycle counters, synchronises
-    if (!init) {
+    if (init.pending()) {
         cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        if (getenv("B200OCR_LSTM_DBG")) cudaMalloc(reinterpret_cast<void**>(&dbg), 9 * sizeof(long long));
-        init = 1;
+        if (getenv("B200OCR_LSTM_DBG") && !dbg) cudaMalloc(reinterpret_cast<void**>(&dbg), 9 * sizeof(long long));
+        init.mark();
     }
     const int pair_groups = (n_lines + kGroups * kLines - 1) / (kGroups * kLines);
     cudaLaunchConfig_t cfg = {};
@@ -386,11 +393,11 @@ cudaError_t launch_lstm_tc(const __half* w_rec, const float* pre, __half* out, i
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (!dbg)
-        return cudaLaunchKernelEx(&cfg, lstm_tc_kernel<false>, w_rec, pre, out, n_lines, T, planes, out_fmt, pair_groups,
+        return cudaLaunchKernelEx(&cfg, lstm_tc_kernel<false>, w_rec, pre, out, n_lines, T, planes, hplanes, out_fmt, pair_groups,
                                   dbg);
     int max_clusters = -1;
     cudaOccupancyMaxActiveClusters(&max_clusters, lstm_tc_kernel<true>, &cfg);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true>, w_rec, pre, out, n_lines, T, planes, out_fmt,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true>, w_rec, pre, out, n_lines, T, planes, hplanes, out_fmt,
                                        pair_groups, dbg);
     if (e == cudaSuccess) {
         long long h[9];

@@ -121,6 +121,38 @@ cudaError_t launch_remap_poly_lines(const uint8_t* img, int img_h, int img_w, co
     return cudaGetLastError();
 }
 
+// Zero padding + stacking of host crops (line_ocr_engine.py:121-127) on the device: the crops arrive packed back to
+// back ([line_h][w_i][3] each, one contiguous host copy per line), and this kernel spreads them into the padded
+// batch.  One thread per 4 output bytes of a row (rows are out_w * 3 bytes, out_w a multiple of 8: 4-byte aligned).
+__global__ void __launch_bounds__(256) pad_lines_kernel(const uint8_t* __restrict__ packed,
+                                                        const int64_t* __restrict__ line_off,
+                                                        const int32_t* __restrict__ widths, int line_h,
+                                                        uint8_t* __restrict__ out, int out_w, int pad) {
+    const int line = blockIdx.z, y = blockIdx.y;
+    const int row_bytes = out_w * 3;
+    const int b0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (b0 >= row_bytes) return;
+    const int w = min(widths[line], out_w - pad);           // lines cut at the batch width keep their left part
+    const int lo = pad * 3, hi = (pad + max(w, 0)) * 3;     // byte range of the row that holds crop pixels
+    const uint8_t* src = packed + line_off[line] + static_cast<size_t>(y) * widths[line] * 3 - lo;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = b0 + k;
+        if (b >= lo && b < hi) v |= static_cast<uint32_t>(__ldg(src + b)) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(line) * line_h + y) * row_bytes + b0) = v;
+}
+
+cudaError_t launch_pad_lines(const uint8_t* packed, const int64_t* line_off, const int32_t* widths, int n, int line_h,
+                             uint8_t* out, int out_w, int pad, cudaStream_t stream) {
+    if (n <= 0 || out_w <= 0) return cudaSuccess;
+    if (n > 65535 || line_h > 65535 || (out_w & 3)) return cudaErrorInvalidValue;
+    dim3 grid((out_w * 3 / 4 + 255) / 256, line_h, n);
+    pad_lines_kernel<<<grid, 256, 0, stream>>>(packed, line_off, widths, line_h, out, out_w, pad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_remap_lines(const uint8_t* img, int img_h, int img_w, const float* coords, const int64_t* coord_off,
                                const int32_t* widths, int n, int line_h, uint8_t* out, int out_w, int pad,
                                cudaStream_t stream) {

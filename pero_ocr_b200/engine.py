@@ -271,7 +271,11 @@ class B200EngineLineOCR:
         # it, none when several ranks share the host (torchrun exports LOCAL_WORLD_SIZE)
         import os
         ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
-        self.host_threads = max(1, min(4, (os.cpu_count() or 2) // (4 * ranks)))
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cores = os.cpu_count() or 2
+        self.host_threads = max(1, min(4, cores // ranks if ranks > 1 else cores // 4))
         self.host_ms = {'stage': 0.0, 'wait': 0.0, 'finish': 0.0}      # where process_lines spends host time
         self._executor = None
         self.want_confidence = False
@@ -299,10 +303,63 @@ class B200EngineLineOCR:
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._slots[k]
 
-    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None, device_fill=None):
-        """Stage one padded uint8 batch of `shape` (filled in place by `fill(view)` in pinned host memory and copied
-        to the device on the side stream -- or produced on the device by `device_fill(dev_batch)`), run the forward
-        on the current stream and start the device->host copies of the results."""
+    def _stage_packed(self, sl, crops, shape, dev, main):
+        """Host crops -> device batch without a padded host copy: every crop is copied ONCE, contiguously, into a
+        pinned buffer ([offsets i64 n | widths i32 n | crops back to back]), one H2D copy on the side stream brings it
+        over, and b200ocr_pad_lines spreads it into the zero-padded batch (line_ocr_engine.py:121-127)."""
+        torch = self.model.torch
+        n, height, width, _ = shape
+        pad = self.line_padding_px
+        t0 = time.perf_counter()
+        widths = np.empty(n, dtype=np.int32)
+        for i, line in enumerate(crops):
+            if line.ndim != 3 or line.shape[0] != height or line.shape[2] != 3:
+                raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
+            widths[i] = line.shape[1]
+        head = (n * 12 + 255) // 256 * 256
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(widths.astype(np.int64) * (3 * height), out=offs[1:])
+        total = head + int(offs[n])
+        if sl.get('pk_pin') is None or sl['pk_pin'].numel() < total:
+            cap = int(total * 1.25) + 4096
+            sl['pk_pin'] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            sl['pk_dev'] = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        pin = sl['pk_pin'].numpy()
+        pin[:n * 8].view(np.int64)[:] = offs[:n]
+        pin[n * 8:n * 12].view(np.int32)[:] = widths
+        body = pin[head:total]
+
+        def copy_range(lo, hi):
+            for i in range(lo, hi):
+                line = crops[i]
+                dst = body[offs[i]:offs[i + 1]].reshape(line.shape)
+                if line.dtype != np.uint8:
+                    raise ValueError('line crops must be uint8')
+                np.copyto(dst, line)
+
+        workers = min(self.host_threads, max(1, n // 16))
+        if workers <= 1:
+            copy_range(0, n)
+        else:
+            step = (n + workers - 1) // workers
+            for j in [self._pool().submit(copy_range, lo, min(n, lo + step)) for lo in range(0, n, step)]:
+                j.result()
+        self.host_ms['stage'] += 1e3 * (time.perf_counter() - t0)
+        pk = sl['pk_dev']
+        with torch.cuda.stream(self._copy_stream):
+            pk[:total].copy_(sl['pk_pin'][:total], non_blocking=True)
+            sl['h2d'].record(self._copy_stream)
+        main.wait_event(sl['h2d'])
+        base = pk.data_ptr()
+        _lib.check(self.model._lib.b200ocr_pad_lines(base + head, base, base + n * 8, n, height, dev.data_ptr(), width,
+                                                     pad, C.c_void_p(main.cuda_stream)))
+        self.h2d_bytes += total
+
+    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None, device_fill=None, packed=None):
+        """Stage one padded uint8 batch of `shape` -- filled in place by `fill(view)` in pinned host memory and copied
+        to the device on the side stream, or spread on the device from `packed` host crops (_stage_packed), or
+        produced on the device by `device_fill(dev_batch)` -- run the forward on the current stream and start the
+        device->host copies of the results."""
         torch = self.model.torch
         sl = self._slot(k)
         n_bytes = int(np.prod(shape))
@@ -313,6 +370,8 @@ class B200EngineLineOCR:
         main = torch.cuda.current_stream(self.device)
         if device_fill is not None:
             self.h2d_bytes += int(device_fill(dev))
+        elif packed is not None:
+            self._stage_packed(sl, packed, shape, dev, main)
         else:
             if sl['pin'] is None or sl['pin'].numel() < n_bytes:
                 sl['pin'] = torch.empty(sl['dev'].numel(), dtype=torch.uint8, pin_memory=True)
@@ -335,6 +394,7 @@ class B200EngineLineOCR:
             lo, hi = sparse_ranges
             sl['sparse'] = sparsify_device(o['logits'], lo, hi, out=sl.get('sparse_buf'))
             sl['sparse_buf'] = sl['sparse']
+            sl['sparse'].prefetch_meta(sl.setdefault('sparse_pin', {}))
         names = ['labels', 'lengths'] + (['logits'] if dense else []) + (['confidence'] if self.want_confidence else [])
         for name in names:
             t = o[name]
@@ -355,8 +415,7 @@ class B200EngineLineOCR:
         self.host_ms['wait'] += 1e3 * (time.perf_counter() - t0)
         res = {name: sl['host'][name].numpy() for name in names}
         if sl.get('sparse') is not None:
-            fetched = sl['sparse'].fetch(self._copy_stream)
-            self._copy_stream.synchronize()
+            fetched = sl['sparse'].fetch(self._copy_stream, pinned=sl.get('sparse_pin'))
             self.d2h_bytes += sum(int(a.nbytes) for a in fetched)
             res['sparse'] = csc_lines(sl['sparse'], fetched)
         return res
@@ -458,7 +517,7 @@ class B200EngineLineOCR:
                         ranges = ([0] * len(chunk), [t_all] * len(chunk))
                 kw = stager(chunk, width)
                 ticket = self._submit(bi & 1, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
-                                      device_fill=kw.get('device_fill'))
+                                      device_fill=kw.get('device_fill'), packed=kw.get('packed'))
                 if in_flight is not None:
                     res = self._collect(in_flight[1])
                     t0 = time.perf_counter()
@@ -474,33 +533,11 @@ class B200EngineLineOCR:
         """list of [H,w,3] uint8 crops -> (transcriptions, logits, logit_coords); semantics of
         line_ocr_engine.py:57-177 for model_type 'ctc': widest-first batches under a pixel budget, 32 px zero
         padding on both sides, over-budget batches cropped, logits sparsified at softmax p < 1e-4.
-        Batches are double-buffered: batch i+1 is padded and uploaded while batch i runs on the GPU."""
-        pad, height = self.line_padding_px, self.line_px_height
+        Batches are double-buffered: batch i+1 is staged and uploaded while batch i runs on the GPU; the crops cross
+        PCIe packed and are zero-padded on the device (b200ocr_pad_lines)."""
 
         def stager(chunk, width):
-            def fill_range(view, lo, hi):
-                for slot in range(lo, hi):
-                    line = lines[chunk[slot]]
-                    if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
-                        raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
-                    end = min(width, pad + line.shape[1])
-                    view[slot, :, :pad] = 0
-                    if end > pad:
-                        view[slot, :, pad:end] = line[:, :end - pad]
-                    view[slot, :, end:] = 0
-
-            def fill(view):
-                # padding a batch is a 40 MB strided copy at config 2: a few host threads share it (NumPy releases
-                # the GIL inside large copies)
-                n = len(chunk)
-                workers = min(self.host_threads, max(1, n // 16))
-                if workers <= 1:
-                    return fill_range(view, 0, n)
-                step = (n + workers - 1) // workers
-                jobs = [self._pool().submit(fill_range, view, lo, min(n, lo + step)) for lo in range(0, n, step)]
-                for j in jobs:
-                    j.result()
-            return {'fill': fill}
+            return {'packed': [lines[i] for i in chunk]}
 
         return self._run_batches([l.shape[1] for l in lines], stager, sparse_logits, tight_crop_logits, no_logits,
                                  return_ids)

@@ -21,11 +21,38 @@ class SparseLogits:
         self.rows = None          # host int array [n]: rows (frames) of every line's matrix
         self._host = {}
 
-    def fetch(self, stream=None):
+    def prefetch_meta(self, pinned):
+        """Starts the copy of the small parts (indptr, base) into the caller's pinned buffers `pinned` (a dict that
+        lives as long as the caller's slot) on the current stream: once that stream's work is known to be complete
+        the total entry count is on the host without another round trip."""
+        torch = self.torch
+        for name in ('indptr', 'base'):
+            src = getattr(self, name)
+            dst = pinned.get(name)
+            if dst is None or dst.shape != src.shape:
+                dst = pinned[name] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            dst.copy_(src, non_blocking=True)
+        self._meta = pinned
+
+    def fetch(self, stream=None, pinned=None):
         """-> (indptr int32 [n, C+1], base int64 [n+1], indices int32 [total], data float32 [total]) as NumPy arrays.
-        Two small copies first (indptr, base), then the used prefix of indices / data."""
+        The small parts first (indptr, base), then the used prefix of indices / data.  With `pinned` (the dict given
+        to prefetch_meta, whose copies must have completed) the big parts go through pinned buffers kept in it: the
+        arrays are views valid until the next fetch into the same dict."""
         torch = self.torch
         stream = stream or torch.cuda.current_stream(self.indptr.device)
+        if pinned is not None and getattr(self, '_meta', None) is pinned:
+            indptr, base = pinned['indptr'].numpy(), pinned['base'].numpy()
+            total = int(base[self.n])
+            for name in ('indices', 'data'):
+                src = getattr(self, name)
+                if pinned.get(name) is None or pinned[name].numel() < total:
+                    pinned[name] = torch.empty(max(total, 1) * 5 // 4 + 1024, dtype=src.dtype, pin_memory=True)
+            with torch.cuda.stream(stream):
+                pinned['indices'][:total].copy_(self.indices[:total], non_blocking=True)
+                pinned['data'][:total].copy_(self.data[:total], non_blocking=True)
+            stream.synchronize()
+            return indptr, base, pinned['indices'][:total].numpy(), pinned['data'][:total].numpy()
         with torch.cuda.stream(stream):
             indptr = self.indptr.cpu()
             base = self.base.cpu()
@@ -70,12 +97,14 @@ def sparsify_device(logits, t_lo=None, t_hi=None, out=None):
 
 
 def csc_lines(sp, fetched=None):
-    """list of scipy.sparse.csc_matrix [rows_i, C] float32 -- the value ``process_lines`` stores in ``TextLine.logits``."""
+    """list of scipy.sparse.csc_matrix [rows_i, C] float32 -- the value ``process_lines`` stores in ``TextLine.logits``.
+    The batch's entries are copied to fresh host memory ONCE; each line's matrix is built on slices of that copy."""
     from scipy import sparse
     indptr, base, indices, data = fetched if fetched is not None else sp.fetch()
+    total = int(base[sp.n])
+    indptr, indices, data = np.array(indptr), np.array(indices[:total]), np.array(data[:total])
     out = []
     for i in range(sp.n):
         b0, b1 = int(base[i]), int(base[i + 1])
-        out.append(sparse.csc_matrix((data[b0:b1].copy(), indices[b0:b1].copy(), indptr[i].copy()),
-                                     shape=(int(sp.rows[i]), sp.c)))
+        out.append(sparse.csc_matrix((data[b0:b1], indices[b0:b1], indptr[i]), shape=(int(sp.rows[i]), sp.c), copy=False))
     return out

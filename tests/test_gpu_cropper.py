@@ -102,3 +102,29 @@ def test_process_baselines_equals_process_lines_on_reference_crops(tmp_path, gol
     assert tr_a == tr_b and co_a == co_b
     for a, b in zip(lg_a, lg_b):
         assert np.array_equal(a, b)
+
+
+def test_pad_lines_builds_the_reference_batch():
+    """b200ocr_pad_lines against the reference's own padding / stacking (line_ocr_engine.py:121-127): ragged widths,
+    a 1-px line, a line wider than the batch (cut on the right), through the engine's packed staging."""
+    import ctypes as C
+    from pero_ocr_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(21)
+    widths = [200, 1, 97, 264, 33, 300]
+    out_w, pad, height = 264, 32, 40
+    lines = [rng.integers(0, 256, (height, w, 3), dtype=np.uint8) for w in widths]
+    want = np.zeros((len(lines), height, out_w, 3), dtype=np.uint8)
+    for i, l in enumerate(lines):
+        w = min(l.shape[1], out_w - pad)
+        want[i, :, pad:pad + w] = l[:, :w]
+    offs = np.zeros(len(lines) + 1, dtype=np.int64)
+    np.cumsum([l.nbytes for l in lines], out=offs[1:])
+    packed = torch.from_numpy(np.concatenate([l.reshape(-1) for l in lines])).cuda()
+    d_off = torch.from_numpy(offs[:-1].copy()).cuda()
+    d_w = torch.tensor(widths, dtype=torch.int32, device='cuda')
+    out = torch.full((len(lines), height, out_w, 3), 0xAB, dtype=torch.uint8, device='cuda')
+    _lib.check(lib.b200ocr_pad_lines(packed.data_ptr(), d_off.data_ptr(), d_w.data_ptr(), len(lines), height,
+                                     out.data_ptr(), out_w, pad, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)

@@ -32,10 +32,16 @@ def _host_only_engine(kind):
     eng._device_ctx = contextlib.nullcontext
     store = {}
 
-    def submit(k, shape, fill, no_logits, sparse_ranges=None, device_fill=None):
+    def submit(k, shape, fill, no_logits, sparse_ranges=None, device_fill=None, packed=None):
         batch = np.empty(shape, dtype=np.uint8)
-        batch[...] = 0xAB                      # stale garbage: fill() must overwrite every byte
-        fill(batch)
+        batch[...] = 0xAB                      # stale garbage: the staging must overwrite every byte
+        if packed is not None:                 # b200ocr_pad_lines' role (remap.cu; GPU-tested in test_gpu_cropper.py)
+            batch[...] = 0
+            for i, line in enumerate(packed):
+                w = min(line.shape[1], shape[2] - eng.line_padding_px)
+                batch[i, :, eng.line_padding_px:eng.line_padding_px + w] = line[:, :w]
+        else:
+            fill(batch)
         with torch.no_grad():
             logits = net(torch.from_numpy(batch).float().div(255.0).permute(0, 3, 1, 2)).numpy()
         ids = greedy_ctc_indices(logits)
