@@ -19,7 +19,20 @@ ENGINE_CASES = {
     'transformer': dict(classes=120, seed=3, out_gain=2.5, net_kw={'layers': 2}, engine_batch_size=1,
                         widths=[256, 180, 77, 40, 224, 500]),
 }
+# config-2 width under the reference engine: 8 lines of up to 1280 px (T = 336), several reference batches (budget 3840 px)
+ENGINE_CASES['lstm_wide'] = dict(net='lstm', classes=120, seed=0, out_gain=6.0, net_kw={}, engine_batch_size=8,
+                                 widths=[1280, 1280, 1279, 1100, 1280, 801, 1280, 640], store_logits=4)
+# the class-count convention of real pero checkpoints: the net emits len(JSON characters) + 1 classes -- U+200B, appended
+# by the engine (pytorch_ocr_engine.py:42), shares the blank's slot, and decoder_factory's letters are the JSON
+# characters + '<BLANK>' (decoding_itf.py:49-50)
+ENGINE_CASES['lstm_c119'] = dict(net='lstm', classes=120, json_chars=119, seed=7, out_gain=6.0, net_kw={},
+                                 engine_batch_size=2, widths=[300, 212, 97, 160])
 PARSENET_CASE = dict(seed=5, downsample=2, height=250, width=330)
+# BASELINE config 4 size: a 3000 x 4000 page at DOWNSAMPLE = 4 -> canvas 768 x 1024, and the adaptive second pass
+# (torch_parsenet.py:60-93); the stand-in's head is biased so that the first pass "detects" 20 px text (>15) and the
+# second pass runs at downsample 4 * 20 / 12
+PARSENET_PAGE_CASE = dict(seed=6, downsample=4, height=3000, width=4000, head_bias=[20.0, 5.0, 1.0, 0.0, 0.0],
+                          head_gain=0.02, stride=6)
 CONFIG1_BEAM_LINES = 6
 
 
@@ -31,7 +44,7 @@ def line_crop(rng, width, height=40):
 
 def engine_lines(kind):
     spec = ENGINE_CASES[kind]
-    rng = np.random.default_rng(100 + spec['seed'])
+    rng = np.random.default_rng(100 + spec['seed'] + (1000 if kind not in ('lstm', 'transformer') else 0))
     lines = [line_crop(rng, w) for w in spec['widths']]
     # one genuinely coloured line: the net sees 3 distinct channels
     lines[1] = rng.integers(0, 256, lines[1].shape, dtype=np.uint8)
@@ -79,10 +92,22 @@ def confidence_logits():
     return out
 
 
-def parsenet_image():
-    spec = PARSENET_CASE
+def parsenet_image(spec=None):
+    spec = spec or PARSENET_CASE
     rng = np.random.default_rng(500 + spec['seed'])
     return rng.integers(0, 256, (spec['height'], spec['width'], 3), dtype=np.uint8)
+
+
+def parsenet_page_net():
+    """The ParseNet stand-in of PARSENET_PAGE_CASE: seeded, with the head scaled down and biased (see the case)."""
+    import torch
+    from pero_ocr_b200.synthetic import make_net
+    spec = PARSENET_PAGE_CASE
+    net = make_net('parsenet', seed=spec['seed'])
+    with torch.no_grad():
+        net.head.weight.mul_(spec['head_gain'])
+        net.head.bias.copy_(torch.tensor(spec['head_bias']))
+    return net
 
 
 # autoregressive Transformer decoding (SURVEY.md 8(f) #3): seeded encoder (pero_ocr_b200/synthetic.py) + seeded decoder

@@ -88,8 +88,8 @@ def _export_engine(tmp, net, name, n_chars):
 def golden_engine(kind, tmp):
     from pero_ocr.ocr_engine.pytorch_ocr_engine import PytorchEngineLineOCR
     spec = cases.ENGINE_CASES[kind]
-    net = make_net(kind, spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
-    js = _export_engine(tmp, net, kind, spec['classes'] - 2)
+    net = make_net(spec.get('net', kind), spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
+    js = _export_engine(tmp, net, kind, spec.get('json_chars', spec['classes'] - 2))
     eng = PytorchEngineLineOCR(js, torch.device('cpu'), batch_size=spec['engine_batch_size'])
     lines = cases.engine_lines(kind)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -98,15 +98,35 @@ def golden_engine(kind, tmp):
         tr_t, lg_t, co_t = eng.process_lines([l.copy() for l in lines], sparse_logits=False, tight_crop_logits=True)
     assert tr == tr_s == tr_t
     out = {'n': np.int64(len(lines)), 'chars': np.array(eng.characters)}
+    keep = spec.get('store_logits', len(lines))            # fixture size: full logits of the first `keep` lines only
     for i in range(len(lines)):
-        out[f'logits_{i}'] = lg[i].astype(np.float32)
-        out[f'tight_{i}'] = lg_t[i].astype(np.float32)
-        sp = lg_s[i]
-        out[f'csc_data_{i}'] = sp.data
-        out[f'csc_indices_{i}'] = sp.indices
-        out[f'csc_indptr_{i}'] = sp.indptr
         out[f'coords_{i}'] = np.array(co[i], dtype=np.int64)
+        if i >= keep:
+            continue
+        out[f'logits_{i}'] = lg[i].astype(np.float32)
+        if keep == len(lines):
+            out[f'tight_{i}'] = lg_t[i].astype(np.float32)
+            sp = lg_s[i]
+            out[f'csc_data_{i}'] = sp.data
+            out[f'csc_indices_{i}'] = sp.indices
+            out[f'csc_indptr_{i}'] = sp.indptr
     out['transcriptions'] = np.array(tr)
+    if 'json_chars' in spec:
+        # the reference's own decoder chain on the reference's own logits, letters as decoder_factory builds them
+        # (decoding_itf.py:49-50): JSON characters + '<BLANK>'
+        _install_stubs()
+        from pero_ocr.core.layout import TextLine
+        from pero_ocr.decoding.decoders import BLANK_SYMBOL, CTCPrefixLogRawNumpyDecoder, GreedyDecoder
+        letters = cases.json_characters(spec['json_chars']) + [BLANK_SYMBOL]
+        gd, bd = GreedyDecoder(letters), CTCPrefixLogRawNumpyDecoder(letters, k=4)
+        g_out, b_out = [], []
+        for i in range(len(lines)):
+            line = TextLine(id=str(i), logits=lg_s[i], logit_coords=co_s[i])
+            lp = line.get_full_logprobs()[co_s[i][0]:co_s[i][1]]
+            g_out.append(gd(lp).best_hyp())
+            b_out.append(bd(lp.astype(np.float64)).best_hyp())
+        out['decoder_greedy'] = np.array(g_out)
+        out['decoder_beam4'] = np.array(b_out)
     # raw per-frame argmax of the full batch logits ("bit-exact CTC argmax indices")
     out['best_path'] = np.concatenate([l.argmax(axis=1).astype(np.int32) for l in lg])
     np.savez_compressed(os.path.join(GOLDEN, f'engine_{kind}.npz'), **out)
@@ -250,6 +270,31 @@ def golden_parsenet(tmp):
     assert np.array_equal(maps, maps2) and ds2 == spec['downsample']
     np.savez_compressed(os.path.join(GOLDEN, 'parsenet.npz'), maps=maps.astype(np.float32))
     return {'maps_shape': list(maps.shape), 'absmax': float(np.abs(maps).max())}
+
+
+def golden_parsenet_page(tmp):
+    """TorchParseNet.get_maps_with_optimal_resolution of the unmodified reference at BASELINE config 4's size (3000 x
+    4000 page, DOWNSAMPLE 4 -> 768 x 1024 canvas) with the adaptive second pass taken (torch_parsenet.py:60-93).  The
+    maps are stored subsampled (every `stride`-th pixel of both passes) -- 15 MB of float32 otherwise."""
+    from pero_ocr.layout_engines.torch_parsenet import TorchParseNet
+    spec = cases.PARSENET_PAGE_CASE
+    net = cases.parsenet_page_net()
+    path = os.path.join(tmp, 'parsenet_page.pt')
+    torch.jit.script(net).save(path + '.cpu')
+    pn = TorchParseNet(path, torch.device('cpu'), downsample=spec['downsample'], adaptive_downsample=True)
+    img = cases.parsenet_image(spec)
+    st = spec['stride']
+    with contextlib.redirect_stdout(io.StringIO()):
+        first = pn.get_maps(img, spec['downsample'])
+        med = pn.get_med_height(first)
+        maps, used = pn.get_maps_with_optimal_resolution(img)
+    assert used != spec['downsample'], 'the case must take the second pass'
+    np.savez_compressed(os.path.join(GOLDEN, 'parsenet_page.npz'), first=first[::st, ::st].astype(np.float32),
+                        first_shape=np.array(first.shape), maps=maps[::st, ::st].astype(np.float32),
+                        maps_shape=np.array(maps.shape), used_downsample=np.float64(used), med_height=np.float64(med),
+                        last_downsample=np.float64(pn.last_downsample))
+    return {'first_shape': list(first.shape), 'second_shape': list(maps.shape), 'used_downsample': float(used),
+            'med_height_first_pass': float(med)}
 
 
 def golden_cropper():
@@ -408,7 +453,10 @@ def main():
         parts = [('architecture_check', check_reference_architecture), ('decoders', golden_decoders),
                  ('engine_lstm', lambda: golden_engine('lstm', tmp)),
                  ('engine_transformer', lambda: golden_engine('transformer', tmp)),
-                 ('parsenet', lambda: golden_parsenet(tmp)), ('confidence', golden_confidence),
+                 ('engine_lstm_wide', lambda: golden_engine('lstm_wide', tmp)),
+                 ('engine_lstm_c119', lambda: golden_engine('lstm_c119', tmp)),
+                 ('parsenet', lambda: golden_parsenet(tmp)), ('parsenet_page', lambda: golden_parsenet_page(tmp)),
+                 ('confidence', golden_confidence),
                  ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder),
                  ('ar_host', lambda: golden_ar_host(tmp))]
         for name, fn in parts:

@@ -415,9 +415,13 @@ class B200EngineLineOCR:
         self.host_ms['wait'] += 1e3 * (time.perf_counter() - t0)
         res = {name: sl['host'][name].numpy() for name in names}
         if sl.get('sparse') is not None:
+            t1 = time.perf_counter()
             fetched = sl['sparse'].fetch(self._copy_stream, pinned=sl.get('sparse_pin'))
-            self.d2h_bytes += sum(int(a.nbytes) for a in fetched)
+            self.host_ms['fetch'] = self.host_ms.get('fetch', 0.0) + 1e3 * (time.perf_counter() - t1)
+            self.d2h_bytes += sum(int(getattr(a, 'array', a).nbytes) for a in fetched)
+            t1 = time.perf_counter()
             res['sparse'] = csc_lines(sl['sparse'], fetched)
+            self.host_ms['csc'] = self.host_ms.get('csc', 0.0) + 1e3 * (time.perf_counter() - t1)
         return res
 
     def _decode_ids(self, labels, lengths):

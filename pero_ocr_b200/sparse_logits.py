@@ -37,22 +37,21 @@ class SparseLogits:
     def fetch(self, stream=None, pinned=None):
         """-> (indptr int32 [n, C+1], base int64 [n+1], indices int32 [total], data float32 [total]) as NumPy arrays.
         The small parts first (indptr, base), then the used prefix of indices / data.  With `pinned` (the dict given
-        to prefetch_meta, whose copies must have completed) the big parts go through pinned buffers kept in it: the
-        arrays are views valid until the next fetch into the same dict."""
+        to prefetch_meta, whose copies must have completed) the small parts are already on the host and the big ones
+        are copied straight into fresh arrays the caller may keep (returned wrapped in _Owned for csc_lines)."""
         torch = self.torch
         stream = stream or torch.cuda.current_stream(self.indptr.device)
         if pinned is not None and getattr(self, '_meta', None) is pinned:
+            # the entry count is already on the host: the big parts go device -> their final (fresh, huge-page advised)
+            # host arrays in ONE pass -- no pinned staging copy that the host would have to copy again
             indptr, base = pinned['indptr'].numpy(), pinned['base'].numpy()
             total = int(base[self.n])
-            for name in ('indices', 'data'):
-                src = getattr(self, name)
-                if pinned.get(name) is None or pinned[name].numel() < total:
-                    pinned[name] = torch.empty(max(total, 1) * 5 // 4 + 1024, dtype=src.dtype, pin_memory=True)
-            with torch.cuda.stream(stream):
-                pinned['indices'][:total].copy_(self.indices[:total], non_blocking=True)
-                pinned['data'][:total].copy_(self.data[:total], non_blocking=True)
-            stream.synchronize()
-            return indptr, base, pinned['indices'][:total].numpy(), pinned['data'][:total].numpy()
+            indices, data = fresh_host_array(total, np.int32), fresh_host_array(total, np.float32)
+            if total:
+                with torch.cuda.stream(stream):
+                    torch.from_numpy(indices).copy_(self.indices[:total])
+                    torch.from_numpy(data).copy_(self.data[:total])
+            return indptr, base, _Owned(indices), _Owned(data)
         with torch.cuda.stream(stream):
             indptr = self.indptr.cpu()
             base = self.base.cpu()
@@ -96,15 +95,57 @@ def sparsify_device(logits, t_lo=None, t_hi=None, out=None):
     return sp
 
 
-def csc_lines(sp, fetched=None):
+class _Owned:
+    """Marks an array fetch() allocated for the caller: csc_lines may slice it without another copy."""
+
+    def __init__(self, array):
+        self.array = array
+
+
+def fresh_host_array(count, dtype):
+    """Pageable host array of `count` elements that the caller will fill and keep (a batch's CSC parts: tens of MB of
+    FRESH memory per batch -- first-touch page faults, not the copy, dominate at 4 KB pages).  Anonymous mmap advised
+    to transparent huge pages where the host allows it (THP "madvise" or "always"); a plain np.empty otherwise."""
+    import mmap
+    nbytes = int(count) * np.dtype(dtype).itemsize
+    if nbytes < (4 << 20) or not hasattr(mmap, 'MADV_HUGEPAGE'):
+        return np.empty(int(count), dtype=dtype)
+    try:
+        m = mmap.mmap(-1, (nbytes + (1 << 21) - 1) >> 21 << 21, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        m.madvise(mmap.MADV_HUGEPAGE)
+        return np.frombuffer(m, dtype=dtype, count=int(count))
+    except (OSError, ValueError, AttributeError):
+        return np.empty(int(count), dtype=dtype)
+
+
+def parallel_copy(dst, src, pool=None, workers=1):
+    """dst[:] = src in `workers` contiguous pieces on `pool` (NumPy releases the GIL inside large copies; the page
+    faults of a fresh destination are taken by the copying threads in parallel)."""
+    n = len(src)
+    if pool is None or workers <= 1 or n < (1 << 20):
+        np.copyto(dst, src)
+        return
+    step = (n + workers - 1) // workers
+    for j in [pool.submit(np.copyto, dst[lo:lo + step], src[lo:lo + step]) for lo in range(0, n, step)]:
+        j.result()
+
+
+def csc_lines(sp, fetched=None, pool=None, workers=1):
     """list of scipy.sparse.csc_matrix [rows_i, C] float32 -- the value ``process_lines`` stores in ``TextLine.logits``.
-    The batch's entries are copied to fresh host memory ONCE; each line's matrix is built on slices of that copy."""
+    The batch's entries are copied to fresh host memory ONCE (optionally by `workers` threads of `pool`); each line's
+    matrix is built on slices of that copy."""
     from scipy import sparse
     indptr, base, indices, data = fetched if fetched is not None else sp.fetch()
     total = int(base[sp.n])
-    indptr, indices, data = np.array(indptr), np.array(indices[:total]), np.array(data[:total])
+    indptr = np.array(indptr)
+    if isinstance(indices, _Owned):
+        own_i, own_d = indices.array, data.array
+    else:
+        own_i, own_d = fresh_host_array(total, np.int32), fresh_host_array(total, np.float32)
+        parallel_copy(own_i, indices[:total], pool, workers)
+        parallel_copy(own_d, data[:total], pool, workers)
     out = []
     for i in range(sp.n):
         b0, b1 = int(base[i]), int(base[i + 1])
-        out.append(sparse.csc_matrix((data[b0:b1], indices[b0:b1], indptr[i]), shape=(int(sp.rows[i]), sp.c), copy=False))
+        out.append(sparse.csc_matrix((own_d[b0:b1], own_i[b0:b1], indptr[i]), shape=(int(sp.rows[i]), sp.c), copy=False))
     return out

@@ -15,9 +15,10 @@ from oracle.nets import make_net
 
 def _engine(kind):
     spec = cases.ENGINE_CASES[kind]
-    net = make_net(kind, spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
-    return OracleEngine(dict(net.state_dict()), cases.json_characters(spec['classes'] - 2), kind=kind,
-                        batch_size=spec['engine_batch_size'])
+    net_kind = spec.get('net', kind)
+    net = make_net(net_kind, spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
+    return OracleEngine(dict(net.state_dict()), cases.json_characters(spec.get('json_chars', spec['classes'] - 2)),
+                        kind=net_kind, batch_size=spec['engine_batch_size'])
 
 
 @pytest.mark.parametrize('kind', ['lstm', 'transformer'])
@@ -68,3 +69,41 @@ def test_confidence_chain_matches_reference(golden_dir):
         np.testing.assert_allclose(full_logprobs(sp), gold[f'logprobs_{i}'], atol=1e-5)
         assert line_confidence(d) == pytest.approx(float(gold['confidence'][i]), rel=1e-6)
         assert line_confident_enough(full_logprobs(sp), 0.5) == bool(gold['confident_enough_0.5'][i])
+
+
+def test_full_width_lines_match_reference(golden_dir):
+    """Config-2 width: 8 lines of up to 1280 px through the unmodified PytorchEngineLineOCR (several of its batches)."""
+    gold = np.load(os.path.join(golden_dir, 'engine_lstm_wide.npz'))
+    eng = _engine('lstm_wide')
+    lines = cases.engine_lines('lstm_wide')
+    tr, lg, co = eng.process_lines(lines, sparse_logits=False)
+    assert tr == list(gold['transcriptions'])
+    for i in range(len(lines)):
+        assert list(co[i]) == list(gold[f'coords_{i}'])
+        if f'logits_{i}' in gold:
+            np.testing.assert_allclose(lg[i], gold[f'logits_{i}'], atol=2e-5)
+    best = np.concatenate([l.argmax(axis=1) for l in lg])
+    srt = np.concatenate([np.sort(l, axis=1)[:, -2:] for l in lg])
+    decided = (srt[:, 1] - srt[:, 0]) > 1e-4
+    assert np.array_equal(best[decided], gold['best_path'][decided])
+
+
+def test_checkpoint_class_convention_matches_reference(golden_dir):
+    """A net that emits len(JSON characters) + 1 classes (the convention of real pero checkpoints: U+200B shares the
+    blank's slot) through the engine oracle and the decoder oracles, letters as decoder_factory builds them
+    (decoding_itf.py:49-50), against the unmodified reference's engine + decoders."""
+    from oracle.decoders_oracle import greedy, prefix_beam
+    gold = np.load(os.path.join(golden_dir, 'engine_lstm_c119.npz'))
+    spec = cases.ENGINE_CASES['lstm_c119']
+    eng = _engine('lstm_c119')
+    assert len(eng.characters) == spec['classes']                       # 119 JSON characters + U+200B
+    lines = cases.engine_lines('lstm_c119')
+    tr, lg, co = eng.process_lines(lines, sparse_logits=True)
+    assert tr == list(gold['transcriptions'])
+    letters = cases.json_characters(spec['json_chars']) + [cases.BLANK]
+    for i in range(len(lines)):
+        lp = full_logprobs(lg[i])[co[i][0]:co[i][1]]
+        assert greedy(lp, letters)[0] == str(gold['decoder_greedy'][i])
+        hyps = prefix_beam(lp.astype(np.float64), 4)
+        best = max(hyps, key=lambda h: h[1])
+        assert ''.join(letters[c] for c in best[0]) == str(gold['decoder_beam4'][i])

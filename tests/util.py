@@ -10,7 +10,7 @@ from oracle.nets import make_net
 
 def make_case_net(kind):
     spec = cases.ENGINE_CASES[kind]
-    return make_net(kind, spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
+    return make_net(spec.get('net', kind), spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
 
 
 def write_engine_json(tmpdir, kind, checkpoint='ck.pt'):
@@ -18,7 +18,8 @@ def write_engine_json(tmpdir, kind, checkpoint='ck.pt'):
     path = os.path.join(str(tmpdir), f'{kind}.json')
     with open(path, 'w', encoding='utf8') as f:
         json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': checkpoint,
-                   'characters': cases.json_characters(spec['classes'] - 2), 'net_name': 'B200_TEST'}, f)
+                   'characters': cases.json_characters(spec.get('json_chars', spec['classes'] - 2)),
+                   'net_name': 'B200_TEST'}, f)
     return path
 
 
