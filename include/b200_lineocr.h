@@ -333,7 +333,11 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
 /* A/B switches for kernel variants (tests, profiling).  flag 1: halo-reuse 3x3 kernel for cin <= 128 (default on);
  * flag 2: split-K kernel for the per-step projections of b200ocr_ar_transcribe (default on; 0 = one K walker per tile);
  * flag 3: the BiLSTM recurrence also multiplies the fp16 rounding residual of h_t (three passes and twice the SM-to-SM
- * exchange per step; default on only in B200OCR_PREC_FP16X3). */
+ * exchange per step; default on only in B200OCR_PREC_FP16X3);
+ * flag 4: staging of the uint8 crop patch of the first convolution from HBM into shared memory: 2 = TMA box load
+ * (default), 1 = 16-byte cp.async, 0 = plain byte loads (also the fallback when the batch width is not a multiple of 16);
+ * flag 5: index of ONE layer whose tensor-core contraction runs on the CUDA-core cross-check kernel while every other
+ * layer stays on its product kernel (-1 = none): isolates a layer on identical inputs. */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

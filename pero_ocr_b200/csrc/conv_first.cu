@@ -15,14 +15,27 @@
 //     (16-byte chunks XOR-swizzled by pixel: conflict-free fragment writes and conflict-free record reads) ->
 //     fully coalesced 16-byte stores.  The kernel is bound by that store stream (the 64-channel hi|lo records of
 //     a 256 x 40 x 1344 batch are 3.5 GB).
+//
+// Staging of the uint8 crop patch (6 image rows x 130 pixels x 3 bytes per CTA) from HBM into shared memory comes in
+// three variants, selectable for A/B (b200ocr_debug_set_flag 4; profiles/r02*_conv_first_staging.md):
+//   STAGE_TMA      one cp.async.bulk.tensor box (104 x 6 32-bit words) per CTA through a 3-D tensor map over the crop
+//                  batch, completing on an mbarrier; rows / columns outside the image are the TMA unit's zero fill
+//                  -- the convolution's zero padding costs no instruction (default whenever W is a multiple of 16)
+//   STAGE_CPASYNC  16-byte cp.async (LDGSTS) chunks, out-of-image chunks zero-filled through the src-size operand
+//   STAGE_PLAIN    one byte per thread and iteration with ordinary loads (any W; round 1's path)
+// The staged bytes are then widened to the fp16 operand patch in shared memory by all threads.
 #include "once.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace {
 
 constexpr int CFM_PX = 128;      // output pixels per CTA row (4 warps x 32)
 constexpr int CFM_ROWS = 4;      // image rows per CTA
 constexpr int CFM_PSTRIDE = 392; // fp16 per staged patch row: 130 pixels x 3 channels + 2 pad
+constexpr int CFM_U8ROW = 416;   // bytes per staged uint8 row: [w0 * 3 - 16, w0 * 3 + 400), 16-byte aligned when W % 16 == 0
+constexpr int CFM_U8OFF = 13;    // patch byte b (pixel w0 - 1, channel 0 = byte 0) sits at CFM_U8OFF + b of its uint8 row
+enum { STAGE_PLAIN = 0, STAGE_CPASYNC = 1, STAGE_TMA = 2 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -44,15 +57,18 @@ __device__ __forceinline__ uint32_t ld_pair(const __half* p) {   // two consecut
     return lo | (hi << 16);
 }
 
-template <int COUT>
+template <int COUT, int STAGE>
 __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                               const uint2* __restrict__ wfrag,
                                                               const float* __restrict__ oscale,
                                                               const float* __restrict__ bias, int act, int fmt,
-                                                              __half* __restrict__ out) {
+                                                              __half* __restrict__ out,
+                                                              const __grid_constant__ CUtensorMap tm_in) {
     constexpr int NT = COUT / 8;
     const int planes = act_planes(fmt);
     __shared__ __align__(16) __half s_p[(CFM_ROWS + 2) * CFM_PSTRIDE];
+    __shared__ __align__(128) uint8_t s_u8[STAGE == STAGE_PLAIN ? 16 : (CFM_ROWS + 2) * CFM_U8ROW];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_sc[COUT], s_b[COUT];
     extern __shared__ uint4 s_stage[];   // [CFM_PX][planes * COUT / 8]: one image row of pixel records
 
@@ -76,15 +92,46 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
     }
     // input patch (rows row0-1 .. row0+CFM_ROWS, pixels w0-1 .. w0+128) as fp16 byte values, zero outside the image
     constexpr int kRowVals = (CFM_PX + 2) * 3;
-    for (int i = threadIdx.x; i < (CFM_ROWS + 2) * CFM_PSTRIDE; i += CFM_PX) {
-        const int r = i / CFM_PSTRIDE;
-        const int b = i - r * CFM_PSTRIDE;
-        const int yy = row0 + r - 1;
-        const int xb = (w0 - 1) * 3 + b;
-        unsigned short v = 0;
-        if (b < kRowVals && yy >= 0 && yy < h && xb >= 0 && xb < w * 3)
-            v = in[(static_cast<size_t>(img) * h + yy) * w * 3 + xb];
-        s_p[i] = __ushort2half_rn(v);
+    if (STAGE == STAGE_PLAIN) {
+        for (int i = threadIdx.x; i < (CFM_ROWS + 2) * CFM_PSTRIDE; i += CFM_PX) {
+            const int r = i / CFM_PSTRIDE;
+            const int b = i - r * CFM_PSTRIDE;
+            const int yy = row0 + r - 1;
+            const int xb = (w0 - 1) * 3 + b;
+            unsigned short v = 0;
+            if (b < kRowVals && yy >= 0 && yy < h && xb >= 0 && xb < w * 3)
+                v = in[(static_cast<size_t>(img) * h + yy) * w * 3 + xb];
+            s_p[i] = __ushort2half_rn(v);
+        }
+    } else {
+        if (STAGE == STAGE_TMA) {
+            // one box: 104 words x 6 rows of image `img`, starting 16 bytes left of pixel w0 and one row above row0
+            if (threadIdx.x == 0) {
+                ptx::mbar_init(&s_bar, 1);
+                ptx::fence_mbar_init();
+                ptx::mbar_expect_tx(&s_bar, (CFM_ROWS + 2) * CFM_U8ROW);
+                ptx::tma_load_3d(s_u8, &tm_in, &s_bar, w0 * 3 / 4 - 4, row0 - 1, img);
+            }
+        } else {
+            const int row_bytes = w * 3;
+            for (int i = threadIdx.x; i < (CFM_ROWS + 2) * (CFM_U8ROW / 16); i += CFM_PX) {
+                const int r = i / (CFM_U8ROW / 16), c = i - r * (CFM_U8ROW / 16);
+                const int yy = row0 + r - 1;
+                const int xb = w0 * 3 - 16 + c * 16;
+                const bool ok = yy >= 0 && yy < h && xb >= 0 && xb < row_bytes;   // W % 16 == 0: chunks never straddle
+                const uint8_t* src = in + (static_cast<size_t>(img) * h + (ok ? yy : 0)) * row_bytes + (ok ? xb : 0);
+                ptx::cp_async_16(s_u8 + r * CFM_U8ROW + c * 16, src, ok ? 16u : 0u);
+            }
+            ptx::cp_async_commit_wait_all();
+        }
+        __syncthreads();   // TMA: the barrier init is visible to the waiters; cp.async: every thread's chunks landed
+        if (STAGE == STAGE_TMA) ptx::mbar_wait(&s_bar, 0);
+        for (int i = threadIdx.x; i < (CFM_ROWS + 2) * CFM_PSTRIDE; i += CFM_PX) {
+            const int r = i / CFM_PSTRIDE;
+            const int b = i - r * CFM_PSTRIDE;
+            const unsigned short v = b < kRowVals ? s_u8[r * CFM_U8ROW + CFM_U8OFF + b] : 0;
+            s_p[i] = __ushort2half_rn(v);
+        }
     }
     // patch offsets of this thread's A-fragment columns: k = 16 ks + 2 tig (+ 8) -> row r = k / 10, value j = k % 10
     int aoff[2][2];
@@ -209,24 +256,39 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
 }
 
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
-                                  const float* bias, int cout, int act, int fmt, __half* out, cudaStream_t stream) {
+                                  const float* bias, int cout, int act, int fmt, __half* out, int staging,
+                                  const CUtensorMap* tm_in, cudaStream_t stream) {
     const int planes = act_planes(fmt);
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
     const size_t dyn = static_cast<size_t>(CFM_PX) * planes * cout * sizeof(__half);
+    if ((w % 16) || (staging == STAGE_TMA && !tm_in)) staging = STAGE_PLAIN;   // bulk variants need 16-byte aligned rows
     static PerDeviceOnce attr_done;
     if (attr_done.pending()) {
-        cudaFuncSetAttribute(conv_first_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(conv_first_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(conv_first_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+#define CFM_ATTR(C, S) cudaFuncSetAttribute(conv_first_mma_kernel<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)
+        CFM_ATTR(64, 0); CFM_ATTR(64, 1); CFM_ATTR(64, 2); CFM_ATTR(32, 0); CFM_ATTR(32, 1); CFM_ATTR(32, 2);
+        CFM_ATTR(16, 0); CFM_ATTR(16, 1); CFM_ATTR(16, 2);
+#undef CFM_ATTR
         attr_done.mark();
     }
     const uint2* wf = reinterpret_cast<const uint2*>(wfrag);
+    static const CUtensorMap no_map = {};
+    const CUtensorMap& tm = tm_in ? *tm_in : no_map;
+#define CFM_LAUNCH(C, S) \
+    conv_first_mma_kernel<C, S><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out, tm)
+#define CFM_STAGE(C)                                        \
+    switch (staging) {                                      \
+        case STAGE_TMA: CFM_LAUNCH(C, STAGE_TMA); break;    \
+        case STAGE_CPASYNC: CFM_LAUNCH(C, STAGE_CPASYNC); break; \
+        default: CFM_LAUNCH(C, STAGE_PLAIN); break;         \
+    }
     switch (cout) {
-        case 64: conv_first_mma_kernel<64><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out); break;
-        case 32: conv_first_mma_kernel<32><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out); break;
-        case 16: conv_first_mma_kernel<16><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out); break;
+        case 64: CFM_STAGE(64); break;
+        case 32: CFM_STAGE(32); break;
+        case 16: CFM_STAGE(16); break;
         default: return cudaErrorInvalidValue;
     }
+#undef CFM_STAGE
+#undef CFM_LAUNCH
     return cudaGetLastError();
 }

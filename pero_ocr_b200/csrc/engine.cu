@@ -106,6 +106,8 @@ struct b200ocr_engine {
     int lstm_hplanes = 1;     // planes of h_t exchanged and multiplied per step (<= lstm_planes; lstm_tc.cuh)
     bool use_ref = false;
     bool use_halo = true;
+    int ref_only_layer = -1;  // debug flag 5: this layer's contraction alone runs on the CUDA-core cross-check kernel
+    int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
     std::vector<LayerRT> layers;
     std::vector<void*> owned;
     // workspace
@@ -300,7 +302,7 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     if (o.epi == EPI_CTC && p.tiles_n != 1)
         return fail(e, B200OCR_E_INVALID, "fused CTC head supports at most 256 classes");
     if (out_s) *out_s = Shape{in_s.n, p.h_out / pool_h, p.w_out / pool_w, g.cout};
-    if (e->use_ref) {
+    if (e->use_ref || (e->ref_only_layer >= 0 && e->ref_only_layer == e->cur_layer && o.epi != EPI_CTC)) {
         if (o.epi == EPI_CTC) return fail(e, B200OCR_E_INVALID, "internal: CTC epilogue has no reference kernel");
         CU_TRY(e, launch_igemm_ref(p, in, g.w, st));
         e->launches++;
@@ -326,6 +328,22 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
         CU_TRY(e, launch_igemm_tc(p, tmA, g.tmB, g.bn, e->num_sms, st));
     }
     e->launches++;
+    return 0;
+}
+
+// 3-D map over the uint8 crop batch [n][h][w*3 bytes] in 32-bit words (a TMA box is at most 256 elements per
+// dimension: 416 bytes = 104 words), box {104, 6, 1}: the first conv's patch (conv_first.cu)
+int make_map_crops(b200ocr_engine* e, CUtensorMap* m, const void* base, int n, int h, int w) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)h * w * 3};
+    cuuint32_t box[3] = {104, 6, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, B200OCR_E_CUDA, "cuTensorMapEncodeTiled(crops) failed: %d", (int)r);
     return 0;
 }
 
@@ -371,6 +389,11 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                 if (dry) dry->hn(slot, hbytes(e, os));
                 else {
                     if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                    CUtensorMap tm_crops;
+                    const bool bulk_ok = (cur.w % 16) == 0 && (reinterpret_cast<uintptr_t>(crops) % 16) == 0;
+                    const int staging = bulk_ok ? e->crop_staging : 0;
+                    if (!e->use_ref && staging == 2)
+                        if (int s = make_map_crops(e, &tm_crops, crops, cur.n, cur.h, cur.w)) return s;
                     ProfScope ps(e, st, PROF_CONV_FIRST);
                     if (e->use_ref)   // CUDA-core fp32 cross-check kernel
                         CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
@@ -378,7 +401,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     else
                         CU_TRY(e, launch_conv_first_mma(crops, cur.n, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
                                                         ly.cout0, ly.act, e->fmt, static_cast<__half*>(e->hbuf[slot]),
-                                                        st));
+                                                        staging, staging == 2 ? &tm_crops : nullptr, st));
                     e->launches++;
                     cur_h = static_cast<__half*>(e->hbuf[slot]);
                 }
@@ -1270,6 +1293,8 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     if (flag == 1) e->use_halo = value != 0;
     else if (flag == 2) e->ar.linear_variant = value != 0 ? 1 : 0;
     else if (flag == 3) e->lstm_hplanes = (value != 0 && e->lstm_planes == 2) ? 2 : 1;
+    else if (flag == 4) e->crop_staging = value < 0 || value > 2 ? 2 : value;
+    else if (flag == 5) e->ref_only_layer = value;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

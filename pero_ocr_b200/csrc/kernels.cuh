@@ -1,5 +1,6 @@
 // Non-GEMM kernels of the line-recognition path + CUDA-core cross-check kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -16,8 +17,11 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
 // The same layer on warp-level tensor cores (conv_first.cu; the product path -- the kernel above is the fp32
 // cross-check).  conv_first_pack turns the PyTorch weight [cout][3][3][3] into per-lane mma.sync fragments
 // (conv_first_wfrag_words(cout) 32-bit words) and the per-channel epilogue scale (power-of-two weight scale / 255).
+// staging: how the uint8 patch reaches shared memory -- 0 plain loads, 1 cp.async, 2 TMA (tm_in: 3-D uint32 tensor map
+// {W*3/4, H, N}, box {104, 6, 1}, no swizzle); the bulk variants need W % 16 == 0 and fall back to 0 otherwise.
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
-                                  const float* bias, int cout, int act, int fmt, __half* out, cudaStream_t stream);
+                                  const float* bias, int cout, int act, int fmt, __half* out, int staging,
+                                  const CUtensorMap* tm_in, cudaStream_t stream);
 size_t conv_first_wfrag_words(int cout);
 void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* oscale);
 

@@ -416,7 +416,7 @@ class B200EngineLineOCR:
         res = {name: sl['host'][name].numpy() for name in names}
         if sl.get('sparse') is not None:
             t1 = time.perf_counter()
-            fetched = sl['sparse'].fetch(self._copy_stream, pinned=sl.get('sparse_pin'))
+            fetched = sl['sparse'].fetch(self._copy_stream, pinned=sl.get('sparse_pin'), pool=self._pool())
             self.host_ms['fetch'] = self.host_ms.get('fetch', 0.0) + 1e3 * (time.perf_counter() - t1)
             self.d2h_bytes += sum(int(getattr(a, 'array', a).nbytes) for a in fetched)
             t1 = time.perf_counter()

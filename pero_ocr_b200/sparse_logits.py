@@ -34,7 +34,7 @@ class SparseLogits:
             dst.copy_(src, non_blocking=True)
         self._meta = pinned
 
-    def fetch(self, stream=None, pinned=None):
+    def fetch(self, stream=None, pinned=None, pool=None):
         """-> (indptr int32 [n, C+1], base int64 [n+1], indices int32 [total], data float32 [total]) as NumPy arrays.
         The small parts first (indptr, base), then the used prefix of indices / data.  With `pinned` (the dict given
         to prefetch_meta, whose copies must have completed) the small parts are already on the host and the big ones
@@ -48,9 +48,21 @@ class SparseLogits:
             total = int(base[self.n])
             indices, data = fresh_host_array(total, np.int32), fresh_host_array(total, np.float32)
             if total:
-                with torch.cuda.stream(stream):
-                    torch.from_numpy(indices).copy_(self.indices[:total])
-                    torch.from_numpy(data).copy_(self.data[:total])
+                def pull(dst, src, st):
+                    with torch.cuda.device(src.device), torch.cuda.stream(st):
+                        torch.from_numpy(dst).copy_(src[:total])
+
+                if pool is not None and total > (1 << 20):
+                    # a pageable D2H copy is bound by the host side of the driver's staging (memcpy + first-touch
+                    # faults of the fresh destination): the two arrays go in parallel, on their own streams
+                    if getattr(self, '_stream2', None) is None:
+                        self._stream2 = torch.cuda.Stream(self.indices.device)
+                    other = pool.submit(pull, indices, self.indices, self._stream2)
+                    pull(data, self.data, stream)
+                    other.result()
+                else:
+                    pull(indices, self.indices, stream)
+                    pull(data, self.data, stream)
             return indptr, base, _Owned(indices), _Owned(data)
         with torch.cuda.stream(stream):
             indptr = self.indptr.cpu()
@@ -144,8 +156,22 @@ def csc_lines(sp, fetched=None, pool=None, workers=1):
         own_i, own_d = fresh_host_array(total, np.int32), fresh_host_array(total, np.float32)
         parallel_copy(own_i, indices[:total], pool, workers)
         parallel_copy(own_d, data[:total], pool, workers)
+    # scipy copies an operand that is a view of a much larger ndarray (check_format -> prune -> _prune_array looks at
+    # `.base.size`): each line's arrays are therefore created over the batch's BUFFER (their base is the buffer
+    # object, not an ndarray), which keeps the single copy single
+    buf_i, buf_d = _buffer_of(own_i), _buffer_of(own_d)
     out = []
     for i in range(sp.n):
         b0, b1 = int(base[i]), int(base[i + 1])
-        out.append(sparse.csc_matrix((own_d[b0:b1], own_i[b0:b1], indptr[i]), shape=(int(sp.rows[i]), sp.c), copy=False))
+        if b1 > b0:
+            di = np.frombuffer(buf_i, dtype=np.int32, count=b1 - b0, offset=4 * b0)
+            dd = np.frombuffer(buf_d, dtype=np.float32, count=b1 - b0, offset=4 * b0)
+        else:
+            di, dd = np.empty(0, dtype=np.int32), np.empty(0, dtype=np.float32)
+        out.append(sparse.csc_matrix((dd, di, indptr[i]), shape=(int(sp.rows[i]), sp.c), copy=False))
     return out
+
+
+def _buffer_of(arr):
+    import mmap
+    return arr.base if isinstance(arr.base, mmap.mmap) else memoryview(arr)

@@ -17,6 +17,10 @@ batch = int(sys.argv[4]) if len(sys.argv) > 4 else 256
 net = synthetic.make_net(kind, 120, seed=0, out_gain=6.0 if kind == 'lstm' else 2.5)
 layers, _ = netdesc.describe_line_net(net)
 rec = LineRecognizer(layers, precision=precision)
+if os.environ.get('B200OCR_CROP_STAGING'):          # A/B of the first conv's uint8 staging (0 plain, 1 cp.async, 2 TMA)
+    rec.set_flag(4, int(os.environ['B200OCR_CROP_STAGING']))
+if os.environ.get('B200OCR_AUTOTUNE_BUDGET'):
+    rec.autotune_precision(budget=float(os.environ['B200OCR_AUTOTUNE_BUDGET']))
 crops = torch.zeros((batch, 40, 1344, 3), dtype=torch.uint8, device='cuda')
 crops[:, :, 32:-32] = torch.from_numpy(synthetic.bench_crops(batch, 1280, seed=0)).cuda()
 out = {}
