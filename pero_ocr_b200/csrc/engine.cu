@@ -107,6 +107,7 @@ struct b200ocr_engine {
     bool use_ref = false;
     bool use_halo = true;
     int ref_only_layer = -1;  // debug flag 5: this layer's contraction alone runs on the CUDA-core cross-check kernel
+    int l2_chunk_lines = 4;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
     int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
     std::vector<LayerRT> layers;
     std::vector<void*> owned;
@@ -386,24 +387,65 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
             case B200OCR_CONV_FIRST: {
                 Shape os{cur.n, cur.h, cur.w, ly.cout0};
                 const int slot = 0;
+                // L2 chunking: the 64-channel records of the first conv are the largest tensor of the step (256 B per
+                // pixel: 3.5 GB at config 2) and are read exactly once, by the next layer.  Run the two layers over
+                // chunks of a few lines, the first conv always writing the SAME region: its records stay dirty in the
+                // 126 MB L2, are consumed from there and overwritten by the next chunk -- they never travel to HBM.
+                LayerRT* nx = li + 1 < L ? &e->layers[li + 1] : nullptr;
+                const bool next_f32 = li + 2 < (int)e->layers.size() &&
+                                      (e->layers[li + 2].kind == B200OCR_UPSAMPLE || e->layers[li + 2].kind == B200OCR_LN_PE);
+                const bool chunked = !dry && !e->use_ref && e->l2_chunk_lines > 0 && cur.n > e->l2_chunk_lines && nx &&
+                                     nx->kind == B200OCR_CONV && !next_f32;
                 if (dry) dry->hn(slot, hbytes(e, os));
                 else {
                     if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
-                    CUtensorMap tm_crops;
-                    const bool bulk_ok = (cur.w % 16) == 0 && (reinterpret_cast<uintptr_t>(crops) % 16) == 0;
+                    const bool bulk_ok = (cur.w % 16) == 0 && (reinterpret_cast<uintptr_t>(crops) % 16) == 0 &&
+                                         ((static_cast<size_t>(cur.h) * cur.w * 3) % 16) == 0;
                     const int staging = bulk_ok ? e->crop_staging : 0;
-                    if (!e->use_ref && staging == 2)
-                        if (int s = make_map_crops(e, &tm_crops, crops, cur.n, cur.h, cur.w)) return s;
-                    ProfScope ps(e, st, PROF_CONV_FIRST);
-                    if (e->use_ref)   // CUDA-core fp32 cross-check kernel
-                        CU_TRY(e, launch_conv_first(crops, cur.n, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
-                                                    e->fmt, static_cast<__half*>(e->hbuf[slot]), st));
-                    else
-                        CU_TRY(e, launch_conv_first_mma(crops, cur.n, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
-                                                        ly.cout0, ly.act, e->fmt, static_cast<__half*>(e->hbuf[slot]),
-                                                        staging, staging == 2 ? &tm_crops : nullptr, st));
-                    e->launches++;
-                    cur_h = static_cast<__half*>(e->hbuf[slot]);
+                    __half* rec = static_cast<__half*>(e->hbuf[slot]);
+                    auto first = [&](const uint8_t* src, int n_lines) -> int {
+                        CUtensorMap tm_crops;
+                        if (!e->use_ref && staging == 2)
+                            if (int s = make_map_crops(e, &tm_crops, src, n_lines, cur.h, cur.w)) return s;
+                        ProfScope ps(e, st, PROF_CONV_FIRST);
+                        if (e->use_ref)   // CUDA-core fp32 cross-check kernel
+                            CU_TRY(e, launch_conv_first(src, n_lines, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
+                                                        e->fmt, rec, st));
+                        else
+                            CU_TRY(e, launch_conv_first_mma(src, n_lines, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
+                                                            ly.cout0, ly.act, e->fmt, rec, staging,
+                                                            staging == 2 ? &tm_crops : nullptr, st));
+                        e->launches++;
+                        return 0;
+                    };
+                    if (!chunked) {
+                        if (int s = first(crops, cur.n)) return s;
+                    } else {
+                        Shape os2{cur.n, (cur.h + 2 * nx->g.pad_h - nx->g.kh + 1) / nx->pool_h,
+                                  (cur.w + 2 * nx->g.pad_w - nx->g.kw + 1) / nx->pool_w, nx->g.cout};
+                        const int slot2 = next_h(slot, -1);
+                        if (hbytes(e, os2) > e->hbuf_bytes[slot2]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
+                        const size_t in_line = static_cast<size_t>(cur.h) * cur.w * 3;
+                        const size_t out_line = hbytes(e, Shape{1, os2.h, os2.w, os2.c}) / sizeof(__half);
+                        for (int c0 = 0; c0 < cur.n; c0 += e->l2_chunk_lines) {
+                            const int nl = std::min(e->l2_chunk_lines, cur.n - c0);
+                            e->cur_layer = li;
+                            if (int s = first(crops + c0 * in_line, nl)) return s;
+                            e->cur_layer = li + 1;
+                            EpiOut eo;
+                            eo.out_h = static_cast<__half*>(e->hbuf[slot2]) + c0 * out_line;
+                            if (int s = run_gemm(e, nx->g, rec, Shape{nl, cur.h, cur.w, ly.cout0}, nx->act, nx->pool_h,
+                                                 nx->pool_w, eo, st, nullptr))
+                                return s;
+                        }
+                        cur_h = static_cast<__half*>(e->hbuf[slot2]);
+                        hslot = slot2;
+                        cur = os2;
+                        cur_f = nullptr;
+                        ++li;   // the next layer has been run chunk by chunk
+                        break;
+                    }
+                    cur_h = rec;
                 }
                 hslot = slot;
                 cur = os;
@@ -1295,6 +1337,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     else if (flag == 3) e->lstm_hplanes = (value != 0 && e->lstm_planes == 2) ? 2 : 1;
     else if (flag == 4) e->crop_staging = value < 0 || value > 2 ? 2 : value;
     else if (flag == 5) e->ref_only_layer = value;
+    else if (flag == 6) e->l2_chunk_lines = value < 0 ? 0 : value;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

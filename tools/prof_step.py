@@ -19,6 +19,8 @@ layers, _ = netdesc.describe_line_net(net)
 rec = LineRecognizer(layers, precision=precision)
 if os.environ.get('B200OCR_CROP_STAGING'):          # A/B of the first conv's uint8 staging (0 plain, 1 cp.async, 2 TMA)
     rec.set_flag(4, int(os.environ['B200OCR_CROP_STAGING']))
+if os.environ.get('B200OCR_L2_CHUNK'):               # lines per chunk of the first two conv layers (flag 6)
+    rec.set_flag(6, int(os.environ['B200OCR_L2_CHUNK']))
 if os.environ.get('B200OCR_AUTOTUNE_BUDGET'):
     rec.autotune_precision(budget=float(os.environ['B200OCR_AUTOTUNE_BUDGET']))
 crops = torch.zeros((batch, 40, 1344, 3), dtype=torch.uint8, device='cuda')
