@@ -547,7 +547,7 @@ class B200EngineLineOCR:
                                  return_ids)
 
     def process_baselines(self, page, lines, cropper, sparse_logits=True, tight_crop_logits=False, no_logits=False,
-                          return_ids=False):
+                          return_ids=False, prepared=None):
         """The page path end to end on the device: `lines` = [(baseline, heights), ...] of one page (`page` a
         cropper.DevicePage), `cropper` a B200LineCropper with a polynomial baseline fit (poly > 0).  Only ~200 bytes
         of line parameters per line are uploaded; the sampling maps, the bilinear resampling, the padding of the
@@ -556,7 +556,8 @@ class B200EngineLineOCR:
         from .cropper import remap_poly_into
         if cropper.line_height != self.line_px_height:
             raise ValueError('cropper and recogniser disagree on the line height')
-        prepared = [cropper.poly_params(b, h) for b, h in lines]
+        if prepared is None:
+            prepared = [cropper.poly_params(b, h) for b, h in lines]
 
         def stager(chunk, width):
             def device_fill(dev_batch):
@@ -566,6 +567,53 @@ class B200EngineLineOCR:
 
         return self._run_batches([p[0].n_out for p in prepared], stager, sparse_logits, tight_crop_logits, no_logits,
                                  return_ids)
+
+    def process_pages(self, pages, cropper, parsenet=None, parsenet_downsample=None, prefetch=2, **kw):
+        """Pages through the page path with the stages of consecutive pages overlapped -- what
+        PageParser.process_page (page_parser.py:515-531) does page after page, synchronously: `pages` is an iterable of
+        (image uint8 [H, W, 3], [(baseline, heights), ...]); yields, in order, (transcriptions, logits, logit_coords,
+        maps) per page (`maps` = parsenet.get_maps(image, parsenet_downsample) or None).  While page i is recognised
+        on the main stream, up to `prefetch` following pages are prepared on host threads: image upload on a side
+        stream, polynomial fits of the baselines (crop_engine.py:54-73), and the ParseNet forward on its own engine.
+        Results are exactly those of process_baselines / get_maps called page by page."""
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        from .cropper import DevicePage
+        torch = self.model.torch
+        lock = threading.Lock()
+        streams = [torch.cuda.Stream(self.device) for _ in range(max(1, prefetch))]
+
+        def prepare(k, image, lines):
+            with torch.cuda.device(self.device), torch.cuda.stream(streams[k % len(streams)]):
+                page = DevicePage(image, self.device)
+                ready = torch.cuda.Event()
+                ready.record(streams[k % len(streams)])
+                maps = None
+                if parsenet is not None:
+                    with lock:                                   # one native engine, not re-entrant
+                        maps = parsenet.get_maps(image, parsenet_downsample or parsenet.init_downsample)
+            fitted = [cropper.poly_params(b, h) for b, h in lines]
+            return page, fitted, ready, maps
+
+        it = iter(pages)
+        with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
+            pending, k = [], 0
+            for item in it:
+                pending.append((pool.submit(prepare, k, item[0], item[1]), item[1]))
+                k += 1
+                if len(pending) >= max(1, prefetch):
+                    break
+            while pending:
+                fut, lines = pending.pop(0)
+                page, fitted, ready, maps = fut.result()
+                nxt = next(it, None)
+                if nxt is not None:
+                    pending.append((pool.submit(prepare, k, nxt[0], nxt[1]), nxt[1]))
+                    k += 1
+                with self._device_ctx():
+                    torch.cuda.current_stream(self.device).wait_event(ready)
+                tr, lg, co = self.process_baselines(page, lines, cropper, prepared=fitted, **kw)
+                yield tr, lg, co, maps
 
     def decode_lines(self, lines, decoder):
         """Recognise and beam-decode in one pass on the device: the work of PageOCR.process_page followed by

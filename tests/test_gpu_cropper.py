@@ -128,3 +128,31 @@ def test_pad_lines_builds_the_reference_batch():
                                      out.data_ptr(), out_w, pad, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_process_pages_pipeline_equals_page_by_page(tmp_path):
+    """process_pages (upload / baseline fits / ParseNet of the following pages overlapped with the recognition of the
+    current one) returns, page for page, exactly what DevicePage + process_baselines + get_maps return one at a time."""
+    from oracle.nets import make_net
+    from pero_ocr_b200.cropper import B200LineCropper, DevicePage
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    from pero_ocr_b200.parsenet import B200ParseNet
+    js = write_engine_json(tmp_path, 'lstm')
+    eng = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=8, module=make_case_net('lstm'))
+    pn = B200ParseNet(None, torch.device('cuda', 0), downsample=2, adaptive_downsample=False,
+                      module=make_net('parsenet', seed=cases.PARSENET_CASE['seed']))
+    cropper = B200LineCropper(line_height=40, poly=2, scale=1)
+    rng = np.random.default_rng(31)
+    pages = []
+    for p in range(5):
+        img = rng.integers(0, 256, (300 + 40 * p, 520, 3), dtype=np.uint8)
+        lines = [([[20, 40 + 50 * i], [250, 44 + 50 * i + p], [500 - 30 * i, 40 + 50 * i]], [22, 10]) for i in range(3 + p % 2)]
+        pages.append((img, lines))
+    got = list(eng.process_pages(iter(pages), cropper, parsenet=pn, parsenet_downsample=2, prefetch=2, sparse_logits=False))
+    assert len(got) == len(pages)
+    for (img, lines), (tr, lg, co, maps) in zip(pages, got):
+        tr_b, lg_b, co_b = eng.process_baselines(DevicePage(img), lines, cropper, sparse_logits=False)
+        assert tr == tr_b and co == co_b
+        for a, b in zip(lg, lg_b):
+            assert np.array_equal(a, b)
+        assert np.array_equal(maps, pn.get_maps(img, 2))
