@@ -107,7 +107,7 @@ struct b200ocr_engine {
     bool use_ref = false;
     bool use_halo = true;
     int ref_only_layer = -1;  // debug flag 5: this layer's contraction alone runs on the CUDA-core cross-check kernel
-    int l2_chunk_lines = 4;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
+    int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
     int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
     std::vector<LayerRT> layers;
     std::vector<void*> owned;

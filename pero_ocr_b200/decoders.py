@@ -86,6 +86,7 @@ def greedy_ids_device(x, layout='ntc', want_confidence=False):
     """Device-resident form: x is a contiguous CUDA float32 tensor; returns CUDA tensors, no synchronisation."""
     torch = _torch()
     lib = _lib.load_library()
+    x = x.contiguous()
     dev = x.device
     if layout == 'ntc':
         n, t, c = x.shape
@@ -112,6 +113,7 @@ def prefix_beam_device(x, k):
     status [N]); no synchronisation."""
     torch = _torch()
     lib = _lib.load_library()
+    x = x.contiguous()
     n, t, c = x.shape
     dev = x.device
     labels = torch.empty((n, k, t), dtype=torch.int32, device=dev)
@@ -129,6 +131,7 @@ def full_logprobs_device(logits):
     core/layout.py:65-72), computed on the device; no synchronisation."""
     torch = _torch()
     lib = _lib.load_library()
+    logits = logits.contiguous()
     n, t, c = logits.shape
     out = torch.empty((n, t, c), dtype=torch.float64, device=logits.device)
     _lib.check(lib.b200ocr_full_logprobs(logits.data_ptr(), n, t, c, out.data_ptr(), _stream(torch, logits.device)))
@@ -139,6 +142,7 @@ def prefix_beam_device_ranges(x, k, t_lo, t_hi):
     """prefix_beam_device on the frame range [t_lo[i], t_hi[i]) of every line (CUDA int32 [N] tensors)."""
     torch = _torch()
     lib = _lib.load_library()
+    x = x.contiguous()
     n, t, c = x.shape
     dev = x.device
     labels = torch.empty((n, k, t), dtype=torch.int32, device=dev)
@@ -265,7 +269,9 @@ class CTCPrefixLogRawNumpyDecoder:
                     bag.add('', 0.0, 0)
                     bags[i] = bag
                 continue
-            x = torch.from_numpy(np.stack([mats[i] for i in idxs])).to(dev)
+            # C order explicitly: get_full_logprobs() of a CSC matrix is Fortran-ordered (scipy's toarray), and np.stack
+            # of Fortran-ordered inputs keeps that order -- the kernel reads [n][t][c]
+            x = torch.from_numpy(np.ascontiguousarray(np.stack([mats[i] for i in idxs]))).to(dev)
             labels = torch.empty((n, k, t), dtype=torch.int32, device=dev)
             lengths = torch.empty((n, k), dtype=torch.int32, device=dev)
             scores = torch.empty((n, k), dtype=torch.float64, device=dev)

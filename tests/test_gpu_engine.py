@@ -274,9 +274,11 @@ def test_layer_correction_modes_match_cuda_core_cross_check(mode):
         a = eng.debug_forward_prefix(crops, i + 1)
         eng.set_flag(5, i)
         b = eng.debug_forward_prefix(crops, i + 1)
-        scale = max(1.0, float(np.abs(b).max()))
-        worst = max(worst, float(np.abs(a - b).max()) / scale)
-        assert np.abs(a - b).max() <= 2e-5 * scale, (i, float(np.abs(a - b).max()), scale)
+        # the read-back is the record's value hi + lo' (lo' has 3 significant bits: steps of 2^-14 of the element), so
+        # two fp32 results a rounding apart may read back one such step apart; a wrong chunk / K-step would be >= 1e-3
+        err = np.abs(a - b) / (np.abs(b) + 0.05)
+        worst = max(worst, float(err.max()))
+        assert err.max() <= 2.0 ** -12, (i, float(err.max()))
     eng.set_flag(5, -1)
     print(f'correction mode {mode}: tcgen05 vs CUDA-core cross-check per layer, worst relative difference {worst:.2e}')
     total, per = eng.executed_passes(3, 328)
