@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
     __shared__ __align__(128) uint8_t s_u8[STAGE == STAGE_PLAIN ? 16 : (CFM_ROWS + 2) * CFM_U8ROW];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_sc[COUT], s_b[COUT];
-    extern __shared__ uint4 s_stage[];   // [CFM_PX][planes * COUT / 8]: one image row of pixel records
+    extern __shared__ uint4 s_stage[];   // [4 warps][16 px][planes * COUT / 8]: one m-tile of pixel records per warp
 
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int tiles_h = (h + CFM_ROWS - 1) / CFM_ROWS;
@@ -146,10 +146,15 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
 
     const int rec = planes * COUT;
     const int chunks = rec / 8;                 // 16-byte chunks per pixel record
+    // Each warp stages ONE 16-pixel m-tile of records at a time in its private slice of shared memory and writes it
+    // back itself (16 px x `rec` fp16 contiguous in HBM: whole 128-byte lines): no block-wide barrier in the row loop
+    // and 16 KB instead of 32 KB of staging per CTA -- the version that staged a whole 128-pixel row per CTA was
+    // limited to 4 CTAs (16 warps) per SM by shared memory and ran at 36 % of the copy bandwidth
+    // (profiles/r02d_conv_first_staging_ab.md).
+    uint4* w_stage = s_stage + warp * 16 * chunks;
     for (int rr = 0; rr < CFM_ROWS; ++rr) {
         const int row = row0 + rr;
         if (row >= h) break;
-        if (rr) __syncthreads();                // previous row's staging has been read
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             const int pb = warp * 32 + mt * 16;
@@ -173,11 +178,12 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
                     mma16816(acc[nt], a, bl.x, bl.y);
                 }
             }
-            // fragment -> staged records: rows (pixels) pb+gid and pb+gid+8, channels 8 nt + 2 tig + {0, 1}
+            __syncwarp();                       // the previous m-tile's records have been read out of the slice
+            // fragment -> staged records: rows (pixels) gid and gid + 8 of the m-tile, channels 8 nt + 2 tig + {0, 1}
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int px = pb + gid + 8 * half;
-                uint4* my = s_stage + px * chunks;
+                const int px = gid + 8 * half;
+                uint4* my = w_stage + px * chunks;
                 const int sw = px & (chunks - 1);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
@@ -202,14 +208,14 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
                     }
                 }
             }
-        }
-        __syncthreads();
-        {
-            const int npx = min(CFM_PX, w - w0);
-            uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row) * w + w0) * rec);
-            for (int i = threadIdx.x; i < npx * chunks; i += CFM_PX) {
-                const int px = i / chunks, c = i - px * chunks;
-                dst[i] = s_stage[px * chunks + (c ^ (px & (chunks - 1)))];
+            __syncwarp();
+            {
+                const int npx = min(16, w - (w0 + pb));     // pixels of this m-tile inside the image (<= 0: none)
+                uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row) * w + w0 + pb) * rec);
+                for (int i = lane; i < npx * chunks; i += 32) {
+                    const int px = i / chunks, c = i - px * chunks;
+                    dst[i] = w_stage[px * chunks + (c ^ (px & (chunks - 1)))];
+                }
             }
         }
     }
@@ -261,7 +267,7 @@ cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const 
     const int planes = act_planes(fmt);
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
-    const size_t dyn = static_cast<size_t>(CFM_PX) * planes * cout * sizeof(__half);
+    const size_t dyn = static_cast<size_t>(CFM_PX / 32) * 16 * planes * cout * sizeof(__half);
     if ((w % 16) || (staging == STAGE_TMA && !tm_in)) staging = STAGE_PLAIN;   // bulk variants need 16-byte aligned rows
     static PerDeviceOnce attr_done;
     if (attr_done.pending()) {
