@@ -535,6 +535,8 @@ def main():
     ap.add_argument('--no-incumbent', action='store_true', help="skip the reference's GPU eager path (N=1 only)")
     ap.add_argument('--incumbent-steps', type=int, default=5)
     ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 3 and 4 (N=1 only)')
+    ap.add_argument('--replicas', type=int, default=int(os.environ.get('B200OCR_REPLICAS', '2')),
+                    help='native engine replicas per GPU, alternating steps on their own streams (1 = one stream)')
     ap.add_argument('--profile-out', default=None, help='write the per-layer kernel table (JSON) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -570,13 +572,16 @@ def main():
 
     # ---- engine through the reference-facing constructor (engine JSON + module)
     net = make_net(args.net)
-    engine = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, precision=args.precision, module=net)
+    engine = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, precision=args.precision, module=net,
+                               replicas=args.replicas)
     engine.max_input_horizontal_pixels = BATCH * WIDTH          # as user_scripts/select_embed_id.py:54-55 does
     rec = engine.model
-    rec.reserve(BATCH, PADDED)
+    recs = engine._models
+    for r in recs:
+        r.reserve(BATCH, PADDED)
     tuned = None
     if args.precision == 'fp16f8' and args.autotune_budget > 0:
-        tuned = rec.autotune_precision(budget=args.autotune_budget)
+        tuned = engine.autotune_precision(budget=args.autotune_budget)
     passes_total, passes_per_layer = rec.executed_passes(BATCH, PADDED)
 
     # ---- synthetic inputs: 4 distinct resident batches (165 MB > L2), seeded per rank
@@ -587,10 +592,23 @@ def main():
         b = torch.zeros((BATCH, 40, PADDED, 3), dtype=torch.uint8, device=dev)
         b[:, :, 32:32 + WIDTH] = torch.from_numpy(host_lines[r * BATCH:(r + 1) * BATCH]).to(dev)
         resident.append(b)
-    outs = {}
+    outs = [{} for _ in recs]
+    run_streams = [torch.cuda.Stream(dev) for _ in recs] if len(recs) > 1 else [torch.cuda.current_stream(dev)]
 
     def step(i):
-        rec.forward(resident[i % n_rot], want_logits=False, out=outs)
+        # consecutive steps alternate between the engine replicas, each on its own stream (one replica: the current
+        # stream): the BiLSTM tail of step i overlaps the convolutions of step i + 1
+        k = i % len(recs)
+        with torch.cuda.stream(run_streams[k]):
+            recs[k].forward(resident[i % n_rot], want_logits=False, out=outs[k])
+
+    def fork():
+        for s_ in run_streams:
+            s_.wait_stream(torch.cuda.current_stream(dev))
+
+    def join():
+        for s_ in run_streams:
+            torch.cuda.current_stream(dev).wait_stream(s_)
 
     def barrier():
         if world > 1:
@@ -603,20 +621,24 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    fork()
     for i in range(args.warmup):
         step(i)
+    join()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = rec.launch_count
+    launches0 = sum(r.launch_count for r in recs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
+    ev0.record()                      # on the current stream; the run streams start after it and are joined before ev1
+    fork()
     for i in range(args.steps):
         step(i)
+    join()
     ev1.record()
     barrier()
-    launches = rec.launch_count - launches0
+    launches = sum(r.launch_count for r in recs) - launches0
     ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
     value = world * BATCH * args.steps / (ms_dev / 1e3)
@@ -676,7 +698,7 @@ def main():
     rec.profile(True)
     prof_steps = 3
     for i in range(prof_steps):
-        step(i)
+        rec.forward(resident[i % n_rot], want_logits=False, out=outs[0])
     tags, lidx, pms = rec.profile_read()
     rec.profile(False)
     total_flops, gemm_flops = rec.flops(BATCH, PADDED)
@@ -718,16 +740,29 @@ def main():
         variants = {}
         gemm_layers = [i for i, k in enumerate(rec._kinds) if k in (L.CONV, L.BILSTM, L.CTC_HEAD)]
         saved = dict(rec.corrections)
+
+        def one_stream(count):
+            for i in range(count):
+                rec.forward(resident[i % n_rot], want_logits=False, out=outs[0])
+
+        one_stream(2)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one_stream(5)
+        b.record()
+        torch.cuda.synchronize()
+        variants['one engine, one stream (the timed arithmetic)'] = {'lines_per_s': BATCH * 5 / (a.elapsed_time(b) / 1e3),
+                                                                     'ms_per_step': a.elapsed_time(b) / 5}
         for name, mode in (('full_correction_everywhere (2 passes)', L.CORR_BOTH),
                            ('no_correction = plain fp16, the mantissa of the incumbent\'s TF32 (1 pass)', L.CORR_NONE)):
             for i in gemm_layers:
                 rec.set_layer_correction(i, mode)
             for i in range(2):
-                step(i)
+                rec.forward(resident[i % n_rot], want_logits=False, out=outs[0])
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for i in range(5):
-                step(i)
+                rec.forward(resident[i % n_rot], want_logits=False, out=outs[0])
             b.record()
             torch.cuda.synchronize()
             variants[name] = {'lines_per_s': BATCH * 5 / (a.elapsed_time(b) / 1e3), 'ms_per_step': a.elapsed_time(b) / 5}
@@ -746,7 +781,8 @@ def main():
                    'net': args.net, 'lines_per_step': BATCH, 'precision': args.precision,
                    'precision_autotune': tuned,
                    'l2_policy': f'{n_rot} distinct resident input batches (165 MB) rotated; per-step activations (>3 GB) exceed L2',
-                   'parallelism': f'batch-parallel x{world}, no data-path collective'},
+                   'parallelism': f'batch-parallel x{world}, no data-path collective',
+                   'streams': f'{len(recs)} engine replica(s) per GPU alternating steps on their own CUDA streams'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
     }
     if variants:

@@ -340,7 +340,9 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
  * layer stays on its product kernel (-1 = none): isolates a layer on identical inputs;
  * flag 6: lines per chunk of the first-conv + second-conv pair (the first conv's records then live and die in L2
  * instead of making a 3.5 GB round trip through HBM); 0 = whole batch at once (default: on B200 the ~130 extra launches
- * of 4-line chunks cost more than the HBM round trip, profiles/r02e_l2_chunking.md). */
+ * of 4-line chunks cost more than the HBM round trip, profiles/r02e_l2_chunking.md);
+ * flag 7: the persistent tensor-core kernels draw their tiles from a global counter (default on) instead of a fixed
+ * 1/grid share per CTA -- what lets two engines on two streams share the GPU without serialising. */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

@@ -20,6 +20,7 @@
 
 namespace {
 
+constexpr int kTileCounters = 1024;
 std::string g_create_error;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -107,6 +108,9 @@ struct b200ocr_engine {
     bool use_ref = false;
     bool use_halo = true;
     int ref_only_layer = -1;  // debug flag 5: this layer's contraction alone runs on the CUDA-core cross-check kernel
+    bool dynamic_tiles = true;   // persistent GEMM kernels draw tiles from a global counter (tilesched.cuh; flag 7)
+    int* tile_counters = nullptr;   // [kTileCounters] zeroed at the start of every layer walk
+    int tile_counter_next = 0;
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
     int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
     std::vector<LayerRT> layers;
@@ -298,6 +302,8 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
         static const int dbg = getenv("B200OCR_IGEMM_DBG") ? atoi(getenv("B200OCR_IGEMM_DBG")) : 0;   // bring-up only
         p.dbg = dbg;
     }
+    p.tile_counter = (e->dynamic_tiles && e->tile_counters && e->tile_counter_next < kTileCounters)
+                         ? e->tile_counters + e->tile_counter_next++ : nullptr;
     if (o.epi == EPI_ACT_F16 && (g.cout % 32))
         return fail(e, B200OCR_E_INVALID, "fp16 activation output needs cout %% 32 == 0 (got %d)", g.cout);
     if (o.epi == EPI_CTC && p.tiles_n != 1)
@@ -379,6 +385,10 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
         return 0;
     };
     const int L = std::min<int>(n_layers, e->layers.size());
+    if (!dry && e->dynamic_tiles && e->tile_counters) {
+        CU_TRY(e, cudaMemsetAsync(e->tile_counters, 0, kTileCounters * sizeof(int), st));
+        e->tile_counter_next = 0;
+    }
     for (int li = 0; li < L; ++li) {
         LayerRT& ly = e->layers[li];
         e->cur_layer = li;
@@ -799,6 +809,9 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                 return bail(fail(e, B200OCR_E_INVALID, "layer %d: unknown kind %d", i, d.kind));
         }
     }
+    if (cudaMalloc(reinterpret_cast<void**>(&e->tile_counters), kTileCounters * sizeof(int)) != cudaSuccess)
+        return bail(fail(e, B200OCR_E_CUDA, "cudaMalloc(tile counters) failed"));
+    e->owned.push_back(e->tile_counters);
     if (desc->precision == B200OCR_PREC_FP16F8W)   // preset: weight-side correction only in the deep 3x3 layers
         for (LayerRT& ly : e->layers)
             if (ly.kind == B200OCR_CONV && ly.g.kh * ly.g.kw == 9 && ly.g.cin >= 256) ly.g.corr = CORR_WEIGHT;
@@ -1338,6 +1351,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     else if (flag == 4) e->crop_staging = value < 0 || value > 2 ? 2 : value;
     else if (flag == 5) e->ref_only_layer = value;
     else if (flag == 6) e->l2_chunk_lines = value < 0 ? 0 : value;
+    else if (flag == 7) e->dynamic_tiles = value != 0;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

@@ -53,6 +53,7 @@ struct IgemmParams {
     float* fmax;
     float* flse;
     float* fprob;             // best-class probability under the reference's sparsified softmax (or null)
+    int* tile_counter;        // dynamic tile scheduler: zeroed device counter of this launch (null = static striding)
     int dbg;                  // bring-up switches (B200OCR_IGEMM_DBG): 1 = skip epilogue stores, 2 = skip MMA issue
 };
 

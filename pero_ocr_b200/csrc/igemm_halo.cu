@@ -13,6 +13,7 @@
 #include "once.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
+#include "tilesched.cuh"
 
 namespace {
 
@@ -74,6 +75,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tfull = b_empty + C::kBStages;              // [2]
     uint64_t* tempty = tfull + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tq_full = tempty + 3;                       // [4] dynamic tile scheduler ring (tilesched.cuh)
+    uint64_t* tq_empty = tq_full + kTileRing;             // [4]
+    int* tq_tile = reinterpret_cast<int*>(tq_empty + kTileRing);
     float* s_vec = reinterpret_cast<float*>(smem + C::kBarOff + 256);
     uint4* s_epi = reinterpret_cast<uint4*>(s_vec + 3 * p.cout_pad);   // kStagedEpi: 256 uint4 per epilogue warp
 
@@ -105,6 +109,10 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_init(&tfull[i], 1);
             ptx::mbar_init(&tempty[i], 8);
         }
+        for (int i = 0; i < kTileRing; ++i) {
+            ptx::mbar_init(&tq_full[i], 1);
+            ptx::mbar_init(&tq_empty[i], 10);   // weight producer + MMA issuer + 8 epilogue warps
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -124,7 +132,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileFeed feed(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+        for (int tile = feed.next(lane); tile < total_tiles; tile = feed.next(lane)) {
             const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
             for (int kc = 0; kc < kchunks; ++kc)
                 for (int ap = 0; ap < planes; ++ap) {
@@ -144,7 +153,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileTake take(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+        for (int tile = take.next_warp(lane); tile < total_tiles; tile = take.next_warp(lane)) {
             const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
             for (int kc = 0; kc < kchunks; ++kc)
                 for (int ap = 0; ap < planes; ++ap) {
@@ -181,7 +191,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool skip_mma = (p.dbg & 2) != 0;             // bring-up: time the pipeline without tensor work
             int as = 0, bs = 0, acc = 0;
             uint32_t aph = 0, bph = 0, acc_phase0 = 0, acc_phase1 = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            TileTake take(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+            for (int tile = take.next(); tile < total_tiles; tile = take.next()) {
                 ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d0 = tmem_base + acc * 2 * BN;
@@ -254,7 +265,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int Hp = p.h_out / p.pool_h, Wp = p.w_out / p.pool_w;
         int acc = 0;
         uint32_t acc_phase0 = 0, acc_phase1 = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileTake take(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+        for (int tile = take.next_warp(lane); tile < total_tiles; tile = take.next_warp(lane)) {
             const Tile t = tile_coord(p, tile, tiles_w, tiles_h);
             const int wo = t.w0 + q * 32 + lane;
             ptx::mbar_wait(&tfull[acc], acc ? acc_phase1 : acc_phase0);

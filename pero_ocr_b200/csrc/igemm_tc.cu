@@ -15,6 +15,7 @@
 #include "once.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
+#include "tilesched.cuh"
 
 namespace {
 
@@ -27,7 +28,7 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes;
     static constexpr int kTmemCols = 512;  // whole TMEM (1 CTA/SM): base address is 0 => warp-uniform operands
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tile ring*/;
 };
 
 struct SegCoord {
@@ -70,6 +71,12 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull = bars + 2 * C::kStages;    // [2]
     uint64_t* tempty = bars + 2 * C::kStages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+    // dynamic tile scheduler (IgemmParams::tile_counter): the producer warp draws tile indices from a global counter
+    // and hands them to the MMA and epilogue warps through a 4-deep ring -- a CTA that starts late (its SM was busy
+    // with another stream's kernel) simply draws fewer tiles, instead of owning a fixed 1/gridDim share
+    uint64_t* tq_full = bars + 2 * C::kStages + 5;   // [4]
+    uint64_t* tq_empty = tq_full + 4;                // [4]
+    int* tq_tile = reinterpret_cast<int*>(tq_empty + 4);   // [4]
     // per-channel epilogue vectors (bias | post_scale | post_shift), cout_pad floats each, 16-byte aligned
     float* s_vec = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);
 
@@ -95,6 +102,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_init(&tfull[i], 1);
             ptx::mbar_init(&tempty[i], 8);  // one arrive per epilogue warp
         }
+        for (int i = 0; i < 4; ++i) {
+            ptx::mbar_init(&tq_full[i], 1);
+            ptx::mbar_init(&tq_empty[i], 9);   // MMA warp + 8 epilogue warps
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -116,7 +127,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileFeed feed(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+        for (int tile = feed.next(lane); tile < total_tiles; tile = feed.next(lane)) {
             const int mt = tile / p.tiles_n;
             const int nt = tile - mt * p.tiles_n;
             SegCoord sc[4];
@@ -161,7 +173,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase0 = 0, acc_phase1 = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            TileTake take(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+            for (int tile = take.next(); tile < total_tiles; tile = take.next()) {
                 ptx::mbar_wait(&tempty[acc], (acc ? acc_phase1 : acc_phase0) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -214,7 +227,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool has_affine = p.post_scale != nullptr;
         int acc = 0;
         uint32_t acc_phase[2] = {0, 0};
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileTake take(p.tile_counter, total_tiles, tq_full, tq_empty, tq_tile);
+        for (int tile = take.next_warp(lane); tile < total_tiles; tile = take.next_warp(lane)) {
             const int mt = tile / p.tiles_n;
             const int nt = tile - mt * p.tiles_n;
             const SegCoord sc = seg_coord(p, mt * 4 + q);

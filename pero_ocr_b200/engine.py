@@ -227,7 +227,7 @@ class B200EngineLineOCR:
     Embedding-conditioned nets (``embed_id``) are not supported and raise at construction.
     """
 
-    def __init__(self, json_def, device=None, batch_size=8, precision=DEFAULT_PRECISION, module=None):
+    def __init__(self, json_def, device=None, batch_size=8, precision=DEFAULT_PRECISION, module=None, replicas=1):
         import torch
         with open(json_def, 'r', encoding='utf8') as f:
             self.config = json.load(f)
@@ -265,6 +265,12 @@ class B200EngineLineOCR:
         self.num_classes = n_classes
         self.model = LineRecognizer(layers, precision=precision, line_height=self.line_px_height,
                                     device=self.device.index or 0)
+        # replicas = 2: a second native engine (own weights copy and workspace) on a second stream.  process_lines then
+        # alternates its batches between the two, so the latency-bound tail of batch i (BiLSTM recurrence: 64 of the
+        # 148 SMs) overlaps the convolutions of batch i+1; the persistent conv kernels draw tiles dynamically
+        # (csrc/tilesched.cuh), which keeps the sharing work-conserving.
+        self._models = [self.model] + [LineRecognizer(layers, precision=precision, line_height=self.line_px_height,
+                                                      device=self.device.index or 0) for _ in range(max(1, replicas) - 1)]
         self._slots = None
         self._copy_stream = None
         # host threads that pad a batch into pinned memory (process_lines): a few when the process has the cores for
@@ -286,6 +292,16 @@ class B200EngineLineOCR:
     def _device_ctx(self):
         return self.model.torch.cuda.device(self.device)
 
+    def autotune_precision(self, budget=3e-4, sample=None):
+        """LineRecognizer.autotune_precision on the first native engine; the chosen per-layer modes are applied to
+        every replica."""
+        with self._device_ctx():
+            rep = self.model.autotune_precision(budget=budget, sample=sample)
+            for other in self._models[1:]:
+                for i in set(other.corrections) | set(self.model.corrections):
+                    other.set_layer_correction(i, self.model.corrections.get(i, _lib.CORR_BOTH))
+        return rep
+
     def _pool(self):
         if getattr(self, '_executor', None) is None:
             from concurrent.futures import ThreadPoolExecutor
@@ -301,6 +317,7 @@ class B200EngineLineOCR:
             self._slots = [dict(pin=None, dev=None, outs={}, host={}, done=torch.cuda.Event(), h2d=torch.cuda.Event())
                            for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(self.device)
+            self._run_streams = [torch.cuda.Stream(self.device) for _ in self._models] if len(self._models) > 1 else None
         return self._slots[k]
 
     def _stage_packed(self, sl, crops, shape, dev, main):
@@ -367,7 +384,19 @@ class B200EngineLineOCR:
             sl['dev'] = torch.empty(n_bytes, dtype=torch.uint8, device=self.device)
             sl['pin'] = None
         dev = sl['dev'][:n_bytes].view(shape)
+        model = self._models[k % len(self._models)]
+        if self._run_streams is not None:
+            # this slot's own stream: ordered after whatever the caller queued on the current stream so far
+            main = self._run_streams[k % len(self._run_streams)]
+            main.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(main):
+                return self._submit_on(sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed)
         main = torch.cuda.current_stream(self.device)
+        return self._submit_on(sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed)
+
+    def _submit_on(self, sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed):
+        torch = self.model.torch
+        n_bytes = int(np.prod(shape))
         if device_fill is not None:
             self.h2d_bytes += int(device_fill(dev))
         elif packed is not None:
@@ -384,7 +413,7 @@ class B200EngineLineOCR:
                 sl['h2d'].record(self._copy_stream)
             main.wait_event(sl['h2d'])
             self.h2d_bytes += n_bytes
-        o = self.model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence, out=sl['outs'])
+        o = model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence, out=sl['outs'])
         sl['outs'] = o
         sl['sparse'] = None
         dense = not no_logits and sparse_ranges is None
