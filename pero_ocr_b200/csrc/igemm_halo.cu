@@ -30,6 +30,13 @@ struct Cfg {
     // busy, issuer never blocked on a barrier).  BN = 64 therefore streams a whole filter ROW (3 taps, 24 MMAs) per
     // stage.  (A third halo stage instead made no difference: the halo loads are not the limiter.)
     static constexpr int kTapsPerStage = BN == 64 ? 3 : 1;
+    // BN = 64 additionally PAIRS the two output rows of a tile in the N dimension.  A weight stage then holds one
+    // filter COLUMN s as three consecutive 64-row blocks W(2,s) | W(1,s) | W(0,s); halo row i feeds output row 0 with
+    // filter row i and output row 1 with filter row i-1, so the two middle halo rows take ONE N = 128 MMA over two
+    // adjacent blocks (accumulator columns [0,64) = row 0, [64,128) = row 1) and the outer halo rows one N = 64 MMA
+    // each: 4 instead of 6 MMAs per (s, K step) and 84 instead of 108 KB of operand reads -- an M = 128 MMA reads
+    // 4 KB of A whatever N is, which is what bounds this layer (profiles/r01d_halo_limits.md).
+    static constexpr bool kPairRows = BN == 64;
     static constexpr int kAStages = 2;
     // BN = 128 stores through the staged epilogue (actfmt.cuh: epi_store32_staged; the un-pooled 128-channel layer
     // spent 0.5 of its 1.4 ms on sector-splitting stores): its 32 KB come out of the weight ring (4 -> 3 stages)
@@ -168,7 +175,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                             for (int tt = 0; tt < C::kTapsPerStage; ++tt)
                                 ptx::tma_load_2d_pred(sB + stage * C::kBStageBytes + tt * C::kBBytes, &tmB, &b_full[stage],
-                                                      kc * 64, ((f8 ? ap : bp) * 9 + tap + tt) * p.cout_pad + t.nt * BN,
+                                                      kc * 64,
+                                                      ((f8 ? ap : bp) * 9 + (C::kPairRows ? (2 - tt) * 3 + tap / 3 : tap + tt)) *
+                                                              p.cout_pad + t.nt * BN,
                                                       leader);
                             if (++stage == C::kBStages) {
                                 stage = 0;
@@ -212,7 +221,32 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             for (int tap0 = 0; tap0 < 9; tap0 += C::kTapsPerStage) {
                                 ptx::mbar_wait(&b_full[bs], bph);
                                 ptx::tc_fence_after();
-                                if (!skip_mma) {
+                                if (!skip_mma && C::kPairRows) {
+                                    // stage = filter column s: blocks W(2,s) | W(1,s) | W(0,s).  Outer halo rows first:
+                                    // they are the MMAs that may have to overwrite a row's accumulator
+                                    constexpr uint32_t idesc_n2 = ptx::idesc_f16_f32(128, 2 * BN);
+                                    constexpr uint32_t idesc8_n2 = ptx::idesc_e5m2_f32(128, 2 * BN);
+                                    const int s = tap0 / 3;
+                                    const uint64_t b0 = desc_hi + ((sB_u + bs * C::kBStageBytes) >> 4);
+#pragma unroll
+                                    for (int step = 0; step < 4; ++step) {
+                                        const int hrow = step == 0 ? 3 : (step == 1 ? 0 : step - 1);   // 3, 0, 1, 2
+                                        const int blk = step == 0 ? 0 : (step == 1 ? 2 : (step == 2 ? 1 : 0));
+                                        const bool wide = step >= 2;
+                                        const uint32_t d = d0 + (step == 0 ? BN : 0);
+                                        const uint64_t a_desc = a_base + ((hrow * kHaloW + s) * 8);
+                                        const uint64_t b_desc = b0 + ((blk * C::kBBytes) >> 4);
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (e5m2) {
+                                                if (k >= f8_k0)
+                                                    ptx::mma_f8_ss(d, a_desc + 2 * k, b_desc + 2 * k, wide ? idesc8_n2 : idesc8, 1u);
+                                            } else
+                                                ptx::mma_f16_ss(d, a_desc + 2 * k, b_desc + 2 * k, wide ? idesc_n2 : idesc,
+                                                                (wide || s != 0 || k != 0) ? 1u : started);
+                                        }
+                                    }
+                                } else if (!skip_mma) {
 #pragma unroll
                                     for (int tt = 0; tt < C::kTapsPerStage; ++tt) {
                                         const int tap = tap0 + tt;

@@ -315,7 +315,7 @@ class B200EngineLineOCR:
         if self._slots is None:
             torch = self.model.torch
             self._slots = [dict(pin=None, dev=None, outs={}, host={}, done=torch.cuda.Event(), h2d=torch.cuda.Event())
-                           for _ in range(2)]
+                           for _ in range(2 * len(self._models))]
             self._copy_stream = torch.cuda.Stream(self.device)
             self._run_streams = [torch.cuda.Stream(self.device) for _ in self._models] if len(self._models) > 1 else None
         return self._slots[k]
@@ -533,7 +533,11 @@ class B200EngineLineOCR:
                     coords_out[idx] = [lo, hi]
                 logits_out[idx] = line_logits.copy()
 
-        in_flight = None
+        # batches in flight before the oldest is collected: one per native engine (replica), so that with two replicas
+        # the tail of batch i, the head of batch i+1 and the staging of batch i+2 are all under way at once
+        depth = len(self._models)
+        nslots = 2 * depth
+        in_flight = []
         with self._device_ctx():
             for bi, (chunk, widest) in enumerate(self._batches(widths)):
                 full_w = widest + 2 * pad
@@ -549,16 +553,17 @@ class B200EngineLineOCR:
                     else:
                         ranges = ([0] * len(chunk), [t_all] * len(chunk))
                 kw = stager(chunk, width)
-                ticket = self._submit(bi & 1, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
+                ticket = self._submit(bi % nslots, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
                                       device_fill=kw.get('device_fill'), packed=kw.get('packed'))
-                if in_flight is not None:
-                    res = self._collect(in_flight[1])
+                in_flight.append((chunk, ticket))
+                if len(in_flight) > depth:
+                    done_chunk, done_ticket = in_flight.pop(0)
+                    res = self._collect(done_ticket)
                     t0 = time.perf_counter()
-                    finish(in_flight[0], res)
+                    finish(done_chunk, res)
                     self.host_ms['finish'] += 1e3 * (time.perf_counter() - t0)
-                in_flight = (chunk, ticket)
-            if in_flight is not None:
-                finish(in_flight[0], self._collect(in_flight[1]))
+            for done_chunk, done_ticket in in_flight:
+                finish(done_chunk, self._collect(done_ticket))
         self.last_line_confidences = confidences if self.want_confidence else None
         return transcriptions, logits_out, coords_out
 

@@ -276,7 +276,9 @@ def test_layer_correction_modes_match_cuda_core_cross_check(mode):
         b = eng.debug_forward_prefix(crops, i + 1)
         # the read-back is the record's value hi + lo' (lo' has 3 significant bits: steps of 2^-14 of the element), so
         # two fp32 results a rounding apart may read back one such step apart; a wrong chunk / K-step would be >= 1e-3
-        err = np.abs(a - b) / (np.abs(b) + 0.05)
+        # (plus, on small elements of deep layers, the fp32 summation-order noise of K = 4608 terms)
+        scale = max(1.0, float(np.sqrt((b.astype(np.float64) ** 2).mean())))
+        err = (np.abs(a - b) - 5e-5 * scale) / (np.abs(b) + 1e-6)
         worst = max(worst, float(err.max()))
         assert err.max() <= 2.0 ** -12, (i, float(err.max()))
     eng.set_flag(5, -1)

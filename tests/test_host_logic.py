@@ -28,6 +28,7 @@ def _host_only_engine(kind):
     eng.host_threads = 3
     eng.host_ms = {'stage': 0.0, 'wait': 0.0, 'finish': 0.0}
     eng._executor = None
+    eng._models = [None]                   # one native engine: two batches in flight
     eng.h2d_bytes = eng.d2h_bytes = 0
     eng._device_ctx = contextlib.nullcontext
     store = {}
