@@ -168,9 +168,19 @@ class B200LineCropper:
     def poly_params(self, baseline, line_heights, target_height=None):
         """The host half of get_crop_inputs for `poly` > 0 (crop_engine.py:54-73): rotated baseline, polynomial fit,
         arc length, crop width.  -> (_lib.PolyLine, float64 offsets [target_height]); the device evaluates the rest
-        (b200ocr_remap_poly_lines).  A geometry failure yields the reference's fallback, a 32 px all-zero crop."""
+        (b200ocr_remap_poly_lines).  A geometry failure yields the reference's fallback, a 32 px all-zero crop.
+        Bit-exactness of this path relies on the host evaluating np.dot(pts, inv(rot)) the way the reference's host
+        does (a 2 x 2 product: fma(y, r1, x * r0) in NumPy's BLAS-free small-matrix path, pinned by
+        tests/golden/cropper.npz in this container); the rotation of the sampled points themselves is restated on the
+        device with explicit rounding (csrc/remap.cu)."""
         if not self.poly:
             raise ValueError('poly_params needs a polynomial baseline fit (poly > 0); use get_crop_inputs otherwise')
+        if self.poly > 3:
+            # b200ocr_poly_line_t carries four coefficients; the reference (np.polyfit of any degree) would crop such
+            # lines, so refuse loudly instead of returning its zero-crop fallback: get_crop_inputs + process_line_maps
+            # take any degree
+            raise ValueError(f'the device-side baseline evaluation supports poly <= 3 (got {self.poly}); '
+                             f'use get_crop_inputs / process_line_maps for higher degrees')
         target_height = target_height or self.line_height
         line = _lib.PolyLine()
         try:

