@@ -372,7 +372,7 @@ class B200EngineLineOCR:
                                                      pad, C.c_void_p(main.cuda_stream)))
         self.h2d_bytes += total
 
-    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None, device_fill=None, packed=None):
+    def _submit(self, k, shape, fill, no_logits, sparse_ranges=None, device_fill=None, packed=None, beam=None):
         """Stage one padded uint8 batch of `shape` -- filled in place by `fill(view)` in pinned host memory and copied
         to the device on the side stream, or spread on the device from `packed` host crops (_stage_packed), or
         produced on the device by `device_fill(dev_batch)` -- run the forward on the current stream and start the
@@ -390,11 +390,12 @@ class B200EngineLineOCR:
             main = self._run_streams[k % len(self._run_streams)]
             main.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(main):
-                return self._submit_on(sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed)
+                return self._submit_on(sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed,
+                                       beam)
         main = torch.cuda.current_stream(self.device)
-        return self._submit_on(sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed)
+        return self._submit_on(sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed, beam)
 
-    def _submit_on(self, sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed):
+    def _submit_on(self, sl, k, model, main, dev, shape, fill, no_logits, sparse_ranges, device_fill, packed, beam=None):
         torch = self.model.torch
         n_bytes = int(np.prod(shape))
         if device_fill is not None:
@@ -413,10 +414,22 @@ class B200EngineLineOCR:
                 sl['h2d'].record(self._copy_stream)
             main.wait_event(sl['h2d'])
             self.h2d_bytes += n_bytes
-        o = model.forward(dev, want_logits=not no_logits, want_confidence=self.want_confidence, out=sl['outs'])
+        o = model.forward(dev, want_logits=(not no_logits) or beam is not None, want_confidence=self.want_confidence,
+                          out=sl['outs'])
         sl['outs'] = o
         sl['sparse'] = None
-        dense = not no_logits and sparse_ranges is None
+        dense = not no_logits and sparse_ranges is None and beam is None
+        if beam is not None:
+            # PageDecoder's chain on the device (decode_lines): dense logits -> what get_full_logprobs() returns after the
+            # sparsification -> prefix beam search on the frames [logit_coords[0], logit_coords[1]) of every line
+            from .decoders import full_logprobs_device, prefix_beam_device_ranges
+            beam_k, lo, hi = beam
+            lp = full_logprobs_device(o['logits'])
+            lo_d = torch.from_numpy(np.asarray(lo, dtype=np.int32)).to(self.device, non_blocking=True)
+            hi_d = torch.from_numpy(np.asarray(hi, dtype=np.int32)).to(self.device, non_blocking=True)
+            b_labels, b_lengths, b_scores, b_status = prefix_beam_device_ranges(lp, beam_k, lo_d, hi_d)
+            o = dict(o, beam_labels=b_labels, beam_lengths=b_lengths, beam_scores=b_scores, beam_status=b_status)
+            sl['beam_keep'] = (lp, lo_d, hi_d)          # alive until this slot is used again
         if not no_logits and sparse_ranges is not None:
             # softmax threshold + CSC on the device (line_ocr_engine.py:152-156, 168-172): only the surviving entries
             # are copied back, in _collect
@@ -425,6 +438,8 @@ class B200EngineLineOCR:
             sl['sparse_buf'] = sl['sparse']
             sl['sparse'].prefetch_meta(sl.setdefault('sparse_pin', {}))
         names = ['labels', 'lengths'] + (['logits'] if dense else []) + (['confidence'] if self.want_confidence else [])
+        if beam is not None:
+            names += ['beam_labels', 'beam_lengths', 'beam_scores', 'beam_status']
         for name in names:
             t = o[name]
             h = sl['host'].get(name)
@@ -654,39 +669,42 @@ class B200EngineLineOCR:
         PageDecoder.process_page with a CTC prefix decoder without LM (page_parser.py:418-430 and 108-142) --
         raw logits -> sparsification semantics -> -80 fill -> log-softmax (core/layout.py:65-72) -> the slice
         [logit_coords[0]:logit_coords[1]] -> prefix beam search -- without the logits ever leaving the GPU.
-        `decoder`: pero_ocr_b200.decoders.CTCPrefixLogRawNumpyDecoder built on `self.characters + ['<BLANK>']`.
+        `decoder`: pero_ocr_b200.decoders.CTCPrefixLogRawNumpyDecoder built on the net's classes (characters +
+        '<BLANK>', the letters decoder_factory builds, decoding_itf.py:49-50).  Batches are staged, run and collected
+        through the same double-buffered pipeline as process_lines.
         -> list of BagOfHypotheses, one per line (what `decoder(logprobs)` returns in the reference chain)."""
-        from .decoders import CTCPrefixLogRawNumpyDecoder, full_logprobs_device, prefix_beam_device_ranges
+        from .decoders import CTCPrefixLogRawNumpyDecoder
         if not isinstance(decoder, CTCPrefixLogRawNumpyDecoder):
             raise TypeError('decode_lines fuses the GPU prefix beam decoder (CTCPrefixLogRawNumpyDecoder, lm=None)')
         if len(decoder._letters) != self.num_classes:
             raise ValueError(f'decoder has {len(decoder._letters)} letters (blank included), the net emits '
                              f'{self.num_classes} classes')
-        torch = self.model.torch
         pad, sub, height = self.line_padding_px, self.net_subsampling, self.line_px_height
         budget = self.max_input_horizontal_pixels
         widths = [l.shape[1] for l in lines]
         bags = [None] * len(lines)
+
+        def finish(chunk, res):
+            for slot, bag in enumerate(decoder.bags_from_host(res['beam_labels'], res['beam_lengths'], res['beam_scores'],
+                                                              res['beam_status'])):
+                bags[chunk[slot]] = bag
+
+        depth = len(self._models)
+        nslots = 2 * depth
+        in_flight = []
         with self._device_ctx():
-            for chunk, widest in self._batches(widths):
+            for bi, (chunk, widest) in enumerate(self._batches(widths)):
                 width = min(widest + 2 * pad, budget)
-                batch = np.zeros((len(chunk), height, width, 3), dtype=np.uint8)
-                for slot, idx in enumerate(chunk):
-                    line = lines[idx]
-                    if line.shape[0] != height or line.ndim != 3 or line.shape[2] != 3:
-                        raise ValueError(f'line crops must be [{height}, w, 3] uint8, got {line.shape}')
-                    end = min(width, pad + line.shape[1])
-                    if end > pad:
-                        batch[slot, :, pad:end] = line[:, :end - pad]
-                dev = torch.from_numpy(batch).to(self.device)
-                self.h2d_bytes += batch.nbytes
-                out = self.model.forward(dev, want_logits=True)
-                lp = full_logprobs_device(out['logits'])
-                lo = torch.full((len(chunk),), pad // sub, dtype=torch.int32, device=self.device)
-                hi = torch.tensor([(pad + widths[i]) // sub for i in chunk], dtype=torch.int32, device=self.device)
-                res = prefix_beam_device_ranges(lp, decoder._k, lo, hi)
-                for slot, bag in enumerate(decoder.bags_from_device(*res)):
-                    bags[chunk[slot]] = bag
+                lo = [pad // sub] * len(chunk)
+                hi = [(pad + widths[i]) // sub for i in chunk]
+                ticket = self._submit(bi % nslots, (len(chunk), height, width, 3), None, True,
+                                      packed=[lines[i] for i in chunk], beam=(decoder._k, lo, hi))
+                in_flight.append((chunk, ticket))
+                if len(in_flight) > depth:
+                    done_chunk, done_ticket = in_flight.pop(0)
+                    finish(done_chunk, self._collect(done_ticket))
+            for done_chunk, done_ticket in in_flight:
+                finish(done_chunk, self._collect(done_ticket))
         return bags
 
     def process_line_maps(self, page, maps, sparse_logits=True, tight_crop_logits=False, no_logits=False,

@@ -26,7 +26,11 @@ if os.environ.get('B200OCR_AUTOTUNE_BUDGET'):
 crops = torch.zeros((batch, 40, 1344, 3), dtype=torch.uint8, device='cuda')
 crops[:, :, 32:-32] = torch.from_numpy(synthetic.bench_crops(batch, 1280, seed=0)).cuda()
 out = {}
-for _ in range(steps):
+for _ in range(max(0, steps - 1)):
     rec.forward(crops, want_logits=False, out=out)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly the last step
+rec.forward(crops, want_logits=False, out=out)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print('done', rec.launch_count)
