@@ -655,19 +655,18 @@ def main():
         if not same:
             raise SystemExit('bench: ranks disagree on the label ids of the same batch')
 
-    # ---- end to end through process_lines, then the gather of label ids.  BASELINE config 5 at 8 GPUs: 100k lines.
-    total_lines = max(world * BATCH * args.steps, 100000 if world == 8 else 0)
-    per_rank = (total_lines + world * BATCH - 1) // (world * BATCH) * BATCH
-    e2e_lines = [host_lines[i % (BATCH * n_rot)] for i in range(per_rank)]
-    e2e_steps = per_rank // BATCH
-
-    def e2e_leg(**kw):
-        engine.process_lines(e2e_lines[:BATCH * 2], **kw)                   # warm-up: pinned buffers, slots
+    # ---- end to end through process_lines, then the gather of the transcripts.  The default call (strings + sparse
+    # logits, page_parser.py:423) runs over steps x 256 lines per rank; the strings-only call also carries BASELINE
+    # config 5 at 8 GPUs: 100k lines sharded over the ranks, NCCL gather of the transcripts.
+    def e2e_leg(n_lines, **kw):
+        lines_ = [host_lines[i % (BATCH * n_rot)] for i in range(n_lines)]
+        steps_ = max(1, n_lines // BATCH)
+        engine.process_lines(lines_[:BATCH * 2 * len(recs)], **kw)        # warm-up: pinned buffers of every slot
         engine.h2d_bytes = engine.d2h_bytes = 0
         engine.host_ms = {k: 0.0 for k in engine.host_ms}
         barrier()
         t0 = time.perf_counter()
-        tr, lg, _ = engine.process_lines(e2e_lines, **kw)
+        tr, lg, _ = engine.process_lines(lines_, **kw)
         gathered = 0
         if world > 1:
             ids = [np.frombuffer(t.encode('utf-32-le'), dtype=np.uint32).astype(np.int32) for t in tr]   # code points
@@ -676,23 +675,32 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         kept = float(np.mean([m.nnz / max(1, m.shape[0]) for m in lg[:8]])) if lg and lg[0] is not None else None
         del lg
-        return {'value': world * len(e2e_lines) / dt, 'unit': UNIT, 'h2d_bytes_per_step': engine.h2d_bytes // e2e_steps,
-                'd2h_bytes_per_step': engine.d2h_bytes // e2e_steps, 'gather_bytes_total': gathered,
-                'host_ms_per_step_rank0': {k: v / e2e_steps for k, v in engine.host_ms.items()},
+        return {'value': world * n_lines / dt, 'unit': UNIT, 'h2d_bytes_per_step': engine.h2d_bytes // steps_,
+                'd2h_bytes_per_step': engine.d2h_bytes // steps_, 'gather_bytes_total': gathered,
+                'lines_total': world * n_lines, 'seconds': dt,
+                'host_ms_per_step_rank0': {k: v / steps_ for k, v in engine.host_ms.items()},
                 'logit_entries_kept_per_frame': kept}
 
-    e2e = e2e_leg()                                                         # the reference caller's call: defaults
+    e2e = e2e_leg(BATCH * args.steps)                                       # the reference caller's call: defaults
     e2e['api'] = 'B200EngineLineOCR.process_lines(lines)  [strings + sparse logits + logit_coords, page_parser.py:423]'
-    e2e['lines_total'] = world * len(e2e_lines)
     e2e['host_threads'] = engine.host_threads
     if e2e.get('logit_entries_kept_per_frame') and e2e['logit_entries_kept_per_frame'] > 60:
         e2e['note'] = ('the random-init bench net keeps every class of every frame (p ~ 1/120 > 1e-4): the degenerate '
-                       'worst case of the sparse path (a trained recogniser keeps a handful of classes per frame)')
-    no_lg = e2e_leg(no_logits=True)
-    e2e['no_logits'] = {k: no_lg[k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'host_ms_per_step_rank0')}
+                       'worst case of the sparse path, bound by 83 MB of fresh host memory per 256-line step (a trained '
+                       'recogniser keeps a handful of classes per frame)')
+    total_lines = max(world * BATCH * args.steps, 100000 if world == 8 else 0)
+    per_rank = (total_lines + world * BATCH - 1) // (world * BATCH) * BATCH
+    no_lg = e2e_leg(per_rank, no_logits=True)
+    e2e['no_logits'] = {k: no_lg[k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'gather_bytes_total',
+                                              'lines_total', 'seconds', 'host_ms_per_step_rank0')}
     e2e['no_logits']['api'] = 'B200EngineLineOCR.process_lines(lines, no_logits=True)  [strings only]'
     if parity:
         e2e['multi_gpu_parity'] = parity
+    config5 = None
+    if world == 8:
+        config5 = {'workload': f'config5: {no_lg["lines_total"]} synthetic 40x1280 line crops sharded batch-parallel across 8 GPUs, '
+                               f'NCCL gather of the transcripts', 'value': no_lg['value'], 'unit': UNIT,
+                   'seconds': no_lg['seconds'], 'gather_bytes_total': no_lg['gather_bytes_total']}
 
     # ---- roofline leg: per-launch CUDA-event timing of the same step (separate from the timed region)
     rec.profile(True)
@@ -787,6 +795,8 @@ def main():
     }
     if variants:
         line['precision_variants'] = variants
+    if config5:
+        line['config5'] = config5
     if rank == 0:
         line['ctc_decode'] = ctc_decode_times(dev, with_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

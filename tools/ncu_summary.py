@@ -70,15 +70,20 @@ def main():
         k['launches'] += 1
         k['ms'] += r['ms'] or 0
         k['traffic_bytes'] += r.get('traffic_bytes') or 0
-        k['tensor_ms'] += (r['ms'] or 0) * (r['tensor_pct_rt'] or r['tensor_pct'] or 0) / 100.0
+        k['tensor_ms'] += (r['ms'] or 0) * (r['tensor_pct'] if r['tensor_pct'] is not None else (r['tensor_pct_rt'] or 0)) / 100.0
     for k in by_kernel.values():
         k['share'] = k['ms'] / total if total else None
         k['traffic_bytes_per_launch'] = k['traffic_bytes'] / k['launches']
         k['tensor_pipe_pct_time_weighted'] = 100.0 * k['tensor_ms'] / k['ms'] if k['ms'] else None
         del k['tensor_ms']
-    json.dump({'source': src, 'total_ms': total, 'by_kernel': by_kernel, 'launches': out}, open(dst + '.json', 'w'), indent=1)
+    weighted = sum((r['ms'] or 0) * (r['tensor_pct'] or 0) for r in out) / total if total else None
+    json.dump({'source': src, 'total_ms': total, 'tensor_pipe_pct_time_weighted_whole_step': weighted, 'by_kernel': by_kernel,
+               'launches': out}, open(dst + '.json', 'w'), indent=1)
     with open(dst + '.md', 'w') as f:
         f.write(f'ncu --set full --clock-control none, one device-resident step ({src}); total {total:.2f} ms under ncu\n\n')
+        f.write('tensor pipe % = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active (= hmma sub-pipe cycles / 4 / active cycles; '
+                'the `_realtime` variant of the metric, which round 1 tabulated, disagrees with it by up to 4x between launches of '
+                'identical work and is not used)\n\n')
         f.write('| # | kernel | grid | regs | ms | share | DRAM rd MB | DRAM wr MB | DRAM GB/s | tensor pipe % | SM % | L2 % |\n')
         f.write('|---|---|---|---|---|---|---|---|---|---|---|---|\n')
         for i, r in enumerate(out):
@@ -86,12 +91,14 @@ def main():
                 return '-' if v is None else f'{v:.{p}f}'
             f.write(f"| {i} | {r['name']} | {fm(r['grid'], 0)} | {fm(r['regs'], 0)} | {fm(r['ms'], 3)} | "
                     f"{fm(100 * (r['ms'] or 0) / total)}% | {fm((r['dram_rd'] or 0) / 1e6)} | {fm((r['dram_wr'] or 0) / 1e6)} | "
-                    f"{fm(r.get('dram_gbs'), 0)} | {fm(r['tensor_pct_rt'] if r['tensor_pct_rt'] is not None else r['tensor_pct'])} | "
+                    f"{fm(r.get('dram_gbs'), 0)} | {fm(r['tensor_pct'] if r['tensor_pct'] is not None else r['tensor_pct_rt'])} | "
                     f"{fm(r['sm_pct'])} | {fm(r['l2_pct'])} |\n")
         f.write('\n| kernel | launches | ms | share | traffic/launch MB | tensor pipe % (time-weighted) |\n|---|---|---|---|---|---|\n')
         for n, k in by_kernel.items():
             f.write(f"| {n} | {k['launches']} | {k['ms']:.3f} | {100 * k['share']:.1f}% | {k['traffic_bytes_per_launch'] / 1e6:.1f} | "
                     f"{k['tensor_pipe_pct_time_weighted']:.1f} |\n")
+    with open(dst + '.md', 'a') as f:
+        f.write(f'\nTensor pipe, time-weighted over the whole step: {weighted:.1f} %\n')
     print(open(dst + '.md').read())
 
 
