@@ -277,11 +277,18 @@ class B200EngineLineOCR:
         # it, none when several ranks share the host (torchrun exports LOCAL_WORLD_SIZE)
         import os
         ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+        total = os.cpu_count() or 2
         try:
-            cores = len(os.sched_getaffinity(0))
+            mine = len(os.sched_getaffinity(0))
         except (AttributeError, OSError):
-            cores = os.cpu_count() or 2
-        self.host_threads = max(1, min(4, cores // ranks if ranks > 1 else cores // 4))
+            mine = total
+        if mine < total:                 # the launcher pinned this process: those cores are ours
+            cores = mine
+        elif ranks > 1:                  # several ranks share the host unpinned: an equal share
+            cores = total // ranks
+        else:                            # the only process: leave most cores to the caller
+            cores = total // 4
+        self.host_threads = max(1, min(4, cores))
         self.host_ms = {'stage': 0.0, 'wait': 0.0, 'finish': 0.0}      # where process_lines spends host time
         self._executor = None
         self.want_confidence = False
