@@ -342,7 +342,9 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
  * instead of making a 3.5 GB round trip through HBM); 0 = whole batch at once (default: on B200 the ~130 extra launches
  * of 4-line chunks cost more than the HBM round trip, profiles/r02e_l2_chunking.md);
  * flag 7: the persistent tensor-core kernels draw their tiles from a global counter (default on) instead of a fixed
- * 1/grid share per CTA -- what lets two engines on two streams share the GPU without serialising. */
+ * 1/grid share per CTA -- what lets two engines on two streams share the GPU without serialising;
+ * flag 8: tcgen05 self-attention of the Transformer variant (64-wide heads, lines of up to 384 frames; default on),
+ * 0 = the fp32 CUDA-core attention kernels for every shape. */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

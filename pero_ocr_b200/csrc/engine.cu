@@ -111,6 +111,7 @@ struct b200ocr_engine {
     bool dynamic_tiles = true;   // persistent GEMM kernels draw tiles from a global counter (tilesched.cuh; flag 7)
     int* tile_counters = nullptr;   // [kTileCounters] zeroed at the start of every layer walk
     int tile_counter_next = 0;
+    bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
     int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
     std::vector<LayerRT> layers;
@@ -575,7 +576,13 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     EpiOut eo;
                     eo.epi = EPI_F32; eo.out_f32 = qkv;
                     if (int s = run_gemm(e, ly.g_in, xh, rows, 0, 1, 1, eo, st, nullptr)) return s;
-                    { ProfScope ps(e, st, PROF_OTHER); CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->fmt, st)); }
+                    {
+                        ProfScope ps(e, st, PROF_OTHER);
+                        if (!e->use_ref && e->attention_tc && attention_tc_supported(T, D, ly.heads))
+                            CU_TRY(e, launch_attention_tc(qkv, cur.n, T, D, ly.heads, ah, e->fmt, st));
+                        else
+                            CU_TRY(e, launch_attention(qkv, cur.n, T, D, ly.heads, ah, e->fmt, st));
+                    }
                     e->launches++;
                     EpiOut er;
                     er.epi = EPI_RES_F32; er.out_f32 = tmp; er.residual = x;
@@ -1352,6 +1359,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     else if (flag == 5) e->ref_only_layer = value;
     else if (flag == 6) e->l2_chunk_lines = value < 0 ? 0 : value;
     else if (flag == 7) e->dynamic_tiles = value != 0;
+    else if (flag == 8) e->attention_tc = value != 0;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

@@ -105,3 +105,8 @@ cudaError_t launch_h2f(const __half* in, int rows, int d, int fmt, float* out, c
 // nn.TransformerEncoderLayer, transformer.py:371-373).
 cudaError_t launch_attention(const float* qkv, int n, int T, int D, int heads, __half* out, int fmt,
                              cudaStream_t stream);
+// The same on tcgen05 for 64-wide heads and lines of up to 384 frames (attention_tc.cu): S = Q K^T and O = P V with
+// hi / lo operand splits, P kept in tensor memory between the two products.
+bool attention_tc_supported(int T, int D, int heads);
+cudaError_t launch_attention_tc(const float* qkv, int n, int T, int D, int heads, __half* out, int fmt,
+                                cudaStream_t stream);
