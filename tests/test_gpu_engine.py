@@ -409,3 +409,29 @@ def test_checkpoint_class_convention(tmp_path, golden_dir):
     assert [b.best_hyp() for b in bags] == [str(x) for x in gold['decoder_beam4']]
     with pytest.raises(ValueError):
         eng.decode_lines(lines, CTCPrefixLogRawNumpyDecoder(letters[:-2] + [BLANK_SYMBOL], 4))
+
+
+@pytest.mark.parametrize('precision', ['fp16f8', 'fp16x3'])
+@pytest.mark.parametrize('width', [40, 264, 1344, 1536])
+def test_tensor_core_attention_matches_cuda_core_attention(width, precision):
+    """attention_tc.cu (tcgen05: S = Q K^T and O = P V with hi / lo operand splits, P kept in tensor memory) against the
+    fp32 CUDA-core attention kernel on the same QKV rows (debug flag 8), for T = 10, 66 (one partial query tile),
+    336 (BASELINE config 3: three query tiles, 96-key last chunk) and 384 (the kernel's limit), and against the
+    torch-CPU fp32 module."""
+    eng, _ = _case_recognizer('transformer', precision)
+    rng = np.random.default_rng(width)
+    n = 3 if width < 1000 else 2
+    crops = np.repeat(rng.integers(0, 256, (n, 40, width, 1), dtype=np.uint8), 3, axis=3)
+    crops[-1, :, width // 2:] = 0                          # a line that ends half way: trailing padding frames
+    d = torch.from_numpy(crops).cuda()
+    a = eng.forward(d, want_logits=True, out={})['logits'].clone()
+    eng.set_flag(8, 0)
+    b = eng.forward(d, want_logits=True, out={})['logits'].clone()
+    torch.cuda.synchronize()
+    diff = (a - b).abs().max().item()
+    print(f'T = {width // 4}: tcgen05 vs CUDA-core attention, max |d logit| = {diff:.2e}')
+    assert diff <= 2e-4
+    net = make_case_net('transformer')
+    with torch.no_grad():
+        ref = net(torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)).permute(0, 2, 1).numpy()
+    assert np.abs(a.cpu().numpy() - ref).max() <= TOL
