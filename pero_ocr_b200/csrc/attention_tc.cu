@@ -124,9 +124,9 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
     const uint64_t desc_hi = ptx::smem_desc_sw128(0);
     uint32_t ph_s = 0, ph_o = 0;
 
-    for (int q0 = 0; q0 < T; q0 += kQTile) {
-        // ---- Q tile (scaled by 1/sqrt(64) = 1/8: exact), hi | lo
-        for (int i = tid; i < kQTile * 8; i += kThreads) {
+    // Q tile (scaled by 1/sqrt(64) = 1/8: exact), hi | lo, staged by the threads [t0, t0 + nt) of the CTA
+    auto stage_q = [&](int q0, int t0, int nt) {
+        for (int i = tid - t0; i < kQTile * 8; i += nt) {
             const int r = i >> 3, c = i & 7;
             uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
             if (q0 + r < T) {
@@ -137,8 +137,11 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
             *reinterpret_cast<uint4*>(sQ + kQBytes + sw128(r, c)) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // st.shared -> tensor-core (async proxy) reads
-        __syncthreads();
+    };
+    stage_q(0, 0, kThreads);
+    __syncthreads();
 
+    for (int q0 = 0; q0 < T; q0 += kQTile) {
         // ---- S = Q K^T into TMEM columns [0, Tp): chunks of <= 128 keys, three operand-split passes each
         if (warp == 4) {
             if (ptx::elect_one()) {
@@ -159,6 +162,11 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
                 ptx::mma_commit(&bars[0]);
             }
             __syncwarp();
+        }
+        if (warp > 4 && q0 + kQTile < T) {
+            // the Q tile is dead once S is complete: warps 5-7 stage the next one while warps 0-3 run the softmax
+            ptx::mbar_wait(&bars[0], ph_s);
+            stage_q(q0 + kQTile, 5 * 32, kThreads - 5 * 32);
         }
         float inv_sum = 0.f;
         if (warp < 4) {
@@ -182,8 +190,8 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const float p0 = c0 + j < T ? expf(__uint_as_float(r[j]) - mx) : 0.f;
-                    const float p1 = c0 + j + 1 < T ? expf(__uint_as_float(r[j + 1]) - mx) : 0.f;
+                    const float p0 = c0 + j < T ? __expf(__uint_as_float(r[j]) - mx) : 0.f;
+                    const float p1 = c0 + j + 1 < T ? __expf(__uint_as_float(r[j + 1]) - mx) : 0.f;
                     sum += p0 + p1;
                     const __half2 h2 = __floats2half2_rn(p0, p1);
                     const float2 f = __half22float2(h2);
@@ -276,7 +284,7 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
         }
         ph_s ^= 1;
         ph_o ^= 1;
-        __syncthreads();   // O and the Q tile are free for the next tile
+        __syncthreads();   // O is free, the next Q tile is in place
     }
 
     ptx::tc_fence_before();

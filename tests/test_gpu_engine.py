@@ -430,7 +430,9 @@ def test_tensor_core_attention_matches_cuda_core_attention(width, precision):
     torch.cuda.synchronize()
     diff = (a - b).abs().max().item()
     print(f'T = {width // 4}: tcgen05 vs CUDA-core attention, max |d logit| = {diff:.2e}')
-    assert diff <= 2e-4
+    # fp16x3 records resolve 2^-22 of a value; an fp16f8 record's e5m2 residual 2^-14 -- two fp32 results a rounding
+    # apart may land one such step apart, which the layers downstream turn into a few 1e-4 at |logit| <= 8.8
+    assert diff <= (1e-4 if precision == 'fp16x3' else 6e-4)
     net = make_case_net('transformer')
     with torch.no_grad():
         ref = net(torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)).permute(0, 2, 1).numpy()
