@@ -34,7 +34,7 @@ constexpr int kKBytes = kMaxKeys * 128;          // one plane of K
 constexpr int kVChunk = kDh * 128;               // one plane of one 64-key chunk of V^T
 constexpr int kVBytes = (kMaxKeys / 64) * kVChunk;
 constexpr int kOCol = 448;                       // TMEM columns [448, 512): O accumulator
-constexpr int kSmemBytes = 2 * kQBytes + 2 * kKBytes + 2 * kVBytes + 64 + 1024;
+constexpr int kSmemBytes = 2 * kQBytes + 2 * kKBytes + 2 * kVBytes + 32 + 2 * kQTile * 4 + 1024;
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile (rows of 128 B, 8-row groups)
 __device__ __forceinline__ uint32_t sw128(int r, int c) {
@@ -66,6 +66,7 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
     uint8_t* sV = sK + 2 * kKBytes;           // [plane][6 chunks][64 rows x 128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kVBytes);   // [0] S done, [1] O done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    float* s_red = reinterpret_cast<float*>(bars + 4);   // [side 0 | side 1][128 rows]: partial row maxima, then sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int line = blockIdx.x / heads, head = blockIdx.x - line * heads;
@@ -163,49 +164,61 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
             }
             __syncwarp();
         }
-        if (warp > 4 && q0 + kQTile < T) {
-            // the Q tile is dead once S is complete: warps 5-7 stage the next one while warps 0-3 run the softmax
-            ptx::mbar_wait(&bars[0], ph_s);
-            stage_q(q0 + kQTile, 5 * 32, kThreads - 5 * 32);
-        }
-        float inv_sum = 0.f;
-        if (warp < 4) {
-            // ---- softmax of this thread's query row (TMEM lane 32 * warp + lane), P written back in place
-            ptx::mbar_wait(&bars[0], ph_s);
-            ptx::tc_fence_after();
-            const uint32_t row_addr = static_cast<uint32_t>(warp * 32) << 16;
-            float mx = -INFINITY;
-            for (int c0 = 0; c0 < Tp; c0 += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(row_addr + c0, r);
-                ptx::tmem_ld_wait();
+        // ---- softmax: all 8 warps.  Warps w and w + 4 share TMEM lane quarter w (one query row per lane) and split
+        // the row's 32-column chunks between them (even / odd); row maximum and row sum meet in shared memory.  P is
+        // written back in place: the 32 fp32 columns of a chunk become 16 columns of P_hi pairs + 16 of P_lo pairs.
+        const int lq = warp & 3, side = warp >> 2;
+        const int rowi = lq * 32 + lane;
+        const uint32_t row_addr = static_cast<uint32_t>(lq * 32) << 16;
+        ptx::mbar_wait(&bars[0], ph_s);
+        ptx::tc_fence_after();
+        float mx = -INFINITY;
+        for (int c0 = side * 32; c0 < Tp; c0 += 64) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(row_addr + c0, r);
+            ptx::tmem_ld_wait();
+            if (c0 + 32 <= T) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+            } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
             }
-            float sum = 0.f;
-            for (int c0 = 0; c0 < Tp; c0 += 32) {
-                uint32_t r[32], w[32];
-                ptx::tmem_ld_32x32b_x32(row_addr + c0, r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = c0 + j < T ? __expf(__uint_as_float(r[j]) - mx) : 0.f;
-                    const float p1 = c0 + j + 1 < T ? __expf(__uint_as_float(r[j + 1]) - mx) : 0.f;
-                    sum += p0 + p1;
-                    const __half2 h2 = __floats2half2_rn(p0, p1);
-                    const float2 f = __half22float2(h2);
-                    const __half2 l2 = __floats2half2_rn(p0 - f.x, p1 - f.y);
-                    w[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);          // columns c0 .. c0+15: P_hi pairs
-                    w[16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l2);   // columns c0+16 .. c0+31: P_lo pairs
-                }
-                ptx::tmem_st_32x32b_x32(row_addr + c0, w);
-            }
-            ptx::tmem_st_wait();
-            inv_sum = 1.f / sum;
-            ptx::tc_fence_before();
         }
+        s_red[side * kQTile + rowi] = mx;
         __syncthreads();
+        mx = fmaxf(s_red[rowi], s_red[kQTile + rowi]);
+        __syncthreads();                 // the two slots per row are reused for the row sums below
+        float sum = 0.f;
+        for (int c0 = side * 32; c0 < Tp; c0 += 64) {
+            uint32_t r[32], w[32];
+            ptx::tmem_ld_32x32b_x32(row_addr + c0, r);
+            ptx::tmem_ld_wait();
+            const bool full = c0 + 32 <= T;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float p0 = __expf(__uint_as_float(r[j]) - mx), p1 = __expf(__uint_as_float(r[j + 1]) - mx);
+                if (!full) {
+                    if (c0 + j >= T) p0 = 0.f;
+                    if (c0 + j + 1 >= T) p1 = 0.f;
+                }
+                sum += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                const float2 f = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(p0 - f.x, p1 - f.y);
+                w[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);          // columns c0 .. c0+15: P_hi pairs
+                w[16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l2);   // columns c0+16 .. c0+31: P_lo pairs
+            }
+            ptx::tmem_st_32x32b_x32(row_addr + c0, w);
+        }
+        ptx::tmem_st_wait();
+        s_red[side * kQTile + rowi] = sum;
+        // the Q tile is dead once S is complete: everybody stages the next one before the barrier that releases P
+        if (q0 + kQTile < T) stage_q(q0 + kQTile, 0, kThreads);
+        ptx::tc_fence_before();
+        __syncthreads();
+        const float inv_sum = 1.f / (s_red[rowi] + s_red[kQTile + rowi]);
 
         // ---- O = P V: A = P from TMEM (8 packed columns per K = 16 keys), B = V^T chunk rows from shared memory
         if (warp == 4) {
@@ -227,7 +240,7 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
             __syncwarp();
         }
         if (warp < 4) {
-            // ---- O / sum -> the head's 64 channels of the activation record of this query
+            // ---- O / sum -> the head's 64 channels of the activation record of this query (warps 0-3: lane quarter = warp)
             ptx::mbar_wait(&bars[1], ph_o);
             ptx::tc_fence_after();
             const int tq = q0 + warp * 32 + lane;

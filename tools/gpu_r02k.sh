@@ -4,7 +4,7 @@ out=gpurun_out; tag=${1:-r02k}
 mkdir -p $out
 python -m pytest tests/test_gpu_engine.py -m gpu -q -s -k "attention" > $out/${tag}_pytest_attention.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_attention.log
 grep -E "passed|failed|FAILED|T = " $out/${tag}_pytest_attention.log | tail -14
-python - <<'PY' > gpurun_out/r02k_attention_ab.json
+python - <<'PY' > $out/${tag}_attention_ab.json
 import json, os, sys, torch
 sys.path.insert(0, os.getcwd())
 from pero_ocr_b200 import netdesc, synthetic
