@@ -81,38 +81,67 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
     }
     if (warp == 4) ptx::tmem_alloc<512>(tmem_slot);
 
+    // Staging is bound by global-load latency, not bandwidth (ncu: half of all stall samples sat behind the two loads of
+    // a piece when every piece was loaded, converted and stored in turn): the loads of kBatch pieces are issued
+    // together, then converted.
+    constexpr int kBatch = 4;
     // ---- K: [key][64] hi | lo.  A piece = (key, 8 channels): 8 lanes read one 256-byte row, a warp 4 rows
-    for (int i = tid; i < Tp * 8; i += kThreads) {
-        const int r = i >> 3, c = i & 7;
-        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-        if (r < T) {
-            const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * 3 * D + D + c * 8);
-            split8(__ldg(src), __ldg(src + 1), 1.f, hi, lo);
+    for (int i0 = tid; i0 < Tp * 8; i0 += kBatch * kThreads) {
+        float4 a[kBatch], b[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int i = i0 + k * kThreads, r = i >> 3, c = i & 7;
+            a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < T) {
+                const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * 3 * D + D + c * 8);
+                a[k] = __ldg(src);
+                b[k] = __ldg(src + 1);
+            }
         }
-        *reinterpret_cast<uint4*>(sK + sw128(r, c)) = hi;
-        *reinterpret_cast<uint4*>(sK + kKBytes + sw128(r, c)) = lo;
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int i = i0 + k * kThreads, r = i >> 3, c = i & 7;
+            if (i < Tp * 8) {
+                uint4 hi, lo;
+                split8(a[k], b[k], 1.f, hi, lo);
+                *reinterpret_cast<uint4*>(sK + sw128(r, c)) = hi;
+                *reinterpret_cast<uint4*>(sK + kKBytes + sw128(r, c)) = lo;
+            }
+        }
     }
     // ---- V^T: [d][key] hi | lo in chunks of 64 keys.  A piece = (key, 8 channels) again, written as 8 two-byte
     // elements down a column; the 32 lanes of a warp take 32 consecutive keys of the same channel group, so one store
     // instruction fills 64 contiguous (swizzled) bytes of a row
-    for (int i = tid; i < Tp * 8; i += kThreads) {
-        const int key = (i & 31) + ((i >> 8) << 5), c = (i >> 5) & 7;     // i = (key / 32) * 256 + c * 32 + key % 32
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (key < T) {
-            const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(key) * 3 * D + 2 * D + c * 8);
-            const float4 a = __ldg(src), b = __ldg(src + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
-        uint8_t* chunk = sV + (key >> 6) * kVChunk;
-        const int kk = key & 63;
+    for (int i0 = tid; i0 < Tp * 8; i0 += kBatch * kThreads) {
+        float4 a[kBatch], b[kBatch];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int d = c * 8 + e;
-            const __half hi = __float2half_rn(v[e]);
-            const __half lo = __float2half_rn(v[e] - __half2float(hi));
-            const uint32_t off = sw128(d, kk >> 3) + (kk & 7) * 2;
-            *reinterpret_cast<__half*>(chunk + off) = hi;
-            *reinterpret_cast<__half*>(chunk + kVBytes + off) = lo;
+        for (int k = 0; k < kBatch; ++k) {
+            const int i = i0 + k * kThreads;
+            const int key = (i & 31) + ((i >> 8) << 5), c = (i >> 5) & 7;   // i = (key / 32) * 256 + c * 32 + key % 32
+            a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (key < T) {
+                const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(key) * 3 * D + 2 * D + c * 8);
+                a[k] = __ldg(src);
+                b[k] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int i = i0 + k * kThreads;
+            if (i >= Tp * 8) break;
+            const int key = (i & 31) + ((i >> 8) << 5), c = (i >> 5) & 7;
+            const float v[8] = {a[k].x, a[k].y, a[k].z, a[k].w, b[k].x, b[k].y, b[k].z, b[k].w};
+            uint8_t* chunk = sV + (key >> 6) * kVChunk;
+            const int kk = key & 63;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int d = c * 8 + e;
+                const __half hi = __float2half_rn(v[e]);
+                const __half lo = __float2half_rn(v[e] - __half2float(hi));
+                const uint32_t off = sw128(d, kk >> 3) + (kk & 7) * 2;
+                *reinterpret_cast<__half*>(chunk + off) = hi;
+                *reinterpret_cast<__half*>(chunk + kVBytes + off) = lo;
+            }
         }
     }
     ptx::tc_fence_before();
@@ -127,15 +156,28 @@ attention_tc_kernel(const float* __restrict__ qkv, int T, int D, int heads, __ha
 
     // Q tile (scaled by 1/sqrt(64) = 1/8: exact), hi | lo, staged by the threads [t0, t0 + nt) of the CTA
     auto stage_q = [&](int q0, int t0, int nt) {
-        for (int i = tid - t0; i < kQTile * 8; i += nt) {
-            const int r = i >> 3, c = i & 7;
-            uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-            if (q0 + r < T) {
-                const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(q0 + r) * 3 * D + c * 8);
-                split8(__ldg(src), __ldg(src + 1), 0.125f, hi, lo);
+        for (int i0 = tid - t0; i0 < kQTile * 8; i0 += kBatch * nt) {
+            float4 a[kBatch], b[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int i = i0 + k * nt, r = i >> 3, c = i & 7;
+                a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < kQTile * 8 && q0 + r < T) {
+                    const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(q0 + r) * 3 * D + c * 8);
+                    a[k] = __ldg(src);
+                    b[k] = __ldg(src + 1);
+                }
             }
-            *reinterpret_cast<uint4*>(sQ + sw128(r, c)) = hi;
-            *reinterpret_cast<uint4*>(sQ + kQBytes + sw128(r, c)) = lo;
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int i = i0 + k * nt, r = i >> 3, c = i & 7;
+                if (i < kQTile * 8) {
+                    uint4 hi, lo;
+                    split8(a[k], b[k], 0.125f, hi, lo);
+                    *reinterpret_cast<uint4*>(sQ + sw128(r, c)) = hi;
+                    *reinterpret_cast<uint4*>(sQ + kQBytes + sw128(r, c)) = lo;
+                }
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // st.shared -> tensor-core (async proxy) reads
     };
