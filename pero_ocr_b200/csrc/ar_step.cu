@@ -151,17 +151,30 @@ __device__ __forceinline__ void group_barrier(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(64) : "memory");
 }
 
+//
+// Two extensions for the token loop (launch_linear_f32_ex):
+//   * split_o / out2: output columns >= split_o go to out2 (rows ldo2 apart) -- the self-attention in-projection
+//     writes q into the step buffer and k | v straight into the cache slot of the position with ONE launch;
+//   * gridDim.z = Z > 1: CTA z contracts the z-th share of the K chunks and stores its raw partial tile at
+//     out + z * part_stride (no bias / activation / residual): the chain of dependent chunk round trips shrinks by Z
+//     and the Z partials are summed, in fixed order, by the kernel that consumes them (sum_layernorm_kernel).
 __global__ void __launch_bounds__(64 * LKG) linear_f32_splitk_kernel(const float* __restrict__ x, long ldx,
                                                                      const float* __restrict__ w,
                                                                      const float* __restrict__ bias,
                                                                      const float* __restrict__ res, long ldr,
                                                                      float* __restrict__ out, long ldo, int M, int O,
-                                                                     int K, int relu) {
+                                                                     int K, int relu, int split_o,
+                                                                     float* __restrict__ out2, long ldo2,
+                                                                     long part_stride) {
     __shared__ float xs[LKG][LBK][LLD];   // [group][k][m]; afterwards [group][m][o] partial sums
     __shared__ float ws[LKG][LBK][LLD];   // [group][k][o]
     const int m0 = blockIdx.y * LBM, o0 = blockIdx.x * LBN;
     const int g = threadIdx.x >> 6, t = threadIdx.x & 63, tm = t >> 3, tn = t & 7;
-    const int chunks = K / LBK;
+    const int all_chunks = K / LBK;
+    const int Z = gridDim.z, z = blockIdx.z;
+    const int c_lo = static_cast<int>(static_cast<long>(all_chunks) * z / Z);
+    const int chunks = static_cast<int>(static_cast<long>(all_chunks) * (z + 1) / Z);
+    if (Z > 1) { out += z * part_stride; bias = nullptr; res = nullptr; relu = 0; }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(64 * LKG) linear_f32_splitk_kernel(const float
             if (o0 + r < O) wv[i] = *reinterpret_cast<const float4*>(w + static_cast<size_t>(o0 + r) * K + c * LBK + k4);
         }
     };
-    int c = g;
+    int c = c_lo + g;
     if (c < chunks) fetch(c);
     for (; c < chunks; c += LKG) {
 #pragma unroll
@@ -226,8 +239,162 @@ __global__ void __launch_bounds__(64 * LKG) linear_f32_splitk_kernel(const float
             v += bias ? bias[o] : 0.f;
             if (relu) v = fmaxf(v, 0.f);
             if (res) v += res[static_cast<long>(m) * ldr + o];
-            out[static_cast<long>(m) * ldo + o] = v;
+            if (o < split_o) out[static_cast<long>(m) * ldo + o] = v;
+            else out2[static_cast<long>(m) * ldo2 + (o - split_o)] = v;
         }
+    }
+}
+
+// LayerNorm over rows of x = sum_z part[z] + bias + res (the out-projection / feed-forward partials of the split-K
+// kernel above, DecoderLayer.infer's  norm(x + sublayer(x)), transformer.py:435, 447, 450).  One warp per row, the row
+// in registers: lane l owns the float4s l + 32 j, j < NV (d = 128 NV).
+template <int NV>
+__global__ void __launch_bounds__(128) sum_layernorm_kernel(const float* __restrict__ part, int Z, long part_stride,
+                                                            const float* __restrict__ bias,
+                                                            const float* res, int rows,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            float* out) {             // out may be res (in place)
+    constexpr int D = 128 * NV;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i4 = lane + 32 * j;
+        v[j] = reinterpret_cast<const float4*>(part + static_cast<size_t>(row) * D)[i4];
+        for (int zz = 1; zz < Z; ++zz) {
+            const float4 u = reinterpret_cast<const float4*>(part + zz * part_stride + static_cast<size_t>(row) * D)[i4];
+            v[j].x += u.x; v[j].y += u.y; v[j].z += u.z; v[j].w += u.w;
+        }
+        const float4 b = reinterpret_cast<const float4*>(bias)[i4];
+        const float4 r = reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * D)[i4];
+        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;      // linear: acc + bias ...
+        v[j].x += r.x; v[j].y += r.y; v[j].z += r.z; v[j].w += r.w;      // ... then the residual, as the fused epilogue
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / D + eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i4 = lane + 32 * j;
+        const float4 g = reinterpret_cast<const float4*>(gamma)[i4], b = reinterpret_cast<const float4*>(beta)[i4];
+        float4 y;
+        y.x = (v[j].x - mean) * rstd * g.x + b.x;
+        y.y = (v[j].y - mean) * rstd * g.y + b.y;
+        y.z = (v[j].z - mean) * rstd * g.z + b.z;
+        y.w = (v[j].w - mean) * rstd * g.w + b.w;
+        reinterpret_cast<float4*>(out + static_cast<size_t>(row) * D)[i4] = y;
+    }
+}
+
+// One CTA (4 warps) per (line, head): the same arithmetic as step_attention_kernel with every global access
+// coalesced and the S positions spread over the CTA.  Scores: 8 lanes share one K row (HD / 8 consecutive floats
+// each), 4 rows per warp instruction, 16 per CTA pass, two passes in flight; values: HD / 4 lanes share one V row
+// (a float4 each), the 4 warps take interleaved rows and their partial sums meet in shared memory in fixed order.
+template <int HD>
+__global__ void __launch_bounds__(128) step_attention_cta_kernel(const float* __restrict__ q, long q_ls,
+                                                                 const float* __restrict__ k,
+                                                                 const float* __restrict__ v, long ps, long ls, int S,
+                                                                 int d, int heads, float* __restrict__ out) {
+    extern __shared__ float s_w[];                  // [S] scores / weights, [4][HD] partial outputs, [8] reductions
+    constexpr int SEG = HD / 8, LPR = HD / 4, RPW = 32 / LPR;
+    float* s_part = s_w + S;
+    float* s_red = s_part + 4 * HD;
+    const int line = blockIdx.x / heads, head = blockIdx.x - line * heads;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rg = lane >> 3, sg = lane & 7;
+    const float scale = powf(static_cast<float>(HD), -0.5f);
+    float qr[SEG];
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) qr[i] = q[line * q_ls + head * HD + sg * SEG + i] * scale;   // q scaled first (:268-271)
+    const float* kb = k + line * ls + head * HD + sg * SEG;
+    float mx = -INFINITY;
+    for (int p0 = warp * 4 + rg; p0 < S; p0 += 32) {
+        const int p1 = p0 + 16;
+        float4 ka[SEG / 4], kc[SEG / 4];
+#pragma unroll
+        for (int e = 0; e < SEG / 4; ++e) {
+            ka[e] = reinterpret_cast<const float4*>(kb + p0 * ps)[e];
+            kc[e] = p1 < S ? reinterpret_cast<const float4*>(kb + p1 * ps)[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < SEG / 4; ++e) {
+            s0 = fmaf(qr[4 * e], ka[e].x, s0); s0 = fmaf(qr[4 * e + 1], ka[e].y, s0);
+            s0 = fmaf(qr[4 * e + 2], ka[e].z, s0); s0 = fmaf(qr[4 * e + 3], ka[e].w, s0);
+            s1 = fmaf(qr[4 * e], kc[e].x, s1); s1 = fmaf(qr[4 * e + 1], kc[e].y, s1);
+            s1 = fmaf(qr[4 * e + 2], kc[e].z, s1); s1 = fmaf(qr[4 * e + 3], kc[e].w, s1);
+        }
+        // rows whose p0 is out of range leave the loop by themselves: the 8 lanes of a row always travel together
+        const unsigned grp = 0xffu << (lane & 24);
+#pragma unroll
+        for (int o = 4; o; o >>= 1) {
+            s0 += __shfl_xor_sync(grp, s0, o);
+            s1 += __shfl_xor_sync(grp, s1, o);
+        }
+        if (sg == 0) {
+            s_w[p0] = s0;
+            if (p1 < S) s_w[p1] = s1;
+        }
+        mx = fmaxf(mx, s0);
+        if (p1 < S) mx = fmaxf(mx, s1);
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    float sum = 0.f;
+    for (int p = threadIdx.x; p < S; p += 128) {
+        const float e = expf(s_w[p] - mx);
+        s_w[p] = e;
+        sum += e;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_red[4 + warp] = sum;
+    __syncthreads();
+    const float inv = 1.f / ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
+    const int vr = lane / LPR, vc = lane - vr * LPR;
+    const float* vb = v + line * ls + head * HD + vc * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = warp * RPW + vr;
+    for (; p + 12 * RPW < S; p += 16 * RPW) {          // four rows of this lane in flight
+        const float4 a0 = *reinterpret_cast<const float4*>(vb + p * ps);
+        const float4 a1 = *reinterpret_cast<const float4*>(vb + (p + 4 * RPW) * ps);
+        const float4 a2 = *reinterpret_cast<const float4*>(vb + (p + 8 * RPW) * ps);
+        const float4 a3 = *reinterpret_cast<const float4*>(vb + (p + 12 * RPW) * ps);
+        const float w0 = s_w[p], w1 = s_w[p + 4 * RPW], w2 = s_w[p + 8 * RPW], w3 = s_w[p + 12 * RPW];
+        acc.x = fmaf(w0, a0.x, acc.x); acc.y = fmaf(w0, a0.y, acc.y); acc.z = fmaf(w0, a0.z, acc.z); acc.w = fmaf(w0, a0.w, acc.w);
+        acc.x = fmaf(w1, a1.x, acc.x); acc.y = fmaf(w1, a1.y, acc.y); acc.z = fmaf(w1, a1.z, acc.z); acc.w = fmaf(w1, a1.w, acc.w);
+        acc.x = fmaf(w2, a2.x, acc.x); acc.y = fmaf(w2, a2.y, acc.y); acc.z = fmaf(w2, a2.z, acc.z); acc.w = fmaf(w2, a2.w, acc.w);
+        acc.x = fmaf(w3, a3.x, acc.x); acc.y = fmaf(w3, a3.y, acc.y); acc.z = fmaf(w3, a3.z, acc.z); acc.w = fmaf(w3, a3.w, acc.w);
+    }
+    for (; p < S; p += 4 * RPW) {
+        const float4 a0 = *reinterpret_cast<const float4*>(vb + p * ps);
+        const float w0 = s_w[p];
+        acc.x = fmaf(w0, a0.x, acc.x); acc.y = fmaf(w0, a0.y, acc.y); acc.z = fmaf(w0, a0.z, acc.z); acc.w = fmaf(w0, a0.w, acc.w);
+    }
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) {               // the RPW rows a warp walks side by side
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane < LPR) *reinterpret_cast<float4*>(s_part + warp * HD + lane * 4) = acc;
+    __syncthreads();
+    if (threadIdx.x < HD) {
+        const int e = threadIdx.x;
+        const float o = (s_part[e] + s_part[HD + e]) + (s_part[2 * HD + e] + s_part[3 * HD + e]);
+        out[static_cast<size_t>(line) * d + head * HD + e] = o * inv;
     }
 }
 
@@ -299,9 +466,40 @@ cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const fl
         return cudaErrorInvalidValue;
     const dim3 grid((O + LBN - 1) / LBN, (M + LBM - 1) / LBM);
     if (variant == 1)
-        linear_f32_splitk_kernel<<<grid, 64 * LKG, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
+        linear_f32_splitk_kernel<<<grid, 64 * LKG, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu, O,
+                                                                nullptr, 0, 0);
     else
         linear_f32_kernel<<<grid, 64, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_linear_f32_ex(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
+                                 float* out, long ldo, int M, int O, int K, int relu, int split_o, float* out2,
+                                 long ldo2, int ksplit, long part_stride, cudaStream_t stream) {
+    if (M <= 0 || O <= 0) return cudaSuccess;
+    if (K <= 0 || (K % LBK) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+        ksplit < 1 || ksplit > K / LBK || (split_o < O && !out2) || (ksplit > 1 && (split_o < O || part_stride < static_cast<long>(M) * ldo)))
+        return cudaErrorInvalidValue;
+    const dim3 grid((O + LBN - 1) / LBN, (M + LBM - 1) / LBM, ksplit);
+    linear_f32_splitk_kernel<<<grid, 64 * LKG, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu,
+                                                            std::min(split_o, O), out2, ldo2, part_stride);
+    return cudaGetLastError();
+}
+
+bool sum_layernorm_supported(int d) { return d == 128 || d == 256 || d == 512 || d == 1024; }
+
+cudaError_t launch_sum_layernorm(const float* part, int Z, long part_stride, const float* bias, const float* res,
+                                 int rows, int d, const float* gamma, const float* beta, float eps, float* out,
+                                 cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    if (!sum_layernorm_supported(d) || Z < 1 || !bias || !res) return cudaErrorInvalidValue;
+    const int grid = (rows + 3) / 4;
+    switch (d) {
+        case 128: sum_layernorm_kernel<1><<<grid, 128, 0, stream>>>(part, Z, part_stride, bias, res, rows, gamma, beta, eps, out); break;
+        case 256: sum_layernorm_kernel<2><<<grid, 128, 0, stream>>>(part, Z, part_stride, bias, res, rows, gamma, beta, eps, out); break;
+        case 512: sum_layernorm_kernel<4><<<grid, 128, 0, stream>>>(part, Z, part_stride, bias, res, rows, gamma, beta, eps, out); break;
+        default: sum_layernorm_kernel<8><<<grid, 128, 0, stream>>>(part, Z, part_stride, bias, res, rows, gamma, beta, eps, out); break;
+    }
     return cudaGetLastError();
 }
 
@@ -318,12 +516,19 @@ cudaError_t launch_ar_init(int32_t* alive, int n, int32_t* state, cudaStream_t s
 }
 
 cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
-                                  int S, int d, int heads, float* out, cudaStream_t stream) {
+                                  int S, int d, int heads, float* out, int variant, cudaStream_t stream) {
     if (n <= 0 || S <= 0) return cudaSuccess;
     const int hd = heads > 0 ? d / heads : 0;
     if (heads <= 0 || hd * heads != d || (hd % 4) || hd > 128 || (ps % 4) || (ls % 4) ||
-        (reinterpret_cast<uintptr_t>(k) & 15))
+        (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
         return cudaErrorInvalidValue;
+    if (variant == 1 && (hd == 32 || hd == 64 || hd == 128) && S <= 8192) {
+        const size_t sm = (static_cast<size_t>(S) + 4 * hd + 8) * sizeof(float);      // < 48 KB
+        if (hd == 32) step_attention_cta_kernel<32><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
+        else if (hd == 64) step_attention_cta_kernel<64><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
+        else step_attention_cta_kernel<128><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
+        return cudaGetLastError();
+    }
     const int warps = 4;
     const size_t smem = static_cast<size_t>(warps) * (S + 128) * sizeof(float);
     if (smem > 160 * 1024) return cudaErrorInvalidValue;

@@ -82,9 +82,14 @@ struct ArLayer {
     Gemm g_memkv;   // rows D..3D-1 of the encoder-decoder in_proj: memory -> K | V
 };
 
+constexpr int kArSplitMax = 4;
+
 struct ArState {
     bool attached = false;
-    int linear_variant = 1;   // launch_linear_f32 variant of the token loop: split-K (b200ocr_debug_set_flag 2, 0 = tiled)
+    // token-loop kernels (b200ocr_debug_set_flag 2): 0 = tiled projections, 1 = split-K projections, 2 (default) =
+    // split-K projections with q | k | v in one launch, the K split of the out-projections and of the second
+    // feed-forward matrix spread over CTAs and summed inside the LayerNorm, CTA-per-(line, head) step attention
+    int linear_variant = 2;
     int heads = 0, dim_ff = 0, classes = 0, D = 0;
     std::vector<ArLayer> layers;
     float *embed = nullptr, *out_w = nullptr, *out_b = nullptr;
@@ -93,6 +98,7 @@ struct ArState {
     float* memkv = nullptr;    // [layer][cap_lines * cap_T][2D]   K | V of the memory frames
     float* selfkv = nullptr;   // [layer][cap_steps][lines][2D]    K | V of the decoded positions
     float *x = nullptr, *q = nullptr, *a = nullptr, *t = nullptr, *f = nullptr, *lg = nullptr;
+    float* part = nullptr;     // [kArSplitMax][lines][D] partial sums of the K-split projections
     int32_t *alive = nullptr, *state = nullptr;
     int32_t* h_state = nullptr;   // pinned host copy of `state`
     std::vector<void*> ws;
@@ -1230,6 +1236,7 @@ int b200ocr_ar_reserve(b200ocr_engine_t* e, int32_t max_lines, int32_t max_width
     CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.q)));
     CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.a)));
     CU_TRY(e, grab(static_cast<size_t>(N) * D * sizeof(float), reinterpret_cast<void**>(&ar.t)));
+    CU_TRY(e, grab(static_cast<size_t>(kArSplitMax) * N * D * sizeof(float), reinterpret_cast<void**>(&ar.part)));
     CU_TRY(e, grab(static_cast<size_t>(N) * ar.dim_ff * sizeof(float), reinterpret_cast<void**>(&ar.f)));
     CU_TRY(e, grab(static_cast<size_t>(N) * ar.classes * sizeof(float), reinterpret_cast<void**>(&ar.lg)));
     CU_TRY(e, grab(static_cast<size_t>(N) * sizeof(int32_t), reinterpret_cast<void**>(&ar.alive)));
@@ -1279,6 +1286,26 @@ int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, 
     }
     AR_LAUNCH(launch_ar_init(ar.alive, n, ar.state, st));
     int done_steps = -1;
+    const int lv = ar.linear_variant >= 2 ? 1 : ar.linear_variant;      // kernel of the plain projections
+    const bool fused = ar.linear_variant >= 2 && sum_layernorm_supported(D);
+    const int att = ar.linear_variant >= 2 ? 1 : 0;
+    const long part_stride = static_cast<long>(ar.cap_lines) * D;
+    auto ksplit = [](int K) { return std::max(1, std::min(kArSplitMax, K / 32 / 8)); };   // >= 8 chunks per CTA
+    // norm(x + W a + b): the projection's K split over CTAs, summed in the LayerNorm (fused), or the fused epilogue
+    // of one CTA per tile + the plain LayerNorm
+    auto proj_norm = [&](const float* a, int K, const float* w, const float* b, const float* gamma,
+                         const float* beta) -> int {
+        if (fused) {
+            const int Z = ksplit(K);
+            AR_LAUNCH(launch_linear_f32_ex(a, K, w, nullptr, nullptr, 0, ar.part, D, n, D, K, 0, D, nullptr, 0, Z,
+                                           part_stride, st));
+            AR_LAUNCH(launch_sum_layernorm(ar.part, Z, part_stride, b, ar.x, n, D, gamma, beta, 1e-5f, ar.x, st));
+        } else {
+            AR_LAUNCH(launch_linear_f32(a, K, w, b, ar.x, D, ar.t, D, n, D, K, 0, lv, st));
+            AR_LAUNCH(launch_layernorm(ar.t, n, D, gamma, beta, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+        }
+        return B200OCR_OK;
+    };
     for (int s = 0; s < max_steps; ++s) {
         AR_LAUNCH(launch_embed_pe(ar.embed, s == 0 ? nullptr : tokens + static_cast<size_t>(s - 1) * n, start_token, n, D,
                                   s, ar.x, st));
@@ -1288,28 +1315,30 @@ int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, 
             float* kv_s = kv + static_cast<size_t>(s) * n * 2 * D;
             const float* mkv = ar.memkv + i * memkv_layer;                  // row (line * T + t) * 2D
             // cached self-attention over positions 0..s (DecoderLayer.infer, transformer.py:431-435)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, ar.linear_variant, st));
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w + static_cast<size_t>(D) * D, ly.self_in_b + D, nullptr, 0,
-                                        kv_s, 2 * D, n, 2 * D, D, 0, ar.linear_variant, st));
+            if (ar.linear_variant >= 2) {
+                AR_LAUNCH(launch_linear_f32_ex(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, 3 * D, D, 0, D,
+                                               kv_s, 2 * D, 1, 0, st));
+            } else {
+                AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, lv, st));
+                AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w + static_cast<size_t>(D) * D, ly.self_in_b + D, nullptr, 0,
+                                            kv_s, 2 * D, n, 2 * D, D, 0, lv, st));
+            }
             AR_LAUNCH(launch_step_attention(ar.q, D, kv, kv + D, static_cast<long>(n) * 2 * D, 2 * D, n, s + 1, D,
-                                            ar.heads, ar.a, st));
-            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.self_out_w, ly.self_out_b, ar.x, D, ar.t, D, n, D, D, 0, ar.linear_variant, st));
-            AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n1w, ly.n1b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+                                            ar.heads, ar.a, att, st));
+            if (int r = proj_norm(ar.a, D, ly.self_out_w, ly.self_out_b, ly.n1w, ly.n1b)) return r;
             // encoder-decoder attention over the T memory frames (:438-447)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, ar.linear_variant, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, lv, st));
             AR_LAUNCH(launch_step_attention(ar.q, D, mkv, mkv + D, 2 * D, static_cast<long>(T) * 2 * D, n, T, D, ar.heads,
-                                            ar.a, st));
-            AR_LAUNCH(launch_linear_f32(ar.a, D, ly.cross_out_w, ly.cross_out_b, ar.x, D, ar.t, D, n, D, D, 0, ar.linear_variant, st));
-            AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n2w, ly.n2b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+                                            ar.a, att, st));
+            if (int r = proj_norm(ar.a, D, ly.cross_out_w, ly.cross_out_b, ly.n2w, ly.n2b)) return r;
             // feed-forward (:449-450)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, ar.linear_variant, st));
-            AR_LAUNCH(launch_linear_f32(ar.f, FF, ly.l2w, ly.l2b, ar.x, D, ar.t, D, n, D, FF, 0, ar.linear_variant, st));
-            AR_LAUNCH(launch_layernorm(ar.t, n, D, ly.n3w, ly.n3b, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, lv, st));
+            if (int r = proj_norm(ar.f, FF, ly.l2w, ly.l2b, ly.n3w, ly.n3b)) return r;
         }
         // dec_out_proj + argmax + alive mask (transformer_ocr_engine.py:69-75)
         float* lg = logits ? logits + static_cast<size_t>(s) * C : ar.lg;
         const long lg_ld = logits ? static_cast<long>(max_steps) * C : C;
-        AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, ar.linear_variant, st));
+        AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, lv, st));
         AR_LAUNCH(launch_argmax_alive(lg, lg_ld, n, C, start_token, s, tokens + static_cast<size_t>(s) * n, ar.alive,
                                       ar.state, st));
         if ((s + 1) % check_every == 0 || s + 1 == max_steps) {
@@ -1353,7 +1382,7 @@ int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, i
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     if (!e) return B200OCR_E_INVALID;
     if (flag == 1) e->use_halo = value != 0;
-    else if (flag == 2) e->ar.linear_variant = value != 0 ? 1 : 0;
+    else if (flag == 2) e->ar.linear_variant = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (flag == 3) e->lstm_hplanes = (value != 0 && e->lstm_planes == 2) ? 2 : 1;
     else if (flag == 4) e->crop_staging = value < 0 || value > 2 ? 2 : value;
     else if (flag == 5) e->ref_only_layer = value;

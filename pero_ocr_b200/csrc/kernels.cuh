@@ -45,9 +45,20 @@ cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start
 // variant 0: one 64-thread group walks K; 1: four groups split K (register prefetch, fixed-order reduction).
 cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
                               float* out, long ldo, int M, int O, int K, int relu, int variant, cudaStream_t stream);
+// The split-K kernel with (a) output columns >= split_o redirected to out2 (rows ldo2 apart) and (b) the K chunks
+// divided over `ksplit` CTAs per tile, CTA z storing its raw partial tile at out + z * part_stride (no bias / relu /
+// residual; needs split_o >= O).  launch_sum_layernorm finishes (b): LayerNorm(sum_z part[z] + bias + res).
+cudaError_t launch_linear_f32_ex(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
+                                 float* out, long ldo, int M, int O, int K, int relu, int split_o, float* out2,
+                                 long ldo2, int ksplit, long part_stride, cudaStream_t stream);
+bool sum_layernorm_supported(int d);
+cudaError_t launch_sum_layernorm(const float* part, int Z, long part_stride, const float* bias, const float* res,
+                                 int rows, int d, const float* gamma, const float* beta, float eps, float* out,
+                                 cudaStream_t stream);
 // one query position per (line, head) against S key / value positions (position p of line l at + p*ps + l*ls).
+// variant 0: one warp per (line, head); 1: one CTA per (line, head), coalesced rows (heads of 32 / 64 / 128).
 cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
-                                  int S, int d, int heads, float* out, cudaStream_t stream);
+                                  int S, int d, int heads, float* out, int variant, cudaStream_t stream);
 // greedy choice + alive mask + stop detection; state = {alive lines, first step after which none was alive or -1}.
 cudaError_t launch_argmax_alive(const float* logits, long ld, int n, int C, int stop_token, int step,
                                 int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream);

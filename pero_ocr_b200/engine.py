@@ -227,7 +227,8 @@ class B200EngineLineOCR:
     Embedding-conditioned nets (``embed_id``) are not supported and raise at construction.
     """
 
-    def __init__(self, json_def, device=None, batch_size=8, precision=DEFAULT_PRECISION, module=None, replicas=1):
+    def __init__(self, json_def, device=None, batch_size=8, precision=DEFAULT_PRECISION, module=None, replicas=1,
+                 pinned_logit_bytes=4 << 30):
         import torch
         with open(json_def, 'r', encoding='utf8') as f:
             self.config = json.load(f)
@@ -295,6 +296,10 @@ class B200EngineLineOCR:
         self.last_confidences = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        # page-locked, recycled host memory for the sparse logits handed to the caller (sparse_logits.PinnedPool):
+        # at most `pinned_logit_bytes` registered at any time (0: always fresh pageable arrays)
+        from .sparse_logits import PinnedPool
+        self.pinned_pool = PinnedPool(pinned_logit_bytes) if pinned_logit_bytes > 0 else None
 
     def _device_ctx(self):
         return self.model.torch.cuda.device(self.device)
@@ -467,7 +472,8 @@ class B200EngineLineOCR:
         res = {name: sl['host'][name].numpy() for name in names}
         if sl.get('sparse') is not None:
             t1 = time.perf_counter()
-            fetched = sl['sparse'].fetch(self._copy_stream, pinned=sl.get('sparse_pin'), pool=self._pool())
+            fetched = sl['sparse'].fetch(self._copy_stream, pinned=sl.get('sparse_pin'), pool=self._pool(),
+                                         blocks=getattr(self, 'pinned_pool', None))
             self.host_ms['fetch'] = self.host_ms.get('fetch', 0.0) + 1e3 * (time.perf_counter() - t1)
             self.d2h_bytes += sum(int(getattr(a, 'array', a).nbytes) for a in fetched)
             t1 = time.perf_counter()

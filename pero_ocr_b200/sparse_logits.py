@@ -34,18 +34,32 @@ class SparseLogits:
             dst.copy_(src, non_blocking=True)
         self._meta = pinned
 
-    def fetch(self, stream=None, pinned=None, pool=None):
+    def fetch(self, stream=None, pinned=None, pool=None, blocks=None):
         """-> (indptr int32 [n, C+1], base int64 [n+1], indices int32 [total], data float32 [total]) as NumPy arrays.
         The small parts first (indptr, base), then the used prefix of indices / data.  With `pinned` (the dict given
         to prefetch_meta, whose copies must have completed) the small parts are already on the host and the big ones
-        are copied straight into fresh arrays the caller may keep (returned wrapped in _Owned for csc_lines)."""
+        are copied straight into arrays the caller may keep (returned wrapped in _Owned for csc_lines): page-locked
+        blocks of `blocks` (a PinnedPool) while it has room, fresh pageable arrays otherwise."""
         torch = self.torch
         stream = stream or torch.cuda.current_stream(self.indptr.device)
         if pinned is not None and getattr(self, '_meta', None) is pinned:
-            # the entry count is already on the host: the big parts go device -> their final (fresh, huge-page advised)
-            # host arrays in ONE pass -- no pinned staging copy that the host would have to copy again
+            # the entry count is already on the host: the big parts go device -> their final host arrays in ONE pass
+            # -- no staging copy that the host would have to copy again
             indptr, base = pinned['indptr'].numpy(), pinned['base'].numpy()
             total = int(base[self.n])
+            if blocks is not None and 4 * total >= PinnedPool.MIN_BYTES:
+                # recycled page-locked destinations: the copy is one DMA at PCIe rate and touches no fresh page
+                bi = blocks.take(4 * total)
+                bd = blocks.take(4 * total) if bi is not None else None
+                if bd is not None:
+                    indices = np.frombuffer(bi, dtype=np.int32, count=total)
+                    data = np.frombuffer(bd, dtype=np.float32, count=total)
+                    with torch.cuda.device(self.indices.device), torch.cuda.stream(stream):
+                        torch.from_numpy(indices).copy_(self.indices[:total], non_blocking=True)
+                        torch.from_numpy(data).copy_(self.data[:total], non_blocking=True)
+                    stream.synchronize()
+                    return indptr, base, _Owned(indices), _Owned(data)
+                del bi
             indices, data = fresh_host_array(total, np.int32), fresh_host_array(total, np.float32)
             if total:
                 def pull(dst, src, st):
@@ -114,6 +128,110 @@ class _Owned:
         self.array = array
 
 
+class _Block:
+    """One page-locked block on loan from a PinnedPool.  It exports the buffer (PEP 688), so every array made over
+    it with np.frombuffer keeps it alive; when the last one is gone the memory goes back to the pool."""
+
+    def __init__(self, pool, mem, nbytes):
+        self._pool, self._mem, self.nbytes = pool, mem, nbytes
+
+    def __buffer__(self, flags):
+        return memoryview(self._mem)
+
+    def __del__(self):
+        pool, mem = self._pool, self._mem
+        self._pool = self._mem = None
+        if pool is not None:
+            pool._give_back(mem, self.nbytes)
+
+
+class PinnedPool:
+    """Page-locked host memory for results the CALLER keeps (the CSC parts of ``TextLine.logits``): anonymous huge-page
+    mappings registered with the driver once (cudaHostRegister) and recycled when the arrays made over them are
+    garbage-collected.  A device->host copy into such a block runs at PCIe rate; into fresh pageable memory it is
+    bound by the driver's staging memcpy and first-touch page faults (~4 GB/s measured).  At most `cap_bytes` are ever
+    registered: beyond that take() returns None and the caller falls back to pageable arrays."""
+    MIN_BYTES = 2 << 20
+
+    def __init__(self, cap_bytes=4 << 30, register=None, unregister=None):
+        import threading
+        self.cap = int(cap_bytes)
+        self.registered = 0
+        self.free = {}                      # block size -> [mmap, ...]
+        self.lock = threading.Lock()
+        self.stats = {'hits': 0, 'new': 0, 'refused': 0}
+        self._register, self._unregister = register or _cuda_host_register, unregister or _cuda_host_unregister
+
+    @staticmethod
+    def block_size(nbytes):
+        """Eight size classes per octave (<= 12.5 % slack), 2 MiB granules."""
+        n = max(int(nbytes), PinnedPool.MIN_BYTES)
+        step = max(1 << 21, (1 << (n.bit_length() - 1)) >> 3)
+        return (n + step - 1) // step * step
+
+    def take(self, nbytes):
+        import mmap
+        size = self.block_size(nbytes)
+        with self.lock:
+            have = self.free.get(size)
+            if have:
+                self.stats['hits'] += 1
+                return _Block(self, have.pop(), size)
+            if self.registered + size > self.cap:
+                self.stats['refused'] += 1
+                return None
+            self.registered += size
+        try:
+            mem = mmap.mmap(-1, size, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+            if hasattr(mmap, 'MADV_HUGEPAGE'):
+                try:
+                    mem.madvise(mmap.MADV_HUGEPAGE)
+                except OSError:
+                    pass
+            self._register(mem, size)
+        except Exception:
+            with self.lock:
+                self.registered -= size
+                self.stats['refused'] += 1
+            return None
+        self.stats['new'] += 1
+        return _Block(self, mem, size)
+
+    def _give_back(self, mem, size):
+        with self.lock:
+            self.free.setdefault(size, []).append(mem)
+
+    def trim(self):
+        """Unregisters and unmaps every block that is not on loan."""
+        with self.lock:
+            blocks, self.free = self.free, {}
+        for size, mems in blocks.items():
+            for mem in mems:
+                try:
+                    self._unregister(mem)
+                    mem.close()
+                except Exception:
+                    pass
+                with self.lock:
+                    self.registered -= size
+
+
+def _address(mem):
+    return C.addressof(C.c_char.from_buffer(mem))
+
+
+def _cuda_host_register(mem, size):
+    import torch
+    err = torch.cuda.cudart().cudaHostRegister(_address(mem), size, 0)
+    if int(err) != 0:
+        raise RuntimeError(f'cudaHostRegister failed: {err}')
+
+
+def _cuda_host_unregister(mem):
+    import torch
+    torch.cuda.cudart().cudaHostUnregister(_address(mem))
+
+
 def fresh_host_array(count, dtype):
     """Pageable host array of `count` elements that the caller will fill and keep (a batch's CSC parts: tens of MB of
     FRESH memory per batch -- first-touch page faults, not the copy, dominate at 4 KB pages).  Anonymous mmap advised
@@ -174,4 +292,4 @@ def csc_lines(sp, fetched=None, pool=None, workers=1):
 
 def _buffer_of(arr):
     import mmap
-    return arr.base if isinstance(arr.base, mmap.mmap) else memoryview(arr)
+    return arr.base if isinstance(arr.base, (mmap.mmap, _Block)) else memoryview(arr)

@@ -437,3 +437,40 @@ def test_tensor_core_attention_matches_cuda_core_attention(width, precision):
     with torch.no_grad():
         ref = net(torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)).permute(0, 2, 1).numpy()
     assert np.abs(a.cpu().numpy() - ref).max() <= TOL
+
+
+def test_recycled_pinned_result_blocks(tmp_path):
+    """Sparse logits of a batch whose CSC parts exceed the pool's threshold (a flat net: every class kept) come back
+    identical through recycled page-locked blocks and through fresh pageable arrays; dropping a call's matrices returns
+    the blocks; a pool that is too small falls back without an error."""
+    import gc
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    from oracle.nets import make_net
+    spec = cases.ENGINE_CASES['lstm']
+    js = write_engine_json(tmp_path, 'lstm')
+    net = make_net('lstm', spec['classes'], seed=3, out_gain=0.05, **spec['net_kw'])       # near-uniform posteriors
+    rng = np.random.default_rng(5)
+    lines = [rng.integers(0, 256, size=(40, 600 + 8 * (i % 5), 3), dtype=np.uint8) for i in range(48)]
+    engines = {name: B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=64, precision='fp16f8', module=net,
+                                       pinned_logit_bytes=cap)
+               for name, cap in (('pool', 1 << 30), ('fresh', 0), ('tiny', 3 << 20))}
+    out = {name: e.process_lines([l.copy() for l in lines]) for name, e in engines.items()}
+    pool = engines['pool'].pinned_pool
+    assert pool.stats['new'] >= 2 and pool.stats['refused'] == 0 and engines['fresh'].pinned_pool is None
+    assert engines['tiny'].pinned_pool.stats['refused'] >= 1
+    kept = np.mean([m.nnz / m.shape[0] for m in out['pool'][1]])
+    assert kept > 60, kept                                              # the case is the dense worst case
+    for name in ('fresh', 'tiny'):
+        assert out[name][0] == out['pool'][0]
+        for a, b in zip(out[name][1], out['pool'][1]):
+            assert a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+            assert np.array_equal(a.data, b.data)
+    first = [m.copy() for m in out['pool'][1]]
+    held = pool.registered
+    del out
+    gc.collect()
+    assert sum(len(v) for v in pool.free.values()) == pool.stats['new']          # everything came back
+    again = engines['pool'].process_lines([l.copy() for l in lines])
+    assert pool.stats['hits'] >= 2 and pool.registered == held                    # served from the returned blocks
+    for a, b in zip(again[1], first):
+        assert np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)

@@ -172,3 +172,30 @@ def test_model_seam_recovers_the_byte_batch_exactly():
     assert back.dtype == torch.uint8 and back.is_contiguous() and np.array_equal(back.numpy(), batch)
     every = torch.arange(256, dtype=torch.float32).div(255.0).view(1, 1, 1, 256).expand(1, 3, 1, 256)
     assert np.array_equal(LineRecognizer.bytes_from_unit_floats(every)[0, 0, :, 0].numpy(), np.arange(256))
+
+
+def test_pinned_pool_lends_and_recycles_blocks():
+    """sparse_logits.PinnedPool without a GPU (registration stubbed): arrays made over a block keep it on loan; it
+    returns when the last one dies; the cap refuses instead of growing."""
+    import gc
+    from pero_ocr_b200.sparse_logits import PinnedPool, _buffer_of
+    registered = []
+    pool = PinnedPool(cap_bytes=32 << 20, register=lambda mem, size: registered.append(size), unregister=lambda mem: None)
+    assert PinnedPool.block_size(1) == 2 << 20 and PinnedPool.block_size(44_000_000) <= 1.125 * 44_000_000
+    blk = pool.take(5 << 20)
+    whole = np.frombuffer(blk, dtype=np.int32, count=1000)
+    assert whole.flags.writeable
+    whole[:] = np.arange(1000)
+    part = np.frombuffer(_buffer_of(whole), dtype=np.int32, count=10, offset=40)
+    del blk, whole
+    gc.collect()
+    assert not pool.free and list(part) == list(range(10, 20))                 # still on loan through `part`
+    del part
+    gc.collect()
+    assert sum(len(v) for v in pool.free.values()) == 1
+    again = pool.take(5 << 20)
+    assert pool.stats == {'hits': 1, 'new': 1, 'refused': 0} and registered == [again.nbytes]
+    assert pool.take(64 << 20) is None and pool.stats['refused'] == 1
+    del again
+    pool.trim()
+    assert pool.registered == 0 and not pool.free
