@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128) step_attention_cta_kernel(const float* __
                                                                  int d, int heads, float* __restrict__ out) {
     extern __shared__ float s_w[];                  // [S] scores / weights, [4][HD] partial outputs, [8] reductions
     constexpr int SEG = HD / 8, LPR = HD / 4, RPW = 32 / LPR;
-    float* s_part = s_w + S;
+    float* s_part = s_w + ((S + 3) & ~3);           // 16-byte aligned
     float* s_red = s_part + 4 * HD;
     const int line = blockIdx.x / heads, head = blockIdx.x - line * heads;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -523,7 +523,7 @@ cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, con
         (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
         return cudaErrorInvalidValue;
     if (variant == 1 && (hd == 32 || hd == 64 || hd == 128) && S <= 8192) {
-        const size_t sm = (static_cast<size_t>(S) + 4 * hd + 8) * sizeof(float);      // < 48 KB
+        const size_t sm = (((static_cast<size_t>(S) + 3) & ~size_t(3)) + 4 * hd + 8) * sizeof(float);      // < 48 KB
         if (hd == 32) step_attention_cta_kernel<32><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
         else if (hd == 64) step_attention_cta_kernel<64><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
         else step_attention_cta_kernel<128><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);

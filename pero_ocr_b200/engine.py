@@ -426,6 +426,7 @@ class B200EngineLineOCR:
                 sl['h2d'].record(self._copy_stream)
             main.wait_event(sl['h2d'])
             self.h2d_bytes += n_bytes
+        t_launch = time.perf_counter()
         o = model.forward(dev, want_logits=(not no_logits) or beam is not None, want_confidence=self.want_confidence,
                           out=sl['outs'])
         sl['outs'] = o
@@ -461,6 +462,7 @@ class B200EngineLineOCR:
             h.copy_(t, non_blocking=True)
             self.d2h_bytes += h.numel() * h.element_size()
         sl['done'].record(main)
+        self.host_ms['launch'] = self.host_ms.get('launch', 0.0) + 1e3 * (time.perf_counter() - t_launch)
         return k, names
 
     def _collect(self, ticket):

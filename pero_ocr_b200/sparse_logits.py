@@ -106,8 +106,16 @@ def sparsify_device(logits, t_lo=None, t_hi=None, out=None):
     if t_lo is not None:
         lo = np.ascontiguousarray(t_lo, dtype=np.int32)
         hi = np.ascontiguousarray(t_hi, dtype=np.int32)
-        lo_d = torch.from_numpy(lo).to(dev, non_blocking=False)
-        hi_d = torch.from_numpy(hi).to(dev, non_blocking=False)
+        # frame ranges through this object's own pinned + device pair, stream-ordered: a synchronous copy here would
+        # make the host wait for everything queued on the stream (the previous batch's forward).  A reused object is
+        # only handed in again after its previous results were collected, so the pair is free
+        if getattr(sp, '_range_pin', None) is None:
+            sp._range_pin = torch.empty((2, n), dtype=torch.int32, pin_memory=True)
+            sp._range_dev = torch.empty((2, n), dtype=torch.int32, device=dev)
+        sp._range_pin[0].numpy()[:] = lo
+        sp._range_pin[1].numpy()[:] = hi
+        sp._range_dev.copy_(sp._range_pin, non_blocking=True)
+        lo_d, hi_d = sp._range_dev[0], sp._range_dev[1]
         sp.rows = np.maximum(np.minimum(hi, t) - np.clip(lo, 0, t), 0)
     else:
         sp.rows = np.full((n,), t, dtype=np.int64)

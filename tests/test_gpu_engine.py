@@ -467,7 +467,7 @@ def test_recycled_pinned_result_blocks(tmp_path):
             assert np.array_equal(a.data, b.data)
     first = [m.copy() for m in out['pool'][1]]
     held = pool.registered
-    del out
+    del out, a, b
     gc.collect()
     assert sum(len(v) for v in pool.free.values()) == pool.stats['new']          # everything came back
     again = engines['pool'].process_lines([l.copy() for l in lines])
