@@ -130,6 +130,31 @@ __device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], int n0, flo
     }
 }
 
+// 256-bit variant (st.global.v8.b32, sm_100): every store instruction fills whole 32-byte sectors of the lane's
+// record -- what the staged variant below buys with a round trip through shared memory, without the round trip.
+// Needs 32-byte aligned record pieces: n0 % 32 == 0 and cout % 32 == 0 (16 for the fp16 planes).
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+__device__ __forceinline__ void epi_store32_v8(const uint32_t (&r)[32], int n0, float acc_scale, const float* s_bias,
+                                               const float* s_scale, const float* s_shift, bool has_affine, int act,
+                                               __half* orow, int cout, int fmt) {
+    uint32_t ph[16], pl[16];
+    epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, fmt, ph, pl);
+    uint8_t* rec = reinterpret_cast<uint8_t*>(orow);
+    st_global_v8(rec + n0 * 2, ph);
+    st_global_v8(rec + n0 * 2 + 32, ph + 8);
+    if (fmt == ACT_F16_HILO) {
+        st_global_v8(rec + cout * 2 + n0 * 2, pl);
+        st_global_v8(rec + cout * 2 + n0 * 2 + 32, pl + 8);
+    } else if (fmt == ACT_F16_F8) {
+        st_global_v8(rec + cout * 2 + n0, pl);
+        st_global_v8(rec + cout * 3 + n0, pl + 8);
+    }
+}
+
 // Warp-cooperative variant: in epi_store32 every lane writes 16-byte pieces of ITS pixel's record, so one store
 // instruction touches 32 records a record-stride apart and fills half a 32-byte sector of each (the no-pool
 // 128-channel layer spent 0.5 of its 1.4 ms on that).  Here the warp parks the 32 x 128 bytes in shared memory

@@ -117,6 +117,7 @@ struct b200ocr_engine {
     bool dynamic_tiles = true;   // persistent GEMM kernels draw tiles from a global counter (tilesched.cuh; flag 7)
     int* tile_counters = nullptr;   // [kTileCounters] zeroed at the start of every layer walk
     int tile_counter_next = 0;
+    int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 256-bit epilogue stores
     bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
     int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
@@ -307,7 +308,7 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     p.out_f32 = o.out_f32; p.best = o.best; p.fmax = o.fmax; p.flse = o.flse; p.fprob = o.fprob;
     {
         static const int dbg = getenv("B200OCR_IGEMM_DBG") ? atoi(getenv("B200OCR_IGEMM_DBG")) : 0;   // bring-up only
-        p.dbg = dbg;
+        p.dbg = dbg | e->igemm_dbg;
     }
     p.tile_counter = (e->dynamic_tiles && e->tile_counters && e->tile_counter_next < kTileCounters)
                          ? e->tile_counters + e->tile_counter_next++ : nullptr;
@@ -1389,6 +1390,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     else if (flag == 6) e->l2_chunk_lines = value < 0 ? 0 : value;
     else if (flag == 7) e->dynamic_tiles = value != 0;
     else if (flag == 8) e->attention_tc = value != 0;
+    else if (flag == 9) e->igemm_dbg = value;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

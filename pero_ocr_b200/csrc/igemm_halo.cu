@@ -342,7 +342,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __half* orow = p.out_h + (static_cast<size_t>(t.img) * Hp * Wp +
                                               static_cast<size_t>(ho / p.pool_h) * Wp + wo / p.pool_w) * p.out_cstride;
                     if (p.dbg & 1) continue;                // bring-up: time the pipeline without the global stores
-                    if (C::kStagedEpi)
+                    if (p.dbg & 4) {
+                        if (writer)
+                            epi_store32_v8(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act,
+                                           orow, p.cout, FMT);
+                    } else if (C::kStagedEpi)
                         epi_store32_staged(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine,
                                            p.act, orow, writer, p.cout, FMT, s_epi + (warp - 3) * 256, lane);
                     else if (writer)

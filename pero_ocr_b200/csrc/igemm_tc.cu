@@ -264,8 +264,12 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]),
                                                          __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), segw)));
                     }
-                    if (writer)
-                        epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
+                    if (writer) {
+                        if (p.dbg & 4)
+                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
+                        else
+                            epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
+                    }
                 }
             } else if (p.epi == EPI_CTC) {
               if (half == 0) {
@@ -360,7 +364,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (valid) {
                         float* dst = p.out_f32 + pix * p.cout + n0;
                         const float* res = (p.epi == EPI_RES_F32) ? p.residual + pix * p.cout + n0 : nullptr;
-                        if ((p.cout & 3) == 0) {
+                        if ((p.dbg & 4) && (p.cout & 31) == 0 && !res) {
+                            // 256-bit stores: whole sectors of this thread's 128-byte piece of the fp32 row
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint32_t w[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    w[e] = __float_as_uint(apply_act(
+                                        fmaf(__uint_as_float(r[j + e]), p.acc_scale, s_bias[n0 + j + e]), p.act));
+                                st_global_v8(dst + j, w);
+                            }
+                        } else if ((p.cout & 3) == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (n0 + j < p.cout) {
