@@ -130,8 +130,9 @@ __device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], int n0, flo
     }
 }
 
-// 256-bit variant (st.global.v8.b32, sm_100): every store instruction fills whole 32-byte sectors of the lane's
-// record -- what the staged variant below buys with a round trip through shared memory, without the round trip.
+// 256-bit variant (st.global.v8.b32, sm_100): in epi_store32 one store instruction touches 32 records a record-stride
+// apart and fills half a 32-byte sector of each; here every instruction fills whole sectors.  (Round 1 bought the same
+// with a detour through shared memory; measured against both, this is the fastest: profiles/r02u_store_ab.json.)
 // Needs 32-byte aligned record pieces: n0 % 32 == 0 and cout % 32 == 0 (16 for the fp16 planes).
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* w) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
@@ -153,47 +154,6 @@ __device__ __forceinline__ void epi_store32_v8(const uint32_t (&r)[32], int n0, 
         st_global_v8(rec + cout * 2 + n0, pl);
         st_global_v8(rec + cout * 3 + n0, pl + 8);
     }
-}
-
-// Warp-cooperative variant: in epi_store32 every lane writes 16-byte pieces of ITS pixel's record, so one store
-// instruction touches 32 records a record-stride apart and fills half a 32-byte sector of each (the no-pool
-// 128-channel layer spent 0.5 of its 1.4 ms on that).  Here the warp parks the 32 x 128 bytes in shared memory
-// (16-byte chunks XOR-swizzled by pixel: conflict-free both ways) and writes them back with 8 consecutive lanes on
-// the 128 bytes of one pixel: whole sectors, 4 pixels per instruction.  Executed by all 32 lanes; `writer` says
-// whether this lane's pixel is stored at all (pooling, image edge).  stage: 256 uint4 (4 KB) private to the warp.
-__device__ __forceinline__ void epi_store32_staged(const uint32_t (&r)[32], int n0, float acc_scale, const float* s_bias,
-                                                   const float* s_scale, const float* s_shift, bool has_affine, int act,
-                                                   __half* orow, bool writer, int cout, int fmt, uint4* stage, int lane) {
-    uint32_t ph[16], pl[16];
-    epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, fmt, ph, pl);
-    uint4* my = stage + lane * 8;
-    const int sw = lane & 7;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) my[j ^ sw] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-    if (fmt != ACT_F16) {   // HILO: 4 chunks of lo; F8: 2 chunks lo' then 2 chunks hi8 -- pl is already in that order
-#pragma unroll
-        for (int j = 0; j < 4; ++j) my[(4 + j) ^ sw] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-    }
-    __syncwarp();
-    const uint32_t wmask = __ballot_sync(0xffffffffu, writer);
-    const unsigned long long my_base = reinterpret_cast<unsigned long long>(orow);
-    const int nch = fmt == ACT_F16 ? 4 : 8;               // 16-byte chunks per pixel
-    const int ppi = 32 / nch;                             // pixels per store instruction
-    const int ch = lane & (nch - 1);
-    // byte offset of chunk `ch` inside the pixel record
-    int off;
-    if (ch < 4) off = n0 * 2 + ch * 16;
-    else if (fmt == ACT_F16_HILO) off = cout * 2 + n0 * 2 + (ch - 4) * 16;
-    else off = cout * 2 + (ch < 6 ? n0 + (ch - 4) * 16 : cout + n0 + (ch - 6) * 16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i * ppi >= 32) break;
-        const int px = i * ppi + lane / nch;
-        const unsigned long long base = __shfl_sync(0xffffffffu, my_base, px);
-        const uint4 v = stage[px * 8 + (ch ^ (px & 7))];
-        if ((wmask >> px) & 1u) *reinterpret_cast<uint4*>(base + off) = v;
-    }
-    __syncwarp();
 }
 
 #endif

@@ -117,7 +117,7 @@ struct b200ocr_engine {
     bool dynamic_tiles = true;   // persistent GEMM kernels draw tiles from a global counter (tilesched.cuh; flag 7)
     int* tile_counters = nullptr;   // [kTileCounters] zeroed at the start of every layer walk
     int tile_counter_next = 0;
-    int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 256-bit epilogue stores
+    int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
     bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
     int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)

@@ -38,12 +38,11 @@ struct Cfg {
     // 4 KB of A whatever N is, which is what bounds this layer (profiles/r01d_halo_limits.md).
     static constexpr bool kPairRows = BN == 64;
     static constexpr int kAStages = 2;
-    // BN = 128 stores through the staged epilogue (actfmt.cuh: epi_store32_staged; the un-pooled 128-channel layer
-    // spent 0.5 of its 1.4 ms on sector-splitting stores): its 32 KB come out of the weight ring (4 -> 3 stages)
-    static constexpr bool kStagedEpi = BN == 128;
-    static constexpr int kBStages = 3;
+    // The epilogue stores 32-byte sectors straight from registers (actfmt.cuh: epi_store32_v8, 256-bit stores); the
+    // shared-memory staged variant of round 1 (whole sectors through a 32 KB detour) measured slower on every layer
+    // (profiles/r02u_store_ab.json) and its 32 KB are back in the weight ring of BN = 128
+    static constexpr int kBStages = BN == 128 ? 4 : 3;
     static constexpr int kBStageBytes = kTapsPerStage * kBBytes;
-    static constexpr int kEpiStageBytes = kStagedEpi ? 8 * 4096 : 0;
     static constexpr int kTmemCols = 512;
     static constexpr int kBarOff = kAStages * kHaloStage + kBStages * kBStageBytes;
     static constexpr int kSmemBytes = kBarOff + 256 + 1024;
@@ -86,7 +85,6 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tq_empty = tq_full + kTileRing;             // [4]
     int* tq_tile = reinterpret_cast<int*>(tq_empty + kTileRing);
     float* s_vec = reinterpret_cast<float*>(smem + C::kBarOff + 256);
-    uint4* s_epi = reinterpret_cast<uint4*>(s_vec + 3 * p.cout_pad);   // kStagedEpi: 256 uint4 per epilogue warp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -342,16 +340,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __half* orow = p.out_h + (static_cast<size_t>(t.img) * Hp * Wp +
                                               static_cast<size_t>(ho / p.pool_h) * Wp + wo / p.pool_w) * p.out_cstride;
                     if (p.dbg & 1) continue;                // bring-up: time the pipeline without the global stores
-                    if (p.dbg & 4) {
-                        if (writer)
-                            epi_store32_v8(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act,
-                                           orow, p.cout, FMT);
-                    } else if (C::kStagedEpi)
-                        epi_store32_staged(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine,
-                                           p.act, orow, writer, p.cout, FMT, s_epi + (warp - 3) * 256, lane);
-                    else if (writer)
+                    if (!writer) continue;
+                    if (p.dbg & 4)                          // A/B: 16-byte stores
                         epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow,
                                     p.cout, FMT);
+                    else
+                        epi_store32_v8(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act,
+                                       orow, p.cout, FMT);
                 }
             }
             ptx::tc_fence_before();
@@ -381,7 +376,7 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
         if (e != cudaSuccess) return e;
         attr_done.mark();
     }
-    const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float) + C::kEpiStageBytes;
+    const size_t smem_bytes = C::kSmemBytes + 3 * static_cast<size_t>(p.cout_pad) * sizeof(float);
     if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
     const int tiles_w = (p.w_out + 127) / 128, tiles_h = (p.h_out + 1) / 2;
     const int total_tiles = p.n_img * tiles_h * tiles_w * p.tiles_n;

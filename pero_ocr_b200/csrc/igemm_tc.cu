@@ -265,10 +265,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                          __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), segw)));
                     }
                     if (writer) {
-                        if (p.dbg & 4)
-                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
-                        else
+                        if (p.dbg & 4)                  // A/B: 16-byte stores
                             epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
+                        else
+                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
                     }
                 }
             } else if (p.epi == EPI_CTC) {
@@ -364,7 +364,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (valid) {
                         float* dst = p.out_f32 + pix * p.cout + n0;
                         const float* res = (p.epi == EPI_RES_F32) ? p.residual + pix * p.cout + n0 : nullptr;
-                        if ((p.dbg & 4) && (p.cout & 31) == 0 && !res) {
+                        if (!(p.dbg & 4) && (p.cout & 31) == 0 && !res) {
                             // 256-bit stores: whole sectors of this thread's 128-byte piece of the fp32 row
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
