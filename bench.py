@@ -707,8 +707,10 @@ def main():
                    'seconds': no_lg['seconds'], 'gather_bytes_total': no_lg['gather_bytes_total']}
 
     # ---- roofline leg: per-launch CUDA-event timing of the same step (separate from the timed region)
+    for i in range(4):                      # the e2e legs above leave the GPU idle between batches: back to steady clocks
+        rec.forward(resident[i % n_rot], want_logits=False, out=outs[0])
     rec.profile(True)
-    prof_steps = 3
+    prof_steps = 6
     for i in range(prof_steps):
         rec.forward(resident[i % n_rot], want_logits=False, out=outs[0])
     tags, lidx, pms = rec.profile_read()

@@ -54,7 +54,7 @@ struct IgemmParams {
     float* flse;
     float* fprob;             // best-class probability under the reference's sparsified softmax (or null)
     int* tile_counter;        // dynamic tile scheduler: zeroed device counter of this launch (null = static striding)
-    int dbg;                  // bring-up switches (B200OCR_IGEMM_DBG, flag 9): 1 = skip epilogue stores, 2 = skip MMA issue, 4 = 16-byte instead of 256-bit epilogue stores
+    int dbg;                  // bring-up switches (B200OCR_IGEMM_DBG, flag 9): 1 = skip epilogue stores, 2 = skip MMA issue, 4 = 16-byte instead of 256-bit epilogue stores, 8 = 4 weight stages in the BN = 128 halo kernel
 };
 
 inline void igemm_fill_geometry(IgemmParams& p, int bn) {

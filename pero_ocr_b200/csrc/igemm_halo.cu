@@ -22,7 +22,7 @@ constexpr int kHaloW = 130, kHaloH = 4;
 constexpr int kHaloBytes = kHaloH * kHaloW * 128;             // 66,560
 constexpr int kHaloStage = ((kHaloBytes + 1023) / 1024) * 1024;  // 66,560 -> 66,560 (65 KB) multiple of 1024
 
-template <int BN>
+template <int BN, int NB>
 struct Cfg {
     static constexpr int kBBytes = BN * 128;
     // An N = 64 MMA lasts 32 clocks, so with one filter tap per weight stage (8 MMAs) the single issuing thread spent
@@ -40,8 +40,9 @@ struct Cfg {
     static constexpr int kAStages = 2;
     // The epilogue stores 32-byte sectors straight from registers (actfmt.cuh: epi_store32_v8, 256-bit stores); the
     // shared-memory staged variant of round 1 (whole sectors through a 32 KB detour) measured slower on every layer
-    // (profiles/r02u_store_ab.json) and its 32 KB are back in the weight ring of BN = 128
-    static constexpr int kBStages = BN == 128 ? 4 : 3;
+    // (profiles/r02u_store_ab.json).  The 32 KB it used would hold a fourth weight stage at BN = 128: measured
+    // slower (conv2_1 / conv2_2 +0.1 ms each, profiles/r02w_store_ab.json), so the ring stays at 3
+    static constexpr int kBStages = NB;        // 3 (A/B of 4 at BN = 128: IgemmParams::dbg bit 8)
     static constexpr int kBStageBytes = kTapsPerStage * kBBytes;
     static constexpr int kTmemCols = 512;
     static constexpr int kBarOff = kAStages * kHaloStage + kBStages * kBStageBytes;
@@ -64,11 +65,11 @@ __device__ __forceinline__ Tile tile_coord(const IgemmParams& p, int tile, int t
     return t;
 }
 
-template <int BN, int FMT>
+template <int BN, int FMT, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmParams p, int tiles_w, int tiles_h, int total_tiles) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -365,13 +366,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-template <int BN, int FMT>
-cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+template <int BN, int FMT, int NB>
+cudaError_t launch_nb(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                       cudaStream_t stream) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, NB>;
     static PerDeviceOnce attr_done;
     if (attr_done.pending()) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BN, FMT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done.mark();
@@ -382,8 +383,15 @@ cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtens
     const int total_tiles = p.n_img * tiles_h * tiles_w * p.tiles_n;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    igemm_halo_kernel<BN, FMT><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p, tiles_w, tiles_h, total_tiles);
+    igemm_halo_kernel<BN, FMT, NB><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p, tiles_w, tiles_h, total_tiles);
     return cudaGetLastError();
+}
+
+template <int BN, int FMT>
+cudaError_t launch_bn(const IgemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                      cudaStream_t stream) {
+    if (BN == 128 && (p.dbg & 8)) return launch_nb<BN, FMT, BN == 128 ? 4 : 3>(p, tmA, tmB, num_sms, stream);
+    return launch_nb<BN, FMT, 3>(p, tmA, tmB, num_sms, stream);
 }
 
 template <int BN>

@@ -25,7 +25,7 @@ out = {}
 ref = None
 res = {'workload': 'config 2 step, 256 x 40 x 1344, fp16f8 autotuned', 'runs': []}
 for rnd in range(2):
-    for variant, name in ((4, 'v4'), (0, 'v8')):
+    for variant, name in ((4, 'v4'), (0, 'v8'), (8, 'v8 + 4 weight stages at BN=128')):
         rec.set_flag(9, variant)
         o = rec.forward(crops, want_logits=True, out={})
         lg = o['logits'].clone()
