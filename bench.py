@@ -416,8 +416,8 @@ def bench_config4(dev, with_cpu, pages=16):
     from pero_ocr_b200.engine import B200EngineLineOCR
     from pero_ocr_b200.parsenet import B200ParseNet
     pn = B200ParseNet(None, dev, downsample=4, adaptive_downsample=False, module=synthetic.make_net('parsenet', seed=1))
-    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=make_net('lstm'))
-    eng.max_input_horizontal_pixels = 64 * 1408
+    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=make_net('lstm'), replicas=2)
+    eng.max_input_horizontal_pixels = 64 * 1408      # 34 of the 2624 px lines per batch: two batches per page
     cropper = B200LineCropper(line_height=40, poly=2, scale=1)
     rng = np.random.default_rng(4)
     imgs = [rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8) for _ in range(2)]     # alternated: 36 MB each
@@ -465,7 +465,7 @@ def bench_config4(dev, with_cpu, pages=16):
     assert n_done == pages * n_lines
     sync_pages_per_s = pages / dt
     out = {'workload': f'config4: {pages} synthetic 4000x3000 pages: ParseNet stand-in forward at downsample 4 (maps '
-                       f'{list(shape)}) + {n_lines} injected baselines per page cropped on the device (40 x ~1300 px) + '
+                       f'{list(shape)}) + {n_lines} injected baselines per page cropped on the device (40 x ~2600 px each) + '
                        f'CNN+BiLSTM line OCR', 'metric': 'pages/sec', 'value': pages / dt_pipe, 'unit': 'pages/s',
            'lines_per_s': pages * n_lines / dt_pipe, 'ms_per_page': 1e3 * dt_pipe / pages,
            'page_by_page': {'pages_per_s': sync_pages_per_s, 'ms_per_page': 1e3 * dt / pages},

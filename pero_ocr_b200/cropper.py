@@ -95,15 +95,25 @@ def remap_poly_into(page, params, offsets, out, pad):
     if n == 0:
         return 0
     arr = (_lib.PolyLine * n)(*params)
-    raw = np.frombuffer(arr, dtype=np.uint8).copy()
-    d_par = torch.from_numpy(raw).to(page.device)
-    d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.float64)).to(page.device)
+    raw = np.frombuffer(arr, dtype=np.uint8)
+    off = np.ascontiguousarray(offsets, dtype=np.float64)
+    # line parameters and offsets go up stream-ordered from page-locked staging (torch's host allocator keeps the block
+    # until the copy has run): a synchronous copy would make the caller wait for everything queued on the stream,
+    # i.e. for the previous batch's forward
+    head = (raw.nbytes + 255) // 256 * 256
+    pin = torch.empty(head + off.nbytes, dtype=torch.uint8, pin_memory=True)
+    pin_np = pin.numpy()
+    pin_np[:raw.nbytes] = raw
+    pin_np[head:].view(np.float64)[:] = off.reshape(-1)
+    d_all = torch.empty(pin.numel(), dtype=torch.uint8, device=page.device)
+    d_all.copy_(pin, non_blocking=True)
+    d_par, d_off = d_all[:raw.nbytes], d_all[head:]
     stream = torch.cuda.current_stream(page.device).cuda_stream
     _lib.check(lib.b200ocr_remap_poly_lines(page.image.data_ptr(), page.shape[0], page.shape[1], d_par.data_ptr(),
                                             d_off.data_ptr(), n, line_h, out.data_ptr(), out_w, pad,
                                             C.c_void_p(stream)))
-    page._keep = (d_par, d_off)            # alive until the kernel has run (stream-ordered free on the next call)
-    return raw.nbytes + d_off.numel() * 8
+    page._keep = d_all                     # alive until the kernel has run (stream-ordered free on the next call)
+    return raw.nbytes + off.nbytes
 
 
 class B200LineCropper:
@@ -192,9 +202,10 @@ class B200LineCropper:
             degree = self.poly if pts.shape[0] > 2 else 1
             coef = np.polyfit(pts[:, 0], pts[:, 1], degree)
             xs = np.arange(pts[:, 0].min(), pts[:, 0].max())
-            ys = np.poly1d(coef)(xs)
+            # np.poly1d(coef)(xs) is np.polyval on the coefficients with leading zeros trimmed
+            ys = np.polyval(coef, xs) if coef[0] != 0 else np.poly1d(coef)(xs)
             seg = ((xs[:-1] - xs[1:]) ** 2 + (ys[:-1] - ys[1:]) ** 2) ** 0.5
-            total = np.concatenate([np.zeros(1), np.cumsum(seg)])[-1]
+            total = np.cumsum(seg)[-1] if seg.shape[0] else np.zeros(1)[-1]   # last of concatenate([0], cumsum(seg))
             n_out = int(total * (target_height / (above + below)))
             if n_out < 1 or len(coef) > 4 or not np.isfinite(total):
                 raise ValueError('empty crop')
