@@ -416,8 +416,10 @@ def bench_config4(dev, with_cpu, pages=16):
     from pero_ocr_b200.engine import B200EngineLineOCR
     from pero_ocr_b200.parsenet import B200ParseNet
     pn = B200ParseNet(None, dev, downsample=4, adaptive_downsample=False, module=synthetic.make_net('parsenet', seed=1))
-    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=make_net('lstm'), replicas=2)
-    eng.max_input_horizontal_pixels = 64 * 1408      # 34 of the 2624 px lines per batch: two batches per page
+    # batch_size 360 -> a pixel budget of 480 * 360 = 172 800 columns (line_ocr_engine.py:30): the 60 lines of a page
+    # (2 624 px each) make ONE batch, so the recurrence (latency-bound: its time follows the line width, not the
+    # batch) runs once per page; two replicas overlap it with the next page's convolutions
+    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=360, module=make_net('lstm'), replicas=2)
     cropper = B200LineCropper(line_height=40, poly=2, scale=1)
     rng = np.random.default_rng(4)
     imgs = [rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8) for _ in range(2)]     # alternated: 36 MB each
@@ -454,12 +456,12 @@ def bench_config4(dev, with_cpu, pages=16):
     def page_source(count):
         for i in range(count):
             yield imgs[i & 1], lines
-    for _ in eng.process_pages(page_source(3), cropper, parsenet=pn, parsenet_downsample=4, no_logits=True):
+    for _ in eng.process_pages(page_source(4), cropper, parsenet=pn, parsenet_downsample=4, no_logits=True, prefetch=3):
         pass
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     n_done = sum(len(r[0]) for r in eng.process_pages(page_source(pages), cropper, parsenet=pn, parsenet_downsample=4,
-                                                        no_logits=True))
+                                                        no_logits=True, prefetch=3))
     torch.cuda.synchronize()
     dt_pipe = time.perf_counter() - t0
     assert n_done == pages * n_lines

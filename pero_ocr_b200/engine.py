@@ -528,48 +528,74 @@ class B200EngineLineOCR:
             yield chunk, widest
 
     def _run_batches(self, widths, stager, sparse_logits, tight_crop_logits, no_logits, return_ids):
-        """Common driver of process_lines / process_line_maps.  `stager(chunk, width)` returns the keyword arguments
-        (`fill=` host stager or `device_fill=` device stager) that produce the padded batch of `chunk`."""
-        count = len(widths)
-        transcriptions = [None] * count
-        logits_out = [None] * count
-        coords_out = [None] * count
-        confidences = [None] * count
+        """Common driver of process_lines / process_line_maps / process_baselines: one job through _run_jobs."""
+        for result in self._run_jobs([(widths, stager)], sparse_logits, tight_crop_logits, no_logits, return_ids):
+            return result
+
+    def _run_jobs(self, jobs, sparse_logits, tight_crop_logits, no_logits, return_ids):
+        """Generator over `jobs` = iterable of (widths, stager): the lines of one call (or one page) each.
+        `stager(chunk, width)` returns the keyword arguments (`fill=` host stager, `packed=` host crops or
+        `device_fill=` device stager) that produce the padded batch of `chunk`.  Yields (transcriptions, logits,
+        logit_coords) per job, in order.  The batch pipeline runs ACROSS jobs: the next job is pulled from the
+        iterable and its first batches are submitted before the last batches of the current one are collected, so
+        consecutive pages overlap on the GPU like consecutive batches of one call do."""
         pad, sub, height = self.line_padding_px, self.net_subsampling, self.line_px_height
         budget = self.max_input_horizontal_pixels
 
-        def finish(chunk, res):
+        def finish(job, chunk, res):
+            widths = job['widths']
             labels, lengths = res['labels'], res['lengths']
             if return_ids:
                 texts = [labels[s, :lengths[s]].copy() for s in range(len(chunk))]
             else:
                 texts = self._decode_ids(labels, lengths)
             for slot, idx in enumerate(chunk):
-                transcriptions[idx] = texts[slot]
+                job['transcriptions'][idx] = texts[slot]
                 if self.want_confidence:
-                    confidences[idx] = float(res['confidence'][slot])
+                    job['confidences'][idx] = float(res['confidence'][slot])
                 if no_logits:
                     continue
                 lo, hi = int(pad // sub), int((pad + widths[idx]) // sub)
                 if sparse_logits:
-                    coords_out[idx] = [None, None] if tight_crop_logits else [lo, hi]
-                    logits_out[idx] = res['sparse'][slot]
+                    job['coords'][idx] = [None, None] if tight_crop_logits else [lo, hi]
+                    job['logits'][idx] = res['sparse'][slot]
                     continue
                 line_logits = res['logits'][slot]
                 if tight_crop_logits:
                     line_logits = line_logits[lo:hi]
-                    coords_out[idx] = [None, None]
+                    job['coords'][idx] = [None, None]
                 else:
-                    coords_out[idx] = [lo, hi]
-                logits_out[idx] = line_logits.copy()
+                    job['coords'][idx] = [lo, hi]
+                job['logits'][idx] = line_logits.copy()
+            job['open'] -= 1
+
+        def collect_oldest(in_flight):
+            job, chunk, ticket = in_flight.pop(0)
+            with self._device_ctx():
+                res = self._collect(ticket)
+            t0 = time.perf_counter()
+            finish(job, chunk, res)
+            self.host_ms['finish'] += 1e3 * (time.perf_counter() - t0)
+
+        def completed(order):
+            """Jobs at the head of `order` whose batches have all been submitted and collected."""
+            while order and order[0]['submitted'] and order[0]['open'] == 0:
+                job = order.pop(0)
+                self.last_line_confidences = job['confidences'] if self.want_confidence else None
+                yield job['transcriptions'], job['logits'], job['coords']
 
         # batches in flight before the oldest is collected: one per native engine (replica), so that with two replicas
         # the tail of batch i, the head of batch i+1 and the staging of batch i+2 are all under way at once
         depth = len(self._models)
         nslots = 2 * depth
-        in_flight = []
-        with self._device_ctx():
-            for bi, (chunk, widest) in enumerate(self._batches(widths)):
+        in_flight, order = [], []
+        bi = 0
+        for widths, stager in jobs:
+            count = len(widths)
+            job = {'widths': widths, 'transcriptions': [None] * count, 'logits': [None] * count,
+                   'coords': [None] * count, 'confidences': [None] * count, 'open': 0, 'submitted': False}
+            order.append(job)
+            for chunk, widest in self._batches(widths):
                 full_w = widest + 2 * pad
                 width = full_w
                 if full_w > budget:
@@ -583,19 +609,20 @@ class B200EngineLineOCR:
                     else:
                         ranges = ([0] * len(chunk), [t_all] * len(chunk))
                 kw = stager(chunk, width)
-                ticket = self._submit(bi % nslots, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
-                                      device_fill=kw.get('device_fill'), packed=kw.get('packed'))
-                in_flight.append((chunk, ticket))
+                with self._device_ctx():
+                    ticket = self._submit(bi % nslots, (len(chunk), height, width, 3), kw.get('fill'), no_logits, ranges,
+                                          device_fill=kw.get('device_fill'), packed=kw.get('packed'))
+                bi += 1
+                job['open'] += 1
+                in_flight.append((job, chunk, ticket))
                 if len(in_flight) > depth:
-                    done_chunk, done_ticket = in_flight.pop(0)
-                    res = self._collect(done_ticket)
-                    t0 = time.perf_counter()
-                    finish(done_chunk, res)
-                    self.host_ms['finish'] += 1e3 * (time.perf_counter() - t0)
-            for done_chunk, done_ticket in in_flight:
-                finish(done_chunk, self._collect(done_ticket))
-        self.last_line_confidences = confidences if self.want_confidence else None
-        return transcriptions, logits_out, coords_out
+                    collect_oldest(in_flight)
+                    yield from completed(order)
+            job['submitted'] = True
+            yield from completed(order)
+        while in_flight:
+            collect_oldest(in_flight)
+            yield from completed(order)
 
     def process_lines(self, lines, sparse_logits=True, tight_crop_logits=False, no_logits=False, return_ids=False):
         """list of [H,w,3] uint8 crops -> (transcriptions, logits, logit_coords); semantics of
@@ -617,11 +644,16 @@ class B200EngineLineOCR:
         of line parameters per line are uploaded; the sampling maps, the bilinear resampling, the padding of the
         batch and the recogniser all run on the GPU.  Results are those of LineCropper.process_page followed by
         process_lines (page_parser.py:384-393, 418-430) on the reference's crops."""
-        from .cropper import remap_poly_into
         if cropper.line_height != self.line_px_height:
             raise ValueError('cropper and recogniser disagree on the line height')
         if prepared is None:
             prepared = [cropper.poly_params(b, h) for b, h in lines]
+        widths, stager = self._baseline_job(page, prepared)
+        return self._run_batches(widths, stager, sparse_logits, tight_crop_logits, no_logits, return_ids)
+
+    def _baseline_job(self, page, prepared):
+        """(widths, stager) of one page for _run_jobs: the crops are resampled on the device straight into the batch."""
+        from .cropper import remap_poly_into
 
         def stager(chunk, width):
             def device_fill(dev_batch):
@@ -629,8 +661,7 @@ class B200EngineLineOCR:
                                        dev_batch, self.line_padding_px)
             return {'device_fill': device_fill}
 
-        return self._run_batches([p[0].n_out for p in prepared], stager, sparse_logits, tight_crop_logits, no_logits,
-                                 return_ids)
+        return [p[0].n_out for p in prepared], stager
 
     def process_pages(self, pages, cropper, parsenet=None, parsenet_downsample=None, prefetch=2, **kw):
         """Pages through the page path with the stages of consecutive pages overlapped -- what
@@ -659,25 +690,36 @@ class B200EngineLineOCR:
             fitted = [cropper.poly_params(b, h) for b, h in lines]
             return page, fitted, ready, maps
 
+        if cropper.line_height != self.line_px_height:
+            raise ValueError('cropper and recogniser disagree on the line height')
         it = iter(pages)
+        maps_of = []                                   # per page, in order: the ParseNet maps (or None)
+
         with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
-            pending, k = [], 0
-            for item in it:
-                pending.append((pool.submit(prepare, k, item[0], item[1]), item[1]))
-                k += 1
-                if len(pending) >= max(1, prefetch):
-                    break
-            while pending:
-                fut, lines = pending.pop(0)
-                page, fitted, ready, maps = fut.result()
-                nxt = next(it, None)
-                if nxt is not None:
-                    pending.append((pool.submit(prepare, k, nxt[0], nxt[1]), nxt[1]))
+            def page_jobs():
+                pending, k = [], 0
+                for item in it:
+                    pending.append(pool.submit(prepare, k, item[0], item[1]))
                     k += 1
-                with self._device_ctx():
-                    torch.cuda.current_stream(self.device).wait_event(ready)
-                tr, lg, co = self.process_baselines(page, lines, cropper, prepared=fitted, **kw)
-                yield tr, lg, co, maps
+                    if len(pending) >= max(1, prefetch):
+                        break
+                while pending:
+                    page, fitted, ready, maps = pending.pop(0).result()
+                    nxt = next(it, None)
+                    if nxt is not None:
+                        pending.append(pool.submit(prepare, k, nxt[0], nxt[1]))
+                        k += 1
+                    with self._device_ctx():
+                        torch.cuda.current_stream(self.device).wait_event(ready)
+                    maps_of.append(maps)
+                    yield self._baseline_job(page, fitted)
+
+            # one batch pipeline across the pages: the first batches of page i+1 are on the GPU before the last ones of
+            # page i are collected
+            flags = {'sparse_logits': True, 'tight_crop_logits': False, 'no_logits': False, 'return_ids': False}
+            flags.update(kw)
+            for tr, lg, co in self._run_jobs(page_jobs(), **flags):
+                yield tr, lg, co, maps_of.pop(0)
 
     def decode_lines(self, lines, decoder):
         """Recognise and beam-decode in one pass on the device: the work of PageOCR.process_page followed by

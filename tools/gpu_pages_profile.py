@@ -21,8 +21,9 @@ from pero_ocr_b200.parsenet import B200ParseNet            # noqa: E402
 
 dev = torch.device('cuda', 0)
 pn = B200ParseNet(None, dev, downsample=4, adaptive_downsample=False, module=synthetic.make_net('parsenet', seed=1))
-eng = B200EngineLineOCR(bench.write_engine_json(), dev, batch_size=8, module=bench.make_net('lstm'))
-eng.max_input_horizontal_pixels = 64 * 1408
+eng = B200EngineLineOCR(bench.write_engine_json(), dev, batch_size=int(os.environ.get('B200OCR_PAGES_BATCH', '360')),
+                        module=bench.make_net('lstm'), replicas=int(os.environ.get('B200OCR_PAGES_REPLICAS', '2')))
+print('budget', eng.max_input_horizontal_pixels, 'replicas', len(eng._models))
 cropper = B200LineCropper(line_height=40, poly=2, scale=1)
 rng = np.random.default_rng(4)
 imgs = [rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8) for _ in range(2)]
