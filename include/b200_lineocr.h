@@ -347,7 +347,9 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
  * 0 = the fp32 CUDA-core attention kernels for every shape;
  * flag 9: bring-up bits of the tensor-core GEMM kernels: 1 = epilogues do not store, 2 = no MMA issued (both give
  * wrong results on purpose: timing only), 4 = 16-byte epilogue stores instead of the 256-bit st.global.v8.b32, 8 = a
- * fourth weight stage in the BN = 128 halo kernel. */
+ * fourth weight stage in the BN = 128 halo kernel;
+ * flag 10: the BiLSTM recurrence is launched on the engine's high-priority side stream (fork / join by events; default
+ * on) so that it overlaps another engine's convolutions on the same GPU instead of waiting for a gap. */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

@@ -117,6 +117,13 @@ struct b200ocr_engine {
     bool dynamic_tiles = true;   // persistent GEMM kernels draw tiles from a global counter (tilesched.cuh; flag 7)
     int* tile_counters = nullptr;   // [kTileCounters] zeroed at the start of every layer walk
     int tile_counter_next = 0;
+    // The BiLSTM recurrence runs on a high-priority side stream (fork / join by events around the launch): its 32-64
+    // CTAs are latency-bound for milliseconds, and when another engine's persistent conv kernels share the GPU
+    // (replicas, engine.py) the block scheduler must place its clusters BEFORE the next conv layer's 148 CTAs,
+    // otherwise the recurrence only starts when the other stream runs dry and nothing overlaps (flag 10)
+    bool lstm_priority = true;
+    cudaStream_t hi_stream = nullptr;
+    cudaEvent_t hi_fork = nullptr, hi_join = nullptr;
     int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
     bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
@@ -528,6 +535,16 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     __half* o = static_cast<__half*>(e->hbuf[slot]);
                     if (e->use_ref) {
                         CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->fmt, e->planes == 1, o, st));
+                    } else if (e->lstm_priority && e->hi_stream) {
+                        CU_TRY(e, cudaEventRecord(e->hi_fork, st));
+                        CU_TRY(e, cudaStreamWaitEvent(e->hi_stream, e->hi_fork, 0));
+                        {
+                            ProfScope ps(e, e->hi_stream, PROF_LSTM);
+                            CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->lstm_planes, e->lstm_hplanes,
+                                                     e->fmt, e->hi_stream));
+                        }
+                        CU_TRY(e, cudaEventRecord(e->hi_join, e->hi_stream));
+                        CU_TRY(e, cudaStreamWaitEvent(st, e->hi_join, 0));
                     } else {
                         ProfScope ps(e, st, PROF_LSTM);
                         CU_TRY(e, launch_lstm_tc(ly.w_rec, eo.out_f32, o, cur.n, T, H, e->lstm_planes, e->lstm_hplanes, e->fmt, st));
@@ -826,6 +843,15 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
     if (cudaMalloc(reinterpret_cast<void**>(&e->tile_counters), kTileCounters * sizeof(int)) != cudaSuccess)
         return bail(fail(e, B200OCR_E_CUDA, "cudaMalloc(tile counters) failed"));
     e->owned.push_back(e->tile_counters);
+    {
+        int lo = 0, hi = 0;                        // numerically lower = higher priority
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&e->hi_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->hi_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->hi_join, cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(e, B200OCR_E_CUDA, "side stream for the recurrence could not be created"));
+        if (const char* v = getenv("B200OCR_LSTM_PRIORITY")) e->lstm_priority = atoi(v) != 0;   // A/B runs of bench.py
+    }
     if (desc->precision == B200OCR_PREC_FP16F8W)   // preset: weight-side correction only in the deep 3x3 layers
         for (LayerRT& ly : e->layers)
             if (ly.kind == B200OCR_CONV && ly.g.kh * ly.g.kw == 9 && ly.g.cin >= 256) ly.g.corr = CORR_WEIGHT;
@@ -913,6 +939,9 @@ void b200ocr_destroy(b200ocr_engine_t* e) {
     if (e->best) { cudaFree(e->best); cudaFree(e->fmax); cudaFree(e->flse); cudaFree(e->fprob); }
     for (void* p : e->ar.ws) cudaFree(p);
     if (e->ar.h_state) cudaFreeHost(e->ar.h_state);
+    if (e->hi_fork) cudaEventDestroy(e->hi_fork);
+    if (e->hi_join) cudaEventDestroy(e->hi_join);
+    if (e->hi_stream) cudaStreamDestroy(e->hi_stream);
     delete e;
 }
 
@@ -1391,6 +1420,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     else if (flag == 7) e->dynamic_tiles = value != 0;
     else if (flag == 8) e->attention_tc = value != 0;
     else if (flag == 9) e->igemm_dbg = value;
+    else if (flag == 10) e->lstm_priority = value != 0;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

@@ -676,18 +676,33 @@ class B200EngineLineOCR:
         from .cropper import DevicePage
         torch = self.model.torch
         lock = threading.Lock()
-        streams = [torch.cuda.Stream(self.device) for _ in range(max(1, prefetch))]
+        prefetch = max(1, int(prefetch))
+        # side streams and worker threads live as long as the engine: torch's caching allocator keeps one pool per
+        # stream, so fresh streams per call would mean fresh cudaMallocs for every page image
+        if len(getattr(self, '_page_streams', ())) < prefetch:
+            with self._device_ctx():
+                self._page_streams = [torch.cuda.Stream(self.device) for _ in range(prefetch)]
+        if getattr(self, '_page_workers', None) is None or self._page_workers._max_workers < prefetch:
+            self._page_workers = ThreadPoolExecutor(max_workers=max(prefetch, 3), thread_name_prefix='b200ocr-page')
+        streams, pool = self._page_streams[:prefetch], self._page_workers
+        page_ms = self.page_ms = {'upload': 0.0, 'parsenet': 0.0, 'fit': 0.0, 'starved': 0.0}   # host time per stage
 
         def prepare(k, image, lines):
+            t0 = time.perf_counter()
             with torch.cuda.device(self.device), torch.cuda.stream(streams[k % len(streams)]):
                 page = DevicePage(image, self.device)
                 ready = torch.cuda.Event()
                 ready.record(streams[k % len(streams)])
+                t1 = time.perf_counter()
                 maps = None
                 if parsenet is not None:
                     with lock:                                   # one native engine, not re-entrant
                         maps = parsenet.get_maps(image, parsenet_downsample or parsenet.init_downsample)
+            t2 = time.perf_counter()
             fitted = [cropper.poly_params(b, h) for b, h in lines]
+            t3 = time.perf_counter()
+            with lock:
+                page_ms['upload'] += 1e3 * (t1 - t0); page_ms['parsenet'] += 1e3 * (t2 - t1); page_ms['fit'] += 1e3 * (t3 - t2)
             return page, fitted, ready, maps
 
         if cropper.line_height != self.line_px_height:
@@ -695,31 +710,32 @@ class B200EngineLineOCR:
         it = iter(pages)
         maps_of = []                                   # per page, in order: the ParseNet maps (or None)
 
-        with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
-            def page_jobs():
-                pending, k = [], 0
-                for item in it:
-                    pending.append(pool.submit(prepare, k, item[0], item[1]))
+        def page_jobs():
+            pending, k = [], 0
+            for item in it:
+                pending.append(pool.submit(prepare, k, item[0], item[1]))
+                k += 1
+                if len(pending) >= prefetch:
+                    break
+            while pending:
+                t0 = time.perf_counter()
+                page, fitted, ready, maps = pending.pop(0).result()
+                page_ms['starved'] += 1e3 * (time.perf_counter() - t0)
+                nxt = next(it, None)
+                if nxt is not None:
+                    pending.append(pool.submit(prepare, k, nxt[0], nxt[1]))
                     k += 1
-                    if len(pending) >= max(1, prefetch):
-                        break
-                while pending:
-                    page, fitted, ready, maps = pending.pop(0).result()
-                    nxt = next(it, None)
-                    if nxt is not None:
-                        pending.append(pool.submit(prepare, k, nxt[0], nxt[1]))
-                        k += 1
-                    with self._device_ctx():
-                        torch.cuda.current_stream(self.device).wait_event(ready)
-                    maps_of.append(maps)
-                    yield self._baseline_job(page, fitted)
+                with self._device_ctx():
+                    torch.cuda.current_stream(self.device).wait_event(ready)
+                maps_of.append(maps)
+                yield self._baseline_job(page, fitted)
 
-            # one batch pipeline across the pages: the first batches of page i+1 are on the GPU before the last ones of
-            # page i are collected
-            flags = {'sparse_logits': True, 'tight_crop_logits': False, 'no_logits': False, 'return_ids': False}
-            flags.update(kw)
-            for tr, lg, co in self._run_jobs(page_jobs(), **flags):
-                yield tr, lg, co, maps_of.pop(0)
+        # one batch pipeline across the pages: the first batches of page i+1 are on the GPU before the last ones of
+        # page i are collected
+        flags = {'sparse_logits': True, 'tight_crop_logits': False, 'no_logits': False, 'return_ids': False}
+        flags.update(kw)
+        for tr, lg, co in self._run_jobs(page_jobs(), **flags):
+            yield tr, lg, co, maps_of.pop(0)
 
     def decode_lines(self, lines, decoder):
         """Recognise and beam-decode in one pass on the device: the work of PageOCR.process_page followed by

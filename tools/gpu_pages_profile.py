@@ -59,6 +59,20 @@ for prefetch in (1, 2, 3):
     timed(f'process_pages 16 pages, prefetch {prefetch} (per page)',
           lambda: [0 for _ in eng.process_pages(source(16), cropper, parsenet=pn, parsenet_downsample=4, no_logits=True,
                                                 prefetch=prefetch)], reps=2)
+eng.host_ms = {k: 0.0 for k in eng.host_ms}
+t0 = time.perf_counter()
+stamps = []
+for _ in eng.process_pages(source(32), cropper, no_logits=True, prefetch=3):
+    stamps.append(time.perf_counter() - t0)
+print('32 pages without ParseNet: host_ms totals', {k: round(v, 1) for k, v in eng.host_ms.items()}, {k: round(v, 1) for k, v in eng.page_ms.items()},
+      'page completion times (ms)', [round(1e3 * x, 1) for x in stamps])
+# device-resident pages, prepared up front: the GPU-side ceiling of the page path (two replicas overlapping)
+pages_dev = [DevicePage(imgs[i & 1]) for i in range(2)]
+torch.cuda.synchronize()
+def resident(n):
+    jobs = (eng._baseline_job(pages_dev[i & 1], fitted) for i in range(n))
+    return [0 for _ in eng._run_jobs(jobs, True, False, True, False)]
+timed('device-resident prepared pages through _run_jobs (per 16)', lambda: resident(16), reps=3)
 timed('process_pages 16 pages without ParseNet (per 16)', lambda: [0 for _ in eng.process_pages(source(16), cropper, no_logits=True)], reps=2)
 
 pr = cProfile.Profile()
