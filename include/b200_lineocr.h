@@ -149,6 +149,16 @@ int b200ocr_set_layer_correction(b200ocr_engine_t* e, int32_t layer, int32_t mod
  * receives the figure of each layer (0 for layers without a contraction). */
 double b200ocr_executed_passes(const b200ocr_engine_t* e, int32_t n, int32_t w, int32_t capacity, float* per_layer);
 
+/* Two (or more) engines on one GPU, each fed on its own stream (the reference has one module and one stream,
+ * pytorch_ocr_engine.py:59-74): after this call every forward of `e` starts its layer walk only when the latest forward
+ * of `after` that was enqueued before it has finished its convolutional front end (everything up to the first BiLSTM
+ * recurrence).  Linked in a ring, the engines hand the whole GPU to one another for their throughput-bound
+ * convolutions while the latency-bound recurrence of the previous batch (32-64 of the 148 SMs) runs beside them;
+ * unlinked, the hardware interleaves the two conv chains layer by layer, both reach their recurrences together, and
+ * 84+ SMs idle for their duration.  `after` = NULL unlinks.  Both engines must live on the same device; an engine
+ * may be destroyed while linked. */
+int b200ocr_run_after(b200ocr_engine_t* e, b200ocr_engine_t* after);
+
 /* Replaces greedy_decode_ctc (pytorch_ocr_engine.py:13-34) and decoding.decoders.GreedyDecoder.__call__
  * (pero_ocr/decoding/decoders.py:42-62) on materialised scores.
  *   scores  device f32, layout 0 = [n][t][c] (run_ocr / decoder layout), 1 = [n][c][t] (model output layout)

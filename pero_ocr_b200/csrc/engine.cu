@@ -121,7 +121,13 @@ struct b200ocr_engine {
     // CTAs are latency-bound for milliseconds, and when another engine's persistent conv kernels share the GPU
     // (replicas, engine.py) the block scheduler must place its clusters BEFORE the next conv layer's 148 CTAs,
     // otherwise the recurrence only starts when the other stream runs dry and nothing overlaps (flag 10)
-    bool lstm_priority = true;
+    // b200ocr_run_after: `front_done` is recorded when this engine's walk reaches its first recurrence; a walk waits
+    // for the `front_done` of `after` first.  `followers` = engines whose `after` is this one (cleared on destroy)
+    cudaEvent_t front_done = nullptr;
+    b200ocr_engine* after = nullptr;
+    std::vector<b200ocr_engine*> followers;
+    bool front_recorded = false;
+    bool lstm_priority = false;
     cudaStream_t hi_stream = nullptr;
     cudaEvent_t hi_fork = nullptr, hi_join = nullptr;
     int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
@@ -400,6 +406,9 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
         return 0;
     };
     const int L = std::min<int>(n_layers, e->layers.size());
+    if (!dry && crops && e->after && e->after->front_done)
+        CU_TRY(e, cudaStreamWaitEvent(st, e->after->front_done, 0));
+    e->front_recorded = false;
     if (!dry && e->dynamic_tiles && e->tile_counters) {
         CU_TRY(e, cudaMemsetAsync(e->tile_counters, 0, kTileCounters * sizeof(int), st));
         e->tile_counter_next = 0;
@@ -533,6 +542,10 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     eo.out_f32 = static_cast<float*>(e->fbuf[1]);
                     if (int s = run_gemm(e, ly.g, cur_h, rows, 0, 1, 1, eo, st, nullptr)) return s;
                     __half* o = static_cast<__half*>(e->hbuf[slot]);
+                    if (e->front_done && !e->followers.empty() && !e->front_recorded) {
+                        CU_TRY(e, cudaEventRecord(e->front_done, st));       // the conv front end of this batch is done
+                        e->front_recorded = true;
+                    }
                     if (e->use_ref) {
                         CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->fmt, e->planes == 1, o, st));
                     } else if (e->lstm_priority && e->hi_stream) {
@@ -939,6 +952,12 @@ void b200ocr_destroy(b200ocr_engine_t* e) {
     if (e->best) { cudaFree(e->best); cudaFree(e->fmax); cudaFree(e->flse); cudaFree(e->fprob); }
     for (void* p : e->ar.ws) cudaFree(p);
     if (e->ar.h_state) cudaFreeHost(e->ar.h_state);
+    if (e->after) {
+        auto& f = e->after->followers;
+        f.erase(std::remove(f.begin(), f.end(), e), f.end());
+    }
+    for (b200ocr_engine* f : e->followers) f->after = nullptr;
+    if (e->front_done) cudaEventDestroy(e->front_done);
     if (e->hi_fork) cudaEventDestroy(e->hi_fork);
     if (e->hi_join) cudaEventDestroy(e->hi_join);
     if (e->hi_stream) cudaStreamDestroy(e->hi_stream);
@@ -1001,6 +1020,29 @@ int b200ocr_set_layer_correction(b200ocr_engine_t* e, int32_t layer, int32_t mod
         case B200OCR_TRANSFORMER_LAYER: ly.g_in.corr = ly.g_out.corr = ly.g_l1.corr = ly.g_l2.corr = mode; break;
         default: return fail(e, B200OCR_E_INVALID, "layer %d has no tensor-core contraction", layer);
     }
+    return B200OCR_OK;
+}
+
+int b200ocr_run_after(b200ocr_engine_t* e, b200ocr_engine_t* after) {
+    if (!e || after == e) return fail(e, B200OCR_E_INVALID, "bad run_after arguments");
+    if (after && after->device != e->device) return fail(e, B200OCR_E_INVALID, "engines live on different devices");
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev != e->device) cudaSetDevice(e->device);
+    if (e->after) {
+        auto& f = e->after->followers;
+        f.erase(std::remove(f.begin(), f.end(), e), f.end());
+        e->after = nullptr;
+    }
+    if (!after) {
+        if (cur_dev != e->device) cudaSetDevice(cur_dev);
+        return B200OCR_OK;
+    }
+    cudaError_t err = after->front_done ? cudaSuccess : cudaEventCreateWithFlags(&after->front_done, cudaEventDisableTiming);
+    if (cur_dev != e->device) cudaSetDevice(cur_dev);
+    if (err != cudaSuccess) return fail(e, B200OCR_E_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(err));
+    after->followers.push_back(e);
+    e->after = after;
     return B200OCR_OK;
 }
 

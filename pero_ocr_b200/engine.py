@@ -65,6 +65,11 @@ class LineRecognizer:
     def use_reference_kernels(self, on):
         _lib.check(self._lib.b200ocr_debug_use_reference_kernels(self._h, 1 if on else 0), self._h)
 
+    def run_after(self, other):
+        """b200ocr_run_after: this engine's forwards start once `other`'s latest forward has finished its convolutional
+        front end (None unlinks)."""
+        _lib.check(self._lib.b200ocr_run_after(self._h, other._h if other is not None else None), self._h)
+
     def set_flag(self, flag, value):
         _lib.check(self._lib.b200ocr_debug_set_flag(self._h, int(flag), int(value)), self._h)
 
@@ -272,6 +277,12 @@ class B200EngineLineOCR:
         # (csrc/tilesched.cuh), which keeps the sharing work-conserving.
         self._models = [self.model] + [LineRecognizer(layers, precision=precision, line_height=self.line_px_height,
                                                       device=self.device.index or 0) for _ in range(max(1, replicas) - 1)]
+        # the replicas pass the GPU to one another for their convolutional front ends (b200ocr_run_after), so that the
+        # recurrence of batch i runs beside the convolutions of batch i+1 instead of beside the recurrence of batch i+1
+        import os as _os
+        if len(self._models) > 1 and _os.environ.get('B200OCR_LINK_REPLICAS', '1') != '0':
+            for i, m in enumerate(self._models):
+                m.run_after(self._models[i - 1])
         self._slots = None
         self._copy_stream = None
         # host threads that pad a batch into pinned memory (process_lines): a few when the process has the cores for
