@@ -335,6 +335,10 @@ int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, 
 int b200ocr_profile(b200ocr_engine_t* e, int32_t on);
 int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, int32_t* layers, float* ms,
                          int32_t* count);
+/* Like b200ocr_profile_read, for timelines across engines and streams: `reference` is a recorded cudaEvent_t created
+ * with timing enabled; start_ms / end_ms (HOST f32 [capacity]) receive each launch's begin and end relative to it. */
+int b200ocr_profile_read_since(b200ocr_engine_t* e, void* reference, int32_t capacity, int32_t* tags, int32_t* layers,
+                               float* start_ms, float* end_ms, int32_t* count);
 
 /* ---- debug / test hooks (not used by the product path) ------------------------------------------------- */
 /* Route every implicit-GEMM layer through a naive one-thread-per-output CUDA-core kernel (same packed fp16
@@ -358,8 +362,9 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
  * flag 9: bring-up bits of the tensor-core GEMM kernels: 1 = epilogues do not store, 2 = no MMA issued (both give
  * wrong results on purpose: timing only), 4 = 16-byte epilogue stores instead of the 256-bit st.global.v8.b32, 8 = a
  * fourth weight stage in the BN = 128 halo kernel;
- * flag 10: the BiLSTM recurrence is launched on the engine's high-priority side stream (fork / join by events; default
- * on) so that it overlaps another engine's convolutions on the same GPU instead of waiting for a gap. */
+ * flag 10: the BiLSTM recurrence is launched on the engine's high-priority side stream (fork / join by events).
+ * Default off: with b200ocr_run_after the recurrence already runs beside the other engine's convolutions, and
+ * the priority changed nothing measurable (profiles/r02B_replica_link_ab.md). */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

@@ -117,10 +117,9 @@ struct b200ocr_engine {
     bool dynamic_tiles = true;   // persistent GEMM kernels draw tiles from a global counter (tilesched.cuh; flag 7)
     int* tile_counters = nullptr;   // [kTileCounters] zeroed at the start of every layer walk
     int tile_counter_next = 0;
-    // The BiLSTM recurrence runs on a high-priority side stream (fork / join by events around the launch): its 32-64
-    // CTAs are latency-bound for milliseconds, and when another engine's persistent conv kernels share the GPU
-    // (replicas, engine.py) the block scheduler must place its clusters BEFORE the next conv layer's 148 CTAs,
-    // otherwise the recurrence only starts when the other stream runs dry and nothing overlaps (flag 10)
+    // Option (flag 10, default off): the BiLSTM recurrence on a high-priority side stream (fork / join by events around
+    // the launch), so that the block scheduler places its clusters before another engine's next conv layer.  Measured
+    // with and without: no difference once the replicas are linked (b200ocr_run_after)
     // b200ocr_run_after: `front_done` is recorded when this engine's walk reaches its first recurrence; a walk waits
     // for the `front_done` of `after` first.  `followers` = engines whose `after` is this one (cleared on destroy)
     cudaEvent_t front_done = nullptr;
@@ -1445,6 +1444,24 @@ int b200ocr_profile_read(b200ocr_engine_t* e, int32_t capacity, int32_t* tags, i
         float t = 0.f;
         CU_TRY(e, cudaEventElapsedTime(&t, e->prof[i].a, e->prof[i].b));
         tags[i] = e->prof[i].tag; layers[i] = e->prof[i].layer; ms[i] = t;
+    }
+    for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.clear();
+    return B200OCR_OK;
+}
+
+int b200ocr_profile_read_since(b200ocr_engine_t* e, void* reference, int32_t capacity, int32_t* tags, int32_t* layers,
+                               float* start_ms, float* end_ms, int32_t* count) {
+    if (!e || !count || !reference) return B200OCR_E_INVALID;
+    CU_TRY(e, cudaDeviceSynchronize());
+    cudaEvent_t ref = static_cast<cudaEvent_t>(reference);
+    const int n = static_cast<int>(e->prof.size());
+    *count = n;
+    for (int i = 0; i < n && i < capacity; ++i) {
+        float a = 0.f, b = 0.f;
+        CU_TRY(e, cudaEventElapsedTime(&a, ref, e->prof[i].a));
+        CU_TRY(e, cudaEventElapsedTime(&b, ref, e->prof[i].b));
+        tags[i] = e->prof[i].tag; layers[i] = e->prof[i].layer; start_ms[i] = a; end_ms[i] = b;
     }
     for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     e->prof.clear();

@@ -209,6 +209,21 @@ class LineRecognizer:
         k = min(count.value, capacity)
         return tags[:k], layers[:k], ms[:k]
 
+    def profile_read_since(self, reference, capacity=4096):
+        """Timeline variant: `reference` a recorded torch.cuda.Event(enable_timing=True); -> tags, layers, start_ms,
+        end_ms relative to it."""
+        tags = np.zeros(capacity, dtype=np.int32)
+        layers = np.zeros(capacity, dtype=np.int32)
+        t0 = np.zeros(capacity, dtype=np.float32)
+        t1 = np.zeros(capacity, dtype=np.float32)
+        count = C.c_int32()
+        _lib.check(self._lib.b200ocr_profile_read_since(self._h, C.c_void_p(reference.cuda_event), capacity,
+                                                        tags.ctypes.data_as(C.c_void_p), layers.ctypes.data_as(C.c_void_p),
+                                                        t0.ctypes.data_as(C.c_void_p), t1.ctypes.data_as(C.c_void_p),
+                                                        C.byref(count)), self._h)
+        k = min(count.value, capacity)
+        return tags[:k], layers[:k], t0[:k], t1[:k]
+
     def debug_forward_prefix(self, crops, n_layers):
         n, h, w, _ = crops.shape
         self.reserve(n, w)

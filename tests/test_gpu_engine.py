@@ -474,3 +474,34 @@ def test_recycled_pinned_result_blocks(tmp_path):
     assert pool.stats['hits'] >= 2 and pool.registered == held                    # served from the returned blocks
     for a, b in zip(again[1], first):
         assert np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+
+
+def test_two_linked_replicas_give_the_single_engine_results(tmp_path, golden_dir):
+    """replicas=2: batches alternate between two native engines on two streams, linked by b200ocr_run_after; results
+    (strings, sparse logits, coords) must be those of one engine on one stream, in the caller's order, and unlinking or
+    destroying one engine of the ring must leave the other usable."""
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    spec = cases.ENGINE_CASES['lstm']
+    js = write_engine_json(tmp_path, 'lstm')
+    net = make_case_net('lstm')
+    rng = np.random.default_rng(11)
+    lines = [rng.integers(0, 256, size=(40, int(w), 3), dtype=np.uint8) for w in rng.integers(40, 900, size=70)]
+    one = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=8, precision='fp16f8', module=net)
+    two = B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=8, precision='fp16f8', module=net, replicas=2)
+    assert len(two._models) == 2
+    a = one.process_lines([l.copy() for l in lines])
+    for _ in range(2):                                   # second pass: every slot and both engines reused
+        b = two.process_lines([l.copy() for l in lines])
+        assert a[0] == b[0] and [list(c) for c in a[2]] == [list(c) for c in b[2]]
+        for x, y in zip(a[1], b[1]):
+            assert x.shape == y.shape and np.array_equal(x.indptr, y.indptr) and np.array_equal(x.indices, y.indices)
+            assert np.array_equal(x.data, y.data)
+    two._models[0].run_after(None)                       # open the ring: still correct
+    assert two.process_lines([l.copy() for l in lines], no_logits=True)[0] == a[0]
+    two._models[0].run_after(two._models[1])
+    first = two._models.pop(0)                           # destroy one engine of the ring while linked
+    two.model = two._models[0]
+    two._run_streams = None
+    two._slots = None
+    first.close()
+    assert two.process_lines([l.copy() for l in lines], no_logits=True)[0] == a[0]
