@@ -141,7 +141,7 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* w) {
 }
 __device__ __forceinline__ void epi_store32_v8(const uint32_t (&r)[32], int n0, float acc_scale, const float* s_bias,
                                                const float* s_scale, const float* s_shift, bool has_affine, int act,
-                                               __half* orow, int cout, int fmt) {
+                                               __half* orow, int cout, int fmt, bool skip_lo = false) {
     uint32_t ph[16], pl[16];
     epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, fmt, ph, pl);
     uint8_t* rec = reinterpret_cast<uint8_t*>(orow);
@@ -151,7 +151,7 @@ __device__ __forceinline__ void epi_store32_v8(const uint32_t (&r)[32], int n0, 
         st_global_v8(rec + cout * 2 + n0 * 2, pl);
         st_global_v8(rec + cout * 2 + n0 * 2 + 32, pl + 8);
     } else if (fmt == ACT_F16_F8) {
-        st_global_v8(rec + cout * 2 + n0, pl);
+        if (!skip_lo) st_global_v8(rec + cout * 2 + n0, pl);      // lo': unread by a weight-side-only consumer
         st_global_v8(rec + cout * 3 + n0, pl + 8);
     }
 }

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
                                                               const uint2* __restrict__ wfrag,
                                                               const float* __restrict__ oscale,
                                                               const float* __restrict__ bias, int act, int fmt,
-                                                              __half* __restrict__ out,
+                                                              __half* __restrict__ out, int skip_lo,
                                                               const __grid_constant__ CUtensorMap tm_in) {
     constexpr int NT = COUT / 8;
     const int planes = act_planes(fmt);
@@ -214,6 +214,9 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
                 uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row) * w + w0 + pb) * rec);
                 for (int i = lane; i < npx * chunks; i += 32) {
                     const int px = i / chunks, c = i - px * chunks;
+                    // skip_lo (ACT_F16_F8): the consumer multiplies with weight-side correction only and never reads
+                    // the lo' plane (chunks [NT, NT + NT/2) of the record) -- a quarter of the bytes stays unwritten
+                    if (skip_lo && c >= NT && c < NT + NT / 2) continue;
                     dst[i] = w_stage[px * chunks + (c ^ (px & (chunks - 1)))];
                 }
             }
@@ -262,8 +265,9 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
 }
 
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
-                                  const float* bias, int cout, int act, int fmt, __half* out, int staging,
+                                  const float* bias, int cout, int act, int fmt, __half* out, int skip_lo, int staging,
                                   const CUtensorMap* tm_in, cudaStream_t stream) {
+    if (fmt != ACT_F16_F8) skip_lo = 0;
     const int planes = act_planes(fmt);
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
@@ -281,7 +285,7 @@ cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const 
     static const CUtensorMap no_map = {};
     const CUtensorMap& tm = tm_in ? *tm_in : no_map;
 #define CFM_LAUNCH(C, S) \
-    conv_first_mma_kernel<C, S><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out, tm)
+    conv_first_mma_kernel<C, S><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out, skip_lo, tm)
 #define CFM_STAGE(C)                                        \
     switch (staging) {                                      \
         case STAGE_TMA: CFM_LAUNCH(C, STAGE_TMA); break;    \

@@ -129,6 +129,11 @@ struct b200ocr_engine {
     bool lstm_priority = false;
     cudaStream_t hi_stream = nullptr;
     cudaEvent_t hi_fork = nullptr, hi_join = nullptr;
+    // Option (flag 11, default off): a producer whose consumer multiplies with weight-side correction only does not
+    // write the lo' plane of its ACT_F16_F8 records -- a quarter of those layers' write traffic.  Measured: no gain
+    // (profiles/r02D_lean_records_ab.json; the layers are not write-bound and holes in the records cost as much as
+    // the bytes they save)
+    bool lean_records = false;
     int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
     bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
@@ -295,6 +300,7 @@ struct EpiOut {
     const float* residual = nullptr;
     int32_t* best = nullptr;
     float *fmax = nullptr, *flse = nullptr, *fprob = nullptr;
+    bool skip_lo = false;   // the consumer of these records never reads their lo' plane
 };
 
 // input: fp16 NHWC [in.n][in.h][in.w][planes * g.cin]
@@ -316,6 +322,7 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     p.bias = g.bias; p.post_scale = g.post_scale; p.post_shift = g.post_shift; p.residual = o.residual;
     p.out_h = o.out_h; p.out_cstride = g.cout * e->planes; p.out_lo_off = e->planes == 2 ? g.cout : -1;
     p.out_fmt = e->fmt;
+    p.out_skip_lo = (o.skip_lo && e->fmt == ACT_F16_F8 && e->lean_records) ? 1 : 0;
     p.acc_scale = e->fmt == ACT_F16_F8 ? 1.f / kF8Scale : 1.f;
     p.out_f32 = o.out_f32; p.best = o.best; p.fmax = o.fmax; p.flse = o.flse; p.fprob = o.fprob;
     {
@@ -405,6 +412,14 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
         return 0;
     };
     const int L = std::min<int>(n_layers, e->layers.size());
+    // does layer li + 1 (executed in this walk, as a tensor-core contraction over layer li's records) skip the
+    // activation-side correction?  Then layer li need not write the lo' plane.
+    auto next_skips_lo = [&](int li) {
+        if (e->fmt != ACT_F16_F8 || !e->lean_records || e->use_ref || li + 1 >= L) return false;
+        const LayerRT& nx = e->layers[li + 1];
+        if (nx.kind != B200OCR_CONV && nx.kind != B200OCR_BILSTM && nx.kind != B200OCR_CTC_HEAD) return false;
+        return nx.g.corr != CORR_BOTH && e->ref_only_layer != li + 1;
+    };
     if (!dry && crops && e->after && e->after->front_done)
         CU_TRY(e, cudaStreamWaitEvent(st, e->after->front_done, 0));
     e->front_recorded = false;
@@ -446,8 +461,8 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                                                         e->fmt, rec, st));
                         else
                             CU_TRY(e, launch_conv_first_mma(src, n_lines, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
-                                                            ly.cout0, ly.act, e->fmt, rec, staging,
-                                                            staging == 2 ? &tm_crops : nullptr, st));
+                                                            ly.cout0, ly.act, e->fmt, rec, next_skips_lo(li) ? 1 : 0,
+                                                            staging, staging == 2 ? &tm_crops : nullptr, st));
                         e->launches++;
                         return 0;
                     };
@@ -506,6 +521,7 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                         if (hbytes(e, os) > e->hbuf_bytes[slot]) return fail(e, B200OCR_E_WORKSPACE, "workspace too small");
                         eo.out_h = static_cast<__half*>(e->hbuf[slot]);
                     }
+                    eo.skip_lo = next_skips_lo(li);
                 }
                 if (!dry) {
                     Shape chk;
@@ -1480,6 +1496,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     else if (flag == 8) e->attention_tc = value != 0;
     else if (flag == 9) e->igemm_dbg = value;
     else if (flag == 10) e->lstm_priority = value != 0;
+    else if (flag == 11) e->lean_records = value != 0;
     else return fail(e, B200OCR_E_INVALID, "unknown debug flag %d", flag);
     return B200OCR_OK;
 }

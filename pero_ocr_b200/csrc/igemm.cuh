@@ -54,6 +54,7 @@ struct IgemmParams {
     float* flse;
     float* fprob;             // best-class probability under the reference's sparsified softmax (or null)
     int* tile_counter;        // dynamic tile scheduler: zeroed device counter of this launch (null = static striding)
+    int out_skip_lo;          // ACT_F16_F8 output: the consumer never reads the lo' plane (weight-side correction only)
     int dbg;                  // bring-up switches (B200OCR_IGEMM_DBG, flag 9): 1 = skip epilogue stores, 2 = skip MMA issue, 4 = 16-byte instead of 256-bit epilogue stores, 8 = 4 weight stages in the BN = 128 halo kernel
 };
 

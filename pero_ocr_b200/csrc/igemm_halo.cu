@@ -347,7 +347,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     p.cout, FMT);
                     else
                         epi_store32_v8(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act,
-                                       orow, p.cout, FMT);
+                                       orow, p.cout, FMT, p.out_skip_lo != 0);
                 }
             }
             ptx::tc_fence_before();

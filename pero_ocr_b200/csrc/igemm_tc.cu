@@ -268,7 +268,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if (p.dbg & 4)                  // A/B: 16-byte stores
                             epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
                         else
-                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
+                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT, p.out_skip_lo != 0);
                     }
                 }
             } else if (p.epi == EPI_CTC) {

@@ -20,7 +20,7 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
 // staging: how the uint8 patch reaches shared memory -- 0 plain loads, 1 cp.async, 2 TMA (tm_in: 3-D uint32 tensor map
 // {W*3/4, H, N}, box {104, 6, 1}, no swizzle); the bulk variants need W % 16 == 0 and fall back to 0 otherwise.
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
-                                  const float* bias, int cout, int act, int fmt, __half* out, int staging,
+                                  const float* bias, int cout, int act, int fmt, __half* out, int skip_lo, int staging,
                                   const CUtensorMap* tm_in, cudaStream_t stream);
 size_t conv_first_wfrag_words(int cout);
 void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* oscale);

@@ -25,8 +25,8 @@ out = {}
 ref = None
 res = {'workload': 'config 2 step, 256 x 40 x 1344, fp16f8 autotuned', 'runs': []}
 for rnd in range(2):
-    for variant, name in ((4, 'v4'), (0, 'v8'), (8, 'v8 + 4 weight stages at BN=128')):
-        rec.set_flag(9, variant)
+    for variant, name in ((0, 'complete records'), (1, "lo' plane unwritten where unread")):
+        rec.set_flag(11, variant)
         o = rec.forward(crops, want_logits=True, out={})
         lg = o['logits'].clone()
         if ref is None:
@@ -45,5 +45,5 @@ for rnd in range(2):
                             'per_launch_ms': [round(float(x), 4) for x in per],
                             'launch_layer': [int(x) for x in lidx[:n]], 'launch_tag': [int(x) for x in tags[:n]],
                             'logits_identical': same})
-rec.set_flag(9, 0)
+rec.set_flag(11, 0)
 print(json.dumps(res, indent=1))
