@@ -342,7 +342,7 @@ def write_engine_json(n_chars=118):
     return js
 
 
-def bench_config3(dev, peak_tf, with_cpu, lines_total=512):
+def bench_config3(dev, peak_tf, with_cpu, lines_total=1536):
     """BASELINE.json config 3: Transformer-encoder variant + CTC prefix beam (k = 16), batch = 256 synthetic 40x1280
     crops, through engine.decode_lines (host crops in, BagOfHypotheses out; the logits never leave the GPU)."""
     import torch

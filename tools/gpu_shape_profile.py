@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 from pero_ocr_b200 import netdesc, synthetic          # noqa: E402
 from pero_ocr_b200.engine import LineRecognizer       # noqa: E402
 
-net = synthetic.make_net('lstm', 120, seed=0, out_gain=6.0)
+kind = os.environ.get('B200OCR_KIND', 'lstm')
+net = synthetic.make_net(kind, 120, seed=0, out_gain=6.0)
 layers, _ = netdesc.describe_line_net(net)
 rec = LineRecognizer(layers, precision='fp16f8')
 rec.autotune_precision(budget=5e-4)
@@ -29,4 +30,5 @@ for n, w in zip(args[0::2], args[1::2]):
     k = len(ms) // 5
     per = ms.reshape(5, k).mean(axis=0)
     print(json.dumps({'lines': n, 'width': w, 'step_ms': round(float(ms.sum() / 5), 3),
-                      'per_launch_ms': [round(float(x), 3) for x in per], 'tags': [int(t) for t in tags[:k]]}))
+                      'per_launch_ms': [round(float(x), 3) for x in per], 'tags': [int(t) for t in tags[:k]],
+                      'layers': [int(t) for t in lidx[:k]]}))
