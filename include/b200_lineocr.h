@@ -364,9 +364,9 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
  * fourth weight stage in the BN = 128 halo kernel;
  * flag 10: the BiLSTM recurrence is launched on the engine's high-priority side stream (fork / join by events).
  * Default off: with b200ocr_run_after the recurrence already runs beside the other engine's convolutions, and
- * the priority changed nothing measurable (profiles/r02B_replica_link_ab.md);
+ * the priority changed nothing measurable (profiles/r02x_replica_link_ab.md);
  * flag 11: a layer whose consumer multiplies with weight-side correction only (b200ocr_set_layer_correction) does
- * not write the lo' plane of its activation records (default off: measured, no gain -- profiles/r02D_lean_records_ab.json). */
+ * not write the lo' plane of its activation records (default off: measured, no gain -- profiles/r02y_lean_records_ab.json). */
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value);
 /* Runs only the first `n_layers` layers of the recogniser on `crops` and copies the fp32-expanded (hi + lo)
  * output activation of the last one to HOST memory `out` (NHWC); shape4 receives {n, h, w, c}.  Synchronises. */

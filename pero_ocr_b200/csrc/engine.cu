@@ -131,7 +131,7 @@ struct b200ocr_engine {
     cudaEvent_t hi_fork = nullptr, hi_join = nullptr;
     // Option (flag 11, default off): a producer whose consumer multiplies with weight-side correction only does not
     // write the lo' plane of its ACT_F16_F8 records -- a quarter of those layers' write traffic.  Measured: no gain
-    // (profiles/r02D_lean_records_ab.json; the layers are not write-bound and holes in the records cost as much as
+    // (profiles/r02y_lean_records_ab.json; the layers are not write-bound and holes in the records cost as much as
     // the bytes they save)
     bool lean_records = false;
     int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
