@@ -199,3 +199,53 @@ def test_pinned_pool_lends_and_recycles_blocks():
     del again
     pool.trim()
     assert pool.registered == 0 and not pool.free
+
+
+def test_batch_pipeline_runs_across_jobs_in_order():
+    """_run_jobs (the driver behind process_lines / process_baselines / process_pages): several jobs through ONE batch
+    pipeline -- every job's results are those of running it alone, jobs complete in order, the next job is pulled and
+    its first batch submitted BEFORE the previous job's last batch is collected, and empty jobs pass through."""
+    eng = _host_only_engine('lstm')
+    lines = cases.engine_lines('lstm')
+    alone = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+    alone3 = eng.process_lines([l.copy() for l in lines[:3]], sparse_logits=False)
+    events = []
+    submit, collect = eng._submit, eng._collect
+
+    def traced_submit(k, *a, **kw):
+        events.append(('submit', k))
+        return submit(k, *a, **kw)
+
+    def traced_collect(ticket):
+        events.append(('collect', ticket[0]))
+        return collect(ticket)
+
+    eng._submit, eng._collect = traced_submit, traced_collect
+    pulled = []
+
+    def jobs():
+        for j, part in enumerate((lines, [], lines[:3], lines)):
+            pulled.append((j, len(events)))
+            part = list(part)
+            yield [l.shape[1] for l in part], (lambda chunk, width, part=part: {'packed': [part[i] for i in chunk]})
+
+    results = list(eng._run_jobs(jobs(), False, False, False, False))
+    assert len(results) == 4 and results[1] == ([], [], [])
+    for got, want in ((results[0], alone), (results[2], alone3), (results[3], alone)):
+        assert got[0] == want[0] and len(got[1]) == len(want[1])
+        for a, b in zip(got[1], want[1]):
+            assert np.array_equal(a, b)
+        assert [list(c) for c in got[2]] == [list(c) for c in want[2]]
+    n_batches = sum(1 for e in events if e[0] == 'submit')
+    assert n_batches == sum(1 for e in events if e[0] == 'collect')
+    # job 3 (the last) was pulled while batches of earlier jobs were still uncollected
+    at = pulled[3][1]
+    assert sum(1 for e in events[:at] if e[0] == 'submit') > sum(1 for e in events[:at] if e[0] == 'collect')
+    # slots rotate over 2 x replicas and a slot is never resubmitted before it was collected
+    busy = set()
+    for kind, k in events:
+        if kind == 'submit':
+            assert k not in busy
+            busy.add(k)
+        else:
+            busy.discard(k)
