@@ -86,6 +86,7 @@ typedef struct b200ocr_layer {
     const float* norm1_b;
     const float* norm2_w;
     const float* norm2_b;
+    float act_slope;         /* B200OCR_ACT_LEAKY_RELU: negative slope (nn.LeakyReLU.negative_slope); 0 = the default 0.01 */
 } b200ocr_layer_t;
 
 typedef struct b200ocr_net_desc {

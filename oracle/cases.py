@@ -27,6 +27,9 @@ ENGINE_CASES['lstm_wide'] = dict(net='lstm', classes=120, seed=0, out_gain=6.0, 
 # characters + '<BLANK>' (decoding_itf.py:49-50)
 ENGINE_CASES['lstm_c119'] = dict(net='lstm', classes=120, json_chars=119, seed=7, out_gain=6.0, net_kw={},
                                  engine_batch_size=2, widths=[300, 212, 97, 160])
+# a second recogniser family: other module names and nesting, LeakyReLU slopes 0.1-0.3, one BiLSTM layer, Conv1d head
+ENGINE_CASES['lstm_alt'] = dict(net='lstm_alt', classes=120, seed=11, out_gain=6.0, net_kw={}, engine_batch_size=2,
+                                widths=[320, 300, 211, 96, 450, 40])
 PARSENET_CASE = dict(seed=5, downsample=2, height=250, width=330)
 # BASELINE config 4 size: a 3000 x 4000 page at DOWNSAMPLE = 4 -> canvas 768 x 1024, and the adaptive second pass
 # (torch_parsenet.py:60-93); the stand-in's head is biased so that the first pass "detects" 20 px text (>15) and the

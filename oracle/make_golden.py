@@ -455,6 +455,7 @@ def main():
                  ('engine_transformer', lambda: golden_engine('transformer', tmp)),
                  ('engine_lstm_wide', lambda: golden_engine('lstm_wide', tmp)),
                  ('engine_lstm_c119', lambda: golden_engine('lstm_c119', tmp)),
+                 ('engine_lstm_alt', lambda: golden_engine('lstm_alt', tmp)),
                  ('parsenet', lambda: golden_parsenet(tmp)), ('parsenet_page', lambda: golden_parsenet_page(tmp)),
                  ('confidence', golden_confidence),
                  ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder),

@@ -32,6 +32,7 @@ class Layer(C.Structure):
         ('in_proj_w', _FP), ('in_proj_b', _FP), ('out_proj_w', _FP), ('out_proj_b', _FP),
         ('lin1_w', _FP), ('lin1_b', _FP), ('lin2_w', _FP), ('lin2_b', _FP),
         ('norm1_w', _FP), ('norm1_b', _FP), ('norm2_w', _FP), ('norm2_b', _FP),
+        ('act_slope', C.c_float),
     ]
 
 

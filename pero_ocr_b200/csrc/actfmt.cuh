@@ -64,23 +64,23 @@ __device__ __forceinline__ float act_load(const __half* rec, int C, int i, int f
 
 // Tensor-core epilogue: 32 consecutive channels [n0, n0 + 32) of one pixel.  r = raw fp32 accumulators (after any
 // max-pool), out = acc * acc_scale + bias -> activation -> optional affine -> record planes, 16-byte stores.
-__device__ __forceinline__ float epi_act(float v, int act) {
+__device__ __forceinline__ float epi_act(float v, int act, float slope) {
     if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    if (act == 2) return v > 0.f ? v : slope * v;
     return v;
 }
 // r -> packed record words of the 32 channels: ph = 16 words fp16 hi; pl = 16 words fp16 lo (HILO) or 8 words lo' +
 // 8 words hi8 (F8).
 __device__ __forceinline__ void epi_pack32(const uint32_t (&r)[32], int n0, float acc_scale, const float* s_bias,
                                            const float* s_scale, const float* s_shift, bool has_affine, int act,
-                                           int fmt, uint32_t (&ph)[16], uint32_t (&pl)[16]) {
+                                           float slope, int fmt, uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + j);
         float v[4] = {fmaf(__uint_as_float(r[j]), acc_scale, b4.x), fmaf(__uint_as_float(r[j + 1]), acc_scale, b4.y),
                       fmaf(__uint_as_float(r[j + 2]), acc_scale, b4.z), fmaf(__uint_as_float(r[j + 3]), acc_scale, b4.w)};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = epi_act(v[e], act);
+        for (int e = 0; e < 4; ++e) v[e] = epi_act(v[e], act, slope);
         if (has_affine) {
             const float4 a4 = *reinterpret_cast<const float4*>(s_scale + n0 + j);
             const float4 s4 = *reinterpret_cast<const float4*>(s_shift + n0 + j);
@@ -109,9 +109,9 @@ __device__ __forceinline__ void epi_pack32(const uint32_t (&r)[32], int n0, floa
 
 __device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], int n0, float acc_scale, const float* s_bias,
                                             const float* s_scale, const float* s_shift, bool has_affine, int act,
-                                            __half* orow, int cout, int fmt) {
+                                            float slope, __half* orow, int cout, int fmt) {
     uint32_t ph[16], pl[16];
-    epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, fmt, ph, pl);
+    epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, slope, fmt, ph, pl);
     uint4* dst = reinterpret_cast<uint4*>(orow + n0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) dst[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
@@ -141,9 +141,9 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* w) {
 }
 __device__ __forceinline__ void epi_store32_v8(const uint32_t (&r)[32], int n0, float acc_scale, const float* s_bias,
                                                const float* s_scale, const float* s_shift, bool has_affine, int act,
-                                               __half* orow, int cout, int fmt, bool skip_lo = false) {
+                                               float slope, __half* orow, int cout, int fmt, bool skip_lo = false) {
     uint32_t ph[16], pl[16];
-    epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, fmt, ph, pl);
+    epi_pack32(r, n0, acc_scale, s_bias, s_scale, s_shift, has_affine, act, slope, fmt, ph, pl);
     uint8_t* rec = reinterpret_cast<uint8_t*>(orow);
     st_global_v8(rec + n0 * 2, ph);
     st_global_v8(rec + n0 * 2 + 32, ph + 8);

@@ -45,9 +45,9 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ float cfm_act(float v, int act) {
+__device__ __forceinline__ float cfm_act(float v, int act, float slope) {
     if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    if (act == 2) return v > 0.f ? v : slope * v;
     return v;
 }
 
@@ -61,8 +61,8 @@ template <int COUT, int STAGE>
 __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                               const uint2* __restrict__ wfrag,
                                                               const float* __restrict__ oscale,
-                                                              const float* __restrict__ bias, int act, int fmt,
-                                                              __half* __restrict__ out, int skip_lo,
+                                                              const float* __restrict__ bias, int act, float slope,
+                                                              int fmt, __half* __restrict__ out, int skip_lo,
                                                               const __grid_constant__ CUtensorMap tm_in) {
     constexpr int NT = COUT / 8;
     const int planes = act_planes(fmt);
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int ch = nt * 8 + tig * 2;
-                    const float v0 = cfm_act(fmaf(acc[nt][2 * half], s_sc[ch], s_b[ch]), act);
-                    const float v1 = cfm_act(fmaf(acc[nt][2 * half + 1], s_sc[ch + 1], s_b[ch + 1]), act);
+                    const float v0 = cfm_act(fmaf(acc[nt][2 * half], s_sc[ch], s_b[ch]), act, slope);
+                    const float v1 = cfm_act(fmaf(acc[nt][2 * half + 1], s_sc[ch + 1], s_b[ch + 1]), act, slope);
                     const __half2 h2 = __floats2half2_rn(v0, v1);
                     reinterpret_cast<uint32_t*>(my + (nt ^ sw))[tig] = *reinterpret_cast<const uint32_t*>(&h2);
                     if (fmt != ACT_F16) {
@@ -265,7 +265,8 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
 }
 
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
-                                  const float* bias, int cout, int act, int fmt, __half* out, int skip_lo, int staging,
+                                  const float* bias, int cout, int act, float slope, int fmt, __half* out, int skip_lo,
+                                  int staging,
                                   const CUtensorMap* tm_in, cudaStream_t stream) {
     if (fmt != ACT_F16_F8) skip_lo = 0;
     const int planes = act_planes(fmt);
@@ -285,7 +286,7 @@ cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const 
     static const CUtensorMap no_map = {};
     const CUtensorMap& tm = tm_in ? *tm_in : no_map;
 #define CFM_LAUNCH(C, S) \
-    conv_first_mma_kernel<C, S><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, fmt, out, skip_lo, tm)
+    conv_first_mma_kernel<C, S><<<grid, CFM_PX, dyn, stream>>>(in, n, h, w, wf, oscale, bias, act, slope, fmt, out, skip_lo, tm)
 #define CFM_STAGE(C)                                        \
     switch (staging) {                                      \
         case STAGE_TMA: CFM_LAUNCH(C, STAGE_TMA); break;    \

@@ -48,6 +48,7 @@ struct Gemm {  // one dense contraction: packed fp16 weights [plane][tap][cout_p
     CUtensorMap tmB;
     int bn_halo = 0;       // tile N of the halo-reuse kernel (0 = not applicable)
     CUtensorMap tmB_halo;
+    float act_slope = 0.01f;   // LeakyReLU negative slope of the layer's fused activation
     int corr = CORR_BOTH;  // fp16f8 only: correction terms of the e5m2 pass (b200ocr_set_layer_correction)
 };
 
@@ -312,7 +313,7 @@ int run_gemm(b200ocr_engine* e, const Gemm& g, const __half* in, Shape in_s, int
     p.kh = g.kh; p.kw = g.kw; p.pad_h = g.pad_h; p.pad_w = g.pad_w;
     p.h_out = in_s.h + 2 * g.pad_h - g.kh + 1;
     p.w_out = in_s.w + 2 * g.pad_w - g.kw + 1;
-    p.pool_h = pool_h; p.pool_w = pool_w; p.act = act; p.npass = e->npass;
+    p.pool_h = pool_h; p.pool_w = pool_w; p.act = act; p.act_slope = g.act_slope; p.npass = e->npass;
     p.corr_mode = e->fmt == ACT_F16_F8 ? g.corr : CORR_BOTH;
     if (p.h_out <= 0 || p.w_out <= 0) return fail(e, B200OCR_E_INVALID, "empty convolution output");
     if (p.h_out % pool_h || p.w_out % pool_w)
@@ -457,11 +458,11 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                             if (int s = make_map_crops(e, &tm_crops, src, n_lines, cur.h, cur.w)) return s;
                         ProfScope ps(e, st, PROF_CONV_FIRST);
                         if (e->use_ref)   // CUDA-core fp32 cross-check kernel
-                            CU_TRY(e, launch_conv_first(src, n_lines, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act,
+                            CU_TRY(e, launch_conv_first(src, n_lines, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act, ly.g.act_slope,
                                                         e->fmt, rec, st));
                         else
                             CU_TRY(e, launch_conv_first_mma(src, n_lines, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
-                                                            ly.cout0, ly.act, e->fmt, rec, next_skips_lo(li) ? 1 : 0,
+                                                            ly.cout0, ly.act, ly.g.act_slope, e->fmt, rec, next_skips_lo(li) ? 1 : 0,
                                                             staging, staging == 2 ? &tm_crops : nullptr, st));
                         e->launches++;
                         return 0;
@@ -780,6 +781,7 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
         const b200ocr_layer_t& d = desc->layers[i];
         LayerRT& ly = e->layers[i];
         ly.kind = d.kind; ly.act = d.act;
+        ly.g.act_slope = d.act_slope > 0.f ? d.act_slope : 0.01f;
         ly.pool_h = d.pool_h > 0 ? d.pool_h : 1;
         ly.pool_w = d.pool_w > 0 ? d.pool_w : 1;
         int s = 0;

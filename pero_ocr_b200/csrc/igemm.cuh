@@ -30,6 +30,7 @@ struct IgemmParams {
     int h_out, w_out;  // conv output geometry before pooling
     int pool_h, pool_w;
     int act;
+    float act_slope;          // LeakyReLU negative slope (act == 2)
     int npass;  // 1 (fp16), 3 (fp16x3: hi*hi + hi*lo + lo*hi) or 2 (fp16 hi*hi + one e5m2 correction pass, actfmt.cuh)
     float acc_scale;  // epilogue multiplies the accumulator by this before the bias (2^-11 when npass == 2, else 1)
     // npass == 2 only: which first-order correction terms the e5m2 pass evaluates.  The pass contracts the

@@ -343,10 +343,10 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (p.dbg & 1) continue;                // bring-up: time the pipeline without the global stores
                     if (!writer) continue;
                     if (p.dbg & 4)                          // A/B: 16-byte stores
-                        epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow,
+                        epi_store32(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, p.act_slope, orow,
                                     p.cout, FMT);
                     else
-                        epi_store32_v8(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act,
+                        epi_store32_v8(rr == 0 ? r0 : r1, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, p.act_slope,
                                        orow, p.cout, FMT, p.out_skip_lo != 0);
                 }
             }

@@ -52,9 +52,9 @@ __device__ __forceinline__ SegCoord seg_coord(const IgemmParams& p, int seg) {
     return c;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    if (act == 2) return v > 0.f ? v : slope * v;
     return v;
 }
 
@@ -266,9 +266,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (writer) {
                         if (p.dbg & 4)                  // A/B: 16-byte stores
-                            epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT);
+                            epi_store32(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, p.act_slope, orow, p.cout, FMT);
                         else
-                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, orow, p.cout, FMT, p.out_skip_lo != 0);
+                            epi_store32_v8(r, n0, p.acc_scale, s_bias, s_scale, s_shift, has_affine, p.act, p.act_slope, orow, p.cout, FMT, p.out_skip_lo != 0);
                     }
                 }
             } else if (p.epi == EPI_CTC) {
@@ -372,7 +372,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                                 for (int e = 0; e < 8; ++e)
                                     w[e] = __float_as_uint(apply_act(
-                                        fmaf(__uint_as_float(r[j + e]), p.acc_scale, s_bias[n0 + j + e]), p.act));
+                                        fmaf(__uint_as_float(r[j + e]), p.acc_scale, s_bias[n0 + j + e]), p.act, p.act_slope));
                                 st_global_v8(dst + j, w);
                             }
                         } else if ((p.cout & 3) == 0) {
@@ -387,8 +387,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                         v.z = fmaf(__uint_as_float(r[j + 2]), p.acc_scale, b.z);
                                         v.w = fmaf(__uint_as_float(r[j + 3]), p.acc_scale, b.w);
                                     }
-                                    v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-                                    v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+                                    v.x = apply_act(v.x, p.act, p.act_slope); v.y = apply_act(v.y, p.act, p.act_slope);
+                                    v.z = apply_act(v.z, p.act, p.act_slope); v.w = apply_act(v.w, p.act, p.act_slope);
                                     if (res) {
                                         const float4 e = __ldg(reinterpret_cast<const float4*>(res + j));
                                         v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
@@ -401,7 +401,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int j = 0; j < 32; ++j) {
                                 if (n0 + j < p.cout) {
                                     float v = fmaf(__uint_as_float(r[j]), p.acc_scale, s_bias[n0 + j]);
-                                    v = apply_act(v, p.act);
+                                    v = apply_act(v, p.act, p.act_slope);
                                     if (res) v += __ldg(res + j);
                                     dst[j] = v;
                                 }

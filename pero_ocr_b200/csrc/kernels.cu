@@ -7,9 +7,9 @@
 
 namespace {
 
-__device__ __forceinline__ float act_fn(float v, int act) {
+__device__ __forceinline__ float act_fn(float v, int act, float slope) {
     if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : 0.01f * v;
+    if (act == 2) return v > 0.f ? v : slope * v;
     return v;
 }
 
@@ -25,7 +25,7 @@ constexpr int CF_ROWS = 4;
 template <int COUT>
 __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                           const float* __restrict__ w_t, const float* __restrict__ bias,
-                                                          int act, int fmt, __half* __restrict__ out) {
+                                                          int act, float slope, int fmt, __half* __restrict__ out) {
     const int planes = act_planes(fmt);
     __shared__ float s_in[CF_ROWS + 2][CF_PX + 2][3];
     __shared__ __align__(16) float s_w[27 * COUT];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(CF_PX) conv_first_kernel(const uint8_t* __rest
                 for (int e = 0; e < 16; e += 4) {
                     float v[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = act_fn(acc[o + e + q] + s_b[o + e + q], act);
+                    for (int q = 0; q < 4; ++q) v[q] = act_fn(acc[o + e + q] + s_b[o + e + q], act, slope);
                     const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
                     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                     ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
@@ -322,7 +322,7 @@ __global__ void igemm_ref_kernel(const IgemmParams p, const __half* __restrict__
                 }
             }
             float v = fmaf(acc, p.acc_scale, p.bias ? p.bias[co] : 0.f);
-            if (p.epi != EPI_RES_F32) v = act_fn(v, p.act);
+            if (p.epi != EPI_RES_F32) v = act_fn(v, p.act, p.act_slope);
             result = fmaxf(result, v);
         }
     const size_t opix = (static_cast<size_t>(img) * Hp + hq) * Wp + wq;
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __res
 }  // namespace
 
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
-                              int act, int fmt, __half* out, cudaStream_t stream) {
+                              int act, float slope, int fmt, __half* out, cudaStream_t stream) {
     const int planes = act_planes(fmt);
     const int tiles_w = (w + CF_PX - 1) / CF_PX;
     const int grid = n * ((h + CF_ROWS - 1) / CF_ROWS) * tiles_w;
@@ -584,9 +584,9 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
         attr_done.mark();
     }
     switch (cout) {
-        case 64: conv_first_kernel<64><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
-        case 32: conv_first_kernel<32><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
-        case 16: conv_first_kernel<16><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, fmt, out); break;
+        case 64: conv_first_kernel<64><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, slope, fmt, out); break;
+        case 32: conv_first_kernel<32><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, slope, fmt, out); break;
+        case 16: conv_first_kernel<16><<<grid, CF_PX, dyn, stream>>>(in, n, h, w, w_t, bias, act, slope, fmt, out); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -12,7 +12,7 @@
 // (replaces the `/255` + permute of run_ocr, pytorch_ocr_engine.py:61-62, and the first conv of the blob).
 // w_t: fp32 [27][cout] (tap-major: (r*3+s)*3+c), cout <= 64.
 cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const float* w_t, const float* bias, int cout,
-                              int act, int fmt, __half* out, cudaStream_t stream);
+                              int act, float slope, int fmt, __half* out, cudaStream_t stream);
 
 // The same layer on warp-level tensor cores (conv_first.cu; the product path -- the kernel above is the fp32
 // cross-check).  conv_first_pack turns the PyTorch weight [cout][3][3][3] into per-lane mma.sync fragments
@@ -20,7 +20,8 @@ cudaError_t launch_conv_first(const uint8_t* in, int n, int h, int w, const floa
 // staging: how the uint8 patch reaches shared memory -- 0 plain loads, 1 cp.async, 2 TMA (tm_in: 3-D uint32 tensor map
 // {W*3/4, H, N}, box {104, 6, 1}, no swizzle); the bulk variants need W % 16 == 0 and fall back to 0 otherwise.
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,
-                                  const float* bias, int cout, int act, int fmt, __half* out, int skip_lo, int staging,
+                                  const float* bias, int cout, int act, float slope, int fmt, __half* out, int skip_lo,
+                                  int staging,
                                   const CUtensorMap* tm_in, cudaStream_t stream);
 size_t conv_first_wfrag_words(int cout);
 void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* oscale);

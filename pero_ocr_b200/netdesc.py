@@ -5,9 +5,10 @@ and ParseNet likewise (pero_ocr/layout_engines/torch_parsenet.py:11-15).  A Torc
 module tree (``original_name``, ``named_children``) and ``state_dict()``, so the same checkpoint file the reference
 loads is walked here and turned into the flat layer list of ``include/b200_lineocr.h``.  Supported vocabulary:
 
-  line recogniser:  ``conv`` = Sequential of Conv2d(3x3, pad 1) / ReLU / LeakyReLU / MaxPool2d / BatchNorm2d,
-                    ``agg`` = Conv2d(k = (H/8, 1)), ``agg_act``, then either ``lstm`` (bidirectional nn.LSTM) or
-                    ``input_norm`` + ``trans_encoder`` (post-LN nn.TransformerEncoder, ReLU), then ``out`` (Linear).
+  line recogniser:  any module tree (names and nesting are free) whose leaf modules, in registration order, are
+                    Conv2d(3x3, pad 1) / ReLU / LeakyReLU(any positive slope) / MaxPool2d / BatchNorm2d / Dropout,
+                    a Conv2d(k = (H/8, 1)) + activation, then either a bidirectional nn.LSTM or LayerNorm +
+                    post-LN nn.TransformerEncoder (ReLU), then Linear / Conv1d(k = 1) as the CTC head.
   page detector:    ``e1 e2 | pool | e3 e4 | pool | d1 d2 | head`` 3x3 convs + nearest x4 upsampling.
 
   TransformerOCR:   the state dict ``TransformerEngineLineOCR`` loads (transformer_ocr_engine.py:21-29) plus the
@@ -35,15 +36,25 @@ def _f32(t):
 
 
 def _act_code(m):
+    """-> (activation code, LeakyReLU negative slope or 0)."""
     n = _name(m)
     if n == 'ReLU':
-        return _lib.ACT_RELU
+        return _lib.ACT_RELU, 0.0
     if n == 'LeakyReLU':
         slope = float(getattr(m, 'negative_slope', 0.01))
-        if abs(slope - 0.01) > 1e-12:
-            raise ValueError(f'LeakyReLU slope {slope} not supported (kernels use 0.01)')
-        return _lib.ACT_LEAKY_RELU
+        if slope == 0.0:
+            return _lib.ACT_RELU, 0.0
+        if slope < 0.0:
+            raise ValueError(f'LeakyReLU slope {slope} < 0: the max-pool is fused BEFORE the activation, which needs a '
+                             f'monotone activation')
+        return _lib.ACT_LEAKY_RELU, slope
     raise ValueError(f'unsupported activation {n}')
+
+
+def _set_act(spec, m):
+    spec['act'], slope = _act_code(m)
+    if slope and slope != 0.01:              # 0.01 is the kernels' default (nn.LeakyReLU's own)
+        spec['act_slope'] = slope
 
 
 def _pair(v):
@@ -58,91 +69,148 @@ def _conv_spec(sd, prefix, first):
                 pad_h=(kh - 1) // 2, pad_w=(kw - 1) // 2, act=_lib.ACT_NONE, pool_h=1, pool_w=1, weight=w, bias=b)
 
 
+_LEAF_TYPES = {'Conv2d', 'Conv1d', 'ReLU', 'LeakyReLU', 'MaxPool2d', 'BatchNorm2d', 'Dropout', 'Dropout2d', 'Identity',
+               'LSTM', 'Linear', 'LayerNorm', 'TransformerEncoder'}
+
+
+def _leaves(module, prefix=''):
+    """(state-dict prefix, module) of the leaf modules in registration order; containers are expanded, whatever
+    their names and nesting."""
+    for name, m in module.named_children():
+        key = prefix + name
+        if _name(m) in _LEAF_TYPES or not any(True for _ in m.named_children()):
+            yield key, m
+        else:
+            yield from _leaves(m, key + '.')
+
+
 def describe_line_net(module):
-    """nn.Module or TorchScript module following the vocabulary above -> (layer specs, num_classes)."""
+    """nn.Module or TorchScript module -> (layer specs, num_classes).
+
+    The walk is driven by module TYPES and tensor shapes, not by attribute names: the leaf modules are taken in
+    registration order (the order `nn.Sequential` runs them and the order every recogniser family seen so far
+    registers them; the channel counts of consecutive layers are checked against each other, which catches a tree
+    registered out of order) and must spell
+        (Conv2d 3x3 pad 1 [ReLU | LeakyReLU] [MaxPool2d] [BatchNorm2d] | Dropout)+
+        Conv2d (k, 1) pad 0 [ReLU | LeakyReLU]                       -- height aggregation
+        LSTM (bidirectional, any number of layers)  |  LayerNorm + TransformerEncoder (post-LN, ReLU)
+        Linear | Conv1d k = 1 | Conv2d 1x1                           -- CTC head
+    """
     sd = {k: v for k, v in module.state_dict().items()}
-    children = dict(module.named_children())
     layers = []
     last_conv = None
-    for idx, (cname, m) in enumerate(children['conv'].named_children()):
+    stage = 'frontend'                       # -> 'agg' -> 'sequence' -> 'head' -> 'done'
+    feat = None
+    pending_norm = None
+    for key, m in _leaves(module):
         n = _name(m)
-        key = f'conv.{cname}'
-        if n == 'Conv2d':
-            spec = _conv_spec(sd, key, first=(last_conv is None and not layers))
-            if (spec['kh'], spec['kw']) != (3, 3):
-                raise ValueError('frontend convolutions must be 3x3')
-            layers.append(spec)
-            last_conv = spec
-        elif n in ('ReLU', 'LeakyReLU'):
-            if last_conv is None or last_conv['act'] != _lib.ACT_NONE or 'post_scale' in last_conv:
-                raise ValueError('activation must directly follow a convolution')
-            last_conv['act'] = _act_code(m)
-        elif n == 'MaxPool2d':
+        if n in ('Dropout', 'Dropout2d', 'Identity'):
+            continue
+        if stage == 'done':
+            raise ValueError(f'module {key} ({n}) after the CTC head')
+        if n == 'Conv2d' and stage in ('frontend', 'agg'):
+            spec = _conv_spec(sd, key, first=not layers)
+            if layers and spec['cin'] != layers[-1]['cout']:
+                raise ValueError(f'{key}: {spec["cin"]} input channels after a layer with {layers[-1]["cout"]} outputs '
+                                 f'(module tree not registered in forward order?)')
+            if (spec['kh'], spec['kw']) == (3, 3) and stage == 'frontend':
+                if _pair(getattr(m, 'padding', (1, 1))) != (1, 1) or _pair(getattr(m, 'stride', (1, 1))) != (1, 1):
+                    raise ValueError(f'{key}: frontend convolutions must have padding 1 and stride 1')
+                layers.append(spec)
+                last_conv = spec
+            elif spec['kw'] == 1 and stage == 'frontend' and layers:
+                if _pair(getattr(m, 'padding', (0, 0))) != (0, 0) or _pair(getattr(m, 'stride', (1, 1))) != (1, 1):
+                    raise ValueError(f'{key}: the height-aggregation convolution must have no padding and stride 1')
+                spec['pad_h'] = spec['pad_w'] = 0
+                layers.append(spec)
+                last_conv = spec
+                stage = 'agg'
+                feat = spec['cout']
+            else:
+                raise ValueError(f'{key}: unsupported convolution {spec["kh"]}x{spec["kw"]} at this position')
+        elif n in ('ReLU', 'LeakyReLU') and stage in ('frontend', 'agg'):
+            if last_conv is None or last_conv['act'] != _lib.ACT_NONE or 'post_scale' in last_conv or \
+                    (last_conv['pool_h'], last_conv['pool_w']) != (1, 1):
+                raise ValueError(f'{key}: an activation must directly follow a convolution')
+            _set_act(last_conv, m)
+        elif n == 'MaxPool2d' and stage == 'frontend':
             ph, pw = _pair(m.kernel_size)
             if (ph, pw) == (1, 1):
                 continue
+            st = getattr(m, 'stride', None)
+            if st is not None and _pair(st) != (ph, pw):
+                raise ValueError(f'{key}: max-pool stride must equal its kernel')
             if last_conv is None or (last_conv['pool_h'], last_conv['pool_w']) != (1, 1) or 'post_scale' in last_conv \
                     or ph not in (1, 2) or pw not in (1, 2) or last_conv['kind'] == _lib.CONV_FIRST:
                 raise ValueError('max-pool must be 2x2 / 2x1 / 1x2 and follow a tensor-core convolution')
             last_conv['pool_h'], last_conv['pool_w'] = ph, pw
-        elif n == 'BatchNorm2d':
+        elif n == 'BatchNorm2d' and stage == 'frontend':
             # eval-mode BN folded to y * scale + shift, applied after activation (+pool) of the preceding conv
             g, b = _f32(sd[key + '.weight']), _f32(sd[key + '.bias'])
             mu, var = _f32(sd[key + '.running_mean']), _f32(sd[key + '.running_var'])
             eps = float(getattr(m, 'eps', 1e-5))
             scale = (g.astype(np.float64) / np.sqrt(var.astype(np.float64) + eps))
             shift = b.astype(np.float64) - mu.astype(np.float64) * scale
-            if last_conv is None or last_conv['kind'] == _lib.CONV_FIRST:
+            if last_conv is None or last_conv['kind'] == _lib.CONV_FIRST or 'post_scale' in last_conv:
                 raise ValueError('BatchNorm must follow a tensor-core convolution')
             last_conv['post_scale'] = scale.astype(np.float32)
             last_conv['post_shift'] = shift.astype(np.float32)
-        elif n == 'Dropout':
-            continue
+        elif n == 'LSTM' and stage == 'agg':
+            if not bool(getattr(m, 'bidirectional', f'{key}.weight_ih_l0_reverse' in sd)):
+                raise ValueError(f'{key}: the recurrence kernel is bidirectional')
+            layer, cin = 0, feat
+            while f'{key}.weight_ih_l{layer}' in sd:
+                spec = dict(kind=_lib.BILSTM, cin=cin)
+                for name, sfx in (('w_ih', 'weight_ih'), ('w_hh', 'weight_hh'), ('b_ih', 'bias_ih'), ('b_hh', 'bias_hh')):
+                    spec[name] = [_f32(sd[f'{key}.{sfx}_l{layer}']), _f32(sd[f'{key}.{sfx}_l{layer}_reverse'])]
+                spec['hidden'] = spec['w_hh'][0].shape[1]
+                if spec['w_ih'][0].shape[1] != cin:
+                    raise ValueError(f'{key} layer {layer}: input width {spec["w_ih"][0].shape[1]} != {cin}')
+                layers.append(spec)
+                cin = 2 * spec['hidden']
+                layer += 1
+            feat = cin
+            stage = 'head'
+        elif n == 'LayerNorm' and stage == 'agg':
+            pending_norm = key
+        elif n == 'TransformerEncoder' and stage == 'agg' and pending_norm is not None:
+            layers.append(dict(kind=_lib.LN_PE, cin=feat, norm1_w=_f32(sd[pending_norm + '.weight']),
+                               norm1_b=_f32(sd[pending_norm + '.bias'])))
+            layer = 0
+            while f'{key}.layers.{layer}.linear1.weight' in sd:
+                p = f'{key}.layers.{layer}.'
+                heads = int(getattr(module, 'num_heads', 8))
+                try:
+                    heads = int(dict(m.named_children())['layers'][layer].self_attn.num_heads)
+                except Exception:
+                    pass
+                layers.append(dict(
+                    kind=_lib.TRANSFORMER_LAYER, cin=feat, heads=heads, dim_ff=sd[p + 'linear1.weight'].shape[0],
+                    in_proj_w=_f32(sd[p + 'self_attn.in_proj_weight']), in_proj_b=_f32(sd[p + 'self_attn.in_proj_bias']),
+                    out_proj_w=_f32(sd[p + 'self_attn.out_proj.weight']), out_proj_b=_f32(sd[p + 'self_attn.out_proj.bias']),
+                    lin1_w=_f32(sd[p + 'linear1.weight']), lin1_b=_f32(sd[p + 'linear1.bias']),
+                    lin2_w=_f32(sd[p + 'linear2.weight']), lin2_b=_f32(sd[p + 'linear2.bias']),
+                    norm1_w=_f32(sd[p + 'norm1.weight']), norm1_b=_f32(sd[p + 'norm1.bias']),
+                    norm2_w=_f32(sd[p + 'norm2.weight']), norm2_b=_f32(sd[p + 'norm2.bias'])))
+                layer += 1
+            stage = 'head'
+        elif n in ('Linear', 'Conv1d', 'Conv2d') and stage == 'head':
+            ow = _f32(sd[key + '.weight'])
+            if ow.ndim > 2:
+                if any(d != 1 for d in ow.shape[2:]):
+                    raise ValueError(f'{key}: a convolutional CTC head must have kernel size 1')
+                ow = np.ascontiguousarray(ow.reshape(ow.shape[0], ow.shape[1]))
+            if ow.shape[1] != feat:
+                raise ValueError(f'{key}: head input width {ow.shape[1]} != {feat}')
+            ob = _f32(sd[key + '.bias']) if key + '.bias' in sd else np.zeros(ow.shape[0], dtype=np.float32)
+            layers.append(dict(kind=_lib.CTC_HEAD, cin=feat, cout=ow.shape[0], kh=1, kw=1, weight=ow, bias=ob))
+            stage = 'done'
         else:
-            raise ValueError(f'unsupported frontend module {n}')
-    agg = _conv_spec(sd, 'agg', first=False)
-    agg['pad_h'] = agg['pad_w'] = 0
-    agg['act'] = _act_code(children['agg_act'])
-    layers.append(agg)
-    d_model = agg['cout']
-    if 'lstm' in children:
-        layer = 0
-        cin = d_model
-        while f'lstm.weight_ih_l{layer}' in sd:
-            spec = dict(kind=_lib.BILSTM, cin=cin)
-            for key, sfx in (('w_ih', 'weight_ih'), ('w_hh', 'weight_hh'), ('b_ih', 'bias_ih'), ('b_hh', 'bias_hh')):
-                spec[key] = [_f32(sd[f'lstm.{sfx}_l{layer}']), _f32(sd[f'lstm.{sfx}_l{layer}_reverse'])]
-            spec['hidden'] = spec['w_hh'][0].shape[1]
-            layers.append(spec)
-            cin = 2 * spec['hidden']
-            layer += 1
-        feat = cin
-    elif 'trans_encoder' in children:
-        layers.append(dict(kind=_lib.LN_PE, cin=d_model, norm1_w=_f32(sd['input_norm.weight']),
-                           norm1_b=_f32(sd['input_norm.bias'])))
-        layer = 0
-        while f'trans_encoder.layers.{layer}.linear1.weight' in sd:
-            p = f'trans_encoder.layers.{layer}.'
-            heads = int(getattr(module, 'num_heads', 8))
-            try:
-                heads = int(dict(children['trans_encoder'].named_children())['layers'][layer].self_attn.num_heads)
-            except Exception:
-                pass
-            layers.append(dict(
-                kind=_lib.TRANSFORMER_LAYER, cin=d_model, heads=heads, dim_ff=sd[p + 'linear1.weight'].shape[0],
-                in_proj_w=_f32(sd[p + 'self_attn.in_proj_weight']), in_proj_b=_f32(sd[p + 'self_attn.in_proj_bias']),
-                out_proj_w=_f32(sd[p + 'self_attn.out_proj.weight']), out_proj_b=_f32(sd[p + 'self_attn.out_proj.bias']),
-                lin1_w=_f32(sd[p + 'linear1.weight']), lin1_b=_f32(sd[p + 'linear1.bias']),
-                lin2_w=_f32(sd[p + 'linear2.weight']), lin2_b=_f32(sd[p + 'linear2.bias']),
-                norm1_w=_f32(sd[p + 'norm1.weight']), norm1_b=_f32(sd[p + 'norm1.bias']),
-                norm2_w=_f32(sd[p + 'norm2.weight']), norm2_b=_f32(sd[p + 'norm2.bias'])))
-            layer += 1
-        feat = d_model
-    else:
-        raise ValueError('sequence encoder must be `lstm` or `input_norm` + `trans_encoder`')
-    ow, ob = _f32(sd['out.weight']), _f32(sd['out.bias'])
-    layers.append(dict(kind=_lib.CTC_HEAD, cin=feat, cout=ow.shape[0], kh=1, kw=1, weight=ow, bias=ob))
-    return layers, ow.shape[0]
+            raise ValueError(f'unsupported module {key} ({n}) in the {stage} part of the recogniser')
+    if stage != 'done':
+        raise ValueError('the recogniser must end in a sequence encoder (bidirectional LSTM, or LayerNorm + '
+                         'TransformerEncoder) and a linear CTC head')
+    return layers, layers[-1]['cout']
 
 
 def describe_transformer_ocr(state_dict, net_config, line_height=40):
@@ -313,6 +381,7 @@ def to_ctypes(layers, precision, line_height, device):
                     'dim_ff'):
             if key in spec:
                 setattr(ly, key, int(spec[key]))
+        ly.act_slope = float(spec.get('act_slope', 0.0))
         for key in ('weight', 'bias', 'post_scale', 'post_shift', 'in_proj_w', 'in_proj_b', 'out_proj_w', 'out_proj_b',
                     'lin1_w', 'lin1_b', 'lin2_w', 'lin2_b', 'norm1_w', 'norm1_b', 'norm2_w', 'norm2_b'):
             if spec.get(key) is not None:

@@ -70,6 +70,33 @@ class LineNetLSTM(nn.Module):
         return y.permute(1, 2, 0)                     # [N,C,T]
 
 
+class LineNetLSTMAlt(nn.Module):
+    """A second recogniser family with the same contract (f32[N,3,40,W] -> f32[N,C,W/4]) and a different module tree:
+    nested blocks under other names, LeakyReLU slopes 0.1 / 0.2 / 0.3, BatchNorm after pooled blocks, a Dropout, a
+    384-wide aggregation, ONE BiLSTM layer and a 1x1 Conv1d as the CTC head.  Exists to pin that the engine builds from
+    module types and shapes, not from attribute names (netdesc.describe_line_net)."""
+
+    def __init__(self, num_classes: int = 120, hidden: int = 256):
+        super().__init__()
+        self.features = nn.Sequential(OrderedDict([
+            ('stem', nn.Sequential(nn.Conv2d(3, 64, 3, padding=1), nn.LeakyReLU(0.1))),
+            ('stage1', nn.Sequential(nn.Conv2d(64, 64, 3, padding=1), nn.LeakyReLU(0.1), nn.MaxPool2d(2, 2),
+                                     nn.BatchNorm2d(64))),
+            ('stage2', nn.Sequential(nn.Conv2d(64, 128, 3, padding=1), nn.ReLU(), nn.Conv2d(128, 128, 3, padding=1),
+                                     nn.LeakyReLU(0.2), nn.MaxPool2d(2, 2))),
+            ('stage3', nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.LeakyReLU(0.2), nn.MaxPool2d((2, 1), (2, 1)),
+                                     nn.BatchNorm2d(256), nn.Dropout2d(0.1))),
+        ]))
+        self.collapse = nn.Sequential(nn.Conv2d(256, 384, kernel_size=(AGG_HEIGHT, 1)), nn.LeakyReLU(0.3))
+        self.rnn = nn.LSTM(384, hidden, num_layers=1, bidirectional=True)
+        self.classifier = nn.Conv1d(2 * hidden, num_classes, kernel_size=1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.collapse(self.features(x)).squeeze(2)     # [N,384,T]
+        y, _ = self.rnn(y.permute(2, 0, 1))                # [T,N,2H]
+        return self.classifier(y.permute(1, 2, 0))         # [N,C,T]
+
+
 class LineNetTransformer(nn.Module):
     """VGG frontend -> LayerNorm + sinusoid PE + post-LN TransformerEncoder -> linear CTC head.
 
@@ -176,7 +203,7 @@ def seeded_state_dict(module: nn.Module, seed: int = 0, out_gain: float = 1.0) -
             a = rng.uniform(0.8, 1.2, shape)
         elif is_ln and leaf == 'bias':
             a = rng.uniform(-0.1, 0.1, shape)
-        elif name.startswith('lstm.') or 'in_proj' in name:
+        elif name.startswith('lstm.') or 'in_proj' in name or leaf.startswith(('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')):
             if len(shape) >= 2:
                 b = 1.0 / math.sqrt(shape[1])
             else:
@@ -185,7 +212,7 @@ def seeded_state_dict(module: nn.Module, seed: int = 0, out_gain: float = 1.0) -
         elif len(shape) >= 2:
             gain = math.sqrt(2.0)
             b = gain * math.sqrt(3.0 / _fan_in(shape))
-            if name == 'out.weight':
+            if name in ('out.weight', 'classifier.weight'):
                 b = out_gain * math.sqrt(3.0 / _fan_in(shape))
             a = rng.uniform(-b, b, shape)
         else:
@@ -197,6 +224,8 @@ def seeded_state_dict(module: nn.Module, seed: int = 0, out_gain: float = 1.0) -
 def make_net(kind: str = 'lstm', num_classes: int = 120, seed: int = 0, out_gain: float = 1.0, **kw) -> nn.Module:
     if kind == 'lstm':
         net = LineNetLSTM(num_classes, **kw)
+    elif kind == 'lstm_alt':
+        net = LineNetLSTMAlt(num_classes, **kw)
     elif kind == 'transformer':
         net = LineNetTransformer(num_classes, **kw)
     elif kind == 'parsenet':

@@ -505,3 +505,34 @@ def test_two_linked_replicas_give_the_single_engine_results(tmp_path, golden_dir
     two._slots = None
     first.close()
     assert two.process_lines([l.copy() for l in lines], no_logits=True)[0] == a[0]
+
+
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16f8'])
+def test_second_recogniser_family_matches_reference_golden(tmp_path, golden_dir, precision):
+    """A recogniser with another module tree (nested blocks under other names, LeakyReLU slopes 0.1 / 0.2 / 0.3, 384-wide
+    aggregation, ONE BiLSTM layer, Conv1d head; synthetic.LineNetLSTMAlt) hosted by the unmodified
+    PytorchEngineLineOCR (tests/golden/engine_lstm_alt.npz) against the CUDA engine built by the type-driven walk
+    of netdesc.describe_line_net."""
+    gold = load_golden(golden_dir, 'engine_lstm_alt.npz')
+    eng = _engine(tmp_path, 'lstm_alt', precision=precision)
+    lines = cases.engine_lines('lstm_alt')
+    tr, lg, co = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+    worst = 0.0
+    for i in range(len(lines)):
+        ref = gold[f'logits_{i}']
+        assert lg[i].shape == ref.shape
+        worst = max(worst, float(np.abs(lg[i] - ref).max()))
+        assert list(co[i]) == list(gold[f'coords_{i}'])
+        srt = np.sort(ref, axis=1)
+        decided = (srt[:, -1] - srt[:, -2]) > MARGIN
+        assert np.array_equal(lg[i].argmax(axis=1)[decided], ref.argmax(axis=1)[decided])
+    print(f'second family, {precision}: max |d logit| = {worst:.2e}')
+    assert worst <= TOL, worst
+    assert tr == list(gold['transcriptions'])
+    # the scripted checkpoint file walks to the same engine
+    scripted = torch.jit.script(make_case_net('lstm_alt'))
+    from pero_ocr_b200 import netdesc
+    a, _ = netdesc.describe_line_net(make_case_net('lstm_alt'))
+    b, _ = netdesc.describe_line_net(scripted)
+    assert [(x['kind'], x.get('act'), x.get('act_slope'), x.get('pool_h'), x.get('pool_w')) for x in a] == \
+           [(x['kind'], x.get('act'), x.get('act_slope'), x.get('pool_h'), x.get('pool_w')) for x in b]

@@ -107,3 +107,52 @@ def test_checkpoint_class_convention_matches_reference(golden_dir):
         hyps = prefix_beam(lp.astype(np.float64), 4)
         best = max(hyps, key=lambda h: h[1])
         assert ''.join(letters[c] for c in best[0]) == str(gold['decoder_beam4'][i])
+
+
+def test_second_recogniser_family_walk_and_golden(golden_dir):
+    """netdesc.describe_line_net is driven by module types and shapes: the second family (other names, nesting,
+    LeakyReLU slopes, Conv1d head) walks to the expected layer list, whose restated forward (plain torch on the walked
+    specs) reproduces the unmodified reference engine's golden logits; a tree registered out of order is refused."""
+    from pero_ocr_b200 import _lib, netdesc, synthetic
+    import torch.nn.functional as F
+    gold = np.load(os.path.join(golden_dir, 'engine_lstm_alt.npz'))
+    spec = cases.ENGINE_CASES['lstm_alt']
+    net = make_net('lstm_alt', spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'])
+    layers, n_classes = netdesc.describe_line_net(net)
+    assert n_classes == 120
+    assert [l['kind'] for l in layers] == [_lib.CONV_FIRST] + [_lib.CONV] * 5 + [_lib.BILSTM, _lib.CTC_HEAD]
+    assert [l.get('act_slope') for l in layers[:6]] == [0.1, 0.1, None, 0.2, 0.2, 0.3]
+    assert [(l['pool_h'], l['pool_w']) for l in layers[:6]] == [(1, 1), (2, 2), (1, 1), (2, 2), (2, 1), (1, 1)]
+
+    def forward(x):                              # the layer list as the engine executes it
+        for l in layers:
+            if l['kind'] in (_lib.CONV_FIRST, _lib.CONV):
+                x = F.conv2d(x, torch.from_numpy(l['weight']), torch.from_numpy(l['bias']), padding=(l['pad_h'], l['pad_w']))
+                x = F.relu(x) if l['act'] == _lib.ACT_RELU else F.leaky_relu(x, l.get('act_slope', 0.01))
+                if (l['pool_h'], l['pool_w']) != (1, 1):
+                    x = F.max_pool2d(x, (l['pool_h'], l['pool_w']))
+                if 'post_scale' in l:
+                    x = x * torch.from_numpy(l['post_scale'])[None, :, None, None] + torch.from_numpy(l['post_shift'])[None, :, None, None]
+            elif l['kind'] == _lib.BILSTM:
+                seq = x.squeeze(2).permute(2, 0, 1) if x.dim() == 4 else x
+                lstm = torch.nn.LSTM(l['cin'], l['hidden'], bidirectional=True)
+                lstm.load_state_dict({f'{k}_l0{sfx}': torch.from_numpy(l[short][d]) for k, short in
+                                      (('weight_ih', 'w_ih'), ('weight_hh', 'w_hh'), ('bias_ih', 'b_ih'), ('bias_hh', 'b_hh'))
+                                      for d, sfx in ((0, ''), (1, '_reverse'))})
+                x, _ = lstm(seq)
+            else:
+                x = (x @ torch.from_numpy(l['weight']).T + torch.from_numpy(l['bias'])).permute(1, 2, 0)
+        return x
+
+    line = cases.engine_lines('lstm_alt')[4]      # the widest line: the width of its reference batch is its own
+    batch = np.zeros((1, 40, int(np.ceil(line.shape[1] / 32) * 32) + 64, 3), dtype=np.uint8)
+    batch[0, :, 32:32 + line.shape[1]] = line
+    with torch.no_grad():
+        got = forward(torch.from_numpy(batch).float().div(255.0).permute(0, 3, 1, 2))[0].numpy().T
+    np.testing.assert_allclose(got, gold['logits_4'], atol=3e-5)
+    # the same modules registered in another order: channel counts do not chain
+    wrong = synthetic.LineNetLSTMAlt(120)
+    feats = list(wrong.features.named_children())
+    wrong.features = torch.nn.Sequential(*[m for _, m in (feats[2], feats[1], feats[0], feats[3])])
+    with pytest.raises(ValueError):
+        netdesc.describe_line_net(wrong)
