@@ -145,6 +145,12 @@ double b200ocr_forward_flops(const b200ocr_engine_t* e, int32_t n, int32_t w, do
  * pero_ocr_b200.engine.LineRecognizer.autotune_precision chooses the modes by measured logit error. */
 int b200ocr_set_layer_correction(b200ocr_engine_t* e, int32_t layer, int32_t mode);
 
+/* Replaces the post-activation per-channel shift of a convolution layer created with post_scale / post_shift
+ * (`shift`: HOST f32 [cout]).  Used for embedding-conditioned recognisers -- `model(batch, ids_embedding)` with one id
+ * for the whole batch (pytorch_ocr_engine.py:64-66), whose gathered vector is such a shift -- when the caller changes
+ * `embed_id` between runs (user_scripts/select_embed_id.py:79-80).  Synchronises the device. */
+int b200ocr_set_layer_post_shift(b200ocr_engine_t* e, int32_t layer, const float* shift);
+
 /* FLOP-weighted tensor-core pass-equivalents the GEMM layers execute per algorithmic FLOP at (n, w) (1 = fp16,
  * 2 = fp16f8, 3 = fp16x3, in between with per-layer corrections); per_layer (HOST f32 [capacity], may be NULL)
  * receives the figure of each layer (0 for layers without a contraction). */

@@ -72,7 +72,7 @@ def _install_stubs():
     mod('arabic_reshaper', ArabicReshaper=_Dummy)
 
 
-def _export_engine(tmp, net, name, n_chars):
+def _export_engine(tmp, net, name, n_chars, extra=None):
     """TorchScript export + engine JSON in the form PytorchEngineLineOCR reads (line_ocr_engine.py:19-46)."""
     ck = os.path.join(tmp, name + '.pt')
     scripted = torch.jit.script(net)
@@ -81,7 +81,7 @@ def _export_engine(tmp, net, name, n_chars):
     js = os.path.join(tmp, name + '.json')
     with open(js, 'w', encoding='utf8') as f:
         json.dump({'line_px_height': 40, 'line_vertical_scale': 1.0, 'checkpoint': name + '.pt',
-                   'characters': cases.json_characters(n_chars), 'net_name': 'B200_GOLDEN'}, f)
+                   'characters': cases.json_characters(n_chars), 'net_name': 'B200_GOLDEN', **(extra or {})}, f)
     return js
 
 
@@ -89,7 +89,8 @@ def golden_engine(kind, tmp):
     from pero_ocr.ocr_engine.pytorch_ocr_engine import PytorchEngineLineOCR
     spec = cases.ENGINE_CASES[kind]
     net = make_net(spec.get('net', kind), spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
-    js = _export_engine(tmp, net, kind, spec.get('json_chars', spec['classes'] - 2))
+    extra = {'embed_id': str(spec['embed_id'])} if 'embed_id' in spec else None
+    js = _export_engine(tmp, net, kind, spec.get('json_chars', spec['classes'] - 2), extra)
     eng = PytorchEngineLineOCR(js, torch.device('cpu'), batch_size=spec['engine_batch_size'])
     lines = cases.engine_lines(kind)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -111,6 +112,18 @@ def golden_engine(kind, tmp):
             out[f'csc_indices_{i}'] = sp.indices
             out[f'csc_indptr_{i}'] = sp.indptr
     out['transcriptions'] = np.array(tr)
+    if 'embed_id' in spec:
+        # the same lines under "embed_id": "mean" (pytorch_ocr_engine.py:46-50) and under another id assigned to the live
+        # engine, the way user_scripts/select_embed_id.py:79-80 does
+        js_mean = _export_engine(tmp, net, kind + '_mean', spec.get('json_chars', spec['classes'] - 2), {'embed_id': 'mean'})
+        eng_mean = PytorchEngineLineOCR(js_mean, torch.device('cpu'), batch_size=spec['engine_batch_size'])
+        out['mean_embed_id'] = np.int64(eng_mean.embed_id)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr_m, lg_m, _ = eng_mean.process_lines([l.copy() for l in lines], sparse_logits=False)
+            eng.embed_id = 0
+            tr_0, lg_0, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+        out['mean_transcriptions'], out['id0_transcriptions'] = np.array(tr_m), np.array(tr_0)
+        out['mean_logits_0'], out['id0_logits_0'] = lg_m[0].astype(np.float32), lg_0[0].astype(np.float32)
     if 'json_chars' in spec:
         # the reference's own decoder chain on the reference's own logits, letters as decoder_factory builds them
         # (decoding_itf.py:49-50): JSON characters + '<BLANK>'
@@ -456,6 +469,7 @@ def main():
                  ('engine_lstm_wide', lambda: golden_engine('lstm_wide', tmp)),
                  ('engine_lstm_c119', lambda: golden_engine('lstm_c119', tmp)),
                  ('engine_lstm_alt', lambda: golden_engine('lstm_alt', tmp)),
+                 ('engine_lstm_embed', lambda: golden_engine('lstm_embed', tmp)),
                  ('parsenet', lambda: golden_parsenet(tmp)), ('parsenet_page', lambda: golden_parsenet_page(tmp)),
                  ('confidence', golden_confidence),
                  ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder),

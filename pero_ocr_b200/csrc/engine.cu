@@ -1040,6 +1040,23 @@ int b200ocr_set_layer_correction(b200ocr_engine_t* e, int32_t layer, int32_t mod
     return B200OCR_OK;
 }
 
+int b200ocr_set_layer_post_shift(b200ocr_engine_t* e, int32_t layer, const float* shift) {
+    if (!e) return B200OCR_E_INVALID;
+    if (layer < 0 || layer >= static_cast<int>(e->layers.size()) || !shift)
+        return fail(e, B200OCR_E_INVALID, "bad set_layer_post_shift arguments (layer %d)", layer);
+    LayerRT& ly = e->layers[layer];
+    if (ly.kind != B200OCR_CONV || !ly.g.post_shift)
+        return fail(e, B200OCR_E_INVALID, "layer %d has no post-activation affine (create it with post_scale / post_shift)", layer);
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev != e->device) cudaSetDevice(e->device);
+    cudaError_t err = cudaDeviceSynchronize();                     // no forward may be reading the old shift
+    if (err == cudaSuccess) err = cudaMemcpy(ly.g.post_shift, shift, ly.g.cout * sizeof(float), cudaMemcpyHostToDevice);
+    if (cur_dev != e->device) cudaSetDevice(cur_dev);
+    if (err != cudaSuccess) return fail(e, B200OCR_E_CUDA, "set_layer_post_shift: %s", cudaGetErrorString(err));
+    return B200OCR_OK;
+}
+
 int b200ocr_run_after(b200ocr_engine_t* e, b200ocr_engine_t* after) {
     if (!e || after == e) return fail(e, B200OCR_E_INVALID, "bad run_after arguments");
     if (after && after->device != e->device) return fail(e, B200OCR_E_INVALID, "engines live on different devices");

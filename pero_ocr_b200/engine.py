@@ -65,6 +65,18 @@ class LineRecognizer:
     def use_reference_kernels(self, on):
         _lib.check(self._lib.b200ocr_debug_use_reference_kernels(self._h, 1 if on else 0), self._h)
 
+    def set_embedding(self, embed_id):
+        """Embedding-conditioned recogniser (netdesc.describe_line_net): switch to the table row `embed_id` (int or
+        "mean") -- b200ocr_set_layer_post_shift on the aggregation layer."""
+        for i, l in enumerate(self._layers):
+            if 'embedding_table' in l:
+                table = l['embedding_table']
+                shift = np.ascontiguousarray(l['embedding_base_shift'] + table[netdesc.resolve_embed_id(embed_id, table.shape[0])],
+                                             dtype=np.float32)
+                _lib.check(self._lib.b200ocr_set_layer_post_shift(self._h, i, shift.ctypes.data_as(C.c_void_p)), self._h)
+                return
+        raise ValueError('the recogniser has no embedding table')
+
     def run_after(self, other):
         """b200ocr_run_after: this engine's forwards start once `other`'s latest forward has finished its convolutional
         front end (None unlinks)."""
@@ -244,7 +256,9 @@ class B200EngineLineOCR:
     The engine JSON is the reference's (keys ``line_px_height, line_vertical_scale, checkpoint, characters,
     net_name``; optional ``max_line_width``); ``checkpoint`` is the same TorchScript file the reference loads
     (the ``.cpu`` suffix rule does not apply -- the weights are read once on the host and packed for the GPU).
-    Embedding-conditioned nets (``embed_id``) are not supported and raise at construction.
+    Embedding-conditioned nets -- ``model(batch, ids)`` with the JSON's ``embed_id`` (an int or "mean",
+    line_ocr_engine.py:36-42) -- are supported in the form netdesc.describe_line_net documents; ``embed_id`` may be
+    reassigned between calls like the reference's attribute (user_scripts/select_embed_id.py:79-80).
     """
 
     def __init__(self, json_def, device=None, batch_size=8, precision=DEFAULT_PRECISION, module=None, replicas=1,
@@ -259,9 +273,10 @@ class B200EngineLineOCR:
         self.characters = list(self.config['characters']) + [u'​']   # pytorch_ocr_engine.py:42
         self.net_name = self.config['net_name']
         self.embed_num = int(self.config['embed_num']) if 'embed_num' in self.config else None
-        self.embed_id = self.config.get('embed_id')
-        if self.embed_id is not None:
-            raise NotImplementedError('embedding-conditioned recognisers (embed_id) are outside the B200 path')
+        self._models = []
+        self._embed_id = None
+        if 'embed_id' in self.config:                                       # line_ocr_engine.py:36-42
+            self._embed_id = 'mean' if self.config['embed_id'] == 'mean' else int(self.config['embed_id'])
         self.max_line_width = int(self.config.get('max_line_width', 1e10))
         self.model_type = 'ctc'
         self.device = device if device is not None else torch.device('cuda', 0)
@@ -273,7 +288,7 @@ class B200EngineLineOCR:
         self.net_subsampling = 4                                            # pytorch_ocr_engine.py:41
         if module is None:
             module = torch.jit.load(self.checkpoint, map_location='cpu')
-        layers, n_classes = netdesc.describe_line_net(module)
+        layers, n_classes = netdesc.describe_line_net(module, embed_id=self._embed_id)
         # The blank is the LAST class (greedy_decode_ctc, pytorch_ocr_engine.py:27) and `characters` must name every
         # other one.  pero checkpoints emit len(JSON characters) + 1 classes -- decoder_factory's letters are the JSON
         # characters + '<BLANK>' (decoding_itf.py:49-50), so the U+200B appended at :42 sits in the blank's slot and is
@@ -329,6 +344,31 @@ class B200EngineLineOCR:
 
     def _device_ctx(self):
         return self.model.torch.cuda.device(self.device)
+
+    @property
+    def embed_id(self):
+        """The reference's attribute (line_ocr_engine.py:36-42; pytorch_ocr_engine.py:46-47 resolves "mean" to the last
+        row at construction): the table row of an embedding-conditioned recogniser, None otherwise.  Assignable."""
+        return self._embed_id
+
+    @embed_id.setter
+    def embed_id(self, value):
+        if value is None:
+            if self._embed_id is not None:
+                raise ValueError('an embedding-conditioned recogniser needs an embed_id')
+            return
+        value = 'mean' if value == 'mean' else int(value)
+        with self._device_ctx():
+            for m in self._models:
+                m.set_embedding(value)
+        self._embed_id = value
+
+    def get_mean_embed_id(self):
+        """pytorch_ocr_engine.py:49-50."""
+        for l in self.model._layers:
+            if 'embedding_table' in l:
+                return l['embedding_table'].shape[0] - 1
+        raise AttributeError('the recogniser has no embeddings_layer')
 
     def autotune_precision(self, budget=3e-4, sample=None):
         """LineRecognizer.autotune_precision on the first native engine; the chosen per-layer modes are applied to

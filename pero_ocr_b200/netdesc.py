@@ -69,7 +69,7 @@ def _conv_spec(sd, prefix, first):
                 pad_h=(kh - 1) // 2, pad_w=(kw - 1) // 2, act=_lib.ACT_NONE, pool_h=1, pool_w=1, weight=w, bias=b)
 
 
-_LEAF_TYPES = {'Conv2d', 'Conv1d', 'ReLU', 'LeakyReLU', 'MaxPool2d', 'BatchNorm2d', 'Dropout', 'Dropout2d', 'Identity',
+_LEAF_TYPES = {'Embedding', 'Conv2d', 'Conv1d', 'ReLU', 'LeakyReLU', 'MaxPool2d', 'BatchNorm2d', 'Dropout', 'Dropout2d', 'Identity',
                'LSTM', 'Linear', 'LayerNorm', 'TransformerEncoder'}
 
 
@@ -84,7 +84,7 @@ def _leaves(module, prefix=''):
             yield from _leaves(m, key + '.')
 
 
-def describe_line_net(module):
+def describe_line_net(module, embed_id=None):
     """nn.Module or TorchScript module -> (layer specs, num_classes).
 
     The walk is driven by module TYPES and tensor shapes, not by attribute names: the leaf modules are taken in
@@ -95,6 +95,12 @@ def describe_line_net(module):
         Conv2d (k, 1) pad 0 [ReLU | LeakyReLU]                       -- height aggregation
         LSTM (bidirectional, any number of layers)  |  LayerNorm + TransformerEncoder (post-LN, ReLU)
         Linear | Conv1d k = 1 | Conv2d 1x1                           -- CTC head
+    An ``nn.Embedding`` anywhere in the tree makes it an embedding-conditioned recogniser, ``model(x, ids)``
+    (pytorch_ocr_engine.py:64-66), of the form "one gathered vector per line added to the aggregated features": the
+    reference passes ONE id for the whole batch, so the vector is a per-channel shift after the aggregation's
+    activation.  It is folded into that layer's post-affine for `embed_id` (an int, or "mean" = the table's last row,
+    pytorch_ocr_engine.py:49-50); the layer spec keeps the table (``embedding_table``) and the shift without it
+    (``embedding_base_shift``) so that the id can be changed later (LineRecognizer.set_embedding).
     """
     sd = {k: v for k, v in module.state_dict().items()}
     layers = []
@@ -102,9 +108,15 @@ def describe_line_net(module):
     stage = 'frontend'                       # -> 'agg' -> 'sequence' -> 'head' -> 'done'
     feat = None
     pending_norm = None
+    embedding = None
     for key, m in _leaves(module):
         n = _name(m)
         if n in ('Dropout', 'Dropout2d', 'Identity'):
+            continue
+        if n == 'Embedding':
+            if embedding is not None:
+                raise ValueError('more than one embedding table')
+            embedding = _f32(sd[key + '.weight'])
             continue
         if stage == 'done':
             raise ValueError(f'module {key} ({n}) after the CTC head')
@@ -210,7 +222,28 @@ def describe_line_net(module):
     if stage != 'done':
         raise ValueError('the recogniser must end in a sequence encoder (bidirectional LSTM, or LayerNorm + '
                          'TransformerEncoder) and a linear CTC head')
+    if embedding is not None:
+        if embed_id is None:
+            raise ValueError('the recogniser takes an embedding id: set "embed_id" in the engine JSON '
+                             '(line_ocr_engine.py:36-42)')
+        agg = [l for l in layers if l['kind'] == _lib.CONV][-1]
+        if embedding.shape[1] != agg['cout']:
+            raise ValueError(f'embedding width {embedding.shape[1]} != aggregated feature width {agg["cout"]}')
+        agg['embedding_table'] = embedding
+        agg['embedding_base_shift'] = agg.get('post_shift', np.zeros(agg['cout'], dtype=np.float32)).copy()
+        agg.setdefault('post_scale', np.ones(agg['cout'], dtype=np.float32))
+        agg['post_shift'] = agg['embedding_base_shift'] + embedding[resolve_embed_id(embed_id, embedding.shape[0])]
+    elif embed_id is not None:
+        raise ValueError('"embed_id" is set but the recogniser has no embedding table')
     return layers, layers[-1]['cout']
+
+
+def resolve_embed_id(embed_id, rows):
+    """int or "mean" (= the last row, pytorch_ocr_engine.py:49-50) -> row index, range-checked."""
+    idx = rows - 1 if embed_id == 'mean' else int(embed_id)
+    if not 0 <= idx < rows:
+        raise IndexError(f'embed_id {embed_id} outside the table of {rows} embeddings')
+    return idx
 
 
 def describe_transformer_ocr(state_dict, net_config, line_height=40):

@@ -70,6 +70,23 @@ class LineNetLSTM(nn.Module):
         return y.permute(1, 2, 0)                     # [N,C,T]
 
 
+class LineNetLSTMEmbed(LineNetLSTM):
+    """Embedding-conditioned recogniser, the form the reference engine hosts as ``model(x, ids)`` with a learned table
+    ``model.embeddings_layer`` (pytorch_ocr_engine.py:46-50, 64-66; the architecture itself lives in the opaque
+    checkpoint): one vector per style id, gathered per line and added to the aggregated features of every frame
+    before the recurrence."""
+
+    def __init__(self, num_classes: int = 120, num_embeddings: int = 6, **kw):
+        super().__init__(num_classes, **kw)
+        self.embeddings_layer = nn.Embedding(num_embeddings, D_MODEL)
+
+    def forward(self, x: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        y = self.agg_act(self.agg(self.conv(x))).squeeze(2)          # [N,512,T]
+        y = y + self.embeddings_layer(ids)[:, :, None]
+        y, _ = self.lstm(y.permute(2, 0, 1))
+        return self.out(y).permute(1, 2, 0)
+
+
 class LineNetLSTMAlt(nn.Module):
     """A second recogniser family with the same contract (f32[N,3,40,W] -> f32[N,C,W/4]) and a different module tree:
     nested blocks under other names, LeakyReLU slopes 0.1 / 0.2 / 0.3, BatchNorm after pooled blocks, a Dropout, a
@@ -226,6 +243,8 @@ def make_net(kind: str = 'lstm', num_classes: int = 120, seed: int = 0, out_gain
         net = LineNetLSTM(num_classes, **kw)
     elif kind == 'lstm_alt':
         net = LineNetLSTMAlt(num_classes, **kw)
+    elif kind == 'lstm_embed':
+        net = LineNetLSTMEmbed(num_classes, **kw)
     elif kind == 'transformer':
         net = LineNetTransformer(num_classes, **kw)
     elif kind == 'parsenet':

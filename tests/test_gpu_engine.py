@@ -536,3 +536,39 @@ def test_second_recogniser_family_matches_reference_golden(tmp_path, golden_dir,
     b, _ = netdesc.describe_line_net(scripted)
     assert [(x['kind'], x.get('act'), x.get('act_slope'), x.get('pool_h'), x.get('pool_w')) for x in a] == \
            [(x['kind'], x.get('act'), x.get('act_slope'), x.get('pool_h'), x.get('pool_w')) for x in b]
+
+
+def test_embedding_conditioned_recogniser_matches_reference_golden(tmp_path, golden_dir):
+    """`model(batch, ids)` with the JSON's embed_id (pytorch_ocr_engine.py:46-50, 64-66): the unmodified reference engine
+    on synthetic.LineNetLSTMEmbed with embed_id 2, with "mean", and with the attribute reassigned to 0 on the live
+    engine (user_scripts/select_embed_id.py:79-80) -- against the CUDA engine, two replicas."""
+    from pero_ocr_b200.engine import B200EngineLineOCR
+    gold = load_golden(golden_dir, 'engine_lstm_embed.npz')
+    spec = cases.ENGINE_CASES['lstm_embed']
+    net = make_case_net('lstm_embed')
+    lines = cases.engine_lines('lstm_embed')
+
+    def build(embed_id, **kw):
+        js = write_engine_json(tmp_path, 'lstm_embed', embed_id=embed_id)
+        return B200EngineLineOCR(js, torch.device('cuda', 0), batch_size=spec['engine_batch_size'], precision='fp16f8',
+                                 module=net, **kw)
+
+    def check(eng, tr_key, logit_key):
+        tr, lg, _ = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+        assert np.abs(lg[0] - gold[logit_key]).max() <= TOL
+        assert tr == list(gold[tr_key])
+
+    eng = build(None, replicas=2)                       # the case's own id (2) from the JSON
+    assert eng.embed_id == 2 and eng.get_mean_embed_id() == int(gold['mean_embed_id'])
+    check(eng, 'transcriptions', 'logits_0')
+    eng.embed_id = 0                                    # reassigned on the live engine: both replicas follow
+    check(eng, 'id0_transcriptions', 'id0_logits_0')
+    eng.embed_id = 'mean'
+    check(eng, 'mean_transcriptions', 'mean_logits_0')
+    check(build('mean'), 'mean_transcriptions', 'mean_logits_0')
+    with pytest.raises(IndexError):
+        eng.embed_id = 6
+    with pytest.raises(ValueError):                     # a table but no id / an id but no table
+        B200EngineLineOCR(write_engine_json(tmp_path, 'lstm'), torch.device('cuda', 0), module=net)
+    with pytest.raises(ValueError):
+        B200EngineLineOCR(write_engine_json(tmp_path, 'lstm', embed_id=1), torch.device('cuda', 0), module=make_case_net('lstm'))

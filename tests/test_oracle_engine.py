@@ -156,3 +156,31 @@ def test_second_recogniser_family_walk_and_golden(golden_dir):
     wrong.features = torch.nn.Sequential(*[m for _, m in (feats[2], feats[1], feats[0], feats[3])])
     with pytest.raises(ValueError):
         netdesc.describe_line_net(wrong)
+
+
+def test_embedding_fold_equals_the_conditioned_forward(golden_dir):
+    """netdesc folds the gathered embedding of `model(x, ids)` (one id per batch, pytorch_ocr_engine.py:64-66) into the
+    aggregation layer's post-activation shift: the shift is table[id] for an int id and the last row for "mean", and
+    the module's own forward with that id reproduces the unmodified reference engine's golden logits."""
+    from pero_ocr_b200 import netdesc
+    gold = np.load(os.path.join(golden_dir, 'engine_lstm_embed.npz'))
+    spec = cases.ENGINE_CASES['lstm_embed']
+    net = make_net('lstm_embed', spec['classes'], seed=spec['seed'], out_gain=spec['out_gain'], **spec['net_kw'])
+    table = net.embeddings_layer.weight.detach().numpy()
+    for embed_id, row in ((2, 2), ('mean', 5), (0, 0)):
+        layers, _ = netdesc.describe_line_net(net, embed_id=embed_id)
+        agg = [l for l in layers if 'embedding_table' in l]
+        assert len(agg) == 1 and np.array_equal(agg[0]['post_shift'], table[row]) and (agg[0]['post_scale'] == 1).all()
+        assert netdesc.resolve_embed_id(embed_id, table.shape[0]) == row
+    with pytest.raises(ValueError):
+        netdesc.describe_line_net(net)
+    with pytest.raises(IndexError):
+        netdesc.describe_line_net(net, embed_id=6)
+    line = cases.engine_lines('lstm_embed')[0]          # the widest line of the case
+    batch = np.zeros((1, 40, int(np.ceil(line.shape[1] / 32) * 32) + 64, 3), dtype=np.uint8)
+    batch[0, :, 32:32 + line.shape[1]] = line
+    x = torch.from_numpy(batch).float().div(255.0).permute(0, 3, 1, 2)
+    with torch.no_grad():
+        for embed_id, key in ((2, 'logits_0'), (5, 'mean_logits_0'), (0, 'id0_logits_0')):
+            got = net(x, torch.tensor([embed_id]))[0].numpy().T
+            np.testing.assert_allclose(got, gold[key], atol=3e-5)
