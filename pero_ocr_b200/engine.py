@@ -778,17 +778,20 @@ class B200EngineLineOCR:
 
         def page_jobs():
             pending, k = [], 0
-            for item in it:
-                pending.append(pool.submit(prepare, k, item[0], item[1]))
+            first = next(it, None)
+            if first is not None:
+                # the first page is prepared alone: three preparations started together share the interpreter and
+                # each takes three times as long, which is pure latency while the GPU still has nothing to do
+                pending.append(pool.submit(prepare, k, first[0], first[1]))
                 k += 1
-                if len(pending) >= prefetch:
-                    break
             while pending:
                 t0 = time.perf_counter()
                 page, fitted, ready, maps = pending.pop(0).result()
                 page_ms['starved'] += 1e3 * (time.perf_counter() - t0)
-                nxt = next(it, None)
-                if nxt is not None:
+                while len(pending) < prefetch:
+                    nxt = next(it, None)
+                    if nxt is None:
+                        break
                     pending.append(pool.submit(prepare, k, nxt[0], nxt[1]))
                     k += 1
                 with self._device_ctx():
