@@ -656,7 +656,22 @@ class B200EngineLineOCR:
         nslots = 2 * depth
         in_flight, order = [], []
         bi = 0
-        for widths, stager in jobs:
+
+        def ready():
+            """Collects, without waiting, the batches at the head of the pipeline whose results have arrived."""
+            slots = getattr(self, '_slots', None)
+            while in_flight and slots is not None and slots[in_flight[0][2][0]]['done'].query():
+                collect_oldest(in_flight)
+
+        jobs = iter(jobs)
+        while True:
+            # pulling the next job may block (process_pages: the page's preparation): hand out what is finished first
+            ready()
+            yield from completed(order)
+            nxt = next(jobs, None)
+            if nxt is None:
+                break
+            widths, stager = nxt
             count = len(widths)
             job = {'widths': widths, 'transcriptions': [None] * count, 'logits': [None] * count,
                    'coords': [None] * count, 'confidences': [None] * count, 'open': 0, 'submitted': False}
@@ -761,9 +776,8 @@ class B200EngineLineOCR:
                 ready.record(streams[k % len(streams)])
                 t1 = time.perf_counter()
                 maps = None
-                if parsenet is not None:
-                    with lock:                                   # one native engine, not re-entrant
-                        maps = parsenet.get_maps(image, parsenet_downsample or parsenet.init_downsample)
+                if parsenet is not None:                         # serialises its own forwards (parsenet.py)
+                    maps = parsenet.get_maps(image, parsenet_downsample or parsenet.init_downsample)
             t2 = time.perf_counter()
             fitted = [cropper.poly_params(b, h) for b, h in lines]
             t3 = time.perf_counter()

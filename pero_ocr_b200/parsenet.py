@@ -34,6 +34,11 @@ class B200ParseNet:
         _lib.check(self._lib.b200ocr_create(C.byref(desc), C.byref(h)))
         self._h = h
         self._reserved = (0, 0)
+        # one native engine = one workspace: forwards are enqueued one after the other on the engine's own stream (the
+        # lock covers the enqueue only, callers on several threads wait for their own result outside it)
+        import threading
+        self._lock = threading.Lock()
+        self._stream = torch.cuda.Stream(self.device)
         self.detection_threshold = detection_threshold
         self.adaptive_downsample = adaptive_downsample
         self.init_downsample = downsample
@@ -67,6 +72,20 @@ class B200ParseNet:
                    self._h)
         return maps
 
+    def _forward_to_host(self, canvas):
+        """uint8 canvas -> float32 [1, H64, W64, C] host array (page-locked; a view of it is what get_maps returns)."""
+        if getattr(self, '_stream', None) is None:          # host-logic tests replace `net` with a CPU callable
+            return self.net(canvas).permute(0, 2, 3, 1).cpu().numpy()
+        torch = self.torch
+        with self._lock, torch.cuda.device(self.device), torch.cuda.stream(self._stream):
+            maps = self.net(canvas).permute(0, 2, 3, 1).contiguous()          # [1, H64, W64, C] on the device
+            host = torch.empty(maps.shape, dtype=maps.dtype, pin_memory=True)
+            host.copy_(maps, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        done.synchronize()
+        return host.numpy()
+
     def get_maps(self, img, downsample):
         import cv2
         img = cv2.resize(img, (0, 0), fx=1 / downsample, fy=1 / downsample, interpolation=cv2.INTER_AREA)
@@ -74,7 +93,7 @@ class B200ParseNet:
         cols = int(np.ceil(img.shape[1] / 64) * 64)
         canvas = np.zeros((1, rows, cols, 3), dtype=np.uint8)
         canvas[0, :img.shape[0], :img.shape[1], :] = img
-        out_map = self.net(canvas).permute(0, 2, 3, 1).cpu().numpy()
+        out_map = self._forward_to_host(canvas)
         return out_map[0, :img.shape[0], :img.shape[1], :]
 
     def get_med_height(self, out_map):
