@@ -168,6 +168,7 @@ class PinnedPool:
         self.free = {}                      # block size -> [mmap, ...]
         self.lock = threading.Lock()
         self.stats = {'hits': 0, 'new': 0, 'refused': 0}
+        self.closed = False
         self._register, self._unregister = register or _cuda_host_register, unregister or _cuda_host_unregister
 
     @staticmethod
@@ -181,6 +182,8 @@ class PinnedPool:
         import mmap
         size = self.block_size(nbytes)
         with self.lock:
+            if self.closed:
+                return None
             have = self.free.get(size)
             if have:
                 self.stats['hits'] += 1
@@ -207,7 +210,26 @@ class PinnedPool:
 
     def _give_back(self, mem, size):
         with self.lock:
-            self.free.setdefault(size, []).append(mem)
+            if not self.closed:
+                self.free.setdefault(size, []).append(mem)
+                return
+            self.registered -= size
+        try:                                 # the pool is gone: the block goes back to the system right away
+            self._unregister(mem)
+            mem.close()
+        except Exception:
+            pass
+
+    def close(self):
+        """No further loans; free blocks are unregistered now, blocks on loan when their last array dies."""
+        self.closed = True
+        self.trim()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def trim(self):
         """Unregisters and unmaps every block that is not on loan."""

@@ -199,6 +199,15 @@ def test_pinned_pool_lends_and_recycles_blocks():
     del again
     pool.trim()
     assert pool.registered == 0 and not pool.free
+    # a closed pool lends nothing, and a block that outlives it is unregistered when its last array dies
+    released = []
+    pool2 = PinnedPool(cap_bytes=32 << 20, register=lambda mem, size: None, unregister=lambda mem: released.append(1))
+    late = np.frombuffer(pool2.take(3 << 20), dtype=np.uint8, count=16)
+    pool2.close()
+    assert pool2.take(3 << 20) is None and pool2.registered > 0 and not released
+    del late
+    gc.collect()
+    assert pool2.registered == 0 and released == [1]
 
 
 def test_batch_pipeline_runs_across_jobs_in_order():
