@@ -757,6 +757,7 @@ class B200EngineLineOCR:
         from .cropper import DevicePage
         torch = self.model.torch
         lock = threading.Lock()
+        fit_lock = threading.Lock()
         prefetch = max(1, int(prefetch))
         # side streams and worker threads live as long as the engine: torch's caching allocator keeps one pool per
         # stream, so fresh streams per call would mean fresh cudaMallocs for every page image
@@ -779,7 +780,9 @@ class B200EngineLineOCR:
                 if parsenet is not None:                         # serialises its own forwards (parsenet.py)
                     maps = parsenet.get_maps(image, parsenet_downsample or parsenet.init_downsample)
             t2 = time.perf_counter()
-            fitted = [cropper.poly_params(b, h) for b, h in lines]
+            with fit_lock:          # interpreter-bound NumPy: three fits at once take longer than three in a row
+                t2 = time.perf_counter()
+                fitted = [cropper.poly_params(b, h) for b, h in lines]
             t3 = time.perf_counter()
             with lock:
                 page_ms['upload'] += 1e3 * (t1 - t0); page_ms['parsenet'] += 1e3 * (t2 - t1); page_ms['fit'] += 1e3 * (t3 - t2)
