@@ -781,11 +781,11 @@ class B200EngineLineOCR:
                     maps = parsenet.get_maps(image, parsenet_downsample or parsenet.init_downsample)
             t2 = time.perf_counter()
             with fit_lock:          # interpreter-bound NumPy: three fits at once take longer than three in a row
-                t2 = time.perf_counter()
+                t2b = time.perf_counter()
                 fitted = [cropper.poly_params(b, h) for b, h in lines]
             t3 = time.perf_counter()
             with lock:
-                page_ms['upload'] += 1e3 * (t1 - t0); page_ms['parsenet'] += 1e3 * (t2 - t1); page_ms['fit'] += 1e3 * (t3 - t2)
+                page_ms['upload'] += 1e3 * (t1 - t0); page_ms['parsenet'] += 1e3 * (t2 - t1); page_ms['fit'] += 1e3 * (t3 - t2b)
             return page, fitted, ready, maps
 
         if cropper.line_height != self.line_px_height:
