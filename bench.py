@@ -350,11 +350,13 @@ def bench_config3(dev, peak_tf, with_cpu, lines_total=1536):
     from pero_ocr_b200.decoders import BLANK_SYMBOL, CTCPrefixLogRawNumpyDecoder
     from pero_ocr_b200.engine import B200EngineLineOCR
     net = make_net('transformer')
-    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=net)
+    # one engine: a second replica (beam search of batch i beside the forward of batch i+1) measured no gain here
+    eng = B200EngineLineOCR(write_engine_json(), dev, batch_size=8, module=net,
+                            replicas=int(os.environ.get('B200OCR_CONFIG3_REPLICAS', '1')))
     eng.max_input_horizontal_pixels = BATCH * WIDTH
     dec = CTCPrefixLogRawNumpyDecoder(eng.characters + [BLANK_SYMBOL], 16)
     lines = list(synthetic.bench_crops(lines_total, WIDTH, seed=0))
-    eng.decode_lines(lines[:BATCH], dec)
+    eng.decode_lines(lines[:BATCH * 2 * len(eng._models)], dec)      # warm-up: every slot of every replica
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     bags = eng.decode_lines(lines, dec)
