@@ -241,20 +241,25 @@ __global__ void __launch_bounds__(ST_THREADS) sparsify_fill_tiled_kernel(const f
     const uint32_t* m = colmask + static_cast<size_t>(line) * chunks * C;
     const int32_t* ip = indptr + static_cast<size_t>(line) * (C + 1);
     const int64_t b0 = base[line];
+    // thread per class: where this chunk's run of column c starts; then warp per column: lane f owns frame f, so a
+    // column's surviving entries (consecutive in the CSC arrays) leave in ONE coalesced store per array
+    uint32_t* s_word = reinterpret_cast<uint32_t*>(tile + ST_FRAMES * pitch);        // [C]
+    long long* s_at = reinterpret_cast<long long*>(s_word + ((C + 1) & ~1));          // [C], 8-byte aligned
     for (int c = threadIdx.x; c < C; c += ST_THREADS) {
-        uint32_t word = m[static_cast<size_t>(k) * C + c];
-        if (!word) continue;
         int before = 0;
         for (int kk = 0; kk < k; ++kk) before += __popc(m[static_cast<size_t>(kk) * C + c]);
-        int64_t at = b0 + ip[c] + before;
-        while (word) {
-            const int f = __ffs(word) - 1;
-            word &= word - 1;
-            if (at < capacity) {
-                indices[at] = rel0 + f;
-                data[at] = tile[f * pitch + c];
-            }
-            ++at;
+        s_word[c] = m[static_cast<size_t>(k) * C + c];
+        s_at[c] = b0 + ip[c] + before;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = warp; c < C; c += ST_THREADS / 32) {
+        const uint32_t word = s_word[c];
+        if (!((word >> lane) & 1u)) continue;
+        const long long at = s_at[c] + __popc(word & ((1u << lane) - 1u));
+        if (at < capacity) {
+            indices[at] = rel0 + lane;
+            data[at] = tile[lane * pitch + c];
         }
     }
 }
@@ -333,7 +338,8 @@ cudaError_t launch_sparsify(const float* logits, int n, int T, int C, const int3
         attr_done.mark();
     }
     const int pitch = (C + 1) | 1;
-    const size_t tile_dyn = (static_cast<size_t>(ST_FRAMES) * pitch + 2 * ST_FRAMES) * sizeof(float);
+    // tile + (mask kernel: 64 floats of frame statistics | fill kernel: C mask words + C 64-bit offsets)
+    const size_t tile_dyn = (static_cast<size_t>(ST_FRAMES) * pitch + 64 + 3 * static_cast<size_t>(C) + 4) * sizeof(float);
     if (tile_dyn <= 200 * 1024 && T > 0) {
         const int chunks = (T + ST_FRAMES - 1) / ST_FRAMES;
         uint32_t* colmask = nullptr;
