@@ -33,6 +33,9 @@ ENGINE_CASES['lstm_alt'] = dict(net='lstm_alt', classes=120, seed=11, out_gain=6
 # embedding-conditioned recogniser hosted by the reference as model(x, ids) (pytorch_ocr_engine.py:64-66)
 ENGINE_CASES['lstm_embed'] = dict(net='lstm_embed', classes=120, seed=13, out_gain=6.0, net_kw={'num_embeddings': 6},
                                   engine_batch_size=2, widths=[280, 264, 150, 72], embed_id=2)
+# BiLSTM hidden size other than 256 (the tcgen05 recurrence kernel's size): the generic recurrence kernel
+ENGINE_CASES['lstm_h128'] = dict(net='lstm', classes=120, seed=17, out_gain=6.0, net_kw={'hidden': 128},
+                                 engine_batch_size=2, widths=[260, 200, 131, 64])
 PARSENET_CASE = dict(seed=5, downsample=2, height=250, width=330)
 # BASELINE config 4 size: a 3000 x 4000 page at DOWNSAMPLE = 4 -> canvas 768 x 1024, and the adaptive second pass
 # (torch_parsenet.py:60-93); the stand-in's head is biased so that the first pass "detects" 20 px text (>15) and the

@@ -470,6 +470,7 @@ def main():
                  ('engine_lstm_c119', lambda: golden_engine('lstm_c119', tmp)),
                  ('engine_lstm_alt', lambda: golden_engine('lstm_alt', tmp)),
                  ('engine_lstm_embed', lambda: golden_engine('lstm_embed', tmp)),
+                 ('engine_lstm_h128', lambda: golden_engine('lstm_h128', tmp)),
                  ('parsenet', lambda: golden_parsenet(tmp)), ('parsenet_page', lambda: golden_parsenet_page(tmp)),
                  ('confidence', golden_confidence),
                  ('cropper', golden_cropper), ('align', golden_align), ('ar_decoder', golden_ar_decoder),

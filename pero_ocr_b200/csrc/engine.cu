@@ -562,7 +562,8 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                         CU_TRY(e, cudaEventRecord(e->front_done, st));       // the conv front end of this batch is done
                         e->front_recorded = true;
                     }
-                    if (e->use_ref) {
+                    if (e->use_ref || H != 256) {
+                        ProfScope ps(e, st, PROF_LSTM);
                         CU_TRY(e, launch_lstm_ref(eo.out_f32, ly.w_hh_t, cur.n, T, H, e->fmt, e->planes == 1, o, st));
                     } else if (e->lstm_priority && e->hi_stream) {
                         CU_TRY(e, cudaEventRecord(e->hi_fork, st));
@@ -813,7 +814,10 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                 break;
             case B200OCR_BILSTM: {
                 const int H = d.hidden;
-                if (H != 256) return bail(fail(e, B200OCR_E_INVALID, "layer %d: BiLSTM hidden size must be 256", i));
+                // H = 256 runs on the tcgen05 cluster kernel (lstm_tc.cu); other sizes on the fp32 CUDA-core recurrence
+                // (kernels.cu: lstm_ref_kernel, one thread per hidden unit) -- functional, not tuned
+                if (H < 32 || H > 1024 || (H % 32))
+                    return bail(fail(e, B200OCR_E_INVALID, "layer %d: BiLSTM hidden size must be a multiple of 32 in [32, 1024] (got %d)", i, H));
                 // input projection of both directions as one GEMM: rows [dir][4H], bias = b_ih + b_hh
                 std::vector<float> wih(static_cast<size_t>(8) * H * d.cin), bsum(8 * H);
                 for (int dir = 0; dir < 2; ++dir) {
@@ -826,7 +830,8 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                 ly.hidden = H;
                 // recurrent weights for the tcgen05 kernel: [dir][plane][cta j][row = gate*32 + u][k]
                 const int P = e->lstm_planes;
-                std::vector<__half> rec(static_cast<size_t>(2) * P * 8 * 128 * H);
+                const bool tc = H == 256;
+                std::vector<__half> rec(tc ? static_cast<size_t>(2) * P * 8 * 128 * H : 0);
                 std::vector<float> wt(static_cast<size_t>(2) * H * 4 * H);
                 for (int dir = 0; dir < 2; ++dir)
                     for (int g = 0; g < 4; ++g)
@@ -835,16 +840,18 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                                 const float v = d.w_hh[dir][(static_cast<size_t>(g) * H + u) * H + k];
                                 const __half hi = __float2half_rn(v);
                                 const int j = u / 32, row = g * 32 + (u % 32);
-                                rec[(((static_cast<size_t>(dir) * P + 0) * 8 + j) * 128 + row) * H + k] = hi;
-                                if (P == 2)
-                                    rec[(((static_cast<size_t>(dir) * P + 1) * 8 + j) * 128 + row) * H + k] =
-                                        __float2half_rn(v - __half2float(hi));
+                                if (tc) {
+                                    rec[(((static_cast<size_t>(dir) * P + 0) * 8 + j) * 128 + row) * H + k] = hi;
+                                    if (P == 2)
+                                        rec[(((static_cast<size_t>(dir) * P + 1) * 8 + j) * 128 + row) * H + k] =
+                                            __float2half_rn(v - __half2float(hi));
+                                }
                                 // cross-check kernel: fp32 (x3) or the fp16-rounded value (fp16 mode), [dir][k][4H]
                                 wt[(static_cast<size_t>(dir) * H + k) * 4 * H + g * H + u] = P == 2 ? v : __half2float(hi);
                             }
-                if ((s = upload(e, rec.data(), rec.size(), &ly.w_rec))) return bail(s);
+                if (tc && (s = upload(e, rec.data(), rec.size(), &ly.w_rec))) return bail(s);
                 if ((s = upload(e, wt.data(), wt.size(), &ly.w_hh_t))) return bail(s);
-                if ((s = make_map_2d(e, &ly.tmW, ly.w_rec, H, static_cast<uint64_t>(2) * P * 8 * 128, 128))) return bail(s);
+                if (tc && (s = make_map_2d(e, &ly.tmW, ly.w_rec, H, static_cast<uint64_t>(2) * P * 8 * 128, 128))) return bail(s);
                 break;
             }
             case B200OCR_LN_PE:

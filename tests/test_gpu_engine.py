@@ -572,3 +572,18 @@ def test_embedding_conditioned_recogniser_matches_reference_golden(tmp_path, gol
         B200EngineLineOCR(write_engine_json(tmp_path, 'lstm'), torch.device('cuda', 0), module=net)
     with pytest.raises(ValueError):
         B200EngineLineOCR(write_engine_json(tmp_path, 'lstm', embed_id=1), torch.device('cuda', 0), module=make_case_net('lstm'))
+
+
+def test_other_lstm_hidden_size_matches_reference_golden(tmp_path, golden_dir):
+    """BiLSTM hidden size 128: the tcgen05 cluster kernel is built for 256, other sizes run on the generic fp32
+    recurrence kernel (kernels.cu: lstm_ref_kernel) behind the same tensor-core input projections -- against the
+    unmodified reference engine's golden."""
+    gold = load_golden(golden_dir, 'engine_lstm_h128.npz')
+    eng = _engine(tmp_path, 'lstm_h128', precision='fp16f8')
+    lines = cases.engine_lines('lstm_h128')
+    tr, lg, co = eng.process_lines([l.copy() for l in lines], sparse_logits=False)
+    worst = max(float(np.abs(lg[i] - gold[f'logits_{i}']).max()) for i in range(len(lines)))
+    print(f'hidden 128: max |d logit| = {worst:.2e}')
+    assert worst <= TOL, worst
+    assert tr == list(gold['transcriptions'])
+    assert [list(c) for c in co] == [list(gold[f'coords_{i}']) for i in range(len(lines))]
