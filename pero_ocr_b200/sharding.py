@@ -50,12 +50,33 @@ def gather_ids(local_ids, local_index, total_lines, group=None, device=None):
     everyone = torch.empty((world * n_max, 2 + l_max), dtype=torch.int32, device=device)
     dist.all_gather_into_tensor(everyone, mine, group=group)
     everyone = everyone.cpu().numpy().reshape(world * n_max, 2 + l_max)
-    out = [None] * total_lines
-    gi, ln = everyone[:, 0].tolist(), everyone[:, 1].tolist()
-    for r, (g, n) in enumerate(zip(gi, ln)):
-        if g >= 0:
-            out[g] = everyone[r, 2:2 + n]            # views of the gathered block
-    return out, int(everyone.nbytes)
+    return GatheredIds(everyone, total_lines), int(everyone.nbytes)
+
+
+class GatheredIds:
+    """The gathered records as a read-only sequence ordered by global line index: item g is the int32 label-id array
+    of line g (a view of the gathered block), None for a line nobody contributed.  Built with two vectorised passes --
+    at 100k lines a Python loop over the records costs more than the collective."""
+
+    def __init__(self, records, total_lines):
+        self._rec = records
+        self._row = np.full(total_lines, -1, dtype=np.int64)
+        valid = np.flatnonzero(records[:, 0] >= 0)
+        self._row[records[valid, 0]] = valid
+        self._len = np.zeros(total_lines, dtype=np.int64)
+        self._len[records[valid, 0]] = records[valid, 1]
+
+    def __len__(self):
+        return len(self._row)
+
+    def __getitem__(self, g):
+        if isinstance(g, slice):
+            return [self[i] for i in range(*g.indices(len(self)))]
+        r = int(self._row[g])
+        return None if r < 0 else self._rec[r, 2:2 + int(self._len[g])]
+
+    def __iter__(self):
+        return (self[g] for g in range(len(self)))
 
 
 class ShardedLineOCR:
