@@ -57,6 +57,10 @@ __device__ __forceinline__ uint32_t ld_pair(const __half* p) {   // two consecut
     return lo | (hi << 16);
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem_cf() {   // generic-proxy smem writes -> visible to tcgen05.mma
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
 template <int COUT, int STAGE>
 __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                               const uint2* __restrict__ wfrag,
@@ -224,6 +228,175 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- tcgen05 variant
+// The same arithmetic on the 5th-generation tensor cores (staging value 3; b200ocr_debug_set_flag 4).  The mma.sync
+// kernel above is bound by L1 / shared-memory wavefronts (ncu: l1tex 85 %): per 16-pixel m-tile a warp moves ~190
+// wavefronts of fragments and staged records for 64 MMAs' worth of work.  Here a CTA of 128 threads owns 128 pixels
+// of CFM_ROWS rows; per row
+//   * thread p gathers the 30 patch values of pixel p (three runs of 10 consecutive fp16 of the staged patch) and
+//     writes its 64-byte K row of the A tile [128 px][K = 32] in the K-major core-matrix layout (no swizzle: 8 rows x
+//     16 bytes per core matrix; consecutive threads write consecutive 16 bytes -- conflict-free);
+//   * one thread issues 4 tcgen05.mma (M = 128, N = COUT, K = 16; two K steps x hi / lo weight planes) into a TMEM
+//     accumulator and commits to an mbarrier; A tiles and accumulators are double-buffered, so the MMAs of row r + 1
+//     run under the epilogue of row r;
+//   * epilogue: tcgen05.ld of the thread's own TMEM lane (its pixel), scale / bias / activation, record planes, 256-bit
+//     stores straight from registers -- no staging of the records in shared memory at all.
+// Shared-memory traffic per 128-pixel row: 8 KB A written + 4 x (4 KB A + COUT x 32 B) read by the tensor core, against
+// ~190 KB of wavefronts for the same pixels above.
+template <int COUT>
+struct CftCfg {
+    static constexpr int kABytes = CFM_PX * 64;             // [128 px][32 fp16]
+    static constexpr int kALbo = (CFM_PX / 8) * 128;        // K-direction core-matrix stride
+    static constexpr int kBPlane = COUT * 64;               // [COUT][32 fp16]
+    static constexpr int kBLbo = (COUT / 8) * 128;
+    static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;
+};
+
+__device__ __forceinline__ uint64_t cft_desc(uint32_t addr, uint32_t lbo) {   // K-major, no swizzle, SBO = 128
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo >> 4) << 16;
+    d |= static_cast<uint64_t>(128 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
+                                                                  const uint4* __restrict__ wk,
+                                                                  const float* __restrict__ oscale,
+                                                                  const float* __restrict__ bias, int act, float slope,
+                                                                  int fmt, __half* __restrict__ out, int skip_lo,
+                                                                  const __grid_constant__ CUtensorMap tm_in) {
+    using C = CftCfg<COUT>;
+    const int planes = act_planes(fmt);
+    __shared__ __align__(16) __half s_p[(CFM_ROWS + 2) * CFM_PSTRIDE];
+    __shared__ __align__(128) uint8_t s_u8[(CFM_ROWS + 2) * CFM_U8ROW];
+    __shared__ __align__(128) uint8_t s_a[2 * C::kABytes];
+    __shared__ __align__(128) uint8_t s_bw[2 * C::kBPlane];
+    __shared__ __align__(8) uint64_t s_bar, s_done[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_sc[COUT];
+    __shared__ __align__(16) float s_b[COUT];
+
+    const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
+    const int tiles_h = (h + CFM_ROWS - 1) / CFM_ROWS;
+    const int tw = blockIdx.x % tiles_w;
+    const int row0 = ((blockIdx.x / tiles_w) % tiles_h) * CFM_ROWS;
+    const int img = blockIdx.x / (tiles_w * tiles_h);
+    const int w0 = tw * CFM_PX;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) {
+        ptx::mbar_init(&s_bar, 1);
+        ptx::mbar_init(&s_done[0], 1);
+        ptx::mbar_init(&s_done[1], 1);
+        ptx::fence_mbar_init();
+        ptx::mbar_expect_tx(&s_bar, (CFM_ROWS + 2) * CFM_U8ROW);
+        ptx::tma_load_3d(s_u8, &tm_in, &s_bar, w0 * 3 / 4 - 4, row0 - 1, img);
+    }
+    if (warp == 0) ptx::tmem_alloc<C::kTmemCols>(&s_tmem);
+    // weights [plane][COUT][32] (k contiguous) -> [plane][k chunk][n][8 fp16]
+    for (int i = tid; i < 2 * COUT * 4; i += CFM_PX) {
+        const int pl = i / (COUT * 4), rest = i - pl * COUT * 4;
+        const int nn = rest >> 2, j = rest & 3;
+        *reinterpret_cast<uint4*>(s_bw + pl * C::kBPlane + j * C::kBLbo + nn * 16) = __ldg(wk + i);
+    }
+    for (int i = tid; i < COUT; i += CFM_PX) {
+        s_sc[i] = oscale[i];
+        s_b[i] = bias ? bias[i] : 0.f;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    ptx::mbar_wait(&s_bar, 0);
+    constexpr int kRowVals = (CFM_PX + 2) * 3;
+    for (int i = tid; i < (CFM_ROWS + 2) * CFM_PSTRIDE; i += CFM_PX) {
+        const int r = i / CFM_PSTRIDE;
+        const int b = i - r * CFM_PSTRIDE;
+        const unsigned short v = b < kRowVals ? s_u8[r * CFM_U8ROW + CFM_U8OFF + b] : 0;
+        s_p[i] = __ushort2half_rn(v);
+    }
+    __syncthreads();
+
+    const int rows = min(CFM_ROWS, h - row0);
+    const uint32_t a_base = ptx::smem_u32(s_a), b_base = ptx::smem_u32(s_bw);
+    constexpr uint32_t idesc = ptx::idesc_f16_f32(CFM_PX, COUT);
+
+    auto build = [&](int rr, int buf) {            // A tile of output row rr: K row of pixel `tid`
+        uint32_t wd[16];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const __half* q = s_p + (rr + r) * CFM_PSTRIDE + 3 * tid;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) wd[5 * r + m] = ld_pair(q + 2 * m);
+        }
+        wd[15] = 0u;
+        uint8_t* dst = s_a + buf * C::kABytes + tid * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + j * C::kALbo) = make_uint4(wd[4 * j], wd[4 * j + 1], wd[4 * j + 2], wd[4 * j + 3]);
+    };
+    auto issue = [&](int buf) {                    // thread 0: 2 K steps x (hi, lo) planes into accumulator `buf`
+        const uint32_t acc = tmem_base + buf * COUT;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                ptx::mma_f16_ss(acc, cft_desc(a_base + buf * C::kABytes + ks * 2 * C::kALbo, C::kALbo),
+                                cft_desc(b_base + pl * C::kBPlane + ks * 2 * C::kBLbo, C::kBLbo), idesc,
+                                (pl | ks) ? 1u : 0u);
+        ptx::mma_commit(&s_done[buf]);
+    };
+
+    build(0, 0);
+    fence_proxy_async_smem_cf();
+    __syncthreads();
+    if (tid == 0) {
+        ptx::tc_fence_after();
+        issue(0);
+    }
+    const int px = w0 + tid;
+    const int rec = planes * COUT;
+    for (int rr = 0; rr < rows; ++rr) {
+        const int buf = rr & 1;
+        if (rr + 1 < rows) {
+            // A[buf ^ 1] was read by the MMAs of row rr - 1 (waited for in the previous iteration) and accumulator
+            // buf ^ 1 was drained by every thread before the barrier below
+            build(rr + 1, buf ^ 1);
+            fence_proxy_async_smem_cf();
+            ptx::tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                ptx::tc_fence_after();
+                issue(buf ^ 1);
+            }
+        }
+        ptx::mbar_wait(&s_done[buf], (rr >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + buf * COUT + (static_cast<uint32_t>(warp * 32) << 16);
+        __half* orow = out + ((static_cast<size_t>(img) * h + row0 + rr) * w + px) * rec;
+#pragma unroll
+        for (int n0 = 0; n0 < COUT; n0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(t_addr + n0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * s_sc[n0 + j]);
+            if (px < w)
+                epi_store32_v8(r, n0, 1.f, s_b, nullptr, nullptr, false, act, slope, orow, COUT, fmt, skip_lo != 0);
+        }
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
 }  // namespace
 
 size_t conv_first_wfrag_words(int cout) { return static_cast<size_t>(2) * 2 * (cout / 8) * 32 * 2; }
@@ -262,6 +435,52 @@ void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* osca
                         wfrag[((((p * 2 + ks) * NT + nt) * 32) + lane) * 2 + q] = lo | (hi << 16);
                     }
                 }
+}
+
+size_t conv_first_tc_words(int cout) { return static_cast<size_t>(2) * cout * 32 / 2; }   // 32-bit words
+
+void conv_first_pack_tc(const float* weight, int cout, uint32_t* wk) {
+    // [plane][cout][k = 10 r + 3 s + c, 32 slots] fp16, weights scaled per output channel like conv_first_pack
+    __half* dst = reinterpret_cast<__half*>(wk);
+    for (int o = 0; o < cout; ++o) {
+        float m = 0.f;
+        for (int i = 0; i < 27; ++i) m = fmaxf(m, fabsf(weight[o * 27 + i]));
+        int ex = 0;
+        if (m > 0.f) frexpf(m, &ex);
+        for (int k = 0; k < 32; ++k) {
+            float v = 0.f;
+            if (k < 30 && k % 10 != 9) {
+                const int r = k / 10, j = k % 10, sx = j / 3, c = j % 3;
+                v = ldexpf(weight[((o * 3 + c) * 3 + r) * 3 + sx], -ex);
+            }
+            const __half hi = __float2half_rn(v);
+            dst[(static_cast<size_t>(0) * cout + o) * 32 + k] = hi;
+            dst[(static_cast<size_t>(1) * cout + o) * 32 + k] = __float2half_rn(v - __half2float(hi));
+        }
+    }
+}
+
+cudaError_t launch_conv_first_tc(const uint8_t* in, int n, int h, int w, const uint32_t* wk, const float* oscale,
+                                 const float* bias, int cout, int act, float slope, int fmt, __half* out, int skip_lo,
+                                 const CUtensorMap* tm_in, cudaStream_t stream) {
+    if (!tm_in || (w % 16) || (cout != 64 && cout != 32)) return cudaErrorInvalidValue;
+    if (fmt != ACT_F16_F8) skip_lo = 0;
+    const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
+    const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
+    const uint4* wv = reinterpret_cast<const uint4*>(wk);
+    // 22 KB of unused dynamic shared memory cap the residency at four CTAs per SM = the 512 TMEM columns
+    constexpr int kPad = 22 * 1024;
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
+        cudaFuncSetAttribute(conv_first_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPad);
+        cudaFuncSetAttribute(conv_first_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPad);
+        attr_done.mark();
+    }
+    if (cout == 64)
+        conv_first_tc_kernel<64><<<grid, CFM_PX, kPad, stream>>>(in, n, h, w, wv, oscale, bias, act, slope, fmt, out, skip_lo, *tm_in);
+    else
+        conv_first_tc_kernel<32><<<grid, CFM_PX, kPad, stream>>>(in, n, h, w, wv, oscale, bias, act, slope, fmt, out, skip_lo, *tm_in);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const uint32_t* wfrag, const float* oscale,

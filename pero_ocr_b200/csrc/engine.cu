@@ -58,6 +58,7 @@ struct LayerRT {
     float* w_t = nullptr;    // CONV_FIRST: fp32 [27][cout]
     float* bias0 = nullptr;  // CONV_FIRST
     uint32_t* wfrag0 = nullptr;   // CONV_FIRST: mma.sync weight fragments (conv_first.cu)
+    uint32_t* wtc0 = nullptr;     // CONV_FIRST: [hi | lo][cout][32] fp16 weights of the tcgen05 variant
     float* oscale0 = nullptr;     // CONV_FIRST: per-channel power-of-two weight scale / 255
     int cout0 = 0;
     int hidden = 0;          // BILSTM
@@ -138,7 +139,8 @@ struct b200ocr_engine {
     int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
     bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
-    int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA; conv_first.cu)
+    int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA) on the mma.sync
+                              // kernel, 3 = TMA staging + the tcgen05 kernel (conv_first.cu)
     std::vector<LayerRT> layers;
     std::vector<void*> owned;
     // workspace
@@ -454,16 +456,20 @@ int walk(b200ocr_engine* e, const uint8_t* crops, int n, int h, int w, int n_lay
                     __half* rec = static_cast<__half*>(e->hbuf[slot]);
                     auto first = [&](const uint8_t* src, int n_lines) -> int {
                         CUtensorMap tm_crops;
-                        if (!e->use_ref && staging == 2)
+                        if (!e->use_ref && staging >= 2)
                             if (int s = make_map_crops(e, &tm_crops, src, n_lines, cur.h, cur.w)) return s;
                         ProfScope ps(e, st, PROF_CONV_FIRST);
                         if (e->use_ref)   // CUDA-core fp32 cross-check kernel
                             CU_TRY(e, launch_conv_first(src, n_lines, cur.h, cur.w, ly.w_t, ly.bias0, ly.cout0, ly.act, ly.g.act_slope,
                                                         e->fmt, rec, st));
+                        else if (staging == 3 && ly.wtc0)    // tcgen05 variant
+                            CU_TRY(e, launch_conv_first_tc(src, n_lines, cur.h, cur.w, ly.wtc0, ly.oscale0, ly.bias0, ly.cout0,
+                                                           ly.act, ly.g.act_slope, e->fmt, rec, next_skips_lo(li) ? 1 : 0,
+                                                           &tm_crops, st));
                         else
                             CU_TRY(e, launch_conv_first_mma(src, n_lines, cur.h, cur.w, ly.wfrag0, ly.oscale0, ly.bias0,
                                                             ly.cout0, ly.act, ly.g.act_slope, e->fmt, rec, next_skips_lo(li) ? 1 : 0,
-                                                            staging, staging == 2 ? &tm_crops : nullptr, st));
+                                                            std::min(staging, 2), staging >= 2 ? &tm_crops : nullptr, st));
                         e->launches++;
                         return 0;
                     };
@@ -804,6 +810,11 @@ int b200ocr_create(const b200ocr_net_desc_t* desc, b200ocr_engine_t** out) {
                 conv_first_pack(d.weight, d.cout, wf.data(), osc.data());
                 if ((s = upload(e, wf.data(), wf.size(), &ly.wfrag0))) return bail(s);
                 if ((s = upload(e, osc.data(), osc.size(), &ly.oscale0))) return bail(s);
+                if (d.cout >= 32) {
+                    std::vector<uint32_t> wk(conv_first_tc_words(d.cout));
+                    conv_first_pack_tc(d.weight, d.cout, wk.data());
+                    if ((s = upload(e, wk.data(), wk.size(), &ly.wtc0))) return bail(s);
+                }
                 break;
             }
             case B200OCR_CONV:
@@ -1515,7 +1526,7 @@ int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     if (flag == 1) e->use_halo = value != 0;
     else if (flag == 2) e->ar.linear_variant = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (flag == 3) e->lstm_hplanes = (value != 0 && e->lstm_planes == 2) ? 2 : 1;
-    else if (flag == 4) e->crop_staging = value < 0 || value > 2 ? 2 : value;
+    else if (flag == 4) e->crop_staging = value < 0 || value > 3 ? 2 : value;
     else if (flag == 5) e->ref_only_layer = value;
     else if (flag == 6) e->l2_chunk_lines = value < 0 ? 0 : value;
     else if (flag == 7) e->dynamic_tiles = value != 0;

@@ -24,6 +24,12 @@ cudaError_t launch_conv_first_mma(const uint8_t* in, int n, int h, int w, const 
                                   int staging,
                                   const CUtensorMap* tm_in, cudaStream_t stream);
 size_t conv_first_wfrag_words(int cout);
+// tcgen05 variant of the first conv (conv_first.cu): weights as [plane hi | lo][cout][32 K slots] fp16
+size_t conv_first_tc_words(int cout);
+void conv_first_pack_tc(const float* weight, int cout, uint32_t* wk);
+cudaError_t launch_conv_first_tc(const uint8_t* in, int n, int h, int w, const uint32_t* wk, const float* oscale,
+                                 const float* bias, int cout, int act, float slope, int fmt, __half* out, int skip_lo,
+                                 const CUtensorMap* tm_in, cudaStream_t stream);
 void conv_first_pack(const float* weight, int cout, uint32_t* wfrag, float* oscale);
 
 // Per-frame argmax (first maximal index, NaN maximal) / max / logsumexp / sparsified-softmax best prob over

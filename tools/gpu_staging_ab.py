@@ -22,13 +22,14 @@ out = {}
 ref = None
 res = {'workload': '256 x 40 x 1344 x 3 uint8 crops -> 64-channel records (conv_first_mma_kernel<64>)', 'runs': []}
 for rnd in range(2):
-    for variant, name in ((0, 'plain'), (1, 'cp.async'), (2, 'tma')):
+    for variant, name in ((0, 'plain'), (1, 'cp.async'), (2, 'tma'), (3, 'tma + tcgen05')):
         rec.set_flag(4, variant)
         o = rec.forward(crops, want_logits=True, out={})
         lg = o['logits'].clone()
         if ref is None:
             ref = lg
         same = bool(torch.equal(lg, ref))
+        dmax = float((lg - ref).abs().max())
         for _ in range(2):
             rec.forward(crops, want_logits=False, out=out)
         rec.profile(True)
@@ -39,5 +40,5 @@ for rnd in range(2):
         first = ms[tags == 0]
         res['runs'].append({'round': rnd, 'staging': name, 'conv_first_ms_mean': float(first.mean()),
                             'conv_first_ms_min': float(first.min()), 'step_ms': float(ms.sum() / 10),
-                            'logits_identical_to_plain': same})
+                            'logits_identical_to_plain': same, 'max_abs_logit_diff_to_plain': dmax})
 print(json.dumps(res, indent=1))
