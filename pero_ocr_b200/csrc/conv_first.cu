@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
 //     writes its 64-byte K row of the A tile [128 px][K = 32] in the K-major core-matrix layout (no swizzle: 8 rows x
 //     16 bytes per core matrix; consecutive threads write consecutive 16 bytes -- conflict-free);
 //   * one thread issues 4 tcgen05.mma (M = 128, N = COUT, K = 16; two K steps x hi / lo weight planes) into a TMEM
-//     accumulator and commits to an mbarrier; A tiles and accumulators are double-buffered, so the MMAs of row r + 1
-//     run under the epilogue of row r;
+//     accumulator and commits to an mbarrier; a CTA is strictly serial (build, MMA, epilogue) and small -- one A tile,
+//     64 TMEM columns, <= 64 registers per thread -- so that EIGHT CTAs share an SM and cover each other's latencies;
 //   * epilogue: tcgen05.ld of the thread's own TMEM lane (its pixel), scale / bias / activation, record planes, 256-bit
 //     stores straight from registers -- no staging of the records in shared memory at all.
 // Shared-memory traffic per 128-pixel row: 8 KB A written + 4 x (4 KB A + COUT x 32 B) read by the tensor core, against
@@ -250,7 +250,7 @@ struct CftCfg {
     static constexpr int kALbo = (CFM_PX / 8) * 128;        // K-direction core-matrix stride
     static constexpr int kBPlane = COUT * 64;               // [COUT][32 fp16]
     static constexpr int kBLbo = (COUT / 8) * 128;
-    static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;
+    static constexpr int kTmemCols = COUT < 32 ? 32 : COUT; // one accumulator: 8 CTAs x 64 columns fill an SM's TMEM
 };
 
 __device__ __forceinline__ uint64_t cft_desc(uint32_t addr, uint32_t lbo) {   // K-major, no swizzle, SBO = 128
@@ -262,8 +262,47 @@ __device__ __forceinline__ uint64_t cft_desc(uint32_t addr, uint32_t lbo) {   //
     return d;
 }
 
+// 16 consecutive channels [n0, n0 + 16) of one pixel: acc * scale + bias -> activation -> record planes.  hi: one
+// 256-bit store; lo' / hi8 (ACT_F16_F8) or lo (ACT_F16_HILO): 128- / 256-bit stores.
+__device__ __forceinline__ void cft_store16(const uint32_t (&r)[16], int n0, const float* s_sc, const float* s_b, int act,
+                                            float slope, __half* orow, int cout, int fmt, bool skip_lo) {
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            v[e] = cfm_act(fmaf(__uint_as_float(r[j + e]), s_sc[n0 + j + e], s_b[n0 + j + e]), act, slope);
+        const __half2 h01 = __floats2half2_rn(v[0], v[1]);
+        const __half2 h23 = __floats2half2_rn(v[2], v[3]);
+        ph[j >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
+        ph[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+        if (fmt != ACT_F16) {
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            if (fmt == ACT_F16_HILO) {
+                const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y);
+                const __half2 l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+                pl[j >> 1] = *reinterpret_cast<const uint32_t*>(&l01);
+                pl[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+            } else {
+                pl[j >> 2] = pack_e5m2x4((v[0] - f01.x) * kF8Scale, (v[1] - f01.y) * kF8Scale,
+                                         (v[2] - f23.x) * kF8Scale, (v[3] - f23.y) * kF8Scale);
+                pl[4 + (j >> 2)] = pack_e5m2x4(f01.x, f01.y, f23.x, f23.y);
+            }
+        }
+    }
+    uint8_t* rec = reinterpret_cast<uint8_t*>(orow);
+    st_global_v8(rec + n0 * 2, ph);
+    if (fmt == ACT_F16_HILO) {
+        st_global_v8(rec + cout * 2 + n0 * 2, pl);
+    } else if (fmt == ACT_F16_F8) {
+        if (!skip_lo) *reinterpret_cast<uint4*>(rec + cout * 2 + n0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        *reinterpret_cast<uint4*>(rec + cout * 3 + n0) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+    }
+}
+
 template <int COUT>
-__global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
+__global__ void __launch_bounds__(CFM_PX, 8) conv_first_tc_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                                   const uint4* __restrict__ wk,
                                                                   const float* __restrict__ oscale,
                                                                   const float* __restrict__ bias, int act, float slope,
@@ -273,9 +312,9 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
     const int planes = act_planes(fmt);
     __shared__ __align__(16) __half s_p[(CFM_ROWS + 2) * CFM_PSTRIDE];
     __shared__ __align__(128) uint8_t s_u8[(CFM_ROWS + 2) * CFM_U8ROW];
-    __shared__ __align__(128) uint8_t s_a[2 * C::kABytes];
+    __shared__ __align__(128) uint8_t s_a[C::kABytes];
     __shared__ __align__(128) uint8_t s_bw[2 * C::kBPlane];
-    __shared__ __align__(8) uint64_t s_bar, s_done[2];
+    __shared__ __align__(8) uint64_t s_bar, s_done;
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_sc[COUT];
     __shared__ __align__(16) float s_b[COUT];
@@ -290,8 +329,7 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
 
     if (tid == 0) {
         ptx::mbar_init(&s_bar, 1);
-        ptx::mbar_init(&s_done[0], 1);
-        ptx::mbar_init(&s_done[1], 1);
+        ptx::mbar_init(&s_done, 1);
         ptx::fence_mbar_init();
         ptx::mbar_expect_tx(&s_bar, (CFM_ROWS + 2) * CFM_U8ROW);
         ptx::tma_load_3d(s_u8, &tm_in, &s_bar, w0 * 3 / 4 - 4, row0 - 1, img);
@@ -324,72 +362,50 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
     const int rows = min(CFM_ROWS, h - row0);
     const uint32_t a_base = ptx::smem_u32(s_a), b_base = ptx::smem_u32(s_bw);
     constexpr uint32_t idesc = ptx::idesc_f16_f32(CFM_PX, COUT);
-
-    auto build = [&](int rr, int buf) {            // A tile of output row rr: K row of pixel `tid`
-        uint32_t wd[16];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const __half* q = s_p + (rr + r) * CFM_PSTRIDE + 3 * tid;
-#pragma unroll
-            for (int m = 0; m < 5; ++m) wd[5 * r + m] = ld_pair(q + 2 * m);
-        }
-        wd[15] = 0u;
-        uint8_t* dst = s_a + buf * C::kABytes + tid * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(dst + j * C::kALbo) = make_uint4(wd[4 * j], wd[4 * j + 1], wd[4 * j + 2], wd[4 * j + 3]);
-    };
-    auto issue = [&](int buf) {                    // thread 0: 2 K steps x (hi, lo) planes into accumulator `buf`
-        const uint32_t acc = tmem_base + buf * COUT;
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-                ptx::mma_f16_ss(acc, cft_desc(a_base + buf * C::kABytes + ks * 2 * C::kALbo, C::kALbo),
-                                cft_desc(b_base + pl * C::kBPlane + ks * 2 * C::kBLbo, C::kBLbo), idesc,
-                                (pl | ks) ? 1u : 0u);
-        ptx::mma_commit(&s_done[buf]);
-    };
-
-    build(0, 0);
-    fence_proxy_async_smem_cf();
-    __syncthreads();
-    if (tid == 0) {
-        ptx::tc_fence_after();
-        issue(0);
-    }
     const int px = w0 + tid;
     const int rec = planes * COUT;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     for (int rr = 0; rr < rows; ++rr) {
-        const int buf = rr & 1;
-        if (rr + 1 < rows) {
-            // A[buf ^ 1] was read by the MMAs of row rr - 1 (waited for in the previous iteration) and accumulator
-            // buf ^ 1 was drained by every thread before the barrier below
-            build(rr + 1, buf ^ 1);
-            fence_proxy_async_smem_cf();
-            ptx::tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                ptx::tc_fence_after();
-                issue(buf ^ 1);
+        {   // A tile of output row rr: the K row of pixel `tid` (k = 10 r + 3 s + c: three runs of ten patch values)
+            uint32_t wd[16];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const __half* q = s_p + (rr + r) * CFM_PSTRIDE + 3 * tid;
+#pragma unroll
+                for (int m = 0; m < 5; ++m) wd[5 * r + m] = ld_pair(q + 2 * m);
             }
+            wd[15] = 0u;
+            uint8_t* dst = s_a + tid * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(dst + j * C::kALbo) = make_uint4(wd[4 * j], wd[4 * j + 1], wd[4 * j + 2], wd[4 * j + 3]);
         }
-        ptx::mbar_wait(&s_done[buf], (rr >> 1) & 1);
+        fence_proxy_async_smem_cf();
+        ptx::tc_fence_before();      // this thread's tcgen05.ld of the previous row are done (wait::ld) and ordered
+        __syncthreads();
+        if (tid == 0) {              // 2 K steps x (hi, lo) weight planes
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    ptx::mma_f16_ss(tmem_base, cft_desc(a_base + ks * 2 * C::kALbo, C::kALbo),
+                                    cft_desc(b_base + pl * C::kBPlane + ks * 2 * C::kBLbo, C::kBLbo), idesc,
+                                    (pl | ks) ? 1u : 0u);
+            ptx::mma_commit(&s_done);
+        }
+        ptx::mbar_wait(&s_done, rr & 1);
         ptx::tc_fence_after();
-        const uint32_t t_addr = tmem_base + buf * COUT + (static_cast<uint32_t>(warp * 32) << 16);
         __half* orow = out + ((static_cast<size_t>(img) * h + row0 + rr) * w + px) * rec;
 #pragma unroll
-        for (int n0 = 0; n0 < COUT; n0 += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(t_addr + n0, r);
+        for (int n0 = 0; n0 < COUT; n0 += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(t_addr + n0, r);
             ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * s_sc[n0 + j]);
-            if (px < w)
-                epi_store32_v8(r, n0, 1.f, s_b, nullptr, nullptr, false, act, slope, orow, COUT, fmt, skip_lo != 0);
+            if (px < w) cft_store16(r, n0, s_sc, s_b, act, slope, orow, COUT, fmt, skip_lo != 0);
         }
-        ptx::tc_fence_before();
     }
+    ptx::tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         ptx::tc_fence_after();
@@ -468,14 +484,8 @@ cudaError_t launch_conv_first_tc(const uint8_t* in, int n, int h, int w, const u
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
     const uint4* wv = reinterpret_cast<const uint4*>(wk);
-    // 22 KB of unused dynamic shared memory cap the residency at four CTAs per SM = the 512 TMEM columns
-    constexpr int kPad = 22 * 1024;
-    static PerDeviceOnce attr_done;
-    if (attr_done.pending()) {
-        cudaFuncSetAttribute(conv_first_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPad);
-        cudaFuncSetAttribute(conv_first_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPad);
-        attr_done.mark();
-    }
+    // 64 registers x 128 threads: eight CTAs per SM = the 512 TMEM columns (8 x 64)
+    constexpr int kPad = 0;
     if (cout == 64)
         conv_first_tc_kernel<64><<<grid, CFM_PX, kPad, stream>>>(in, n, h, w, wv, oscale, bias, act, slope, fmt, out, skip_lo, *tm_in);
     else
