@@ -237,11 +237,12 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
 //   * thread p gathers the 30 patch values of pixel p (three runs of 10 consecutive fp16 of the staged patch) and
 //     writes its 64-byte K row of the A tile [128 px][K = 32] in the K-major core-matrix layout (no swizzle: 8 rows x
 //     16 bytes per core matrix; consecutive threads write consecutive 16 bytes -- conflict-free);
-//   * one thread issues 4 tcgen05.mma (M = 128, N = COUT, K = 16; two K steps x hi / lo weight planes) into a TMEM
-//     accumulator and commits to an mbarrier; a CTA is strictly serial (build, MMA, epilogue) and small -- one A tile,
-//     64 TMEM columns, <= 64 registers per thread -- so that EIGHT CTAs share an SM and cover each other's latencies;
-//   * epilogue: tcgen05.ld of the thread's own TMEM lane (its pixel), scale / bias / activation, record planes, 256-bit
-//     stores straight from registers -- no staging of the records in shared memory at all.
+//   * one thread issues 4 tcgen05.mma (M = 128, N = COUT, K = 16; two K steps x hi / lo weight planes) into one of two
+//     TMEM accumulators and commits to an mbarrier: the MMAs of row r + 1 run under the epilogue of row r;
+//   * epilogue: tcgen05.ld of the thread's own TMEM lane (its pixel), scale / bias / activation, record planes; the
+//     record is parked in the warp's private stage with 16-byte accesses (XOR-swizzled: conflict-free) and the warp
+//     writes its 32 records, contiguous in HBM, with fully coalesced stores.  (Storing each thread's record straight
+//     from registers -- 32-byte pieces 256 bytes apart -- costs more L1 wavefronts than the detour: measured.)
 // Shared-memory traffic per 128-pixel row: 8 KB A written + 4 x (4 KB A + COUT x 32 B) read by the tensor core, against
 // ~190 KB of wavefronts for the same pixels above.
 template <int COUT>
@@ -250,7 +251,7 @@ struct CftCfg {
     static constexpr int kALbo = (CFM_PX / 8) * 128;        // K-direction core-matrix stride
     static constexpr int kBPlane = COUT * 64;               // [COUT][32 fp16]
     static constexpr int kBLbo = (COUT / 8) * 128;
-    static constexpr int kTmemCols = COUT < 32 ? 32 : COUT; // one accumulator: 8 CTAs x 64 columns fill an SM's TMEM
+    static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;   // two accumulators
 };
 
 __device__ __forceinline__ uint64_t cft_desc(uint32_t addr, uint32_t lbo) {   // K-major, no swizzle, SBO = 128
@@ -262,13 +263,12 @@ __device__ __forceinline__ uint64_t cft_desc(uint32_t addr, uint32_t lbo) {   //
     return d;
 }
 
-// 16 consecutive channels [n0, n0 + 16) of one pixel: acc * scale + bias -> activation -> record planes.  hi: one
-// 256-bit store; lo' / hi8 (ACT_F16_F8) or lo (ACT_F16_HILO): 128- / 256-bit stores.
-__device__ __forceinline__ void cft_store16(const uint32_t (&r)[16], int n0, const float* s_sc, const float* s_b, int act,
-                                            float slope, __half* orow, int cout, int fmt, bool skip_lo) {
-    uint32_t ph[8], pl[8];
+// 32 consecutive channels [n0, n0 + 32) of the thread's pixel -> packed record words (ph: 16 words hi; pl: HILO 16
+// words lo, F8 8 words lo' + 8 words hi8), per-channel scale folded into the fma.
+__device__ __forceinline__ void cft_pack32(const uint32_t (&r)[32], int n0, const float* s_sc, const float* s_b, int act,
+                                           float slope, int fmt, uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
+    for (int j = 0; j < 32; j += 4) {
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -287,22 +287,14 @@ __device__ __forceinline__ void cft_store16(const uint32_t (&r)[16], int n0, con
             } else {
                 pl[j >> 2] = pack_e5m2x4((v[0] - f01.x) * kF8Scale, (v[1] - f01.y) * kF8Scale,
                                          (v[2] - f23.x) * kF8Scale, (v[3] - f23.y) * kF8Scale);
-                pl[4 + (j >> 2)] = pack_e5m2x4(f01.x, f01.y, f23.x, f23.y);
+                pl[8 + (j >> 2)] = pack_e5m2x4(f01.x, f01.y, f23.x, f23.y);
             }
         }
-    }
-    uint8_t* rec = reinterpret_cast<uint8_t*>(orow);
-    st_global_v8(rec + n0 * 2, ph);
-    if (fmt == ACT_F16_HILO) {
-        st_global_v8(rec + cout * 2 + n0 * 2, pl);
-    } else if (fmt == ACT_F16_F8) {
-        if (!skip_lo) *reinterpret_cast<uint4*>(rec + cout * 2 + n0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-        *reinterpret_cast<uint4*>(rec + cout * 3 + n0) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
     }
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(CFM_PX, 8) conv_first_tc_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
+__global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t* __restrict__ in, int n, int h, int w,
                                                                   const uint4* __restrict__ wk,
                                                                   const float* __restrict__ oscale,
                                                                   const float* __restrict__ bias, int act, float slope,
@@ -311,13 +303,15 @@ __global__ void __launch_bounds__(CFM_PX, 8) conv_first_tc_kernel(const uint8_t*
     using C = CftCfg<COUT>;
     const int planes = act_planes(fmt);
     __shared__ __align__(16) __half s_p[(CFM_ROWS + 2) * CFM_PSTRIDE];
-    __shared__ __align__(128) uint8_t s_u8[(CFM_ROWS + 2) * CFM_U8ROW];
     __shared__ __align__(128) uint8_t s_a[C::kABytes];
+    uint8_t* s_u8 = s_a;       // the staged uint8 patch (2.5 KB) lives in the A tile's space until it is widened
+    static_assert((CFM_ROWS + 2) * CFM_U8ROW <= C::kABytes, "patch must fit the A tile");
     __shared__ __align__(128) uint8_t s_bw[2 * C::kBPlane];
-    __shared__ __align__(8) uint64_t s_bar, s_done;
+    __shared__ __align__(8) uint64_t s_bar, s_done[2];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_sc[COUT];
     __shared__ __align__(16) float s_b[COUT];
+    extern __shared__ uint4 s_stage_tc[];        // [4 warps][32 px][planes * COUT / 8 chunks of 16 bytes]
 
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int tiles_h = (h + CFM_ROWS - 1) / CFM_ROWS;
@@ -325,11 +319,12 @@ __global__ void __launch_bounds__(CFM_PX, 8) conv_first_tc_kernel(const uint8_t*
     const int row0 = ((blockIdx.x / tiles_w) % tiles_h) * CFM_ROWS;
     const int img = blockIdx.x / (tiles_w * tiles_h);
     const int w0 = tw * CFM_PX;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         ptx::mbar_init(&s_bar, 1);
-        ptx::mbar_init(&s_done, 1);
+        ptx::mbar_init(&s_done[0], 1);
+        ptx::mbar_init(&s_done[1], 1);
         ptx::fence_mbar_init();
         ptx::mbar_expect_tx(&s_bar, (CFM_ROWS + 2) * CFM_U8ROW);
         ptx::tma_load_3d(s_u8, &tm_in, &s_bar, w0 * 3 / 4 - 4, row0 - 1, img);
@@ -362,48 +357,96 @@ __global__ void __launch_bounds__(CFM_PX, 8) conv_first_tc_kernel(const uint8_t*
     const int rows = min(CFM_ROWS, h - row0);
     const uint32_t a_base = ptx::smem_u32(s_a), b_base = ptx::smem_u32(s_bw);
     constexpr uint32_t idesc = ptx::idesc_f16_f32(CFM_PX, COUT);
-    const int px = w0 + tid;
-    const int rec = planes * COUT;
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int rr = 0; rr < rows; ++rr) {
-        {   // A tile of output row rr: the K row of pixel `tid` (k = 10 r + 3 s + c: three runs of ten patch values)
-            uint32_t wd[16];
+
+    auto build = [&](int rr) {                     // A tile of output row rr: the K row of pixel `tid`
+        uint32_t wd[16];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const __half* q = s_p + (rr + r) * CFM_PSTRIDE + 3 * tid;
+        for (int r = 0; r < 3; ++r) {
+            const __half* q = s_p + (rr + r) * CFM_PSTRIDE + 3 * tid;
 #pragma unroll
-                for (int m = 0; m < 5; ++m) wd[5 * r + m] = ld_pair(q + 2 * m);
-            }
-            wd[15] = 0u;
-            uint8_t* dst = s_a + tid * 16;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(dst + j * C::kALbo) = make_uint4(wd[4 * j], wd[4 * j + 1], wd[4 * j + 2], wd[4 * j + 3]);
+            for (int m = 0; m < 5; ++m) wd[5 * r + m] = ld_pair(q + 2 * m);
         }
-        fence_proxy_async_smem_cf();
-        ptx::tc_fence_before();      // this thread's tcgen05.ld of the previous row are done (wait::ld) and ordered
-        __syncthreads();
-        if (tid == 0) {              // 2 K steps x (hi, lo) weight planes
-            ptx::tc_fence_after();
+        wd[15] = 0u;
+        uint8_t* dst = s_a + tid * 16;
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl)
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + j * C::kALbo) = make_uint4(wd[4 * j], wd[4 * j + 1], wd[4 * j + 2], wd[4 * j + 3]);
+    };
+    auto issue = [&](int buf) {                    // thread 0: 2 K steps x (hi, lo) planes into accumulator `buf`
+        const uint32_t acc = tmem_base + buf * COUT;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                    ptx::mma_f16_ss(tmem_base, cft_desc(a_base + ks * 2 * C::kALbo, C::kALbo),
-                                    cft_desc(b_base + pl * C::kBPlane + ks * 2 * C::kBLbo, C::kBLbo), idesc,
-                                    (pl | ks) ? 1u : 0u);
-            ptx::mma_commit(&s_done);
-        }
-        ptx::mbar_wait(&s_done, rr & 1);
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                ptx::mma_f16_ss(acc, cft_desc(a_base + ks * 2 * C::kALbo, C::kALbo),
+                                cft_desc(b_base + pl * C::kBPlane + ks * 2 * C::kBLbo, C::kBLbo), idesc,
+                                (pl | ks) ? 1u : 0u);
+        ptx::mma_commit(&s_done[buf]);
+    };
+
+    build(0);
+    fence_proxy_async_smem_cf();
+    __syncthreads();
+    if (tid == 0) {
         ptx::tc_fence_after();
-        __half* orow = out + ((static_cast<size_t>(img) * h + row0 + rr) * w + px) * rec;
-#pragma unroll
-        for (int n0 = 0; n0 < COUT; n0 += 16) {
-            uint32_t r[16];
-            ptx::tmem_ld_32x32b_x16(t_addr + n0, r);
-            ptx::tmem_ld_wait();
-            if (px < w) cft_store16(r, n0, s_sc, s_b, act, slope, orow, COUT, fmt, skip_lo != 0);
+        issue(0);
+    }
+    const int rec = planes * COUT;               // fp16 units per pixel record
+    const int chunks = rec / 8;                  // 16-byte chunks per record (16 for the two-plane formats at COUT = 64)
+    uint4* stage = s_stage_tc + warp * 32 * chunks;
+    const int px0 = w0 + warp * 32;              // first pixel of this warp's 32
+    for (int rr = 0; rr < rows; ++rr) {
+        const int buf = rr & 1;
+        ptx::mbar_wait(&s_done[buf], (rr >> 1) & 1);          // MMAs of row rr done: A is free, accumulator buf is full
+        ptx::tc_fence_after();
+        if (rr + 1 < rows) {
+            build(rr + 1);
+            fence_proxy_async_smem_cf();
+            ptx::tc_fence_before();                           // the tcgen05.ld of row rr - 1 (accumulator buf ^ 1) are done
+            __syncthreads();
+            if (tid == 0) {
+                ptx::tc_fence_after();
+                issue(buf ^ 1);                               // runs under this row's epilogue
+            }
         }
+        // epilogue: this thread's pixel = its TMEM lane; the record is parked in the warp's stage (16-byte chunks
+        // XOR-swizzled by pixel) and the warp writes its 32 records -- contiguous in HBM -- with coalesced stores
+        const uint32_t t_addr = tmem_base + buf * COUT + (static_cast<uint32_t>(warp * 32) << 16);
+        uint4* my = stage + lane * chunks;
+        const int sw = lane & (chunks - 1);
+#pragma unroll
+        for (int n0 = 0; n0 < COUT; n0 += 32) {
+            uint32_t r[32], ph[16], pl[16];
+            ptx::tmem_ld_32x32b_x32(t_addr + n0, r);
+            ptx::tmem_ld_wait();
+            cft_pack32(r, n0, s_sc, s_b, act, slope, fmt, ph, pl);
+            const int c_hi = n0 / 8;                          // chunk of channel n0 in the hi plane
+#pragma unroll
+            for (int j = 0; j < 4; ++j) my[(c_hi + j) ^ sw] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+            if (fmt == ACT_F16_HILO) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    my[(COUT / 8 + c_hi + j) ^ sw] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            } else if (fmt == ACT_F16_F8) {
+                const int c_lo = COUT / 8 + n0 / 16, c_h8 = COUT / 8 + COUT / 16 + n0 / 16;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    my[(c_lo + j) ^ sw] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    my[(c_h8 + j) ^ sw] = make_uint4(pl[8 + 4 * j], pl[8 + 4 * j + 1], pl[8 + 4 * j + 2], pl[8 + 4 * j + 3]);
+                }
+            }
+        }
+        __syncwarp();
+        {
+            const int npx = min(32, w - px0);                 // pixels of this warp inside the image (<= 0: none)
+            uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row0 + rr) * w + px0) * rec);
+            for (int i = lane; i < npx * chunks; i += 32) {
+                const int p = i / chunks, c = i - p * chunks;
+                if (skip_lo && c >= COUT / 8 && c < COUT / 8 + COUT / 16) continue;
+                dst[i] = stage[p * chunks + (c ^ (p & (chunks - 1)))];
+            }
+        }
+        __syncwarp();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -484,8 +527,14 @@ cudaError_t launch_conv_first_tc(const uint8_t* in, int n, int h, int w, const u
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
     const uint4* wv = reinterpret_cast<const uint4*>(wk);
-    // 64 registers x 128 threads: eight CTAs per SM = the 512 TMEM columns (8 x 64)
-    constexpr int kPad = 0;
+    // dynamic shared memory: each warp's stage of 32 pixel records
+    const int kPad = 4 * 32 * act_planes(fmt) * cout * static_cast<int>(sizeof(__half));
+    static PerDeviceOnce attr_done;
+    if (attr_done.pending()) {
+        cudaFuncSetAttribute(conv_first_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(conv_first_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done.mark();
+    }
     if (cout == 64)
         conv_first_tc_kernel<64><<<grid, CFM_PX, kPad, stream>>>(in, n, h, w, wv, oscale, bias, act, slope, fmt, out, skip_lo, *tm_in);
     else
