@@ -355,8 +355,9 @@ int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
  * flag 2: split-K kernel for the per-step projections of b200ocr_ar_transcribe (default on; 0 = one K walker per tile);
  * flag 3: the BiLSTM recurrence also multiplies the fp16 rounding residual of h_t (three passes and twice the SM-to-SM
  * exchange per step; default on only in B200OCR_PREC_FP16X3);
- * flag 4: staging of the uint8 crop patch of the first convolution from HBM into shared memory: 2 = TMA box load
- * (default), 1 = 16-byte cp.async, 0 = plain byte loads (also the fallback when the batch width is not a multiple of 16);
+ * flag 4: the first convolution: 3 = TMA box load of the uint8 crop patch + the tcgen05 kernel (default for 32 / 64
+ * output channels), 2 = TMA box load + the mma.sync kernel, 1 = 16-byte cp.async, 0 = plain byte loads (the last two
+ * also on mma.sync; 0 is the fallback when the batch width is not a multiple of 16);
  * flag 5: index of ONE layer whose tensor-core contraction runs on the CUDA-core cross-check kernel while every other
  * layer stays on its product kernel (-1 = none): isolates a layer on identical inputs;
  * flag 6: lines per chunk of the first-conv + second-conv pair (the first conv's records then live and die in L2

@@ -139,7 +139,7 @@ struct b200ocr_engine {
     int igemm_dbg = 0;           // OR-ed into IgemmParams::dbg (flag 9): 4 = 16-byte epilogue stores
     bool attention_tc = true;    // Transformer variant: tcgen05 attention where it applies (attention_tc.cu; flag 8)
     int l2_chunk_lines = 0;   // first conv + next layer run over chunks of this many lines (0 = whole batch; flag 6)
-    int crop_staging = 2;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA) on the mma.sync
+    int crop_staging = 3;     // first conv: how the uint8 patch is staged (0 plain loads, 1 cp.async, 2 TMA) on the mma.sync
                               // kernel, 3 = TMA staging + the tcgen05 kernel (conv_first.cu)
     std::vector<LayerRT> layers;
     std::vector<void*> owned;
