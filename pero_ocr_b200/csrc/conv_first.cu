@@ -57,6 +57,15 @@ __device__ __forceinline__ uint32_t ld_pair(const __half* p) {   // two consecut
     return lo | (hi << 16);
 }
 
+// bulk copy shared::cta -> global (bytes a multiple of 16, both addresses 16-byte aligned), bulk-group completion
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async_smem_cf() {   // generic-proxy smem writes -> visible to tcgen05.mma
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
@@ -240,9 +249,10 @@ __global__ void __launch_bounds__(CFM_PX, 5) conv_first_mma_kernel(const uint8_t
 //   * one thread issues 4 tcgen05.mma (M = 128, N = COUT, K = 16; two K steps x hi / lo weight planes) into one of two
 //     TMEM accumulators and commits to an mbarrier: the MMAs of row r + 1 run under the epilogue of row r;
 //   * epilogue: tcgen05.ld of the thread's own TMEM lane (its pixel), scale / bias / activation, record planes; the
-//     record is parked in the warp's private stage with 16-byte accesses (XOR-swizzled: conflict-free) and the warp
-//     writes its 32 records, contiguous in HBM, with fully coalesced stores.  (Storing each thread's record straight
-//     from registers -- 32-byte pieces 256 bytes apart -- costs more L1 wavefronts than the detour: measured.)
+//     record is assembled in the thread's slot of a shared-memory stage (conflict-free 16-byte stores) and leaves as
+//     one cp.async.bulk shared -> global per pixel.  (Measured on the way: each thread storing its record straight
+//     from registers -- 32-byte pieces 256 bytes apart -- 1.55-1.70 ms; parking the records and reading them back for
+//     coalesced 16-byte stores 1.32 ms; the mma.sync kernel 1.45-1.55 ms.)
 // Shared-memory traffic per 128-pixel row: 8 KB A written + 4 x (4 KB A + COUT x 32 B) read by the tensor core, against
 // ~190 KB of wavefronts for the same pixels above.
 template <int COUT>
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_sc[COUT];
     __shared__ __align__(16) float s_b[COUT];
-    extern __shared__ uint4 s_stage_tc[];        // [4 warps][32 px][planes * COUT / 8 chunks of 16 bytes]
+    extern __shared__ uint4 s_stage_tc[];        // [4 warps][32 px][planes * COUT / 8 + 1 chunks of 16 bytes]
 
     const int tiles_w = (w + CFM_PX - 1) / CFM_PX;
     const int tiles_h = (h + CFM_ROWS - 1) / CFM_ROWS;
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
     }
     const int rec = planes * COUT;               // fp16 units per pixel record
     const int chunks = rec / 8;                  // 16-byte chunks per record (16 for the two-plane formats at COUT = 64)
-    uint4* stage = s_stage_tc + warp * 32 * chunks;
+    uint4* stage = s_stage_tc + warp * 32 * (chunks + 1);
     const int px0 = w0 + warp * 32;              // first pixel of this warp's 32
     for (int rr = 0; rr < rows; ++rr) {
         const int buf = rr & 1;
@@ -409,11 +419,14 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
                 issue(buf ^ 1);                               // runs under this row's epilogue
             }
         }
-        // epilogue: this thread's pixel = its TMEM lane; the record is parked in the warp's stage (16-byte chunks
-        // XOR-swizzled by pixel) and the warp writes its 32 records -- contiguous in HBM -- with coalesced stores
+        // epilogue: this thread's pixel = its TMEM lane.  The record is assembled in the thread's own slot of the stage
+        // (slots 16 bytes longer than a record: consecutive lanes start in consecutive bank groups, the 16-byte
+        // stores are conflict-free) and leaves as ONE bulk copy shared -> global per pixel (cp.async.bulk: the record
+        // is contiguous on both sides); no read-back through the LSU, no warp-level synchronisation -- a thread only
+        // waits for its own previous copy before it reuses its slot
         const uint32_t t_addr = tmem_base + buf * COUT + (static_cast<uint32_t>(warp * 32) << 16);
-        uint4* my = stage + lane * chunks;
-        const int sw = lane & (chunks - 1);
+        bulk_wait_read_all();
+        uint4* my = stage + lane * (chunks + 1);
 #pragma unroll
         for (int n0 = 0; n0 < COUT; n0 += 32) {
             uint32_t r[32], ph[16], pl[16];
@@ -422,32 +435,34 @@ __global__ void __launch_bounds__(CFM_PX, 4) conv_first_tc_kernel(const uint8_t*
             cft_pack32(r, n0, s_sc, s_b, act, slope, fmt, ph, pl);
             const int c_hi = n0 / 8;                          // chunk of channel n0 in the hi plane
 #pragma unroll
-            for (int j = 0; j < 4; ++j) my[(c_hi + j) ^ sw] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) my[c_hi + j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
             if (fmt == ACT_F16_HILO) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    my[(COUT / 8 + c_hi + j) ^ sw] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    my[COUT / 8 + c_hi + j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
             } else if (fmt == ACT_F16_F8) {
                 const int c_lo = COUT / 8 + n0 / 16, c_h8 = COUT / 8 + COUT / 16 + n0 / 16;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    my[(c_lo + j) ^ sw] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    my[(c_h8 + j) ^ sw] = make_uint4(pl[8 + 4 * j], pl[8 + 4 * j + 1], pl[8 + 4 * j + 2], pl[8 + 4 * j + 3]);
+                    my[c_lo + j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    my[c_h8 + j] = make_uint4(pl[8 + 4 * j], pl[8 + 4 * j + 1], pl[8 + 4 * j + 2], pl[8 + 4 * j + 3]);
                 }
             }
         }
-        __syncwarp();
-        {
-            const int npx = min(32, w - px0);                 // pixels of this warp inside the image (<= 0: none)
-            uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * h + row0 + rr) * w + px0) * rec);
-            for (int i = lane; i < npx * chunks; i += 32) {
-                const int p = i / chunks, c = i - p * chunks;
-                if (skip_lo && c >= COUT / 8 && c < COUT / 8 + COUT / 16) continue;
-                dst[i] = stage[p * chunks + (c ^ (p & (chunks - 1)))];
+        fence_proxy_async_smem_cf();
+        if (px0 + lane < w) {
+            uint8_t* dst = reinterpret_cast<uint8_t*>(out + ((static_cast<size_t>(img) * h + row0 + rr) * w + px0 + lane) * rec);
+            const uint32_t src = ptx::smem_u32(my);
+            if (skip_lo && fmt == ACT_F16_F8) {               // the lo' plane stays unwritten: hi, then hi8
+                bulk_store(dst, src, COUT * 2);
+                bulk_store(dst + COUT * 3, src + COUT * 3, COUT);
+            } else {
+                bulk_store(dst, src, rec * 2);
             }
         }
-        __syncwarp();
+        bulk_commit();
     }
+    bulk_wait_all();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -528,7 +543,7 @@ cudaError_t launch_conv_first_tc(const uint8_t* in, int n, int h, int w, const u
     const int grid = n * ((h + CFM_ROWS - 1) / CFM_ROWS) * tiles_w;
     const uint4* wv = reinterpret_cast<const uint4*>(wk);
     // dynamic shared memory: each warp's stage of 32 pixel records
-    const int kPad = 4 * 32 * act_planes(fmt) * cout * static_cast<int>(sizeof(__half));
+    const int kPad = 4 * 32 * (act_planes(fmt) * cout * static_cast<int>(sizeof(__half)) + 16);
     static PerDeviceOnce attr_done;
     if (attr_done.pending()) {
         cudaFuncSetAttribute(conv_first_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
