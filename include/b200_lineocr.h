@@ -29,7 +29,7 @@ enum b200ocr_status {
 };
 
 enum b200ocr_layer_kind {
-    B200OCR_CONV_FIRST = 1, /* u8 NHWC image -> /255 -> 3x3 conv (pad 1) + bias + act; CUDA cores (K = 27) */
+    B200OCR_CONV_FIRST = 1, /* u8 NHWC image -> /255 -> 3x3 conv (pad 1) + bias + act; tcgen05 (K = 27 padded to 32), conv_first.cu */
     B200OCR_CONV = 2,       /* kh x kw conv, fp16 NHWC in, tcgen05 implicit GEMM, fused bias+act+affine+max-pool */
     B200OCR_BILSTM = 3,     /* one bidirectional LSTM layer (PyTorch gate order i,f,g,o) */
     B200OCR_CTC_HEAD = 4,   /* per-frame linear -> logits [N,T,C] (+ fused per-frame argmax / max / logsumexp) */
