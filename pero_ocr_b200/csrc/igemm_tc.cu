@@ -3,13 +3,16 @@
 // Replaces the cuDNN / cuBLAS calls hidden inside the reference's TorchScript recogniser blob
 // (pero_ocr/ocr_engine/pytorch_ocr_engine.py:64-69; layer list = pero_ocr/ocr_engine/transformer.py:75-148,335-363).
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0     TMA producer: per (pass, tap, 64-channel chunk) four 4-D box loads of the NHWC activation
-//              (shifted by the tap; out-of-bounds = conv zero padding, filled by TMA) + one 2-D load of the weights
-//   warp 1     allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
-//   warps 2-5  epilogue: tcgen05.ld (one output pixel per thread, 32 channels per load), bias + activation,
-//              max-pool by warp shuffles, BatchNorm affine, fp16 hi/lo split, vectorised NHWC stores -- or the
-//              fused CTC epilogue (per-frame argmax / max / logsumexp; logits optional)
+// Structure (one persistent CTA per SM, 320 threads):
+//   warp 0     draws tiles (global counter, tilesched.cuh) and is the TMA producer: per (pass, tap, 64-channel chunk)
+//              four 4-D box loads of the NHWC activation (shifted by the tap; out-of-bounds = conv zero padding,
+//              filled by TMA) + one 2-D load of the weights
+//   warp 1     allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16; kind::f16 for the fp16 pass, kind::f8f6f4 with
+//              K=32 for the e5m2 correction pass) into one of two TMEM accumulators
+//   warps 2-9  epilogue, two warps per TMEM lane quarter (each takes half of the BN columns): tcgen05.ld (one
+//              output pixel per thread, 32 channels per load), bias + activation, max-pool by warp shuffles,
+//              BatchNorm affine, record planes, 256-bit NHWC stores -- or the fused CTC epilogue (per-frame argmax /
+//              max / logsumexp; logits optional)
 // A tile is 4 segments of 32 output pixels (th x 32/th); segment q feeds TMEM lanes [32q, 32q+32), so a 2x2 or
 // 2x1 max-pool never leaves the warp.
 #include "once.cuh"
