@@ -195,11 +195,13 @@ def test_halo_kernel_matches_per_tap_kernel(width, precision):
     assert torch.equal(a['labels'], b['labels'])
 
 
-@pytest.mark.parametrize('width', [40, 136, 264])
+@pytest.mark.parametrize('width', [40, 136, 264, 128, 272, 1344])
 def test_first_conv_tensor_core_kernel_is_fp32_grade(width):
-    """conv_first.cu (mma.sync, weights split hi+lo per channel scale, 1/255 in the epilogue) against torch fp32
-    conv2d(x / 255) and against the CUDA-core fp32 cross-check kernel, read back after the first layer.  The fp16x3
-    record (hi + lo) resolves ~2^-22 of the value, so the bar is a few fp32 ulps of the largest activation."""
+    """conv_first.cu (uint8 pixels as exact fp16 operands, weights split hi + lo per channel scale, 1/255 in the epilogue)
+    against torch fp32 conv2d(x / 255) and against the CUDA-core fp32 cross-check kernel, read back after the first
+    layer -- the tcgen05 kernel (widths that are multiples of 16: TMA-staged patch) and the mma.sync kernel under its
+    staging variants (flag 4; other widths fall back to plain loads).  The fp16x3 record (hi + lo) resolves ~2^-22 of
+    the value, so the bar is a few fp32 ulps of the largest activation."""
     from pero_ocr_b200 import netdesc
     from pero_ocr_b200.engine import LineRecognizer
     net = make_case_net('lstm')
@@ -210,16 +212,44 @@ def test_first_conv_tensor_core_kernel_is_fp32_grade(width):
     crops[0, :, :7] = 255                                   # saturated block at the left edge
     crops[1] = 0                                            # all-zero line: output = act(bias)
     d = torch.from_numpy(crops).cuda()
-    got = eng.debug_forward_prefix(d, 1)                    # [n, h, w, 64] fp32
-    eng.use_reference_kernels(True)
-    ref_kernel = eng.debug_forward_prefix(d, 1)
     conv = net.conv[0]
     with torch.no_grad():
         x = torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)
         want = torch.relu(conv(x)).permute(0, 2, 3, 1).numpy()
     scale = float(np.abs(want).max())
+    for staging in (3, 2, 1, 0):                            # 3 = tcgen05 (the default), 2 / 1 / 0 = mma.sync variants
+        eng.set_flag(4, staging)
+        got = eng.debug_forward_prefix(d, 1)                # [n, h, w, 64] fp32
+        assert np.abs(got - want).max() <= 4e-6 * max(scale, 1.0), staging
+    eng.set_flag(4, 3)
+    eng.use_reference_kernels(True)
+    ref_kernel = eng.debug_forward_prefix(d, 1)
     assert np.abs(ref_kernel - want).max() <= 4e-6 * max(scale, 1.0)
-    assert np.abs(got - want).max() <= 4e-6 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize('fmt_precision', ['fp16f8', 'fp16'])
+def test_first_conv_with_32_channels_and_leaky_slope(fmt_precision):
+    """The first conv alone with 32 output channels and LeakyReLU(0.2), both kernels, in the one- and two-plane record
+    formats (read back through the record: the bar is the record's resolution)."""
+    from pero_ocr_b200 import _lib
+    from pero_ocr_b200.engine import LineRecognizer
+    rng = np.random.default_rng(9)
+    wgt = (rng.standard_normal((32, 3, 3, 3)) * 0.3).astype(np.float32)
+    bias = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    layers = [dict(kind=_lib.CONV_FIRST, cin=3, cout=32, kh=3, kw=3, pad_h=1, pad_w=1, act=_lib.ACT_LEAKY_RELU, act_slope=0.2,
+                   pool_h=1, pool_w=1, weight=wgt, bias=bias)]
+    eng = LineRecognizer(layers, precision=fmt_precision)
+    crops = rng.integers(0, 256, (2, 40, 160, 3), dtype=np.uint8)
+    d = torch.from_numpy(crops).cuda()
+    with torch.no_grad():
+        x = torch.from_numpy(crops).float().div(255.0).permute(0, 3, 1, 2)
+        want = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, torch.from_numpy(wgt), torch.from_numpy(bias),
+                                                                        padding=1), 0.2).permute(0, 2, 3, 1).numpy()
+    tol = (2.0 ** -11 if fmt_precision == 'fp16' else 2.0 ** -13) * float(np.abs(want).max())
+    for staging in (3, 2):
+        eng.set_flag(4, staging)
+        got = eng.debug_forward_prefix(d, 1)
+        assert got.shape == want.shape and np.abs(got - want).max() <= tol, (staging, float(np.abs(got - want).max()), tol)
 
 
 def test_transformer_variant_on_a_very_long_line():
