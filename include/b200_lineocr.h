@@ -215,6 +215,12 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
                         const int64_t* coord_off, const int32_t* widths, int32_t n, int32_t line_h, uint8_t* out,
                         int32_t out_w, int32_t pad, void* cuda_stream);
 
+/* Plumbing for results that go straight into caller-owned host memory (the CSC parts of TextLine.logits, which the
+ * reference builds on the host, line_ocr_engine.py:168-172): one stream-ordered device -> host copy.  `host_dst` should
+ * be page-locked (cudaHostRegister / cudaHostAlloc) for the copy to be asynchronous; the caller synchronises the
+ * stream before reading. */
+int b200ocr_memcpy_d2h_async(void* host_dst, const void* device_src, int64_t bytes, void* cuda_stream);
+
 /* Replaces the zero padding + stacking of BaseEngineLineOCR.process_lines (pero_ocr/ocr_engine/line_ocr_engine.py:
  * 121-127: `batch_data[i, :, 32:32 + w_i] = line_i`, lines beyond the batch width cut) on the device, so that the host
  * stages each crop with ONE contiguous copy and no padding bytes cross PCIe.

@@ -75,6 +75,7 @@ EXPORTS = {
     'b200ocr_set_layer_correction': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     'b200ocr_executed_passes': (C.c_double, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'b200ocr_run_after': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'b200ocr_memcpy_d2h_async': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'b200ocr_set_layer_post_shift': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'b200ocr_profile_read_since': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]),

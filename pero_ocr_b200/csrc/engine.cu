@@ -1203,6 +1203,16 @@ int b200ocr_remap_lines(const uint8_t* image, int32_t img_h, int32_t img_w, cons
     return B200OCR_OK;
 }
 
+int b200ocr_memcpy_d2h_async(void* host_dst, const void* device_src, int64_t bytes, void* cuda_stream) {
+    if (bytes < 0 || (bytes > 0 && (!host_dst || !device_src)))
+        return fail(nullptr, B200OCR_E_INVALID, "bad memcpy_d2h_async arguments");
+    if (bytes == 0) return B200OCR_OK;
+    DeviceGuard guard(device_src);
+    CU_TRY(nullptr, cudaMemcpyAsync(host_dst, device_src, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost,
+                                    static_cast<cudaStream_t>(cuda_stream)));
+    return B200OCR_OK;
+}
+
 int b200ocr_pad_lines(const uint8_t* packed, const int64_t* line_off, const int32_t* widths, int32_t n, int32_t line_h,
                       uint8_t* out, int32_t out_w, int32_t pad, void* cuda_stream) {
     if (n < 0 || line_h <= 0 || !out || out_w <= 0 || (out_w % 4) || pad < 0 || (n > 0 && (!packed || !line_off || !widths)))

@@ -54,9 +54,12 @@ class SparseLogits:
                 if bd is not None:
                     indices = np.frombuffer(bi, dtype=np.int32, count=total)
                     data = np.frombuffer(bd, dtype=np.float32, count=total)
-                    with torch.cuda.device(self.indices.device), torch.cuda.stream(stream):
-                        torch.from_numpy(indices).copy_(self.indices[:total], non_blocking=True)
-                        torch.from_numpy(data).copy_(self.data[:total], non_blocking=True)
+                    # straight cudaMemcpyAsync into the registered block: no torch tensor over the caller's arrays (torch
+                    # keeps such a tensor alive past the copy when it does not recognise the memory as page-locked)
+                    lib = _lib.load_library()
+                    for dst, src in ((indices, self.indices), (data, self.data)):
+                        _lib.check(lib.b200ocr_memcpy_d2h_async(C.c_void_p(dst.ctypes.data), C.c_void_p(src.data_ptr()),
+                                                                4 * total, C.c_void_p(stream.cuda_stream)))
                     stream.synchronize()
                     return indptr, base, _Owned(indices), _Owned(data)
                 del bi
