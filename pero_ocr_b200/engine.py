@@ -595,8 +595,12 @@ class B200EngineLineOCR:
 
     def _run_batches(self, widths, stager, sparse_logits, tight_crop_logits, no_logits, return_ids):
         """Common driver of process_lines / process_line_maps / process_baselines: one job through _run_jobs."""
-        for result in self._run_jobs([(widths, stager)], sparse_logits, tight_crop_logits, no_logits, return_ids):
-            return result
+        gen = self._run_jobs([(widths, stager)], sparse_logits, tight_crop_logits, no_logits, return_ids)
+        try:
+            return next(gen)
+        finally:
+            gen.close()         # unwinds the pipeline's frames now: they reference the results (and through them the
+                                # page-locked blocks) and sit in a reference cycle that only the cyclic GC would free
 
     def _run_jobs(self, jobs, sparse_logits, tight_crop_logits, no_logits, return_ids):
         """Generator over `jobs` = iterable of (widths, stager): the lines of one call (or one page) each.

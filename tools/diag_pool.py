@@ -45,3 +45,35 @@ def show(obj, depth=0, seen=None):
             show(r, depth + 1, seen)
 if w_blk() is not None:
     show(w_blk())
+print('slots keys', [sorted(k for k in sl.keys()) for sl in (eng._slots or [])][:1])
+print('gc.garbage', len(gc.garbage))
+import threading
+print('threads', [t.name for t in threading.enumerate()])
+eng._slots = None
+gc.collect()
+print('after dropping slots', {k: len(v) for k, v in pool.free.items()}, w_blk() is not None)
+eng._executor = None
+gc.collect()
+print('after dropping executor', {k: len(v) for k, v in pool.free.items()}, w_blk() is not None)
+models = eng._models
+del eng
+gc.collect()
+print('after dropping engine', {k: len(v) for k, v in pool.free.items()}, w_blk() is not None)
+del models
+gc.collect()
+print('after dropping models', {k: len(v) for k, v in pool.free.items()}, w_blk() is not None)
+import scipy.sparse as sp
+objs = [o for o in gc.get_objects() if isinstance(o, sp.csc_matrix)]
+print('live csc matrices', len(objs))
+if objs:
+    for r in gc.get_referrers(objs[0])[:5]:
+        d = type(r).__name__
+        if isinstance(r, (list, tuple)): d += f' len={len(r)}'
+        if isinstance(r, dict): d += ' keys=' + str(list(r.keys())[:8])
+        print('  csc referrer:', d)
+        for r2 in gc.get_referrers(r)[:4]:
+            d2 = type(r2).__name__
+            if isinstance(r2, dict): d2 += ' keys=' + str(list(r2.keys())[:8])
+            if hasattr(r2, 'gi_code'): d2 += ' ' + r2.gi_code.co_name
+            if hasattr(r2, 'f_code'): d2 += ' ' + r2.f_code.co_name
+            print('     <-', d2[:160])
