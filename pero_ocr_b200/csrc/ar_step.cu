@@ -20,12 +20,18 @@
 
 namespace {
 
-// tokens == nullptr: every line starts from `start_token` (position 0).
+// tokens == nullptr: every line starts from `start_token` (position 0).  pos_dev != nullptr: the position is read from
+// device memory and `tokens` is the BASE of the [position][line] token matrix (the previous position's row is the
+// input; position 0 starts from `start_token`) -- every argument is then the same for all positions (CUDA graph).
 __global__ void embed_pe_kernel(const float* __restrict__ table, const int32_t* __restrict__ tokens, int start_token,
-                                int n, int d, int pos, float* __restrict__ out) {
+                                int n, int d, int pos, const int32_t* __restrict__ pos_dev, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * d) return;
     const int line = i / d, c = i - line * d;
+    if (pos_dev) {
+        pos = *pos_dev;
+        tokens = pos > 0 ? tokens + static_cast<size_t>(pos - 1) * n : nullptr;
+    }
     const int tok = tokens ? tokens[line] : start_token;
     // pe[pos, 2m] = sin(pos * exp(2m * -ln(1e4)/d)), pe[pos, 2m+1] = cos(same)   (transformer.py:321-328)
     const int m2 = c & ~1;
@@ -165,7 +171,8 @@ __global__ void __launch_bounds__(64 * LKG) linear_f32_splitk_kernel(const float
                                                                      float* __restrict__ out, long ldo, int M, int O,
                                                                      int K, int relu, int split_o,
                                                                      float* __restrict__ out2, long ldo2,
-                                                                     long part_stride) {
+                                                                     long part_stride, const int32_t* __restrict__ pos_dev,
+                                                                     long out_pos_stride, long out2_pos_stride) {
     __shared__ float xs[LKG][LBK][LLD];   // [group][k][m]; afterwards [group][m][o] partial sums
     __shared__ float ws[LKG][LBK][LLD];   // [group][k][o]
     const int m0 = blockIdx.y * LBM, o0 = blockIdx.x * LBN;
@@ -175,6 +182,11 @@ __global__ void __launch_bounds__(64 * LKG) linear_f32_splitk_kernel(const float
     const int c_lo = static_cast<int>(static_cast<long>(all_chunks) * z / Z);
     const int chunks = static_cast<int>(static_cast<long>(all_chunks) * (z + 1) / Z);
     if (Z > 1) { out += z * part_stride; bias = nullptr; res = nullptr; relu = 0; }
+    if (pos_dev) {                       // outputs that move with the decoded position (cache slot, logits row)
+        const long pos = *pos_dev;
+        out += pos * out_pos_stride;
+        if (out2) out2 += pos * out2_pos_stride;
+    }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -306,10 +318,12 @@ template <int HD>
 __global__ void __launch_bounds__(128) step_attention_cta_kernel(const float* __restrict__ q, long q_ls,
                                                                  const float* __restrict__ k,
                                                                  const float* __restrict__ v, long ps, long ls, int S,
-                                                                 int d, int heads, float* __restrict__ out) {
+                                                                 int d, int heads, float* __restrict__ out,
+                                                                 const int32_t* __restrict__ pos_dev) {
     extern __shared__ float s_w[];                  // [S] scores / weights, [4][HD] partial outputs, [8] reductions
     constexpr int SEG = HD / 8, LPR = HD / 4, RPW = 32 / LPR;
-    float* s_part = s_w + ((S + 3) & ~3);           // 16-byte aligned
+    float* s_part = s_w + ((S + 3) & ~3);           // 16-byte aligned (S = the launch's upper bound)
+    if (pos_dev) S = min(S, *pos_dev + 1);          // cached self-attention: positions 0 .. pos
     float* s_red = s_part + 4 * HD;
     const int line = blockIdx.x / heads, head = blockIdx.x - line * heads;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -408,10 +422,17 @@ __device__ __forceinline__ bool score_better(float v, int i, float bv, int bi) {
 
 // One CTA for the whole batch (a few hundred lines x a few hundred classes): warp per line.
 // state[0] = lines still alive after this step, state[1] = first step after which none was (-1 until then).
+// use_pos: the step is state[2]; `logits` / `tokens_out` are bases that advance by logits_pos_stride / n per position, and
+// state[2] is incremented at the end (the token loop as a replayed CUDA graph).
 __global__ void argmax_alive_kernel(const float* __restrict__ logits, long ld, int n, int C, int stop_token, int step,
                                     int32_t* __restrict__ tokens_out, int32_t* __restrict__ alive,
-                                    int32_t* __restrict__ state) {
+                                    int32_t* __restrict__ state, int use_pos, long logits_pos_stride) {
     __shared__ int total;
+    if (use_pos) {
+        step = state[2];
+        logits += step * logits_pos_stride;
+        tokens_out += static_cast<size_t>(step) * n;
+    }
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
@@ -441,21 +462,22 @@ __global__ void argmax_alive_kernel(const float* __restrict__ logits, long ld, i
     if (threadIdx.x == 0) {
         state[0] = total;
         if (total == 0 && state[1] < 0) state[1] = step;
+        if (use_pos) state[2] = step + 1;
     }
 }
 
 __global__ void ar_init_kernel(int32_t* alive, int n, int32_t* state) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) alive[i] = 1;
-    if (i == 0) { state[0] = n; state[1] = -1; }
+    if (i == 0) { state[0] = n; state[1] = -1; state[2] = 0; }
 }
 
 }  // namespace
 
 cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start_token, int n, int d, int pos,
-                            float* out, cudaStream_t stream) {
+                            float* out, cudaStream_t stream, const int32_t* pos_dev) {
     if (n <= 0) return cudaSuccess;
-    embed_pe_kernel<<<(n * d + 255) / 256, 256, 0, stream>>>(table, tokens, start_token, n, d, pos, out);
+    embed_pe_kernel<<<(n * d + 255) / 256, 256, 0, stream>>>(table, tokens, start_token, n, d, pos, pos_dev, out);
     return cudaGetLastError();
 }
 
@@ -467,7 +489,7 @@ cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const fl
     const dim3 grid((O + LBN - 1) / LBN, (M + LBM - 1) / LBM);
     if (variant == 1)
         linear_f32_splitk_kernel<<<grid, 64 * LKG, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu, O,
-                                                                nullptr, 0, 0);
+                                                                nullptr, 0, 0, nullptr, 0, 0);
     else
         linear_f32_kernel<<<grid, 64, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu);
     return cudaGetLastError();
@@ -475,14 +497,16 @@ cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const fl
 
 cudaError_t launch_linear_f32_ex(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
                                  float* out, long ldo, int M, int O, int K, int relu, int split_o, float* out2,
-                                 long ldo2, int ksplit, long part_stride, cudaStream_t stream) {
+                                 long ldo2, int ksplit, long part_stride, cudaStream_t stream, const int32_t* pos_dev,
+                                 long out_pos_stride, long out2_pos_stride) {
     if (M <= 0 || O <= 0) return cudaSuccess;
     if (K <= 0 || (K % LBK) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
         ksplit < 1 || ksplit > K / LBK || (split_o < O && !out2) || (ksplit > 1 && (split_o < O || part_stride < static_cast<long>(M) * ldo)))
         return cudaErrorInvalidValue;
     const dim3 grid((O + LBN - 1) / LBN, (M + LBM - 1) / LBM, ksplit);
     linear_f32_splitk_kernel<<<grid, 64 * LKG, 0, stream>>>(x, ldx, w, bias, res, ldr, out, ldo, M, O, K, relu,
-                                                            std::min(split_o, O), out2, ldo2, part_stride);
+                                                            std::min(split_o, O), out2, ldo2, part_stride, pos_dev,
+                                                            out_pos_stride, out2_pos_stride);
     return cudaGetLastError();
 }
 
@@ -504,9 +528,11 @@ cudaError_t launch_sum_layernorm(const float* part, int Z, long part_stride, con
 }
 
 cudaError_t launch_argmax_alive(const float* logits, long ld, int n, int C, int stop_token, int step,
-                                int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream) {
+                                int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream, int use_pos,
+                                long logits_pos_stride) {
     if (n <= 0) return cudaSuccess;
-    argmax_alive_kernel<<<1, 256, 0, stream>>>(logits, ld, n, C, stop_token, step, tokens_out, alive, state);
+    argmax_alive_kernel<<<1, 256, 0, stream>>>(logits, ld, n, C, stop_token, step, tokens_out, alive, state, use_pos,
+                                               logits_pos_stride);
     return cudaGetLastError();
 }
 
@@ -516,7 +542,8 @@ cudaError_t launch_ar_init(int32_t* alive, int n, int32_t* state, cudaStream_t s
 }
 
 cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
-                                  int S, int d, int heads, float* out, int variant, cudaStream_t stream) {
+                                  int S, int d, int heads, float* out, int variant, cudaStream_t stream,
+                                  const int32_t* pos_dev) {
     if (n <= 0 || S <= 0) return cudaSuccess;
     const int hd = heads > 0 ? d / heads : 0;
     if (heads <= 0 || hd * heads != d || (hd % 4) || hd > 128 || (ps % 4) || (ls % 4) ||
@@ -524,11 +551,12 @@ cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, con
         return cudaErrorInvalidValue;
     if (variant == 1 && (hd == 32 || hd == 64 || hd == 128) && S <= 8192) {
         const size_t sm = (((static_cast<size_t>(S) + 3) & ~size_t(3)) + 4 * hd + 8) * sizeof(float);      // < 48 KB
-        if (hd == 32) step_attention_cta_kernel<32><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
-        else if (hd == 64) step_attention_cta_kernel<64><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
-        else step_attention_cta_kernel<128><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out);
+        if (hd == 32) step_attention_cta_kernel<32><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out, pos_dev);
+        else if (hd == 64) step_attention_cta_kernel<64><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out, pos_dev);
+        else step_attention_cta_kernel<128><<<n * heads, 128, sm, stream>>>(q, q_ls, k, v, ps, ls, S, d, heads, out, pos_dev);
         return cudaGetLastError();
     }
+    if (pos_dev) return cudaErrorInvalidValue;      // the device-side position needs the CTA-per-head kernel
     const int warps = 4;
     const size_t smem = static_cast<size_t>(warps) * (S + 128) * sizeof(float);
     if (smem > 160 * 1024) return cudaErrorInvalidValue;

@@ -101,6 +101,20 @@ struct ArState {
     float* selfkv = nullptr;   // [layer][cap_steps][lines][2D]    K | V of the decoded positions
     float *x = nullptr, *q = nullptr, *a = nullptr, *t = nullptr, *f = nullptr, *lg = nullptr;
     float* part = nullptr;     // [kArSplitMax][lines][D] partial sums of the K-split projections
+    // token loop v3: the launches of one position as a CUDA graph, replayed on the engine's own stream
+    struct GraphKey {
+        int n, T, max_steps, start_token;
+        const void *tokens, *logits, *workspace;
+        int variant;
+        bool operator==(const GraphKey& o) const {
+            return n == o.n && T == o.T && max_steps == o.max_steps && start_token == o.start_token && tokens == o.tokens &&
+                   logits == o.logits && workspace == o.workspace && variant == o.variant;
+        }
+    };
+    GraphKey gkey{};
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t loop_stream = nullptr;
+    cudaEvent_t loop_fork = nullptr, loop_join = nullptr;
     int32_t *alive = nullptr, *state = nullptr;
     int32_t* h_state = nullptr;   // pinned host copy of `state`
     std::vector<void*> ws;
@@ -987,6 +1001,10 @@ void b200ocr_destroy(b200ocr_engine_t* e) {
     if (e->best) { cudaFree(e->best); cudaFree(e->fmax); cudaFree(e->flse); cudaFree(e->fprob); }
     for (void* p : e->ar.ws) cudaFree(p);
     if (e->ar.h_state) cudaFreeHost(e->ar.h_state);
+    if (e->ar.gexec) cudaGraphExecDestroy(e->ar.gexec);
+    if (e->ar.loop_fork) cudaEventDestroy(e->ar.loop_fork);
+    if (e->ar.loop_join) cudaEventDestroy(e->ar.loop_join);
+    if (e->ar.loop_stream) cudaStreamDestroy(e->ar.loop_stream);
     if (e->after) {
         auto& f = e->after->followers;
         f.erase(std::remove(f.begin(), f.end(), e), f.end());
@@ -1374,7 +1392,7 @@ int b200ocr_ar_reserve(b200ocr_engine_t* e, int32_t max_lines, int32_t max_width
     CU_TRY(e, grab(static_cast<size_t>(N) * ar.dim_ff * sizeof(float), reinterpret_cast<void**>(&ar.f)));
     CU_TRY(e, grab(static_cast<size_t>(N) * ar.classes * sizeof(float), reinterpret_cast<void**>(&ar.lg)));
     CU_TRY(e, grab(static_cast<size_t>(N) * sizeof(int32_t), reinterpret_cast<void**>(&ar.alive)));
-    CU_TRY(e, grab(2 * sizeof(int32_t), reinterpret_cast<void**>(&ar.state)));
+    CU_TRY(e, grab(4 * sizeof(int32_t), reinterpret_cast<void**>(&ar.state)));
     ar.cap_lines = N; ar.cap_T = T; ar.cap_steps = S;
     return B200OCR_OK;
 }
@@ -1425,64 +1443,132 @@ int b200ocr_ar_transcribe(b200ocr_engine_t* e, const uint8_t* crops, int32_t n, 
     const int att = ar.linear_variant >= 2 ? 1 : 0;
     const long part_stride = static_cast<long>(ar.cap_lines) * D;
     auto ksplit = [](int K) { return std::max(1, std::min(kArSplitMax, K / 32 / 8)); };   // >= 8 chunks per CTA
-    // norm(x + W a + b): the projection's K split over CTAs, summed in the LayerNorm (fused), or the fused epilogue
-    // of one CTA per tile + the plain LayerNorm
-    auto proj_norm = [&](const float* a, int K, const float* w, const float* b, const float* gamma,
-                         const float* beta) -> int {
-        if (fused) {
-            const int Z = ksplit(K);
-            AR_LAUNCH(launch_linear_f32_ex(a, K, w, nullptr, nullptr, 0, ar.part, D, n, D, K, 0, D, nullptr, 0, Z,
-                                           part_stride, st));
-            AR_LAUNCH(launch_sum_layernorm(ar.part, Z, part_stride, b, ar.x, n, D, gamma, beta, 1e-5f, ar.x, st));
-        } else {
-            AR_LAUNCH(launch_linear_f32(a, K, w, b, ar.x, D, ar.t, D, n, D, K, 0, lv, st));
-            AR_LAUNCH(launch_layernorm(ar.t, n, D, gamma, beta, 1e-5f, 0, ar.x, nullptr, e->fmt, st));
-        }
-        return B200OCR_OK;
-    };
-    for (int s = 0; s < max_steps; ++s) {
-        AR_LAUNCH(launch_embed_pe(ar.embed, s == 0 ? nullptr : tokens + static_cast<size_t>(s - 1) * n, start_token, n, D,
-                                  s, ar.x, st));
+    const int hd = ar.heads > 0 ? D / ar.heads : 0;
+    // The launches of one decoded position.  pos_dev == nullptr: position `s` as immediates.  pos_dev != nullptr
+    // (token loop v3): the position is the device-side counter state[2] -- cache slot, token row, logits row and the
+    // self-attention length are derived from it inside the kernels, so the arguments are the same for every
+    // position and the 25 launches are captured ONCE into a CUDA graph and replayed.
+    auto position = [&](int s, cudaStream_t ls, const int32_t* pos_dev) -> int {
+        // norm(x + W a + b): the projection's K split over CTAs, summed in the LayerNorm (fused), or the fused epilogue
+        // of one CTA per tile + the plain LayerNorm
+        auto proj_norm = [&](const float* a, int K, const float* w, const float* b, const float* gamma,
+                             const float* beta) -> int {
+            if (fused) {
+                const int Z = ksplit(K);
+                AR_LAUNCH(launch_linear_f32_ex(a, K, w, nullptr, nullptr, 0, ar.part, D, n, D, K, 0, D, nullptr, 0, Z,
+                                               part_stride, ls));
+                AR_LAUNCH(launch_sum_layernorm(ar.part, Z, part_stride, b, ar.x, n, D, gamma, beta, 1e-5f, ar.x, ls));
+            } else {
+                AR_LAUNCH(launch_linear_f32(a, K, w, b, ar.x, D, ar.t, D, n, D, K, 0, lv, ls));
+                AR_LAUNCH(launch_layernorm(ar.t, n, D, gamma, beta, 1e-5f, 0, ar.x, nullptr, e->fmt, ls));
+            }
+            return B200OCR_OK;
+        };
+        const int32_t* prev = pos_dev ? tokens : (s == 0 ? nullptr : tokens + static_cast<size_t>(s - 1) * n);
+        AR_LAUNCH(launch_embed_pe(ar.embed, prev, start_token, n, D, s, ar.x, ls, pos_dev));
         for (int i = 0; i < L; ++i) {
             const ArLayer& ly = ar.layers[i];
             float* kv = ar.selfkv + i * selfkv_layer;                       // position p at + p * n * 2D
-            float* kv_s = kv + static_cast<size_t>(s) * n * 2 * D;
+            float* kv_s = pos_dev ? kv : kv + static_cast<size_t>(s) * n * 2 * D;
             const float* mkv = ar.memkv + i * memkv_layer;                  // row (line * T + t) * 2D
             // cached self-attention over positions 0..s (DecoderLayer.infer, transformer.py:431-435)
             if (ar.linear_variant >= 2) {
                 AR_LAUNCH(launch_linear_f32_ex(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, 3 * D, D, 0, D,
-                                               kv_s, 2 * D, 1, 0, st));
+                                               kv_s, 2 * D, 1, 0, ls, pos_dev, 0, static_cast<long>(n) * 2 * D));
             } else {
-                AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, lv, st));
+                AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w, ly.self_in_b, nullptr, 0, ar.q, D, n, D, D, 0, lv, ls));
                 AR_LAUNCH(launch_linear_f32(ar.x, D, ly.self_in_w + static_cast<size_t>(D) * D, ly.self_in_b + D, nullptr, 0,
-                                            kv_s, 2 * D, n, 2 * D, D, 0, lv, st));
+                                            kv_s, 2 * D, n, 2 * D, D, 0, lv, ls));
             }
-            AR_LAUNCH(launch_step_attention(ar.q, D, kv, kv + D, static_cast<long>(n) * 2 * D, 2 * D, n, s + 1, D,
-                                            ar.heads, ar.a, att, st));
+            AR_LAUNCH(launch_step_attention(ar.q, D, kv, kv + D, static_cast<long>(n) * 2 * D, 2 * D, n,
+                                            pos_dev ? max_steps : s + 1, D, ar.heads, ar.a, att, ls, pos_dev));
             if (int r = proj_norm(ar.a, D, ly.self_out_w, ly.self_out_b, ly.n1w, ly.n1b)) return r;
             // encoder-decoder attention over the T memory frames (:438-447)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, lv, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.cross_q_w, ly.cross_q_b, nullptr, 0, ar.q, D, n, D, D, 0, lv, ls));
             AR_LAUNCH(launch_step_attention(ar.q, D, mkv, mkv + D, 2 * D, static_cast<long>(T) * 2 * D, n, T, D, ar.heads,
-                                            ar.a, att, st));
+                                            ar.a, att, ls));
             if (int r = proj_norm(ar.a, D, ly.cross_out_w, ly.cross_out_b, ly.n2w, ly.n2b)) return r;
             // feed-forward (:449-450)
-            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, lv, st));
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ly.l1w, ly.l1b, nullptr, 0, ar.f, FF, n, FF, D, 1, lv, ls));
             if (int r = proj_norm(ar.f, FF, ly.l2w, ly.l2b, ly.n3w, ly.n3b)) return r;
         }
         // dec_out_proj + argmax + alive mask (transformer_ocr_engine.py:69-75)
-        float* lg = logits ? logits + static_cast<size_t>(s) * C : ar.lg;
         const long lg_ld = logits ? static_cast<long>(max_steps) * C : C;
-        AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, lv, st));
-        AR_LAUNCH(launch_argmax_alive(lg, lg_ld, n, C, start_token, s, tokens + static_cast<size_t>(s) * n, ar.alive,
-                                      ar.state, st));
-        if ((s + 1) % check_every == 0 || s + 1 == max_steps) {
-            CU_TRY(e, cudaMemcpyAsync(ar.h_state, ar.state, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            CU_TRY(e, cudaStreamSynchronize(st));
-            if (ar.h_state[1] >= 0) {
-                done_steps = ar.h_state[1] + 1;
-                break;
+        const long lg_pos = logits ? C : 0;                                 // the logits row of a position
+        if (pos_dev) {
+            float* lg = logits ? logits : ar.lg;
+            AR_LAUNCH(launch_linear_f32_ex(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, C, nullptr, 0, 1, 0,
+                                           ls, pos_dev, lg_pos, 0));
+            AR_LAUNCH(launch_argmax_alive(lg, lg_ld, n, C, start_token, 0, tokens, ar.alive, ar.state, ls, 1, lg_pos));
+        } else {
+            float* lg = logits ? logits + static_cast<size_t>(s) * C : ar.lg;
+            AR_LAUNCH(launch_linear_f32(ar.x, D, ar.out_w, ar.out_b, nullptr, 0, lg, lg_ld, n, C, D, 0, lv, ls));
+            AR_LAUNCH(launch_argmax_alive(lg, lg_ld, n, C, start_token, s, tokens + static_cast<size_t>(s) * n, ar.alive,
+                                          ar.state, ls));
+        }
+        return B200OCR_OK;
+    };
+    auto finished = [&](cudaStream_t ls) -> int {          // 1: every line has emitted the stop symbol, 0: not yet, < 0: error
+        if (cudaMemcpyAsync(ar.h_state, ar.state, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ls) != cudaSuccess ||
+            cudaStreamSynchronize(ls) != cudaSuccess)
+            return -1;
+        if (ar.h_state[1] >= 0) {
+            done_steps = ar.h_state[1] + 1;
+            return 1;
+        }
+        return 0;
+    };
+    const bool graph = ar.linear_variant >= 3 && fused && (hd == 32 || hd == 64 || hd == 128) && max_steps > 2;
+    if (!graph) {
+        for (int s = 0; s < max_steps; ++s) {
+            if (int r = position(s, st, nullptr)) return r;
+            if ((s + 1) % check_every == 0 || s + 1 == max_steps) {
+                const int f = finished(st);
+                if (f < 0) return fail(e, B200OCR_E_CUDA, "token loop: stop check failed: %s", cudaGetErrorString(cudaGetLastError()));
+                if (f) break;
             }
         }
+    } else {
+        // the loop runs on the engine's own stream (the caller's may be the legacy default stream, which cannot be
+        // captured), forked from and joined to the caller's stream by events
+        if (!ar.loop_stream) {
+            CU_TRY(e, cudaStreamCreateWithFlags(&ar.loop_stream, cudaStreamNonBlocking));
+            CU_TRY(e, cudaEventCreateWithFlags(&ar.loop_fork, cudaEventDisableTiming));
+            CU_TRY(e, cudaEventCreateWithFlags(&ar.loop_join, cudaEventDisableTiming));
+        }
+        cudaStream_t ls = ar.loop_stream;
+        CU_TRY(e, cudaEventRecord(ar.loop_fork, st));
+        CU_TRY(e, cudaStreamWaitEvent(ls, ar.loop_fork, 0));
+        const int32_t* pos_dev = ar.state + 2;
+        const int64_t before = e->launches;
+        if (int r = position(0, ls, pos_dev)) return r;    // position 0 eagerly: one-time kernel attributes are set here
+        const int per_position = static_cast<int>(e->launches - before);
+        const ArState::GraphKey key{n, T, max_steps, start_token, tokens, logits, ar.x, ar.linear_variant};
+        if (!ar.gexec || !(ar.gkey == key)) {
+            if (ar.gexec) { cudaGraphExecDestroy(ar.gexec); ar.gexec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU_TRY(e, cudaStreamBeginCapture(ls, cudaStreamCaptureModeThreadLocal));
+            const int rc = position(1, ls, pos_dev);
+            const cudaError_t ce = cudaStreamEndCapture(ls, &g);
+            e->launches -= per_position;                   // captured, not launched
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(e, B200OCR_E_CUDA, "token loop: graph capture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&ar.gexec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) return fail(e, B200OCR_E_CUDA, "token loop: graph instantiation failed: %s", cudaGetErrorString(ie));
+            ar.gkey = key;
+        }
+        for (int s = 1; s < max_steps; ++s) {
+            CU_TRY(e, cudaGraphLaunch(ar.gexec, ls));
+            e->launches += per_position;
+            if ((s + 1) % check_every == 0 || s + 1 == max_steps) {
+                const int f = finished(ls);
+                if (f < 0) return fail(e, B200OCR_E_CUDA, "token loop: stop check failed: %s", cudaGetErrorString(cudaGetLastError()));
+                if (f) break;
+            }
+        }
+        CU_TRY(e, cudaEventRecord(ar.loop_join, ls));
+        CU_TRY(e, cudaStreamWaitEvent(st, ar.loop_join, 0));
     }
 #undef AR_LAUNCH
     *steps = done_steps >= 0 ? done_steps : max_steps;
@@ -1534,7 +1620,7 @@ int b200ocr_profile_read_since(b200ocr_engine_t* e, void* reference, int32_t cap
 int b200ocr_debug_set_flag(b200ocr_engine_t* e, int32_t flag, int32_t value) {
     if (!e) return B200OCR_E_INVALID;
     if (flag == 1) e->use_halo = value != 0;
-    else if (flag == 2) e->ar.linear_variant = value < 0 ? 0 : (value > 2 ? 2 : value);
+    else if (flag == 2) e->ar.linear_variant = value < 0 ? 0 : (value > 3 ? 3 : value);
     else if (flag == 3) e->lstm_hplanes = (value != 0 && e->lstm_planes == 2) ? 2 : 1;
     else if (flag == 4) e->crop_staging = value < 0 || value > 3 ? 2 : value;
     else if (flag == 5) e->ref_only_layer = value;

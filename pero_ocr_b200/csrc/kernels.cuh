@@ -46,8 +46,10 @@ size_t force_align_workspace_bytes(int n, int t_max, int l_max);
 
 // Autoregressive decoder step kernels (ar_step.cu; transformer_ocr_engine.py:49-89, transformer.py:183-305, 418-462).
 // embed_pe: out[line][:] = table[tokens ? tokens[line] : start_token][:] + sinusoid(pos)   (fp32 [n][d])
+// pos_dev (optional, all four launchers below): the decoded position lives in device memory, so that the launch
+// arguments of a position are the same for every position and the token loop can be replayed as a CUDA graph.
 cudaError_t launch_embed_pe(const float* table, const int32_t* tokens, int start_token, int n, int d, int pos,
-                            float* out, cudaStream_t stream);
+                            float* out, cudaStream_t stream, const int32_t* pos_dev = nullptr);
 // out[m][o] = act(x[m][:] . w[o][:] + bias[o]) (+ res[m][o]); fp32, w = Linear weight [O][K], K % 32 == 0.
 // variant 0: one 64-thread group walks K; 1: four groups split K (register prefetch, fixed-order reduction).
 cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
@@ -57,7 +59,8 @@ cudaError_t launch_linear_f32(const float* x, long ldx, const float* w, const fl
 // residual; needs split_o >= O).  launch_sum_layernorm finishes (b): LayerNorm(sum_z part[z] + bias + res).
 cudaError_t launch_linear_f32_ex(const float* x, long ldx, const float* w, const float* bias, const float* res, long ldr,
                                  float* out, long ldo, int M, int O, int K, int relu, int split_o, float* out2,
-                                 long ldo2, int ksplit, long part_stride, cudaStream_t stream);
+                                 long ldo2, int ksplit, long part_stride, cudaStream_t stream,
+                                 const int32_t* pos_dev = nullptr, long out_pos_stride = 0, long out2_pos_stride = 0);
 bool sum_layernorm_supported(int d);
 cudaError_t launch_sum_layernorm(const float* part, int Z, long part_stride, const float* bias, const float* res,
                                  int rows, int d, const float* gamma, const float* beta, float eps, float* out,
@@ -65,10 +68,12 @@ cudaError_t launch_sum_layernorm(const float* part, int Z, long part_stride, con
 // one query position per (line, head) against S key / value positions (position p of line l at + p*ps + l*ls).
 // variant 0: one warp per (line, head); 1: one CTA per (line, head), coalesced rows (heads of 32 / 64 / 128).
 cudaError_t launch_step_attention(const float* q, long q_ls, const float* k, const float* v, long ps, long ls, int n,
-                                  int S, int d, int heads, float* out, int variant, cudaStream_t stream);
+                                  int S, int d, int heads, float* out, int variant, cudaStream_t stream,
+                                  const int32_t* pos_dev = nullptr);
 // greedy choice + alive mask + stop detection; state = {alive lines, first step after which none was alive or -1}.
 cudaError_t launch_argmax_alive(const float* logits, long ld, int n, int C, int stop_token, int step,
-                                int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream);
+                                int32_t* tokens_out, int32_t* alive, int32_t* state, cudaStream_t stream, int use_pos = 0,
+                                long logits_pos_stride = 0);
 cudaError_t launch_ar_init(int32_t* alive, int n, int32_t* state, cudaStream_t stream);
 
 // Per-character confidences (char_conf.cu; core/confidence_estimation.py:73-104).

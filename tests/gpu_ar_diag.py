@@ -58,7 +58,7 @@ def main():
         'max_abs_diff_to_default': float(np.abs(logits_v[:, :steps] - logits[:, :steps]).max()) if logits_v.shape == logits.shape else None}
     # timing of both variants, crops resident on the device: golden batch (warm), 64 and 256 lines x 1088 px
     sb = cases.AR_CASE['classes'] - 2
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         eng.net.set_flag(2, variant)
         for name, n in (('n3', 3), ('n64', 64), ('n256', 256)):
             rng = np.random.default_rng(5)

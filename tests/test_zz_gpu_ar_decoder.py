@@ -57,12 +57,13 @@ def _oracle_memory(net, nchw_u8):
         return net.trans_encoder(net.input_norm(y) + net.pe[:y.size(0)]).numpy()
 
 
-@pytest.mark.parametrize('linear_variant', [2, 1, 0])
+@pytest.mark.parametrize('linear_variant', [3, 2, 1, 0])
 def test_transcribe_batch_matches_reference_golden(tmp_path, golden_dir, linear_variant):
     gold = load_golden(golden_dir, 'ar_decoder.npz')
     net, dec, sd = cases.ar_state_dict()
     eng = _engine(tmp_path, sd)
-    # token-loop kernels: 2 = default (q|k|v in one launch, K split over CTAs + summing LayerNorm, CTA-per-head step
+    # token-loop kernels: 3 = the launches of a position replayed as a CUDA graph (device-side position counter) on top
+    # of 2 = (q|k|v in one launch, K split over CTAs + summing LayerNorm, CTA-per-head step
     # attention), 1 = split-K projections + warp-per-head attention, 0 = single K walker
     eng.net.set_flag(2, linear_variant)
     assert eng.sentence_boundary_ind == cases.AR_CASE['classes'] - 2 and eng.ignore_ind == cases.AR_CASE['classes'] - 1
