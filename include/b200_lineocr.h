@@ -358,7 +358,9 @@ int b200ocr_profile_read_since(b200ocr_engine_t* e, void* reference, int32_t cap
  * operands, fp32 accumulate) so the tcgen05 path can be checked on a GPU box where the reference is absent. */
 int b200ocr_debug_use_reference_kernels(b200ocr_engine_t* e, int32_t on);
 /* A/B switches for kernel variants (tests, profiling).  flag 1: halo-reuse 3x3 kernel for cin <= 128 (default on);
- * flag 2: split-K kernel for the per-step projections of b200ocr_ar_transcribe (default on; 0 = one K walker per tile);
+ * flag 2: token-loop kernels of b200ocr_ar_transcribe: 0 = one K walker per projection tile, 1 = split-K projections,
+ * 2 = 1 + q | k | v in one launch, K split over CTAs summed in the LayerNorm, CTA-per-(line, head) step attention,
+ * 3 (default) = 2 with the decoded position in device memory and the launches of a position replayed as a CUDA graph;
  * flag 3: the BiLSTM recurrence also multiplies the fp16 rounding residual of h_t (three passes and twice the SM-to-SM
  * exchange per step; default on only in B200OCR_PREC_FP16X3);
  * flag 4: the first convolution: 3 = TMA box load of the uint8 crop patch + the tcgen05 kernel (default for 32 / 64

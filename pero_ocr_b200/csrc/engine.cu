@@ -88,10 +88,11 @@ constexpr int kArSplitMax = 4;
 
 struct ArState {
     bool attached = false;
-    // token-loop kernels (b200ocr_debug_set_flag 2): 0 = tiled projections, 1 = split-K projections, 2 (default) =
-    // split-K projections with q | k | v in one launch, the K split of the out-projections and of the second
-    // feed-forward matrix spread over CTAs and summed inside the LayerNorm, CTA-per-(line, head) step attention
-    int linear_variant = 2;
+    // token-loop kernels (b200ocr_debug_set_flag 2): 0 = tiled projections, 1 = split-K projections, 2 = split-K
+    // projections with q | k | v in one launch, the K split of the out-projections and of the second feed-forward
+    // matrix spread over CTAs and summed inside the LayerNorm, CTA-per-(line, head) step attention; 3 (default) = 2 with
+    // the position in device memory and the 25 launches of a position replayed as a CUDA graph
+    int linear_variant = 3;
     int heads = 0, dim_ff = 0, classes = 0, D = 0;
     std::vector<ArLayer> layers;
     float *embed = nullptr, *out_w = nullptr, *out_b = nullptr;
