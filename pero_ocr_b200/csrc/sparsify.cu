@@ -308,11 +308,84 @@ __global__ void full_logprobs_kernel(const float* __restrict__ logits, long fram
     }
 }
 
+// Tiled variant: CTA per chunk of 32 frames of the flattened [frames][C] matrix.  The chunk is read once, coalesced,
+// into shared memory; thread f < 32 makes the sequential passes of frame f there (same order as the kernel above: the
+// results are bit-identical); then all threads write the chunk's doubles in memory order (coalesced).
+__global__ void __launch_bounds__(ST_THREADS) full_logprobs_tiled_kernel(const float* __restrict__ logits, long frames,
+                                                                         int C, double* __restrict__ out) {
+    extern __shared__ float s_dyn[];
+    const int pitch = st_pitch(C);
+    float* tile = s_dyn;
+    float* s_mx = s_dyn + ST_FRAMES * pitch;      // [32] max of the raw frame
+    float* s_sum = s_mx + ST_FRAMES;              // [32] sum of exp(raw - max)
+    float* s_mx2 = s_sum + ST_FRAMES;             // [32] max of the densified frame
+    float* s_lse = s_mx2 + ST_FRAMES;             // [32] log of the densified frame's sum
+    const long f0 = static_cast<long>(blockIdx.x) * ST_FRAMES;
+    const int nf = static_cast<int>(min(static_cast<long>(ST_FRAMES), frames - f0));
+    const float* src = logits + f0 * C;
+    for (int i = threadIdx.x; i < nf * C; i += ST_THREADS) {
+        const int f = i / C, c = i - f * C;
+        tile[f * pitch + c] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < nf) {
+        const float* row = tile + threadIdx.x * pitch;
+        float mx = row[0];
+        bool nan = mx != mx;
+        for (int c = 1; c < C; ++c) {
+            const float v = row[c];
+            if (v != v) nan = true;
+            mx = fmaxf(mx, v);
+        }
+        if (nan) mx = __int_as_float(0x7fc00000);
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+        float mx2 = -INFINITY;
+        bool nan2 = false;
+        for (int c = 0; c < C; ++c) {
+            const float v = row[c];
+            const float d = sp_keep(v, mx, sum) ? v : -80.f;
+            if (d != d) nan2 = true;
+            mx2 = fmaxf(mx2, d);
+        }
+        if (nan2) mx2 = __int_as_float(0x7fc00000);
+        float sum2 = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float v = row[c];
+            const float d = sp_keep(v, mx, sum) ? v : -80.f;
+            sum2 += expf(d - mx2);
+        }
+        s_mx[threadIdx.x] = mx;
+        s_sum[threadIdx.x] = sum;
+        s_mx2[threadIdx.x] = mx2;
+        s_lse[threadIdx.x] = logf(sum2);
+    }
+    __syncthreads();
+    double* dst = out + f0 * C;
+    for (int i = threadIdx.x; i < nf * C; i += ST_THREADS) {
+        const int f = i / C, c = i - f * C;
+        const float v = tile[f * pitch + c];
+        const float d = sp_keep(v, s_mx[f], s_sum[f]) ? v : -80.f;
+        dst[i] = static_cast<double>((d - s_mx2[f]) - s_lse[f]);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_full_logprobs(const float* logits, int n, int T, int C, double* out, cudaStream_t stream) {
     const long frames = static_cast<long>(n) * T;
     if (frames <= 0) return cudaSuccess;
+    const size_t dyn = (static_cast<size_t>(ST_FRAMES) * ((C + 1) | 1) + 4 * ST_FRAMES) * sizeof(float);
+    if (dyn <= 200 * 1024) {
+        static PerDeviceOnce attr_done;
+        if (attr_done.pending()) {
+            cudaFuncSetAttribute(full_logprobs_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done.mark();
+        }
+        full_logprobs_tiled_kernel<<<static_cast<unsigned>((frames + ST_FRAMES - 1) / ST_FRAMES), ST_THREADS, dyn, stream>>>(
+            logits, frames, C, out);
+        return cudaGetLastError();
+    }
     full_logprobs_kernel<<<static_cast<unsigned>((frames + 127) / 128), 128, 0, stream>>>(logits, frames, C, out);
     return cudaGetLastError();
 }

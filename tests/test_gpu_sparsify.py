@@ -89,3 +89,26 @@ def test_sparsify_nan_and_config1_size():
     assert flips <= 2
     total = int(sp.base.cpu()[-1])
     assert total == sum(m.nnz for m in got)
+
+
+def test_full_logprobs_device_matches_the_reference_chain():
+    """b200ocr_full_logprobs (tiled kernel) against what TextLine.get_full_logprobs() returns after the reference's
+    sparsify -> CSC round trip (line_ocr_engine.py:168-172, core/layout.py:65-72), frame counts that are not multiples
+    of the kernel's 32-frame chunk, a NaN and exact zeros included."""
+    from oracle.forward_oracle import full_logprobs, sparsify_logits
+    from pero_ocr_b200.decoders import full_logprobs_device
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal((5, 77, 120)) * 6.0).astype(np.float32)
+    x[1, 3, 5] = 0.0
+    x[2, 40] = 0.0
+    x[3, 10, 7] = np.nan
+    got = full_logprobs_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert got.dtype == np.float64 and got.shape == x.shape
+    for i in range(x.shape[0]):
+        if i == 3:
+            continue                                        # the NaN frame: compared separately below
+        want = full_logprobs(sparsify_logits(x[i]))
+        np.testing.assert_allclose(got[i], want, atol=2e-5)
+    assert np.isnan(got[3, 10]).all()                       # a NaN poisons its frame, as in NumPy
+    rest = np.delete(np.arange(77), 10)
+    np.testing.assert_allclose(got[3][rest], full_logprobs(sparsify_logits(x[3]))[rest], atol=2e-5)
