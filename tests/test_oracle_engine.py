@@ -184,3 +184,43 @@ def test_embedding_fold_equals_the_conditioned_forward(golden_dir):
         for embed_id, key in ((2, 'logits_0'), (5, 'mean_logits_0'), (0, 'id0_logits_0')):
             got = net(x, torch.tensor([embed_id]))[0].numpy().T
             np.testing.assert_allclose(got, gold[key], atol=3e-5)
+
+
+def test_netdesc_refuses_what_the_kernels_do_not_run():
+    """Error behaviour of the type-driven walk: every unsupported shape is a ValueError at construction time, never a
+    silent fallback (there is no generic executor behind it)."""
+    from torch import nn
+    from pero_ocr_b200 import netdesc
+
+    def line_net(front, agg=None, seq=None, head=None):
+        m = nn.Module()
+        m.front = nn.Sequential(*front)
+        m.agg = agg if agg is not None else nn.Sequential(nn.Conv2d(64, 128, (5, 1)), nn.ReLU())
+        m.seq = seq if seq is not None else nn.LSTM(128, 256, bidirectional=True)
+        m.head = head if head is not None else nn.Linear(512, 10)
+        return m
+
+    ok_front = [nn.Conv2d(3, 64, 3, padding=1), nn.ReLU()]
+    layers, classes = netdesc.describe_line_net(line_net(ok_front))
+    assert classes == 10 and len(layers) == 4
+    bad = {
+        '5x5 frontend conv': line_net([nn.Conv2d(3, 64, 5, padding=2), nn.ReLU()]),
+        'unpadded frontend conv': line_net([nn.Conv2d(3, 64, 3, padding=0), nn.ReLU()]),
+        'strided frontend conv': line_net([nn.Conv2d(3, 64, 3, padding=1, stride=2), nn.ReLU()]),
+        '3x3 max-pool': line_net(ok_front + [nn.Conv2d(64, 64, 3, padding=1), nn.ReLU(), nn.MaxPool2d(3, 3)]),
+        'overlapping max-pool': line_net(ok_front + [nn.Conv2d(64, 64, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 1)]),
+        'pool straight after the first conv': line_net(ok_front + [nn.MaxPool2d(2, 2)]),
+        'two activations in a row': line_net(ok_front + [nn.ReLU()]),
+        'negative LeakyReLU slope': line_net([nn.Conv2d(3, 64, 3, padding=1), nn.LeakyReLU(-0.1)]),
+        'other activation': line_net([nn.Conv2d(3, 64, 3, padding=1), nn.Tanh()]),
+        'unidirectional LSTM': line_net(ok_front, seq=nn.LSTM(128, 256, bidirectional=False), head=nn.Linear(256, 10)),
+        'GRU': line_net(ok_front, seq=nn.GRU(128, 256, bidirectional=True)),
+        'channel mismatch': line_net(ok_front, agg=nn.Sequential(nn.Conv2d(32, 128, (5, 1)), nn.ReLU())),
+        'head width mismatch': line_net(ok_front, head=nn.Linear(256, 10)),
+        'wide head kernel': line_net(ok_front, head=nn.Conv1d(512, 10, 3)),
+        'no head': line_net(ok_front, head=nn.Identity()),
+    }
+    for name, net in bad.items():
+        with pytest.raises(ValueError):
+            netdesc.describe_line_net(net)
+            pytest.fail(f'{name} was accepted')
