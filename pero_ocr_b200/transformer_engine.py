@@ -62,15 +62,23 @@ class ARLineRecognizer(LineRecognizer):
             max_steps = w // 4 + 1                     # :79: `len(partial_transcripts) > inputs.shape[-1] // 4`
         self.reserve_ar(n, w, max_steps)
         dev = crops.device
-        tokens = torch.empty((max_steps, n), dtype=torch.int32, device=dev)
-        logits = torch.empty((n, max_steps, self.num_classes), dtype=torch.float32, device=dev) if want_logits else None
+        # persistent output buffers per shape: the library replays the launches of a position as a CUDA graph that was
+        # captured with these addresses; the caller receives copies of the used prefix
+        bufs = self.__dict__.setdefault('_ar_out', {})
+        key = (n, max_steps, bool(want_logits), dev.index)
+        if key not in bufs:
+            if len(bufs) >= 4:
+                bufs.clear()
+            bufs[key] = (torch.empty((max_steps, n), dtype=torch.int32, device=dev),
+                         torch.empty((n, max_steps, self.num_classes), dtype=torch.float32, device=dev) if want_logits else None)
+        tokens, logits = bufs[key]
         steps = C.c_int32(0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self._lib.b200ocr_ar_transcribe(
             self._h, crops.data_ptr(), n, h, w, int(start_token), int(max_steps), int(check_every), tokens.data_ptr(),
             logits.data_ptr() if want_logits else None, C.byref(steps), C.c_void_p(stream)), self._h)
         k = int(steps.value)
-        return tokens[:k], (logits[:, :k] if want_logits else None), k
+        return tokens[:k].clone(), (logits[:, :k].clone() if want_logits else None), k
 
 
 def softmax(x, axis):
